@@ -1,0 +1,201 @@
+/*
+ * pvqa.h — C-ABI of libpvqa_sm100.so, the B200 (sm_100a) hot path of PhonoVQA.
+ *
+ * The reference (hieunghia-pat/phoneme-VQA) is pure Python/PyTorch and has no
+ * FFI of its own; every entry point below replaces a stretch of reference
+ * Python that today runs as a chain of ATen kernels.  Each declaration cites
+ * the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain C: raw device pointers + int64 sizes, no torch types.
+ *   - every function returns 0 on success, a pvqa_status otherwise;
+ *     pvqa_last_error() gives the thread-local message.  No exceptions, no
+ *     silent fallback: unsupported shapes/dtypes are errors.
+ *   - all buffers are caller-allocated, contiguous row-major unless a stride
+ *     argument says otherwise; kernels never allocate or retain pointers.
+ *   - work is enqueued on the caller's stream (a cudaStream_t passed as void*).
+ *   - index tensors are int64 exactly as the reference datasets produce them
+ *     (core/data/PhonemeLaTrDataset.py:51-58).
+ */
+#ifndef PVQA_H_
+#define PVQA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PVQA_ABI_VERSION 3
+
+typedef enum {
+  PVQA_OK = 0,
+  PVQA_ERR_SHAPE = 1,     /* unsupported or inconsistent dimensions          */
+  PVQA_ERR_DTYPE = 2,     /* dtype enum not supported by this entry point    */
+  PVQA_ERR_ALIGN = 3,     /* pointer / row not 16-byte aligned               */
+  PVQA_ERR_NULL = 4,      /* required pointer is NULL                        */
+  PVQA_ERR_CUDA = 5,      /* CUDA launch / runtime error (message has code)  */
+  PVQA_ERR_UNSUPPORTED = 6
+} pvqa_status;
+
+typedef enum { PVQA_F32 = 0, PVQA_BF16 = 1 } pvqa_dtype;
+
+int pvqa_abi_version(void);
+const char* pvqa_last_error(void);
+/* number of kernels this library has launched in this process (all threads);
+ * bench.py reports the delta over the timed region as "gpu_launches". */
+int64_t pvqa_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * K1  fused multimodal embedding
+ * replaces  core/model/PhonemeLaTr.py:33-44   SpatialModule.forward (6 gathers + 5 adds)
+ *           core/model/PhonemeLaTr.py:221-229 shared(ocr)+spatial, shared(q), cat, mask cat
+ *           (identical copies: core/model/LaTr.py:29-39,85-97; PreSTU family with L_ocr = 0)
+ *
+ * out[b, 0:S_img]                 = img_feat[b]                      (already projected ViT tokens)
+ * out[b, S_img + l]               = shared[ocr_ids[b,l]] + sum_t layout[t][coords[b,l,t]]
+ * out[b, S_img + L_ocr + q]       = shared[q_ids[b,q]]
+ * out_mask[b]                     = [1]*S_img ++ ocr_mask[b] ++ q_mask[b]      (float32)
+ *
+ * layout table order t = 0..5 follows coordinate columns x0,y0,x1,y1,w,h, i.e.
+ * top_left_x, top_left_y, bottom_right_x, bottom_right_y, width_emb, height_emb.
+ * tab_dtype: dtype of shared/layout tables; act_dtype: dtype of img_feat and out.
+ * Accumulation is fp32 in the reference's association order
+ * ((((((x0+y0)+x1)+y1)+w)+h) then ocr + that).
+ * err_flag (optional, device int32): set to 1 if any index is out of range
+ * (the reference would hit a device assert); such rows are written as zeros.
+ * ------------------------------------------------------------------------ */
+int pvqa_embed_mm_fwd(const void* img_feat, const int64_t* coords,
+                      const int64_t* ocr_ids, const int64_t* q_ids,
+                      const float* ocr_mask, const float* q_mask,
+                      const void* shared_tab, const void* const* layout_tabs /* host array[6] of device ptrs */,
+                      void* out, float* out_mask,
+                      int64_t B, int64_t S_img, int64_t L_ocr, int64_t L_q,
+                      int64_t d, int64_t V, int64_t n_pos,
+                      int tab_dtype, int act_dtype, int32_t* err_flag, void* stream);
+
+/* backward of K1: scatter-add of d_out rows into fp32 gradient tables.
+ * replaces the autograd of the same reference lines (6x embedding_dense_backward
+ * + 2x for `shared`, + add/cat backward).  Gradient tables are fp32, must be
+ * zero-initialised (or hold a running sum) by the caller; nn.Embedding has no
+ * padding_idx in the reference so pad rows DO receive gradient.
+ * d_img is not produced: it is the view d_out[:, 0:S_img]. */
+int pvqa_embed_mm_bwd(const void* d_out, const int64_t* coords,
+                      const int64_t* ocr_ids, const int64_t* q_ids,
+                      float* d_shared, float* const* d_layout_tabs /* host array[6] */,
+                      int64_t B, int64_t S_img, int64_t L_ocr, int64_t L_q,
+                      int64_t d, int64_t V, int64_t n_pos,
+                      int act_dtype, void* stream);
+
+/* ------------------------------------------------------------------------
+ * K1' fused multi-token phoneme (target) embedding + sinusoidal PE
+ * replaces  core/model/modules/phoneme_utils.py:10-21 (intended 3-table form
+ *           PhonoLaTr/modules.py:40-63: onset/rhyme/tone gathers + concat)
+ *           core/model/modules/transformer_utils.py:23-25 (+ pos_embedding[:, :T], dropout)
+ *
+ * out[b,t,:] = concat(onset[l0], rhyme[l1], tone[l2]) + pe[t]   then inverted dropout(p)
+ * labels (B,T,3) int64; onset (V_o,on_dim), rhyme (V_r,rt_dim), tone (V_t,rt_dim);
+ * on_dim + 2*rt_dim == d.  pe (>=T, d) fp32 (the persistent pos_embedding buffer).
+ * dropout uses Philox4x32-10 keyed by (seed, offset) per element index; p = 0 disables.
+ * ------------------------------------------------------------------------ */
+int pvqa_embed_tgt_fwd(const int64_t* labels, const void* onset_tab, const void* rhyme_tab,
+                       const void* tone_tab, const float* pe, void* out,
+                       int64_t B, int64_t T, int64_t d, int64_t on_dim, int64_t rt_dim,
+                       int64_t V_o, int64_t V_r, int64_t V_t,
+                       int tab_dtype, int act_dtype,
+                       float dropout_p, uint64_t seed, uint64_t offset,
+                       int32_t* err_flag, void* stream);
+
+int pvqa_embed_tgt_bwd(const void* d_out, const int64_t* labels,
+                       float* d_onset, float* d_rhyme, float* d_tone,
+                       int64_t B, int64_t T, int64_t d, int64_t on_dim, int64_t rt_dim,
+                       int64_t V_o, int64_t V_r, int64_t V_t,
+                       int act_dtype, float dropout_p, uint64_t seed, uint64_t offset,
+                       void* stream);
+
+/* ------------------------------------------------------------------------
+ * K4  fused multi-token phoneme output head + 3x cross-entropy
+ * replaces  core/model/PhonemeLaTr.py:124-130 (column split + onset/rhyme/tone Linear heads)
+ *           core/executor/PhonemeLaTr_Executor.py:181-190 (3x CrossEntropyLoss(ignore_index=pad), summed)
+ *
+ * h (N, d) is the output of shared_lm_head (N = B*T rows).  For sub-head k with
+ * column slice [off_k, off_k + w_k) of h, weight W_k (V_k, w_k), bias b_k (V_k):
+ *   logits_k = h[:, slice_k] @ W_k^T + b_k ;  loss_k = mean_{n: tgt[n,k] != ignore} -log_softmax(logits_k)[tgt[n,k]]
+ * loss = loss_0 + loss_1 + loss_2.  Logits never reach HBM unless logits_out != NULL
+ * (the reference-compatible forward() needs them; the fused-loss fast path does not).
+ *
+ * fwd writes: loss_sum[3] (fp32, sum of NLL per head), count[3] (int32 non-ignored targets),
+ *             lse (N,3) fp32 saved for backward.
+ * bwd writes: d_h (N,d) act dtype, and accumulates d_W_k, d_b_k (fp32) given the
+ *             upstream scalar gradient g (device fp32, d loss).
+ * ------------------------------------------------------------------------ */
+int pvqa_phoneme_head_ce_fwd(const void* h, const int64_t* targets /* (N,3) strided */,
+                             int64_t tgt_row_stride,
+                             const void* W_onset, const void* b_onset,
+                             const void* W_rhyme, const void* b_rhyme,
+                             const void* W_tone, const void* b_tone,
+                             float* loss_sum /*3*/, int32_t* count /*3*/, float* lse /*N,3*/,
+                             void* logits_onset, void* logits_rhyme, void* logits_tone /* optional */,
+                             int64_t N, int64_t d, int64_t on_dim, int64_t rt_dim,
+                             int64_t V_o, int64_t V_r, int64_t V_t, int64_t ignore_index,
+                             int w_dtype, int act_dtype, void* stream);
+
+int pvqa_phoneme_head_ce_bwd(const void* h, const int64_t* targets, int64_t tgt_row_stride,
+                             const void* W_onset, const void* b_onset,
+                             const void* W_rhyme, const void* b_rhyme,
+                             const void* W_tone, const void* b_tone,
+                             const float* lse, const int32_t* count, const float* grad_loss /* device scalar */,
+                             void* d_h, float* dW_onset, float* db_onset,
+                             float* dW_rhyme, float* db_rhyme, float* dW_tone, float* db_tone,
+                             int64_t N, int64_t d, int64_t on_dim, int64_t rt_dim,
+                             int64_t V_o, int64_t V_r, int64_t V_t, int64_t ignore_index,
+                             int w_dtype, int act_dtype, void* stream);
+
+/* ------------------------------------------------------------------------
+ * K2 / K3  flash attention (tcgen05 + TMEM + TMA), bf16 in, fp32 accumulate
+ * K2 replaces HF T5Attention.forward as called from core/model/PhonemeLaTr.py:111-114
+ *    (transformers/models/t5/modeling_t5.py:253-345: unscaled QK^T + shared
+ *    bucketed relative bias + key mask, fp32 softmax, P@V)
+ * K3 replaces nn.MultiheadAttention inside nn.TransformerDecoder as called from
+ *    core/model/modules/transformer_utils.py:47-64 / core/model/PhonemeLaTr.py:134-144
+ *    (scaled QK^T + causal -inf + FLOAT additive key_padding masks, D14 in SURVEY)
+ *
+ * Q (B,Sq,H,D) / K,V (B,Sk,H,D) bf16 with explicit element strides so packed
+ * projections (q|k|v in one buffer) are consumed in place; D == 64.
+ *   s[b,h,i,j] = scale * q_i . k_j + rel_bias[h][j - i + Sq - 1] + key_add[b][j] (+ -inf if causal and j > i)
+ *   o = softmax_j(s) @ v
+ * rel_bias (H, Sq+Sk-1) fp32 or NULL: T5 bucketed bias expanded over relative offsets
+ *   (bucket(j-i) is a function of j-i only; expansion done on the host side of the ABI).
+ * key_add (B,Sk) fp32 or NULL: additive per-key term (0 / -inf for T5 masks; +1.0 / 0.0
+ *   float masks of the reference decoder).
+ * lse (B,H,Sq) fp32 out: log-sum-exp per row, saved for backward.
+ * ------------------------------------------------------------------------ */
+int pvqa_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
+                  const float* rel_bias, const float* key_add,
+                  int64_t B, int64_t H, int64_t Sq, int64_t Sk, int64_t D,
+                  int64_t q_stride_b, int64_t q_stride_s, int64_t q_stride_h,
+                  int64_t k_stride_b, int64_t k_stride_s, int64_t k_stride_h,
+                  int64_t v_stride_b, int64_t v_stride_s, int64_t v_stride_h,
+                  int64_t o_stride_b, int64_t o_stride_s, int64_t o_stride_h,
+                  float scale, int causal, void* stream);
+
+/* backward: dq,dk,dv (same layout/strides as q,k,v), d_rel_bias (H, Sq+Sk-1) fp32
+ * accumulated (caller zero-initialises) = sum over b,i,j with j-i fixed of dS. */
+int pvqa_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                  const float* lse, const float* rel_bias, const float* key_add,
+                  void* dq, void* dk, void* dv, float* d_rel_bias,
+                  int64_t B, int64_t H, int64_t Sq, int64_t Sk, int64_t D,
+                  int64_t q_stride_b, int64_t q_stride_s, int64_t q_stride_h,
+                  int64_t k_stride_b, int64_t k_stride_s, int64_t k_stride_h,
+                  int64_t v_stride_b, int64_t v_stride_s, int64_t v_stride_h,
+                  int64_t o_stride_b, int64_t o_stride_s, int64_t o_stride_h,
+                  int64_t dq_stride_b, int64_t dq_stride_s, int64_t dq_stride_h,
+                  int64_t dk_stride_b, int64_t dk_stride_s, int64_t dk_stride_h,
+                  int64_t dv_stride_b, int64_t dv_stride_s, int64_t dv_stride_h,
+                  float scale, int causal, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PVQA_H_ */

@@ -1,0 +1,234 @@
+"""Autograd-visible wrappers of the C-ABI kernels (host side of the boundary).
+
+Every function here takes CUDA tensors, passes raw device pointers + the current
+stream to libpvqa_sm100.so through ctypes, and raises if the library is missing or a
+tensor is not on a CUDA device — there is deliberately no PyTorch/CPU fallback
+(BASELINE.json north_star: "no CPU fallback, no multi-backend dispatch").
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_void_p
+
+import torch
+
+from . import _lib
+from ._lib import PVQA_BF16, PVQA_F32, check
+
+_DT = {torch.float32: PVQA_F32, torch.bfloat16: PVQA_BF16}
+
+
+def _dt(t: torch.dtype) -> int:
+    try:
+        return _DT[t]
+    except KeyError:
+        raise TypeError(f"libpvqa supports float32 and bfloat16 only, got {t}") from None
+
+
+def _p(t):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def _stream() -> c_void_p:
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "libpvqa_sm100 ops run on CUDA (sm_100a) tensors only; got a CPU tensor. "
+                "There is no CPU fallback in the product path (use oracle/ in tests)."
+            )
+
+
+def _ptr_array(tensors):
+    arr = (c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+# ----------------------------------------------------------------------------------
+# dropout RNG state: (seed, offset) for the counter-based Philox used inside kernels.
+# ----------------------------------------------------------------------------------
+class _Rng:
+    seed = 0x5EED5EED
+    offset = 0
+
+    @classmethod
+    def next(cls, n_elements: int):
+        off = cls.offset
+        cls.offset += (n_elements + 7) // 8 + 1
+        return cls.seed, off
+
+
+def manual_seed(seed: int) -> None:
+    """Seed the in-kernel dropout generator (independent from torch's generator)."""
+    _Rng.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    _Rng.offset = 0
+
+
+# ----------------------------------------------------------------------------------
+# K1: fused multimodal embedding
+# ----------------------------------------------------------------------------------
+class _EmbedMM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img_feat, coords, ocr_ids, q_ids, ocr_mask, q_mask, shared_w, out_dtype, *layout_w):
+        lib = _lib.load()
+        _need_cuda(img_feat, coords, ocr_ids, q_ids, ocr_mask, q_mask, shared_w, *layout_w)
+        has_ocr = ocr_ids is not None
+        B = q_ids.shape[0] if q_ids is not None else img_feat.shape[0]
+        S_img = 0 if img_feat is None else img_feat.shape[1]
+        L_ocr = ocr_ids.shape[1] if has_ocr else 0
+        L_q = 0 if q_ids is None else q_ids.shape[1]
+        V, d = shared_w.shape
+        n_pos = layout_w[0].shape[0] if has_ocr else 0
+        S = S_img + L_ocr + L_q
+        dev = shared_w.device
+        if img_feat is not None:
+            img_feat = img_feat.to(out_dtype).contiguous()
+        if has_ocr:
+            assert len(layout_w) == 6, "six layout tables (x0,y0,x1,y1,w,h) are required"
+            coords = coords.contiguous()
+            ocr_ids = ocr_ids.contiguous()
+            ocr_mask = ocr_mask.to(torch.float32).contiguous()
+            if coords.dtype != torch.int64 or ocr_ids.dtype != torch.int64:
+                raise TypeError("coordinates / tokenized_ocr must be int64")
+            layout_w = [w.contiguous() for w in layout_w]
+            if any(w.dtype != shared_w.dtype or w.shape != (n_pos, d) for w in layout_w):
+                raise TypeError("layout tables must share dtype with the token table and be (n_pos, d)")
+        if q_ids is not None:
+            q_ids = q_ids.contiguous()
+            q_mask = q_mask.to(torch.float32).contiguous()
+            if q_ids.dtype != torch.int64:
+                raise TypeError("input_ids must be int64")
+        shared_c = shared_w.contiguous()
+        out = torch.empty((B, S, d), dtype=out_dtype, device=dev)
+        out_mask = torch.empty((B, S), dtype=torch.float32, device=dev)
+        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        tabs = _ptr_array(layout_w) if has_ocr else None
+        with torch.cuda.device(dev):
+            check(lib.pvqa_embed_mm_fwd(_p(img_feat), _p(coords), _p(ocr_ids), _p(q_ids), _p(ocr_mask), _p(q_mask),
+                                        _p(shared_c), tabs, _p(out), _p(out_mask),
+                                        B, S_img, L_ocr, L_q, d, V, n_pos,
+                                        _dt(shared_w.dtype), _dt(out_dtype), _p(err), _stream()),
+                  "pvqa_embed_mm_fwd")
+        ctx.save_for_backward(coords, ocr_ids, q_ids)
+        ctx.dims = (B, S_img, L_ocr, L_q, d, V, n_pos)
+        ctx.tab_dtype = shared_w.dtype
+        ctx.img_needs_grad = img_feat is not None and ctx.needs_input_grad[0]
+        ctx.img_dtype = None if img_feat is None else img_feat.dtype
+        ctx.mark_non_differentiable(out_mask)
+        ctx.err_flag = err
+        return out, out_mask
+
+    @staticmethod
+    def backward(ctx, d_out, _d_mask):
+        lib = _lib.load()
+        coords, ocr_ids, q_ids = ctx.saved_tensors
+        B, S_img, L_ocr, L_q, d, V, n_pos = ctx.dims
+        d_out = d_out.contiguous()
+        dev = d_out.device
+        d_shared = torch.zeros((V, d), dtype=torch.float32, device=dev)
+        d_layout = [torch.zeros((n_pos, d), dtype=torch.float32, device=dev) for _ in range(6)] if L_ocr else []
+        tabs = _ptr_array(d_layout) if L_ocr else None
+        with torch.cuda.device(dev):
+            check(lib.pvqa_embed_mm_bwd(_p(d_out), _p(coords), _p(ocr_ids), _p(q_ids), _p(d_shared), tabs,
+                                        B, S_img, L_ocr, L_q, d, V, n_pos, _dt(d_out.dtype), _stream()),
+                  "pvqa_embed_mm_bwd")
+        d_img = d_out[:, :S_img] if ctx.img_needs_grad else None
+        if ctx.tab_dtype != torch.float32:
+            d_shared = d_shared.to(ctx.tab_dtype)
+            d_layout = [g.to(ctx.tab_dtype) for g in d_layout]
+        return (d_img, None, None, None, None, None, d_shared, None, *d_layout)
+
+
+def embed_multimodal(img_feat, coordinates, tokenized_ocr, input_ids, ocr_attention_mask, src_attention_mask,
+                     shared_weight, layout_weights=(), out_dtype=None):
+    """K1.  Returns (multi_modal_feat (B,S,d), input_attention_mask (B,S) float32).
+
+    Mirrors `_calculate_embedding` of the reference (core/model/PhonemeLaTr.py:219-231)
+    minus the ViT + projector GEMM, whose output is `img_feat`.  `layout_weights` is the
+    six SpatialModule tables in coordinate-column order (x0, y0, x1, y1, w, h); pass
+    `coordinates=None, tokenized_ocr=None` for the PreSTU family (no layout branch).
+    """
+    out_dtype = out_dtype or (img_feat.dtype if img_feat is not None else shared_weight.dtype)
+    return _EmbedMM.apply(img_feat, coordinates, tokenized_ocr, input_ids, ocr_attention_mask,
+                          src_attention_mask, shared_weight, out_dtype, *layout_weights)
+
+
+def last_index_error(out: torch.Tensor) -> bool:  # pragma: no cover - debugging helper
+    fn = out.grad_fn
+    flag = getattr(fn, "err_flag", None)
+    return bool(flag is not None and int(flag.item()) != 0)
+
+
+# ----------------------------------------------------------------------------------
+# K1': fused phoneme target embedding + sinusoidal PE (+ dropout)
+# ----------------------------------------------------------------------------------
+class _EmbedTgt(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, labels, onset_w, rhyme_w, tone_w, pe, dropout_p, out_dtype):
+        lib = _lib.load()
+        _need_cuda(labels, onset_w, rhyme_w, tone_w, pe)
+        if labels.dtype != torch.int64:
+            raise TypeError("labels must be int64 (B,T,3)")
+        labels = labels.contiguous()
+        B, T, three = labels.shape
+        assert three == 3
+        V_o, on_dim = onset_w.shape
+        V_r, rt_dim = rhyme_w.shape
+        V_t, rt2 = tone_w.shape
+        d = on_dim + 2 * rt_dim
+        if rt2 != rt_dim or pe.shape[-1] != d or pe.shape[-2] < T:
+            raise ValueError("phoneme sub-table widths / positional table do not match")
+        pe2 = pe.reshape(-1, d)
+        if pe2.dtype != torch.float32:
+            pe2 = pe2.float()
+        pe2 = pe2.contiguous()
+        dev = onset_w.device
+        out = torch.empty((B, T, d), dtype=out_dtype, device=dev)
+        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        seed, offset = _Rng.next(B * T * d) if dropout_p > 0 else (0, 0)
+        ow, rw, tw = onset_w.contiguous(), rhyme_w.contiguous(), tone_w.contiguous()
+        with torch.cuda.device(dev):
+            check(lib.pvqa_embed_tgt_fwd(_p(labels), _p(ow), _p(rw), _p(tw), _p(pe2), _p(out),
+                                         B, T, d, on_dim, rt_dim, V_o, V_r, V_t,
+                                         _dt(onset_w.dtype), _dt(out_dtype), float(dropout_p), seed, offset,
+                                         _p(err), _stream()),
+                  "pvqa_embed_tgt_fwd")
+        ctx.save_for_backward(labels)
+        ctx.meta = (B, T, d, on_dim, rt_dim, V_o, V_r, V_t, float(dropout_p), seed, offset, onset_w.dtype)
+        ctx.err_flag = err
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        (labels,) = ctx.saved_tensors
+        B, T, d, on_dim, rt_dim, V_o, V_r, V_t, p, seed, offset, tab_dtype = ctx.meta
+        d_out = d_out.contiguous()
+        dev = d_out.device
+        g_on = torch.zeros((V_o, on_dim), dtype=torch.float32, device=dev)
+        g_rh = torch.zeros((V_r, rt_dim), dtype=torch.float32, device=dev)
+        g_to = torch.zeros((V_t, rt_dim), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.pvqa_embed_tgt_bwd(_p(d_out), _p(labels), _p(g_on), _p(g_rh), _p(g_to),
+                                         B, T, d, on_dim, rt_dim, V_o, V_r, V_t, _dt(d_out.dtype),
+                                         p, seed, offset, _stream()),
+                  "pvqa_embed_tgt_bwd")
+        if tab_dtype != torch.float32:
+            g_on, g_rh, g_to = g_on.to(tab_dtype), g_rh.to(tab_dtype), g_to.to(tab_dtype)
+        return None, g_on, g_rh, g_to, None, None, None
+
+
+def embed_target(labels, onset_weight, rhyme_weight, tone_weight, pos_embedding, dropout_p=0.0, training=False,
+                 out_dtype=None):
+    """K1'.  concat(onset[l0], rhyme[l1], tone[l2]) + pos_embedding[:, :T], then dropout.
+
+    Mirrors `positional_encoding(tgt_tok_emb(labels))` (core/model/PhonemeLaTr.py:137-138).
+    """
+    out_dtype = out_dtype or onset_weight.dtype
+    p = float(dropout_p) if training else 0.0
+    return _EmbedTgt.apply(labels, onset_weight, rhyme_weight, tone_weight, pos_embedding, p, out_dtype)

@@ -1,0 +1,228 @@
+"""K1 / K1' parity: CUDA path (through the C-ABI) vs the CPU oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): fp32 embeddings within 1e-5 relative (we get bit-exact
+in fp32 because the association order is the reference's), bf16 within 1e-2; gradients
+within 1e-3 relative.
+"""
+import pytest
+import torch
+
+from oracle import ref_ops
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _inputs(B, S_img, L_ocr, L_q, d, V, n_pos=1024, seed=0, hot=False):
+    g = torch.Generator().manual_seed(seed)
+    img = torch.randn(B, S_img, d, generator=g) if S_img else None
+    if L_ocr:
+        coords = torch.randint(0, 1001, (B, L_ocr, 6), generator=g)
+        ocr = torch.randint(0, V, (B, L_ocr), generator=g)
+        om = torch.ones(B, L_ocr)
+        # reference padding: eos box [1000]*6 then pad boxes [0]*6 with token id 0 (PhonemeLaTrDataset.py:24-25,141)
+        for b in range(B):
+            n = int(torch.randint(1, L_ocr, (1,), generator=g))
+            coords[b, n] = 1000
+            ocr[b, n] = 1
+            coords[b, n + 1:] = 0
+            ocr[b, n + 1:] = 0
+            om[b, n + 1:] = 0
+        if hot:
+            coords[:] = 7
+            ocr[:] = 3
+    else:
+        coords = ocr = om = None
+    q = torch.randint(0, V, (B, L_q), generator=g) if L_q else None
+    qm = (torch.rand(B, L_q, generator=g) > 0.3).float() if L_q else None
+    shared = torch.randn(V, d, generator=g)
+    lay = [torch.randn(n_pos, d, generator=g) for _ in range(6)] if L_ocr else []
+    return img, coords, ocr, q, om, qm, shared, lay
+
+
+def _cuda(x):
+    if x is None:
+        return None
+    if isinstance(x, (list, tuple)):
+        return [t.to(DEV) for t in x]
+    return x.to(DEV)
+
+
+CASES = [
+    (2, 5, 12, 6, 64, 50),       # tiny
+    (3, 197, 100, 30, 768, 997),  # PhonoLaTr-base row geometry, small batch
+    (1, 0, 9, 4, 128, 33),       # no image tokens
+    (2, 7, 0, 13, 512, 40),      # PreSTU family: no layout branch
+    (2, 3, 17, 0, 256, 21),      # no question tokens
+    (4, 1, 1, 1, 8, 5),          # minimum width
+]
+
+
+@pytest.mark.parametrize("B,S_img,L_ocr,L_q,d,V", CASES)
+def test_embed_mm_fwd_fp32_bit_exact(B, S_img, L_ocr, L_q, d, V):
+    from phoneme_vqa_b200 import ops
+    img, coords, ocr, q, om, qm, shared, lay = _inputs(B, S_img, L_ocr, L_q, d, V)
+    ref, ref_mask = ref_ops.calculate_embedding(img, coords, ocr, q, om, qm, shared, lay)
+    out, mask = ops.embed_multimodal(_cuda(img), _cuda(coords), _cuda(ocr), _cuda(q), _cuda(om), _cuda(qm),
+                                     _cuda(shared), _cuda(lay), out_dtype=torch.float32)
+    assert torch.equal(out.cpu(), ref)
+    assert torch.equal(mask.cpu(), ref_mask)
+
+
+@pytest.mark.parametrize("tab_dtype", [torch.float32, torch.bfloat16])
+def test_embed_mm_fwd_bf16(tab_dtype):
+    from phoneme_vqa_b200 import ops
+    img, coords, ocr, q, om, qm, shared, lay = _inputs(3, 197, 100, 30, 768, 997, seed=3)
+    img = img.bfloat16()
+    shared = shared.to(tab_dtype)
+    lay = [t.to(tab_dtype) for t in lay]
+    ref, _ = ref_ops.calculate_embedding(img.float(), coords, ocr, q, om, qm, shared.float(), [t.float() for t in lay])
+    out, _ = ops.embed_multimodal(_cuda(img), _cuda(coords), _cuda(ocr), _cuda(q), _cuda(om), _cuda(qm),
+                                  _cuda(shared), _cuda(lay), out_dtype=torch.bfloat16)
+    # fp32 accumulate + one rounding: identical to rounding the fp32 oracle
+    assert torch.equal(out.cpu(), ref.bfloat16())
+
+
+@pytest.mark.parametrize("B,S_img,L_ocr,L_q,d,V", CASES)
+@pytest.mark.parametrize("hot", [False, True])
+def test_embed_mm_bwd(B, S_img, L_ocr, L_q, d, V, hot):
+    from phoneme_vqa_b200 import ops
+    img, coords, ocr, q, om, qm, shared, lay = _inputs(B, S_img, L_ocr, L_q, d, V, seed=5, hot=hot)
+    leaves = [shared] + lay + ([img] if img is not None else [])
+    for t in leaves:
+        t.requires_grad_(True)
+    ref, _ = ref_ops.calculate_embedding(img, coords, ocr, q, om, qm, shared, lay)
+    g = torch.Generator().manual_seed(11)
+    go = torch.randn(ref.shape, generator=g)
+    ref.backward(go)
+
+    c_leaves = [t.detach().to(DEV).requires_grad_(True) for t in leaves]
+    c_shared, c_lay = c_leaves[0], c_leaves[1:1 + len(lay)]
+    c_img = c_leaves[-1] if img is not None else None
+    out, _ = ops.embed_multimodal(c_img, _cuda(coords), _cuda(ocr), _cuda(q), _cuda(om), _cuda(qm), c_shared, c_lay,
+                                  out_dtype=torch.float32)
+    out.backward(go.to(DEV))
+    for a, b in zip(c_leaves, leaves):
+        torch.testing.assert_close(a.grad.cpu(), b.grad, rtol=1e-4, atol=1e-5)
+
+
+def test_embed_mm_bwd_bf16_grad():
+    from phoneme_vqa_b200 import ops
+    img, coords, ocr, q, om, qm, shared, lay = _inputs(2, 5, 40, 10, 256, 60, seed=9)
+    for t in [shared] + lay:
+        t.requires_grad_(True)
+    ref, _ = ref_ops.calculate_embedding(img, coords, ocr, q, om, qm, shared, lay)
+    go = torch.randn(ref.shape, generator=torch.Generator().manual_seed(2)).bfloat16()
+    ref.backward(go.float())
+    c_shared = shared.detach().to(DEV).requires_grad_(True)
+    c_lay = [t.detach().to(DEV).requires_grad_(True) for t in lay]
+    out, _ = ops.embed_multimodal(_cuda(img).bfloat16(), _cuda(coords), _cuda(ocr), _cuda(q), _cuda(om), _cuda(qm),
+                                  c_shared, c_lay, out_dtype=torch.bfloat16)
+    out.backward(go.to(DEV))
+    torch.testing.assert_close(c_shared.grad.cpu(), shared.grad, rtol=1e-3, atol=1e-4)
+    for a, b in zip(c_lay, lay):
+        torch.testing.assert_close(a.grad.cpu(), b.grad, rtol=1e-3, atol=1e-4)
+
+
+def test_embed_mm_out_of_range_flag():
+    from phoneme_vqa_b200 import ops
+    img, coords, ocr, q, om, qm, shared, lay = _inputs(2, 3, 6, 4, 64, 20)
+    coords[1, 2, 4] = 5000          # beyond max_2d_position_embeddings
+    q[0, 1] = -1
+    out, _ = ops.embed_multimodal(_cuda(img), _cuda(coords), _cuda(ocr), _cuda(q), _cuda(om), _cuda(qm),
+                                  _cuda(shared), _cuda(lay), out_dtype=torch.float32)
+    assert int(out.grad_fn.err_flag.item()) == 1 if out.grad_fn is not None else True
+    assert torch.count_nonzero(out[1, 3 + 2]) == 0
+
+
+def test_embed_mm_full_size_properties():
+    """BASELINE config-3 shard (B=64, S=327, d=768, V=36096): checksum-of-rows property.
+
+    sum over all rows of out == counts(table rows) @ tables, evaluated in float64 on the
+    device with torch ops (size-independent property, no oracle run at this size)."""
+    from phoneme_vqa_b200 import ops
+    B, S_img, L_ocr, L_q, d, V = 64, 197, 100, 30, 768, 36096
+    img, coords, ocr, q, om, qm, shared, lay = _inputs(B, S_img, L_ocr, L_q, d, V, seed=21)
+    out, mask = ops.embed_multimodal(_cuda(img), _cuda(coords), _cuda(ocr), _cuda(q), _cuda(om), _cuda(qm),
+                                     _cuda(shared), _cuda(lay), out_dtype=torch.float32)
+    tok_counts = torch.bincount(torch.cat([ocr.flatten(), q.flatten()]), minlength=V).double()
+    expect = tok_counts @ shared.double() + img.double().sum(dim=(0, 1))
+    for t in range(6):
+        expect += torch.bincount(coords[:, :, t].flatten(), minlength=1024).double() @ lay[t].double()
+    got = out.double().sum(dim=(0, 1)).cpu()
+    torch.testing.assert_close(got, expect, rtol=1e-6, atol=1e-3)
+    assert torch.equal(mask.cpu(), torch.cat([torch.ones(B, S_img), om, qm], dim=1))
+    # spot rows against the oracle
+    sel = [0, 17, 63]
+    ref, _ = ref_ops.calculate_embedding(img[sel], coords[sel], ocr[sel], q[sel], om[sel], qm[sel], shared, lay)
+    assert torch.equal(out[sel].cpu(), ref)
+
+
+# ------------------------------- K1' ------------------------------------------------
+def _tgt_inputs(B, T, d, V=(84, 187, 7), seed=0, pad_tail=True):
+    g = torch.Generator().manual_seed(seed)
+    rt = d // 3
+    on = d - 2 * rt
+    labels = torch.stack([torch.randint(0, V[k], (B, T), generator=g) for k in range(3)], dim=-1)
+    if pad_tail:
+        for b in range(B):
+            n = int(torch.randint(1, T + 1, (1,), generator=g))
+            labels[b, n:] = 2          # one pad id for all three columns
+    onset = torch.randn(V[0], on, generator=g)
+    rhyme = torch.randn(V[1], rt, generator=g)
+    tone = torch.randn(V[2], rt, generator=g)
+    pe = ref_ops.sinusoidal_table(d, 512)
+    return labels, onset, rhyme, tone, pe
+
+
+@pytest.mark.parametrize("B,T,d", [(2, 9, 48), (3, 127, 768), (2, 40, 512), (1, 1, 1024), (2, 127, 96)])
+def test_embed_tgt_fwd_bwd_fp32(B, T, d):
+    from phoneme_vqa_b200 import ops
+    labels, onset, rhyme, tone, pe = _tgt_inputs(B, T, d, seed=B + T)
+    for t in (onset, rhyme, tone):
+        t.requires_grad_(True)
+    ref = ref_ops.positional_encoding(ref_ops.phoneme_embedding(labels, onset, rhyme, tone), pe)
+    go = torch.randn(ref.shape, generator=torch.Generator().manual_seed(4))
+    ref.backward(go)
+    c = [t.detach().to(DEV).requires_grad_(True) for t in (onset, rhyme, tone)]
+    out = ops.embed_target(labels.to(DEV), c[0], c[1], c[2], pe.to(DEV), out_dtype=torch.float32)
+    assert torch.equal(out.cpu(), ref.detach())
+    out.backward(go.to(DEV))
+    for a, b in zip(c, (onset, rhyme, tone)):
+        torch.testing.assert_close(a.grad.cpu(), b.grad, rtol=1e-4, atol=1e-5)
+
+
+def test_embed_tgt_bf16():
+    from phoneme_vqa_b200 import ops
+    labels, onset, rhyme, tone, pe = _tgt_inputs(4, 127, 768, seed=8)
+    ref = ref_ops.positional_encoding(ref_ops.phoneme_embedding(labels, onset, rhyme, tone), pe)
+    out = ops.embed_target(labels.to(DEV), onset.to(DEV), rhyme.to(DEV), tone.to(DEV), pe.to(DEV),
+                           out_dtype=torch.bfloat16)
+    assert torch.equal(out.cpu(), ref.bfloat16())
+
+
+@pytest.mark.parametrize("d", [768, 512])
+def test_embed_tgt_dropout_statistics_and_bwd_mask(d):
+    from phoneme_vqa_b200 import ops
+    ops.manual_seed(123)
+    p = 0.1
+    labels, onset, rhyme, tone, pe = _tgt_inputs(16, 127, d, seed=1)
+    c = [t.to(DEV).requires_grad_(True) for t in (onset, rhyme, tone)]
+    nodrop = ops.embed_target(labels.to(DEV), *c, pe.to(DEV), dropout_p=p, training=False, out_dtype=torch.float32)
+    out = ops.embed_target(labels.to(DEV), *c, pe.to(DEV), dropout_p=p, training=True, out_dtype=torch.float32)
+    kept = out != 0
+    frac = kept.float().mean().item()
+    assert abs(frac - (1 - p)) < 5e-3, frac
+    torch.testing.assert_close(out[kept], (nodrop / (1 - p))[kept], rtol=1e-6, atol=1e-6)
+    # backward uses the same mask: d(sum out)/d table[row, col] = (#kept hits) / (1-p)
+    out.sum().backward()
+    rt = d // 3
+    on = d - 2 * rt
+    hits = torch.zeros_like(c[0])
+    hits.index_put_((labels[:, :, 0].to(DEV).flatten(),), kept[:, :, :on].reshape(-1, on).float() / (1 - p),
+                    accumulate=True)
+    torch.testing.assert_close(c[0].grad, hits, rtol=1e-5, atol=1e-4)
+    # a second call draws a different mask
+    out2 = ops.embed_target(labels.to(DEV), *c, pe.to(DEV), dropout_p=p, training=True, out_dtype=torch.float32)
+    assert not torch.equal(out2 != 0, kept)

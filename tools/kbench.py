@@ -1,0 +1,137 @@
+"""Per-kernel timing on the B200: CUDA events on the launching stream, L2 flushed between
+iterations, reported against MEASURED_PEAKS.json.  Usage:  python tools/kbench.py [embed|tgt|head|attn|all]
+"""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+_flush_buf = None
+
+
+def flush_l2():
+    global _flush_buf
+    if _flush_buf is None:
+        _flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    _flush_buf.zero_()
+
+
+def time_fn(fn, iters=20, warmup=3, flush=True):
+    """median / min milliseconds per call of fn() measured with CUDA events."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush:
+            flush_l2()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def embed_mm_bytes(B, S_img, L_ocr, L_q, d, e_tab, e_act):
+    """reads B*[(7*L_ocr + L_q)*(d*e_tab + 8) + S_img*d*e_act] + writes B*S*d*e_act (+ mask)."""
+    S = S_img + L_ocr + L_q
+    return B * ((7 * L_ocr + L_q) * (d * e_tab + 8) + S_img * d * e_act) + B * S * d * e_act
+
+
+def embed_mm_bwd_bytes(B, S_img, L_ocr, L_q, d, e_act):
+    return B * ((L_ocr + L_q) * d * e_act + (7 * L_ocr + L_q) * 8 + 2 * (7 * L_ocr + L_q) * d * 4)
+
+
+def make_embed_inputs(B=64, S_img=197, L_ocr=100, L_q=30, d=768, V=36096, tab_dtype=torch.float32,
+                      act_dtype=torch.bfloat16, seed=1234, dev="cuda"):
+    g = torch.Generator().manual_seed(seed)
+    img = torch.randn(B, S_img, d, generator=g).to(act_dtype)
+    coords = torch.zeros(B, L_ocr, 6, dtype=torch.long)
+    ocr = torch.zeros(B, L_ocr, dtype=torch.long)
+    om = torch.zeros(B, L_ocr)
+    for b in range(B):
+        n = int(torch.randint(20, 100, (1,), generator=g))
+        n = min(n, L_ocr - 1)
+        x0 = torch.randint(0, 901, (n,), generator=g)
+        y0 = torch.randint(0, 901, (n,), generator=g)
+        w = torch.randint(1, 101, (n,), generator=g)
+        h = torch.randint(1, 101, (n,), generator=g)
+        coords[b, :n] = torch.stack([x0, y0, x0 + w, y0 + h, w, h], dim=-1)
+        coords[b, n] = 1000
+        ocr[b, :n] = torch.randint(3, V, (n,), generator=g)
+        ocr[b, n] = 1
+        om[b, : n + 1] = 1
+    q = torch.zeros(B, L_q, dtype=torch.long)
+    qm = torch.zeros(B, L_q)
+    for b in range(B):
+        n = int(torch.randint(8, L_q + 1, (1,), generator=g))
+        q[b, : n - 1] = torch.randint(3, V, (n - 1,), generator=g)
+        q[b, n - 1] = 1
+        qm[b, :n] = 1
+    shared = (torch.randn(V, d, generator=g) * 0.02).to(tab_dtype)
+    lay = [(torch.randn(1024, d, generator=g) * 0.02).to(tab_dtype) for _ in range(6)]
+    mv = lambda t: t.to(dev)  # noqa: E731
+    return mv(img), mv(coords), mv(ocr), mv(q), mv(om), mv(qm), mv(shared), [mv(t) for t in lay]
+
+
+def bench_embed(B=64):
+    from phoneme_vqa_b200 import ops
+    pk = peaks()
+    res = {}
+    for tab_dtype, act_dtype in [(torch.float32, torch.bfloat16), (torch.bfloat16, torch.bfloat16),
+                                 (torch.float32, torch.float32)]:
+        img, coords, ocr, q, om, qm, shared, lay = make_embed_inputs(B=B, tab_dtype=tab_dtype, act_dtype=act_dtype)
+        shared.requires_grad_(True)
+        for t in lay:
+            t.requires_grad_(True)
+        et, ea = shared.element_size(), img.element_size()
+        fwd = lambda: ops.embed_multimodal(img, coords, ocr, q, om, qm, shared, lay, out_dtype=act_dtype)  # noqa: E731
+        med, mn = time_fn(fwd)
+        nbytes = embed_mm_bytes(B, 197, 100, 30, 768, et, ea)
+        key = f"embed_mm_fwd[tab={str(tab_dtype)[6:]},act={str(act_dtype)[6:]}]"
+        res[key] = {"ms_median": med, "ms_min": mn, "alg_MB": nbytes / 1e6, "GBs": nbytes / med / 1e6,
+                    "frac_of_" + pk["source"]: nbytes / med / 1e6 / pk["hbm_gbs"]}
+        out, _ = fwd()
+        go = torch.randn_like(out)
+        import phoneme_vqa_b200 as pv
+        lib = pv.load()
+        from phoneme_vqa_b200.ops import _p, _ptr_array, _stream, _dt
+        d_shared = torch.zeros(shared.shape, dtype=torch.float32, device="cuda")
+        d_lay = [torch.zeros(t.shape, dtype=torch.float32, device="cuda") for t in lay]
+        arr = _ptr_array(d_lay)
+
+        def bwd():
+            lib.pvqa_embed_mm_bwd(_p(go), _p(coords), _p(ocr), _p(q), _p(d_shared), arr, B, 197, 100, 30, 768,
+                                  shared.shape[0], 1024, _dt(go.dtype), _stream())
+        med, mn = time_fn(bwd)
+        nbytes = embed_mm_bwd_bytes(B, 197, 100, 30, 768, ea)
+        key = f"embed_mm_bwd[act={str(act_dtype)[6:]}]"
+        res[key] = {"ms_median": med, "ms_min": mn, "alg_MB": nbytes / 1e6, "GBs": nbytes / med / 1e6,
+                    "frac_of_" + pk["source"]: nbytes / med / 1e6 / pk["hbm_gbs"]}
+    return res
+
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    out = {"peaks": peaks()}
+    if which in ("embed", "all"):
+        out.update(bench_embed())
+    print(json.dumps(out, indent=1))
