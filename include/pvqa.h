@@ -127,8 +127,11 @@ int pvqa_embed_tgt_bwd(const void* d_out, const int64_t* labels,
  *
  * fwd writes: loss_sum[3] (fp32, sum of NLL per head), count[3] (int32 non-ignored targets),
  *             lse (N,3) fp32 saved for backward.
- * bwd writes: d_h (N,d) act dtype, and accumulates d_W_k, d_b_k (fp32) given the
- *             upstream scalar gradient g (device fp32, d loss).
+ * bwd writes: dlogits_k (N,V_k) act dtype = grad_loss/count_k * (softmax(logits_k) - onehot(tgt))
+ *             (zero on ignored rows), recomputing the logits from h; the three small
+ *             GEMMs d_h = dlogits_k @ W_k, dW_k = dlogits_k^T @ h_k, db_k = sum dlogits_k are
+ *             left to the caller's GEMM library (9 MB of dlogits at B=64; the logits
+ *             themselves are never written).
  * ------------------------------------------------------------------------ */
 int pvqa_phoneme_head_ce_fwd(const void* h, const int64_t* targets /* (N,3) strided */,
                              int64_t tgt_row_stride,
@@ -146,8 +149,7 @@ int pvqa_phoneme_head_ce_bwd(const void* h, const int64_t* targets, int64_t tgt_
                              const void* W_rhyme, const void* b_rhyme,
                              const void* W_tone, const void* b_tone,
                              const float* lse, const int32_t* count, const float* grad_loss /* device scalar */,
-                             void* d_h, float* dW_onset, float* db_onset,
-                             float* dW_rhyme, float* db_rhyme, float* dW_tone, float* db_tone,
+                             void* dlogits_onset, void* dlogits_rhyme, void* dlogits_tone,
                              int64_t N, int64_t d, int64_t on_dim, int64_t rt_dim,
                              int64_t V_o, int64_t V_r, int64_t V_t, int64_t ignore_index,
                              int w_dtype, int act_dtype, void* stream);

@@ -1,0 +1,256 @@
+"""CPU restatement of the reference MODELS (TEST INFRASTRUCTURE ONLY — see ref_ops.py header).
+
+The reference composes HuggingFace ``T5EncoderModel`` / ``ViTModel`` and
+``torch.nn.TransformerDecoder``; those libraries are third-party code that is not under
+/root/reference (requirements.txt:1, unpinned; installed here: transformers 5.5.0,
+torch 2.11.0).  The restatement therefore composes the *same library modules* in the
+same way as core/model/PhonemeLaTr.py does, with ``from_pretrained`` replaced by
+config-init (no network) and the 3-table ``PhonemeEmbedding`` the call site expects
+(SURVEY.md D1).  It is pinned to the real reference by tests/golden/model_*.npz, written
+by oracle/make_golden.py from the reference classes themselves.
+
+Used as: parity checker in tests/, CPU baseline in bench.py (``cpu_baseline`` /
+``--impl reference``).
+"""
+from __future__ import annotations
+
+import math
+import zlib
+
+import numpy as np
+import torch
+import torch.nn as nn
+from transformers import T5Config, T5EncoderModel, ViTConfig, ViTModel
+
+from . import ref_ops
+
+
+def make_config(d_model=768, d_kv=64, num_heads=12, d_ff=3072, num_layers=12, vocab_size=36096,
+                num_decoder_layers=4, n_head=12, max_2d_position_embeddings=1024, vit_config=None,
+                dropout_rate=0.1, feed_forward_proj="relu"):
+    cfg = T5Config(d_model=d_model, d_kv=d_kv, num_heads=num_heads, d_ff=d_ff, num_layers=num_layers,
+                   vocab_size=vocab_size, dropout_rate=dropout_rate, feed_forward_proj=feed_forward_proj)
+    cfg.update({"max_2d_position_embeddings": max_2d_position_embeddings, "vit_model": "random-init",
+                "num_decoder_layers": num_decoder_layers, "n_head": n_head, "random_init": True,
+                "vit_config": vit_config})
+    return cfg
+
+
+TINY_VIT = dict(hidden_size=32, num_hidden_layers=2, num_attention_heads=2, intermediate_size=64,
+                image_size=32, patch_size=16)
+
+
+def tiny_config(**kw):
+    base = dict(d_model=192, d_kv=64, num_heads=3, d_ff=256, num_layers=2, vocab_size=120,
+                num_decoder_layers=2, n_head=3, vit_config=TINY_VIT)
+    base.update(kw)
+    return make_config(**base)
+
+
+# core/model/PhonemeLaTr.py:17-44
+class SpatialModule(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        n, d = config.max_2d_position_embeddings, config.d_model
+        self.top_left_x = nn.Embedding(n, d)
+        self.bottom_right_x = nn.Embedding(n, d)
+        self.top_left_y = nn.Embedding(n, d)
+        self.bottom_right_y = nn.Embedding(n, d)
+        self.width_emb = nn.Embedding(n, d)
+        self.height_emb = nn.Embedding(n, d)
+
+    def forward(self, coordinates):
+        return ref_ops.spatial_module(coordinates, [self.top_left_x.weight, self.top_left_y.weight,
+                                                    self.bottom_right_x.weight, self.bottom_right_y.weight,
+                                                    self.width_emb.weight, self.height_emb.weight])
+
+
+# PhonoLaTr/modules.py:27-63 as called at core/model/PhonemeLaTr.py:72-78
+class PhonemeEmbedding(nn.Module):
+    def __init__(self, on_v, rh_v, to_v, on_dim, rt_dim):
+        super().__init__()
+        self.onset_embedding = nn.Embedding(on_v, on_dim)
+        self.rhyme_embedding = nn.Embedding(rh_v, rt_dim)
+        self.tone_embedding = nn.Embedding(to_v, rt_dim)
+
+    def forward(self, t):
+        return ref_ops.phoneme_embedding(t, self.onset_embedding.weight, self.rhyme_embedding.weight,
+                                         self.tone_embedding.weight)
+
+
+# core/model/modules/transformer_utils.py:6-25
+class SinusoidalPositionalEncoding(nn.Module):
+    def __init__(self, emb_size, dropout, maxlen=5000):
+        super().__init__()
+        self.dropout = nn.Dropout(dropout)
+        self.register_buffer("pos_embedding", ref_ops.sinusoidal_table(emb_size, maxlen))
+
+    def forward(self, x):
+        return self.dropout(ref_ops.positional_encoding(x, self.pos_embedding))
+
+
+# core/model/modules/transformer_utils.py:38-64
+class BaseDecoder(nn.Module):
+    def __init__(self, emb_size, num_layers, n_head):
+        super().__init__()
+        self.decoder = nn.TransformerDecoder(
+            nn.TransformerDecoderLayer(d_model=emb_size, nhead=n_head, batch_first=True), num_layers=num_layers)
+
+    def forward(self, tgt, memory, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None,
+                memory_key_padding_mask=None):
+        return self.decoder(tgt=tgt, memory=memory, tgt_mask=tgt_mask, memory_mask=memory_mask,
+                            tgt_key_padding_mask=tgt_key_padding_mask,
+                            memory_key_padding_mask=memory_key_padding_mask)
+
+
+def _vit_from(config):
+    vc = getattr(config, "vit_config", None)
+    return ViTModel(ViTConfig(**vc) if isinstance(vc, dict) else ViTConfig())
+
+
+# core/model/PhonemeLaTr.py:46-236
+class PhonemeLaTr(nn.Module):
+    def __init__(self, config, onset_vocab_size, rhyme_vocab_size, tone_vocab_size):
+        super().__init__()
+        self.config = config
+        self.encoder = T5EncoderModel(config)
+        self.spatial_feat_extractor = SpatialModule(config)
+        self.vit = _vit_from(config)
+        self.visual_projector = nn.Linear(self.vit.config.hidden_size, config.d_model)
+        for _, child in self.vit.named_children():
+            for p in child.parameters():
+                p.requires_grad = False
+        d = config.d_model
+        self.rhyme_tone_embed_dim = d // 3
+        self.onset_embed_dim = int(d - self.rhyme_tone_embed_dim * 2)
+        self.tgt_tok_emb = PhonemeEmbedding(onset_vocab_size, rhyme_vocab_size, tone_vocab_size,
+                                            self.onset_embed_dim, self.rhyme_tone_embed_dim)
+        self.positional_encoding = SinusoidalPositionalEncoding(d, dropout=0.1)
+        self.decoder = BaseDecoder(d, config.num_decoder_layers, config.n_head)
+        self.shared_lm_head = nn.Linear(d, d)
+        self.onset_lm_head = nn.Linear(self.onset_embed_dim, onset_vocab_size)
+        self.rhyme_lm_head = nn.Linear(self.rhyme_tone_embed_dim, rhyme_vocab_size)
+        self.tone_lm_head = nn.Linear(self.rhyme_tone_embed_dim, tone_vocab_size)
+
+    def _calculate_embedding(self, pixel_values, coordinates, input_ids, ocr_attention_mask, src_attention_mask,
+                             tokenized_ocr):
+        img_feat = self.visual_projector(self.vit(pixel_values).last_hidden_state)
+        spatial = self.spatial_feat_extractor(coordinates)
+        layout_feat = self.encoder.shared(tokenized_ocr) + spatial
+        feat = torch.cat([img_feat, layout_feat, self.encoder.shared(input_ids)], axis=1)
+        mask = torch.cat([torch.ones(img_feat.shape[:2]).to(img_feat.device), ocr_attention_mask,
+                          src_attention_mask], axis=1)
+        return feat, mask
+
+    @staticmethod
+    def _square_mask(sz, device):
+        m = (torch.triu(torch.ones((sz, sz), device=device)) == 1).transpose(0, 1)
+        return m.float().masked_fill(m == 0, float("-inf")).masked_fill(m == 1, float(0.0))
+
+    def decode(self, labels, enc, enc_mask, label_mask=None):
+        emb = self.positional_encoding(self.tgt_tok_emb(labels))
+        return self.decoder(emb, enc, tgt_mask=self._square_mask(labels.size(1), labels.device),
+                            memory_key_padding_mask=enc_mask, tgt_key_padding_mask=label_mask)
+
+    def _split_heads(self, h):
+        on, rt = self.onset_embed_dim, self.rhyme_tone_embed_dim
+        return (self.onset_lm_head(h[:, :, :on]), self.rhyme_lm_head(h[:, :, on:on + rt]),
+                self.tone_lm_head(h[:, :, on + rt:]))
+
+    def forward(self, pixel_values, coordinates, input_ids, labels, src_attention_mask, label_attention_mask,
+                ocr_attention_mask, tokenized_ocr):
+        emb, mask = self._calculate_embedding(pixel_values, coordinates, input_ids, ocr_attention_mask,
+                                              src_attention_mask, tokenized_ocr)
+        enc = self.encoder(attention_mask=mask, inputs_embeds=emb).last_hidden_state
+        dec = self.decode(labels, enc, mask, label_attention_mask)
+        return self._split_heads(self.shared_lm_head(dec))
+
+    @torch.no_grad()
+    def greedy_generate(self, pixel_values, coordinates, input_ids, src_attention_mask, ocr_attention_mask,
+                        tokenized_ocr, start_symbol, end_symbol, max_len=100):
+        bz = input_ids.size(0)
+        emb, mask = self._calculate_embedding(pixel_values, coordinates, input_ids, ocr_attention_mask,
+                                              src_attention_mask, tokenized_ocr)
+        enc = self.encoder(attention_mask=mask, inputs_embeds=emb).last_hidden_state
+        ys = torch.tensor([[[start_symbol, 0, 0]]], dtype=torch.long).repeat(bz, 1, 1)
+        for _ in range(max_len):
+            out = self.decode(ys, enc, mask)
+            on, rh, to = self._split_heads(out)        # reference :195-205: no shared_lm_head here
+            nxt = torch.stack([on[:, -1].argmax(-1), rh[:, -1].argmax(-1), to[:, -1].argmax(-1)], dim=-1)
+            ys = torch.cat([ys, nxt.unsqueeze(1)], dim=1)
+            if torch.any(ys[:, :, 0] == end_symbol, dim=1).sum() == bz:
+                break
+        return ys
+
+
+# core/executor/PhonemeLaTr_Executor.py:161-196 — one training step's loss
+def phoneme_latr_loss(model, batch, pad_id):
+    labels = batch["label_ids"]
+    trg_input = labels[:, :-1]
+    on, rh, to = model(pixel_values=batch["pixel_values"], coordinates=batch["coordinates"],
+                       input_ids=batch["input_ids"], labels=trg_input,
+                       src_attention_mask=batch["src_attention_mask"],
+                       label_attention_mask=batch["label_attention_mask"][:, :-1],
+                       ocr_attention_mask=batch["ocr_attention_mask"], tokenized_ocr=batch["tokenized_ocr"])
+    ce = nn.functional.cross_entropy
+    return (ce(on.reshape(-1, on.shape[-1]), labels[:, 1:, 0].reshape(-1), ignore_index=pad_id)
+            + ce(rh.reshape(-1, rh.shape[-1]), labels[:, 1:, 1].reshape(-1), ignore_index=pad_id)
+            + ce(to.reshape(-1, to.shape[-1]), labels[:, 1:, 2].reshape(-1), ignore_index=pad_id))
+
+
+# ----------------------------------------------------------------------------------
+# deterministic weights / batches shared by the golden generator, the tests and bench.py
+# ----------------------------------------------------------------------------------
+def deterministic_state_dict(model: nn.Module, scale=0.05) -> dict:
+    """Every floating tensor of state_dict() is replaced by a function of (key, shape) only
+    (numpy legacy RandomState, stable across versions) so fixtures need not store weights."""
+    sd = {}
+    for k, v in model.state_dict().items():
+        if not v.is_floating_point() or k.endswith("pos_embedding"):
+            sd[k] = v.clone()
+            continue
+        rs = np.random.RandomState(zlib.crc32(k.replace("encoder.encoder.embed_tokens", "encoder.shared").encode()))
+        x = rs.standard_normal(tuple(v.shape)).astype(np.float32) * scale
+        if "norm" in k and k.endswith("weight"):
+            x = 1.0 + x
+        sd[k] = torch.from_numpy(x).reshape(v.shape)
+    return sd
+
+
+def synthetic_batch(B, cfg, T=127, L_ocr=100, L_q=30, V_sub=(84, 187, 7), seed=1234, image=224,
+                    pad_id=2, bos_id=3, eos_id=4):
+    """SURVEY.md §8d synthetic batch; field names/dtypes as core/data/PhonemeLaTrDataset.py:51-58."""
+    g = torch.Generator().manual_seed(seed)
+    V = cfg.vocab_size
+    coords = torch.zeros(B, L_ocr, 6, dtype=torch.long)
+    ocr = torch.zeros(B, L_ocr, dtype=torch.long)
+    om = torch.zeros(B, L_ocr)
+    q = torch.zeros(B, L_q, dtype=torch.long)
+    qm = torch.zeros(B, L_q)
+    labels = torch.full((B, T + 1, 3), pad_id, dtype=torch.long)
+    lmask = torch.ones(B, T + 1)                       # 1.0 = pad (float(create_mask), PhonemeLaTrDataset.py:55)
+    for b in range(B):
+        n = int(torch.randint(min(20, L_ocr - 1), min(100, L_ocr), (1,), generator=g))
+        x0 = torch.randint(0, 901, (n,), generator=g)
+        y0 = torch.randint(0, 901, (n,), generator=g)
+        w = torch.randint(1, 101, (n,), generator=g)
+        h = torch.randint(1, 101, (n,), generator=g)
+        coords[b, :n] = torch.stack([x0, y0, x0 + w, y0 + h, w, h], dim=-1)
+        coords[b, n] = 1000
+        ocr[b, :n] = torch.randint(3, V, (n,), generator=g)
+        ocr[b, n] = 1
+        om[b, : n + 1] = 1
+        nq = int(torch.randint(min(8, L_q), L_q + 1, (1,), generator=g))
+        q[b, : nq - 1] = torch.randint(3, V, (nq - 1,), generator=g)
+        q[b, nq - 1] = 1
+        qm[b, :nq] = 1
+        ln = int(torch.randint(min(4, T), min(40, T) + 1, (1,), generator=g))
+        labels[b, 0] = torch.tensor([bos_id, 0, 0])
+        labels[b, 1:ln, 0] = torch.randint(5, V_sub[0], (ln - 1,), generator=g)
+        labels[b, 1:ln, 1] = torch.randint(2, V_sub[1], (ln - 1,), generator=g)
+        labels[b, 1:ln, 2] = torch.randint(0, V_sub[2], (ln - 1,), generator=g)
+        labels[b, ln] = torch.tensor([eos_id, 0, 0])
+        lmask[b, : ln + 1] = 0
+    pix = torch.randn(B, 3, image, image, generator=g)
+    return {"pixel_values": pix, "coordinates": coords, "input_ids": q, "src_attention_mask": qm,
+            "label_ids": labels, "label_attention_mask": lmask, "tokenized_ocr": ocr, "ocr_attention_mask": om}

@@ -1,0 +1,267 @@
+// head.cu — K4 (small-vocabulary variant): fused multi-token phoneme head + 3x cross-entropy.
+//
+// reference semantics restated (no code shared):
+//   core/model/PhonemeLaTr.py:124-130                     column split + onset/rhyme/tone Linear heads
+//   core/executor/PhonemeLaTr_Executor.py:181-190,263-265 3x CrossEntropyLoss(ignore_index=pad), summed
+//
+// Shapes are tiny for a GEMM (N=8128 rows, K=256 per head, V = 84/187/7): 1.2 GFLOP against
+// 12.5 MB of activations, so the kernel is organised around reading h exactly once and never
+// writing logits: one warp owns a row, each lane holds 8 columns of each head's K-slice, the
+// 32-way dot-product reductions are done as a 31-shuffle transpose-reduce per block of 32
+// vocabulary entries (instead of 5 shuffles per entry), and log-sum-exp is kept online.
+// Weights (142 KB in bf16) stay L1/L2 resident.
+#include "common.cuh"
+
+namespace pvqa {
+
+struct HeadParams {
+  const void* h;              // (N, d) act dtype
+  const int64_t* tgt;         // (N, 3) with row stride tgt_stride (elements)
+  long long tgt_stride;
+  const void* W[3];           // (V_k, w_k) w dtype
+  const void* b[3];           // (V_k) w dtype
+  float* loss_sum;            // [3]
+  int* count;                 // [3]
+  float* lse;                 // (N, 3)
+  void* logits[3];            // optional (N, V_k) act dtype
+  // backward
+  const float* grad_loss;     // device scalar
+  void* dlogits[3];           // (N, V_k) act dtype
+  int N, d, wdim[3], off[3], V[3];
+  long long ignore_index;
+};
+
+constexpr int kHeadThreads = 256;
+constexpr int kMaxChunks = 2;   // per-lane 8-column chunks per head slice: supports w_k <= 512
+
+// sum x[i] over lanes so that lane l ends with the total of x[l] (31 shuffles).
+__device__ __forceinline__ float transpose_reduce32(float (&x)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? x[i] : x[i + s];
+      const float keep = up ? x[i + s] : x[i];
+      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return x[0];
+}
+
+template <typename WT>
+__device__ __forceinline__ float dot_chunks(const float (&hv)[kMaxChunks][8], const WT* wrow, int lane, int w) {
+  float acc = 0.f;
+#pragma unroll
+  for (int c = 0; c < kMaxChunks; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    if (col < w) {
+      f8 wv = Vec8<WT>::load(wrow + col);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = fmaf(hv[c][j], wv.v[j], acc);
+    }
+  }
+  return acc;
+}
+
+// MODE 0: forward (loss sums, counts, lse, optional logits); MODE 1: backward (dlogits)
+template <typename WT, typename AT, int MODE>
+__global__ void __launch_bounds__(kHeadThreads)
+phoneme_head_kernel(const HeadParams p) {
+  const int lane = threadIdx.x & 31;
+  const int warps = kHeadThreads / 32;
+  const AT* h = reinterpret_cast<const AT*>(p.h);
+  float loss_acc[3] = {0.f, 0.f, 0.f};
+  int cnt_acc[3] = {0, 0, 0};
+  float gl = 0.f;
+  if (MODE == 1) gl = *p.grad_loss;
+
+  for (int n = blockIdx.x * warps + (threadIdx.x >> 5); n < p.N; n += gridDim.x * warps) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int w = p.wdim[k], V = p.V[k];
+      const WT* W = reinterpret_cast<const WT*>(p.W[k]);
+      const WT* bias = reinterpret_cast<const WT*>(p.b[k]);
+      // this lane's columns of the head's K-slice
+      float hv[kMaxChunks][8];
+#pragma unroll
+      for (int c = 0; c < kMaxChunks; ++c) {
+        const int col = (c * 32 + lane) * 8;
+        if (col < w) {
+          f8 t = Vec8<AT>::load(h + (long long)n * p.d + p.off[k] + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) hv[c][j] = t.v[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) hv[c][j] = 0.f;
+        }
+      }
+      const long long tgt = p.tgt[(long long)n * p.tgt_stride + k];
+      const bool valid = tgt != p.ignore_index;
+
+      if (MODE == 0) {
+        // online log-sum-exp, lane l tracks vocabulary entries v0 + l
+        float m = -INFINITY, s = 0.f, tl = 0.f;
+        for (int v0 = 0; v0 < V; v0 += 32) {
+          float x[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = (v0 + i < V) ? dot_chunks<WT>(hv, W + (long long)(v0 + i) * w, lane, w) : 0.f;
+          float logit = transpose_reduce32(x, lane);
+          const int v = v0 + lane;
+          if (v < V) {
+            logit += to_f32(bias[v]);
+            if (p.logits[k]) reinterpret_cast<AT*>(p.logits[k])[(long long)n * V + v] = from_f32<AT>(logit);
+            const float mn = fmaxf(m, logit);
+            s = s * __expf(m - mn) + __expf(logit - mn);
+            m = mn;
+            if (v == tgt) tl = logit;
+          }
+        }
+        // merge lanes
+        float M = m;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+        float S = (m == -INFINITY) ? 0.f : s * __expf(m - M);
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+          S += __shfl_xor_sync(0xffffffffu, S, o);
+          tl += __shfl_xor_sync(0xffffffffu, tl, o);
+        }
+        const float lse = M + __logf(S);
+        if (lane == 0) p.lse[(long long)n * 3 + k] = lse;
+        if (valid) { loss_acc[k] += lse - tl; cnt_acc[k] += 1; }
+      } else {
+        const float lse = p.lse[(long long)n * 3 + k];
+        const int cnt = p.count[k];
+        const float g = (valid && cnt > 0) ? gl / (float)cnt : 0.f;
+        AT* dl = reinterpret_cast<AT*>(p.dlogits[k]) + (long long)n * V;
+        for (int v0 = 0; v0 < V; v0 += 32) {
+          const int v = v0 + lane;
+          if (!valid) {                      // warp-uniform: ignored rows get zero gradient, skip the math
+            if (v < V) dl[v] = from_f32<AT>(0.f);
+            continue;
+          }
+          float x[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = (v0 + i < V) ? dot_chunks<WT>(hv, W + (long long)(v0 + i) * w, lane, w) : 0.f;
+          float logit = transpose_reduce32(x, lane);
+          if (v < V) {
+            logit += to_f32(bias[v]);
+            const float prob = __expf(logit - lse);
+            dl[v] = from_f32<AT>(g * (prob - (v == tgt ? 1.f : 0.f)));
+          }
+        }
+      }
+    }
+  }
+  if (MODE == 0) {
+    // one atomic per warp per head
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (cnt_acc[k]) { atomicAdd(p.loss_sum + k, loss_acc[k]); atomicAdd(p.count + k, cnt_acc[k]); }
+      }
+    }
+  }
+}
+
+static int validate_head(const char* fn, int64_t N, int64_t d, int64_t on_dim, int64_t rt_dim, int64_t V_o,
+                         int64_t V_r, int64_t V_t, int w_dtype, int act_dtype) {
+  PVQA_REQUIRE(N >= 0 && d > 0 && on_dim > 0 && rt_dim > 0, PVQA_ERR_SHAPE, "%s: bad dimension", fn);
+  PVQA_REQUIRE(on_dim + 2 * rt_dim == d, PVQA_ERR_SHAPE, "%s: on_dim + 2*rt_dim != d", fn);
+  PVQA_REQUIRE(on_dim % 8 == 0 && rt_dim % 8 == 0, PVQA_ERR_SHAPE,
+               "%s: head slice widths (%lld, %lld) must be multiples of 8", fn, (long long)on_dim, (long long)rt_dim);
+  PVQA_REQUIRE(on_dim <= kMaxChunks * 256 && rt_dim <= kMaxChunks * 256, PVQA_ERR_SHAPE,
+               "%s: head slice wider than %d", fn, kMaxChunks * 256);
+  PVQA_REQUIRE(V_o > 0 && V_r > 0 && V_t > 0, PVQA_ERR_SHAPE, "%s: empty vocabulary", fn);
+  PVQA_REQUIRE((w_dtype == PVQA_F32 || w_dtype == PVQA_BF16) && (act_dtype == PVQA_F32 || act_dtype == PVQA_BF16),
+               PVQA_ERR_DTYPE, "%s: bad dtype", fn);
+  return PVQA_OK;
+}
+
+template <int MODE>
+static void launch_head(const HeadParams& p, int w_dtype, int act_dtype, cudaStream_t st) {
+  const int warps = kHeadThreads / 32;
+  long long need = ((long long)p.N + warps - 1) / warps;
+  long long cap = (long long)num_sms() * 4;
+  const int grid = (int)(need < cap ? (need < 1 ? 1 : need) : cap);
+  if (w_dtype == PVQA_BF16 && act_dtype == PVQA_BF16)
+    phoneme_head_kernel<__nv_bfloat16, __nv_bfloat16, MODE><<<grid, kHeadThreads, 0, st>>>(p);
+  else if (w_dtype == PVQA_F32 && act_dtype == PVQA_F32)
+    phoneme_head_kernel<float, float, MODE><<<grid, kHeadThreads, 0, st>>>(p);
+  else if (w_dtype == PVQA_F32)
+    phoneme_head_kernel<float, __nv_bfloat16, MODE><<<grid, kHeadThreads, 0, st>>>(p);
+  else
+    phoneme_head_kernel<__nv_bfloat16, float, MODE><<<grid, kHeadThreads, 0, st>>>(p);
+  count_launch();
+}
+
+}  // namespace pvqa
+
+using namespace pvqa;
+
+extern "C" int pvqa_phoneme_head_ce_fwd(const void* h, const int64_t* targets, int64_t tgt_row_stride,
+                                        const void* W_onset, const void* b_onset, const void* W_rhyme,
+                                        const void* b_rhyme, const void* W_tone, const void* b_tone,
+                                        float* loss_sum, int32_t* count, float* lse, void* logits_onset,
+                                        void* logits_rhyme, void* logits_tone, int64_t N, int64_t d,
+                                        int64_t on_dim, int64_t rt_dim, int64_t V_o, int64_t V_r, int64_t V_t,
+                                        int64_t ignore_index, int w_dtype, int act_dtype, void* stream) {
+  int rc = validate_head("phoneme_head_ce_fwd", N, d, on_dim, rt_dim, V_o, V_r, V_t, w_dtype, act_dtype);
+  if (rc) return rc;
+  PVQA_REQUIRE(loss_sum && count, PVQA_ERR_NULL, "phoneme_head_ce_fwd: loss_sum/count NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(loss_sum, 0, 3 * sizeof(float), st);
+  cudaMemsetAsync(count, 0, 3 * sizeof(int32_t), st);
+  if (N == 0) return PVQA_OK;
+  PVQA_REQUIRE(h && targets && W_onset && b_onset && W_rhyme && b_rhyme && W_tone && b_tone && lse, PVQA_ERR_NULL,
+               "phoneme_head_ce_fwd: NULL pointer");
+  PVQA_REQUIRE(aligned16(h) && aligned16(W_onset) && aligned16(W_rhyme) && aligned16(W_tone), PVQA_ERR_ALIGN,
+               "phoneme_head_ce_fwd: h / W must be 16-byte aligned");
+  HeadParams p{};
+  p.h = h; p.tgt = targets; p.tgt_stride = tgt_row_stride;
+  p.W[0] = W_onset; p.W[1] = W_rhyme; p.W[2] = W_tone;
+  p.b[0] = b_onset; p.b[1] = b_rhyme; p.b[2] = b_tone;
+  p.loss_sum = loss_sum; p.count = count; p.lse = lse;
+  p.logits[0] = logits_onset; p.logits[1] = logits_rhyme; p.logits[2] = logits_tone;
+  p.N = (int)N; p.d = (int)d;
+  p.wdim[0] = (int)on_dim; p.wdim[1] = p.wdim[2] = (int)rt_dim;
+  p.off[0] = 0; p.off[1] = (int)on_dim; p.off[2] = (int)(on_dim + rt_dim);
+  p.V[0] = (int)V_o; p.V[1] = (int)V_r; p.V[2] = (int)V_t;
+  p.ignore_index = ignore_index;
+  launch_head<0>(p, w_dtype, act_dtype, st);
+  PVQA_CHECK_LAUNCH("phoneme_head_ce_fwd");
+  return PVQA_OK;
+}
+
+extern "C" int pvqa_phoneme_head_ce_bwd(const void* h, const int64_t* targets, int64_t tgt_row_stride,
+                                        const void* W_onset, const void* b_onset, const void* W_rhyme,
+                                        const void* b_rhyme, const void* W_tone, const void* b_tone,
+                                        const float* lse, const int32_t* count, const float* grad_loss,
+                                        void* dlogits_onset, void* dlogits_rhyme, void* dlogits_tone, int64_t N,
+                                        int64_t d, int64_t on_dim, int64_t rt_dim, int64_t V_o, int64_t V_r,
+                                        int64_t V_t, int64_t ignore_index, int w_dtype, int act_dtype,
+                                        void* stream) {
+  int rc = validate_head("phoneme_head_ce_bwd", N, d, on_dim, rt_dim, V_o, V_r, V_t, w_dtype, act_dtype);
+  if (rc) return rc;
+  if (N == 0) return PVQA_OK;
+  PVQA_REQUIRE(h && targets && W_onset && b_onset && W_rhyme && b_rhyme && W_tone && b_tone && lse && count &&
+                   grad_loss && dlogits_onset && dlogits_rhyme && dlogits_tone,
+               PVQA_ERR_NULL, "phoneme_head_ce_bwd: NULL pointer");
+  PVQA_REQUIRE(aligned16(h) && aligned16(W_onset) && aligned16(W_rhyme) && aligned16(W_tone), PVQA_ERR_ALIGN,
+               "phoneme_head_ce_bwd: h / W must be 16-byte aligned");
+  HeadParams p{};
+  p.h = h; p.tgt = targets; p.tgt_stride = tgt_row_stride;
+  p.W[0] = W_onset; p.W[1] = W_rhyme; p.W[2] = W_tone;
+  p.b[0] = b_onset; p.b[1] = b_rhyme; p.b[2] = b_tone;
+  p.lse = const_cast<float*>(lse); p.count = const_cast<int*>(count); p.grad_loss = grad_loss;
+  p.dlogits[0] = dlogits_onset; p.dlogits[1] = dlogits_rhyme; p.dlogits[2] = dlogits_tone;
+  p.N = (int)N; p.d = (int)d;
+  p.wdim[0] = (int)on_dim; p.wdim[1] = p.wdim[2] = (int)rt_dim;
+  p.off[0] = 0; p.off[1] = (int)on_dim; p.off[2] = (int)(on_dim + rt_dim);
+  p.V[0] = (int)V_o; p.V[1] = (int)V_r; p.V[2] = (int)V_t;
+  p.ignore_index = ignore_index;
+  launch_head<1>(p, w_dtype, act_dtype, (cudaStream_t)stream);
+  PVQA_CHECK_LAUNCH("phoneme_head_ce_bwd");
+  return PVQA_OK;
+}

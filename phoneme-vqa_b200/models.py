@@ -1,0 +1,258 @@
+"""Drop-in model classes: same names, constructor / forward / generate signatures and
+state_dict keys as the reference's ``core.model`` classes, with the hot
+path (fused embeddings, attention, phoneme head + loss) running in libpvqa_sm100.so.
+
+Selecting them from the reference's YAML is ``MODEL_CLASS: "PhonemeLaTr"`` after
+``from phoneme_vqa_b200.models import *`` has been added to ``core/model/__init__.py``
+(see INTEGRATION.md).
+"""
+from __future__ import annotations
+
+import contextlib
+import os
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .modules import (BaseDecoder, PhonemeEmbedding, SinusoidalPositionalEncoding, SpatialModule, T5EncoderModel,
+                      T5Stack, _lin, _t5_init)
+
+__all__ = ["LaTr_config", "CustomizedLaTr_config", "CustomizedPreSTU_config", "PhonemeLaTr", "PhonemePreSTU"]
+
+
+def _random_init(config) -> bool:
+    return os.environ.get("PVQA_RANDOM_INIT", "0") == "1" or bool(getattr(config, "random_init", False))
+
+
+def _auto_config(name):
+    from transformers import AutoConfig
+    return AutoConfig.from_pretrained(name)
+
+
+# reference: core/model/LaTr.py:5-12
+class LaTr_config:
+    def build(self, config):
+        model_config = _auto_config(config.backbone_name)
+        model_config.update({"max_2d_position_embeddings": config.max_2d_position_embeddings,
+                             "vit_model": config.vit_model_name})
+        return model_config
+
+
+# reference: core/model/PhonemeLaTr.py:6-15 (same class in CustomizedLaTr.py)
+class CustomizedLaTr_config:
+    def build(self, config):
+        model_config = _auto_config(config.encoder_name)
+        model_config.update({"max_2d_position_embeddings": config.max_2d_position_embeddings,
+                             "vit_model": config.vit_model_name,
+                             "num_decoder_layers": config.num_decoder_layers,
+                             "n_head": config.n_head})
+        return model_config
+
+
+# reference: core/model/PhonemePreSTU.py:6-14
+class CustomizedPreSTU_config:
+    def build(self, config):
+        model_config = _auto_config(config.encoder_name)
+        model_config.update({"vit_model": config.vit_model_name,
+                             "num_decoder_layers": config.num_decoder_layers,
+                             "n_head": config.n_head})
+        return model_config
+
+
+def _build_vit(config):
+    """HF ViTModel (library code: the ViT tower is outside the three north-star kernels).
+    Pretrained weights like the reference unless random init was requested (no network here)."""
+    from transformers import ViTConfig, ViTModel
+    if _random_init(config):
+        vc = getattr(config, "vit_config", None)
+        vcfg = ViTConfig(**vc) if isinstance(vc, dict) else ViTConfig()
+        vcfg._attn_implementation = "sdpa"
+        return ViTModel(vcfg)
+    return ViTModel.from_pretrained(config.vit_model, attn_implementation="sdpa")
+
+
+def _load_pretrained_t5_encoder(encoder: T5EncoderModel, config):
+    if _random_init(config):
+        return
+    from transformers import T5EncoderModel as HFEncoder
+    sd = HFEncoder.from_pretrained(config._name_or_path).state_dict()
+    encoder.load_state_dict(sd, strict=True)
+
+
+class _VisionMixin:
+    """frozen-ViT handling shared by the LaTr / PreSTU families."""
+
+    def _vit_tokens(self, pixel_values):
+        frozen = not any(p.requires_grad for p in self.vit.parameters())
+        ctx = torch.no_grad() if frozen else contextlib.nullcontext()
+        amp = (torch.autocast("cuda", dtype=torch.bfloat16) if self.compute_dtype == torch.bfloat16
+               else contextlib.nullcontext())
+        with ctx, amp:
+            # ViTModel.forward minus the pooler (never used by the reference: PhonemeLaTr.py:220)
+            emb = self.vit.embeddings(pixel_values)
+            seq = self.vit.encoder(emb).last_hidden_state
+            seq = self.vit.layernorm(seq)
+        return seq
+
+    def set_compute_dtype(self, dtype):
+        assert dtype in (torch.float32, torch.bfloat16)
+        self.compute_dtype = dtype
+        return self
+
+
+class PhonemeLaTr(nn.Module, _VisionMixin):
+    """reference: core/model/PhonemeLaTr.py:46-236"""
+
+    def __init__(self, config, onset_vocab_size, rhyme_vocab_size, tone_vocab_size):
+        super().__init__()
+        self.config = config
+        self.compute_dtype = torch.float32
+        self.encoder = T5EncoderModel(config)
+        _load_pretrained_t5_encoder(self.encoder, config)
+
+        self.spatial_feat_extractor = SpatialModule(config)
+        self.vit = _build_vit(config)
+        self.visual_projector = nn.Linear(self.vit.config.hidden_size, config.d_model)
+
+        # freeze ViT (reference :63-66)
+        for _, child in self.vit.named_children():
+            for param in child.parameters():
+                param.requires_grad = False
+
+        d = config.d_model
+        self.rhyme_tone_embed_dim = d // 3
+        self.onset_embed_dim = int(d - self.rhyme_tone_embed_dim * 2)
+        self.tgt_tok_emb = PhonemeEmbedding(onset_vocab_size, rhyme_vocab_size, tone_vocab_size,
+                                            self.onset_embed_dim, self.rhyme_tone_embed_dim)
+        self.positional_encoding = SinusoidalPositionalEncoding(d, dropout=0.1)
+        self.decoder = BaseDecoder(emb_size=d, num_layers=config.num_decoder_layers, n_head=config.n_head)
+        self.shared_lm_head = nn.Linear(d, d)
+        self.onset_lm_head = nn.Linear(self.onset_embed_dim, onset_vocab_size)
+        self.rhyme_lm_head = nn.Linear(self.rhyme_tone_embed_dim, rhyme_vocab_size)
+        self.tone_lm_head = nn.Linear(self.rhyme_tone_embed_dim, tone_vocab_size)
+
+    # -- reference :219-231 ---------------------------------------------------------
+    def _calculate_embedding(self, pixel_values, coordinates, input_ids, ocr_attention_mask, src_attention_mask,
+                             tokenized_ocr):
+        vit_tokens = self._vit_tokens(pixel_values)
+        img_feat = _lin(vit_tokens.to(self.compute_dtype), self.visual_projector.weight, self.visual_projector.bias)
+        return ops.embed_multimodal(img_feat, coordinates, tokenized_ocr, input_ids, ocr_attention_mask,
+                                    src_attention_mask, self.encoder.shared.weight,
+                                    self.spatial_feat_extractor.tables(), out_dtype=self.compute_dtype)
+
+    def _encode(self, pixel_values, coordinates, input_ids, ocr_attention_mask, src_attention_mask, tokenized_ocr):
+        inputs_embeds, attention_mask = self._calculate_embedding(
+            pixel_values, coordinates, input_ids, ocr_attention_mask, src_attention_mask, tokenized_ocr)
+        enc = self.encoder.encoder(inputs_embeds, attention_mask, compute_dtype=self.compute_dtype)
+        return enc, attention_mask
+
+    # -- reference :134-144 ---------------------------------------------------------
+    def decode(self, labels, encoder_outputs, encoder_attention_mask, label_attention_mask=None):
+        emb = self.tgt_tok_emb(labels, self.positional_encoding.pos_embedding,
+                               dropout_p=self.positional_encoding.p, training=self.training,
+                               out_dtype=torch.float32)
+        # square-subsequent float mask == causal flag; float key masks are additive
+        return self.decoder(emb, encoder_outputs, tgt_mask=None,
+                            memory_key_padding_mask=encoder_attention_mask,
+                            tgt_key_padding_mask=label_attention_mask,
+                            compute_dtype=self.compute_dtype, causal=True)
+
+    def _heads(self, h):
+        on, rt = self.onset_embed_dim, self.rhyme_tone_embed_dim
+        return (_lin(h[:, :, :on], self.onset_lm_head.weight, self.onset_lm_head.bias),
+                _lin(h[:, :, on:on + rt], self.rhyme_lm_head.weight, self.rhyme_lm_head.bias),
+                _lin(h[:, :, on + rt:], self.tone_lm_head.weight, self.tone_lm_head.bias))
+
+    # -- reference :98-132 ----------------------------------------------------------
+    def forward(self, pixel_values, coordinates, input_ids, labels, src_attention_mask, label_attention_mask,
+                ocr_attention_mask, tokenized_ocr):
+        enc, attention_mask = self._encode(pixel_values, coordinates, input_ids, ocr_attention_mask,
+                                           src_attention_mask, tokenized_ocr)
+        dec = self.decode(labels, enc, attention_mask, label_attention_mask)
+        h = _lin(dec.to(self.compute_dtype), self.shared_lm_head.weight, self.shared_lm_head.bias)
+        on, rh, to = self._heads(h)
+        return on.float(), rh.float(), to.float()
+
+    def forward_loss(self, pixel_values, coordinates, input_ids, labels, src_attention_mask, label_attention_mask,
+                     ocr_attention_mask, tokenized_ocr, targets, ignore_index):
+        """Fused fast path: model forward + the executor's 3x CrossEntropyLoss
+        (core/executor/PhonemeLaTr_Executor.py:181-190) without materialising logits.
+        `targets` = labels[:, 1:, :] of the executor, `labels` = labels[:, :-1]."""
+        enc, attention_mask = self._encode(pixel_values, coordinates, input_ids, ocr_attention_mask,
+                                           src_attention_mask, tokenized_ocr)
+        dec = self.decode(labels, enc, attention_mask, label_attention_mask)
+        h = _lin(dec.to(self.compute_dtype), self.shared_lm_head.weight, self.shared_lm_head.bias)
+        return ops.phoneme_head_ce(h.reshape(-1, h.shape[-1]), targets.reshape(-1, 3),
+                                   self.onset_lm_head.weight, self.onset_lm_head.bias,
+                                   self.rhyme_lm_head.weight, self.rhyme_lm_head.bias,
+                                   self.tone_lm_head.weight, self.tone_lm_head.bias, ignore_index)
+
+    # -- reference :146-217 ---------------------------------------------------------
+    def generate(self, pixel_values, coordinates, input_ids, src_attention_mask, ocr_attention_mask, tokenized_ocr,
+                 start_symbol, end_symbol, max_length=20, isgreedy=True, num_beam=2):
+        return self.greedy_generate(pixel_values, coordinates, input_ids, src_attention_mask, ocr_attention_mask,
+                                    tokenized_ocr, start_symbol, end_symbol, max_length)
+
+    @torch.no_grad()
+    def greedy_generate(self, pixel_values, coordinates, input_ids, src_attention_mask, ocr_attention_mask,
+                        tokenized_ocr, start_symbol, end_symbol, max_len=100):
+        bz = input_ids.size(0)
+        dev = input_ids.device
+        enc, attention_mask = self._encode(pixel_values, coordinates, input_ids, ocr_attention_mask,
+                                           src_attention_mask, tokenized_ocr)
+        ys = torch.tensor([[[start_symbol, 0, 0]]], dtype=torch.long, device=dev).repeat(bz, 1, 1)
+        for _ in range(max_len):
+            out = self.decode(ys, enc, attention_mask)
+            # NOTE: like the reference (:195-205) greedy decoding does NOT apply shared_lm_head
+            on, rh, to = self._heads(out[:, -1:].to(self.compute_dtype))
+            nxt = torch.stack([on[:, -1].float().argmax(-1), rh[:, -1].float().argmax(-1),
+                               to[:, -1].float().argmax(-1)], dim=-1)
+            ys = torch.cat([ys, nxt.unsqueeze(1)], dim=1)
+            if torch.any(ys[:, :, 0] == end_symbol, dim=1).sum() == bz:
+                break
+        return ys
+
+
+class PhonemePreSTU(nn.Module, _VisionMixin):
+    """reference: core/model/PhonemePreSTU.py:16-199 (intended behaviour).
+    No layout branch, ViT NOT frozen."""
+
+    def __init__(self, config, onset_vocab_size, rhyme_vocab_size, tone_vocab_size):
+        super().__init__()
+        self.config = config
+        self.compute_dtype = torch.float32
+        self.encoder = T5EncoderModel(config)
+        _load_pretrained_t5_encoder(self.encoder, config)
+        self.vit = _build_vit(config)
+        self.visual_projector = nn.Linear(self.vit.config.hidden_size, config.d_model)
+        d = config.d_model
+        self.rhyme_tone_embed_dim = d // 3
+        self.onset_embed_dim = int(d - self.rhyme_tone_embed_dim * 2)
+        self.tgt_tok_emb = PhonemeEmbedding(onset_vocab_size, rhyme_vocab_size, tone_vocab_size,
+                                            self.onset_embed_dim, self.rhyme_tone_embed_dim)
+        self.positional_encoding = SinusoidalPositionalEncoding(d, dropout=0.1)
+        self.decoder = BaseDecoder(emb_size=d, num_layers=config.num_decoder_layers, n_head=config.n_head)
+        self.shared_lm_head = nn.Linear(d, d)
+        self.onset_lm_head = nn.Linear(self.onset_embed_dim, onset_vocab_size)
+        self.rhyme_lm_head = nn.Linear(self.rhyme_tone_embed_dim, rhyme_vocab_size)
+        self.tone_lm_head = nn.Linear(self.rhyme_tone_embed_dim, tone_vocab_size)
+
+    def _calculate_embedding(self, pixel_values, input_ids, src_attention_mask):
+        vit_tokens = self._vit_tokens(pixel_values)
+        img_feat = _lin(vit_tokens.to(self.compute_dtype), self.visual_projector.weight, self.visual_projector.bias)
+        return ops.embed_multimodal(img_feat, None, None, input_ids, None, src_attention_mask,
+                                    self.encoder.shared.weight, (), out_dtype=self.compute_dtype)
+
+    calculate_embedding = _calculate_embedding   # the reference's forward calls this name (D5)
+
+    decode = PhonemeLaTr.decode
+    _heads = PhonemeLaTr._heads
+
+    def forward(self, pixel_values, input_ids, labels, src_attention_mask, label_attention_mask):
+        inputs_embeds, attention_mask = self._calculate_embedding(pixel_values, input_ids, src_attention_mask)
+        enc = self.encoder.encoder(inputs_embeds, attention_mask, compute_dtype=self.compute_dtype)
+        dec = self.decode(labels, enc, attention_mask, label_attention_mask)
+        h = _lin(dec.to(self.compute_dtype), self.shared_lm_head.weight, self.shared_lm_head.bias)
+        on, rh, to = self._heads(h)
+        return on.float(), rh.float(), to.float()

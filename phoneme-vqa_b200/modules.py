@@ -1,0 +1,457 @@
+"""Host-side building blocks with the reference's module / parameter names.
+
+Each class mirrors a module of the reference (or of the libraries it calls) closely enough
+that ``state_dict()`` keys and tensor shapes are identical, so checkpoints written by the
+reference load with ``strict=True``.  Dense linears stay cuBLAS (torch);
+the gather/scatter embeddings, attention and the phoneme head + loss call libpvqa_sm100.so
+through ``ops``.
+
+Precision: parameters are fp32 masters.  ``compute_dtype`` (fp32 or bf16) selects the
+activation dtype of linears / attention / kernels; the residual stream and all
+normalisation statistics stay fp32, which is what ``torch.autocast(bfloat16)`` gives the
+reference.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+
+def _lin(x, weight, bias=None):
+    """F.linear in x's dtype with fp32 master weights."""
+    w = weight if weight.dtype == x.dtype else weight.to(x.dtype)
+    b = None if bias is None else (bias if bias.dtype == x.dtype else bias.to(x.dtype))
+    return F.linear(x, w, b)
+
+
+# ----------------------------------------------------------------------------------
+# reference: core/model/PhonemeLaTr.py:17-44 (identical copies in LaTr.py, CustomizedLaTr.py)
+# ----------------------------------------------------------------------------------
+class SpatialModule(nn.Module):
+    """Six 2-D layout tables.  forward() is only used stand-alone; inside the models the
+    six gathers are fused with the token embedding and the concat by K1."""
+
+    ORDER = ("top_left_x", "top_left_y", "bottom_right_x", "bottom_right_y", "width_emb", "height_emb")
+
+    def __init__(self, config):
+        super().__init__()
+        n, d = config.max_2d_position_embeddings, config.d_model
+        # registration order follows the reference so state_dict() key order matches too
+        self.top_left_x = nn.Embedding(n, d)
+        self.bottom_right_x = nn.Embedding(n, d)
+        self.top_left_y = nn.Embedding(n, d)
+        self.bottom_right_y = nn.Embedding(n, d)
+        self.width_emb = nn.Embedding(n, d)
+        self.height_emb = nn.Embedding(n, d)
+
+    def tables(self):
+        """weights in coordinate-column order x0, y0, x1, y1, w, h"""
+        return [getattr(self, n).weight for n in self.ORDER]
+
+    def forward(self, coordinates):
+        B, L, _ = coordinates.shape
+        w = self.top_left_x.weight
+        zero_tok = torch.zeros((1, w.shape[1]), dtype=w.dtype, device=w.device)
+        ids = torch.zeros((B, L), dtype=torch.long, device=coordinates.device)
+        ones = torch.ones((B, L), dtype=torch.float32, device=coordinates.device)
+        out, _ = ops.embed_multimodal(None, coordinates, ids, None, ones, None, zero_tok, self.tables(),
+                                      out_dtype=w.dtype)
+        return out
+
+
+# ----------------------------------------------------------------------------------
+# reference: PhonoLaTr/modules.py:27-63 (3-table form expected by core/model/PhonemeLaTr.py:72-78)
+# ----------------------------------------------------------------------------------
+class PhonemeEmbedding(nn.Module):
+    def __init__(self, onset_vocab_size, rhyme_vocab_size, tone_vocab_size, onset_embed_dim, rhyme_tone_embed_dim):
+        super().__init__()
+        self.onset_embedding = nn.Embedding(onset_vocab_size, onset_embed_dim)
+        self.rhyme_embedding = nn.Embedding(rhyme_vocab_size, rhyme_tone_embed_dim)
+        self.tone_embedding = nn.Embedding(tone_vocab_size, rhyme_tone_embed_dim)
+
+    def forward(self, phoneme_tensor, pos_embedding=None, dropout_p=0.0, training=False, out_dtype=None):
+        d = self.onset_embedding.embedding_dim + 2 * self.rhyme_embedding.embedding_dim
+        if pos_embedding is None:
+            pos_embedding = torch.zeros((phoneme_tensor.shape[1], d), device=phoneme_tensor.device)
+        return ops.embed_target(phoneme_tensor, self.onset_embedding.weight, self.rhyme_embedding.weight,
+                                self.tone_embedding.weight, pos_embedding, dropout_p=dropout_p,
+                                training=training, out_dtype=out_dtype)
+
+
+# reference: core/model/modules/transformer_utils.py:6-25
+class SinusoidalPositionalEncoding(nn.Module):
+    def __init__(self, emb_size: int, dropout: float, maxlen: int = 5000):
+        super().__init__()
+        den = torch.exp(-torch.arange(0, emb_size, 2) * math.log(10000) / emb_size)
+        pos = torch.arange(0, maxlen).reshape(maxlen, 1)
+        pos_embedding = torch.zeros((maxlen, emb_size))
+        pos_embedding[:, 0::2] = torch.sin(pos * den)
+        pos_embedding[:, 1::2] = torch.cos(pos * den)
+        self.p = dropout
+        self.dropout = nn.Dropout(dropout)
+        self.register_buffer("pos_embedding", pos_embedding.unsqueeze(0))
+
+    def forward(self, token_embedding):
+        return self.dropout(token_embedding + self.pos_embedding[:, : token_embedding.size(1)].to(token_embedding.dtype))
+
+
+# ----------------------------------------------------------------------------------
+# T5 encoder (HF transformers T5Stack layout: modeling_t5.py:46-70,153-500,617-793)
+# ----------------------------------------------------------------------------------
+class T5LayerNorm(nn.Module):
+    def __init__(self, hidden_size, eps=1e-6):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(hidden_size))
+        self.variance_epsilon = eps
+
+    def forward(self, x, out_dtype=None):
+        return ops.rms_norm(x, self.weight, self.variance_epsilon, out_dtype or x.dtype)
+
+
+_BUCKET_CACHE: dict = {}
+
+
+def t5_bucket_lut(q_len, k_len, bidirectional, num_buckets, max_distance, device):
+    """bucket id for every relative offset rel = j - i in [-(q_len-1), k_len-1] (HF formula,
+    modeling_t5.py:190-235, evaluated with the same torch float32 ops so ids are bit-exact)."""
+    key = (q_len, k_len, bidirectional, num_buckets, max_distance, str(device))
+    lut = _BUCKET_CACHE.get(key)
+    if lut is None:
+        rel = torch.arange(-(q_len - 1), k_len, dtype=torch.long)
+        nb = num_buckets
+        buckets = torch.zeros_like(rel)
+        if bidirectional:
+            nb //= 2
+            buckets = buckets + (rel > 0).long() * nb
+            rp = rel.abs()
+        else:
+            rp = -torch.min(rel, torch.zeros_like(rel))
+        max_exact = nb // 2
+        is_small = rp < max_exact
+        large = max_exact + (torch.log(rp.float() / max_exact) / math.log(max_distance / max_exact)
+                             * (nb - max_exact)).long()
+        large = torch.min(large, torch.full_like(large, nb - 1))
+        lut = (buckets + torch.where(is_small, rp, large)).to(device)
+        _BUCKET_CACHE[key] = lut
+    return lut
+
+
+class T5Attention(nn.Module):
+    def __init__(self, config, has_relative_attention_bias=False):
+        super().__init__()
+        self.is_decoder = getattr(config, "is_decoder", False)
+        self.has_relative_attention_bias = has_relative_attention_bias
+        self.relative_attention_num_buckets = config.relative_attention_num_buckets
+        self.relative_attention_max_distance = config.relative_attention_max_distance
+        self.d_model = config.d_model
+        self.key_value_proj_dim = config.d_kv
+        self.n_heads = config.num_heads
+        self.dropout = config.dropout_rate
+        self.inner_dim = self.n_heads * self.key_value_proj_dim
+        self.q = nn.Linear(self.d_model, self.inner_dim, bias=False)
+        self.k = nn.Linear(self.d_model, self.inner_dim, bias=False)
+        self.v = nn.Linear(self.d_model, self.inner_dim, bias=False)
+        self.o = nn.Linear(self.inner_dim, self.d_model, bias=False)
+        if has_relative_attention_bias:
+            self.relative_attention_bias = nn.Embedding(self.relative_attention_num_buckets, self.n_heads)
+
+    def rel_bias(self, q_len, k_len):
+        """(H, q_len + k_len - 1) fp32: bias as a function of the relative offset j - i."""
+        lut = t5_bucket_lut(q_len, k_len, not self.is_decoder, self.relative_attention_num_buckets,
+                            self.relative_attention_max_distance, self.relative_attention_bias.weight.device)
+        return self.relative_attention_bias.weight.float()[lut].t().contiguous()
+
+    def forward(self, x, rel_bias, key_add, kv=None, causal=False, dense_bias=None):
+        """x (B,S,d) compute dtype.  Self-attention when kv is None, else cross-attention on kv."""
+        B, S, _ = x.shape
+        H, D = self.n_heads, self.key_value_proj_dim
+        p_drop = self.dropout if self.training else 0.0
+        if kv is None:
+            w = torch.cat([self.q.weight, self.k.weight, self.v.weight], dim=0)
+            qkv = _lin(x, w).view(B, S, 3, H, D)
+            o = ops.attention_self(qkv, scale=1.0, rel_bias=rel_bias, key_add=key_add, causal=causal,
+                                   dropout_p=p_drop, dense_bias=dense_bias)
+        else:
+            q = _lin(x, self.q.weight).view(B, S, H, D)
+            w = torch.cat([self.k.weight, self.v.weight], dim=0)
+            kvp = _lin(kv, w).view(B, kv.shape[1], 2, H, D)
+            o = ops.attention_cross(q, kvp, scale=1.0, rel_bias=rel_bias, key_add=key_add, dropout_p=p_drop)
+        return _lin(o.reshape(B, S, H * D), self.o.weight)
+
+
+class T5LayerSelfAttention(nn.Module):
+    def __init__(self, config, has_relative_attention_bias=False):
+        super().__init__()
+        self.SelfAttention = T5Attention(config, has_relative_attention_bias)
+        self.layer_norm = T5LayerNorm(config.d_model, eps=config.layer_norm_epsilon)
+        self.dropout = nn.Dropout(config.dropout_rate)
+
+    def forward(self, hidden, rel_bias, key_add, compute_dtype, causal=False, dense_bias=None):
+        normed = self.layer_norm(hidden, out_dtype=compute_dtype)
+        attn = self.SelfAttention(normed, rel_bias, key_add, causal=causal, dense_bias=dense_bias)
+        return ops.residual_dropout_add(hidden, attn, self.dropout.p, self.training)
+
+
+class T5LayerCrossAttention(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.EncDecAttention = T5Attention(config, has_relative_attention_bias=False)
+        self.layer_norm = T5LayerNorm(config.d_model, eps=config.layer_norm_epsilon)
+        self.dropout = nn.Dropout(config.dropout_rate)
+
+    def forward(self, hidden, memory, key_add, compute_dtype):
+        normed = self.layer_norm(hidden, out_dtype=compute_dtype)
+        attn = self.EncDecAttention(normed, None, key_add, kv=memory)
+        return ops.residual_dropout_add(hidden, attn, self.dropout.p, self.training)
+
+
+class T5DenseActDense(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.wi = nn.Linear(config.d_model, config.d_ff, bias=False)
+        self.wo = nn.Linear(config.d_ff, config.d_model, bias=False)
+        self.dropout = nn.Dropout(config.dropout_rate)
+        self.act_name = config.dense_act_fn
+
+    def forward(self, x):
+        h = _lin(x, self.wi.weight)
+        h = F.relu(h) if self.act_name == "relu" else F.gelu(h, approximate="tanh" if self.act_name == "gelu_new" else "none")
+        h = F.dropout(h, self.dropout.p, self.training)
+        return _lin(h, self.wo.weight)
+
+
+class T5DenseGatedActDense(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.wi_0 = nn.Linear(config.d_model, config.d_ff, bias=False)
+        self.wi_1 = nn.Linear(config.d_model, config.d_ff, bias=False)
+        self.wo = nn.Linear(config.d_ff, config.d_model, bias=False)
+        self.dropout = nn.Dropout(config.dropout_rate)
+        self.act_name = config.dense_act_fn
+
+    def forward(self, x):
+        g = _lin(x, self.wi_0.weight)
+        g = F.relu(g) if self.act_name == "relu" else F.gelu(g, approximate="tanh" if self.act_name == "gelu_new" else "none")
+        h = g * _lin(x, self.wi_1.weight)
+        h = F.dropout(h, self.dropout.p, self.training)
+        return _lin(h, self.wo.weight)
+
+
+class T5LayerFF(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        gated = getattr(config, "is_gated_act", False)
+        self.DenseReluDense = T5DenseGatedActDense(config) if gated else T5DenseActDense(config)
+        self.layer_norm = T5LayerNorm(config.d_model, eps=config.layer_norm_epsilon)
+        self.dropout = nn.Dropout(config.dropout_rate)
+
+    def forward(self, hidden, compute_dtype):
+        normed = self.layer_norm(hidden, out_dtype=compute_dtype)
+        ff = self.DenseReluDense(normed)
+        return ops.residual_dropout_add(hidden, ff, self.dropout.p, self.training)
+
+
+class T5Block(nn.Module):
+    def __init__(self, config, has_relative_attention_bias=False, is_decoder=False):
+        super().__init__()
+        self.is_decoder = is_decoder
+        self.layer = nn.ModuleList([T5LayerSelfAttention(config, has_relative_attention_bias)])
+        if is_decoder:
+            self.layer.append(T5LayerCrossAttention(config))
+        self.layer.append(T5LayerFF(config))
+
+    def forward(self, hidden, rel_bias, key_add, compute_dtype, memory=None, memory_key_add=None, causal=False,
+                dense_bias=None):
+        hidden = self.layer[0](hidden, rel_bias, key_add, compute_dtype, causal=causal, dense_bias=dense_bias)
+        if self.is_decoder:
+            hidden = self.layer[1](hidden, memory, memory_key_add, compute_dtype)
+        return self.layer[-1](hidden, compute_dtype)
+
+
+def _t5_init(module, config):
+    """HF T5PreTrainedModel._init_weights (factor = config.initializer_factor)."""
+    factor = config.initializer_factor
+    d_model, d_kv, n_heads, d_ff = config.d_model, config.d_kv, config.num_heads, config.d_ff
+    for m in module.modules():
+        if isinstance(m, T5LayerNorm):
+            nn.init.constant_(m.weight, factor * 1.0)
+        elif isinstance(m, T5DenseActDense):
+            nn.init.normal_(m.wi.weight, mean=0.0, std=factor * (d_model ** -0.5))
+            nn.init.normal_(m.wo.weight, mean=0.0, std=factor * (d_ff ** -0.5))
+        elif isinstance(m, T5DenseGatedActDense):
+            nn.init.normal_(m.wi_0.weight, mean=0.0, std=factor * (d_model ** -0.5))
+            nn.init.normal_(m.wi_1.weight, mean=0.0, std=factor * (d_model ** -0.5))
+            nn.init.normal_(m.wo.weight, mean=0.0, std=factor * (d_ff ** -0.5))
+        elif isinstance(m, T5Attention):
+            nn.init.normal_(m.q.weight, mean=0.0, std=factor * ((d_model * d_kv) ** -0.5))
+            nn.init.normal_(m.k.weight, mean=0.0, std=factor * (d_model ** -0.5))
+            nn.init.normal_(m.v.weight, mean=0.0, std=factor * (d_model ** -0.5))
+            nn.init.normal_(m.o.weight, mean=0.0, std=factor * ((n_heads * d_kv) ** -0.5))
+            if m.has_relative_attention_bias:
+                nn.init.normal_(m.relative_attention_bias.weight, mean=0.0, std=factor * (d_model ** -0.5))
+
+
+class T5Stack(nn.Module):
+    """Encoder (or decoder) stack with HF's parameter names: embed_tokens, block.{i}.layer.{j}..., final_layer_norm."""
+
+    def __init__(self, config, embed_tokens=None, is_decoder=False, num_layers=None):
+        super().__init__()
+        self.config = config
+        self.is_decoder = is_decoder
+        self.embed_tokens = embed_tokens if embed_tokens is not None else nn.Embedding(config.vocab_size, config.d_model)
+        n = num_layers if num_layers is not None else config.num_layers
+        self.block = nn.ModuleList([T5Block(config, has_relative_attention_bias=(i == 0), is_decoder=is_decoder)
+                                    for i in range(n)])
+        for b in self.block:
+            b.layer[0].SelfAttention.is_decoder = is_decoder
+        self.final_layer_norm = T5LayerNorm(config.d_model, eps=config.layer_norm_epsilon)
+        self.dropout = nn.Dropout(config.dropout_rate)
+
+    @staticmethod
+    def key_add_from_mask(attention_mask):
+        """HF create_bidirectional_mask semantics (masking_utils, probed in SURVEY §8c): key j is
+        masked iff attention_mask[b, j] == 0; masked keys get finfo.min (== -inf for softmax)."""
+        if attention_mask is None:
+            return None
+        return torch.where(attention_mask != 0, 0.0, float("-inf")).to(torch.float32)
+
+    def forward(self, inputs_embeds, attention_mask=None, compute_dtype=torch.float32, memory=None,
+                memory_mask=None, external_rel_bias=None, dense_bias=None):
+        hidden = F.dropout(inputs_embeds.float(), self.dropout.p, self.training)
+        S = hidden.shape[1]
+        if dense_bias is not None or external_rel_bias is not None:
+            rel_bias = external_rel_bias     # SaL: bias supplied by the caller, mask NOT added
+            key_add = None
+        else:
+            rel_bias = self.block[0].layer[0].SelfAttention.rel_bias(S, S)
+            key_add = self.key_add_from_mask(attention_mask)
+        mem = None if memory is None else memory.to(compute_dtype)
+        mem_key_add = self.key_add_from_mask(memory_mask) if memory is not None else None
+        for blk in self.block:
+            hidden = blk(hidden, rel_bias, key_add, compute_dtype, memory=mem, memory_key_add=mem_key_add,
+                         causal=self.is_decoder, dense_bias=dense_bias)
+        hidden = self.final_layer_norm(hidden, out_dtype=torch.float32)
+        return F.dropout(hidden, self.dropout.p, self.training)
+
+
+class T5EncoderModel(nn.Module):
+    """`.shared` + `.encoder` exactly like HF's T5EncoderModel (tied embed_tokens)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.shared = nn.Embedding(config.vocab_size, config.d_model)
+        self.encoder = T5Stack(config, self.shared, is_decoder=False)
+        _t5_init(self, config)
+        nn.init.normal_(self.shared.weight, mean=0.0, std=config.initializer_factor * 1.0)
+
+
+# ----------------------------------------------------------------------------------
+# target-side decoder: torch nn.TransformerDecoder parameter layout
+# reference: core/model/modules/transformer_utils.py:38-64
+# ----------------------------------------------------------------------------------
+class _MHAParams(nn.Module):
+    """Parameter holder with nn.MultiheadAttention's names (in_proj_weight, in_proj_bias, out_proj.*)."""
+
+    def __init__(self, d_model, n_head):
+        super().__init__()
+        self.embed_dim, self.num_heads = d_model, n_head
+        self.head_dim = d_model // n_head
+        assert self.head_dim * n_head == d_model, "embed_dim must be divisible by num_heads"
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * d_model, d_model))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * d_model))
+        self.out_proj = nn.Linear(d_model, d_model)
+        nn.init.xavier_uniform_(self.in_proj_weight)
+        nn.init.constant_(self.out_proj.bias, 0.0)
+
+
+class TransformerDecoderLayer(nn.Module):
+    """Post-norm decoder layer (torch defaults: relu, dim_feedforward 2048, dropout .1, eps 1e-5)."""
+
+    def __init__(self, d_model, n_head, dim_feedforward=2048, dropout=0.1, layer_norm_eps=1e-5):
+        super().__init__()
+        self.self_attn = _MHAParams(d_model, n_head)
+        self.multihead_attn = _MHAParams(d_model, n_head)
+        self.linear1 = nn.Linear(d_model, dim_feedforward)
+        self.dropout = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(dim_feedforward, d_model)
+        self.norm1 = nn.LayerNorm(d_model, eps=layer_norm_eps)
+        self.norm2 = nn.LayerNorm(d_model, eps=layer_norm_eps)
+        self.norm3 = nn.LayerNorm(d_model, eps=layer_norm_eps)
+        self.dropout1 = nn.Dropout(dropout)
+        self.dropout2 = nn.Dropout(dropout)
+        self.dropout3 = nn.Dropout(dropout)
+        self.p = dropout
+
+    def forward(self, x, memory, tgt_key_add, memory_key_add, compute_dtype, causal=True):
+        B, T, d = x.shape
+        sa, ca = self.self_attn, self.multihead_attn
+        H, D = sa.num_heads, sa.head_dim
+        p_attn = self.p if self.training else 0.0
+        scale = 1.0 / math.sqrt(D)
+        xc = x.to(compute_dtype)
+        qkv = _lin(xc, sa.in_proj_weight, sa.in_proj_bias).view(B, T, 3, H, D)
+        a = ops.attention_self(qkv, scale=scale, rel_bias=None, key_add=tgt_key_add, causal=causal, dropout_p=p_attn)
+        a = _lin(a.reshape(B, T, d), sa.out_proj.weight, sa.out_proj.bias)
+        x = F.layer_norm(ops.residual_dropout_add(x, a, self.p, self.training), (d,), self.norm1.weight,
+                         self.norm1.bias, self.norm1.eps)
+        xc = x.to(compute_dtype)
+        q = _lin(xc, ca.in_proj_weight[:d], ca.in_proj_bias[:d]).view(B, T, H, D)
+        kv = _lin(memory, ca.in_proj_weight[d:], ca.in_proj_bias[d:]).view(B, memory.shape[1], 2, H, D)
+        c = ops.attention_cross(q, kv, scale=scale, rel_bias=None, key_add=memory_key_add, dropout_p=p_attn)
+        c = _lin(c.reshape(B, T, d), ca.out_proj.weight, ca.out_proj.bias)
+        x = F.layer_norm(ops.residual_dropout_add(x, c, self.p, self.training), (d,), self.norm2.weight,
+                         self.norm2.bias, self.norm2.eps)
+        xc = x.to(compute_dtype)
+        h = F.dropout(F.relu(_lin(xc, self.linear1.weight, self.linear1.bias)), self.p, self.training)
+        h = _lin(h, self.linear2.weight, self.linear2.bias)
+        x = F.layer_norm(ops.residual_dropout_add(x, h, self.p, self.training), (d,), self.norm3.weight,
+                         self.norm3.bias, self.norm3.eps)
+        return x
+
+
+class _DecoderStack(nn.Module):
+    def __init__(self, d_model, n_head, num_layers):
+        super().__init__()
+        self.layers = nn.ModuleList([TransformerDecoderLayer(d_model, n_head) for _ in range(num_layers)])
+        # nn.TransformerDecoder deep-copies ONE initialised layer: all layers start identical
+        for layer in self.layers[1:]:
+            layer.load_state_dict(self.layers[0].state_dict())
+        self.num_layers = num_layers
+
+
+class BaseDecoder(nn.Module):
+    """reference: core/model/modules/transformer_utils.py:38-64.  The float masks are ADDED
+    to the scores exactly like nn.MultiheadAttention does with float masks:
+    tgt_key_padding_mask (1.0 = pad) and memory_key_padding_mask (1.0 = valid) are per-key
+    additive terms, the square-subsequent mask is the kernel's causal flag."""
+
+    def __init__(self, emb_size: int, num_layers: int, n_head: int, batch_first: bool = True):
+        super().__init__()
+        assert batch_first
+        self.decoder = _DecoderStack(emb_size, n_head, num_layers)
+
+    def forward(self, tgt, memory, tgt_mask=None, memory_mask=None, tgt_key_padding_mask=None,
+                memory_key_padding_mask=None, compute_dtype=torch.float32, causal=True):
+        if memory_mask is not None:
+            raise NotImplementedError("memory_mask is never passed by the reference models")
+
+        def as_add(m):
+            if m is None:
+                return None
+            if m.dtype == torch.bool:          # bool masks mask (PhonemeSaL passes bool)
+                return torch.where(m, float("-inf"), 0.0).to(torch.float32)
+            return m.to(torch.float32)         # float masks are additive
+
+        tka, mka = as_add(tgt_key_padding_mask), as_add(memory_key_padding_mask)
+        x = tgt.float()
+        mem = memory.to(compute_dtype)
+        for layer in self.decoder.layers:
+            x = layer(x, mem, tka, mka, compute_dtype, causal=causal)
+        return x

@@ -232,3 +232,131 @@ def embed_target(labels, onset_weight, rhyme_weight, tone_weight, pos_embedding,
     out_dtype = out_dtype or onset_weight.dtype
     p = float(dropout_p) if training else 0.0
     return _EmbedTgt.apply(labels, onset_weight, rhyme_weight, tone_weight, pos_embedding, p, out_dtype)
+
+
+# ----------------------------------------------------------------------------------
+# Normalisation / residual glue (plain torch on the device; fusion candidates)
+# ----------------------------------------------------------------------------------
+def rms_norm(x, weight, eps, out_dtype):
+    """T5LayerNorm (modeling_t5.py:46-70): fp32 variance, no mean subtraction, no bias."""
+    xf = x.float()
+    var = xf.pow(2).mean(-1, keepdim=True)
+    return (weight.float() * (xf * torch.rsqrt(var + eps))).to(out_dtype)
+
+
+def residual_dropout_add(hidden, update, p, training):
+    """hidden (fp32 residual stream) + dropout(update)."""
+    if training and p > 0.0:
+        update = torch.nn.functional.dropout(update, p, True)
+    return hidden + update.to(hidden.dtype)
+
+
+# ----------------------------------------------------------------------------------
+# K2 / K3: attention
+# ----------------------------------------------------------------------------------
+def _rel_to_dense(rel_bias, Sq, Sk):
+    """(H, Sq+Sk-1) -> (H, Sq, Sk): dense[h,i,j] = rel_bias[h, j - i + Sq - 1]"""
+    i = torch.arange(Sq, device=rel_bias.device)[:, None]
+    j = torch.arange(Sk, device=rel_bias.device)[None, :]
+    return rel_bias[:, (j - i + Sq - 1)]
+
+
+def _attention_core(q, k, v, scale, rel_bias, key_add, causal, dropout_p, dense_bias):
+    """q (B,Sq,H,D), k/v (B,Sk,H,D) (strided views are fine) -> (B,Sq,H,D)."""
+    return _attention_torch(q, k, v, scale, rel_bias, key_add, causal, dropout_p, dense_bias)
+
+
+def _attention_torch(q, k, v, scale, rel_bias, key_add, causal, dropout_p, dense_bias):
+    # INTERIM (development only): torch math with the exact score semantics of the kernels.
+    B, Sq, H, D = q.shape
+    Sk = k.shape[1]
+    s = torch.einsum("bihd,bjhd->bhij", q.float(), k.float()) * scale
+    if rel_bias is not None:
+        s = s + _rel_to_dense(rel_bias, Sq, Sk)[None]
+    if dense_bias is not None:
+        s = s + dense_bias
+    if key_add is not None:
+        s = s + key_add[:, None, None, :]
+    if causal:
+        s = s + torch.full((Sq, Sk), float("-inf"), device=s.device).triu(1)
+    p = torch.softmax(s, dim=-1)
+    if dropout_p > 0:
+        p = torch.nn.functional.dropout(p, dropout_p, True)
+    return torch.einsum("bhij,bjhd->bihd", p.to(v.dtype), v)
+
+
+def attention_self(qkv, scale, rel_bias=None, key_add=None, causal=False, dropout_p=0.0, dense_bias=None):
+    """qkv (B,S,3,H,D) packed projection output."""
+    return _attention_core(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], scale, rel_bias, key_add, causal, dropout_p,
+                           dense_bias)
+
+
+def attention_cross(q, kv, scale, rel_bias=None, key_add=None, dropout_p=0.0):
+    """q (B,Sq,H,D); kv (B,Sk,2,H,D) packed."""
+    return _attention_core(q, kv[:, :, 0], kv[:, :, 1], scale, rel_bias, key_add, False, dropout_p, None)
+
+
+# ----------------------------------------------------------------------------------
+# K4: fused phoneme head + 3x cross-entropy (logits never materialised)
+# ----------------------------------------------------------------------------------
+class _PhonemeHeadCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, targets, W_on, b_on, W_rh, b_rh, W_to, b_to, ignore_index):
+        lib = _lib.load()
+        _need_cuda(h, targets, W_on, b_on, W_rh, b_rh, W_to, b_to)
+        if targets.dtype != torch.int64 or targets.shape[-1] != 3 or targets.stride(-1) != 1:
+            raise TypeError("targets must be int64 (N,3) with unit inner stride")
+        h = h.contiguous()
+        N, d = h.shape
+        V_o, on_dim = W_on.shape
+        V_r, rt_dim = W_rh.shape
+        V_t, _ = W_to.shape
+        wdt = h.dtype          # weights are consumed in the activation dtype (fp32 masters cast once: 71k elements)
+        ws = [t.to(wdt).contiguous() for t in (W_on, b_on, W_rh, b_rh, W_to, b_to)]
+        dev = h.device
+        loss_sum = torch.empty(3, dtype=torch.float32, device=dev)
+        count = torch.empty(3, dtype=torch.int32, device=dev)
+        lse = torch.empty((N, 3), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.pvqa_phoneme_head_ce_fwd(_p(h), _p(targets), targets.stride(0), *[_p(w) for w in ws],
+                                               _p(loss_sum), _p(count), _p(lse), None, None, None,
+                                               N, d, on_dim, rt_dim, V_o, V_r, V_t, int(ignore_index),
+                                               _dt(wdt), _dt(h.dtype), _stream()),
+                  "pvqa_phoneme_head_ce_fwd")
+        # mean over non-ignored targets per head, summed (nan if a head has no valid target, like torch)
+        loss = (loss_sum / count.to(torch.float32)).sum()
+        ctx.save_for_backward(h, targets, lse, count, *ws)
+        ctx.meta = (N, d, on_dim, rt_dim, V_o, V_r, V_t, int(ignore_index), (W_on.dtype, b_on.dtype))
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        h, targets, lse, count, W_on, b_on, W_rh, b_rh, W_to, b_to = ctx.saved_tensors
+        N, d, on_dim, rt_dim, V_o, V_r, V_t, ignore_index, (w_dtype, b_dtype) = ctx.meta
+        dev = h.device
+        g = g.to(torch.float32).reshape(1).contiguous()
+        dls = [torch.empty((N, V), dtype=h.dtype, device=dev) for V in (V_o, V_r, V_t)]
+        with torch.cuda.device(dev):
+            check(lib.pvqa_phoneme_head_ce_bwd(_p(h), _p(targets), targets.stride(0), _p(W_on), _p(b_on), _p(W_rh),
+                                               _p(b_rh), _p(W_to), _p(b_to), _p(lse), _p(count), _p(g),
+                                               _p(dls[0]), _p(dls[1]), _p(dls[2]),
+                                               N, d, on_dim, rt_dim, V_o, V_r, V_t, ignore_index,
+                                               _dt(W_on.dtype), _dt(h.dtype), _stream()),
+                  "pvqa_phoneme_head_ce_bwd")
+        # the three small GEMMs (cuBLAS): d_h slices, dW_k, db_k
+        d_h = torch.empty_like(h)
+        offs = (0, on_dim, on_dim + rt_dim)
+        widths = (on_dim, rt_dim, rt_dim)
+        grads = []
+        for dl, W, off, w in zip(dls, (W_on, W_rh, W_to), offs, widths):
+            d_h[:, off:off + w] = dl @ W
+            grads.append((dl.t() @ h[:, off:off + w]).to(w_dtype))
+            grads.append(dl.sum(0, dtype=torch.float32).to(b_dtype))
+        return (d_h, None, *grads, None)
+
+
+def phoneme_head_ce(h, targets, W_onset, b_onset, W_rhyme, b_rhyme, W_tone, b_tone, ignore_index):
+    """K4.  h (N,d) = shared_lm_head output, targets (N,3) int64.  Returns the scalar
+    onset+rhyme+tone cross-entropy of core/executor/PhonemeLaTr_Executor.py:181-190."""
+    return _PhonemeHeadCE.apply(h, targets, W_onset, b_onset, W_rhyme, b_rhyme, W_tone, b_tone, ignore_index)

@@ -23,7 +23,7 @@ def _inputs(B, S_img, L_ocr, L_q, d, V, n_pos=1024, seed=0, hot=False):
         om = torch.ones(B, L_ocr)
         # reference padding: eos box [1000]*6 then pad boxes [0]*6 with token id 0 (PhonemeLaTrDataset.py:24-25,141)
         for b in range(B):
-            n = int(torch.randint(1, L_ocr, (1,), generator=g))
+            n = int(torch.randint(0, L_ocr, (1,), generator=g))
             coords[b, n] = 1000
             ocr[b, n] = 1
             coords[b, n + 1:] = 0

