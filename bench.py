@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py — train samples/s of PhonoLaTr-base on N B200s (BASELINE.json metric), one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = the reference's `_train_epoch` body (core/executor/PhonemeLaTr_Executor.py:161-198)
+on one synthetic batch: forward, 3x cross-entropy, zero_grad, backward, Adam step, LinearLR step.
+Workload: PhonemeLaTr with T5-base dims (d 768, 12 L, 12 H), ViT-B/16-224 frozen, 4-layer target
+decoder, phoneme vocab (84,187,7), per-GPU batch 64, S = 197+100+30 = 327, T = 127, bf16 compute
+with fp32 master weights / residual stream; random-init weights, synthetic data (no network).
+
+  value  : whole-job samples/s, inputs already resident in HBM, CUDA-event timed, max over ranks
+  e2e    : same step driven from pinned HOST batches: H2D of every field + loss.item() per step
+  roofline / kernels : per-kernel CUDA-event durations measured live in a separate profiled pass
+           of the same steps (events around every C-ABI launch), against MEASURED_PEAKS.json
+  cpu_baseline : the oracle port of the reference model on the host cores, bounded sample
+  --impl reference : the reference arm = that same CPU port, K steps (rank 0 only)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOAD = "PhonemeLaTr T5-base, per-GPU batch {B}, S=327 (197 ViT + 100 OCR + 30 question), T=127, phoneme vocab 84/187/7"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return p["hbm_gbs"], p.get("bf16_tflops_sustained", p["bf16_tflops"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------
+# CPU arm: oracle port of the reference model on the host cores
+# --------------------------------------------------------------------------------------
+def cpu_reference_run(batch_size, steps, warmup, threads=None):
+    from oracle import ref_model
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    cfg = ref_model.make_config()                      # T5-base dims, ViT-B/16, 4-layer decoder
+    torch.manual_seed(0)
+    model = ref_model.PhonemeLaTr(cfg, 84, 187, 7)
+    model.train()
+    optim = torch.optim.Adam(model.parameters(), lr=5e-5, betas=(0.9, 0.98), eps=1e-9)
+    sched = torch.optim.lr_scheduler.LinearLR(optim, total_iters=2000)
+    batch = ref_model.synthetic_batch(batch_size, cfg, seed=1234)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        loss = ref_model.phoneme_latr_loss(model, batch, 2)
+        optim.zero_grad()
+        loss.backward()
+        optim.step()
+        sched.step()
+        _ = loss.item()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"value": batch_size * len(times) / total, "unit": "samples/s", "cores": threads, "kind": "port",
+            "sample": f"{len(times)} fwd+loss+bwd+Adam step(s) of the oracle port (HF T5/ViT + nn.TransformerDecoder, "
+                      f"fp32) at batch {batch_size} of the same PhonoLaTr-base workload, after {warmup} warm-up",
+            "ms_per_step": 1e3 * total / len(times)}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = cpu_reference_run(args.cpu_batch, args.steps, min(args.warmup, 1))
+    line = {"impl": "reference", "metric": "train samples/sec (PhonoLaTr-base)", "value": res["value"],
+            "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
+            "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD.format(B=args.cpu_batch) + " (CPU sample batch)"},
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------
+def run_b200_arm(args):
+    import torch.distributed as dist
+    import phoneme_vqa_b200 as pv
+    from phoneme_vqa_b200 import models, ops, parallel, synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    pv.load()
+
+    B = args.batch
+    cfg = synthetic.t5_config("base")
+    torch.manual_seed(0)
+    model = models.PhonemeLaTr(cfg, *synthetic.PHONEME_VOCAB).to(dev)
+    model.set_compute_dtype(torch.bfloat16 if args.dtype == "bf16" else torch.float32)
+    model.train()
+    ops.manual_seed(1234 + rank)
+    reducer = parallel.GradReducer(model, bucket_mb=32.0)
+    reducer.broadcast_parameters(0)
+    optim = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=5e-5, betas=(0.9, 0.98),
+                             eps=1e-9, fused=True)
+    sched = torch.optim.lr_scheduler.LinearLR(optim, total_iters=2000)
+
+    n_distinct = 4
+    host = [synthetic.phoneme_latr_batch(B, cfg.vocab_size, seed=1234 + rank * 1000 + i, pin=True)
+            for i in range(n_distinct)]
+    resident = [{k: v.to(dev) for k, v in b.items()} for b in host]
+    h2d_bytes = synthetic.batch_bytes(host[0])
+
+    def step(b):
+        labels = b["label_ids"]
+        loss = model.forward_loss(b["pixel_values"], b["coordinates"], b["input_ids"], labels[:, :-1],
+                                  b["src_attention_mask"], b["label_attention_mask"][:, :-1],
+                                  b["ocr_attention_mask"], b["tokenized_ocr"], targets=labels[:, 1:],
+                                  ignore_index=synthetic.PAD_ID)
+        optim.zero_grad(set_to_none=True)
+        loss.backward()
+        reducer.finish()
+        optim.step()
+        sched.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps, from_host):
+        barrier()
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        last = None
+        for i in range(n_steps):
+            if from_host:
+                b = {k: v.to(dev, non_blocking=True) for k, v in host[i % n_distinct].items()}
+                last = step(b).item()                  # device -> host read of the step's loss
+            else:
+                last = step(resident[i % n_distinct])
+        e.record()
+        barrier()
+        ms = a.elapsed_time(e)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, last
+
+    for i in range(args.warmup):
+        step(resident[i % n_distinct])
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = pv.launch_count()
+    ms, last = timed(args.steps, from_host=False)
+    launches = pv.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, last_loss = timed(args.steps, from_host=True)
+
+    # profiled pass: CUDA events around every C-ABI launch, same steps
+    ops.KernelTimer.reset(True)
+    timed(min(args.steps, 5), from_host=False)
+    torch.cuda.synchronize()
+    ksum = ops.KernelTimer.summary()
+    ops.KernelTimer.reset(False)
+    n_prof = min(args.steps, 5)
+
+    if rank == 0:
+        hbm, tf, src = _peaks()
+        alg = kernel_algorithmic(B, cfg)
+        kernels = {}
+        for name, (n, total_ms) in ksum.items():
+            avg_ms = total_ms / n
+            entry = {"launches_per_step": n / n_prof, "avg_ms": avg_ms, "share_of_step": total_ms / n_prof / (ms / args.steps)}
+            if name in alg:
+                kind, amount = alg[name]
+                if kind == "hbm":
+                    ach = amount / avg_ms / 1e6
+                    entry.update({"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm})
+                else:
+                    ach = amount / avg_ms / 1e9
+                    entry.update({"bound": "tensor", "achieved": ach, "peak": tf, "unit": "TFLOP/s", "frac": ach / tf})
+            kernels[name] = entry
+        dom = max((k for k in kernels if "bound" in kernels[k]), key=lambda k: kernels[k]["avg_ms"] * kernels[k]["launches_per_step"],
+                  default=None)
+        roofline = None
+        if dom:
+            roofline = {k: kernels[dom][k] for k in ("bound", "achieved", "peak", "unit", "frac")}
+            roofline.update({"kernel": dom, "traffic": None, "peak_source": src,
+                             "avg_launch_ms": kernels[dom]["avg_ms"]})
+        value = world * B * args.steps / (ms / 1e3)
+        line = {
+            "metric": "train samples/sec (PhonoLaTr-base)", "value": value, "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": WORKLOAD.format(B=B), "global_batch": world * B,
+                       "parallelism": f"dp{world}", "weights": "random-init",
+                       "l2": "no flush: per-step working set (0.9 GB weights+Adam state read, >10 GB activations) "
+                             "exceeds the 126 MB L2; 4 distinct batches cycled"},
+            "e2e": {"value": world * B * args.steps / (ms_e2e / 1e3), "unit": "samples/s",
+                    "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "kernels": kernels,
+            "final_loss": float(last_loss),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            res = cpu_reference_run(args.cpu_batch, 1, 1)
+            line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def kernel_algorithmic(B, cfg, S_img=197, L_ocr=100, L_q=30, T=127):
+    """algorithmic bytes / flops per launch of each C-ABI kernel."""
+    d, H, D = cfg.d_model, cfg.num_heads, cfg.d_kv
+    S = S_img + L_ocr + L_q
+    e_tab, e_act = 4, 2
+    return {
+        "embed_mm_fwd": ("hbm", B * ((7 * L_ocr + L_q) * (d * e_tab + 8) + S_img * d * e_act) + B * S * d * e_act),
+        "embed_mm_bwd": ("hbm", B * ((L_ocr + L_q) * d * e_act + (7 * L_ocr + L_q) * 8 + 2 * (7 * L_ocr + L_q) * d * 4)),
+        "embed_tgt_fwd": ("hbm", B * T * (3 * 8 + d * 4 + d * 4 + d * 4)),
+        "embed_tgt_bwd": ("hbm", B * T * (3 * 8 + d * 4 + 2 * d * 4)),
+        "phoneme_head_ce_fwd": ("hbm", B * T * (d * e_act + 3 * 8 + 3 * 4)),
+        "phoneme_head_ce_bwd": ("hbm", B * T * (d * e_act + 3 * 8 + 3 * 4 + 278 * e_act)),
+        "attn_fwd_enc": ("tensor", 4.0 * B * H * S * S * D),
+        "attn_bwd_enc": ("tensor", 10.0 * B * H * S * S * D),
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="per-GPU batch")
+    ap.add_argument("--cpu-batch", type=int, default=4, help="batch of the bounded CPU sample")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py --impl b200 needs a CUDA device; there is no CPU fallback "
+                             "(use --impl reference for the CPU arm)")
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

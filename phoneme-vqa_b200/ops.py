@@ -42,6 +42,40 @@ def _need_cuda(*ts):
             )
 
 
+class KernelTimer:
+    """Optional per-kernel CUDA-event timing (bench.py's live roofline numbers).  Events are
+    recorded on the launching stream immediately around the C-ABI call."""
+    enabled = False
+    records: dict = {}
+
+    @classmethod
+    def reset(cls, enabled=True):
+        cls.enabled = enabled
+        cls.records = {}
+
+    @classmethod
+    def summary(cls):
+        """name -> (launches, total_ms); call after torch.cuda.synchronize()."""
+        return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in cls.records.items()}
+
+
+class _prof:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if KernelTimer.enabled:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if KernelTimer.enabled:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            KernelTimer.records.setdefault(self.name, []).append((self.a, b))
+        return False
+
+
 def _ptr_array(tensors):
     arr = (c_void_p * len(tensors))()
     for i, t in enumerate(tensors):
@@ -108,7 +142,7 @@ class _EmbedMM(torch.autograd.Function):
         out_mask = torch.empty((B, S), dtype=torch.float32, device=dev)
         err = torch.zeros(1, dtype=torch.int32, device=dev)
         tabs = _ptr_array(layout_w) if has_ocr else None
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), _prof("embed_mm_fwd"):
             check(lib.pvqa_embed_mm_fwd(_p(img_feat), _p(coords), _p(ocr_ids), _p(q_ids), _p(ocr_mask), _p(q_mask),
                                         _p(shared_c), tabs, _p(out), _p(out_mask),
                                         B, S_img, L_ocr, L_q, d, V, n_pos,
@@ -133,7 +167,7 @@ class _EmbedMM(torch.autograd.Function):
         d_shared = torch.zeros((V, d), dtype=torch.float32, device=dev)
         d_layout = [torch.zeros((n_pos, d), dtype=torch.float32, device=dev) for _ in range(6)] if L_ocr else []
         tabs = _ptr_array(d_layout) if L_ocr else None
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), _prof("embed_mm_bwd"):
             check(lib.pvqa_embed_mm_bwd(_p(d_out), _p(coords), _p(ocr_ids), _p(q_ids), _p(d_shared), tabs,
                                         B, S_img, L_ocr, L_q, d, V, n_pos, _dt(d_out.dtype), _stream()),
                   "pvqa_embed_mm_bwd")
@@ -192,7 +226,7 @@ class _EmbedTgt(torch.autograd.Function):
         err = torch.zeros(1, dtype=torch.int32, device=dev)
         seed, offset = _Rng.next(B * T * d) if dropout_p > 0 else (0, 0)
         ow, rw, tw = onset_w.contiguous(), rhyme_w.contiguous(), tone_w.contiguous()
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), _prof("embed_tgt_fwd"):
             check(lib.pvqa_embed_tgt_fwd(_p(labels), _p(ow), _p(rw), _p(tw), _p(pe2), _p(out),
                                          B, T, d, on_dim, rt_dim, V_o, V_r, V_t,
                                          _dt(onset_w.dtype), _dt(out_dtype), float(dropout_p), seed, offset,
@@ -213,7 +247,7 @@ class _EmbedTgt(torch.autograd.Function):
         g_on = torch.zeros((V_o, on_dim), dtype=torch.float32, device=dev)
         g_rh = torch.zeros((V_r, rt_dim), dtype=torch.float32, device=dev)
         g_to = torch.zeros((V_t, rt_dim), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), _prof("embed_tgt_bwd"):
             check(lib.pvqa_embed_tgt_bwd(_p(d_out), _p(labels), _p(g_on), _p(g_rh), _p(g_to),
                                          B, T, d, on_dim, rt_dim, V_o, V_r, V_t, _dt(d_out.dtype),
                                          p, seed, offset, _stream()),
@@ -317,7 +351,7 @@ class _PhonemeHeadCE(torch.autograd.Function):
         loss_sum = torch.empty(3, dtype=torch.float32, device=dev)
         count = torch.empty(3, dtype=torch.int32, device=dev)
         lse = torch.empty((N, 3), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), _prof("phoneme_head_ce_fwd"):
             check(lib.pvqa_phoneme_head_ce_fwd(_p(h), _p(targets), targets.stride(0), *[_p(w) for w in ws],
                                                _p(loss_sum), _p(count), _p(lse), None, None, None,
                                                N, d, on_dim, rt_dim, V_o, V_r, V_t, int(ignore_index),
@@ -337,7 +371,7 @@ class _PhonemeHeadCE(torch.autograd.Function):
         dev = h.device
         g = g.to(torch.float32).reshape(1).contiguous()
         dls = [torch.empty((N, V), dtype=h.dtype, device=dev) for V in (V_o, V_r, V_t)]
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev), _prof("phoneme_head_ce_bwd"):
             check(lib.pvqa_phoneme_head_ce_bwd(_p(h), _p(targets), targets.stride(0), _p(W_on), _p(b_on), _p(W_rh),
                                                _p(b_rh), _p(W_to), _p(b_to), _p(lse), _p(count), _p(g),
                                                _p(dls[0]), _p(dls[1]), _p(dls[2]),

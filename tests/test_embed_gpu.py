@@ -222,7 +222,7 @@ def test_embed_tgt_dropout_statistics_and_bwd_mask(d):
     hits = torch.zeros_like(c[0])
     hits.index_put_((labels[:, :, 0].to(DEV).flatten(),), kept[:, :, :on].reshape(-1, on).float() / (1 - p),
                     accumulate=True)
-    torch.testing.assert_close(c[0].grad, hits, rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(c[0].grad, hits, rtol=1e-4, atol=1e-4)
     # a second call draws a different mask
     out2 = ops.embed_target(labels.to(DEV), *c, pe.to(DEV), dropout_p=p, training=True, out_dtype=torch.float32)
     assert not torch.equal(out2 != 0, kept)

@@ -34,9 +34,9 @@ def test_phoneme_head_ce_fp32(N, d):
     c = [t.detach().to(DEV).requires_grad_(True) for t in leaves]
     loss = ops.phoneme_head_ce(c[0], tg.to(DEV), c[1], c[4], c[2], c[5], c[3], c[6], 2)
     loss.backward()
-    torch.testing.assert_close(loss.cpu(), ref.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(loss.cpu(), ref.detach(), rtol=1e-5, atol=1e-6, equal_nan=True)
     for a, b in zip(c, leaves):
-        torch.testing.assert_close(a.grad.cpu(), b.grad, rtol=1e-3, atol=1e-6)
+        torch.testing.assert_close(a.grad.cpu(), b.grad, rtol=1e-3, atol=1e-6, equal_nan=True)
 
 
 def test_phoneme_head_ce_bf16():

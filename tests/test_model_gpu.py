@@ -13,6 +13,9 @@ from oracle import ref_model
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
+# fp32 parity mode: no TF32 anywhere (cudnn convolutions default to TF32, which alone costs ~3e-4)
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 VOCAB = (21, 33, 7)
 
@@ -65,8 +68,12 @@ def test_forward_matches_reference_golden_fp32():
     assert np.array_equal(ys.cpu().numpy(), g["greedy_ids"])
 
 
-@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-3), (torch.bfloat16, 5e-2)])
-def test_loss_and_grads_match_oracle(dtype, tol):
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_loss_and_grads_match_oracle(dtype):
+    """fp32 mode: loss and every gradient within 1e-3 relative of the oracle.
+    bf16 mode: loss within 1e-3; gradients are held to the error the REFERENCE ITSELF shows when
+    run under torch.autocast(bfloat16) (measured here on the oracle, typically ~0.13 on this
+    tiny random-weight model): product error <= 1.25x that + 1e-2, per parameter."""
     cfg = ref_model.tiny_config()
     oracle, model = _pair(cfg)
     model.set_compute_dtype(dtype)
@@ -75,16 +82,25 @@ def test_loss_and_grads_match_oracle(dtype, tol):
     _no_dropout(oracle); _no_dropout(model)
     ref_loss = ref_model.phoneme_latr_loss(oracle, batch, 2)
     ref_loss.backward()
+    ref_grads = {k: p.grad.clone() for k, p in oracle.named_parameters() if p.grad is not None}
     loss = ref_model.phoneme_latr_loss(model, _to(batch, DEV), 2)
     loss.backward()
-    assert abs(loss.item() - ref_loss.item()) <= tol * abs(ref_loss.item())
-    ref_grads = {k: p.grad for k, p in oracle.named_parameters() if p.grad is not None}
+    assert abs(loss.item() - ref_loss.item()) <= 1e-3 * abs(ref_loss.item())
     got = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
     assert set(ref_grads) == set(got)
-    for k, gr in ref_grads.items():
-        a = got[k].float().cpu()
-        err = (a - gr).norm() / (gr.norm() + 1e-12)
-        assert err <= (tol if dtype == torch.float32 else 8e-2), (k, float(err))
+    errs = {k: float((got[k].float().cpu() - gr).norm() / (gr.norm() + 1e-12)) for k, gr in ref_grads.items()}
+    if dtype == torch.float32:
+        worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+        assert worst[0][1] <= 1e-3, worst
+    else:
+        oracle.zero_grad(set_to_none=True)
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            l2 = ref_model.phoneme_latr_loss(oracle, batch, 2)
+        l2.backward()
+        base = {k: float((p.grad.float() - ref_grads[k]).norm() / (ref_grads[k].norm() + 1e-12))
+                for k, p in oracle.named_parameters() if p.grad is not None}
+        bad = {k: (errs[k], base[k]) for k in errs if errs[k] > 1.25 * base[k] + 1e-2}
+        assert not bad, bad
 
 
 def test_fused_loss_path_matches_logits_path():
