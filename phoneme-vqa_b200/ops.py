@@ -295,6 +295,36 @@ def _rel_to_dense(rel_bias, Sq, Sk):
     return rel_bias[:, (j - i + Sq - 1)]
 
 
+def _check_attn_operand(t, name):
+    if t.dtype != torch.bfloat16 or t.dim() != 4 or t.stride(3) != 1:
+        raise TypeError(f"attention {name} must be a bf16 (B,S,H,D) view with unit stride on D")
+
+
+def attention_fwd_raw(q, k, v, scale, rel_bias=None, key_add=None, causal=False):
+    """tcgen05 flash-attention forward through the C-ABI.  Returns (o (B,Sq,H,D) bf16, lse (B,H,Sq) fp32)."""
+    lib = _lib.load()
+    _need_cuda(q, k, v, rel_bias, key_add)
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _check_attn_operand(t, n)
+    B, Sq, H, D = q.shape
+    Sk = k.shape[1]
+    dev = q.device
+    o = torch.empty((B, Sq, H, D), dtype=torch.bfloat16, device=dev)
+    lse = torch.empty((B, H, Sq), dtype=torch.float32, device=dev)
+    if rel_bias is not None:
+        rel_bias = rel_bias.to(torch.float32).contiguous()
+        assert rel_bias.shape == (H, Sq + Sk - 1)
+    if key_add is not None:
+        key_add = key_add.to(torch.float32).contiguous()
+        assert key_add.shape == (B, Sk)
+    with torch.cuda.device(dev), _prof("attn_fwd"):
+        check(lib.pvqa_attn_fwd(_p(q), _p(k), _p(v), _p(o), _p(lse), _p(rel_bias), _p(key_add), B, H, Sq, Sk, D,
+                                q.stride(0), q.stride(1), q.stride(2), k.stride(0), k.stride(1), k.stride(2),
+                                v.stride(0), v.stride(1), v.stride(2), o.stride(0), o.stride(1), o.stride(2),
+                                float(scale), int(bool(causal)), _stream()), "pvqa_attn_fwd")
+    return o, lse
+
+
 def _attention_core(q, k, v, scale, rel_bias, key_add, causal, dropout_p, dense_bias):
     """q (B,Sq,H,D), k/v (B,Sk,H,D) (strided views are fine) -> (B,Sq,H,D)."""
     return _attention_torch(q, k, v, scale, rel_bias, key_add, causal, dropout_p, dense_bias)

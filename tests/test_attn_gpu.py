@@ -1,0 +1,83 @@
+"""K2 / K3 parity: tcgen05 flash attention (through the C-ABI) vs the CPU oracle restatements of
+HF T5Attention's core and nn.MultiheadAttention's core (oracle/ref_ops.py)."""
+import math
+
+import pytest
+import torch
+
+from oracle import ref_ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _qkv(B, Sq, Sk, H, D=64, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    q = (torch.randn(B, Sq, H, D, generator=g) * scale).bfloat16()
+    k = (torch.randn(B, Sk, H, D, generator=g) * scale).bfloat16()
+    v = torch.randn(B, Sk, H, D, generator=g).bfloat16()
+    return q, k, v
+
+
+def _t(x):  # (B,S,H,D) -> (B,H,S,D) float
+    return x.float().transpose(1, 2)
+
+
+def _rel_dense(rel, Sq, Sk):
+    i = torch.arange(Sq)[:, None]
+    j = torch.arange(Sk)[None, :]
+    return rel[:, (j - i + Sq - 1)]
+
+
+T5_CASES = [(1, 128, 128, 1), (2, 327, 327, 3), (1, 100, 100, 2), (2, 464, 464, 2), (1, 707, 707, 1), (3, 1, 5, 2),
+            (1, 129, 257, 1)]
+
+
+@pytest.mark.parametrize("B,Sq,Sk,H", T5_CASES)
+def test_t5_attention_fwd(B, Sq, Sk, H):
+    from phoneme_vqa_b200 import ops
+    q, k, v = _qkv(B, Sq, Sk, H, seed=Sq, scale=0.35)
+    g = torch.Generator().manual_seed(1)
+    rel = torch.randn(H, Sq + Sk - 1, generator=g)
+    valid = torch.rand(B, Sk, generator=g) > 0.2
+    valid[:, 0] = True
+    ref = ref_ops.t5_attention_core(_t(q), _t(k), _t(v), _rel_dense(rel, Sq, Sk)[None], key_valid=valid)
+    key_add = torch.where(valid, 0.0, float("-inf"))
+    o, lse = ops.attention_fwd_raw(q.to(DEV), k.to(DEV), v.to(DEV), 1.0, rel.to(DEV), key_add.to(DEV))
+    got = o.float().cpu().transpose(1, 2)
+    err = (got - ref).abs().max().item()
+    assert err <= 2e-2, err                       # bf16 P and bf16 output
+    assert (got - ref).norm() / ref.norm() <= 1e-2
+    # lse against fp64 scores
+    s = torch.einsum("bhid,bhjd->bhij", _t(q).double(), _t(k).double()) + _rel_dense(rel, Sq, Sk)[None].double()
+    s = s.masked_fill(~valid[:, None, None, :], float("-inf"))
+    torch.testing.assert_close(lse.cpu().double(), torch.logsumexp(s, -1), rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("B,T,S,H", [(2, 127, 327, 3), (1, 40, 64, 2), (2, 9, 17, 1)])
+def test_mha_cross_attention_fwd_float_masks(B, T, S, H):
+    from phoneme_vqa_b200 import ops
+    q, k, v = _qkv(B, T, S, H, seed=T)
+    g = torch.Generator().manual_seed(2)
+    key_add = (torch.rand(B, S, generator=g) > 0.3).float()       # reference passes 1.0 = valid, ADDED (D14)
+    ref = ref_ops.mha_attention_core(_t(q), _t(k), _t(v), causal=False, key_add=key_add)
+    o, _ = ops.attention_fwd_raw(q.to(DEV), k.to(DEV), v.to(DEV), 1.0 / math.sqrt(64), None, key_add.to(DEV))
+    got = o.float().cpu().transpose(1, 2)
+    assert (got - ref).abs().max().item() <= 2e-2
+    assert (got - ref).norm() / ref.norm() <= 1e-2
+
+
+@pytest.mark.parametrize("B,T,H", [(2, 127, 3), (1, 128, 1), (1, 300, 2), (2, 1, 1)])
+def test_mha_causal_self_attention_fwd_packed_qkv(B, T, H):
+    from phoneme_vqa_b200 import ops
+    g = torch.Generator().manual_seed(T)
+    qkv = torch.randn(B, T, 3, H, 64, generator=g).bfloat16()
+    key_add = (torch.rand(B, T, generator=g) > 0.7).float()       # 1.0 = pad, ADDED
+    q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    ref = ref_ops.mha_attention_core(_t(q), _t(k), _t(v), causal=True, key_add=key_add)
+    qkv_d = qkv.to(DEV)
+    o, _ = ops.attention_fwd_raw(qkv_d[:, :, 0], qkv_d[:, :, 1], qkv_d[:, :, 2], 1.0 / math.sqrt(64), None,
+                                 key_add.to(DEV), causal=True)
+    got = o.float().cpu().transpose(1, 2)
+    assert (got - ref).abs().max().item() <= 2e-2
+    assert (got - ref).norm() / ref.norm() <= 1e-2
