@@ -182,17 +182,20 @@ int pvqa_attn_fwd(const void* q, const void* k, const void* v, void* o, float* l
                   int64_t o_stride_b, int64_t o_stride_s, int64_t o_stride_h,
                   float scale, int causal, void* stream);
 
-/* backward: dq,dk,dv (same layout/strides as q,k,v), d_rel_bias (H, Sq+Sk-1) fp32
- * accumulated (caller zero-initialises) = sum over b,i,j with j-i fixed of dS. */
+/* backward.  dk, dv: bf16 with explicit strides (may point into a packed d(qkv) buffer).
+ * dq_accum: fp32 (B,Sq,H,64) contiguous, ZERO-INITIALISED by the caller — every 128-key tile
+ * adds its partial dQ with fp32 reductions; the caller converts/copies it to bf16.
+ * d_rel_bias (H, Sq+Sk-1) fp32, accumulated (caller zero-initialises) = sum_{b,i,j: j-i fixed} dS, or NULL.
+ * o, d_o: forward output and its gradient (bf16, strided). */
 int pvqa_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
                   const float* lse, const float* rel_bias, const float* key_add,
-                  void* dq, void* dk, void* dv, float* d_rel_bias,
+                  float* dq_accum, void* dk, void* dv, float* d_rel_bias,
                   int64_t B, int64_t H, int64_t Sq, int64_t Sk, int64_t D,
                   int64_t q_stride_b, int64_t q_stride_s, int64_t q_stride_h,
                   int64_t k_stride_b, int64_t k_stride_s, int64_t k_stride_h,
                   int64_t v_stride_b, int64_t v_stride_s, int64_t v_stride_h,
                   int64_t o_stride_b, int64_t o_stride_s, int64_t o_stride_h,
-                  int64_t dq_stride_b, int64_t dq_stride_s, int64_t dq_stride_h,
+                  int64_t do_stride_b, int64_t do_stride_s, int64_t do_stride_h,
                   int64_t dk_stride_b, int64_t dk_stride_s, int64_t dk_stride_h,
                   int64_t dv_stride_b, int64_t dv_stride_s, int64_t dv_stride_h,
                   float scale, int causal, void* stream);

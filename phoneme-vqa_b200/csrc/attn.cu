@@ -242,6 +242,293 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------------
+// backward.  One CTA = one (batch, head, 128-key tile); loop over 128-query tiles.
+//   S  = Q K^T, dP = dO V^T                       (tcgen05, TMEM [0,128) and [128,256))
+//   P  = exp2(s - lse), dS = P * (dP - delta)      (256 threads: row = TMEM lane, half of the columns each)
+//   dV += P^T dO, dK += dS^T Q  (A operands read MN-major from the same [query][key] smem tiles)
+//   dQ_m = dS K -> TMEM (aliasing S) -> fp32 RED into the dq accumulator (other key tiles add to it)
+//   d_rel[j-i] += dS : diagonal sums of the bf16 dS tile in smem, one diagonal per thread, overlapped with the MMAs
+// ---------------------------------------------------------------------------------
+constexpr int kBwdThreads2 = 256;
+constexpr uint32_t kBwdTmemCols = 512;   // S/dQ [0,128) | dP [128,256) | dV [256,320) | dK [320,384)
+constexpr int kBOffK = 0;
+constexpr int kBOffV = kBOffK + kBN * kD * 2;
+constexpr int kBOffQ = kBOffV + kBN * kD * 2;
+constexpr int kBOffdO = kBOffQ + kBM * kD * 2;
+constexpr int kBOffP = kBOffdO + kBM * kD * 2;            // 64 KB
+constexpr int kBOffdS = kBOffP + kBM * kBN * 2;           // 96 KB
+constexpr int kBOffBar = kBOffdS + kBM * kBN * 2;         // 128 KB
+constexpr int kBOffFloats = kBOffBar + 64;
+
+struct AttnBwdParams {
+  const __nv_bfloat16* o;
+  const __nv_bfloat16* d_o;
+  const float* lse;
+  const float* rel_bias;
+  const float* key_add;
+  float* dq_accum;            // (B,Sq,H,64) fp32, zero-initialised
+  __nv_bfloat16* dk;
+  __nv_bfloat16* dv;
+  float* d_rel;               // (H, Sq+Sk-1) fp32 accumulated, or null
+  int B, H, Sq, Sk;
+  long long o_stride_b, o_stride_s, o_stride_h;
+  long long do_stride_b, do_stride_s, do_stride_h;
+  long long dk_stride_b, dk_stride_s, dk_stride_h;
+  long long dv_stride_b, dv_stride_s, dv_stride_h;
+  float scale;
+  int causal;
+};
+
+__global__ void __launch_bounds__(kBwdThreads2, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
+                const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bar_kv = reinterpret_cast<uint64_t*>(smem + kBOffBar);
+  uint64_t* bar_ld = bar_kv + 1;
+  uint64_t* bar_s = bar_kv + 2;
+  uint64_t* bar_dq = bar_kv + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 4);
+  const int n_rel = p.rel_bias ? (p.Sq + p.Sk - 1) : 0;
+  const int n_win = p.rel_bias ? (p.Sq + kBN - 1) : 0;      // rel offsets this key tile can see
+  float* s_rel = reinterpret_cast<float*>(smem + kBOffFloats);   // [n_win] bias * log2e
+  float* s_drel = s_rel + n_win;                                 // [n_win] gradient accumulator
+  float* s_kadd = s_drel + n_win;                                // [kBN]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rowl = (warp & 3) * 32 + lane;     // row inside the 128-row tile == TMEM lane
+  const int half = warp >> 2;                  // which half of the columns this thread owns
+  const int j0 = blockIdx.x * kBN;
+  const int h = blockIdx.y, b = blockIdx.z;
+
+  if (tid == 0) {
+    tc05::prefetch_tmap(&tmQ); tc05::prefetch_tmap(&tmK); tc05::prefetch_tmap(&tmV); tc05::prefetch_tmap(&tmdO);
+    tc05::mbar_init(bar_kv, 1); tc05::mbar_init(bar_ld, 1); tc05::mbar_init(bar_s, 1); tc05::mbar_init(bar_dq, 1);
+    tc05::fence_barrier_init();
+  }
+  if (warp == 0) {
+    tc05::tmem_alloc(tmem_slot, kBwdTmemCols);
+    tc05::tmem_relinquish();
+  }
+  // window of relative offsets: global rel index r = j - i + Sq - 1 = j0 + w, w in [0, n_win)
+  for (int w = tid; w < n_win; w += kBwdThreads2) {
+    const int r = j0 + w;
+    s_rel[w] = (r < n_rel) ? p.rel_bias[(long long)h * n_rel + r] * kLog2e : 0.f;
+    s_drel[w] = 0.f;
+  }
+  if (tid < kBN) {
+    const int j = j0 + tid;
+    s_kadd[tid] = (p.key_add && j < p.Sk) ? p.key_add[(long long)b * p.Sk + j] * kLog2e : 0.f;
+  }
+  tc05::tc_fence_before_sync();
+  __syncthreads();
+  tc05::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+
+  if (tid == 0) {
+    tc05::mbar_expect_tx(bar_kv, 2 * kBN * kD * 2);
+    tc05::tma_load_4d(smem + kBOffK, &tmK, bar_kv, 0, h, j0, b);
+    tc05::tma_load_4d(smem + kBOffV, &tmV, bar_kv, 0, h, j0, b);
+  }
+
+  const float sl2 = p.scale * kLog2e;
+  const uint32_t idesc_s = tc05::idesc_bf16(kBM, kBN, 0, 0);
+  const uint32_t idesc_dkv = tc05::idesc_bf16(kBN, kD, 1, 1);   // A = P^T / dS^T (MN-major), B = dO / Q (MN-major)
+  const uint32_t idesc_dq = tc05::idesc_bf16(kBM, kD, 0, 1);    // A = dS (K-major), B = K (MN-major)
+  const uint32_t k_addr = tc05::smem_u32(smem + kBOffK), v_addr = tc05::smem_u32(smem + kBOffV);
+  const uint32_t q_addr = tc05::smem_u32(smem + kBOffQ), do_addr = tc05::smem_u32(smem + kBOffdO);
+  const uint32_t p_addr = tc05::smem_u32(smem + kBOffP), ds_addr = tc05::smem_u32(smem + kBOffdS);
+
+  const int m_tiles = (p.Sq + kBM - 1) / kBM;
+  const int m_first = p.causal ? (j0 / kBM) : 0;      // query tiles entirely above the diagonal see nothing
+  int it = 0;
+  for (int mt = m_first; mt < m_tiles; ++mt, ++it) {
+    const int i0 = mt * kBM;
+    const uint32_t ph = it & 1;
+    if (tid == 0) {
+      tc05::mbar_expect_tx(bar_ld, 2 * kBM * kD * 2);
+      tc05::tma_load_4d(smem + kBOffQ, &tmQ, bar_ld, 0, h, i0, b);
+      tc05::tma_load_4d(smem + kBOffdO, &tmdO, bar_ld, 0, h, i0, b);
+      if (it == 0) tc05::mbar_wait(bar_kv, 0);
+      tc05::mbar_wait(bar_ld, ph);
+      tc05::tc_fence_after_sync();
+#pragma unroll
+      for (int ks = 0; ks < kD / 16; ++ks) {      // S = Q K^T
+        tc05::mma_bf16_ss(tmem_base, tc05::smem_desc_sw128(q_addr + ks * 32, 16, 1024),
+                          tc05::smem_desc_sw128(k_addr + ks * 32, 16, 1024), idesc_s, ks > 0);
+      }
+#pragma unroll
+      for (int ks = 0; ks < kD / 16; ++ks) {      // dP = dO V^T
+        tc05::mma_bf16_ss(tmem_base + kBN, tc05::smem_desc_sw128(do_addr + ks * 32, 16, 1024),
+                          tc05::smem_desc_sw128(v_addr + ks * 32, 16, 1024), idesc_s, ks > 0);
+      }
+      tc05::mma_commit(bar_s);
+    }
+    // ---- per-row statistics (overlaps the MMAs): lse and delta = rowsum(dO * O) ----
+    const int i = i0 + rowl;
+    float lse2 = 0.f, delta = 0.f;
+    const bool row_ok = i < p.Sq;
+    if (row_ok) {
+      lse2 = p.lse[((long long)b * p.H + h) * p.Sq + i] * kLog2e;
+      const __nv_bfloat16* orow = p.o + (long long)b * p.o_stride_b + (long long)i * p.o_stride_s + (long long)h * p.o_stride_h;
+      const __nv_bfloat16* grow = p.d_o + (long long)b * p.do_stride_b + (long long)i * p.do_stride_s + (long long)h * p.do_stride_h;
+#pragma unroll
+      for (int c = 0; c < kD / 8; ++c) {
+        f8 a = Vec8<__nv_bfloat16>::load(orow + c * 8);
+        f8 g = Vec8<__nv_bfloat16>::load(grow + c * 8);
+#pragma unroll
+        for (int x = 0; x < 8; ++x) delta = fmaf(a.v[x], g.v[x], delta);
+      }
+    }
+    const bool row_live = row_ok && (lse2 != -INFINITY);
+    tc05::mbar_wait(bar_s, ph);
+    tc05::tc_fence_after_sync();
+
+    // ---- P and dS for this thread's 64 columns (sub-tile `half`) ----
+    const int wbase = p.Sq - 1 - i;                  // window index = jl + wbase  (jl = j - j0)
+    uint8_t* prow = smem + kBOffP + half * (kBM * 128) + rowl * 128;
+    uint8_t* dsrow = smem + kBOffdS + half * (kBM * 128) + rowl * 128;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t rs[32], rp[32];
+      tc05::tmem_ld_32x32(tmem_row + half * 64 + c * 32, rs);
+      tc05::tmem_ld_32x32(tmem_row + kBN + half * 64 + c * 32, rp);
+      tc05::tmem_ld_wait();
+      float pv[32], dsv[32];
+#pragma unroll
+      for (int x = 0; x < 32; ++x) {
+        const int jl = half * 64 + c * 32 + x;
+        const int j = j0 + jl;
+        float s = __uint_as_float(rs[x]) * sl2 + s_kadd[jl];
+        if (n_win) s += s_rel[min(max(jl + wbase, 0), n_win - 1)];
+        const bool dead = !row_live || j >= p.Sk || (p.causal && j > i);
+        const float pr = dead ? 0.f : fast_exp2(s - lse2);
+        pv[x] = pr;
+        dsv[x] = pr * (__uint_as_float(rp[x]) - delta) * p.scale;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 u, w;
+        u.x = f32x2_to_bf16x2(pv[q * 8 + 0], pv[q * 8 + 1]);  u.y = f32x2_to_bf16x2(pv[q * 8 + 2], pv[q * 8 + 3]);
+        u.z = f32x2_to_bf16x2(pv[q * 8 + 4], pv[q * 8 + 5]);  u.w = f32x2_to_bf16x2(pv[q * 8 + 6], pv[q * 8 + 7]);
+        w.x = f32x2_to_bf16x2(dsv[q * 8 + 0], dsv[q * 8 + 1]); w.y = f32x2_to_bf16x2(dsv[q * 8 + 2], dsv[q * 8 + 3]);
+        w.z = f32x2_to_bf16x2(dsv[q * 8 + 4], dsv[q * 8 + 5]); w.w = f32x2_to_bf16x2(dsv[q * 8 + 6], dsv[q * 8 + 7]);
+        const int chunk = (c * 4 + q) ^ (rowl & 7);
+        *reinterpret_cast<uint4*>(prow + chunk * 16) = u;
+        *reinterpret_cast<uint4*>(dsrow + chunk * 16) = w;
+      }
+    }
+    tc05::fence_proxy_async_smem();
+    tc05::tc_fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      tc05::tc_fence_after_sync();
+#pragma unroll
+      for (int ks = 0; ks < kBM / 16; ++ks) {     // dV += P^T dO ; dK += dS^T Q   (K = 128 query rows, 16 per step)
+        const uint64_t ap = tc05::smem_desc_sw128(p_addr + ks * 2048, kBM * 128, 1024);
+        const uint64_t bdo = tc05::smem_desc_sw128(do_addr + ks * 2048, 16, 1024);
+        tc05::mma_bf16_ss(tmem_base + 256, ap, bdo, idesc_dkv, (it > 0) || (ks > 0));
+      }
+#pragma unroll
+      for (int ks = 0; ks < kBM / 16; ++ks) {
+        const uint64_t ads = tc05::smem_desc_sw128(ds_addr + ks * 2048, kBM * 128, 1024);
+        const uint64_t bq = tc05::smem_desc_sw128(q_addr + ks * 2048, 16, 1024);
+        tc05::mma_bf16_ss(tmem_base + 320, ads, bq, idesc_dkv, (it > 0) || (ks > 0));
+      }
+#pragma unroll
+      for (int ks = 0; ks < kBN / 16; ++ks) {     // dQ_m = dS K    (K = 128 keys)
+        const uint64_t ads = tc05::smem_desc_sw128(ds_addr + (ks >> 2) * (kBM * 128) + (ks & 3) * 32, 16, 1024);
+        const uint64_t bk = tc05::smem_desc_sw128(k_addr + ks * 2048, 16, 1024);
+        tc05::mma_bf16_ss(tmem_base, ads, bk, idesc_dq, ks > 0);
+      }
+      tc05::mma_commit(bar_dq);
+    }
+    // ---- d_rel: one diagonal of the dS tile per thread (generic-proxy reads, overlapping the MMAs) ----
+    if (p.d_rel && tid < 2 * kBM - 1) {
+      const int delta_ij = tid - (kBM - 1);          // jl - il
+      float acc = 0.f;
+      const int il_lo = max(0, -delta_ij), il_hi = min(kBM - 1, kBN - 1 - delta_ij);
+      for (int il = il_lo; il <= il_hi; ++il) {
+        const int jl = il + delta_ij;
+        const uint8_t* e = smem + kBOffdS + (jl >> 6) * (kBM * 128) + il * 128 +
+                           ((((jl & 63) >> 3) ^ (il & 7)) << 4) + (jl & 7) * 2;
+        acc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(e));
+      }
+      const int w = delta_ij - i0 + p.Sq - 1;        // window index of rel = (j0+jl) - (i0+il) + Sq-1, minus j0
+      if (w >= 0 && w < n_win) s_drel[w] += acc;     // each w is owned by exactly one thread per step
+    }
+    tc05::mbar_wait(bar_dq, ph);
+    tc05::tc_fence_after_sync();
+    {
+      uint32_t r[32];
+      tc05::tmem_ld_32x32(tmem_row + half * 32, r);
+      tc05::tmem_ld_wait();
+      if (row_ok) {
+        float* dst = p.dq_accum + (((long long)b * p.Sq + i) * p.H + h) * kD + half * 32;
+#pragma unroll
+        for (int x = 0; x < 32; x += 4)
+          red_add_v4(dst + x, __uint_as_float(r[x]), __uint_as_float(r[x + 1]), __uint_as_float(r[x + 2]),
+                     __uint_as_float(r[x + 3]));
+      }
+    }
+    tc05::tc_fence_before_sync();
+    __syncthreads();
+    tc05::tc_fence_after_sync();
+  }
+
+  // ---- epilogue: dV, dK rows (key j0 + rowl), columns [32*half, +32) ----
+  if (it > 0) {
+    const int j = j0 + rowl;
+    uint32_t rv[32], rk[32];
+    tc05::tmem_ld_32x32(tmem_row + 256 + half * 32, rv);
+    tc05::tmem_ld_32x32(tmem_row + 320 + half * 32, rk);
+    tc05::tmem_ld_wait();
+    if (j < p.Sk) {
+      __nv_bfloat16* dvrow = p.dv + (long long)b * p.dv_stride_b + (long long)j * p.dv_stride_s + (long long)h * p.dv_stride_h + half * 32;
+      __nv_bfloat16* dkrow = p.dk + (long long)b * p.dk_stride_b + (long long)j * p.dk_stride_s + (long long)h * p.dk_stride_h + half * 32;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4 u, w;
+        u.x = f32x2_to_bf16x2(__uint_as_float(rv[c * 8 + 0]), __uint_as_float(rv[c * 8 + 1]));
+        u.y = f32x2_to_bf16x2(__uint_as_float(rv[c * 8 + 2]), __uint_as_float(rv[c * 8 + 3]));
+        u.z = f32x2_to_bf16x2(__uint_as_float(rv[c * 8 + 4]), __uint_as_float(rv[c * 8 + 5]));
+        u.w = f32x2_to_bf16x2(__uint_as_float(rv[c * 8 + 6]), __uint_as_float(rv[c * 8 + 7]));
+        w.x = f32x2_to_bf16x2(__uint_as_float(rk[c * 8 + 0]), __uint_as_float(rk[c * 8 + 1]));
+        w.y = f32x2_to_bf16x2(__uint_as_float(rk[c * 8 + 2]), __uint_as_float(rk[c * 8 + 3]));
+        w.z = f32x2_to_bf16x2(__uint_as_float(rk[c * 8 + 4]), __uint_as_float(rk[c * 8 + 5]));
+        w.w = f32x2_to_bf16x2(__uint_as_float(rk[c * 8 + 6]), __uint_as_float(rk[c * 8 + 7]));
+        *reinterpret_cast<uint4*>(dvrow + c * 8) = u;
+        *reinterpret_cast<uint4*>(dkrow + c * 8) = w;
+      }
+    }
+  } else {
+    // causal tile with no visible query rows cannot happen (the diagonal tile always exists); keep outputs defined
+    const int j = j0 + rowl;
+    if (j < p.Sk) {
+      __nv_bfloat16* dvrow = p.dv + (long long)b * p.dv_stride_b + (long long)j * p.dv_stride_s + (long long)h * p.dv_stride_h + half * 32;
+      __nv_bfloat16* dkrow = p.dk + (long long)b * p.dk_stride_b + (long long)j * p.dk_stride_s + (long long)h * p.dk_stride_h + half * 32;
+      for (int c = 0; c < 4; ++c) {
+        *reinterpret_cast<uint4*>(dvrow + c * 8) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(dkrow + c * 8) = make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+  if (p.d_rel) {
+    const float inv_scale = 1.0f / p.scale;          // the smem tile holds scale * dS
+    for (int w = tid; w < n_win; w += kBwdThreads2) {
+      const int r = j0 + w;
+      const float g = s_drel[w];
+      if (r < n_rel && g != 0.f) atomicAdd(p.d_rel + (long long)h * n_rel + r, g * inv_scale);
+    }
+  }
+  tc05::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc05::tmem_dealloc(tmem_base, kBwdTmemCols);
+}
+
+// ---------------------------------------------------------------------------------
 // host side: TMA descriptors
 // ---------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -321,5 +608,60 @@ extern "C" int pvqa_attn_fwd(const void* q, const void* k, const void* v, void* 
   attn_fwd_kernel<<<grid, kAttnThreads, smem_bytes, (cudaStream_t)stream>>>(tq, tk, tv, p);
   count_launch();
   PVQA_CHECK_LAUNCH("attn_fwd");
+  return PVQA_OK;
+}
+
+
+extern "C" int pvqa_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
+                             const float* lse, const float* rel_bias, const float* key_add, float* dq_accum,
+                             void* dk, void* dv, float* d_rel_bias, int64_t B, int64_t H, int64_t Sq, int64_t Sk,
+                             int64_t D, int64_t q_stride_b, int64_t q_stride_s, int64_t q_stride_h,
+                             int64_t k_stride_b, int64_t k_stride_s, int64_t k_stride_h, int64_t v_stride_b,
+                             int64_t v_stride_s, int64_t v_stride_h, int64_t o_stride_b, int64_t o_stride_s,
+                             int64_t o_stride_h, int64_t do_stride_b, int64_t do_stride_s, int64_t do_stride_h,
+                             int64_t dk_stride_b, int64_t dk_stride_s, int64_t dk_stride_h, int64_t dv_stride_b,
+                             int64_t dv_stride_s, int64_t dv_stride_h, float scale, int causal, void* stream) {
+  PVQA_REQUIRE(D == kD, PVQA_ERR_SHAPE, "attn_bwd: head dim %lld unsupported (kernel is specialised for 64)", (long long)D);
+  PVQA_REQUIRE(B >= 0 && H > 0 && Sq >= 0 && Sk >= 0, PVQA_ERR_SHAPE, "attn_bwd: bad dimension");
+  if (B == 0 || Sq == 0 || Sk == 0) return PVQA_OK;
+  PVQA_REQUIRE(q && k && v && o && d_o && lse && dq_accum && dk && dv, PVQA_ERR_NULL, "attn_bwd: NULL pointer");
+  PVQA_REQUIRE(!causal || Sq == Sk, PVQA_ERR_SHAPE, "attn_bwd: causal requires Sq == Sk");
+  PVQA_REQUIRE(scale != 0.f, PVQA_ERR_SHAPE, "attn_bwd: scale must be non-zero");
+  PVQA_REQUIRE(!d_rel_bias || rel_bias, PVQA_ERR_NULL, "attn_bwd: d_rel_bias requested without rel_bias");
+  PVQA_REQUIRE(H <= 65535 && B <= 65535, PVQA_ERR_SHAPE, "attn_bwd: H and B must be <= 65535");
+  auto al8 = [](int64_t a, int64_t b2, int64_t c) { return a % 8 == 0 && b2 % 8 == 0 && c % 8 == 0; };
+  PVQA_REQUIRE(aligned16(o) && aligned16(d_o) && aligned16(dk) && aligned16(dv) && aligned16(dq_accum) &&
+                   al8(o_stride_b, o_stride_s, o_stride_h) && al8(do_stride_b, do_stride_s, do_stride_h) &&
+                   al8(dk_stride_b, dk_stride_s, dk_stride_h) && al8(dv_stride_b, dv_stride_s, dv_stride_h),
+               PVQA_ERR_ALIGN, "attn_bwd: rows must be 16-byte aligned");
+  const int64_t n_floats = (rel_bias ? 2 * (Sq + kBN - 1) : 0) + kBN;
+  const size_t smem_bytes = 1024 + kBOffFloats + (size_t)n_floats * 4;
+  PVQA_REQUIRE(smem_bytes <= 220 * 1024, PVQA_ERR_SHAPE, "attn_bwd: Sq too large for the bias window buffers");
+  CUtensorMap tq, tk, tv, tdo;
+  int rc;
+  if ((rc = make_tmap(&tq, q, B, Sq, H, q_stride_b, q_stride_s, q_stride_h, kBM, "q"))) return rc;
+  if ((rc = make_tmap(&tk, k, B, Sk, H, k_stride_b, k_stride_s, k_stride_h, kBN, "k"))) return rc;
+  if ((rc = make_tmap(&tv, v, B, Sk, H, v_stride_b, v_stride_s, v_stride_h, kBN, "v"))) return rc;
+  if ((rc = make_tmap(&tdo, d_o, B, Sq, H, do_stride_b, do_stride_s, do_stride_h, kBM, "d_o"))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return fail(PVQA_ERR_CUDA, "attn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  AttnBwdParams p{};
+  p.o = reinterpret_cast<const __nv_bfloat16*>(o); p.d_o = reinterpret_cast<const __nv_bfloat16*>(d_o);
+  p.lse = lse; p.rel_bias = rel_bias; p.key_add = key_add; p.dq_accum = dq_accum;
+  p.dk = reinterpret_cast<__nv_bfloat16*>(dk); p.dv = reinterpret_cast<__nv_bfloat16*>(dv); p.d_rel = d_rel_bias;
+  p.B = (int)B; p.H = (int)H; p.Sq = (int)Sq; p.Sk = (int)Sk;
+  p.o_stride_b = o_stride_b; p.o_stride_s = o_stride_s; p.o_stride_h = o_stride_h;
+  p.do_stride_b = do_stride_b; p.do_stride_s = do_stride_s; p.do_stride_h = do_stride_h;
+  p.dk_stride_b = dk_stride_b; p.dk_stride_s = dk_stride_s; p.dk_stride_h = dk_stride_h;
+  p.dv_stride_b = dv_stride_b; p.dv_stride_s = dv_stride_s; p.dv_stride_h = dv_stride_h;
+  p.scale = scale; p.causal = causal;
+  dim3 grid((unsigned)((Sk + kBN - 1) / kBN), (unsigned)H, (unsigned)B);
+  attn_bwd_kernel<<<grid, kBwdThreads2, smem_bytes, (cudaStream_t)stream>>>(tq, tk, tv, tdo, p);
+  count_launch();
+  PVQA_CHECK_LAUNCH("attn_bwd");
   return PVQA_OK;
 }

@@ -325,38 +325,98 @@ def attention_fwd_raw(q, k, v, scale, rel_bias=None, key_add=None, causal=False)
     return o, lse
 
 
+def attention_bwd_raw(q, k, v, o, d_o, lse, scale, rel_bias, key_add, causal, dk, dv, want_d_rel):
+    """tcgen05 flash-attention backward through the C-ABI.  dk/dv are caller-provided bf16 (B,Sk,H,D)
+    views (possibly into a packed buffer).  Returns (dq_accum fp32 (B,Sq,H,D), d_rel or None)."""
+    lib = _lib.load()
+    B, Sq, H, D = q.shape
+    Sk = k.shape[1]
+    dev = q.device
+    dq_accum = torch.zeros((B, Sq, H, D), dtype=torch.float32, device=dev)
+    d_rel = torch.zeros((H, Sq + Sk - 1), dtype=torch.float32, device=dev) if want_d_rel else None
+    if d_o.stride(3) != 1:
+        d_o = d_o.contiguous()
+    with torch.cuda.device(dev), _prof("attn_bwd"):
+        check(lib.pvqa_attn_bwd(_p(q), _p(k), _p(v), _p(o), _p(d_o), _p(lse), _p(rel_bias), _p(key_add),
+                                _p(dq_accum), _p(dk), _p(dv), _p(d_rel), B, H, Sq, Sk, D,
+                                q.stride(0), q.stride(1), q.stride(2), k.stride(0), k.stride(1), k.stride(2),
+                                v.stride(0), v.stride(1), v.stride(2), o.stride(0), o.stride(1), o.stride(2),
+                                d_o.stride(0), d_o.stride(1), d_o.stride(2), dk.stride(0), dk.stride(1), dk.stride(2),
+                                dv.stride(0), dv.stride(1), dv.stride(2), float(scale), int(bool(causal)), _stream()),
+              "pvqa_attn_bwd")
+    return dq_accum, d_rel
+
+
+def _prep_bias(rel_bias, key_add):
+    rb = None if rel_bias is None else rel_bias.detach().to(torch.float32).contiguous()
+    ka = None if key_add is None else key_add.detach().to(torch.float32).contiguous()
+    return rb, ka
+
+
+class _AttnSelf(torch.autograd.Function):
+    """packed (B,S,3,H,D) bf16 projection -> (B,S,H,D); d(qkv) comes back packed for the QKV GEMM backward."""
+
+    @staticmethod
+    def forward(ctx, qkv, rel_bias, key_add, scale, causal):
+        rb, ka = _prep_bias(rel_bias, key_add)
+        qkv = qkv.contiguous()
+        o, lse = attention_fwd_raw(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], scale, rb, ka, causal)
+        ctx.save_for_backward(qkv, o, lse, rb, ka)
+        ctx.meta = (float(scale), bool(causal), rel_bias is not None and ctx.needs_input_grad[1],
+                    None if rel_bias is None else rel_bias.dtype)
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        qkv, o, lse, rb, ka = ctx.saved_tensors
+        scale, causal, want_rel, rel_dtype = ctx.meta
+        dqkv = torch.empty_like(qkv)
+        dq_acc, d_rel = attention_bwd_raw(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], o, d_o.to(torch.bfloat16), lse,
+                                          scale, rb, ka, causal, dqkv[:, :, 1], dqkv[:, :, 2], want_rel)
+        dqkv[:, :, 0].copy_(dq_acc)
+        return dqkv, (d_rel.to(rel_dtype) if want_rel else None), None, None, None
+
+
+class _AttnCross(torch.autograd.Function):
+    """q (B,Sq,H,D) + packed kv (B,Sk,2,H,D), bf16."""
+
+    @staticmethod
+    def forward(ctx, q, kv, rel_bias, key_add, scale):
+        rb, ka = _prep_bias(rel_bias, key_add)
+        q, kv = q.contiguous(), kv.contiguous()
+        o, lse = attention_fwd_raw(q, kv[:, :, 0], kv[:, :, 1], scale, rb, ka, False)
+        ctx.save_for_backward(q, kv, o, lse, rb, ka)
+        ctx.meta = (float(scale), rel_bias is not None and ctx.needs_input_grad[2],
+                    None if rel_bias is None else rel_bias.dtype)
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        q, kv, o, lse, rb, ka = ctx.saved_tensors
+        scale, want_rel, rel_dtype = ctx.meta
+        dkv = torch.empty_like(kv)
+        dq_acc, d_rel = attention_bwd_raw(q, kv[:, :, 0], kv[:, :, 1], o, d_o.to(torch.bfloat16), lse, scale, rb, ka,
+                                          False, dkv[:, :, 0], dkv[:, :, 1], want_rel)
+        return dq_acc.to(torch.bfloat16), dkv, (d_rel.to(rel_dtype) if want_rel else None), None, None
+
+
 def _attention_core(q, k, v, scale, rel_bias, key_add, causal, dropout_p, dense_bias):
     """q (B,Sq,H,D), k/v (B,Sk,H,D) (strided views are fine) -> (B,Sq,H,D)."""
     return _attention_torch(q, k, v, scale, rel_bias, key_add, causal, dropout_p, dense_bias)
 
 
-def _attention_torch(q, k, v, scale, rel_bias, key_add, causal, dropout_p, dense_bias):
-    # INTERIM (development only): torch math with the exact score semantics of the kernels.
-    B, Sq, H, D = q.shape
-    Sk = k.shape[1]
-    s = torch.einsum("bihd,bjhd->bhij", q.float(), k.float()) * scale
-    if rel_bias is not None:
-        s = s + _rel_to_dense(rel_bias, Sq, Sk)[None]
-    if dense_bias is not None:
-        s = s + dense_bias
-    if key_add is not None:
-        s = s + key_add[:, None, None, :]
-    if causal:
-        s = s + torch.full((Sq, Sk), float("-inf"), device=s.device).triu(1)
-    p = torch.softmax(s, dim=-1)
-    if dropout_p > 0:
-        p = torch.nn.functional.dropout(p, dropout_p, True)
-    return torch.einsum("bhij,bjhd->bihd", p.to(v.dtype), v)
-
-
 def attention_self(qkv, scale, rel_bias=None, key_add=None, causal=False, dropout_p=0.0, dense_bias=None):
     """qkv (B,S,3,H,D) packed projection output."""
+    if qkv.dtype == torch.bfloat16 and dense_bias is None and dropout_p == 0.0:
+        return _AttnSelf.apply(qkv, rel_bias, key_add, scale, causal)
     return _attention_core(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], scale, rel_bias, key_add, causal, dropout_p,
                            dense_bias)
 
 
 def attention_cross(q, kv, scale, rel_bias=None, key_add=None, dropout_p=0.0):
     """q (B,Sq,H,D); kv (B,Sk,2,H,D) packed."""
+    if q.dtype == torch.bfloat16 and dropout_p == 0.0:
+        return _AttnCross.apply(q, kv, rel_bias, key_add, scale)
     return _attention_core(q, kv[:, :, 0], kv[:, :, 1], scale, rel_bias, key_add, False, dropout_p, None)
 
 

@@ -81,3 +81,84 @@ def test_mha_causal_self_attention_fwd_packed_qkv(B, T, H):
     got = o.float().cpu().transpose(1, 2)
     assert (got - ref).abs().max().item() <= 2e-2
     assert (got - ref).norm() / ref.norm() <= 1e-2
+
+
+# ------------------------------- backward -------------------------------------------
+def _ref_grads(q, k, v, scale, rel, key_add, causal, go):
+    """fp32 autograd through the oracle-equivalent math (scores exactly as the kernels define them)."""
+    qf, kf, vf = [t.float().transpose(1, 2).clone().requires_grad_(True) for t in (q, k, v)]
+    relp = None if rel is None else rel.clone().requires_grad_(True)
+    Sq, Sk = qf.shape[2], kf.shape[2]
+    s = torch.matmul(qf, kf.transpose(-1, -2)) * scale
+    if relp is not None:
+        s = s + _rel_dense(relp, Sq, Sk)[None]
+    if key_add is not None:
+        s = s + key_add[:, None, None, :]
+    if causal:
+        s = s + torch.full((Sq, Sk), float("-inf")).triu(1)
+    o = torch.matmul(torch.softmax(s, -1), vf)
+    o.backward(go.float().transpose(1, 2))
+    tr = lambda t: t.grad.transpose(1, 2)  # noqa: E731
+    return o.detach().transpose(1, 2), tr(qf), tr(kf), tr(vf), (None if relp is None else relp.grad)
+
+
+def _close(a, b, tol=2e-2):
+    err = (a.float().cpu() - b).norm() / (b.norm() + 1e-12)
+    assert err <= tol, float(err)
+
+
+@pytest.mark.parametrize("B,S,H", [(1, 128, 1), (2, 327, 3), (1, 100, 2), (1, 464, 2), (2, 5, 1)])
+def test_t5_self_attention_bwd_packed(B, S, H):
+    from phoneme_vqa_b200 import ops
+    g = torch.Generator().manual_seed(S)
+    qkv = (torch.randn(B, S, 3, H, 64, generator=g) * 0.5).bfloat16()
+    rel = torch.randn(H, 2 * S - 1, generator=g)
+    valid = torch.rand(B, S, generator=g) > 0.2
+    valid[:, 0] = True
+    key_add = torch.where(valid, 0.0, float("-inf"))
+    go = torch.randn(B, S, H, 64, generator=g).bfloat16()
+    _, dq, dk, dv, drel = _ref_grads(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], 1.0, rel, key_add, False, go)
+    qd = qkv.to(DEV).requires_grad_(True)
+    reld = rel.to(DEV).requires_grad_(True)
+    o = ops.attention_self(qd, 1.0, rel_bias=reld, key_add=key_add.to(DEV))
+    o.backward(go.to(DEV))
+    _close(qd.grad[:, :, 0], dq)
+    _close(qd.grad[:, :, 1], dk)
+    _close(qd.grad[:, :, 2], dv)
+    _close(reld.grad, drel)
+
+
+@pytest.mark.parametrize("B,T,H", [(2, 127, 3), (1, 300, 2), (2, 1, 1)])
+def test_mha_causal_self_attention_bwd(B, T, H):
+    from phoneme_vqa_b200 import ops
+    g = torch.Generator().manual_seed(T)
+    qkv = torch.randn(B, T, 3, H, 64, generator=g).bfloat16()
+    key_add = (torch.rand(B, T, generator=g) > 0.7).float()
+    go = torch.randn(B, T, H, 64, generator=g).bfloat16()
+    sc = 1.0 / math.sqrt(64)
+    _, dq, dk, dv, _ = _ref_grads(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], sc, None, key_add, True, go)
+    qd = qkv.to(DEV).requires_grad_(True)
+    o = ops.attention_self(qd, sc, key_add=key_add.to(DEV), causal=True)
+    o.backward(go.to(DEV))
+    _close(qd.grad[:, :, 0], dq)
+    _close(qd.grad[:, :, 1], dk)
+    _close(qd.grad[:, :, 2], dv)
+
+
+@pytest.mark.parametrize("B,T,S,H", [(2, 127, 327, 3), (1, 40, 64, 2)])
+def test_mha_cross_attention_bwd(B, T, S, H):
+    from phoneme_vqa_b200 import ops
+    g = torch.Generator().manual_seed(T + S)
+    q = torch.randn(B, T, H, 64, generator=g).bfloat16()
+    kv = torch.randn(B, S, 2, H, 64, generator=g).bfloat16()
+    key_add = (torch.rand(B, S, generator=g) > 0.3).float()
+    go = torch.randn(B, T, H, 64, generator=g).bfloat16()
+    sc = 1.0 / math.sqrt(64)
+    _, dq, dk, dv, _ = _ref_grads(q, kv[:, :, 0], kv[:, :, 1], sc, None, key_add, False, go)
+    qd = q.to(DEV).requires_grad_(True)
+    kvd = kv.to(DEV).requires_grad_(True)
+    o = ops.attention_cross(qd, kvd, sc, key_add=key_add.to(DEV))
+    o.backward(go.to(DEV))
+    _close(qd.grad, dq)
+    _close(kvd.grad[:, :, 0], dk)
+    _close(kvd.grad[:, :, 1], dv)
