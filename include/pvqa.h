@@ -172,6 +172,9 @@ int pvqa_phoneme_head_ce_bwd(const void* h, const int64_t* targets, int64_t tgt_
  * key_add (B,Sk) fp32 or NULL: additive per-key term (0 / -inf for T5 masks; +1.0 / 0.0
  *   float masks of the reference decoder).
  * lse (B,H,Sq) fp32 out: log-sum-exp per row, saved for backward.
+ * dropout_p > 0: inverted dropout on the softmax probabilities (HF modeling_t5.py:332 /
+ *   nn.MultiheadAttention dropout) with an in-kernel Philox4x32-10 stream keyed by
+ *   (seed, offset, b, h, i, j); p is quantised to 1/256.  Backward must get the same triple.
  * ------------------------------------------------------------------------ */
 int pvqa_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
                   const float* rel_bias, const float* key_add,
@@ -180,7 +183,8 @@ int pvqa_attn_fwd(const void* q, const void* k, const void* v, void* o, float* l
                   int64_t k_stride_b, int64_t k_stride_s, int64_t k_stride_h,
                   int64_t v_stride_b, int64_t v_stride_s, int64_t v_stride_h,
                   int64_t o_stride_b, int64_t o_stride_s, int64_t o_stride_h,
-                  float scale, int causal, void* stream);
+                  float scale, int causal,
+                  float dropout_p, uint64_t seed, uint64_t offset, void* stream);
 
 /* backward.  dk, dv: bf16 with explicit strides (may point into a packed d(qkv) buffer).
  * dq_accum: fp32 (B,Sq,H,64) contiguous, ZERO-INITIALISED by the caller — every 128-key tile
@@ -198,7 +202,39 @@ int pvqa_attn_bwd(const void* q, const void* k, const void* v, const void* o, co
                   int64_t do_stride_b, int64_t do_stride_s, int64_t do_stride_h,
                   int64_t dk_stride_b, int64_t dk_stride_s, int64_t dk_stride_h,
                   int64_t dv_stride_b, int64_t dv_stride_s, int64_t dv_stride_h,
-                  float scale, int causal, void* stream);
+                  float scale, int causal,
+                  float dropout_p, uint64_t seed, uint64_t offset, void* stream);
+
+/* ------------------------------------------------------------------------
+ * fp32 parity-mode attention (CUDA cores, no tensor-core rounding): same score definition as
+ * pvqa_attn_fwd/bwd with fp32 operands and outputs, explicit strides everywhere.
+ * Used when compute_dtype = float32 so logits stay within 1e-5 of the reference.
+ * delta_ws: (B,H,Sq) fp32 workspace (rowsum(dO*O), written by the dQ pass, read by the dK/dV pass).
+ * ------------------------------------------------------------------------ */
+int pvqa_attn_f32_fwd(const float* q, const float* k, const float* v, float* o, float* lse,
+                      const float* rel_bias, const float* key_add,
+                      int64_t B, int64_t H, int64_t Sq, int64_t Sk, int64_t D,
+                      int64_t q_stride_b, int64_t q_stride_s, int64_t q_stride_h,
+                      int64_t k_stride_b, int64_t k_stride_s, int64_t k_stride_h,
+                      int64_t v_stride_b, int64_t v_stride_s, int64_t v_stride_h,
+                      int64_t o_stride_b, int64_t o_stride_s, int64_t o_stride_h,
+                      float scale, int causal,
+                      float dropout_p, uint64_t seed, uint64_t offset, void* stream);
+
+int pvqa_attn_f32_bwd(const float* q, const float* k, const float* v, const float* o, const float* d_o,
+                      const float* lse, const float* rel_bias, const float* key_add,
+                      float* dq, float* dk, float* dv, float* d_rel_bias, float* delta_ws,
+                      int64_t B, int64_t H, int64_t Sq, int64_t Sk, int64_t D,
+                      int64_t q_stride_b, int64_t q_stride_s, int64_t q_stride_h,
+                      int64_t k_stride_b, int64_t k_stride_s, int64_t k_stride_h,
+                      int64_t v_stride_b, int64_t v_stride_s, int64_t v_stride_h,
+                      int64_t o_stride_b, int64_t o_stride_s, int64_t o_stride_h,
+                      int64_t do_stride_b, int64_t do_stride_s, int64_t do_stride_h,
+                      int64_t dq_stride_b, int64_t dq_stride_s, int64_t dq_stride_h,
+                      int64_t dk_stride_b, int64_t dk_stride_s, int64_t dk_stride_h,
+                      int64_t dv_stride_b, int64_t dv_stride_s, int64_t dv_stride_h,
+                      float scale, int causal,
+                      float dropout_p, uint64_t seed, uint64_t offset, void* stream);
 
 #ifdef __cplusplus
 }

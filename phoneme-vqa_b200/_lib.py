@@ -17,12 +17,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libpvqa_sm100.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
-SOURCES = ["api.cu", "embed.cu", "head.cu", "attn.cu", "norm.cu"]
+SOURCES = ["api.cu", "embed.cu", "head.cu", "attn.cu", "attn_simt.cu", "norm.cu"]
 HEADERS = ["common.cuh", "tc05.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
+    "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
 ]
 
@@ -71,8 +71,10 @@ _SIGNATURES = {
     "pvqa_embed_tgt_bwd": (c_int, [_vp] * 5 + _i64x(8) + [c_int, _f, c_uint64, c_uint64, _vp]),
     "pvqa_phoneme_head_ce_fwd": (c_int, [_vp, _vp, _i64] + [_vp] * 12 + _i64x(8) + [c_int, c_int, _vp]),
     "pvqa_phoneme_head_ce_bwd": (c_int, [_vp, _vp, _i64] + [_vp] * 12 + _i64x(8) + [c_int, c_int, _vp]),
-    "pvqa_attn_fwd": (c_int, [_vp] * 7 + _i64x(5) + _i64x(12) + [_f, c_int, _vp]),
-    "pvqa_attn_bwd": (c_int, [_vp] * 12 + _i64x(5) + _i64x(21) + [_f, c_int, _vp]),
+    "pvqa_attn_fwd": (c_int, [_vp] * 7 + _i64x(5) + _i64x(12) + [_f, c_int, _f, c_uint64, c_uint64, _vp]),
+    "pvqa_attn_bwd": (c_int, [_vp] * 12 + _i64x(5) + _i64x(21) + [_f, c_int, _f, c_uint64, c_uint64, _vp]),
+    "pvqa_attn_f32_fwd": (c_int, [_vp] * 7 + _i64x(5) + _i64x(12) + [_f, c_int, _f, c_uint64, c_uint64, _vp]),
+    "pvqa_attn_f32_bwd": (c_int, [_vp] * 13 + _i64x(5) + _i64x(24) + [_f, c_int, _f, c_uint64, c_uint64, _vp]),
 }
 
 

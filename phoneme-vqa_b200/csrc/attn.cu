@@ -35,6 +35,9 @@ struct AttnFwdParams {
   long long o_stride_b, o_stride_s, o_stride_h;
   float scale;
   int causal;
+  uint32_t drop_thr8;         // 0 = no dropout; drop probability = thr8/256
+  float drop_scale;           // 1 / keep probability
+  uint64_t seed, offset;
 };
 
 // smem carve-up (bytes from the 1024-aligned base)
@@ -172,6 +175,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         pv[x] = fast_exp2(s - m_safe);
         sum += pv[x];
       }
+      if (p.drop_thr8) {      // dropout acts on the normalised probabilities: the row sum stays undropped
+        const uint64_t grow = ((uint64_t)(b * p.H + h) * p.Sq + min(i, p.Sq - 1)) * (uint64_t)((p.Sk + 15) >> 4);
+#pragma unroll
+        for (int g2 = 0; g2 < 2; ++g2) {
+          const uint32_t keep = attn_dropout_keep16(p.seed, p.offset, grow + ((j0 + c * 32) >> 4) + g2, p.drop_thr8);
+#pragma unroll
+          for (int x = 0; x < 16; ++x) pv[g2 * 16 + x] = ((keep >> x) & 1u) ? pv[g2 * 16 + x] * p.drop_scale : 0.f;
+        }
+      }
       // 32 columns = 4 chunks of 8 bf16 (16 B); sub-tile = c / 2, chunk-in-row = (c % 2) * 4 + q
       uint8_t* prow = smem + kOffP + (c >> 1) * (kBM * 128) + tid * 128;
 #pragma unroll
@@ -277,6 +289,9 @@ struct AttnBwdParams {
   long long dv_stride_b, dv_stride_s, dv_stride_h;
   float scale;
   int causal;
+  uint32_t drop_thr8;
+  float drop_scale;
+  uint64_t seed, offset;
 };
 
 __global__ void __launch_bounds__(kBwdThreads2, 1)
@@ -406,7 +421,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const bool dead = !row_live || j >= p.Sk || (p.causal && j > i);
         const float pr = dead ? 0.f : fast_exp2(s - lse2);
         pv[x] = pr;
-        dsv[x] = pr * (__uint_as_float(rp[x]) - delta) * p.scale;
+        dsv[x] = __uint_as_float(rp[x]);
+      }
+      if (p.drop_thr8) {      // P_drop = P*M/keep feeds dV; dP = M/keep * dP_drop feeds dS
+        const uint64_t grow = ((uint64_t)(b * p.H + h) * p.Sq + min(i, p.Sq - 1)) * (uint64_t)((p.Sk + 15) >> 4);
+#pragma unroll
+        for (int g2 = 0; g2 < 2; ++g2) {
+          const uint32_t keep = attn_dropout_keep16(p.seed, p.offset,
+                                                    grow + ((j0 + half * 64 + c * 32) >> 4) + g2, p.drop_thr8);
+#pragma unroll
+          for (int x = 0; x < 16; ++x) {
+            const float mk = ((keep >> x) & 1u) ? p.drop_scale : 0.f;
+            const float pr = pv[g2 * 16 + x];
+            dsv[g2 * 16 + x] = pr * (mk * dsv[g2 * 16 + x] - delta) * p.scale;
+            pv[g2 * 16 + x] = pr * mk;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int x = 0; x < 32; ++x) dsv[x] = pv[x] * (dsv[x] - delta) * p.scale;
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -574,7 +607,9 @@ extern "C" int pvqa_attn_fwd(const void* q, const void* k, const void* v, void* 
                              int64_t Sk, int64_t D, int64_t q_stride_b, int64_t q_stride_s, int64_t q_stride_h,
                              int64_t k_stride_b, int64_t k_stride_s, int64_t k_stride_h, int64_t v_stride_b,
                              int64_t v_stride_s, int64_t v_stride_h, int64_t o_stride_b, int64_t o_stride_s,
-                             int64_t o_stride_h, float scale, int causal, void* stream) {
+                             int64_t o_stride_h, float scale, int causal, float dropout_p, uint64_t seed,
+                             uint64_t offset, void* stream) {
+  PVQA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, PVQA_ERR_SHAPE, "attn_fwd: dropout_p must be in [0,1)");
   PVQA_REQUIRE(D == kD, PVQA_ERR_SHAPE, "attn_fwd: head dim %lld unsupported (kernel is specialised for 64)", (long long)D);
   PVQA_REQUIRE(B >= 0 && H > 0 && Sq >= 0 && Sk >= 0, PVQA_ERR_SHAPE, "attn_fwd: bad dimension");
   if (B == 0 || Sq == 0) return PVQA_OK;
@@ -604,6 +639,9 @@ extern "C" int pvqa_attn_fwd(const void* q, const void* k, const void* v, void* 
   p.B = (int)B; p.H = (int)H; p.Sq = (int)Sq; p.Sk = (int)Sk;
   p.o_stride_b = o_stride_b; p.o_stride_s = o_stride_s; p.o_stride_h = o_stride_h;
   p.scale = scale; p.causal = causal;
+  p.drop_thr8 = (uint32_t)lrintf(dropout_p * 256.f);
+  p.drop_scale = p.drop_thr8 ? 256.f / (256.f - (float)p.drop_thr8) : 1.f;
+  p.seed = seed; p.offset = offset;
   dim3 grid((unsigned)((Sq + kBM - 1) / kBM), (unsigned)H, (unsigned)B);
   attn_fwd_kernel<<<grid, kAttnThreads, smem_bytes, (cudaStream_t)stream>>>(tq, tk, tv, p);
   count_launch();
@@ -620,7 +658,9 @@ extern "C" int pvqa_attn_bwd(const void* q, const void* k, const void* v, const 
                              int64_t v_stride_s, int64_t v_stride_h, int64_t o_stride_b, int64_t o_stride_s,
                              int64_t o_stride_h, int64_t do_stride_b, int64_t do_stride_s, int64_t do_stride_h,
                              int64_t dk_stride_b, int64_t dk_stride_s, int64_t dk_stride_h, int64_t dv_stride_b,
-                             int64_t dv_stride_s, int64_t dv_stride_h, float scale, int causal, void* stream) {
+                             int64_t dv_stride_s, int64_t dv_stride_h, float scale, int causal, float dropout_p,
+                             uint64_t seed, uint64_t offset, void* stream) {
+  PVQA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, PVQA_ERR_SHAPE, "attn_bwd: dropout_p must be in [0,1)");
   PVQA_REQUIRE(D == kD, PVQA_ERR_SHAPE, "attn_bwd: head dim %lld unsupported (kernel is specialised for 64)", (long long)D);
   PVQA_REQUIRE(B >= 0 && H > 0 && Sq >= 0 && Sk >= 0, PVQA_ERR_SHAPE, "attn_bwd: bad dimension");
   if (B == 0 || Sq == 0 || Sk == 0) return PVQA_OK;
@@ -659,6 +699,9 @@ extern "C" int pvqa_attn_bwd(const void* q, const void* k, const void* v, const 
   p.dk_stride_b = dk_stride_b; p.dk_stride_s = dk_stride_s; p.dk_stride_h = dk_stride_h;
   p.dv_stride_b = dv_stride_b; p.dv_stride_s = dv_stride_s; p.dv_stride_h = dv_stride_h;
   p.scale = scale; p.causal = causal;
+  p.drop_thr8 = (uint32_t)lrintf(dropout_p * 256.f);
+  p.drop_scale = p.drop_thr8 ? 256.f / (256.f - (float)p.drop_thr8) : 1.f;
+  p.seed = seed; p.offset = offset;
   dim3 grid((unsigned)((Sk + kBN - 1) / kBN), (unsigned)H, (unsigned)B);
   attn_bwd_kernel<<<grid, kBwdThreads2, smem_bytes, (cudaStream_t)stream>>>(tq, tk, tv, tdo, p);
   count_launch();

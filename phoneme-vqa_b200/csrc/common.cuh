@@ -165,4 +165,21 @@ __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t offset
   return m;
 }
 
+// attention-probability dropout: keep-mask for 16 consecutive keys of one query row.
+// group = (row_linear * groups_per_row + j / 16); 8 random bits per element, keep iff byte >= thr8,
+// so the drop probability is thr8/256 (p quantised to 1/256; the 1/keep scale uses the quantised value).
+__device__ __forceinline__ uint32_t attn_dropout_keep16(uint64_t seed, uint64_t offset, uint64_t group, uint32_t thr8) {
+  const uint64_t c = offset + group;
+  uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0x5A17u, 0u),
+                          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  uint32_t m = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int bb = 0; bb < 4; ++bb) m |= (((w[i] >> (8 * bb)) & 0xffu) >= thr8 ? 1u : 0u) << (4 * i + bb);
+  }
+  return m;
+}
+
 }  // namespace pvqa

@@ -286,65 +286,80 @@ def residual_dropout_add(hidden, update, p, training):
 
 
 # ----------------------------------------------------------------------------------
-# K2 / K3: attention
+# K2 / K3: attention.  bf16 -> tcgen05/TMA flash kernels; fp32 (parity mode) -> fp32 CUDA-core kernels.
 # ----------------------------------------------------------------------------------
-def _rel_to_dense(rel_bias, Sq, Sk):
-    """(H, Sq+Sk-1) -> (H, Sq, Sk): dense[h,i,j] = rel_bias[h, j - i + Sq - 1]"""
-    i = torch.arange(Sq, device=rel_bias.device)[:, None]
-    j = torch.arange(Sk, device=rel_bias.device)[None, :]
-    return rel_bias[:, (j - i + Sq - 1)]
+def _check_attn_operand(t, name, dtype):
+    if t.dtype != dtype or t.dim() != 4 or t.stride(3) != 1:
+        raise TypeError(f"attention {name} must be a {dtype} (B,S,H,D) view with unit stride on D")
 
 
-def _check_attn_operand(t, name):
-    if t.dtype != torch.bfloat16 or t.dim() != 4 or t.stride(3) != 1:
-        raise TypeError(f"attention {name} must be a bf16 (B,S,H,D) view with unit stride on D")
+def _st3(t):
+    return t.stride(0), t.stride(1), t.stride(2)
 
 
-def attention_fwd_raw(q, k, v, scale, rel_bias=None, key_add=None, causal=False):
-    """tcgen05 flash-attention forward through the C-ABI.  Returns (o (B,Sq,H,D) bf16, lse (B,H,Sq) fp32)."""
+def _drop_args(dropout_p, B, H, Sq, Sk):
+    if dropout_p <= 0.0:
+        return 0.0, 0, 0
+    seed, off = _Rng.next(8 * B * H * Sq * ((Sk + 15) // 16))
+    return float(dropout_p), seed, off
+
+
+def attention_fwd_raw(q, k, v, scale, rel_bias=None, key_add=None, causal=False, drop=(0.0, 0, 0)):
+    """Forward through the C-ABI.  q (B,Sq,H,D), k/v (B,Sk,H,D) strided views (bf16 or fp32).
+    Returns (o (B,Sq,H,D) same dtype, lse (B,H,Sq) fp32)."""
     lib = _lib.load()
     _need_cuda(q, k, v, rel_bias, key_add)
+    dtype = q.dtype
+    if dtype not in (torch.bfloat16, torch.float32):
+        raise TypeError("attention supports bfloat16 (tcgen05) and float32 (parity mode)")
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
-        _check_attn_operand(t, n)
+        _check_attn_operand(t, n, dtype)
     B, Sq, H, D = q.shape
     Sk = k.shape[1]
     dev = q.device
-    o = torch.empty((B, Sq, H, D), dtype=torch.bfloat16, device=dev)
+    o = torch.empty((B, Sq, H, D), dtype=dtype, device=dev)
     lse = torch.empty((B, H, Sq), dtype=torch.float32, device=dev)
-    if rel_bias is not None:
-        rel_bias = rel_bias.to(torch.float32).contiguous()
-        assert rel_bias.shape == (H, Sq + Sk - 1)
-    if key_add is not None:
-        key_add = key_add.to(torch.float32).contiguous()
-        assert key_add.shape == (B, Sk)
-    with torch.cuda.device(dev), _prof("attn_fwd"):
-        check(lib.pvqa_attn_fwd(_p(q), _p(k), _p(v), _p(o), _p(lse), _p(rel_bias), _p(key_add), B, H, Sq, Sk, D,
-                                q.stride(0), q.stride(1), q.stride(2), k.stride(0), k.stride(1), k.stride(2),
-                                v.stride(0), v.stride(1), v.stride(2), o.stride(0), o.stride(1), o.stride(2),
-                                float(scale), int(bool(causal)), _stream()), "pvqa_attn_fwd")
+    if rel_bias is not None and tuple(rel_bias.shape) != (H, Sq + Sk - 1):
+        raise ValueError(f"rel_bias must be (H, Sq+Sk-1) = {(H, Sq + Sk - 1)}, got {tuple(rel_bias.shape)}")
+    if key_add is not None and tuple(key_add.shape) != (B, Sk):
+        raise ValueError(f"key_add must be (B, Sk) = {(B, Sk)}, got {tuple(key_add.shape)}")
+    fn, name = (lib.pvqa_attn_fwd, "attn_fwd") if dtype == torch.bfloat16 else (lib.pvqa_attn_f32_fwd, "attn_f32_fwd")
+    with torch.cuda.device(dev), _prof(f"{name}[Sq={Sq},Sk={Sk}]"):
+        check(fn(_p(q), _p(k), _p(v), _p(o), _p(lse), _p(rel_bias), _p(key_add), B, H, Sq, Sk, D,
+                 *_st3(q), *_st3(k), *_st3(v), *_st3(o), float(scale), int(bool(causal)),
+                 float(drop[0]), int(drop[1]), int(drop[2]), _stream()), "pvqa_" + name)
     return o, lse
 
 
-def attention_bwd_raw(q, k, v, o, d_o, lse, scale, rel_bias, key_add, causal, dk, dv, want_d_rel):
-    """tcgen05 flash-attention backward through the C-ABI.  dk/dv are caller-provided bf16 (B,Sk,H,D)
-    views (possibly into a packed buffer).  Returns (dq_accum fp32 (B,Sq,H,D), d_rel or None)."""
+def attention_bwd_raw(q, k, v, o, d_o, lse, scale, rel_bias, key_add, causal, dk, dv, want_d_rel, drop=(0.0, 0, 0)):
+    """Backward through the C-ABI.  dk/dv are caller-provided (B,Sk,H,D) views (possibly into a packed
+    buffer) in q's dtype.  Returns (dq fp32 (B,Sq,H,D), d_rel fp32 or None)."""
     lib = _lib.load()
     B, Sq, H, D = q.shape
     Sk = k.shape[1]
     dev = q.device
-    dq_accum = torch.zeros((B, Sq, H, D), dtype=torch.float32, device=dev)
     d_rel = torch.zeros((H, Sq + Sk - 1), dtype=torch.float32, device=dev) if want_d_rel else None
+    d_o = d_o.to(q.dtype)
     if d_o.stride(3) != 1:
         d_o = d_o.contiguous()
-    with torch.cuda.device(dev), _prof("attn_bwd"):
-        check(lib.pvqa_attn_bwd(_p(q), _p(k), _p(v), _p(o), _p(d_o), _p(lse), _p(rel_bias), _p(key_add),
-                                _p(dq_accum), _p(dk), _p(dv), _p(d_rel), B, H, Sq, Sk, D,
-                                q.stride(0), q.stride(1), q.stride(2), k.stride(0), k.stride(1), k.stride(2),
-                                v.stride(0), v.stride(1), v.stride(2), o.stride(0), o.stride(1), o.stride(2),
-                                d_o.stride(0), d_o.stride(1), d_o.stride(2), dk.stride(0), dk.stride(1), dk.stride(2),
-                                dv.stride(0), dv.stride(1), dv.stride(2), float(scale), int(bool(causal)), _stream()),
-              "pvqa_attn_bwd")
-    return dq_accum, d_rel
+    if q.dtype == torch.bfloat16:
+        dq = torch.zeros((B, Sq, H, D), dtype=torch.float32, device=dev)      # fp32 accumulator (RED target)
+        with torch.cuda.device(dev), _prof(f"attn_bwd[Sq={Sq},Sk={Sk}]"):
+            check(lib.pvqa_attn_bwd(_p(q), _p(k), _p(v), _p(o), _p(d_o), _p(lse), _p(rel_bias), _p(key_add),
+                                    _p(dq), _p(dk), _p(dv), _p(d_rel), B, H, Sq, Sk, D,
+                                    *_st3(q), *_st3(k), *_st3(v), *_st3(o), *_st3(d_o), *_st3(dk), *_st3(dv),
+                                    float(scale), int(bool(causal)), float(drop[0]), int(drop[1]), int(drop[2]),
+                                    _stream()), "pvqa_attn_bwd")
+    else:
+        dq = torch.empty((B, Sq, H, D), dtype=torch.float32, device=dev)
+        ws = torch.empty((B, H, Sq), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev), _prof(f"attn_f32_bwd[Sq={Sq},Sk={Sk}]"):
+            check(lib.pvqa_attn_f32_bwd(_p(q), _p(k), _p(v), _p(o), _p(d_o), _p(lse), _p(rel_bias), _p(key_add),
+                                        _p(dq), _p(dk), _p(dv), _p(d_rel), _p(ws), B, H, Sq, Sk, D,
+                                        *_st3(q), *_st3(k), *_st3(v), *_st3(o), *_st3(d_o), *_st3(dq), *_st3(dk),
+                                        *_st3(dv), float(scale), int(bool(causal)), float(drop[0]), int(drop[1]),
+                                        int(drop[2]), _stream()), "pvqa_attn_f32_bwd")
+    return dq, d_rel
 
 
 def _prep_bias(rel_bias, key_add):
@@ -354,133 +369,64 @@ def _prep_bias(rel_bias, key_add):
 
 
 class _AttnSelf(torch.autograd.Function):
-    """packed (B,S,3,H,D) bf16 projection -> (B,S,H,D); d(qkv) comes back packed for the QKV GEMM backward."""
+    """packed (B,S,3,H,D) projection -> (B,S,H,D); d(qkv) comes back packed for the QKV GEMM backward."""
 
     @staticmethod
-    def forward(ctx, qkv, rel_bias, key_add, scale, causal):
+    def forward(ctx, qkv, rel_bias, key_add, scale, causal, dropout_p):
         rb, ka = _prep_bias(rel_bias, key_add)
         qkv = qkv.contiguous()
-        o, lse = attention_fwd_raw(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], scale, rb, ka, causal)
+        B, S, _, H, _ = qkv.shape
+        drop = _drop_args(dropout_p, B, H, S, S)
+        o, lse = attention_fwd_raw(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], scale, rb, ka, causal, drop)
         ctx.save_for_backward(qkv, o, lse, rb, ka)
         ctx.meta = (float(scale), bool(causal), rel_bias is not None and ctx.needs_input_grad[1],
-                    None if rel_bias is None else rel_bias.dtype)
+                    None if rel_bias is None else rel_bias.dtype, drop)
         return o
 
     @staticmethod
     def backward(ctx, d_o):
         qkv, o, lse, rb, ka = ctx.saved_tensors
-        scale, causal, want_rel, rel_dtype = ctx.meta
+        scale, causal, want_rel, rel_dtype, drop = ctx.meta
         dqkv = torch.empty_like(qkv)
-        dq_acc, d_rel = attention_bwd_raw(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], o, d_o.to(torch.bfloat16), lse,
-                                          scale, rb, ka, causal, dqkv[:, :, 1], dqkv[:, :, 2], want_rel)
-        dqkv[:, :, 0].copy_(dq_acc)
-        return dqkv, (d_rel.to(rel_dtype) if want_rel else None), None, None, None
+        dq, d_rel = attention_bwd_raw(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], o, d_o, lse, scale, rb, ka, causal,
+                                      dqkv[:, :, 1], dqkv[:, :, 2], want_rel, drop)
+        dqkv[:, :, 0].copy_(dq)
+        return dqkv, (d_rel.to(rel_dtype) if want_rel else None), None, None, None, None
 
 
 class _AttnCross(torch.autograd.Function):
-    """q (B,Sq,H,D) + packed kv (B,Sk,2,H,D), bf16."""
+    """q (B,Sq,H,D) + packed kv (B,Sk,2,H,D)."""
 
     @staticmethod
-    def forward(ctx, q, kv, rel_bias, key_add, scale):
+    def forward(ctx, q, kv, rel_bias, key_add, scale, dropout_p):
         rb, ka = _prep_bias(rel_bias, key_add)
         q, kv = q.contiguous(), kv.contiguous()
-        o, lse = attention_fwd_raw(q, kv[:, :, 0], kv[:, :, 1], scale, rb, ka, False)
+        B, Sq, H, _ = q.shape
+        drop = _drop_args(dropout_p, B, H, Sq, kv.shape[1])
+        o, lse = attention_fwd_raw(q, kv[:, :, 0], kv[:, :, 1], scale, rb, ka, False, drop)
         ctx.save_for_backward(q, kv, o, lse, rb, ka)
         ctx.meta = (float(scale), rel_bias is not None and ctx.needs_input_grad[2],
-                    None if rel_bias is None else rel_bias.dtype)
+                    None if rel_bias is None else rel_bias.dtype, drop)
         return o
 
     @staticmethod
     def backward(ctx, d_o):
         q, kv, o, lse, rb, ka = ctx.saved_tensors
-        scale, want_rel, rel_dtype = ctx.meta
+        scale, want_rel, rel_dtype, drop = ctx.meta
         dkv = torch.empty_like(kv)
-        dq_acc, d_rel = attention_bwd_raw(q, kv[:, :, 0], kv[:, :, 1], o, d_o.to(torch.bfloat16), lse, scale, rb, ka,
-                                          False, dkv[:, :, 0], dkv[:, :, 1], want_rel)
-        return dq_acc.to(torch.bfloat16), dkv, (d_rel.to(rel_dtype) if want_rel else None), None, None
-
-
-def _attention_core(q, k, v, scale, rel_bias, key_add, causal, dropout_p, dense_bias):
-    """q (B,Sq,H,D), k/v (B,Sk,H,D) (strided views are fine) -> (B,Sq,H,D)."""
-    return _attention_torch(q, k, v, scale, rel_bias, key_add, causal, dropout_p, dense_bias)
+        dq, d_rel = attention_bwd_raw(q, kv[:, :, 0], kv[:, :, 1], o, d_o, lse, scale, rb, ka, False,
+                                      dkv[:, :, 0], dkv[:, :, 1], want_rel, drop)
+        return dq.to(q.dtype), dkv, (d_rel.to(rel_dtype) if want_rel else None), None, None, None
 
 
 def attention_self(qkv, scale, rel_bias=None, key_add=None, causal=False, dropout_p=0.0, dense_bias=None):
-    """qkv (B,S,3,H,D) packed projection output."""
-    if qkv.dtype == torch.bfloat16 and dense_bias is None and dropout_p == 0.0:
-        return _AttnSelf.apply(qkv, rel_bias, key_add, scale, causal)
-    return _attention_core(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], scale, rel_bias, key_add, causal, dropout_p,
-                           dense_bias)
+    """qkv (B,S,3,H,D) packed projection output (bf16 or fp32).
+    scores = scale * q.k + rel_bias[h, j-i+S-1] + key_add[b, j] (+ -inf above the diagonal if causal)."""
+    if dense_bias is not None:
+        raise NotImplementedError("dense (B,H,S,S) position bias (SaL family) is not built yet — SURVEY §8f rank 2")
+    return _AttnSelf.apply(qkv, rel_bias, key_add, scale, causal, float(dropout_p))
 
 
 def attention_cross(q, kv, scale, rel_bias=None, key_add=None, dropout_p=0.0):
     """q (B,Sq,H,D); kv (B,Sk,2,H,D) packed."""
-    if q.dtype == torch.bfloat16 and dropout_p == 0.0:
-        return _AttnCross.apply(q, kv, rel_bias, key_add, scale)
-    return _attention_core(q, kv[:, :, 0], kv[:, :, 1], scale, rel_bias, key_add, False, dropout_p, None)
-
-
-# ----------------------------------------------------------------------------------
-# K4: fused phoneme head + 3x cross-entropy (logits never materialised)
-# ----------------------------------------------------------------------------------
-class _PhonemeHeadCE(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, h, targets, W_on, b_on, W_rh, b_rh, W_to, b_to, ignore_index):
-        lib = _lib.load()
-        _need_cuda(h, targets, W_on, b_on, W_rh, b_rh, W_to, b_to)
-        if targets.dtype != torch.int64 or targets.shape[-1] != 3 or targets.stride(-1) != 1:
-            raise TypeError("targets must be int64 (N,3) with unit inner stride")
-        h = h.contiguous()
-        N, d = h.shape
-        V_o, on_dim = W_on.shape
-        V_r, rt_dim = W_rh.shape
-        V_t, _ = W_to.shape
-        wdt = h.dtype          # weights are consumed in the activation dtype (fp32 masters cast once: 71k elements)
-        ws = [t.to(wdt).contiguous() for t in (W_on, b_on, W_rh, b_rh, W_to, b_to)]
-        dev = h.device
-        loss_sum = torch.empty(3, dtype=torch.float32, device=dev)
-        count = torch.empty(3, dtype=torch.int32, device=dev)
-        lse = torch.empty((N, 3), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev), _prof("phoneme_head_ce_fwd"):
-            check(lib.pvqa_phoneme_head_ce_fwd(_p(h), _p(targets), targets.stride(0), *[_p(w) for w in ws],
-                                               _p(loss_sum), _p(count), _p(lse), None, None, None,
-                                               N, d, on_dim, rt_dim, V_o, V_r, V_t, int(ignore_index),
-                                               _dt(wdt), _dt(h.dtype), _stream()),
-                  "pvqa_phoneme_head_ce_fwd")
-        # mean over non-ignored targets per head, summed (nan if a head has no valid target, like torch)
-        loss = (loss_sum / count.to(torch.float32)).sum()
-        ctx.save_for_backward(h, targets, lse, count, *ws)
-        ctx.meta = (N, d, on_dim, rt_dim, V_o, V_r, V_t, int(ignore_index), (W_on.dtype, b_on.dtype))
-        return loss
-
-    @staticmethod
-    def backward(ctx, g):
-        lib = _lib.load()
-        h, targets, lse, count, W_on, b_on, W_rh, b_rh, W_to, b_to = ctx.saved_tensors
-        N, d, on_dim, rt_dim, V_o, V_r, V_t, ignore_index, (w_dtype, b_dtype) = ctx.meta
-        dev = h.device
-        g = g.to(torch.float32).reshape(1).contiguous()
-        dls = [torch.empty((N, V), dtype=h.dtype, device=dev) for V in (V_o, V_r, V_t)]
-        with torch.cuda.device(dev), _prof("phoneme_head_ce_bwd"):
-            check(lib.pvqa_phoneme_head_ce_bwd(_p(h), _p(targets), targets.stride(0), _p(W_on), _p(b_on), _p(W_rh),
-                                               _p(b_rh), _p(W_to), _p(b_to), _p(lse), _p(count), _p(g),
-                                               _p(dls[0]), _p(dls[1]), _p(dls[2]),
-                                               N, d, on_dim, rt_dim, V_o, V_r, V_t, ignore_index,
-                                               _dt(W_on.dtype), _dt(h.dtype), _stream()),
-                  "pvqa_phoneme_head_ce_bwd")
-        # the three small GEMMs (cuBLAS): d_h slices, dW_k, db_k
-        d_h = torch.empty_like(h)
-        offs = (0, on_dim, on_dim + rt_dim)
-        widths = (on_dim, rt_dim, rt_dim)
-        grads = []
-        for dl, W, off, w in zip(dls, (W_on, W_rh, W_to), offs, widths):
-            d_h[:, off:off + w] = dl @ W
-            grads.append((dl.t() @ h[:, off:off + w]).to(w_dtype))
-            grads.append(dl.sum(0, dtype=torch.float32).to(b_dtype))
-        return (d_h, None, *grads, None)
-
-
-def phoneme_head_ce(h, targets, W_onset, b_onset, W_rhyme, b_rhyme, W_tone, b_tone, ignore_index):
-    """K4.  h (N,d) = shared_lm_head output, targets (N,3) int64.  Returns the scalar
-    onset+rhyme+tone cross-entropy of core/executor/PhonemeLaTr_Executor.py:181-190."""
-    return _PhonemeHeadCE.apply(h, targets, W_onset, b_onset, W_rhyme, b_rhyme, W_tone, b_tone, ignore_index)
+    return _AttnCross.apply(q, kv, rel_bias, key_add, scale, float(dropout_p))

@@ -166,3 +166,62 @@ def test_mha_cross_attention_bwd(B, T, S, H):
     _close(qd.grad, dq)
     _close(kvd.grad[:, :, 0], dk)
     _close(kvd.grad[:, :, 1], dv)
+
+
+# ------------------------------- fp32 parity-mode kernels -----------------------------
+@pytest.mark.parametrize("B,S,H,causal", [(2, 37, 2, False), (1, 130, 3, True), (2, 327, 1, False)])
+def test_fp32_attention_fwd_bwd_tight(B, S, H, causal):
+    from phoneme_vqa_b200 import ops
+    g = torch.Generator().manual_seed(S)
+    qkv = torch.randn(B, S, 3, H, 64, generator=g) * 0.5
+    rel = None if causal else torch.randn(H, 2 * S - 1, generator=g)
+    key_add = (torch.rand(B, S, generator=g) > 0.7).float()
+    go = torch.randn(B, S, H, 64, generator=g)
+    sc = 0.125 if causal else 1.0
+    o_ref, dq, dk, dv, drel = _ref_grads(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], sc, rel, key_add, causal, go)
+    qd = qkv.to(DEV).requires_grad_(True)
+    reld = None if rel is None else rel.to(DEV).requires_grad_(True)
+    o = ops.attention_self(qd, sc, rel_bias=reld, key_add=key_add.to(DEV), causal=causal)
+    torch.testing.assert_close(o.detach().cpu(), o_ref, rtol=1e-5, atol=1e-5)
+    o.backward(go.to(DEV))
+    torch.testing.assert_close(qd.grad[:, :, 0].cpu(), dq, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(qd.grad[:, :, 1].cpu(), dk, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(qd.grad[:, :, 2].cpu(), dv, rtol=1e-4, atol=1e-5)
+    if rel is not None:
+        torch.testing.assert_close(reld.grad.cpu(), drel, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_attention_dropout_mask_is_consistent_between_fwd_and_bwd(dtype):
+    """With V = one-hot rows the output IS the dropped probability matrix, so the keep-mask can be read
+    back; the backward must then equal autograd through softmax * mask / keep."""
+    from phoneme_vqa_b200 import ops
+    B, S, H, p = 2, 64, 2, 0.25
+    g = torch.Generator().manual_seed(5)
+    q = torch.randn(B, S, H, 64, generator=g) * 0.3
+    k = torch.randn(B, S, H, 64, generator=g) * 0.3
+    v = torch.eye(64)[None, :, None, :].expand(B, S, H, 64).contiguous()
+    qkv = torch.stack([q, k, v], dim=2).to(dtype)
+    go = torch.randn(B, S, H, 64, generator=g).to(dtype)
+    ops.manual_seed(77)
+    qd = qkv.to(DEV).requires_grad_(True)
+    o = ops.attention_self(qd, 1.0, dropout_p=p)
+    pd = o.detach().float().cpu().transpose(1, 2)                 # (B,H,S,S) dropped probabilities
+    mask = (pd != 0).float()
+    keep = 1.0 - round(p * 256) / 256.0
+    assert abs(mask.mean().item() - keep) < 2e-2
+    qf, kf = [t.float().transpose(1, 2).requires_grad_(True) for t in (qkv[:, :, 0], qkv[:, :, 1])]
+    vf = qkv[:, :, 2].float().transpose(1, 2).requires_grad_(True)
+    pr = torch.softmax(torch.matmul(qf, kf.transpose(-1, -2)), -1) * mask / keep
+    torch.testing.assert_close(pd, pr.detach(), rtol=2e-2, atol=2e-3)
+    torch.matmul(pr, vf).backward(go.float().transpose(1, 2))
+    o.backward(go.to(DEV))
+    tol = 1e-4 if dtype == torch.float32 else 3e-2
+    for idx, ref in ((0, qf), (1, kf), (2, vf)):
+        _close(qd.grad[:, :, idx], ref.grad.transpose(1, 2), tol)
+    # same seed -> same mask; next call -> different mask
+    ops.manual_seed(77)
+    o2 = ops.attention_self(qkv.to(DEV), 1.0, dropout_p=p)
+    assert torch.equal(o2, o.detach())
+    o3 = ops.attention_self(qkv.to(DEV), 1.0, dropout_p=p)
+    assert not torch.equal(o3 != 0, o2 != 0)
