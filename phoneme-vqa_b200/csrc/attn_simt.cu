@@ -68,7 +68,7 @@ attn_f32_fwd_kernel(const SimtParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = blockIdx.x * kSimtWarps + warp, h = blockIdx.y, b = blockIdx.z;
   if (i >= p.Sq) return;
-  float* s_q = sm + warp * (kSD + p.Sk);
+  float* s_q = sm + warp * (kSD + ((p.Sk + 3) & ~3));      // keep every warp's slice 16-byte aligned
   float* s_p = s_q + kSD;
   const float* qrow = p.q + b * p.qsb + i * p.qss + h * p.qsh;
   s_q[2 * lane] = qrow[2 * lane];
@@ -112,7 +112,7 @@ attn_f32_bwd_q_kernel(const SimtParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = blockIdx.x * kSimtWarps + warp, h = blockIdx.y, b = blockIdx.z;
   if (i >= p.Sq) return;
-  float* s_q = sm + warp * (2 * kSD + p.Sk);
+  float* s_q = sm + warp * (2 * kSD + ((p.Sk + 3) & ~3));
   float* s_do = s_q + kSD;
   float* s_ds = s_do + kSD;
   const float* qrow = p.q + b * p.qsb + i * p.qss + h * p.qsh;
@@ -154,10 +154,10 @@ attn_f32_bwd_kv_kernel(const SimtParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j = blockIdx.x * kSimtWarps + warp, h = blockIdx.y, b = blockIdx.z;
   if (j >= p.Sk) return;
-  float* s_k = sm + warp * (2 * kSD + 2 * p.Sq);
+  float* s_k = sm + warp * (2 * kSD + 2 * ((p.Sq + 3) & ~3));
   float* s_v = s_k + kSD;
   float* s_pd = s_v + kSD;
-  float* s_ds = s_pd + p.Sq;
+  float* s_ds = s_pd + ((p.Sq + 3) & ~3);
   const float* krow = p.k + b * p.ksb + j * p.kss + h * p.ksh;
   const float* vrow = p.v + b * p.vsb + j * p.vss + h * p.vsh;
   s_k[2 * lane] = krow[2 * lane]; s_k[2 * lane + 1] = krow[2 * lane + 1];
@@ -231,7 +231,7 @@ extern "C" int pvqa_attn_f32_fwd(const float* q, const float* k, const float* v,
   p.drop_thr8 = (uint32_t)lrintf(dropout_p * 256.f);
   p.drop_scale = p.drop_thr8 ? 256.f / (256.f - (float)p.drop_thr8) : 1.f;
   p.seed = seed; p.offset = offset;
-  const size_t smem = (size_t)kSimtWarps * (kSD + Sk) * sizeof(float);
+  const size_t smem = (size_t)kSimtWarps * (kSD + ((Sk + 3) & ~3)) * sizeof(float);
   static size_t smem_cap = 48 * 1024;
   if (smem > smem_cap) {
     cudaError_t e = cudaFuncSetAttribute(attn_f32_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -282,8 +282,8 @@ extern "C" int pvqa_attn_f32_bwd(const float* q, const float* k, const float* v,
   p.drop_scale = p.drop_thr8 ? 256.f / (256.f - (float)p.drop_thr8) : 1.f;
   p.seed = seed; p.offset = offset;
   cudaStream_t st_ = (cudaStream_t)stream;
-  const size_t smem_q = (size_t)kSimtWarps * (2 * kSD + Sk) * sizeof(float);
-  const size_t smem_kv = (size_t)kSimtWarps * (2 * kSD + 2 * Sq) * sizeof(float);
+  const size_t smem_q = (size_t)kSimtWarps * (2 * kSD + ((Sk + 3) & ~3)) * sizeof(float);
+  const size_t smem_kv = (size_t)kSimtWarps * (2 * kSD + 2 * ((Sq + 3) & ~3)) * sizeof(float);
   static size_t cap_q = 48 * 1024, cap_kv = 48 * 1024;
   if (smem_q > cap_q) {
     cudaError_t e = cudaFuncSetAttribute(attn_f32_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q);

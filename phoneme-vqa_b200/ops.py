@@ -430,3 +430,69 @@ def attention_self(qkv, scale, rel_bias=None, key_add=None, causal=False, dropou
 def attention_cross(q, kv, scale, rel_bias=None, key_add=None, dropout_p=0.0):
     """q (B,Sq,H,D); kv (B,Sk,2,H,D) packed."""
     return _AttnCross.apply(q, kv, rel_bias, key_add, scale, float(dropout_p))
+
+
+# ----------------------------------------------------------------------------------
+# K4: fused phoneme head + 3x cross-entropy (logits never materialised)
+# ----------------------------------------------------------------------------------
+class _PhonemeHeadCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, targets, W_on, b_on, W_rh, b_rh, W_to, b_to, ignore_index):
+        lib = _lib.load()
+        _need_cuda(h, targets, W_on, b_on, W_rh, b_rh, W_to, b_to)
+        if targets.dtype != torch.int64 or targets.shape[-1] != 3 or targets.stride(-1) != 1:
+            raise TypeError("targets must be int64 (N,3) with unit inner stride")
+        h = h.contiguous()
+        N, d = h.shape
+        V_o, on_dim = W_on.shape
+        V_r, rt_dim = W_rh.shape
+        V_t, _ = W_to.shape
+        wdt = h.dtype          # weights are consumed in the activation dtype (fp32 masters cast once: 71k elements)
+        ws = [t.to(wdt).contiguous() for t in (W_on, b_on, W_rh, b_rh, W_to, b_to)]
+        dev = h.device
+        loss_sum = torch.empty(3, dtype=torch.float32, device=dev)
+        count = torch.empty(3, dtype=torch.int32, device=dev)
+        lse = torch.empty((N, 3), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev), _prof("phoneme_head_ce_fwd"):
+            check(lib.pvqa_phoneme_head_ce_fwd(_p(h), _p(targets), targets.stride(0), *[_p(w) for w in ws],
+                                               _p(loss_sum), _p(count), _p(lse), None, None, None,
+                                               N, d, on_dim, rt_dim, V_o, V_r, V_t, int(ignore_index),
+                                               _dt(wdt), _dt(h.dtype), _stream()),
+                  "pvqa_phoneme_head_ce_fwd")
+        # mean over non-ignored targets per head, summed (nan if a head has no valid target, like torch)
+        loss = (loss_sum / count.to(torch.float32)).sum()
+        ctx.save_for_backward(h, targets, lse, count, *ws)
+        ctx.meta = (N, d, on_dim, rt_dim, V_o, V_r, V_t, int(ignore_index), (W_on.dtype, b_on.dtype))
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        h, targets, lse, count, W_on, b_on, W_rh, b_rh, W_to, b_to = ctx.saved_tensors
+        N, d, on_dim, rt_dim, V_o, V_r, V_t, ignore_index, (w_dtype, b_dtype) = ctx.meta
+        dev = h.device
+        g = g.to(torch.float32).reshape(1).contiguous()
+        dls = [torch.empty((N, V), dtype=h.dtype, device=dev) for V in (V_o, V_r, V_t)]
+        with torch.cuda.device(dev), _prof("phoneme_head_ce_bwd"):
+            check(lib.pvqa_phoneme_head_ce_bwd(_p(h), _p(targets), targets.stride(0), _p(W_on), _p(b_on), _p(W_rh),
+                                               _p(b_rh), _p(W_to), _p(b_to), _p(lse), _p(count), _p(g),
+                                               _p(dls[0]), _p(dls[1]), _p(dls[2]),
+                                               N, d, on_dim, rt_dim, V_o, V_r, V_t, ignore_index,
+                                               _dt(W_on.dtype), _dt(h.dtype), _stream()),
+                  "pvqa_phoneme_head_ce_bwd")
+        # the three small GEMMs (cuBLAS): d_h slices, dW_k, db_k
+        d_h = torch.empty_like(h)
+        offs = (0, on_dim, on_dim + rt_dim)
+        widths = (on_dim, rt_dim, rt_dim)
+        grads = []
+        for dl, W, off, w in zip(dls, (W_on, W_rh, W_to), offs, widths):
+            d_h[:, off:off + w] = dl @ W
+            grads.append((dl.t() @ h[:, off:off + w]).to(w_dtype))
+            grads.append(dl.sum(0, dtype=torch.float32).to(b_dtype))
+        return (d_h, None, *grads, None)
+
+
+def phoneme_head_ce(h, targets, W_onset, b_onset, W_rhyme, b_rhyme, W_tone, b_tone, ignore_index):
+    """K4.  h (N,d) = shared_lm_head output, targets (N,3) int64.  Returns the scalar
+    onset+rhyme+tone cross-entropy of core/executor/PhonemeLaTr_Executor.py:181-190."""
+    return _PhonemeHeadCE.apply(h, targets, W_onset, b_onset, W_rhyme, b_rhyme, W_tone, b_tone, ignore_index)
