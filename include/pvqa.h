@@ -236,6 +236,31 @@ int pvqa_attn_f32_bwd(const float* q, const float* k, const float* v, const floa
                       float scale, int causal,
                       float dropout_p, uint64_t seed, uint64_t offset, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Fused glue of the transformer blocks (HBM-bound, one launch each)
+ * rms_norm      replaces HF T5LayerNorm.forward (transformers modeling_t5.py:46-70), called from every
+ *               T5 block reached through core/model/PhonemeLaTr.py:111-114: y = w * x * rsqrt(mean(x^2)+eps),
+ *               statistics in fp32; rstd (N) saved for backward.  bwd accumulates dw (fp32, caller zeroes).
+ * residual_dropout_add  replaces `hidden + dropout(sublayer)` (T5LayerSelfAttention/T5LayerFF.forward;
+ *               torch TransformerDecoderLayer x + dropoutN(...)): out fp32 = hidden fp32 + dropout(update).
+ *               bwd: d_update = d_out * mask / keep (d_hidden is d_out itself).
+ * relu_dropout  replaces dropout(relu(wi(x))) of T5DenseActDense / TransformerDecoderLayer._ff_block;
+ *               backward needs only y (y != 0 <=> x > 0 and kept).
+ * Dropout: Philox4x32-10 keyed by (seed, offset + element/8), p quantised to 1/65536.
+ * ------------------------------------------------------------------------ */
+int pvqa_rms_norm_fwd(const void* x, const float* w, void* y, float* rstd, int64_t N, int64_t d, float eps,
+                      int x_dtype, int y_dtype, void* stream);
+int pvqa_rms_norm_bwd(const void* dy, const void* x, const float* w, const float* rstd, void* dx, float* dw,
+                      int64_t N, int64_t d, int x_dtype, int y_dtype, void* stream);
+int pvqa_residual_dropout_add(const float* hidden, const void* update, float* out, int64_t n, int upd_dtype,
+                              float dropout_p, uint64_t seed, uint64_t offset, void* stream);
+int pvqa_residual_dropout_bwd(const float* d_out, void* d_update, int64_t n, int upd_dtype, float dropout_p,
+                              uint64_t seed, uint64_t offset, void* stream);
+int pvqa_relu_dropout_fwd(const void* x, void* y, int64_t n, int dtype, float dropout_p, uint64_t seed,
+                          uint64_t offset, void* stream);
+int pvqa_relu_dropout_bwd(const void* dy, const void* y, void* dx, int64_t n, int dtype, float dropout_p,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,343 @@
+// norm.cu — fused normalisation / residual / activation glue of the T5 encoder block and the
+// target decoder (HBM-bound element-wise work).
+//
+// reference semantics restated (no code shared):
+//   T5LayerNorm                      transformers modeling_t5.py:46-70   (RMS norm: fp32 variance, no mean, no bias)
+//   hidden + dropout(sublayer(...))  transformers modeling_t5.py:T5LayerSelfAttention/T5LayerFF.forward
+//   dropout(act(wi(x)))              transformers modeling_t5.py:84-103 (T5DenseActDense), torch TransformerDecoderLayer._ff_block
+// Each of these is 4-10 ATen kernels (pow, mean, rsqrt, mul, to, native_dropout, add ...) in the reference;
+// here each is one launch reading its operands once.
+#include "common.cuh"
+
+namespace pvqa {
+
+constexpr int kNormThreads = 256;
+constexpr int kMaxVec = 8;          // float4 chunks per lane: d <= 32 * 4 * 8 = 1024
+
+__device__ __forceinline__ float warp_sum_n(float x) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+
+template <typename T> __device__ __forceinline__ float4 load4(const T* p);
+template <> __device__ __forceinline__ float4 load4<float>(const float* p) {
+  return *reinterpret_cast<const float4*>(p);
+}
+template <> __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  uint2 u = *reinterpret_cast<const uint2*>(p);
+  float4 r;
+  bf16x2_to_f32(u.x, r.x, r.y);
+  bf16x2_to_f32(u.y, r.z, r.w);
+  return r;
+}
+template <typename T> __device__ __forceinline__ void store4(T* p, float4 v);
+template <> __device__ __forceinline__ void store4<float>(float* p, float4 v) {
+  *reinterpret_cast<float4*>(p) = v;
+}
+template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
+  uint2 u;
+  u.x = f32x2_to_bf16x2(v.x, v.y);
+  u.y = f32x2_to_bf16x2(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// ---------------- RMS norm forward: one warp per row, the row stays in registers ----------------
+template <typename XT, typename YT>
+__global__ void __launch_bounds__(kNormThreads)
+rms_norm_fwd_kernel(const XT* __restrict__ x, const float* __restrict__ w, YT* __restrict__ y,
+                    float* __restrict__ rstd, int N, int d, float eps) {
+  const int lane = threadIdx.x & 31;
+  for (int row = blockIdx.x * (kNormThreads / 32) + (threadIdx.x >> 5); row < N; row += gridDim.x * (kNormThreads / 32)) {
+    const XT* xr = x + (long long)row * d;
+    float4 v[kMaxVec];
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxVec; ++c) {
+      if ((c * 32 + lane) * 4 < d) {
+        v[c] = load4<XT>(xr + (c * 32 + lane) * 4);
+        ss += v[c].x * v[c].x + v[c].y * v[c].y + v[c].z * v[c].z + v[c].w * v[c].w;
+      }
+    }
+    ss = warp_sum_n(ss);
+    const float r = rsqrtf(ss / (float)d + eps);
+    if (lane == 0 && rstd) rstd[row] = r;
+    YT* yr = y + (long long)row * d;
+#pragma unroll
+    for (int c = 0; c < kMaxVec; ++c) {
+      if ((c * 32 + lane) * 4 < d) {
+        const float4 ww = *reinterpret_cast<const float4*>(w + (c * 32 + lane) * 4);
+        float4 o;
+        o.x = ww.x * (v[c].x * r); o.y = ww.y * (v[c].y * r); o.z = ww.z * (v[c].z * r); o.w = ww.w * (v[c].w * r);
+        store4<YT>(yr + (c * 32 + lane) * 4, o);
+      }
+    }
+  }
+}
+
+// ---------------- RMS norm backward ----------------
+// dx = rstd * (g - xhat * mean(g * xhat)),  g = dy * w,  xhat = x * rstd;   dw += sum_rows dy * xhat
+template <typename XT, typename YT>
+__global__ void __launch_bounds__(kNormThreads)
+rms_norm_bwd_kernel(const YT* __restrict__ dy, const XT* __restrict__ x, const float* __restrict__ w,
+                    const float* __restrict__ rstd, XT* __restrict__ dx, float* __restrict__ dw, int N, int d) {
+  extern __shared__ float s_dw[];             // [d] block partial
+  const int lane = threadIdx.x & 31;
+  for (int c = threadIdx.x; c < d; c += kNormThreads) s_dw[c] = 0.f;
+  __syncthreads();
+  float4 acc[kMaxVec];
+#pragma unroll
+  for (int c = 0; c < kMaxVec; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int row = blockIdx.x * (kNormThreads / 32) + (threadIdx.x >> 5); row < N; row += gridDim.x * (kNormThreads / 32)) {
+    const float r = rstd[row];
+    const XT* xr = x + (long long)row * d;
+    const YT* gr = dy + (long long)row * d;
+    float4 xh[kMaxVec], g[kMaxVec];
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < kMaxVec; ++c) {
+      if ((c * 32 + lane) * 4 < d) {
+        const int col = (c * 32 + lane) * 4;
+        const float4 xv = load4<XT>(xr + col);
+        const float4 gy = load4<YT>(gr + col);
+        const float4 ww = *reinterpret_cast<const float4*>(w + col);
+        xh[c] = make_float4(xv.x * r, xv.y * r, xv.z * r, xv.w * r);
+        g[c] = make_float4(gy.x * ww.x, gy.y * ww.y, gy.z * ww.z, gy.w * ww.w);
+        dot += g[c].x * xh[c].x + g[c].y * xh[c].y + g[c].z * xh[c].z + g[c].w * xh[c].w;
+        acc[c].x += gy.x * xh[c].x; acc[c].y += gy.y * xh[c].y; acc[c].z += gy.z * xh[c].z; acc[c].w += gy.w * xh[c].w;
+      }
+    }
+    dot = warp_sum_n(dot) / (float)d;
+    XT* dr = dx + (long long)row * d;
+#pragma unroll
+    for (int c = 0; c < kMaxVec; ++c) {
+      if ((c * 32 + lane) * 4 < d) {
+        float4 o;
+        o.x = r * (g[c].x - xh[c].x * dot); o.y = r * (g[c].y - xh[c].y * dot);
+        o.z = r * (g[c].z - xh[c].z * dot); o.w = r * (g[c].w - xh[c].w * dot);
+        store4<XT>(dr + (c * 32 + lane) * 4, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < kMaxVec; ++c) {
+    if ((c * 32 + lane) * 4 < d) {
+      const int col = (c * 32 + lane) * 4;
+      atomicAdd(s_dw + col, acc[c].x); atomicAdd(s_dw + col + 1, acc[c].y);
+      atomicAdd(s_dw + col + 2, acc[c].z); atomicAdd(s_dw + col + 3, acc[c].w);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += kNormThreads) atomicAdd(dw + c, s_dw[c]);
+}
+
+// ---------------- out = hidden + dropout(update) ----------------
+template <typename UT>
+__global__ void __launch_bounds__(kNormThreads)
+residual_dropout_add_kernel(const float* __restrict__ hidden, const UT* __restrict__ upd, float* __restrict__ out,
+                            long long n8, uint32_t thr16, float scale, uint64_t seed, uint64_t offset) {
+  for (long long i = (long long)blockIdx.x * kNormThreads + threadIdx.x; i < n8; i += (long long)gridDim.x * kNormThreads) {
+    f8 h = Vec8<float>::load_stream(hidden + i * 8);
+    f8 u = Vec8<UT>::load_stream(upd + i * 8);
+    if (thr16) {
+      const uint32_t m = dropout_keep8(seed, offset, (uint64_t)i * 8, thr16);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) h.v[j] += ((m >> j) & 1u) ? u.v[j] * scale : 0.f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) h.v[j] += u.v[j];
+    }
+    Vec8<float>::store(out + i * 8, h);
+  }
+}
+// d_update = d_out * mask * scale (cast to the update's dtype); d_hidden is d_out itself.
+template <typename UT>
+__global__ void __launch_bounds__(kNormThreads)
+residual_dropout_bwd_kernel(const float* __restrict__ d_out, UT* __restrict__ d_upd, long long n8, uint32_t thr16,
+                            float scale, uint64_t seed, uint64_t offset) {
+  for (long long i = (long long)blockIdx.x * kNormThreads + threadIdx.x; i < n8; i += (long long)gridDim.x * kNormThreads) {
+    f8 g = Vec8<float>::load_stream(d_out + i * 8);
+    if (thr16) {
+      const uint32_t m = dropout_keep8(seed, offset, (uint64_t)i * 8, thr16);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g.v[j] = ((m >> j) & 1u) ? g.v[j] * scale : 0.f;
+    }
+    Vec8<UT>::store(d_upd + i * 8, g);
+  }
+}
+
+// ---------------- y = dropout(relu(x)) in place-able form; backward needs only y ----------------
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads)
+relu_dropout_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long n8, uint32_t thr16, float scale,
+                        uint64_t seed, uint64_t offset) {
+  for (long long i = (long long)blockIdx.x * kNormThreads + threadIdx.x; i < n8; i += (long long)gridDim.x * kNormThreads) {
+    f8 v = Vec8<T>::load_stream(x + i * 8);
+    uint32_t m = 0xffu;
+    if (thr16) m = dropout_keep8(seed, offset, (uint64_t)i * 8, thr16);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v.v[j] = (((m >> j) & 1u) && v.v[j] > 0.f) ? v.v[j] * scale : 0.f;
+    Vec8<T>::store(y + i * 8, v);
+  }
+}
+// dx = (y != 0) ? dy * scale : 0     (y != 0 <=> x > 0 and kept)
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads)
+relu_dropout_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, long long n8, float scale) {
+  for (long long i = (long long)blockIdx.x * kNormThreads + threadIdx.x; i < n8; i += (long long)gridDim.x * kNormThreads) {
+    f8 g = Vec8<T>::load_stream(dy + i * 8);
+    f8 v = Vec8<T>::load_stream(y + i * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g.v[j] = (v.v[j] != 0.f) ? g.v[j] * scale : 0.f;
+    Vec8<T>::store(dx + i * 8, g);
+  }
+}
+
+static int ew_grid(long long n8) {
+  long long need = (n8 + kNormThreads - 1) / kNormThreads;
+  long long cap = (long long)num_sms() * 8;
+  return (int)(need < cap ? (need < 1 ? 1 : need) : cap);
+}
+static void drop_consts(float p, uint32_t& thr16, float& scale) {
+  thr16 = p > 0.f ? (uint32_t)lrintf(p * 65536.f) : 0u;
+  scale = thr16 ? 65536.f / (65536.f - (float)thr16) : 1.f;
+}
+
+}  // namespace pvqa
+
+using namespace pvqa;
+
+extern "C" int pvqa_rms_norm_fwd(const void* x, const float* w, void* y, float* rstd, int64_t N, int64_t d,
+                                 float eps, int x_dtype, int y_dtype, void* stream) {
+  PVQA_REQUIRE(N >= 0 && d > 0, PVQA_ERR_SHAPE, "rms_norm_fwd: bad dimension");
+  PVQA_REQUIRE(d % 4 == 0 && d <= 128 * kMaxVec, PVQA_ERR_SHAPE,
+               "rms_norm_fwd: d=%lld must be a multiple of 4 and <= %d", (long long)d, 128 * kMaxVec);
+  if (N == 0) return PVQA_OK;
+  PVQA_REQUIRE(x && w && y, PVQA_ERR_NULL, "rms_norm_fwd: NULL pointer");
+  PVQA_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y), PVQA_ERR_ALIGN, "rms_norm_fwd: 16-byte alignment required");
+  const int warps = kNormThreads / 32;
+  long long need = (N + warps - 1) / warps, cap = (long long)num_sms() * 8;
+  const int grid = (int)(need < cap ? need : cap);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x_dtype == PVQA_F32 && y_dtype == PVQA_BF16)
+    rms_norm_fwd_kernel<float, __nv_bfloat16><<<grid, kNormThreads, 0, st>>>((const float*)x, w, (__nv_bfloat16*)y, rstd, (int)N, (int)d, eps);
+  else if (x_dtype == PVQA_F32 && y_dtype == PVQA_F32)
+    rms_norm_fwd_kernel<float, float><<<grid, kNormThreads, 0, st>>>((const float*)x, w, (float*)y, rstd, (int)N, (int)d, eps);
+  else if (x_dtype == PVQA_BF16 && y_dtype == PVQA_BF16)
+    rms_norm_fwd_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, kNormThreads, 0, st>>>((const __nv_bfloat16*)x, w, (__nv_bfloat16*)y, rstd, (int)N, (int)d, eps);
+  else
+    return fail(PVQA_ERR_DTYPE, "rms_norm_fwd: unsupported dtype combination");
+  count_launch();
+  PVQA_CHECK_LAUNCH("rms_norm_fwd");
+  return PVQA_OK;
+}
+
+extern "C" int pvqa_rms_norm_bwd(const void* dy, const void* x, const float* w, const float* rstd, void* dx,
+                                 float* dw /* accumulated */, int64_t N, int64_t d, int x_dtype, int y_dtype,
+                                 void* stream) {
+  PVQA_REQUIRE(N >= 0 && d > 0, PVQA_ERR_SHAPE, "rms_norm_bwd: bad dimension");
+  PVQA_REQUIRE(d % 4 == 0 && d <= 128 * kMaxVec, PVQA_ERR_SHAPE, "rms_norm_bwd: d must be a multiple of 4 and <= %d", 128 * kMaxVec);
+  if (N == 0) return PVQA_OK;
+  PVQA_REQUIRE(dy && x && w && rstd && dx && dw, PVQA_ERR_NULL, "rms_norm_bwd: NULL pointer");
+  PVQA_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(w) && aligned16(dx), PVQA_ERR_ALIGN, "rms_norm_bwd: 16-byte alignment required");
+  const int warps = kNormThreads / 32;
+  long long need = (N + warps - 1) / warps, cap = (long long)num_sms() * 2;
+  const int grid = (int)(need < cap ? need : cap);
+  const size_t smem = (size_t)d * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x_dtype == PVQA_F32 && y_dtype == PVQA_BF16)
+    rms_norm_bwd_kernel<float, __nv_bfloat16><<<grid, kNormThreads, smem, st>>>((const __nv_bfloat16*)dy, (const float*)x, w, rstd, (float*)dx, dw, (int)N, (int)d);
+  else if (x_dtype == PVQA_F32 && y_dtype == PVQA_F32)
+    rms_norm_bwd_kernel<float, float><<<grid, kNormThreads, smem, st>>>((const float*)dy, (const float*)x, w, rstd, (float*)dx, dw, (int)N, (int)d);
+  else if (x_dtype == PVQA_BF16 && y_dtype == PVQA_BF16)
+    rms_norm_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, kNormThreads, smem, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, w, rstd, (__nv_bfloat16*)dx, dw, (int)N, (int)d);
+  else
+    return fail(PVQA_ERR_DTYPE, "rms_norm_bwd: unsupported dtype combination");
+  count_launch();
+  PVQA_CHECK_LAUNCH("rms_norm_bwd");
+  return PVQA_OK;
+}
+
+extern "C" int pvqa_residual_dropout_add(const float* hidden, const void* update, float* out, int64_t n,
+                                         int upd_dtype, float dropout_p, uint64_t seed, uint64_t offset, void* stream) {
+  PVQA_REQUIRE(n >= 0 && n % 8 == 0, PVQA_ERR_SHAPE, "residual_dropout_add: element count must be a multiple of 8");
+  PVQA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, PVQA_ERR_SHAPE, "residual_dropout_add: dropout_p must be in [0,1)");
+  if (n == 0) return PVQA_OK;
+  PVQA_REQUIRE(hidden && update && out, PVQA_ERR_NULL, "residual_dropout_add: NULL pointer");
+  PVQA_REQUIRE(aligned16(hidden) && aligned16(update) && aligned16(out), PVQA_ERR_ALIGN, "residual_dropout_add: 16-byte alignment required");
+  uint32_t thr; float sc;
+  drop_consts(dropout_p, thr, sc);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (upd_dtype == PVQA_BF16)
+    residual_dropout_add_kernel<__nv_bfloat16><<<ew_grid(n / 8), kNormThreads, 0, st>>>(hidden, (const __nv_bfloat16*)update, out, n / 8, thr, sc, seed, offset);
+  else if (upd_dtype == PVQA_F32)
+    residual_dropout_add_kernel<float><<<ew_grid(n / 8), kNormThreads, 0, st>>>(hidden, (const float*)update, out, n / 8, thr, sc, seed, offset);
+  else
+    return fail(PVQA_ERR_DTYPE, "residual_dropout_add: bad dtype");
+  count_launch();
+  PVQA_CHECK_LAUNCH("residual_dropout_add");
+  return PVQA_OK;
+}
+
+extern "C" int pvqa_residual_dropout_bwd(const float* d_out, void* d_update, int64_t n, int upd_dtype, float dropout_p,
+                                         uint64_t seed, uint64_t offset, void* stream) {
+  PVQA_REQUIRE(n >= 0 && n % 8 == 0, PVQA_ERR_SHAPE, "residual_dropout_bwd: element count must be a multiple of 8");
+  PVQA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, PVQA_ERR_SHAPE, "residual_dropout_bwd: dropout_p must be in [0,1)");
+  if (n == 0) return PVQA_OK;
+  PVQA_REQUIRE(d_out && d_update, PVQA_ERR_NULL, "residual_dropout_bwd: NULL pointer");
+  PVQA_REQUIRE(aligned16(d_out) && aligned16(d_update), PVQA_ERR_ALIGN, "residual_dropout_bwd: 16-byte alignment required");
+  uint32_t thr; float sc;
+  drop_consts(dropout_p, thr, sc);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (upd_dtype == PVQA_BF16)
+    residual_dropout_bwd_kernel<__nv_bfloat16><<<ew_grid(n / 8), kNormThreads, 0, st>>>(d_out, (__nv_bfloat16*)d_update, n / 8, thr, sc, seed, offset);
+  else if (upd_dtype == PVQA_F32)
+    residual_dropout_bwd_kernel<float><<<ew_grid(n / 8), kNormThreads, 0, st>>>(d_out, (float*)d_update, n / 8, thr, sc, seed, offset);
+  else
+    return fail(PVQA_ERR_DTYPE, "residual_dropout_bwd: bad dtype");
+  count_launch();
+  PVQA_CHECK_LAUNCH("residual_dropout_bwd");
+  return PVQA_OK;
+}
+
+extern "C" int pvqa_relu_dropout_fwd(const void* x, void* y, int64_t n, int dtype, float dropout_p, uint64_t seed,
+                                     uint64_t offset, void* stream) {
+  PVQA_REQUIRE(n >= 0 && n % 8 == 0, PVQA_ERR_SHAPE, "relu_dropout_fwd: element count must be a multiple of 8");
+  PVQA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, PVQA_ERR_SHAPE, "relu_dropout_fwd: dropout_p must be in [0,1)");
+  if (n == 0) return PVQA_OK;
+  PVQA_REQUIRE(x && y, PVQA_ERR_NULL, "relu_dropout_fwd: NULL pointer");
+  PVQA_REQUIRE(aligned16(x) && aligned16(y), PVQA_ERR_ALIGN, "relu_dropout_fwd: 16-byte alignment required");
+  uint32_t thr; float sc;
+  drop_consts(dropout_p, thr, sc);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == PVQA_BF16)
+    relu_dropout_fwd_kernel<__nv_bfloat16><<<ew_grid(n / 8), kNormThreads, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n / 8, thr, sc, seed, offset);
+  else if (dtype == PVQA_F32)
+    relu_dropout_fwd_kernel<float><<<ew_grid(n / 8), kNormThreads, 0, st>>>((const float*)x, (float*)y, n / 8, thr, sc, seed, offset);
+  else
+    return fail(PVQA_ERR_DTYPE, "relu_dropout_fwd: bad dtype");
+  count_launch();
+  PVQA_CHECK_LAUNCH("relu_dropout_fwd");
+  return PVQA_OK;
+}
+
+extern "C" int pvqa_relu_dropout_bwd(const void* dy, const void* y, void* dx, int64_t n, int dtype, float dropout_p,
+                                     void* stream) {
+  PVQA_REQUIRE(n >= 0 && n % 8 == 0, PVQA_ERR_SHAPE, "relu_dropout_bwd: element count must be a multiple of 8");
+  PVQA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, PVQA_ERR_SHAPE, "relu_dropout_bwd: dropout_p must be in [0,1)");
+  if (n == 0) return PVQA_OK;
+  PVQA_REQUIRE(dy && y && dx, PVQA_ERR_NULL, "relu_dropout_bwd: NULL pointer");
+  PVQA_REQUIRE(aligned16(dy) && aligned16(y) && aligned16(dx), PVQA_ERR_ALIGN, "relu_dropout_bwd: 16-byte alignment required");
+  uint32_t thr; float sc;
+  drop_consts(dropout_p, thr, sc);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == PVQA_BF16)
+    relu_dropout_bwd_kernel<__nv_bfloat16><<<ew_grid(n / 8), kNormThreads, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (__nv_bfloat16*)dx, n / 8, sc);
+  else if (dtype == PVQA_F32)
+    relu_dropout_bwd_kernel<float><<<ew_grid(n / 8), kNormThreads, 0, st>>>((const float*)dy, (const float*)y, (float*)dx, n / 8, sc);
+  else
+    return fail(PVQA_ERR_DTYPE, "relu_dropout_bwd: bad dtype");
+  count_launch();
+  PVQA_CHECK_LAUNCH("relu_dropout_bwd");
+  return PVQA_OK;
+}

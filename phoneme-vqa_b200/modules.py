@@ -23,11 +23,113 @@ import torch.nn.functional as F
 from . import ops
 
 
+class _ShadowWeights:
+    """Low-precision shadows of the fp32 master weights used by the bf16 compute path.
+
+    A shadow may be the row-wise concatenation of several masters (packed q|k|v projection).
+    Masters are compared by `_version` (bumped by the optimizer's in-place update); when any
+    entry is stale ALL registered shadows are refreshed with one multi-tensor copy, so a training
+    step pays one cast launch instead of one per linear per direction."""
+
+    def __init__(self):
+        self.entries = {}     # key -> dict(masters, shadow, views, versions)
+
+    def get(self, masters, dtype):
+        key = tuple(id(m) for m in masters) + (dtype,)
+        e = self.entries.get(key)
+        if e is None or e["shadow"].device != masters[0].device or any(r() is not m for r, m in zip(e["refs"], masters)):
+            import weakref
+            rows = sum(m.shape[0] for m in masters)
+            shadow = torch.empty((rows,) + tuple(masters[0].shape[1:]), dtype=dtype, device=masters[0].device)
+            views, off = [], 0
+            for m in masters:
+                views.append(shadow[off:off + m.shape[0]])
+                off += m.shape[0]
+            e = {"refs": [weakref.ref(m) for m in masters], "shadow": shadow, "views": views, "versions": None}
+            self.entries[key] = e
+        if e["versions"] != tuple(m._version for m in masters):
+            self.refresh()
+        return e["shadow"]
+
+    @torch.no_grad()
+    def refresh(self):
+        dst, src = [], []
+        dead = []
+        for key, e in self.entries.items():
+            ms = [r() for r in e["refs"]]
+            if any(m is None for m in ms):
+                dead.append(key)
+                continue
+            ver = tuple(m._version for m in ms)
+            if e["versions"] != ver:
+                dst.extend(e["views"])
+                src.extend(m.detach() for m in ms)
+                e["versions"] = ver
+        for key in dead:
+            del self.entries[key]
+        if dst:
+            torch._foreach_copy_(dst, src)
+
+
+SHADOWS = _ShadowWeights()
+
+
+class _LinearLP(torch.autograd.Function):
+    """y = x W^T + b with W, b given as low-precision shadows; weight/bias gradients are produced
+    directly in fp32 (bf16 x bf16 -> fp32 GEMM output) and routed to the fp32 masters."""
+
+    @staticmethod
+    def forward(ctx, x, w_lp, b_lp, n_masters, *masters):
+        ctx.save_for_backward(x, w_lp)
+        ctx.n_w = n_masters
+        ctx.has_bias = b_lp is not None
+        ctx.rows = [m.shape[0] for m in masters[:n_masters]]
+        return F.linear(x, w_lp, b_lp)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w_lp = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        x2 = x.reshape(-1, x.shape[-1])
+        dx = (dy2 @ w_lp).view(x.shape) if ctx.needs_input_grad[0] else None
+        dW = torch.mm(dy2.t(), x2, out_dtype=torch.float32)
+        grads, off = [], 0
+        for r in ctx.rows:
+            grads.append(dW[off:off + r])
+            off += r
+        if ctx.has_bias:
+            db = dy2.sum(0, dtype=torch.float32)
+            off = 0
+            for r in ctx.rows:
+                grads.append(db[off:off + r])
+                off += r
+        return (dx, None, None, None, *grads)
+
+
+def _lin_multi(x, weights, biases=None):
+    """Linear with the row-wise concatenation of `weights` (and `biases`); fp32 masters."""
+    if x.dtype == weights[0].dtype:
+        w = weights[0] if len(weights) == 1 else torch.cat(list(weights), dim=0)
+        b = None if biases is None else (biases[0] if len(biases) == 1 else torch.cat(list(biases), dim=0))
+        return F.linear(x, w, b)
+    w_lp = SHADOWS.get(list(weights), x.dtype)
+    b_lp = None if biases is None else SHADOWS.get(list(biases), x.dtype)
+    masters = list(weights) + (list(biases) if biases is not None else [])
+    return _LinearLP.apply(x, w_lp, b_lp, len(weights), *masters)
+
+
 def _lin(x, weight, bias=None):
     """F.linear in x's dtype with fp32 master weights."""
-    w = weight if weight.dtype == x.dtype else weight.to(x.dtype)
-    b = None if bias is None else (bias if bias.dtype == x.dtype else bias.to(x.dtype))
-    return F.linear(x, w, b)
+    return _lin_multi(x, [weight], None if bias is None else [bias])
+
+
+def _lin_rows(x, weight, bias, r0, r1):
+    """Linear with rows [r0, r1) of a packed master weight/bias (nn.MultiheadAttention in_proj slices)."""
+    if x.dtype == weight.dtype:
+        return F.linear(x, weight[r0:r1], bias[r0:r1])
+    w_lp = SHADOWS.get([weight], x.dtype)[r0:r1]
+    b_lp = SHADOWS.get([bias], x.dtype)[r0:r1]
+    return _LinearLP.apply(x, w_lp, b_lp, 1, weight[r0:r1], bias[r0:r1])
 
 
 # ----------------------------------------------------------------------------------
@@ -173,14 +275,12 @@ class T5Attention(nn.Module):
         H, D = self.n_heads, self.key_value_proj_dim
         p_drop = self.dropout if self.training else 0.0
         if kv is None:
-            w = torch.cat([self.q.weight, self.k.weight, self.v.weight], dim=0)
-            qkv = _lin(x, w).view(B, S, 3, H, D)
+            qkv = _lin_multi(x, [self.q.weight, self.k.weight, self.v.weight]).view(B, S, 3, H, D)
             o = ops.attention_self(qkv, scale=1.0, rel_bias=rel_bias, key_add=key_add, causal=causal,
                                    dropout_p=p_drop, dense_bias=dense_bias)
         else:
             q = _lin(x, self.q.weight).view(B, S, H, D)
-            w = torch.cat([self.k.weight, self.v.weight], dim=0)
-            kvp = _lin(kv, w).view(B, kv.shape[1], 2, H, D)
+            kvp = _lin_multi(kv, [self.k.weight, self.v.weight]).view(B, kv.shape[1], 2, H, D)
             o = ops.attention_cross(q, kvp, scale=1.0, rel_bias=rel_bias, key_add=key_add, dropout_p=p_drop)
         return _lin(o.reshape(B, S, H * D), self.o.weight)
 
@@ -221,8 +321,11 @@ class T5DenseActDense(nn.Module):
 
     def forward(self, x):
         h = _lin(x, self.wi.weight)
-        h = F.relu(h) if self.act_name == "relu" else F.gelu(h, approximate="tanh" if self.act_name == "gelu_new" else "none")
-        h = F.dropout(h, self.dropout.p, self.training)
+        if self.act_name == "relu":
+            h = ops.relu_dropout(h, self.dropout.p, self.training)
+        else:
+            h = F.gelu(h, approximate="tanh" if self.act_name == "gelu_new" else "none")
+            h = F.dropout(h, self.dropout.p, self.training)
         return _lin(h, self.wo.weight)
 
 
@@ -402,14 +505,14 @@ class TransformerDecoderLayer(nn.Module):
         x = F.layer_norm(ops.residual_dropout_add(x, a, self.p, self.training), (d,), self.norm1.weight,
                          self.norm1.bias, self.norm1.eps)
         xc = x.to(compute_dtype)
-        q = _lin(xc, ca.in_proj_weight[:d], ca.in_proj_bias[:d]).view(B, T, H, D)
-        kv = _lin(memory, ca.in_proj_weight[d:], ca.in_proj_bias[d:]).view(B, memory.shape[1], 2, H, D)
+        q = _lin_rows(xc, ca.in_proj_weight, ca.in_proj_bias, 0, d).view(B, T, H, D)
+        kv = _lin_rows(memory, ca.in_proj_weight, ca.in_proj_bias, d, 3 * d).view(B, memory.shape[1], 2, H, D)
         c = ops.attention_cross(q, kv, scale=scale, rel_bias=None, key_add=memory_key_add, dropout_p=p_attn)
         c = _lin(c.reshape(B, T, d), ca.out_proj.weight, ca.out_proj.bias)
         x = F.layer_norm(ops.residual_dropout_add(x, c, self.p, self.training), (d,), self.norm2.weight,
                          self.norm2.bias, self.norm2.eps)
         xc = x.to(compute_dtype)
-        h = F.dropout(F.relu(_lin(xc, self.linear1.weight, self.linear1.bias)), self.p, self.training)
+        h = ops.relu_dropout(_lin(xc, self.linear1.weight, self.linear1.bias), self.p, self.training)
         h = _lin(h, self.linear2.weight, self.linear2.bias)
         x = F.layer_norm(ops.residual_dropout_add(x, h, self.p, self.training), (d,), self.norm3.weight,
                          self.norm3.bias, self.norm3.eps)

@@ -269,20 +269,117 @@ def embed_target(labels, onset_weight, rhyme_weight, tone_weight, pos_embedding,
 
 
 # ----------------------------------------------------------------------------------
-# Normalisation / residual glue (plain torch on the device; fusion candidates)
+# Fused glue: RMS norm, residual + dropout, relu + dropout, bf16 linear with fp32 weight gradients
 # ----------------------------------------------------------------------------------
+class _RmsNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, eps, out_dtype):
+        lib = _lib.load()
+        _need_cuda(x, weight)
+        shape = x.shape
+        d = shape[-1]
+        x2 = x.reshape(-1, d).contiguous()
+        N = x2.shape[0]
+        w = weight.to(torch.float32).contiguous()
+        y = torch.empty((N, d), dtype=out_dtype, device=x.device)
+        rstd = torch.empty(N, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device), _prof("rms_norm_fwd"):
+            check(lib.pvqa_rms_norm_fwd(_p(x2), _p(w), _p(y), _p(rstd), N, d, float(eps), _dt(x2.dtype), _dt(out_dtype),
+                                        _stream()), "pvqa_rms_norm_fwd")
+        ctx.save_for_backward(x2, w, rstd)
+        ctx.meta = (shape, weight.dtype)
+        return y.view(shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x2, w, rstd = ctx.saved_tensors
+        shape, w_dtype = ctx.meta
+        N, d = x2.shape
+        dy2 = dy.reshape(N, d).contiguous()
+        dx = torch.empty_like(x2)
+        dw = torch.zeros(d, dtype=torch.float32, device=x2.device)
+        with torch.cuda.device(x2.device), _prof("rms_norm_bwd"):
+            check(lib.pvqa_rms_norm_bwd(_p(dy2), _p(x2), _p(w), _p(rstd), _p(dx), _p(dw), N, d, _dt(x2.dtype),
+                                        _dt(dy2.dtype), _stream()), "pvqa_rms_norm_bwd")
+        return dx.view(shape), dw.to(w_dtype), None, None
+
+
 def rms_norm(x, weight, eps, out_dtype):
     """T5LayerNorm (modeling_t5.py:46-70): fp32 variance, no mean subtraction, no bias."""
-    xf = x.float()
-    var = xf.pow(2).mean(-1, keepdim=True)
-    return (weight.float() * (xf * torch.rsqrt(var + eps))).to(out_dtype)
+    if x.dtype == torch.bfloat16:
+        out_dtype = torch.bfloat16
+    return _RmsNorm.apply(x, weight, eps, out_dtype)
+
+
+class _ResidualDropoutAdd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, hidden, update, p):
+        lib = _lib.load()
+        _need_cuda(hidden, update)
+        hidden = hidden.contiguous()
+        update = update.contiguous()
+        n = hidden.numel()
+        out = torch.empty_like(hidden)
+        seed, off = _Rng.next(n) if p > 0 else (0, 0)
+        with torch.cuda.device(hidden.device), _prof("residual_dropout_add"):
+            check(lib.pvqa_residual_dropout_add(_p(hidden), _p(update), _p(out), n, _dt(update.dtype), float(p), seed,
+                                                off, _stream()), "pvqa_residual_dropout_add")
+        ctx.meta = (float(p), seed, off, update.dtype, update.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        p, seed, off, udt, ushape = ctx.meta
+        d_out = d_out.contiguous()
+        d_upd = torch.empty(ushape, dtype=udt, device=d_out.device)
+        with torch.cuda.device(d_out.device), _prof("residual_dropout_bwd"):
+            check(lib.pvqa_residual_dropout_bwd(_p(d_out), _p(d_upd), d_out.numel(), _dt(udt), p, seed, off, _stream()),
+                  "pvqa_residual_dropout_bwd")
+        return d_out, d_upd, None
 
 
 def residual_dropout_add(hidden, update, p, training):
-    """hidden (fp32 residual stream) + dropout(update)."""
-    if training and p > 0.0:
-        update = torch.nn.functional.dropout(update, p, True)
-    return hidden + update.to(hidden.dtype)
+    """hidden (fp32 residual stream) + dropout(update) in one pass."""
+    p = float(p) if training else 0.0
+    if hidden.dtype != torch.float32 or hidden.numel() % 8 != 0 or hidden.shape != update.shape:
+        raise TypeError("residual_dropout_add expects an fp32 residual stream with numel % 8 == 0")
+    return _ResidualDropoutAdd.apply(hidden, update, p)
+
+
+class _ReluDropout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p):
+        lib = _lib.load()
+        _need_cuda(x)
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        seed, off = _Rng.next(x.numel()) if p > 0 else (0, 0)
+        with torch.cuda.device(x.device), _prof("relu_dropout_fwd"):
+            check(lib.pvqa_relu_dropout_fwd(_p(x), _p(y), x.numel(), _dt(x.dtype), float(p), seed, off, _stream()),
+                  "pvqa_relu_dropout_fwd")
+        ctx.save_for_backward(y)
+        ctx.p = float(p)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        (y,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(y)
+        with torch.cuda.device(y.device), _prof("relu_dropout_bwd"):
+            check(lib.pvqa_relu_dropout_bwd(_p(dy), _p(y), _p(dx), y.numel(), _dt(y.dtype), ctx.p, _stream()),
+                  "pvqa_relu_dropout_bwd")
+        return dx, None
+
+
+def relu_dropout(x, p, training):
+    """dropout(relu(x)) in one pass (T5DenseActDense / TransformerDecoderLayer feed-forward)."""
+    if x.numel() % 8 != 0:
+        raise TypeError("relu_dropout expects numel % 8 == 0")
+    return _ReluDropout.apply(x, float(p) if training else 0.0)
 
 
 # ----------------------------------------------------------------------------------

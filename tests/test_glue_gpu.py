@@ -1,0 +1,87 @@
+"""Fused glue kernels (RMS norm, residual+dropout, relu+dropout, shadow-weight linear) vs torch math."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("N,d,ydt", [(37, 768, torch.bfloat16), (5, 192, torch.float32), (4096, 1024, torch.bfloat16),
+                                     (3, 512, torch.float32)])
+def test_rms_norm_fwd_bwd(N, d, ydt):
+    from phoneme_vqa_b200 import ops
+    g = torch.Generator().manual_seed(N)
+    x = torch.randn(N, d, generator=g).to(DEV).requires_grad_(True)
+    w = (1 + 0.1 * torch.randn(d, generator=g)).to(DEV).requires_grad_(True)
+    go = torch.randn(N, d, generator=g).to(DEV).to(ydt)
+    y = ops.rms_norm(x, w, 1e-6, ydt)
+    y.backward(go)
+    xr = x.detach().clone().requires_grad_(True)
+    wr = w.detach().clone().requires_grad_(True)
+    var = xr.pow(2).mean(-1, keepdim=True)
+    yr = wr * (xr * torch.rsqrt(var + 1e-6))          # HF T5LayerNorm
+    yr.backward(go.float())
+    tol = 1e-5 if ydt == torch.float32 else 1e-2
+    torch.testing.assert_close(y.float(), yr.detach(), rtol=tol, atol=tol)
+    torch.testing.assert_close(x.grad, xr.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(w.grad, wr.grad, rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("udt", [torch.float32, torch.bfloat16])
+def test_residual_dropout_add(udt):
+    from phoneme_vqa_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    h = torch.randn(8, 50, 768, generator=g).to(DEV).requires_grad_(True)
+    u = (torch.randn(8, 50, 768, generator=g) + 3.0).to(DEV).to(udt).requires_grad_(True)
+    out = ops.residual_dropout_add(h, u, 0.1, training=False)
+    torch.testing.assert_close(out, h.detach() + u.detach().float())
+    ops.manual_seed(5)
+    out = ops.residual_dropout_add(h, u, 0.1, training=True)
+    delta = out.detach() - h.detach()
+    kept = delta != 0
+    assert abs(kept.float().mean().item() - 0.9) < 5e-3
+    torch.testing.assert_close(delta[kept], (u.detach().float() / 0.9)[kept], rtol=2e-3, atol=2e-3)
+    out.sum().backward()
+    torch.testing.assert_close(h.grad, torch.ones_like(h))
+    torch.testing.assert_close(u.grad.float(), kept.float() / 0.9, rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_relu_dropout(dt):
+    from phoneme_vqa_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(64, 3072, generator=g).to(DEV).to(dt).requires_grad_(True)
+    y = ops.relu_dropout(x, 0.1, training=False)
+    assert torch.equal(y, torch.relu(x.detach()))
+    ops.manual_seed(9)
+    y = ops.relu_dropout(x, 0.1, training=True)
+    pos = x.detach() > 0
+    kept = y != 0
+    assert not (kept & ~pos).any()
+    assert abs(kept[pos].float().mean().item() - 0.9) < 1e-2
+    torch.testing.assert_close(y[kept].float(), (x.detach().float() / 0.9)[kept], rtol=1e-2, atol=1e-2)
+    go = torch.randn(64, 3072, generator=g).to(DEV).to(dt)
+    y.backward(go)
+    torch.testing.assert_close(x.grad.float(), (go.float() / 0.9) * kept.float(), rtol=1e-2, atol=1e-2)
+
+
+def test_shadow_weight_linear_fp32_grads_and_refresh():
+    from phoneme_vqa_b200 import modules as M
+    torch.manual_seed(0)
+    lin_q, lin_k = torch.nn.Linear(64, 32).to(DEV), torch.nn.Linear(64, 48).to(DEV)
+    x = torch.randn(10, 64, device=DEV).bfloat16().requires_grad_(True)
+    y = M._lin_multi(x, [lin_q.weight, lin_k.weight], [lin_q.bias, lin_k.bias])
+    assert y.dtype == torch.bfloat16 and y.shape == (10, 80)
+    ref = torch.nn.functional.linear(x.float(), torch.cat([lin_q.weight, lin_k.weight]).bfloat16().float(),
+                                     torch.cat([lin_q.bias, lin_k.bias]).bfloat16().float())
+    torch.testing.assert_close(y.float(), ref, rtol=2e-2, atol=2e-2)
+    go = torch.randn_like(y)
+    y.backward(go)
+    assert lin_q.weight.grad.dtype == torch.float32
+    torch.testing.assert_close(lin_q.weight.grad, (go.float().t() @ x.detach().float())[:32], rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(lin_k.bias.grad, go.float().sum(0)[32:], rtol=1e-3, atol=1e-3)
+    # an optimizer-style in-place update must invalidate the shadow
+    with torch.no_grad():
+        lin_q.weight.add_(1.0)
+    y2 = M._lin_multi(x, [lin_q.weight, lin_k.weight], [lin_q.bias, lin_k.bias])
+    assert (y2[:, :32].float() - y[:, :32].float()).abs().max() > 0.1
