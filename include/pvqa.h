@@ -194,6 +194,7 @@ int pvqa_attn_fwd(const void* q, const void* k, const void* v, void* o, float* l
 int pvqa_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
                   const float* lse, const float* rel_bias, const float* key_add,
                   float* dq_accum, void* dk, void* dv, float* d_rel_bias,
+                  float* delta_ws /* (B,H,Sq) fp32 workspace: rowsum(dO*O) */,
                   int64_t B, int64_t H, int64_t Sq, int64_t Sk, int64_t D,
                   int64_t q_stride_b, int64_t q_stride_s, int64_t q_stride_h,
                   int64_t k_stride_b, int64_t k_stride_s, int64_t k_stride_h,

@@ -72,7 +72,7 @@ _SIGNATURES = {
     "pvqa_phoneme_head_ce_fwd": (c_int, [_vp, _vp, _i64] + [_vp] * 12 + _i64x(8) + [c_int, c_int, _vp]),
     "pvqa_phoneme_head_ce_bwd": (c_int, [_vp, _vp, _i64] + [_vp] * 12 + _i64x(8) + [c_int, c_int, _vp]),
     "pvqa_attn_fwd": (c_int, [_vp] * 7 + _i64x(5) + _i64x(12) + [_f, c_int, _f, c_uint64, c_uint64, _vp]),
-    "pvqa_attn_bwd": (c_int, [_vp] * 12 + _i64x(5) + _i64x(21) + [_f, c_int, _f, c_uint64, c_uint64, _vp]),
+    "pvqa_attn_bwd": (c_int, [_vp] * 13 + _i64x(5) + _i64x(21) + [_f, c_int, _f, c_uint64, c_uint64, _vp]),
     "pvqa_attn_f32_fwd": (c_int, [_vp] * 7 + _i64x(5) + _i64x(12) + [_f, c_int, _f, c_uint64, c_uint64, _vp]),
     "pvqa_rms_norm_fwd": (c_int, [_vp] * 4 + _i64x(2) + [_f, c_int, c_int, _vp]),
     "pvqa_rms_norm_bwd": (c_int, [_vp] * 6 + _i64x(2) + [c_int, c_int, _vp]),

@@ -441,9 +441,10 @@ def attention_bwd_raw(q, k, v, o, d_o, lse, scale, rel_bias, key_add, causal, dk
         d_o = d_o.contiguous()
     if q.dtype == torch.bfloat16:
         dq = torch.zeros((B, Sq, H, D), dtype=torch.float32, device=dev)      # fp32 accumulator (RED target)
+        ws = torch.empty((B, H, Sq), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev), _prof(f"attn_bwd[Sq={Sq},Sk={Sk}]"):
             check(lib.pvqa_attn_bwd(_p(q), _p(k), _p(v), _p(o), _p(d_o), _p(lse), _p(rel_bias), _p(key_add),
-                                    _p(dq), _p(dk), _p(dv), _p(d_rel), B, H, Sq, Sk, D,
+                                    _p(dq), _p(dk), _p(dv), _p(d_rel), _p(ws), B, H, Sq, Sk, D,
                                     *_st3(q), *_st3(k), *_st3(v), *_st3(o), *_st3(d_o), *_st3(dk), *_st3(dv),
                                     float(scale), int(bool(causal)), float(drop[0]), int(drop[1]), int(drop[2]),
                                     _stream()), "pvqa_attn_bwd")

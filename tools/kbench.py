@@ -137,9 +137,55 @@ def bench_embed(B=64):
     return res
 
 
+def bench_attn(B=64, H=12, S=327, T=127, dropout=0.1, iters=10):
+    """tcgen05 attention kernels at the PhonoLaTr-base shapes; TFLOP/s against the measured bf16 peak.
+    flops: fwd 4*B*H*Sq*Sk*D, bwd 10*B*H*Sq*Sk*D (5 GEMMs), causal halves both."""
+    import math
+    from phoneme_vqa_b200 import ops
+    pk = peaks()
+    res = {}
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for name, Sq, Sk, causal, rel, scale in [("enc_self", S, S, False, True, 1.0), ("dec_self", T, T, True, False, 0.125),
+                                            ("dec_cross", T, S, False, False, 0.125)]:
+        q = (torch.randn(B, Sq, H, 64, device="cuda", generator=g) * 0.5).bfloat16()
+        kv = (torch.randn(B, Sk, 2, H, 64, device="cuda", generator=g) * 0.5).bfloat16()
+        k, v = kv[:, :, 0], kv[:, :, 1]
+        rb = torch.randn(H, Sq + Sk - 1, device="cuda", generator=g) if rel else None
+        ka = torch.zeros(B, Sk, device="cuda")
+        go = torch.randn(B, Sq, H, 64, device="cuda", generator=g).bfloat16()
+        for p in (0.0, dropout):
+            drop = (p, 1234, 0)
+            fwd = lambda: ops.attention_fwd_raw(q, k, v, scale, rb, ka, causal, drop)  # noqa: E731
+            o, lse = fwd()
+            dkv = torch.empty_like(kv)
+            bwd = lambda: ops.attention_bwd_raw(q, k, v, o, go, lse, scale, rb, ka, causal, dkv[:, :, 0], dkv[:, :, 1],  # noqa: E731
+                                                rel, drop)
+            ops.KernelTimer.reset(True)
+            for _ in range(3):
+                fwd(); bwd()
+            torch.cuda.synchronize()
+            ops.KernelTimer.reset(True)
+            for _ in range(iters):
+                flush_l2(); fwd(); flush_l2(); bwd()
+            torch.cuda.synchronize()
+            summ = ops.KernelTimer.summary()
+            ops.KernelTimer.reset(False)
+            fl = 4.0 * B * H * Sq * Sk * 64 * (0.5 if causal else 1.0)
+            for kname, (n, tot) in summ.items():
+                ms = tot / n
+                f = fl if "fwd" in kname else 2.5 * fl
+                res[f"{name}:{kname.split('[')[0]}:p={p}"] = {"ms": ms, "TFLOPs": f / ms / 1e9,
+                                                              "frac_of_bf16_peak": f / ms / 1e9 / pk["bf16_tflops"]}
+    return res
+
+
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
     out = {"peaks": peaks()}
     if which in ("embed", "all"):
         out.update(bench_embed())
+    if which in ("attn", "all"):
+        out.update(bench_attn())
+    if which == "attn_small":       # short run for ncu
+        out.update(bench_attn(B=8, iters=1))
     print(json.dumps(out, indent=1))
