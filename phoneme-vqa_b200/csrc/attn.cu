@@ -56,10 +56,10 @@ __device__ __forceinline__ uint4 keep_bytes16(uint64_t seed, uint64_t offset, ui
 constexpr int kFwdThreads = 256;
 constexpr uint32_t kTmemCols = 256;   // S: [0,128)  O_j: [128,192)   (power of two >= 192)
 constexpr int kOffQ = 0;
-constexpr int kOffK = kOffQ + kBM * kD * 2;            // 16 KB
-constexpr int kOffV = kOffK + kBN * kD * 2;            // 32 KB
-constexpr int kOffP = kOffV + kBN * kD * 2;            // 48 KB, 32 KB long (two [128][64] sub-tiles)
-constexpr int kOffBar = kOffP + kBM * kBN * 2;         // 80 KB
+constexpr int kOffKV = kOffQ + kBM * kD * 2;           // 16 KB: three rotating 16 KB buffers for K_j, V_j, K_{j+1}
+constexpr int kKVBuf = kBN * kD * 2;
+constexpr int kOffP = kOffKV + 3 * kKVBuf;             // 64 KB, 32 KB long (two [128][64] sub-tiles)
+constexpr int kOffBar = kOffP + kBM * kBN * 2;         // 96 KB
 constexpr int kOffXchg = kOffBar + 64;                 // [2][128] floats
 constexpr int kOffFloats = kOffXchg + 2 * kBM * 4;     // key_add (padded) then rel bias (padded)
 constexpr int kRelPad = 128;
@@ -85,10 +85,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + kOffBar);
-  uint64_t* bar_kv = bar_q + 1;
-  uint64_t* bar_s = bar_q + 2;
-  uint64_t* bar_o = bar_q + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 4);
+  uint64_t* bar_k = bar_q + 1;            // [2] by tile parity
+  uint64_t* bar_v = bar_q + 3;            // [2]
+  uint64_t* bar_s = bar_q + 5;
+  uint64_t* bar_o = bar_q + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 7);
   float* s_x = reinterpret_cast<float*>(smem + kOffXchg);
   const int n_tiles_all = (p.Sk + kBN - 1) / kBN;
   const int n_kpad = n_tiles_all * kBN;
@@ -104,7 +105,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (tid == 0) {
     tc05::prefetch_tmap(&tmQ); tc05::prefetch_tmap(&tmK); tc05::prefetch_tmap(&tmV);
-    tc05::mbar_init(bar_q, 1); tc05::mbar_init(bar_kv, 1); tc05::mbar_init(bar_s, 1); tc05::mbar_init(bar_o, 1);
+    tc05::mbar_init(bar_q, 1); tc05::mbar_init(bar_k, 1); tc05::mbar_init(bar_k + 1, 1);
+    tc05::mbar_init(bar_v, 1); tc05::mbar_init(bar_v + 1, 1); tc05::mbar_init(bar_s, 1); tc05::mbar_init(bar_o, 1);
     tc05::fence_barrier_init();
   }
   if (warp == 0) {
@@ -127,19 +129,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
 
+  int n_tiles = n_tiles_all;
+  if (p.causal) n_tiles = min(n_tiles, min(i0 + kBM - 1, p.Sq - 1) / kBN + 1);
+  // K_j lives in buffer (2j) % 3, V_j in (2j+1) % 3: K_{j+1} reuses V_{j-1}'s buffer, V_{j+1} reuses K_j's
   if (tid == 0) {
     tc05::mbar_expect_tx(bar_q, kBM * kD * 2);
     tc05::tma_load_4d(smem + kOffQ, &tmQ, bar_q, 0, h, i0, b);
+    tc05::mbar_expect_tx(bar_k, kKVBuf);
+    tc05::tma_load_4d(smem + kOffKV, &tmK, bar_k, 0, h, 0, b);
+    tc05::mbar_expect_tx(bar_v, kKVBuf);
+    tc05::tma_load_4d(smem + kOffKV + kKVBuf, &tmV, bar_v, 0, h, 0, b);
   }
 
   const int i = i0 + rowl;
   const float sl2 = p.scale * kLog2e;
-  int n_tiles = n_tiles_all;
-  if (p.causal) n_tiles = min(n_tiles, min(i0 + kBM - 1, p.Sq - 1) / kBN + 1);
   const uint32_t idesc_qk = tc05::idesc_bf16(kBM, kBN, 0, 0);
   const uint32_t idesc_pv = tc05::idesc_bf16(kBM, kD, 0, 1);      // B = V is MN-major (d contiguous)
-  const uint32_t q_addr = tc05::smem_u32(smem + kOffQ), k_addr = tc05::smem_u32(smem + kOffK);
-  const uint32_t v_addr = tc05::smem_u32(smem + kOffV), p_addr = tc05::smem_u32(smem + kOffP);
+  const uint32_t q_addr = tc05::smem_u32(smem + kOffQ), kv_addr = tc05::smem_u32(smem + kOffKV);
+  const uint32_t p_addr = tc05::smem_u32(smem + kOffP);
   const float* relrow = s_rel + (p.Sq - 1 - i) + kRelPad;         // relrow[j] = bias of key j for this row
   // with dropout the 1/keep factor is folded into the exponent: p' = p/keep, row sums carry the same factor
   const float m_shift = DROP ? log2f(p.drop_scale) : 0.f;
@@ -156,11 +163,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   for (int t = 0; t < n_tiles; ++t) {
     const int j0 = t * kBN;
     const uint32_t ph = t & 1;
+    const uint32_t k_addr = kv_addr + ((2 * t) % 3) * kKVBuf;
+    const uint32_t v_addr = kv_addr + ((2 * t + 1) % 3) * kKVBuf;
     if (tid == 0) {
-      tc05::mbar_expect_tx(bar_kv, 2 * kBN * kD * 2);
-      tc05::tma_load_4d(smem + kOffK, &tmK, bar_kv, 0, h, j0, b);
-      tc05::tma_load_4d(smem + kOffV, &tmV, bar_kv, 0, h, j0, b);
-      tc05::mbar_wait(bar_kv, ph);
+      if (t + 1 < n_tiles) {        // prefetch K_{j+1} into the buffer V_{j-1} vacated at the end of the last tile
+        tc05::mbar_expect_tx(bar_k + ((t + 1) & 1), kKVBuf);
+        tc05::tma_load_4d(smem + kOffKV + ((2 * t + 2) % 3) * kKVBuf, &tmK, bar_k + ((t + 1) & 1), 0, h, j0 + kBN, b);
+      }
+      tc05::mbar_wait(bar_k + (t & 1), (t >> 1) & 1);
       tc05::tc_fence_after_sync();
 #pragma unroll
       for (int ks = 0; ks < kD / 16; ++ks)      // S = Q K^T : 32 bytes per k-step inside the 128-byte swizzled row
@@ -171,6 +181,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const bool diag = p.causal && (j0 + kBN - 1 > i0);     // tile touches the diagonal (CTA-uniform)
     tc05::mbar_wait(bar_s, ph);
     tc05::tc_fence_after_sync();
+    if (tid == 0 && t + 1 < n_tiles) {   // K_j is consumed: its buffer takes V_{j+1}
+      tc05::mbar_expect_tx(bar_v + ((t + 1) & 1), kKVBuf);
+      tc05::tma_load_4d(smem + kOffKV + ((2 * t) % 3) * kKVBuf, &tmV, bar_v + ((t + 1) & 1), 0, h, j0 + kBN, b);
+    }
 
     // ---- pass A: biased scores (written back to TMEM) and the row max over this thread's 64 columns ----
     float mx = -INFINITY;
@@ -252,6 +266,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc05::tc_fence_before_sync();
     __syncthreads();
     if (tid == 0) {
+      tc05::mbar_wait(bar_v + (t & 1), (t >> 1) & 1);
       tc05::tc_fence_after_sync();
       // O_j = P V : 8 k-steps of 16 keys.  A = P (K-major: sub-tile ks/4, +32 B per step),
       // B = V (MN-major: 16 keys = 2 swizzle atoms of 8 rows x 128 B = 2048 B per step)
@@ -380,7 +395,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int n_win = p.Sq + kBN - 1;                              // rel offsets this key tile can see
   float* s_kadd = reinterpret_cast<float*>(smem + kBOffFloats);  // [kBN], -inf beyond Sk
   float* s_rel = s_kadd + kBN;                                   // [kRelPad + n_win] bias * log2e (index w + kRelPad)
-  float* s_drel = s_rel + kRelPad + n_win;                       // [2][n_win] gradient accumulators
+  float* s_drel = s_rel + kRelPad + n_win;                       // [n_win] gradient accumulator (smem atomics)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rowl = (warp & 3) * 32 + lane;     // row inside the 128-row tile == TMEM lane
@@ -408,7 +423,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int r = j0 + x - kRelPad;
       s_rel[x] = (x >= kRelPad && r < n_rel) ? p.rel_bias[(long long)h * n_rel + r] * kLog2e : 0.f;
     }
-    for (int x = tid; x < 2 * n_win; x += kBwdThreads2) s_drel[x] = 0.f;
+    for (int x = tid; x < n_win; x += kBwdThreads2) s_drel[x] = 0.f;
   }
   tc05::tc_fence_before_sync();
   __syncthreads();
@@ -516,6 +531,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int x = 0; x < 32; ++x) dsv[x] = pv[x] * (__uint_as_float(rp[x]) - delta) * p.scale;
       }
+      if (HAS_REL && p.d_rel) {
+        // d_rel[j-i] += dS: this warp holds a 32x32 block (lane = row, register = column).  Lane L collects the
+        // diagonals d' = col - row == L (mod 32): one shuffle per column, two accumulators for the wrap.
+        float accp = 0.f, accn = 0.f;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const float vsh = __shfl_sync(0xffffffffu, dsv[c], (c - lane) & 31);
+          if (lane <= c) accp += vsh; else accn += vsh;
+        }
+        // window index of rel = (j0+jl) - (i0+il) + Sq-1, minus j0;  jl - il = (jl0 - 32*(warp&3)) + d'
+        const int wpos = jl0 - (warp & 3) * 32 + lane - i0 + p.Sq - 1;
+        if (wpos >= 0 && wpos < n_win) atomicAdd(s_drel + wpos, accp);
+        if (lane > 0 && wpos - 32 >= 0 && wpos - 32 < n_win) atomicAdd(s_drel + wpos - 32, accn);
+      }
       uint8_t* prow = smem + kBOffP + (qd >> 1) * (kBM * 128) + rowl * 128;
       uint8_t* dsrow = smem + kBOffdS + (qd >> 1) * (kBM * 128) + rowl * 128;
 #pragma unroll
@@ -544,24 +573,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                           tc05::smem_desc_sw128(ds_addr + (ks >> 2) * (kBM * 128) + (ks & 3) * 32, 16, 1024),
                           tc05::smem_desc_sw128(k_addr + ks * 2048, 16, 1024), idesc_dq, ks > 0);
       tc05::mma_commit(bar_dq);
-    }
-    // ---- d_rel: half a diagonal of the dS tile per thread (generic-proxy reads, overlapping the MMAs) ----
-    if (HAS_REL && p.d_rel) {
-      const int dg = tid & 255, part = tid >> 8;
-      if (dg < 2 * kBM - 1) {
-        const int delta_ij = dg - (kBM - 1);          // jl - il
-        const int il_lo = max(0, -delta_ij), il_hi = min(kBM - 1, kBN - 1 - delta_ij);
-        float acc = 0.f;
-#pragma unroll 4
-        for (int il = il_lo + part; il <= il_hi; il += 2) {
-          const int jl = il + delta_ij;
-          const uint8_t* e = smem + kBOffdS + (jl >> 6) * (kBM * 128) + il * 128 +
-                             ((((jl & 63) >> 3) ^ (il & 7)) << 4) + (jl & 7) * 2;
-          acc += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(e));
-        }
-        const int w = delta_ij - i0 + p.Sq - 1;       // window index of rel = (j0+jl) - (i0+il) + Sq-1, minus j0
-        if (w >= 0 && w < n_win) s_drel[part * n_win + w] += acc;   // (part, w) is owned by exactly one thread
-      }
     }
     tc05::mbar_wait(bar_dq, ph);
     tc05::tc_fence_after_sync();
@@ -612,7 +623,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float inv_scale = 1.0f / p.scale;          // the smem tile holds scale * dS
     for (int w = tid; w < n_win; w += kBwdThreads2) {
       const int r = j0 + w;
-      const float g = s_drel[w] + s_drel[n_win + w];
+      const float g = s_drel[w];
       if (r < n_rel && g != 0.f) atomicAdd(p.d_rel + (long long)h * n_rel + r, g * inv_scale);
     }
   }
@@ -740,7 +751,7 @@ extern "C" int pvqa_attn_bwd(const void* q, const void* k, const void* v, const 
                    al8(dk_stride_b, dk_stride_s, dk_stride_h) && al8(dv_stride_b, dv_stride_s, dv_stride_h),
                PVQA_ERR_ALIGN, "attn_bwd: rows must be 16-byte aligned");
   const int64_t n_win = Sq + kBN - 1;
-  const int64_t n_floats = kBN + (rel_bias ? kRelPad + 3 * n_win : 0);
+  const int64_t n_floats = kBN + (rel_bias ? kRelPad + 2 * n_win : 0);
   const size_t smem_bytes = 1024 + kBOffFloats + (size_t)n_floats * 4;
   PVQA_REQUIRE(smem_bytes <= 225 * 1024, PVQA_ERR_SHAPE, "attn_bwd: Sq too large for the bias window buffers");
   CUtensorMap tq, tk, tv, tdo;

@@ -25,7 +25,8 @@ for r in rows[1:]:
     for k in KEYS:
         if k in idx:
             print(f"   {k} = {r[idx[k]]}")
-    stalls = [(h, float(r[i])) for h, i in idx.items() if "issue_stalled" in h and h.endswith("_per_warp_active.pct")
-              and r[i] not in ("", "n/a")]
+    stalls = [(h, float(r[i])) for h, i in idx.items() if h.startswith("smsp__average_warps_issue_stalled_")
+              and h.endswith("_per_issue_active.ratio") and r[i] not in ("", "n/a")]
     stalls.sort(key=lambda kv: -kv[1])
-    print("   top stalls:", ", ".join(f"{h.split('issue_stalled_')[1].split('_per_warp')[0]}={v:.1f}" for h, v in stalls[:6]))
+    print("   stalled warps per issue:", ", ".join(
+        f"{h.split('issue_stalled_')[1].split('_per_issue')[0]}={v:.2f}" for h, v in stalls[:7]))
