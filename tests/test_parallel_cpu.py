@@ -1,0 +1,83 @@
+"""GradReducer (bucketed gradient all-reduce overlapped with backward) on 2 gloo ranks, CPU."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _make_model():
+    torch.manual_seed(0)
+    m = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.ReLU(), torch.nn.Linear(32, 32), torch.nn.ReLU(),
+                            torch.nn.Linear(32, 4))
+    m.frozen = torch.nn.Linear(4, 4)
+    for p in m.frozen.parameters():
+        p.requires_grad = False
+    return m
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import phoneme_vqa_b200.parallel as par
+    model = _make_model()
+    if rank == 1:                                    # ranks start different: broadcast must fix it
+        with torch.no_grad():
+            for p in model.parameters():
+                p.add_(1.0)
+    red = par.GradReducer(model, bucket_mb=0.002)    # tiny buckets -> several of them
+    red.broadcast_parameters(0)
+    assert len(red.buckets) >= 3
+    g = torch.Generator().manual_seed(100)
+    x = torch.randn(8, 16, generator=g)
+    y = torch.randn(8, 4, generator=g)
+    xs, ys = x[rank * 4:(rank + 1) * 4], y[rank * 4:(rank + 1) * 4]
+    loss = torch.nn.functional.mse_loss(model(xs), ys)
+    loss.backward()
+    red.finish()
+    grads = [p.grad.clone() for p in model.parameters() if p.requires_grad]
+    # toggle the trainable set (encoder freeze, PhonemeLaTr_Executor.py:152-159) and make sure re-bucketing works
+    for p in model[0].parameters():
+        p.requires_grad = False
+    assert red.maybe_rebuild()
+    model.zero_grad(set_to_none=True)
+    loss = torch.nn.functional.mse_loss(model(xs), ys)
+    loss.backward()
+    red.finish()
+    grads2 = [p.grad.clone() for p in model.parameters() if p.requires_grad]
+    if rank == 0:
+        q.put((grads, grads2))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradients_equal_single_process_global_batch():
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    grads, grads2 = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    model = _make_model()
+    g = torch.Generator().manual_seed(100)
+    x = torch.randn(8, 16, generator=g)
+    y = torch.randn(8, 4, generator=g)
+    torch.nn.functional.mse_loss(model(x), y).backward()          # equal shard sizes: mean of means == global mean
+    ref = [p.grad for p in model.parameters() if p.requires_grad]
+    assert len(ref) == len(grads)
+    for a, b in zip(grads, ref):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
+    ref2 = [p.grad for p in list(model.parameters())[2:] if p.requires_grad]
+    for a, b in zip(grads2, ref2):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
