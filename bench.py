@@ -137,7 +137,7 @@ def run_reference_arm(args):
             "config": {"workload": WORKLOAD.format(B=args.cpu_batch) + " (CPU sample batch)"},
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # --------------------------------------------------------------------------------------
@@ -146,7 +146,7 @@ def run_reference_arm(args):
 def run_b200_arm(args):
     import torch.distributed as dist
     import phoneme_vqa_b200 as pv
-    from phoneme_vqa_b200 import models, ops, parallel, synthetic
+    from phoneme_vqa_b200 import models, ops, parallel, synthetic, train
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -166,9 +166,8 @@ def run_b200_arm(args):
     ops.manual_seed(1234 + rank)
     reducer = parallel.GradReducer(model, bucket_mb=32.0)
     reducer.broadcast_parameters(0)
-    optim = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=5e-5, betas=(0.9, 0.98),
-                             eps=1e-9, fused=True)
-    sched = torch.optim.lr_scheduler.LinearLR(optim, total_iters=2000)
+    trainer = train.TrainStep(model, reducer if world > 1 else None, lr=5e-5, betas=(0.9, 0.98), eps=1e-9,
+                              warmup_iters=2000, ignore_index=synthetic.PAD_ID, use_graph=not args.no_graph)
 
     n_distinct = 4
     host = [synthetic.phoneme_latr_batch(B, cfg.vocab_size, seed=1234 + rank * 1000 + i, pin=True)
@@ -177,17 +176,7 @@ def run_b200_arm(args):
     h2d_bytes = synthetic.batch_bytes(host[0])
 
     def step(b):
-        labels = b["label_ids"]
-        loss = model.forward_loss(b["pixel_values"], b["coordinates"], b["input_ids"], labels[:, :-1],
-                                  b["src_attention_mask"], b["label_attention_mask"][:, :-1],
-                                  b["ocr_attention_mask"], b["tokenized_ocr"], targets=labels[:, 1:],
-                                  ignore_index=synthetic.PAD_ID)
-        optim.zero_grad(set_to_none=True)
-        loss.backward()
-        reducer.finish()
-        optim.step()
-        sched.step()
-        return loss
+        return trainer(b)
 
     def barrier():
         if world > 1:
@@ -201,8 +190,7 @@ def run_b200_arm(args):
         last = None
         for i in range(n_steps):
             if from_host:
-                b = {k: v.to(dev, non_blocking=True) for k, v in host[i % n_distinct].items()}
-                last = step(b).item()                  # device -> host read of the step's loss
+                last = step(host[i % n_distinct]).item()   # pinned host -> device copies + loss read every step
             else:
                 last = step(resident[i % n_distinct])
         e.record()
@@ -221,13 +209,15 @@ def run_b200_arm(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    launches0 = pv.launch_count()
+    launches0, replays0 = pv.launch_count(), trainer.replays
     ms, last = timed(args.steps, from_host=False)
-    launches = pv.launch_count() - launches0
+    # kernels of libpvqa_sm100.so executed in the timed region: eager launches + (kernels per graph) x replays
+    launches = (pv.launch_count() - launches0) + trainer.launches_per_replay * (trainer.replays - replays0)
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, last_loss = timed(args.steps, from_host=True)
 
-    # profiled pass: CUDA events around every C-ABI launch, same steps
+    # profiled pass: CUDA events around every C-ABI launch, same steps, eager (events cannot sit inside a graph)
+    trainer.use_graph = False
     ops.KernelTimer.reset(True)
     timed(min(args.steps, 5), from_host=False)
     torch.cuda.synchronize()
@@ -238,12 +228,14 @@ def run_b200_arm(args):
     if rank == 0:
         hbm, tf, src = _peaks()
         alg = kernel_algorithmic(B, cfg)
+        traffic = _measured_traffic()
         kernels = {}
         for name, (n, total_ms) in ksum.items():
             avg_ms = total_ms / n
             entry = {"launches_per_step": n / n_prof, "avg_ms": avg_ms, "share_of_step": total_ms / n_prof / (ms / args.steps)}
-            if name in alg:
-                kind, amount = alg[name]
+            work = alg.get(name) or attention_flops(name, B, cfg)
+            if work:
+                kind, amount = work
                 if kind == "hbm":
                     ach = amount / avg_ms / 1e6
                     entry.update({"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm})
@@ -256,8 +248,10 @@ def run_b200_arm(args):
         roofline = None
         if dom:
             roofline = {k: kernels[dom][k] for k in ("bound", "achieved", "peak", "unit", "frac")}
-            roofline.update({"kernel": dom, "traffic": None, "peak_source": src,
-                             "avg_launch_ms": kernels[dom]["avg_ms"]})
+            roofline.update({"kernel": dom, "traffic": traffic.get(dom.split("[")[0]), "peak_source": src,
+                             "avg_launch_ms": kernels[dom]["avg_ms"],
+                             "note": "achieved = algorithmic flops (or bytes) per launch / CUDA-event duration of that "
+                                     "launch inside the step; traffic = ncu dram bytes per launch (profiles/)"})
         value = world * B * args.steps / (ms / 1e3)
         line = {
             "metric": "train samples/sec (PhonoLaTr-base)", "value": value, "unit": "samples/s", "n_gpus": world,
@@ -265,6 +259,7 @@ def run_b200_arm(args):
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": WORKLOAD.format(B=B), "global_batch": world * B,
                        "parallelism": f"dp{world}", "weights": "random-init",
+                       "launch": "eager" if args.no_graph else "one CUDA graph per step",
                        "l2": "no flush: per-step working set (0.9 GB weights+Adam state read, >10 GB activations) "
                              "exceeds the 126 MB L2; 4 distinct batches cycled"},
             "e2e": {"value": world * B * args.steps / (ms_e2e / 1e3), "unit": "samples/s",
@@ -275,10 +270,33 @@ def run_b200_arm(args):
         if world == 1 and not args.no_cpu_baseline:
             res = cpu_reference_run(args.cpu_batch, 1, 1)
             line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _measured_traffic():
+    """ncu `dram__bytes_read.sum + dram__bytes_write.sum` per launch at the bench shape, recorded under profiles/."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return {}
+
+
+def attention_flops(name, B, cfg):
+    """attn_{fwd,bwd}[Sq=..,Sk=..]: 4*B*H*Sq*Sk*D forward (2 GEMMs), 2.5x that backward (5 GEMMs);
+    the causal decoder self-attention (Sq == Sk == T) only needs the lower triangle."""
+    import re
+    m = re.match(r"attn_(fwd|bwd)\[Sq=(\d+),Sk=(\d+)\]", name)
+    if not m:
+        return None
+    sq, sk = int(m.group(2)), int(m.group(3))
+    fl = 4.0 * B * cfg.num_heads * sq * sk * cfg.d_kv
+    if sq == sk and sq < 197:        # target-side self-attention is causal
+        fl *= 0.5
+    return ("tensor", fl if m.group(1) == "fwd" else 2.5 * fl)
 
 
 def kernel_algorithmic(B, cfg, S_img=197, L_ocr=100, L_q=30, T=127):
@@ -293,9 +311,24 @@ def kernel_algorithmic(B, cfg, S_img=197, L_ocr=100, L_q=30, T=127):
         "embed_tgt_bwd": ("hbm", B * T * (3 * 8 + d * 4 + 2 * d * 4)),
         "phoneme_head_ce_fwd": ("hbm", B * T * (d * e_act + 3 * 8 + 3 * 4)),
         "phoneme_head_ce_bwd": ("hbm", B * T * (d * e_act + 3 * 8 + 3 * 4 + 278 * e_act)),
-        "attn_fwd_enc": ("tensor", 4.0 * B * H * S * S * D),
-        "attn_bwd_enc": ("tensor", 10.0 * B * H * S * S * D),
     }
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Libraries (NCCL's version banner, HF warnings) print to stdout; the contract is ONE JSON line there.
+    Point fd 1 at stderr for the run and keep the real stdout for the final line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
 
 
 def main():
@@ -308,7 +341,9 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=4, help="batch of the bounded CPU sample")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of one CUDA graph")
     args = ap.parse_args()
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:

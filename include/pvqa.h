@@ -46,6 +46,10 @@ const char* pvqa_last_error(void);
 /* number of kernels this library has launched in this process (all threads);
  * bench.py reports the delta over the timed region as "gpu_launches". */
 int64_t pvqa_launch_count(void);
+/* Optional: register a device-resident uint64 step counter.  Every dropout kernel adds its value to the
+ * Philox offset it was launched with, so a CUDA graph capturing a whole training step draws fresh masks on
+ * each replay (the caller increments the counter between replays).  NULL (default) disables it. */
+int pvqa_set_rng_step_counter(const uint64_t* device_counter);
 
 /* ------------------------------------------------------------------------
  * K1  fused multimodal embedding

@@ -16,6 +16,7 @@ int fail(int code, const char* fmt, ...) {
 }
 
 std::atomic<long long> g_launch_count{0};
+const unsigned long long* g_rng_base = nullptr;
 
 int num_sms() {
   // cached per device id; the library is used with one device per process (one rank per GPU)
@@ -37,3 +38,7 @@ int num_sms() {
 extern "C" int pvqa_abi_version(void) { return PVQA_ABI_VERSION; }
 extern "C" const char* pvqa_last_error(void) { return pvqa::last_error_buf(); }
 extern "C" int64_t pvqa_launch_count(void) { return (int64_t)pvqa::g_launch_count.load(); }
+extern "C" int pvqa_set_rng_step_counter(const uint64_t* device_counter) {
+  pvqa::g_rng_base = reinterpret_cast<const unsigned long long*>(device_counter);
+  return PVQA_OK;
+}

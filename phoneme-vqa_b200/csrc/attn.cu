@@ -76,6 +76,7 @@ struct AttnFwdParams {
   uint32_t drop_thr8;         // 0 = no dropout; drop probability = thr8/256
   float drop_scale;           // 1 / keep probability
   uint64_t seed, offset;
+  const unsigned long long* rng_base;
 };
 
 template <bool HAS_REL, bool DROP>
@@ -152,6 +153,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const float m_shift = DROP ? log2f(p.drop_scale) : 0.f;
   const uint32_t thr4 = p.drop_thr8 * 0x01010101u;
   const uint64_t drop_row = ((uint64_t)(b * p.H + h) * p.Sq + min(i, p.Sq - 1)) * (uint64_t)((p.Sk + 15) >> 4);
+  const uint64_t rng_off = p.offset + ((DROP && p.rng_base) ? *p.rng_base : 0ull);
 
   float m_run = -INFINITY, l_run = 0.f;
   float o_acc[32];
@@ -241,7 +243,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (DROP) {
 #pragma unroll
         for (int g2 = 0; g2 < 2; ++g2) {
-          const uint4 kb = keep_bytes16(p.seed, p.offset, drop_row + ((j0 + half * 64 + c * 32) >> 4) + g2, thr4);
+          const uint4 kb = keep_bytes16(p.seed, rng_off, drop_row + ((j0 + half * 64 + c * 32) >> 4) + g2, thr4);
           const uint32_t kw[4] = {kb.x, kb.y, kb.z, kb.w};
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
@@ -350,6 +352,7 @@ struct AttnBwdParams {
   uint32_t drop_thr8;
   float drop_scale;
   uint64_t seed, offset;
+  const unsigned long long* rng_base;
 };
 
 struct AttnPrepParams {
@@ -452,6 +455,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t p_addr = tc05::smem_u32(smem + kBOffP), ds_addr = tc05::smem_u32(smem + kBOffdS);
   const uint32_t thr4 = p.drop_thr8 * 0x01010101u;
   const int jl0 = qd * 32;                      // first local key column of this thread
+  const uint64_t rng_off = p.offset + ((DROP && p.rng_base) ? *p.rng_base : 0ull);
 
   int it = 0;
   for (int mt = m_first; mt < m_tiles; ++mt, ++it) {
@@ -514,7 +518,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint64_t drop_row = ((uint64_t)(b * p.H + h) * p.Sq + min(i, p.Sq - 1)) * (uint64_t)((p.Sk + 15) >> 4);
 #pragma unroll
         for (int g2 = 0; g2 < 2; ++g2) {
-          const uint4 kb = keep_bytes16(p.seed, p.offset, drop_row + ((j0 + jl0) >> 4) + g2, thr4);
+          const uint4 kb = keep_bytes16(p.seed, rng_off, drop_row + ((j0 + jl0) >> 4) + g2, thr4);
           const uint32_t kw[4] = {kb.x, kb.y, kb.z, kb.w};
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
@@ -708,7 +712,7 @@ extern "C" int pvqa_attn_fwd(const void* q, const void* k, const void* v, void* 
   p.scale = scale; p.causal = causal;
   p.drop_thr8 = (uint32_t)lrintf(dropout_p * 256.f);
   p.drop_scale = p.drop_thr8 ? 256.f / (256.f - (float)p.drop_thr8) : 1.f;
-  p.seed = seed; p.offset = offset;
+  p.seed = seed; p.offset = offset; p.rng_base = g_rng_base;
   const bool rel = rel_bias != nullptr, drop = p.drop_thr8 != 0;
   auto kern = rel ? (drop ? attn_fwd_kernel<true, true> : attn_fwd_kernel<true, false>)
                   : (drop ? attn_fwd_kernel<false, true> : attn_fwd_kernel<false, false>);
@@ -782,7 +786,7 @@ extern "C" int pvqa_attn_bwd(const void* q, const void* k, const void* v, const 
   p.scale = scale; p.causal = causal;
   p.drop_thr8 = (uint32_t)lrintf(dropout_p * 256.f);
   p.drop_scale = p.drop_thr8 ? 256.f / (256.f - (float)p.drop_thr8) : 1.f;
-  p.seed = seed; p.offset = offset;
+  p.seed = seed; p.offset = offset; p.rng_base = g_rng_base;
   const bool rel = rel_bias != nullptr, drop = p.drop_thr8 != 0;
   auto kern = rel ? (drop ? attn_bwd_kernel<true, true> : attn_bwd_kernel<true, false>)
                   : (drop ? attn_bwd_kernel<false, true> : attn_bwd_kernel<false, false>);

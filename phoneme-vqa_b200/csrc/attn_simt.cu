@@ -23,7 +23,7 @@ struct SimtParams {
   long long qsb, qss, qsh, ksb, kss, ksh, vsb, vss, vsh, osb, oss, osh;
   long long dosb, doss, dosh, dqsb, dqss, dqsh, dksb, dkss, dksh, dvsb, dvss, dvsh;
   float scale; int causal;
-  uint32_t drop_thr8; float drop_scale; uint64_t seed, offset;
+  uint32_t drop_thr8; float drop_scale; uint64_t seed, offset; const unsigned long long* rng_base;
 };
 
 __device__ __forceinline__ float warp_sum(float x) {
@@ -57,7 +57,7 @@ __device__ __forceinline__ float score(const SimtParams& p, float dot, int b, in
 __device__ __forceinline__ float keep_scale(const SimtParams& p, int b, int h, int i, int j) {
   if (!p.drop_thr8) return 1.f;
   const uint64_t grow = ((uint64_t)(b * p.H + h) * p.Sq + i) * (uint64_t)((p.Sk + 15) >> 4);
-  const uint32_t keep = attn_dropout_keep16(p.seed, p.offset, grow + (j >> 4), p.drop_thr8);
+  const uint32_t keep = attn_dropout_keep16(p.seed, p.offset + (p.rng_base ? *p.rng_base : 0ull), grow + (j >> 4), p.drop_thr8);
   return ((keep >> (j & 15)) & 1u) ? p.drop_scale : 0.f;
 }
 
@@ -230,7 +230,7 @@ extern "C" int pvqa_attn_f32_fwd(const float* q, const float* k, const float* v,
   p.scale = scale; p.causal = causal;
   p.drop_thr8 = (uint32_t)lrintf(dropout_p * 256.f);
   p.drop_scale = p.drop_thr8 ? 256.f / (256.f - (float)p.drop_thr8) : 1.f;
-  p.seed = seed; p.offset = offset;
+  p.seed = seed; p.offset = offset; p.rng_base = g_rng_base;
   const size_t smem = (size_t)kSimtWarps * (kSD + ((Sk + 3) & ~3)) * sizeof(float);
   static size_t smem_cap = 48 * 1024;
   if (smem > smem_cap) {
@@ -280,7 +280,7 @@ extern "C" int pvqa_attn_f32_bwd(const float* q, const float* k, const float* v,
   p.scale = scale; p.causal = causal;
   p.drop_thr8 = (uint32_t)lrintf(dropout_p * 256.f);
   p.drop_scale = p.drop_thr8 ? 256.f / (256.f - (float)p.drop_thr8) : 1.f;
-  p.seed = seed; p.offset = offset;
+  p.seed = seed; p.offset = offset; p.rng_base = g_rng_base;
   cudaStream_t st_ = (cudaStream_t)stream;
   const size_t smem_q = (size_t)kSimtWarps * (2 * kSD + ((Sk + 3) & ~3)) * sizeof(float);
   const size_t smem_kv = (size_t)kSimtWarps * (2 * kSD + 2 * ((Sq + 3) & ~3)) * sizeof(float);

@@ -279,6 +279,7 @@ struct EmbedTgtParams {
   int V[3];
   float dropout_p;
   uint64_t seed, offset;
+  const unsigned long long* rng_base;
   int32_t* err_flag;
 };
 
@@ -314,7 +315,7 @@ embed_tgt_fwd_vec_kernel(const EmbedTgtParams p) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) a.v[j] += pe.v[j];
     if (p.dropout_p > 0.f) {
-      const uint32_t m = dropout_keep8(p.seed, p.offset, (uint64_t)(row * p.d + col), thr16);
+      const uint32_t m = dropout_keep8(p.seed, p.offset + (p.rng_base ? *p.rng_base : 0ull), (uint64_t)(row * p.d + col), thr16);
 #pragma unroll
       for (int j = 0; j < 8; ++j) a.v[j] = ((m >> j) & 1u) ? a.v[j] * keep_scale : 0.f;
     }
@@ -346,7 +347,7 @@ embed_tgt_fwd_scalar_kernel(const EmbedTgtParams p) {
     a += p.pe[(long long)t * p.d + col];
     if (p.dropout_p > 0.f) {
       const uint64_t e = (uint64_t)i;
-      const uint32_t m = dropout_keep8(p.seed, p.offset, e & ~7ull, thr16);
+      const uint32_t m = dropout_keep8(p.seed, p.offset + (p.rng_base ? *p.rng_base : 0ull), e & ~7ull, thr16);
       a = ((m >> (e & 7)) & 1u) ? a * keep_scale : 0.f;
     }
     out[i] = from_f32<ActT>(a);
@@ -366,6 +367,7 @@ struct EmbedTgtBwdParams {
   int slabs[3];               // column slabs per sub-table
   float dropout_p;
   uint64_t seed, offset;
+  const unsigned long long* rng_base;
 };
 
 template <typename ActT, int VEC>
@@ -409,7 +411,7 @@ embed_tgt_bwd_kernel(const EmbedTgtBwdParams p) {
           g[i][0] = to_f32(dout[e]);
         }
         if (p.dropout_p > 0.f) {
-          const uint32_t m = dropout_keep8(p.seed, p.offset, (uint64_t)e & ~7ull, thr16);
+          const uint32_t m = dropout_keep8(p.seed, p.offset + (p.rng_base ? *p.rng_base : 0ull), (uint64_t)e & ~7ull, thr16);
 #pragma unroll
           for (int j = 0; j < VEC; ++j)
             g[i][j] = ((m >> (((uint64_t)e + j) & 7)) & 1u) ? g[i][j] * keep_scale : 0.f;
@@ -562,7 +564,7 @@ extern "C" int pvqa_embed_tgt_fwd(const int64_t* labels, const void* onset_tab, 
   p.labels = labels; p.tab[0] = onset_tab; p.tab[1] = rhyme_tab; p.tab[2] = tone_tab; p.pe = pe; p.out = out;
   p.B = (int)B; p.T = (int)T; p.d = (int)d; p.on_dim = (int)on_dim; p.rt_dim = (int)rt_dim;
   p.V[0] = (int)V_o; p.V[1] = (int)V_r; p.V[2] = (int)V_t;
-  p.dropout_p = dropout_p; p.seed = seed; p.offset = offset; p.err_flag = err_flag;
+  p.dropout_p = dropout_p; p.seed = seed; p.offset = offset; p.rng_base = g_rng_base; p.err_flag = err_flag;
   cudaStream_t st = (cudaStream_t)stream;
   const bool vec = (on_dim % 8 == 0) && (rt_dim % 8 == 0) && aligned16(onset_tab) && aligned16(rhyme_tab) &&
                    aligned16(tone_tab) && aligned16(pe) && aligned16(out);
@@ -603,7 +605,7 @@ extern "C" int pvqa_embed_tgt_bwd(const void* d_out, const int64_t* labels, floa
   p.B = (int)B; p.T = (int)T; p.d = (int)d; p.on_dim = (int)on_dim; p.rt_dim = (int)rt_dim;
   p.V[0] = (int)V_o; p.V[1] = (int)V_r; p.V[2] = (int)V_t;
   p.runs = (int)((T + kRun - 1) / kRun);
-  p.dropout_p = dropout_p; p.seed = seed; p.offset = offset;
+  p.dropout_p = dropout_p; p.seed = seed; p.offset = offset; p.rng_base = g_rng_base;
   cudaStream_t st = (cudaStream_t)stream;
   const bool vec = (on_dim % 4 == 0) && (rt_dim % 4 == 0) && aligned16(d_out) && aligned16(d_onset) &&
                    aligned16(d_rhyme) && aligned16(d_tone);

@@ -135,7 +135,8 @@ rms_norm_bwd_kernel(const YT* __restrict__ dy, const XT* __restrict__ x, const f
 template <typename UT>
 __global__ void __launch_bounds__(kNormThreads)
 residual_dropout_add_kernel(const float* __restrict__ hidden, const UT* __restrict__ upd, float* __restrict__ out,
-                            long long n8, uint32_t thr16, float scale, uint64_t seed, uint64_t offset) {
+                            long long n8, uint32_t thr16, float scale, uint64_t seed, uint64_t offset, const unsigned long long* rng_base) {
+  if (thr16 && rng_base) offset += *rng_base;
   for (long long i = (long long)blockIdx.x * kNormThreads + threadIdx.x; i < n8; i += (long long)gridDim.x * kNormThreads) {
     f8 h = Vec8<float>::load_stream(hidden + i * 8);
     f8 u = Vec8<UT>::load_stream(upd + i * 8);
@@ -154,7 +155,8 @@ residual_dropout_add_kernel(const float* __restrict__ hidden, const UT* __restri
 template <typename UT>
 __global__ void __launch_bounds__(kNormThreads)
 residual_dropout_bwd_kernel(const float* __restrict__ d_out, UT* __restrict__ d_upd, long long n8, uint32_t thr16,
-                            float scale, uint64_t seed, uint64_t offset) {
+                            float scale, uint64_t seed, uint64_t offset, const unsigned long long* rng_base) {
+  if (thr16 && rng_base) offset += *rng_base;
   for (long long i = (long long)blockIdx.x * kNormThreads + threadIdx.x; i < n8; i += (long long)gridDim.x * kNormThreads) {
     f8 g = Vec8<float>::load_stream(d_out + i * 8);
     if (thr16) {
@@ -170,7 +172,8 @@ residual_dropout_bwd_kernel(const float* __restrict__ d_out, UT* __restrict__ d_
 template <typename T>
 __global__ void __launch_bounds__(kNormThreads)
 relu_dropout_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long n8, uint32_t thr16, float scale,
-                        uint64_t seed, uint64_t offset) {
+                        uint64_t seed, uint64_t offset, const unsigned long long* rng_base) {
+  if (thr16 && rng_base) offset += *rng_base;
   for (long long i = (long long)blockIdx.x * kNormThreads + threadIdx.x; i < n8; i += (long long)gridDim.x * kNormThreads) {
     f8 v = Vec8<T>::load_stream(x + i * 8);
     uint32_t m = 0xffu;
@@ -269,9 +272,9 @@ extern "C" int pvqa_residual_dropout_add(const float* hidden, const void* update
   drop_consts(dropout_p, thr, sc);
   cudaStream_t st = (cudaStream_t)stream;
   if (upd_dtype == PVQA_BF16)
-    residual_dropout_add_kernel<__nv_bfloat16><<<ew_grid(n / 8), kNormThreads, 0, st>>>(hidden, (const __nv_bfloat16*)update, out, n / 8, thr, sc, seed, offset);
+    residual_dropout_add_kernel<__nv_bfloat16><<<ew_grid(n / 8), kNormThreads, 0, st>>>(hidden, (const __nv_bfloat16*)update, out, n / 8, thr, sc, seed, offset, g_rng_base);
   else if (upd_dtype == PVQA_F32)
-    residual_dropout_add_kernel<float><<<ew_grid(n / 8), kNormThreads, 0, st>>>(hidden, (const float*)update, out, n / 8, thr, sc, seed, offset);
+    residual_dropout_add_kernel<float><<<ew_grid(n / 8), kNormThreads, 0, st>>>(hidden, (const float*)update, out, n / 8, thr, sc, seed, offset, g_rng_base);
   else
     return fail(PVQA_ERR_DTYPE, "residual_dropout_add: bad dtype");
   count_launch();
@@ -290,9 +293,9 @@ extern "C" int pvqa_residual_dropout_bwd(const float* d_out, void* d_update, int
   drop_consts(dropout_p, thr, sc);
   cudaStream_t st = (cudaStream_t)stream;
   if (upd_dtype == PVQA_BF16)
-    residual_dropout_bwd_kernel<__nv_bfloat16><<<ew_grid(n / 8), kNormThreads, 0, st>>>(d_out, (__nv_bfloat16*)d_update, n / 8, thr, sc, seed, offset);
+    residual_dropout_bwd_kernel<__nv_bfloat16><<<ew_grid(n / 8), kNormThreads, 0, st>>>(d_out, (__nv_bfloat16*)d_update, n / 8, thr, sc, seed, offset, g_rng_base);
   else if (upd_dtype == PVQA_F32)
-    residual_dropout_bwd_kernel<float><<<ew_grid(n / 8), kNormThreads, 0, st>>>(d_out, (float*)d_update, n / 8, thr, sc, seed, offset);
+    residual_dropout_bwd_kernel<float><<<ew_grid(n / 8), kNormThreads, 0, st>>>(d_out, (float*)d_update, n / 8, thr, sc, seed, offset, g_rng_base);
   else
     return fail(PVQA_ERR_DTYPE, "residual_dropout_bwd: bad dtype");
   count_launch();
@@ -311,9 +314,9 @@ extern "C" int pvqa_relu_dropout_fwd(const void* x, void* y, int64_t n, int dtyp
   drop_consts(dropout_p, thr, sc);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == PVQA_BF16)
-    relu_dropout_fwd_kernel<__nv_bfloat16><<<ew_grid(n / 8), kNormThreads, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n / 8, thr, sc, seed, offset);
+    relu_dropout_fwd_kernel<__nv_bfloat16><<<ew_grid(n / 8), kNormThreads, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n / 8, thr, sc, seed, offset, g_rng_base);
   else if (dtype == PVQA_F32)
-    relu_dropout_fwd_kernel<float><<<ew_grid(n / 8), kNormThreads, 0, st>>>((const float*)x, (float*)y, n / 8, thr, sc, seed, offset);
+    relu_dropout_fwd_kernel<float><<<ew_grid(n / 8), kNormThreads, 0, st>>>((const float*)x, (float*)y, n / 8, thr, sc, seed, offset, g_rng_base);
   else
     return fail(PVQA_ERR_DTYPE, "relu_dropout_fwd: bad dtype");
   count_launch();

@@ -51,6 +51,11 @@ class _ShadowWeights:
             self.refresh()
         return e["shadow"]
 
+    def invalidate(self):
+        """force the next lookup to refresh (used right before CUDA-graph capture)"""
+        for e in self.entries.values():
+            e["versions"] = None
+
     @torch.no_grad()
     def refresh(self):
         dst, src = [], []
