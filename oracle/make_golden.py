@@ -106,6 +106,47 @@ def golden_model():
     print("model golden: loss", loss.item(), "keys", len(out["state_dict_keys"]))
 
 
+def golden_latr():
+    import importlib
+    import transformers
+    ref_mod = importlib.import_module('core.model.LaTr')
+    cfg = ref_model.tiny_config()
+    ref_mod.T5ForConditionalGeneration = type("T5", (), {"from_pretrained": staticmethod(
+        lambda name: transformers.T5ForConditionalGeneration(cfg))})
+    ref_mod.ViTModel = type("ViT", (), {"from_pretrained": staticmethod(lambda name: ref_model._vit_from(cfg))})
+    torch.manual_seed(0)
+    model = ref_mod.LaTr(cfg)
+    model.load_state_dict(ref_model.deterministic_state_dict(model), strict=True)
+    batch = ref_model.latr_batch(3, cfg)
+    model.eval()
+    labels = batch["label_ids"]
+    logits = model(pixel_values=batch["pixel_values"], coordinates=batch["coordinates"], input_ids=batch["input_ids"],
+                   labels=labels[:, :-1], src_attention_mask=batch["src_attention_mask"],
+                   label_attention_mask=batch["label_attention_mask"][:, :-1],
+                   ocr_attention_mask=batch["ocr_attention_mask"], tokenized_ocr=batch["tokenized_ocr"])
+    out = {"logits": logits.detach().numpy()}
+    model.train()
+    for m in model.modules():
+        if isinstance(m, nn.Dropout):
+            m.p = 0.0
+        if hasattr(m, "dropout") and isinstance(getattr(m, "dropout"), float):
+            m.dropout = 0.0
+    loss = ref_model.latr_loss(model, batch)
+    loss.backward()
+    out["loss"] = np.array(loss.item(), dtype=np.float64)
+    grads = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+    out["grad_keys"] = np.array(sorted(grads.keys()))
+    out["grad_norms"] = np.array([grads[k].double().norm().item() for k in sorted(grads.keys())])
+    model.eval()
+    ys = model.generate(batch["pixel_values"], batch["coordinates"], batch["input_ids"], batch["src_attention_mask"],
+                        batch["ocr_attention_mask"], batch["tokenized_ocr"], max_length=8)
+    out["generate_ids"] = ys.numpy()
+    out["state_dict_keys"] = np.array(list(model.state_dict().keys()))
+    out["state_dict_shapes"] = np.array([json.dumps(list(v.shape)) for v in model.state_dict().values()])
+    np.savez_compressed(os.path.join(GOLD, "model_latr_tiny.npz"), **out)
+    print("latr golden: loss", loss.item(), "generate", ys.tolist())
+
+
 def golden_ops():
     """op-level goldens from reference modules: SpatialModule, SinusoidalPositionalEncoding."""
     import importlib
@@ -132,6 +173,7 @@ if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     golden_ops()
     golden_model()
+    golden_latr()
     try:
         from oracle import make_golden_text
         make_golden_text.main()

@@ -20,7 +20,7 @@ import zlib
 import numpy as np
 import torch
 import torch.nn as nn
-from transformers import T5Config, T5EncoderModel, ViTConfig, ViTModel
+from transformers import T5Config, T5EncoderModel, T5ForConditionalGeneration, ViTConfig, ViTModel
 
 from . import ref_ops
 
@@ -29,7 +29,8 @@ def make_config(d_model=768, d_kv=64, num_heads=12, d_ff=3072, num_layers=12, vo
                 num_decoder_layers=4, n_head=12, max_2d_position_embeddings=1024, vit_config=None,
                 dropout_rate=0.1, feed_forward_proj="relu"):
     cfg = T5Config(d_model=d_model, d_kv=d_kv, num_heads=num_heads, d_ff=d_ff, num_layers=num_layers,
-                   vocab_size=vocab_size, dropout_rate=dropout_rate, feed_forward_proj=feed_forward_proj)
+                   vocab_size=vocab_size, dropout_rate=dropout_rate, feed_forward_proj=feed_forward_proj,
+                   decoder_start_token_id=0)
     cfg.update({"max_2d_position_embeddings": max_2d_position_embeddings, "vit_model": "random-init",
                 "num_decoder_layers": num_decoder_layers, "n_head": n_head, "random_init": True,
                 "vit_config": vit_config})
@@ -181,6 +182,70 @@ class PhonemeLaTr(nn.Module):
             if torch.any(ys[:, :, 0] == end_symbol, dim=1).sum() == bz:
                 break
         return ys
+
+
+# core/model/LaTr.py:42-111
+class LaTr(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.backbone = T5ForConditionalGeneration(config)
+        self.spatial_feat_extractor = SpatialModule(config)
+        self.vit = _vit_from(config)
+        self.visual_projector = nn.Linear(self.vit.config.hidden_size, config.d_model)
+        for _, child in self.vit.named_children():
+            for p in child.parameters():
+                p.requires_grad = False
+
+    def calculate_embedding(self, pixel_values, coordinates, input_ids, ocr_attention_mask, src_attention_mask,
+                            tokenized_ocr):
+        img_feat = self.visual_projector(self.vit(pixel_values).last_hidden_state)
+        layout_feat = self.backbone.shared(tokenized_ocr) + self.spatial_feat_extractor(coordinates)
+        feat = torch.cat([img_feat, layout_feat, self.backbone.shared(input_ids)], axis=1)
+        mask = torch.cat([torch.ones(img_feat.shape[:2]).to(img_feat.device), ocr_attention_mask,
+                          src_attention_mask], axis=1)
+        return feat, mask
+
+    def forward(self, pixel_values, coordinates, input_ids, labels, src_attention_mask, label_attention_mask,
+                ocr_attention_mask, tokenized_ocr):
+        emb, mask = self.calculate_embedding(pixel_values, coordinates, input_ids, ocr_attention_mask,
+                                             src_attention_mask, tokenized_ocr)
+        enc = self.backbone.encoder(attention_mask=mask, inputs_embeds=emb).last_hidden_state
+        dec = self.backbone.decoder(encoder_hidden_states=enc, inputs_embeds=self.backbone.shared(labels),
+                                    attention_mask=label_attention_mask).last_hidden_state
+        return self.backbone.lm_head(dec)
+
+    def generate(self, pixel_values, coordinates, input_ids, src_attention_mask, ocr_attention_mask, tokenized_ocr,
+                 max_length=20):
+        emb, _ = self.calculate_embedding(pixel_values, coordinates, input_ids, ocr_attention_mask,
+                                          src_attention_mask, tokenized_ocr)
+        return self.backbone.generate(inputs_embeds=emb, max_length=max_length, do_sample=False, num_beams=1)
+
+
+# core/executor/LaTr_Executor.py:140-163 — one training step's loss (labels from the HF tokenizer, pad id 0)
+def latr_loss(model, batch, pad_id=0):
+    labels = batch["label_ids"]
+    logits = model(pixel_values=batch["pixel_values"], coordinates=batch["coordinates"], input_ids=batch["input_ids"],
+                   labels=labels[:, :-1], src_attention_mask=batch["src_attention_mask"],
+                   label_attention_mask=batch["label_attention_mask"][:, :-1],
+                   ocr_attention_mask=batch["ocr_attention_mask"], tokenized_ocr=batch["tokenized_ocr"])
+    return nn.functional.cross_entropy(logits.reshape(-1, logits.shape[-1]), labels[:, 1:].reshape(-1),
+                                       ignore_index=pad_id)
+
+
+def latr_batch(B, cfg, T=19, L_ocr=12, L_q=6, seed=3, image=32):
+    """LaTr labels: "<pad> " + answer tokens + eos, padded with 0; attention mask 1 = valid (int64)."""
+    b = synthetic_batch(B, cfg, T=T, L_ocr=L_ocr, L_q=L_q, seed=seed, image=image)
+    g = torch.Generator().manual_seed(seed + 1)
+    labels = torch.zeros(B, T + 1, dtype=torch.long)
+    mask = torch.zeros(B, T + 1, dtype=torch.long)
+    for i in range(B):
+        n = int(torch.randint(2, T, (1,), generator=g))
+        labels[i, 1:n] = torch.randint(3, cfg.vocab_size, (n - 1,), generator=g)
+        labels[i, n] = 1
+        mask[i, : n + 1] = 1
+    b["label_ids"], b["label_attention_mask"] = labels, mask
+    return b
 
 
 # core/executor/PhonemeLaTr_Executor.py:161-196 — one training step's loss

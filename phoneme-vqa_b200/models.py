@@ -16,9 +16,9 @@ import torch.nn as nn
 
 from . import ops
 from .modules import (BaseDecoder, PhonemeEmbedding, SinusoidalPositionalEncoding, SpatialModule, T5EncoderModel,
-                      T5Stack, _lin, _t5_init)
+                      T5ForConditionalGeneration, T5Stack, _lin, _t5_init)
 
-__all__ = ["LaTr_config", "CustomizedLaTr_config", "CustomizedPreSTU_config", "PhonemeLaTr", "PhonemePreSTU"]
+__all__ = ["LaTr_config", "CustomizedLaTr_config", "CustomizedPreSTU_config", "PhonemeLaTr", "PhonemePreSTU", "LaTr"]
 
 
 def _random_init(config) -> bool:
@@ -256,3 +256,86 @@ class PhonemePreSTU(nn.Module, _VisionMixin):
         h = _lin(dec.to(self.compute_dtype), self.shared_lm_head.weight, self.shared_lm_head.bias)
         on, rh, to = self._heads(h)
         return on.float(), rh.float(), to.float()
+
+
+def _load_pretrained_t5(backbone: T5ForConditionalGeneration, config):
+    if _random_init(config):
+        return
+    from transformers import T5ForConditionalGeneration as HF
+    backbone.load_state_dict(HF.from_pretrained(config._name_or_path).state_dict(), strict=True)
+
+
+class LaTr(nn.Module, _VisionMixin):
+    """reference: core/model/LaTr.py:42-111 — T5 encoder + T5 decoder + lm_head over the T5 vocabulary."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.compute_dtype = torch.float32
+        self.backbone = T5ForConditionalGeneration(config)
+        _load_pretrained_t5(self.backbone, config)
+        self.spatial_feat_extractor = SpatialModule(config)
+        self.vit = _build_vit(config)
+        self.visual_projector = nn.Linear(self.vit.config.hidden_size, config.d_model)
+        for _, child in self.vit.named_children():
+            for param in child.parameters():
+                param.requires_grad = False
+
+    # reference :85-97
+    def calculate_embedding(self, pixel_values, coordinates, input_ids, ocr_attention_mask, src_attention_mask,
+                            tokenized_ocr):
+        vit_tokens = self._vit_tokens(pixel_values)
+        img_feat = _lin(vit_tokens.to(self.compute_dtype), self.visual_projector.weight, self.visual_projector.bias)
+        return ops.embed_multimodal(img_feat, coordinates, tokenized_ocr, input_ids, ocr_attention_mask,
+                                    src_attention_mask, self.backbone.shared.weight,
+                                    self.spatial_feat_extractor.tables(), out_dtype=self.compute_dtype)
+
+    def _decoder_hidden(self, pixel_values, coordinates, input_ids, labels, src_attention_mask, label_attention_mask,
+                        ocr_attention_mask, tokenized_ocr):
+        inputs_embeds, attention_mask = self.calculate_embedding(
+            pixel_values, coordinates, input_ids, ocr_attention_mask, src_attention_mask, tokenized_ocr)
+        enc = self.backbone.encoder(inputs_embeds, attention_mask, compute_dtype=self.compute_dtype)
+        # reference :76-80: decoder gets NO encoder_attention_mask; label mask is 1 = valid (int64)
+        tgt = torch.nn.functional.embedding(labels, self.backbone.shared.weight)
+        return self.backbone.decoder(tgt, label_attention_mask, compute_dtype=self.compute_dtype, memory=enc,
+                                     memory_mask=None)
+
+    # reference :58-83
+    def forward(self, pixel_values, coordinates, input_ids, labels, src_attention_mask, label_attention_mask,
+                ocr_attention_mask, tokenized_ocr):
+        dec = self._decoder_hidden(pixel_values, coordinates, input_ids, labels, src_attention_mask,
+                                   label_attention_mask, ocr_attention_mask, tokenized_ocr)
+        # lm_head is called directly: no d_model**-0.5 rescale (reference :83)
+        return _lin(dec.to(self.compute_dtype), self.backbone.lm_head.weight).float()
+
+    def forward_loss(self, pixel_values, coordinates, input_ids, labels, src_attention_mask, label_attention_mask,
+                     ocr_attention_mask, tokenized_ocr, targets, ignore_index):
+        """model forward + CrossEntropyLoss(ignore_index=pad) of core/executor/LaTr_Executor.py:160-163."""
+        logits = self.forward(pixel_values, coordinates, input_ids, labels, src_attention_mask, label_attention_mask,
+                              ocr_attention_mask, tokenized_ocr)
+        return torch.nn.functional.cross_entropy(logits.reshape(-1, logits.shape[-1]), targets.reshape(-1),
+                                                 ignore_index=ignore_index)
+
+    # reference :99-111 — HF greedy generation from inputs_embeds (no encoder attention mask is passed there)
+    @torch.no_grad()
+    def generate(self, pixel_values, coordinates, input_ids, src_attention_mask, ocr_attention_mask, tokenized_ocr,
+                 max_length=20):
+        inputs_embeds, _ = self.calculate_embedding(pixel_values, coordinates, input_ids, ocr_attention_mask,
+                                                    src_attention_mask, tokenized_ocr)
+        enc = self.backbone.encoder(inputs_embeds, None, compute_dtype=self.compute_dtype)
+        cfg = self.config
+        start = cfg.decoder_start_token_id if cfg.decoder_start_token_id is not None else cfg.pad_token_id
+        B = inputs_embeds.shape[0]
+        ys = torch.full((B, 1), start, dtype=torch.long, device=inputs_embeds.device)
+        done = torch.zeros(B, dtype=torch.bool, device=ys.device)
+        for _ in range(max_length - 1):
+            tgt = torch.nn.functional.embedding(ys, self.backbone.shared.weight)
+            dec = self.backbone.decoder(tgt, None, compute_dtype=self.compute_dtype, memory=enc, memory_mask=None)
+            logits = _lin(dec[:, -1:].to(self.compute_dtype), self.backbone.lm_head.weight).float()
+            nxt = logits[:, -1].argmax(-1)
+            nxt = torch.where(done, torch.full_like(nxt, cfg.pad_token_id), nxt)
+            ys = torch.cat([ys, nxt[:, None]], dim=1)
+            done = done | (nxt == cfg.eos_token_id)
+            if bool(done.all()):
+                break
+        return ys

@@ -448,6 +448,26 @@ class T5Stack(nn.Module):
         return F.dropout(hidden, self.dropout.p, self.training)
 
 
+class T5ForConditionalGeneration(nn.Module):
+    """`.shared`, `.encoder`, `.decoder`, `.lm_head` with HF's names and weight tying
+    (transformers T5ForConditionalGeneration; used by the plain LaTr / PreSTU family, core/model/LaTr.py:47)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.shared = nn.Embedding(config.vocab_size, config.d_model)
+        self.encoder = T5Stack(config, self.shared, is_decoder=False)
+        n_dec = getattr(config, "num_decoder_layers", None) or config.num_layers
+        self.decoder = T5Stack(config, self.shared, is_decoder=True, num_layers=n_dec)
+        self.lm_head = nn.Linear(config.d_model, config.vocab_size, bias=False)
+        _t5_init(self, config)
+        nn.init.normal_(self.shared.weight, mean=0.0, std=config.initializer_factor * 1.0)
+        if getattr(config, "tie_word_embeddings", True):
+            self.lm_head.weight = self.shared.weight
+        else:
+            nn.init.normal_(self.lm_head.weight, mean=0.0, std=config.initializer_factor * 1.0)
+
+
 class T5EncoderModel(nn.Module):
     """`.shared` + `.encoder` exactly like HF's T5EncoderModel (tied embed_tokens)."""
 

@@ -18,7 +18,7 @@ def t5_config(size="base", vocab_size=36096, num_decoder_layers=4, n_head=None, 
     dims = {"small": dict(d_model=512, d_kv=64, num_heads=8, d_ff=2048, num_layers=6),
             "base": dict(d_model=768, d_kv=64, num_heads=12, d_ff=3072, num_layers=12),
             "large": dict(d_model=1024, d_kv=64, num_heads=16, d_ff=4096, num_layers=24)}[size]
-    cfg = T5Config(vocab_size=vocab_size, dropout_rate=0.1, feed_forward_proj="relu", **dims)
+    cfg = T5Config(vocab_size=vocab_size, dropout_rate=0.1, feed_forward_proj="relu", decoder_start_token_id=0, **dims)
     cfg.update({"max_2d_position_embeddings": 1024, "vit_model": "google/vit-base-patch16-224-in21k",
                 "num_decoder_layers": num_decoder_layers, "n_head": n_head or dims["num_heads"],
                 "random_init": True, "vit_config": vit_config})

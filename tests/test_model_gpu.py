@@ -121,3 +121,65 @@ def test_fused_loss_path_matches_logits_path():
     for k, p in model.named_parameters():
         if p.grad is not None:
             torch.testing.assert_close(p.grad, ref_grads[k], rtol=1e-3, atol=1e-6)
+
+
+# ------------------------------- LaTr (T5 decoder + vocabulary head) ---------------------------------
+def _latr_pair(cfg):
+    import phoneme_vqa_b200.models as M
+    oracle = ref_model.LaTr(cfg)
+    oracle.load_state_dict(ref_model.deterministic_state_dict(oracle), strict=True)
+    model = M.LaTr(cfg)
+    model.load_state_dict(oracle.state_dict(), strict=True)
+    return oracle, model.to(DEV)
+
+
+def _latr_fwd(model, b):
+    labels = b["label_ids"]
+    return model(pixel_values=b["pixel_values"], coordinates=b["coordinates"], input_ids=b["input_ids"],
+                 labels=labels[:, :-1], src_attention_mask=b["src_attention_mask"],
+                 label_attention_mask=b["label_attention_mask"][:, :-1],
+                 ocr_attention_mask=b["ocr_attention_mask"], tokenized_ocr=b["tokenized_ocr"])
+
+
+def test_latr_forward_and_generate_match_reference_golden_fp32():
+    g = np.load(os.path.join(GOLD, "model_latr_tiny.npz"))
+    cfg = ref_model.tiny_config()
+    _, model = _latr_pair(cfg)
+    model.eval()
+    batch = ref_model.latr_batch(3, cfg)
+    logits = _latr_fwd(model, _to(batch, DEV))
+    np.testing.assert_allclose(logits.detach().cpu().numpy(), g["logits"], rtol=2e-4, atol=2e-5)
+    ys = model.generate(*[batch[k].to(DEV) for k in ("pixel_values", "coordinates", "input_ids", "src_attention_mask",
+                                                      "ocr_attention_mask", "tokenized_ocr")], max_length=8)
+    assert np.array_equal(ys.cpu().numpy(), g["generate_ids"])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_latr_loss_and_grads_match_oracle(dtype):
+    cfg = ref_model.tiny_config()
+    oracle, model = _latr_pair(cfg)
+    model.set_compute_dtype(dtype)
+    batch = ref_model.latr_batch(4, cfg, T=23, L_ocr=20, L_q=8, seed=9)
+    oracle.train(); model.train()
+    _no_dropout(oracle); _no_dropout(model)
+    ref_loss = ref_model.latr_loss(oracle, batch)
+    ref_loss.backward()
+    ref_grads = {k: p.grad.clone() for k, p in oracle.named_parameters() if p.grad is not None}
+    loss = ref_model.latr_loss(model, _to(batch, DEV))
+    loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= (1e-3 if dtype == torch.float32 else 3e-3) * abs(ref_loss.item())
+    got = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+    assert set(ref_grads) == set(got)
+    errs = {k: float((got[k].float().cpu() - gr).norm() / (gr.norm() + 1e-12)) for k, gr in ref_grads.items()}
+    if dtype == torch.float32:
+        worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+        assert worst[0][1] <= 1e-3, worst
+    else:
+        oracle.zero_grad(set_to_none=True)
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            l2 = ref_model.latr_loss(oracle, batch)
+        l2.backward()
+        base = {k: float((p.grad.float() - ref_grads[k]).norm() / (ref_grads[k].norm() + 1e-12))
+                for k, p in oracle.named_parameters() if p.grad is not None}
+        bad = {k: (errs[k], base[k]) for k in errs if errs[k] > 1.25 * base[k] + 1e-2}
+        assert not bad, bad

@@ -81,3 +81,48 @@ def test_product_model_state_dict_layout_matches_reference():
     oracle.load_state_dict(model.state_dict(), strict=True)       # product -> reference
     frozen = {k for k, p in model.named_parameters() if not p.requires_grad}
     assert frozen == {k for k, p in oracle.named_parameters() if not p.requires_grad}
+
+
+def test_latr_oracle_matches_reference_golden():
+    g = np.load(os.path.join(GOLD, "model_latr_tiny.npz"))
+    cfg = ref_model.tiny_config()
+    model = ref_model.LaTr(cfg)
+    assert list(model.state_dict().keys()) == list(g["state_dict_keys"])
+    model.load_state_dict(ref_model.deterministic_state_dict(model), strict=True)
+    batch = ref_model.latr_batch(3, cfg)
+    model.eval()
+    labels = batch["label_ids"]
+    logits = model(pixel_values=batch["pixel_values"], coordinates=batch["coordinates"], input_ids=batch["input_ids"],
+                   labels=labels[:, :-1], src_attention_mask=batch["src_attention_mask"],
+                   label_attention_mask=batch["label_attention_mask"][:, :-1],
+                   ocr_attention_mask=batch["ocr_attention_mask"], tokenized_ocr=batch["tokenized_ocr"])
+    np.testing.assert_allclose(logits.detach().numpy(), g["logits"], rtol=1e-5, atol=1e-6)
+    model.train()
+    _disable_dropout(model)
+    loss = ref_model.latr_loss(model, batch)
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), float(g["loss"]), rtol=1e-6)
+    grads = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+    assert sorted(grads.keys()) == list(g["grad_keys"])
+    norms = np.array([grads[k].double().norm().item() for k in sorted(grads.keys())])
+    np.testing.assert_allclose(norms, g["grad_norms"], rtol=1e-4, atol=1e-9)
+    model.eval()
+    ys = model.generate(batch["pixel_values"], batch["coordinates"], batch["input_ids"], batch["src_attention_mask"],
+                        batch["ocr_attention_mask"], batch["tokenized_ocr"], max_length=8)
+    assert np.array_equal(ys.numpy(), g["generate_ids"])
+
+
+def test_product_latr_state_dict_layout_matches_reference():
+    import phoneme_vqa_b200.models as M
+    g = np.load(os.path.join(GOLD, "model_latr_tiny.npz"))
+    cfg = ref_model.tiny_config()
+    model = M.LaTr(cfg)
+    sd = model.state_dict()
+    assert list(sd.keys()) == list(g["state_dict_keys"])
+    assert [json.dumps(list(v.shape)) for v in sd.values()] == list(g["state_dict_shapes"])
+    oracle = ref_model.LaTr(cfg)
+    model.load_state_dict(oracle.state_dict(), strict=True)
+    oracle.load_state_dict(model.state_dict(), strict=True)
+    # tied weights stay tied after loading
+    assert model.backbone.lm_head.weight is model.backbone.shared.weight
+    assert model.backbone.decoder.embed_tokens.weight is model.backbone.shared.weight
