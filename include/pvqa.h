@@ -159,6 +159,19 @@ int pvqa_phoneme_head_ce_bwd(const void* h, const int64_t* targets, int64_t tgt_
                              int w_dtype, int act_dtype, void* stream);
 
 /* ------------------------------------------------------------------------
+ * K4 large-vocabulary variant (LaTr): softmax + cross-entropy + gradient over a CHUNK of logits rows
+ * replaces  core/model/LaTr.py:83 (lm_head logits) + core/executor/base_executor.py:169 /
+ *           core/executor/LaTr_Executor.py:160-163 (CrossEntropyLoss(ignore_index=pad))
+ * logits (n,V) fp32 for one chunk of rows (the host produces them chunk by chunk with its GEMM library, so
+ * the full (B*T, 36096) logits / log-softmax / gradient tensors of the reference never exist);
+ * writes dlogits (n,V) bf16 = (softmax - onehot(target)) * (*inv_count) (zeros on ignored rows) and adds
+ * sum_n (lse_n - logit_n[target]) into *loss_sum.  inv_count = 1 / #non-ignored targets of the WHOLE batch.
+ * ------------------------------------------------------------------------ */
+int pvqa_vocab_ce_grad(const float* logits, const int64_t* targets, int64_t tgt_stride,
+                       const float* inv_count, float* loss_sum, void* dlogits_bf16,
+                       int64_t n, int64_t V, int64_t ignore_index, void* stream);
+
+/* ------------------------------------------------------------------------
  * K2 / K3  flash attention (tcgen05 + TMEM + TMA), bf16 in, fp32 accumulate
  * K2 replaces HF T5Attention.forward as called from core/model/PhonemeLaTr.py:111-114
  *    (transformers/models/t5/modeling_t5.py:253-345: unscaled QK^T + shared

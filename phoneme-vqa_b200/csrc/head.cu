@@ -196,6 +196,87 @@ static void launch_head(const HeadParams& p, int w_dtype, int act_dtype, cudaStr
   count_launch();
 }
 
+// ---------------------------------------------------------------------------------
+// K4 (large-vocabulary variant, LaTr): softmax + cross-entropy + gradient over one CHUNK of logits rows.
+// reference: core/model/LaTr.py:83 (lm_head) + core/executor/LaTr_Executor.py:160-163 / base_executor.py:169
+// (CrossEntropyLoss(ignore_index=pad)).  The host computes logits chunk-by-chunk with cuBLAS
+// (rows x 36096 fp32, ~150 MB, instead of the reference's 1.2 GB logits + 1.2 GB log-softmax + 1.2 GB grad),
+// this kernel turns a chunk in place into loss contributions and bf16 dlogits = (softmax - onehot) * inv_count,
+// which feed the dh / dW GEMMs of the same chunk.  One CTA per row, two passes (second one mostly from L2).
+// ---------------------------------------------------------------------------------
+constexpr int kCeThreads = 256;
+
+template <int VEC>
+__global__ void __launch_bounds__(kCeThreads)
+vocab_ce_grad_kernel(const float* __restrict__ logits, const int64_t* __restrict__ targets, long long tgt_stride,
+                     const float* __restrict__ inv_count, float* __restrict__ loss_sum,
+                     __nv_bfloat16* __restrict__ dlogits, int n, int V, long long ignore_index) {
+  __shared__ float s_m[kCeThreads / 32], s_s[kCeThreads / 32];
+  const int row = blockIdx.x;
+  if (row >= n) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* x = logits + (long long)row * V;
+  __nv_bfloat16* g = dlogits + (long long)row * V;
+  const long long tgt = targets[(long long)row * tgt_stride];
+  if (tgt == ignore_index) {                       // ignored row: zero gradient, no loss (CTA-uniform)
+    for (int c = tid * VEC; c < V; c += kCeThreads * VEC) {
+      if (VEC == 4) *reinterpret_cast<uint2*>(g + c) = make_uint2(0u, 0u);
+      else g[c] = __float2bfloat16_rn(0.f);
+    }
+    return;
+  }
+  float m = -INFINITY, s = 0.f;
+  for (int c = tid * VEC; c < V; c += kCeThreads * VEC) {
+    float v[4];
+    if (VEC == 4) { const float4 t = *reinterpret_cast<const float4*>(x + c); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else v[0] = x[c];
+    float mx = v[0];
+#pragma unroll
+    for (int k = 1; k < VEC; ++k) mx = fmaxf(mx, v[k]);
+    const float mn = fmaxf(m, mx);
+    float add = 0.f;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) add += __expf(v[k] - mn);
+    s = s * __expf(m - mn) + add;
+    m = mn;
+  }
+  // warp then block reduction of (m, s)
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const float mo = __shfl_xor_sync(0xffffffffu, m, o), so = __shfl_xor_sync(0xffffffffu, s, o);
+    const float mn = fmaxf(m, mo);
+    s = (m == -INFINITY ? 0.f : s * __expf(m - mn)) + (mo == -INFINITY ? 0.f : so * __expf(mo - mn));
+    m = mn;
+  }
+  if (lane == 0) { s_m[warp] = m; s_s[warp] = s; }
+  __syncthreads();
+  float M = s_m[0], S = s_s[0];
+#pragma unroll
+  for (int w = 1; w < kCeThreads / 32; ++w) {
+    const float mn = fmaxf(M, s_m[w]);
+    S = S * __expf(M - mn) + s_s[w] * __expf(s_m[w] - mn);
+    M = mn;
+  }
+  const float lse = M + __logf(S);
+  const float scale = *inv_count;
+  if (tid == 0) atomicAdd(loss_sum, lse - x[tgt]);
+  for (int c = tid * VEC; c < V; c += kCeThreads * VEC) {
+    float v[4];
+    if (VEC == 4) { const float4 t = *reinterpret_cast<const float4*>(x + c); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else v[0] = x[c];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) v[k] = (__expf(v[k] - lse) - ((long long)(c + k) == tgt ? 1.f : 0.f)) * scale;
+    if (VEC == 4) {
+      uint2 u;
+      u.x = f32x2_to_bf16x2(v[0], v[1]);
+      u.y = f32x2_to_bf16x2(v[2], v[3]);
+      *reinterpret_cast<uint2*>(g + c) = u;
+    } else {
+      g[c] = __float2bfloat16_rn(v[0]);
+    }
+  }
+}
+
 }  // namespace pvqa
 
 using namespace pvqa;
@@ -263,5 +344,26 @@ extern "C" int pvqa_phoneme_head_ce_bwd(const void* h, const int64_t* targets, i
   p.ignore_index = ignore_index;
   launch_head<1>(p, w_dtype, act_dtype, (cudaStream_t)stream);
   PVQA_CHECK_LAUNCH("phoneme_head_ce_bwd");
+  return PVQA_OK;
+}
+
+extern "C" int pvqa_vocab_ce_grad(const float* logits, const int64_t* targets, int64_t tgt_stride,
+                                  const float* inv_count, float* loss_sum, void* dlogits_bf16, int64_t n, int64_t V,
+                                  int64_t ignore_index, void* stream) {
+  PVQA_REQUIRE(n >= 0 && V > 0, PVQA_ERR_SHAPE, "vocab_ce_grad: bad dimension");
+  if (n == 0) return PVQA_OK;
+  PVQA_REQUIRE(logits && targets && inv_count && loss_sum && dlogits_bf16, PVQA_ERR_NULL, "vocab_ce_grad: NULL pointer");
+  PVQA_REQUIRE(n < (1ll << 31) && V < (1ll << 31), PVQA_ERR_SHAPE, "vocab_ce_grad: dimension too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (V % 4 == 0 && aligned16(logits) && (reinterpret_cast<uintptr_t>(dlogits_bf16) & 7) == 0)
+    vocab_ce_grad_kernel<4><<<(int)n, kCeThreads, 0, st>>>(logits, targets, tgt_stride, inv_count, loss_sum,
+                                                          reinterpret_cast<__nv_bfloat16*>(dlogits_bf16), (int)n, (int)V,
+                                                          ignore_index);
+  else
+    vocab_ce_grad_kernel<1><<<(int)n, kCeThreads, 0, st>>>(logits, targets, tgt_stride, inv_count, loss_sum,
+                                                          reinterpret_cast<__nv_bfloat16*>(dlogits_bf16), (int)n, (int)V,
+                                                          ignore_index);
+  count_launch();
+  PVQA_CHECK_LAUNCH("vocab_ce_grad");
   return PVQA_OK;
 }

@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .modules import (BaseDecoder, PhonemeEmbedding, SinusoidalPositionalEncoding, SpatialModule, T5EncoderModel,
+from .modules import (SHADOWS, BaseDecoder, PhonemeEmbedding, SinusoidalPositionalEncoding, SpatialModule, T5EncoderModel,
                       T5ForConditionalGeneration, T5Stack, _lin, _t5_init)
 
 __all__ = ["LaTr_config", "CustomizedLaTr_config", "CustomizedPreSTU_config", "PhonemeLaTr", "PhonemePreSTU", "LaTr"]
@@ -311,10 +311,12 @@ class LaTr(nn.Module, _VisionMixin):
     def forward_loss(self, pixel_values, coordinates, input_ids, labels, src_attention_mask, label_attention_mask,
                      ocr_attention_mask, tokenized_ocr, targets, ignore_index):
         """model forward + CrossEntropyLoss(ignore_index=pad) of core/executor/LaTr_Executor.py:160-163."""
-        logits = self.forward(pixel_values, coordinates, input_ids, labels, src_attention_mask, label_attention_mask,
-                              ocr_attention_mask, tokenized_ocr)
-        return torch.nn.functional.cross_entropy(logits.reshape(-1, logits.shape[-1]), targets.reshape(-1),
-                                                 ignore_index=ignore_index)
+        dec = self._decoder_hidden(pixel_values, coordinates, input_ids, labels, src_attention_mask,
+                                   label_attention_mask, ocr_attention_mask, tokenized_ocr)
+        h = dec.to(self.compute_dtype).reshape(-1, dec.shape[-1])
+        w = self.backbone.lm_head.weight
+        w_lp = SHADOWS.get([w], h.dtype) if h.dtype != w.dtype else None
+        return ops.vocab_head_ce(h, w, targets, ignore_index, w_lp=w_lp)
 
     # reference :99-111 — HF greedy generation from inputs_embeds (no encoder attention mask is passed there)
     @torch.no_grad()

@@ -594,3 +594,68 @@ def phoneme_head_ce(h, targets, W_onset, b_onset, W_rhyme, b_rhyme, W_tone, b_to
     """K4.  h (N,d) = shared_lm_head output, targets (N,3) int64.  Returns the scalar
     onset+rhyme+tone cross-entropy of core/executor/PhonemeLaTr_Executor.py:181-190."""
     return _PhonemeHeadCE.apply(h, targets, W_onset, b_onset, W_rhyme, b_rhyme, W_tone, b_tone, ignore_index)
+
+
+# ----------------------------------------------------------------------------------
+# K4 (large vocabulary, LaTr): chunked lm_head + cross-entropy; full logits never exist
+# ----------------------------------------------------------------------------------
+class _VocabHeadCE(torch.autograd.Function):
+    """loss = CE(h @ W^T, targets).  Forward walks the rows in chunks: cuBLAS logits chunk (fp32) ->
+    pvqa_vocab_ce_grad (loss + bf16 dlogits in one pass) -> cuBLAS dh chunk and dW accumulation.  The gradients
+    are therefore produced during forward (like fused linear-cross-entropy implementations) and only scaled
+    by the incoming grad in backward."""
+
+    @staticmethod
+    def forward(ctx, h, weight, w_lp, targets, ignore_index, chunk_rows):
+        lib = _lib.load()
+        _need_cuda(h, weight, targets)
+        N, d = h.shape
+        V = weight.shape[0]
+        dev = h.device
+        targets = targets.reshape(-1).contiguous()
+        cdt = h.dtype
+        w_c = w_lp if w_lp is not None else weight.to(cdt)
+        count = (targets != ignore_index).sum().to(torch.float32)
+        inv_count = (1.0 / count).reshape(1)          # inf -> nan loss when nothing is valid, like torch
+        loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
+        need_h = ctx.needs_input_grad[0]
+        need_w = ctx.needs_input_grad[1]
+        d_h = torch.empty((N, d), dtype=cdt, device=dev) if need_h else None
+        d_w = torch.zeros((V, d), dtype=torch.float32, device=dev) if need_w else None
+        hb = h if cdt == torch.bfloat16 else None
+        for r0 in range(0, N, chunk_rows):
+            r1 = min(N, r0 + chunk_rows)
+            hc = h[r0:r1]
+            logits = torch.mm(hc, w_c.t(), out_dtype=torch.float32) if cdt == torch.bfloat16 else hc @ w_c.t()
+            dl = torch.empty((r1 - r0, V), dtype=torch.bfloat16, device=dev)
+            with torch.cuda.device(dev), _prof("vocab_ce_grad"):
+                check(lib.pvqa_vocab_ce_grad(_p(logits), _p(targets[r0:r1]), 1, _p(inv_count), _p(loss_sum), _p(dl),
+                                             r1 - r0, V, int(ignore_index), _stream()), "pvqa_vocab_ce_grad")
+            if cdt == torch.bfloat16:
+                if need_h:
+                    torch.mm(dl, w_c, out=d_h[r0:r1])
+                if need_w:
+                    d_w = torch.addmm(d_w, dl.t(), hc, out_dtype=torch.float32)
+            else:                      # fp32 parity mode: keep the GEMMs in fp32
+                dlf = dl.float()
+                if need_h:
+                    torch.mm(dlf, w_c, out=d_h[r0:r1])
+                if need_w:
+                    d_w.addmm_(dlf.t(), hc)
+            del logits, dl
+        ctx.save_for_backward(d_h, d_w)
+        ctx.w_dtype = weight.dtype
+        return (loss_sum * inv_count).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        d_h, d_w = ctx.saved_tensors
+        gh = None if d_h is None else d_h * g.to(d_h.dtype)
+        gw = None if d_w is None else (d_w * g).to(ctx.w_dtype)
+        return gh, gw, None, None, None, None
+
+
+def vocab_head_ce(h, weight, targets, ignore_index, w_lp=None, chunk_rows=1024):
+    """K4-large.  h (N,d) decoder output, weight (V,d) lm_head (fp32 master; w_lp = optional bf16 shadow),
+    targets (N,) int64.  Returns mean cross-entropy over non-ignored targets."""
+    return _VocabHeadCE.apply(h.contiguous(), weight, w_lp, targets, ignore_index, int(chunk_rows))

@@ -60,3 +60,29 @@ def test_phoneme_head_ce_strided_targets_and_all_ignored_head():
     loss = ops.phoneme_head_ce(h.to(DEV), tview.to(DEV), Ws[0].to(DEV), bs[0].to(DEV), Ws[1].to(DEV), bs[1].to(DEV),
                                Ws[2].to(DEV), bs[2].to(DEV), -100)
     torch.testing.assert_close(loss.cpu(), ref, rtol=1e-5, atol=1e-6)
+
+
+# ------------------------------- K4 large-vocabulary variant (LaTr) ------------------------------------
+@pytest.mark.parametrize("N,d,V,dtype", [(50, 64, 120, torch.float32), (300, 192, 1000, torch.float32),
+                                         (2500, 768, 36096, torch.bfloat16), (7, 32, 37, torch.float32)])
+def test_vocab_head_ce_chunked(N, d, V, dtype):
+    from phoneme_vqa_b200 import ops
+    g = torch.Generator().manual_seed(N)
+    h = torch.randn(N, d, generator=g)
+    W = torch.randn(V, d, generator=g) * 0.05
+    tg = torch.randint(0, V, (N,), generator=g)
+    tg[torch.rand(N, generator=g) < 0.5] = 0            # pad id 0 ignored
+    hr = h.to(dtype).float().requires_grad_(True)
+    Wr = (W.to(dtype).float() if dtype == torch.bfloat16 else W.clone()).requires_grad_(True)
+    ref, _ = ref_ops.vocab_head_ce(hr, Wr, tg, ignore_index=0)
+    ref.backward()
+    hd = h.to(DEV).to(dtype).requires_grad_(True)
+    Wd = W.to(DEV).requires_grad_(True)
+    loss = ops.vocab_head_ce(hd, Wd, tg.to(DEV), 0, w_lp=(Wd.detach().to(dtype) if dtype != torch.float32 else None),
+                             chunk_rows=1024 if N > 1024 else 64)
+    loss.backward()
+    tol = 1e-5 if dtype == torch.float32 else 2e-3
+    torch.testing.assert_close(loss.cpu(), ref.detach(), rtol=tol, atol=tol)
+    gtol = 2e-2 if dtype == torch.float32 else 5e-2    # dlogits are stored in bf16
+    assert (hd.grad.float().cpu() - hr.grad).norm() / hr.grad.norm() <= gtol
+    assert (Wd.grad.float().cpu() - Wr.grad).norm() / Wr.grad.norm() <= gtol
