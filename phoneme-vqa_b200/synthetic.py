@@ -73,3 +73,23 @@ def phoneme_latr_batch(B, vocab_size, T=127, L_ocr=100, L_q=30, V_sub=PHONEME_VO
 
 def batch_bytes(batch) -> int:
     return sum(v.numel() * v.element_size() for v in batch.values())
+
+
+def latr_batch(B, vocab_size, T=127, L_ocr=100, L_q=30, seed=1234, image=224, device="cpu", pin=False):
+    """plain LaTr labels: "<pad> " + answer sub-tokens + eos (id 1), pad id 0; attention mask 1 = valid (int64)
+    (core/data/LaTrDataset.py answer encoding)."""
+    batch = phoneme_latr_batch(B, vocab_size, T=T, L_ocr=L_ocr, L_q=L_q, seed=seed, image=image)
+    g = torch.Generator().manual_seed(seed + 17)
+    ln = torch.randint(min(4, T), min(40, T) + 1, (B,), generator=g)
+    tpos = torch.arange(T + 1)[None, :]
+    lab = torch.randint(3, vocab_size, (B, T + 1), generator=g)
+    lab = torch.where(tpos == 0, torch.zeros_like(lab), lab)
+    lab = torch.where(tpos == ln[:, None], torch.ones_like(lab), lab)
+    lab = torch.where(tpos > ln[:, None], torch.zeros_like(lab), lab)
+    batch["label_ids"] = lab
+    batch["label_attention_mask"] = (tpos <= ln[:, None]).long()
+    if pin:
+        batch = {k: v.pin_memory() for k, v in batch.items()}
+    if device != "cpu":
+        batch = {k: v.to(device) for k, v in batch.items()}
+    return batch

@@ -72,12 +72,12 @@ def test_vocab_head_ce_chunked(N, d, V, dtype):
     W = torch.randn(V, d, generator=g) * 0.05
     tg = torch.randint(0, V, (N,), generator=g)
     tg[torch.rand(N, generator=g) < 0.5] = 0            # pad id 0 ignored
-    hr = h.to(dtype).float().requires_grad_(True)
+    hr = h.to(dtype).float().clone().requires_grad_(True)
     Wr = (W.to(dtype).float() if dtype == torch.bfloat16 else W.clone()).requires_grad_(True)
     ref, _ = ref_ops.vocab_head_ce(hr, Wr, tg, ignore_index=0)
     ref.backward()
-    hd = h.to(DEV).to(dtype).requires_grad_(True)
-    Wd = W.to(DEV).requires_grad_(True)
+    hd = h.detach().to(DEV).to(dtype).requires_grad_(True)
+    Wd = W.detach().to(DEV).requires_grad_(True)
     loss = ops.vocab_head_ce(hd, Wd, tg.to(DEV), 0, w_lp=(Wd.detach().to(dtype) if dtype != torch.float32 else None),
                              chunk_rows=1024 if N > 1024 else 64)
     loss.backward()
