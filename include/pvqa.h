@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PVQA_ABI_VERSION 3
+#define PVQA_ABI_VERSION 4
 
 typedef enum {
   PVQA_OK = 0,
@@ -189,6 +189,10 @@ int pvqa_vocab_ce_grad(const float* logits, const int64_t* targets, int64_t tgt_
  * key_add (B,Sk) fp32 or NULL: additive per-key term (0 / -inf for T5 masks; +1.0 / 0.0
  *   float masks of the reference decoder).
  * lse (B,H,Sq) fp32 out: log-sum-exp per row, saved for backward.
+ * scp_bucket (B,L,L) uint8 + scp_table (H,32) fp32, or NULL: the SaL family's spatial (SCP) bias
+ *   (core/model/modules/SaL_utils.py:131-195,208-223): s += scp_table[h][scp_bucket[b][i-q0][j-q0]] for
+ *   q0 <= i,j < q0+L (the OCR x OCR block), computed in-kernel instead of materialising (B,H,S,S) fp32.
+ *   q0 and L must be multiples of 16.  Backward accumulates d_scp_table (H,32).
  * dropout_p > 0: inverted dropout on the softmax probabilities (HF modeling_t5.py:332 /
  *   nn.MultiheadAttention dropout) with an in-kernel Philox4x32-10 stream keyed by
  *   (seed, offset, b, h, i, j); p is quantised to 1/256.  Backward must get the same triple.
@@ -201,7 +205,9 @@ int pvqa_attn_fwd(const void* q, const void* k, const void* v, void* o, float* l
                   int64_t v_stride_b, int64_t v_stride_s, int64_t v_stride_h,
                   int64_t o_stride_b, int64_t o_stride_s, int64_t o_stride_h,
                   float scale, int causal,
-                  float dropout_p, uint64_t seed, uint64_t offset, void* stream);
+                  float dropout_p, uint64_t seed, uint64_t offset,
+                  const uint8_t* scp_bucket, const float* scp_table, int64_t scp_q0, int64_t scp_L,
+                  void* stream);
 
 /* backward.  dk, dv: bf16 with explicit strides (may point into a packed d(qkv) buffer).
  * dq_accum: fp32 (B,Sq,H,64) contiguous, ZERO-INITIALISED by the caller — every 128-key tile
@@ -221,7 +227,9 @@ int pvqa_attn_bwd(const void* q, const void* k, const void* v, const void* o, co
                   int64_t dk_stride_b, int64_t dk_stride_s, int64_t dk_stride_h,
                   int64_t dv_stride_b, int64_t dv_stride_s, int64_t dv_stride_h,
                   float scale, int causal,
-                  float dropout_p, uint64_t seed, uint64_t offset, void* stream);
+                  float dropout_p, uint64_t seed, uint64_t offset,
+                  const uint8_t* scp_bucket, const float* scp_table, float* d_scp_table,
+                  int64_t scp_q0, int64_t scp_L, void* stream);
 
 /* ------------------------------------------------------------------------
  * fp32 parity-mode attention (CUDA cores, no tensor-core rounding): same score definition as
@@ -237,7 +245,9 @@ int pvqa_attn_f32_fwd(const float* q, const float* k, const float* v, float* o, 
                       int64_t v_stride_b, int64_t v_stride_s, int64_t v_stride_h,
                       int64_t o_stride_b, int64_t o_stride_s, int64_t o_stride_h,
                       float scale, int causal,
-                      float dropout_p, uint64_t seed, uint64_t offset, void* stream);
+                      float dropout_p, uint64_t seed, uint64_t offset,
+                      const uint8_t* scp_bucket, const float* scp_table, int64_t scp_q0, int64_t scp_L,
+                      void* stream);
 
 int pvqa_attn_f32_bwd(const float* q, const float* k, const float* v, const float* o, const float* d_o,
                       const float* lse, const float* rel_bias, const float* key_add,
@@ -252,7 +262,9 @@ int pvqa_attn_f32_bwd(const float* q, const float* k, const float* v, const floa
                       int64_t dk_stride_b, int64_t dk_stride_s, int64_t dk_stride_h,
                       int64_t dv_stride_b, int64_t dv_stride_s, int64_t dv_stride_h,
                       float scale, int causal,
-                      float dropout_p, uint64_t seed, uint64_t offset, void* stream);
+                      float dropout_p, uint64_t seed, uint64_t offset,
+                      const uint8_t* scp_bucket, const float* scp_table, float* d_scp_table,
+                      int64_t scp_q0, int64_t scp_L, void* stream);
 
 /* ------------------------------------------------------------------------
  * Fused glue of the transformer blocks (HBM-bound, one launch each)

@@ -147,6 +147,26 @@ def golden_latr():
     print("latr golden: loss", loss.item(), "generate", ys.tolist())
 
 
+def golden_sal_bias():
+    """real outputs of the reference's bias modules (they import; only T52DStack does not run — SURVEY D8)."""
+    from core.model.modules.SaL_utils import (RelativePositionBias1D, RelativePositionBiasAggregated,
+                                              SCPRelativePositionBias)
+    H, B, S, q0, L = 3, 2, 64, 16, 32
+    agg = RelativePositionBiasAggregated(Relative1D=RelativePositionBias1D(num_heads=H, device="cpu"),
+                                         SCP=SCPRelativePositionBias(num_heads=H, device="cpu"))
+    agg.load_state_dict(ref_model.deterministic_state_dict(agg, scale=1.0))
+    g = torch.Generator().manual_seed(12)
+    xy = torch.rand(B, L, 2, generator=g) * 0.8
+    coords = torch.cat([xy, xy + torch.rand(B, L, 2, generator=g) * 0.19], dim=-1)
+    out = agg(torch.zeros(B, S, 8), torch.ones(B, S), coords, q0, L)
+    np.savez_compressed(os.path.join(GOLD, "sal_bias.npz"), coords=coords.numpy(), bias=out.detach().numpy(),
+                        H=H, S=S, q0=q0, L=L,
+                        rel_table=agg.Relative1D.relative_attention_bias.weight.detach().numpy(),
+                        scp_table=agg.SCP.relative_attention_bias.weight.detach().numpy(),
+                        state_dict_keys=np.array(list(agg.state_dict().keys())))
+    print("sal bias golden", tuple(out.shape))
+
+
 def golden_ops():
     """op-level goldens from reference modules: SpatialModule, SinusoidalPositionalEncoding."""
     import importlib
@@ -174,6 +194,7 @@ if __name__ == "__main__":
     golden_ops()
     golden_model()
     golden_latr()
+    golden_sal_bias()
     try:
         from oracle import make_golden_text
         make_golden_text.main()

@@ -248,6 +248,170 @@ def latr_batch(B, cfg, T=19, L_ocr=12, L_q=6, seed=3, image=32):
     return b
 
 
+# ----------------------------------------------------------------------------------
+# SaL family.  The reference's T52DStack (a copy of HF-4.x T5Stack.forward with `position_bias` injected,
+# core/model/modules/SaL_utils.py:226-500) does not run under transformers 5.5, so the encoder is
+# restated as a loop over HF T5Block with the external bias: no attention mask is added when the
+# bias is external, and layer 0's own relative_attention_bias stays an unused parameter.  The bias modules DO
+# import; tests/golden/sal_bias.npz holds their real outputs.
+# ----------------------------------------------------------------------------------
+def scp_distance_lut(grid=11):
+    """core/model/modules/SaL_utils.py:171-195: 5 * Euclidean cell distance, (x, y, x', y')."""
+    xs, ys = np.mgrid[0:grid, 0:grid]
+    out = np.zeros((grid, grid, grid, grid))
+    for x in range(grid):
+        for y in range(grid):
+            out[x, y] = np.sqrt((xs - x) ** 2 + (ys - y) ** 2)
+    return out * 5
+
+
+def sal_position_bias(rel_table, scp_table, S, coordinates, max_ques, max_ocr):
+    """core/model/modules/SaL_utils.py:81-120,131-139,152-168,208-223 -> (B,H,S,S)."""
+    B = coordinates.shape[0]
+    pos = torch.arange(S)
+    rel = ref_ops.t5_relative_bucket((pos[None, :] - pos[:, None]).numpy(), True, 32, 128)
+    bias = torch.nn.functional.embedding(torch.as_tensor(rel), rel_table).permute(2, 0, 1)[None].repeat(B, 1, 1, 1)
+    xc = coordinates[:, :, [0, 2]].mean(dim=-1)
+    yc = coordinates[:, :, [1, 3]].mean(dim=-1)
+    xi = np.int32(np.floor(xc.numpy() * 11))
+    yi = np.int32(np.floor(yc.numpy() * 11))
+    lut = scp_distance_lut()
+    d = lut[xi[:, :, None], yi[:, :, None], xi[:, None, :], yi[:, None, :]]          # (B,L,L)
+    bk = ref_ops.t5_relative_bucket(torch.tensor(d).to(torch.long).numpy(), True, 32, 100)
+    scp = torch.nn.functional.embedding(torch.as_tensor(bk), scp_table).permute(0, 3, 1, 2)
+    bias[:, :, max_ques:max_ques + max_ocr, max_ques:max_ques + max_ocr] += scp
+    return bias
+
+
+class _BiasTable(nn.Module):
+    def __init__(self, num_heads):
+        super().__init__()
+        self.relative_attention_bias = nn.Embedding(32, num_heads)
+
+
+class _BiasAggregated(nn.Module):
+    def __init__(self, num_heads):
+        super().__init__()
+        self.Relative1D = _BiasTable(num_heads)
+        self.SCP = _BiasTable(num_heads)
+
+
+# core/model/PhonemeSaL.py:28-207
+class PhonemeSaL(nn.Module):
+    def __init__(self, config, vocab_size, obj_dropout=0.1, ocr_dropout=0.1):
+        super().__init__()
+        from transformers.models.t5.modeling_t5 import T5LayerNorm
+        self.config = config
+        self.vocab_size = vocab_size
+        self.encoder = T5EncoderModel(config)
+        self.encoder.resize_token_embeddings(config.new_token_embedding_size)
+        self.rel2Dbias = _BiasAggregated(config.num_heads)
+        d = config.d_model
+        self.obj_dropout = nn.Dropout(obj_dropout)
+        self.obj_feature_projector = nn.Linear(config.obj_hidden, d)
+        self.obj_bbox_projector = nn.Linear(4, d)
+        self.obj_feature_layer_norm = T5LayerNorm(d)
+        self.ocr_dropout = nn.Dropout(ocr_dropout)
+        self.ocr_feature_projector = nn.Linear(config.ocr_hidden, d)
+        self.ocr_bbox_projector = nn.Linear(4, d)
+        self.ocr_feature_layer_norm = T5LayerNorm(d)
+        self.tgt_tok_emb = nn.Embedding(vocab_size, d)
+        self.positional_encoding = SinusoidalPositionalEncoding(d, dropout=0.1)
+        self.decoder = BaseDecoder(d, config.num_decoder_layers, config.n_head)
+        self.lm_head = nn.Linear(d, vocab_size)
+        self.loss_fn = nn.CrossEntropyLoss(ignore_index=0)
+
+    def _encode(self, b):
+        obj = (self.obj_feature_layer_norm(self.obj_feature_projector(b["obj_features"]))
+               + self.obj_feature_layer_norm(self.obj_bbox_projector(b["obj_coordinates"]))
+               + self.encoder.shared(b["tokenized_obj"]))
+        ocr = (self.ocr_feature_layer_norm(self.ocr_feature_projector(b["ocr_features"]))
+               + self.ocr_feature_layer_norm(self.ocr_bbox_projector(b["ocr_coordinates"]))
+               + self.encoder.shared(b["tokenized_ocr"]))
+        feat = torch.cat([self.encoder.shared(b["input_ids"]), ocr, obj], dim=1)
+        mask = torch.cat([b["src_attention_mask"], b["ocr_attention_mask"], b["obj_attention_mask"]], dim=1)
+        bias = sal_position_bias(self.rel2Dbias.Relative1D.relative_attention_bias.weight,
+                                 self.rel2Dbias.SCP.relative_attention_bias.weight, feat.shape[1],
+                                 b["ocr_coordinates"], b["max_ques"], b["max_ocr"])
+        stack = self.encoder.encoder
+        h = stack.dropout(feat)
+        for blk in stack.block:
+            h = blk(h, attention_mask=None, position_bias=bias)[0]
+        h = stack.dropout(stack.final_layer_norm(h))
+        return h, mask
+
+    def decode(self, labels, enc, enc_mask, label_mask=None):
+        emb = self.positional_encoding(self.tgt_tok_emb(labels))
+        return self.decoder(emb, enc, tgt_mask=PhonemeLaTr._square_mask(labels.size(1), labels.device),
+                            memory_key_padding_mask=enc_mask, tgt_key_padding_mask=label_mask)
+
+    def forward(self, b):
+        enc, mask = self._encode(b)
+        dec = self.decode(b["label_ids"], enc, mask, b["label_attention_mask"])
+        logits = self.lm_head(dec)
+        loss = self.loss_fn(logits.reshape((-1, self.vocab_size)), b["shifted_right_label_ids"].reshape(-1))
+        return logits, loss
+
+    @torch.no_grad()
+    def generate(self, b, start_symbol, end_symbol, max_len=100):
+        enc, mask = self._encode(b)
+        bz = b["input_ids"].size(0)
+        ys = torch.tensor([start_symbol], dtype=torch.long).repeat(bz, 1)
+        brk = torch.zeros_like(ys).fill_(0)
+        for _ in range(max_len):
+            out = self.decode(ys, enc, mask)
+            nxt = torch.argmax(self.lm_head(out)[:, -1], dim=-1)
+            brk = torch.where((nxt == end_symbol)[:, None], 1, brk)
+            ys = torch.cat([ys, nxt.unsqueeze(1)], dim=1)
+            if torch.all(brk):
+                break
+        return ys
+
+
+def sal_config(**kw):
+    cfg = tiny_config(**kw)
+    cfg.update({"ocr_hidden": 24, "obj_hidden": 40, "new_token_embedding_size": 130})
+    return cfg
+
+
+def sal_batch(B, cfg, T=11, L_q=16, L_ocr=32, L_obj=16, vocab=253, seed=5):
+    """field names / dtypes of core/data/PhonemeSaLDataset.py:78-92 (float masks, bool label mask, boxes in [0,1))."""
+    g = torch.Generator().manual_seed(seed)
+    V = cfg.new_token_embedding_size
+
+    def toks(L):
+        ids = torch.zeros(B, L, dtype=torch.long)
+        mask = torch.zeros(B, L)
+        for i in range(B):
+            n = int(torch.randint(1, L, (1,), generator=g))
+            ids[i, :n] = torch.randint(3, V, (n,), generator=g)
+            ids[i, n] = 1
+            mask[i, : n + 1] = 1
+        return ids, mask
+
+    q, qm = toks(L_q)
+    ocr, om = toks(L_ocr)
+    obj, bm = toks(L_obj)
+
+    def boxes(L):
+        xy = torch.rand(B, L, 2, generator=g) * 0.8
+        wh = torch.rand(B, L, 2, generator=g) * 0.19
+        return torch.cat([xy, xy + wh], dim=-1)
+
+    labels = torch.zeros(B, T + 1, dtype=torch.long)
+    for i in range(B):
+        n = int(torch.randint(2, T, (1,), generator=g))
+        labels[i, 0] = 1
+        labels[i, 1:n] = torch.randint(4, vocab, (n - 1,), generator=g)
+        labels[i, n] = 2
+    return {"input_ids": q, "src_attention_mask": qm, "label_ids": labels[:, :-1],
+            "shifted_right_label_ids": labels[:, 1:], "label_attention_mask": labels[:, :-1] == 0,
+            "tokenized_ocr": ocr, "ocr_attention_mask": om, "ocr_coordinates": boxes(L_ocr),
+            "ocr_features": torch.randn(B, L_ocr, cfg.ocr_hidden, generator=g),
+            "tokenized_obj": obj, "obj_attention_mask": bm, "obj_coordinates": boxes(L_obj),
+            "obj_features": torch.randn(B, L_obj, cfg.obj_hidden, generator=g), "max_ocr": L_ocr, "max_ques": L_q}
+
+
 # core/executor/PhonemeLaTr_Executor.py:161-196 — one training step's loss
 def phoneme_latr_loss(model, batch, pad_id):
     labels = batch["label_ids"]

@@ -77,7 +77,29 @@ struct AttnFwdParams {
   float drop_scale;           // 1 / keep probability
   uint64_t seed, offset;
   const unsigned long long* rng_base;
+  // SaL spatial (SCP) bias: bias += scp_tab[h][scp_bucket[b][i-q0][j-q0]] on the OCR x OCR block
+  const uint8_t* scp_bucket;  // (B, L, L) or null
+  const float* scp_tab;       // (H, 32)
+  int scp_q0, scp_L;
 };
+
+// 32 bucket ids (bytes) of one row chunk -> add the staged per-head table values; chunk starts are multiples of 16
+// relative to the block (host checks q0 % 16 == 0 and L % 16 == 0), so each 16-byte half is inside or outside.
+__device__ __forceinline__ void load_scp32(const uint8_t* row, int jj0, int L, const float* s_tab, float (&out)[32]) {
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+    const int jj = jj0 + hf * 16;
+    if (jj >= 0 && jj < L) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(row + jj));
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int k = 0; k < 16; ++k) out[hf * 16 + k] = s_tab[(w[k >> 2] >> (8 * (k & 3))) & 31u];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) out[hf * 16 + k] = 0.f;
+    }
+  }
+}
 
 template <bool HAS_REL, bool DROP>
 __global__ void __launch_bounds__(kFwdThreads, 2)
@@ -96,7 +118,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int n_kpad = n_tiles_all * kBN;
   float* s_kadd = reinterpret_cast<float*>(smem + kOffFloats);       // [n_kpad], -inf beyond Sk
   float* s_rel = s_kadd + n_kpad;                                     // [kRelPad + Sq + n_kpad], index r + kRelPad
+  float* s_scp = s_rel + (HAS_REL ? kRelPad + p.Sq + n_kpad : 0);     // [32] SCP table of this head (SaL)
   const int n_rel = p.Sq + p.Sk - 1;
+  const bool has_scp = HAS_REL && p.scp_bucket != nullptr;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rowl = (warp & 3) * 32 + lane;          // row in the tile == TMEM lane
@@ -123,6 +147,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int r = x - kRelPad;
       s_rel[x] = (r >= 0 && r < n_rel) ? p.rel_bias[(long long)h * n_rel + r] * kLog2e : 0.f;
     }
+    if (has_scp && tid < 32) s_scp[tid] = p.scp_tab[h * 32 + tid] * kLog2e;
   }
   tc05::tc_fence_before_sync();
   __syncthreads();
@@ -154,6 +179,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t thr4 = p.drop_thr8 * 0x01010101u;
   const uint64_t drop_row = ((uint64_t)(b * p.H + h) * p.Sq + min(i, p.Sq - 1)) * (uint64_t)((p.Sk + 15) >> 4);
   const uint64_t rng_off = p.offset + ((DROP && p.rng_base) ? *p.rng_base : 0ull);
+  const uint8_t* scp_row = nullptr;                 // this row's bucket ids inside the OCR block, if it is in it
+  if (has_scp && i >= p.scp_q0 && i < p.scp_q0 + p.scp_L && i < p.Sq)
+    scp_row = p.scp_bucket + ((long long)b * p.scp_L + (i - p.scp_q0)) * p.scp_L;
 
   float m_run = -INFINITY, l_run = 0.f;
   float o_acc[32];
@@ -196,7 +224,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       uint32_t r[32];
       tc05::tmem_ld_32x32(tmem_row + half * 64 + c * 32, r);
       tc05::tmem_ld_wait();
-      if (diag) {
+      if (has_scp && scp_row != nullptr && jb + 32 > p.scp_q0 && jb < p.scp_q0 + p.scp_L) {
+        float sb[32];
+        load_scp32(scp_row, jb - p.scp_q0, p.scp_L, s_scp, sb);
+#pragma unroll
+        for (int x = 0; x < 32; ++x) {
+          const float s = fmaf(__uint_as_float(r[x]), sl2, s_kadd[jb + x] + relrow[jb + x] + sb[x]);
+          mx = fmaxf(mx, s);
+          r[x] = __float_as_uint(s);
+        }
+      } else if (diag) {
 #pragma unroll
         for (int x = 0; x < 32; ++x) {
           float bias = s_kadd[jb + x];
@@ -353,6 +390,10 @@ struct AttnBwdParams {
   float drop_scale;
   uint64_t seed, offset;
   const unsigned long long* rng_base;
+  const uint8_t* scp_bucket;  // SaL SCP bias (see AttnFwdParams)
+  const float* scp_tab;
+  float* d_scp;               // (H, 32) fp32 accumulated, or null
+  int scp_q0, scp_L;
 };
 
 struct AttnPrepParams {
@@ -399,6 +440,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   float* s_kadd = reinterpret_cast<float*>(smem + kBOffFloats);  // [kBN], -inf beyond Sk
   float* s_rel = s_kadd + kBN;                                   // [kRelPad + n_win] bias * log2e (index w + kRelPad)
   float* s_drel = s_rel + kRelPad + n_win;                       // [n_win] gradient accumulator (smem atomics)
+  float* s_scp = s_drel + n_win;                                 // [32] SCP table of this head
+  float* s_dscp = s_scp + 32;                                    // [16 warps][32] SCP gradient bins
+  const bool has_scp = HAS_REL && p.scp_bucket != nullptr;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rowl = (warp & 3) * 32 + lane;     // row inside the 128-row tile == TMEM lane
@@ -427,6 +471,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       s_rel[x] = (x >= kRelPad && r < n_rel) ? p.rel_bias[(long long)h * n_rel + r] * kLog2e : 0.f;
     }
     for (int x = tid; x < n_win; x += kBwdThreads2) s_drel[x] = 0.f;
+    if (has_scp) {
+      if (tid < 32) s_scp[tid] = p.scp_tab[h * 32 + tid] * kLog2e;
+      s_dscp[tid] = 0.f;                       // 512 threads == 16 x 32 bins
+    }
   }
   tc05::tc_fence_before_sync();
   __syncthreads();
@@ -506,13 +554,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tc05::tmem_ld_32x32(tmem_row + kBN + jl0, rp);
       tc05::tmem_ld_wait();
       float pv[32], dsv[32];
+      const uint8_t* scp_row = nullptr;
+      const int jj0 = j0 + jl0 - p.scp_q0;           // this chunk's first column inside the OCR block
+      if (has_scp && row_ok && i >= p.scp_q0 && i < p.scp_q0 + p.scp_L && jj0 + 32 > 0 && jj0 < p.scp_L)
+        scp_row = p.scp_bucket + ((long long)b * p.scp_L + (i - p.scp_q0)) * p.scp_L;
+      if (scp_row) {
+        float sb[32];
+        load_scp32(scp_row, jj0, p.scp_L, s_scp, sb);
 #pragma unroll
-      for (int x = 0; x < 32; ++x) {
-        float bias = s_kadd[jl0 + x];
-        if (HAS_REL) bias += relrow[jl0 + x];
-        float s = fmaf(__uint_as_float(rs[x]), sl2, bias);
-        if (diag && (j0 + jl0 + x > i)) s = -INFINITY;
-        pv[x] = fast_exp2(s - lse2);
+        for (int x = 0; x < 32; ++x)
+          pv[x] = fast_exp2(fmaf(__uint_as_float(rs[x]), sl2, s_kadd[jl0 + x] + relrow[jl0 + x] + sb[x]) - lse2);
+      } else {
+#pragma unroll
+        for (int x = 0; x < 32; ++x) {
+          float bias = s_kadd[jl0 + x];
+          if (HAS_REL) bias += relrow[jl0 + x];
+          float s = fmaf(__uint_as_float(rs[x]), sl2, bias);
+          if (diag && (j0 + jl0 + x > i)) s = -INFINITY;
+          pv[x] = fast_exp2(s - lse2);
+        }
       }
       if (DROP) {      // P_drop = P*M/keep feeds dV; dP = M/keep * dP_drop feeds dS
         const uint64_t drop_row = ((uint64_t)(b * p.H + h) * p.Sq + min(i, p.Sq - 1)) * (uint64_t)((p.Sk + 15) >> 4);
@@ -534,6 +594,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       } else {
 #pragma unroll
         for (int x = 0; x < 32; ++x) dsv[x] = pv[x] * (__uint_as_float(rp[x]) - delta) * p.scale;
+      }
+      if (scp_row && p.d_scp) {
+        // d_scp[bucket] += dS on the OCR x OCR block: per-warp shared-memory bins (conflicting lanes serialise)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int jj = jj0 + hf * 16;
+          if (jj >= 0 && jj < p.scp_L) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(scp_row + jj));
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+              atomicAdd(s_dscp + warp * 32 + ((w[k >> 2] >> (8 * (k & 3))) & 31u), dsv[hf * 16 + k]);
+          }
+        }
       }
       if (HAS_REL && p.d_rel) {
         // d_rel[j-i] += dS: this warp holds a 32x32 block (lane = row, register = column).  Lane L collects the
@@ -633,6 +707,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   tc05::tc_fence_before_sync();
   __syncthreads();
+  if (has_scp && p.d_scp && tid < 32) {
+    float g = 0.f;
+#pragma unroll
+    for (int w = 0; w < kBwdThreads2 / 32; ++w) g += s_dscp[w * 32 + tid];
+    if (g != 0.f) atomicAdd(p.d_scp + h * 32 + tid, g / p.scale);
+  }
   if (warp == 0) tc05::tmem_dealloc(tmem_base, kBwdTmemCols);
 }
 
@@ -683,8 +763,16 @@ extern "C" int pvqa_attn_fwd(const void* q, const void* k, const void* v, void* 
                              int64_t k_stride_b, int64_t k_stride_s, int64_t k_stride_h, int64_t v_stride_b,
                              int64_t v_stride_s, int64_t v_stride_h, int64_t o_stride_b, int64_t o_stride_s,
                              int64_t o_stride_h, float scale, int causal, float dropout_p, uint64_t seed,
-                             uint64_t offset, void* stream) {
+                             uint64_t offset, const uint8_t* scp_bucket, const float* scp_table, int64_t scp_q0,
+                             int64_t scp_L, void* stream) {
   PVQA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, PVQA_ERR_SHAPE, "attn_fwd: dropout_p must be in [0,1)");
+  if (scp_bucket) {
+    PVQA_REQUIRE(rel_bias && scp_table, PVQA_ERR_NULL, "attn_fwd: the SCP bias needs rel_bias and scp_table");
+    PVQA_REQUIRE(!causal && Sq == Sk && scp_q0 >= 0 && scp_L > 0 && scp_q0 + scp_L <= Sk, PVQA_ERR_SHAPE,
+                 "attn_fwd: bad SCP block");
+    PVQA_REQUIRE(scp_q0 % 16 == 0 && scp_L % 16 == 0 && aligned16(scp_bucket), PVQA_ERR_ALIGN,
+                 "attn_fwd: SCP block offset/size must be multiples of 16");
+  }
   PVQA_REQUIRE(D == kD, PVQA_ERR_SHAPE, "attn_fwd: head dim %lld unsupported (kernel is specialised for 64)", (long long)D);
   PVQA_REQUIRE(B >= 0 && H > 0 && Sq >= 0 && Sk >= 0, PVQA_ERR_SHAPE, "attn_fwd: bad dimension");
   if (B == 0 || Sq == 0) return PVQA_OK;
@@ -696,7 +784,7 @@ extern "C" int pvqa_attn_fwd(const void* q, const void* k, const void* v, void* 
                    o_stride_b % 8 == 0,
                PVQA_ERR_ALIGN, "attn_fwd: output rows must be 16-byte aligned");
   const int64_t n_kpad = (Sk + kBN - 1) / kBN * kBN;
-  const int64_t n_floats = n_kpad + (rel_bias ? kRelPad + Sq + n_kpad : 0);
+  const int64_t n_floats = n_kpad + (rel_bias ? kRelPad + Sq + n_kpad + 32 : 0);
   const size_t smem_bytes = 1024 + kOffFloats + (size_t)n_floats * 4;
   PVQA_REQUIRE(smem_bytes <= 113 * 1024, PVQA_ERR_SHAPE,
                "attn_fwd: Sq/Sk too large for the bias staging buffers (2 CTAs per SM budget)");
@@ -713,6 +801,7 @@ extern "C" int pvqa_attn_fwd(const void* q, const void* k, const void* v, void* 
   p.drop_thr8 = (uint32_t)lrintf(dropout_p * 256.f);
   p.drop_scale = p.drop_thr8 ? 256.f / (256.f - (float)p.drop_thr8) : 1.f;
   p.seed = seed; p.offset = offset; p.rng_base = g_rng_base;
+  p.scp_bucket = scp_bucket; p.scp_tab = scp_table; p.scp_q0 = (int)scp_q0; p.scp_L = (int)scp_L;
   const bool rel = rel_bias != nullptr, drop = p.drop_thr8 != 0;
   auto kern = rel ? (drop ? attn_fwd_kernel<true, true> : attn_fwd_kernel<true, false>)
                   : (drop ? attn_fwd_kernel<false, true> : attn_fwd_kernel<false, false>);
@@ -739,8 +828,16 @@ extern "C" int pvqa_attn_bwd(const void* q, const void* k, const void* v, const 
                              int64_t o_stride_s, int64_t o_stride_h, int64_t do_stride_b, int64_t do_stride_s,
                              int64_t do_stride_h, int64_t dk_stride_b, int64_t dk_stride_s, int64_t dk_stride_h,
                              int64_t dv_stride_b, int64_t dv_stride_s, int64_t dv_stride_h, float scale, int causal,
-                             float dropout_p, uint64_t seed, uint64_t offset, void* stream) {
+                             float dropout_p, uint64_t seed, uint64_t offset, const uint8_t* scp_bucket,
+                             const float* scp_table, float* d_scp_table, int64_t scp_q0, int64_t scp_L, void* stream) {
   PVQA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, PVQA_ERR_SHAPE, "attn_bwd: dropout_p must be in [0,1)");
+  if (scp_bucket) {
+    PVQA_REQUIRE(rel_bias && scp_table, PVQA_ERR_NULL, "attn_bwd: the SCP bias needs rel_bias and scp_table");
+    PVQA_REQUIRE(!causal && Sq == Sk && scp_q0 >= 0 && scp_L > 0 && scp_q0 + scp_L <= Sk, PVQA_ERR_SHAPE,
+                 "attn_bwd: bad SCP block");
+    PVQA_REQUIRE(scp_q0 % 16 == 0 && scp_L % 16 == 0 && aligned16(scp_bucket), PVQA_ERR_ALIGN,
+                 "attn_bwd: SCP block offset/size must be multiples of 16");
+  }
   PVQA_REQUIRE(D == kD, PVQA_ERR_SHAPE, "attn_bwd: head dim %lld unsupported (kernel is specialised for 64)", (long long)D);
   PVQA_REQUIRE(B >= 0 && H > 0 && Sq >= 0 && Sk >= 0, PVQA_ERR_SHAPE, "attn_bwd: bad dimension");
   if (B == 0 || Sq == 0 || Sk == 0) return PVQA_OK;
@@ -755,7 +852,7 @@ extern "C" int pvqa_attn_bwd(const void* q, const void* k, const void* v, const 
                    al8(dk_stride_b, dk_stride_s, dk_stride_h) && al8(dv_stride_b, dv_stride_s, dv_stride_h),
                PVQA_ERR_ALIGN, "attn_bwd: rows must be 16-byte aligned");
   const int64_t n_win = Sq + kBN - 1;
-  const int64_t n_floats = kBN + (rel_bias ? kRelPad + 2 * n_win : 0);
+  const int64_t n_floats = kBN + (rel_bias ? kRelPad + 2 * n_win + 32 + 512 : 0);
   const size_t smem_bytes = 1024 + kBOffFloats + (size_t)n_floats * 4;
   PVQA_REQUIRE(smem_bytes <= 225 * 1024, PVQA_ERR_SHAPE, "attn_bwd: Sq too large for the bias window buffers");
   CUtensorMap tq, tk, tv, tdo;
@@ -787,6 +884,7 @@ extern "C" int pvqa_attn_bwd(const void* q, const void* k, const void* v, const 
   p.drop_thr8 = (uint32_t)lrintf(dropout_p * 256.f);
   p.drop_scale = p.drop_thr8 ? 256.f / (256.f - (float)p.drop_thr8) : 1.f;
   p.seed = seed; p.offset = offset; p.rng_base = g_rng_base;
+  p.scp_bucket = scp_bucket; p.scp_tab = scp_table; p.d_scp = d_scp_table; p.scp_q0 = (int)scp_q0; p.scp_L = (int)scp_L;
   const bool rel = rel_bias != nullptr, drop = p.drop_thr8 != 0;
   auto kern = rel ? (drop ? attn_bwd_kernel<true, true> : attn_bwd_kernel<true, false>)
                   : (drop ? attn_bwd_kernel<false, true> : attn_bwd_kernel<false, false>);

@@ -24,6 +24,7 @@ struct SimtParams {
   long long dosb, doss, dosh, dqsb, dqss, dqsh, dksb, dkss, dksh, dvsb, dvss, dvsh;
   float scale; int causal;
   uint32_t drop_thr8; float drop_scale; uint64_t seed, offset; const unsigned long long* rng_base;
+  const uint8_t* scp_bucket; const float* scp_tab; float* d_scp; int scp_q0, scp_L;
 };
 
 __device__ __forceinline__ float warp_sum(float x) {
@@ -51,6 +52,11 @@ __device__ __forceinline__ float score(const SimtParams& p, float dot, int b, in
   float s = dot * p.scale;
   if (p.rel_bias) s += p.rel_bias[(long long)h * (p.Sq + p.Sk - 1) + (j - i + p.Sq - 1)];
   if (p.key_add) s += p.key_add[(long long)b * p.Sk + j];
+  if (p.scp_bucket) {
+    const int ii = i - p.scp_q0, jj = j - p.scp_q0;
+    if (ii >= 0 && ii < p.scp_L && jj >= 0 && jj < p.scp_L)
+      s += p.scp_tab[h * 32 + (p.scp_bucket[((long long)b * p.scp_L + ii) * p.scp_L + jj] & 31)];
+  }
   if (p.causal && j > i) s = -INFINITY;
   return s;
 }
@@ -132,6 +138,11 @@ attn_f32_bwd_q_kernel(const SimtParams p) {
     const float ds = pr * (dP - delta);
     s_ds[j] = ds;
     if (p.d_rel && ds != 0.f) atomicAdd(p.d_rel + (long long)h * (p.Sq + p.Sk - 1) + (j - i + p.Sq - 1), ds);
+    if (p.d_scp && ds != 0.f) {
+      const int ii = i - p.scp_q0, jj = j - p.scp_q0;
+      if (ii >= 0 && ii < p.scp_L && jj >= 0 && jj < p.scp_L)
+        atomicAdd(p.d_scp + h * 32 + (p.scp_bucket[((long long)b * p.scp_L + ii) * p.scp_L + jj] & 31), ds);
+    }
   }
   __syncwarp();
   float a0 = 0.f, a1 = 0.f;
@@ -212,7 +223,8 @@ extern "C" int pvqa_attn_f32_fwd(const float* q, const float* k, const float* v,
                                  int64_t k_stride_b, int64_t k_stride_s, int64_t k_stride_h, int64_t v_stride_b,
                                  int64_t v_stride_s, int64_t v_stride_h, int64_t o_stride_b, int64_t o_stride_s,
                                  int64_t o_stride_h, float scale, int causal, float dropout_p, uint64_t seed,
-                                 uint64_t offset, void* stream) {
+                                 uint64_t offset, const uint8_t* scp_bucket, const float* scp_table, int64_t scp_q0,
+                                 int64_t scp_L, void* stream) {
   const int64_t st[] = {q_stride_b, q_stride_s, q_stride_h, k_stride_b, k_stride_s, k_stride_h,
                         v_stride_b, v_stride_s, v_stride_h, o_stride_b, o_stride_s, o_stride_h};
   int rc = simt_common_checks("attn_f32_fwd", B, H, Sq, Sk, D, causal, dropout_p, st, 12);
@@ -231,6 +243,9 @@ extern "C" int pvqa_attn_f32_fwd(const float* q, const float* k, const float* v,
   p.drop_thr8 = (uint32_t)lrintf(dropout_p * 256.f);
   p.drop_scale = p.drop_thr8 ? 256.f / (256.f - (float)p.drop_thr8) : 1.f;
   p.seed = seed; p.offset = offset; p.rng_base = g_rng_base;
+  p.scp_bucket = scp_bucket; p.scp_tab = scp_table; p.scp_q0 = (int)scp_q0; p.scp_L = (int)scp_L;
+  PVQA_REQUIRE(!scp_bucket || (scp_table && scp_q0 >= 0 && scp_L > 0 && scp_q0 + scp_L <= Sk && Sq == Sk), PVQA_ERR_SHAPE,
+               "attn_f32_fwd: bad SCP block");
   const size_t smem = (size_t)kSimtWarps * (kSD + ((Sk + 3) & ~3)) * sizeof(float);
   static size_t smem_cap = 48 * 1024;
   if (smem > smem_cap) {
@@ -255,7 +270,8 @@ extern "C" int pvqa_attn_f32_bwd(const float* q, const float* k, const float* v,
                                  int64_t do_stride_h, int64_t dq_stride_b, int64_t dq_stride_s, int64_t dq_stride_h,
                                  int64_t dk_stride_b, int64_t dk_stride_s, int64_t dk_stride_h, int64_t dv_stride_b,
                                  int64_t dv_stride_s, int64_t dv_stride_h, float scale, int causal, float dropout_p,
-                                 uint64_t seed, uint64_t offset, void* stream) {
+                                 uint64_t seed, uint64_t offset, const uint8_t* scp_bucket, const float* scp_table,
+                                 float* d_scp_table, int64_t scp_q0, int64_t scp_L, void* stream) {
   const int64_t st[] = {q_stride_b, q_stride_s, q_stride_h, k_stride_b, k_stride_s, k_stride_h, v_stride_b,
                         v_stride_s, v_stride_h, o_stride_b, o_stride_s, o_stride_h, do_stride_b, do_stride_s,
                         do_stride_h, dq_stride_b, dq_stride_s, dq_stride_h, dk_stride_b, dk_stride_s, dk_stride_h,
@@ -281,6 +297,9 @@ extern "C" int pvqa_attn_f32_bwd(const float* q, const float* k, const float* v,
   p.drop_thr8 = (uint32_t)lrintf(dropout_p * 256.f);
   p.drop_scale = p.drop_thr8 ? 256.f / (256.f - (float)p.drop_thr8) : 1.f;
   p.seed = seed; p.offset = offset; p.rng_base = g_rng_base;
+  p.scp_bucket = scp_bucket; p.scp_tab = scp_table; p.d_scp = d_scp_table; p.scp_q0 = (int)scp_q0; p.scp_L = (int)scp_L;
+  PVQA_REQUIRE(!scp_bucket || (scp_table && scp_q0 >= 0 && scp_L > 0 && scp_q0 + scp_L <= Sk && Sq == Sk), PVQA_ERR_SHAPE,
+               "attn_f32_bwd: bad SCP block");
   cudaStream_t st_ = (cudaStream_t)stream;
   const size_t smem_q = (size_t)kSimtWarps * (2 * kSD + ((Sk + 3) & ~3)) * sizeof(float);
   const size_t smem_kv = (size_t)kSimtWarps * (2 * kSD + 2 * ((Sq + 3) & ~3)) * sizeof(float);

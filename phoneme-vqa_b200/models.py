@@ -15,10 +15,11 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .modules import (SHADOWS, BaseDecoder, PhonemeEmbedding, SinusoidalPositionalEncoding, SpatialModule, T5EncoderModel,
+from .modules import (SHADOWS, BaseDecoder, RelativePositionBias1D, RelativePositionBiasAggregated,
+                      SCPRelativePositionBias, T5LayerNorm, PhonemeEmbedding, SinusoidalPositionalEncoding, SpatialModule, T5EncoderModel,
                       T5ForConditionalGeneration, T5Stack, _lin, _t5_init)
 
-__all__ = ["LaTr_config", "CustomizedLaTr_config", "CustomizedPreSTU_config", "PhonemeLaTr", "PhonemePreSTU", "LaTr"]
+__all__ = ["LaTr_config", "CustomizedLaTr_config", "CustomizedPreSTU_config", "PhonemeLaTr", "PhonemePreSTU", "LaTr", "PhonemeSaL", "CustomizedSaL_config"]
 
 
 def _random_init(config) -> bool:
@@ -338,6 +339,130 @@ class LaTr(nn.Module, _VisionMixin):
             nxt = torch.where(done, torch.full_like(nxt, cfg.pad_token_id), nxt)
             ys = torch.cat([ys, nxt[:, None]], dim=1)
             done = done | (nxt == cfg.eos_token_id)
+            if bool(done.all()):
+                break
+        return ys
+
+
+# reference: core/model/PhonemeSaL.py:15-25
+class CustomizedSaL_config:
+    def build(self, config, new_token_embedding_size):
+        model_config = _auto_config(config.backbone_name)
+        model_config.update({"ocr_hidden": config.ocr_hidden, "obj_hidden": config.obj_hidden,
+                             "new_token_embedding_size": new_token_embedding_size,
+                             "num_decoder_layers": config.num_decoder_layers, "n_head": config.n_head})
+        return model_config
+
+
+class PhonemeSaL(nn.Module):
+    """reference: core/model/PhonemeSaL.py:28-207.  question ‖ OCR(det+rec features, box, token) ‖ objects ->
+    T5 encoder with EXTERNAL 1-D + SCP position bias (the attention mask is then NOT applied: HF only adds it
+    when it computes the bias itself — SURVEY D14) -> 4-layer target decoder over the flat 253-phoneme
+    vocabulary -> lm_head, CrossEntropyLoss(ignore_index=0) inside the model."""
+
+    def __init__(self, config, vocab_size, obj_dropout=0.1, ocr_dropout=0.1):
+        super().__init__()
+        self.config = config
+        self.vocab_size = vocab_size
+        self.compute_dtype = torch.float32
+        self.encoder = T5EncoderModel(config)
+        _load_pretrained_t5_encoder(self.encoder, config)
+        new_size = getattr(config, "new_token_embedding_size", None)
+        if new_size is not None and new_size != self.encoder.shared.num_embeddings:
+            self._resize_token_embeddings(new_size)
+        self.rel2Dbias = RelativePositionBiasAggregated(
+            Relative1D=RelativePositionBias1D(num_heads=config.num_heads),
+            SCP=SCPRelativePositionBias(num_heads=config.num_heads))
+        d = config.d_model
+        self.obj_dropout = nn.Dropout(obj_dropout)          # declared by the reference, never applied (:44,:49)
+        self.obj_feature_projector = nn.Linear(config.obj_hidden, d)
+        self.obj_bbox_projector = nn.Linear(4, d)
+        self.obj_feature_layer_norm = T5LayerNorm(d)
+        self.ocr_dropout = nn.Dropout(ocr_dropout)
+        self.ocr_feature_projector = nn.Linear(config.ocr_hidden, d)
+        self.ocr_bbox_projector = nn.Linear(4, d)
+        self.ocr_feature_layer_norm = T5LayerNorm(d)
+        self.tgt_tok_emb = nn.Embedding(num_embeddings=vocab_size, embedding_dim=d)
+        self.positional_encoding = SinusoidalPositionalEncoding(d, dropout=0.1)
+        self.decoder = BaseDecoder(emb_size=d, num_layers=config.num_decoder_layers, n_head=config.n_head)
+        self.lm_head = nn.Linear(d, vocab_size)
+        self.loss_fn = nn.CrossEntropyLoss(ignore_index=0)
+
+    def set_compute_dtype(self, dtype):
+        assert dtype in (torch.float32, torch.bfloat16)
+        self.compute_dtype = dtype
+        return self
+
+    def _resize_token_embeddings(self, n):
+        old = self.encoder.shared
+        new = nn.Embedding(n, old.embedding_dim)
+        nn.init.normal_(new.weight, mean=0.0, std=self.config.initializer_factor)
+        k = min(n, old.num_embeddings)
+        new.weight.data[:k] = old.weight.data[:k]
+        self.encoder.shared = new
+        self.encoder.encoder.embed_tokens = new
+
+    # reference :194-202 — the same T5LayerNorm module normalises both the feature and the box projection
+    def _modality_embedding(self, tokens, coords, feats, feat_proj, box_proj, norm):
+        cd = self.compute_dtype
+        a = norm(_lin(feats.to(cd), feat_proj.weight, feat_proj.bias).float(), out_dtype=torch.float32)
+        b = norm(_lin(coords.to(cd), box_proj.weight, box_proj.bias).float(), out_dtype=torch.float32)
+        return a + b + torch.nn.functional.embedding(tokens, self.encoder.shared.weight)
+
+    def _calculate_obj_embedding(self, tokenized_obj, obj_coordinates, obj_features):
+        return self._modality_embedding(tokenized_obj, obj_coordinates, obj_features, self.obj_feature_projector,
+                                        self.obj_bbox_projector, self.obj_feature_layer_norm)
+
+    def _calculate_ocr_embedding(self, tokenized_ocr, ocr_coordinates, ocr_features):
+        return self._modality_embedding(tokenized_ocr, ocr_coordinates, ocr_features, self.ocr_feature_projector,
+                                        self.ocr_bbox_projector, self.ocr_feature_layer_norm)
+
+    def _encode(self, input_ids, src_attention_mask, tokenized_ocr, ocr_attention_mask, ocr_coordinates, ocr_features,
+                tokenized_obj, obj_attention_mask, obj_coordinates, obj_features, max_ocr, max_ques):
+        obj = self._calculate_obj_embedding(tokenized_obj, obj_coordinates, obj_features)
+        ocr = self._calculate_ocr_embedding(tokenized_ocr, ocr_coordinates, ocr_features)
+        ques = torch.nn.functional.embedding(input_ids, self.encoder.shared.weight)
+        feat = torch.cat([ques, ocr, obj], dim=1)
+        mask = torch.cat([src_attention_mask, ocr_attention_mask, obj_attention_mask], dim=1)
+        rel, scp = self.rel2Dbias(feat.shape[1], ocr_coordinates, int(max_ques), int(max_ocr))
+        enc = self.encoder.encoder(feat, None, compute_dtype=self.compute_dtype, external_rel_bias=rel, scp=scp)
+        return enc, mask
+
+    # reference :122-131
+    def decode(self, labels, encoder_outputs, encoder_attention_mask, label_attention_mask=None):
+        emb = self.positional_encoding(torch.nn.functional.embedding(labels, self.tgt_tok_emb.weight))
+        return self.decoder(emb, encoder_outputs, memory_key_padding_mask=encoder_attention_mask,
+                            tgt_key_padding_mask=label_attention_mask, compute_dtype=self.compute_dtype, causal=True)
+
+    # reference :73-120
+    def forward(self, input_ids, src_attention_mask, label_ids, shifted_right_label_ids, label_attention_mask,
+                tokenized_ocr, ocr_attention_mask, ocr_coordinates, ocr_features, tokenized_obj, obj_attention_mask,
+                obj_coordinates, obj_features, max_ocr, max_ques):
+        enc, mask = self._encode(input_ids, src_attention_mask, tokenized_ocr, ocr_attention_mask, ocr_coordinates,
+                                 ocr_features, tokenized_obj, obj_attention_mask, obj_coordinates, obj_features,
+                                 max_ocr, max_ques)
+        dec = self.decode(label_ids, enc, mask, label_attention_mask)
+        logits = _lin(dec.to(self.compute_dtype), self.lm_head.weight, self.lm_head.bias).float()
+        loss = self.loss_fn(logits.reshape((-1, self.vocab_size)), shifted_right_label_ids.reshape(-1))
+        return logits, loss
+
+    # reference :134-192
+    @torch.no_grad()
+    def generate(self, input_ids, src_attention_mask, tokenized_ocr, ocr_attention_mask, ocr_coordinates,
+                 ocr_features, tokenized_obj, obj_attention_mask, obj_coordinates, obj_features, max_ocr, max_ques,
+                 start_symbol, end_symbol, max_len=100):
+        bz = input_ids.size(0)
+        enc, mask = self._encode(input_ids, src_attention_mask, tokenized_ocr, ocr_attention_mask, ocr_coordinates,
+                                 ocr_features, tokenized_obj, obj_attention_mask, obj_coordinates, obj_features,
+                                 max_ocr, max_ques)
+        ys = torch.full((bz, 1), start_symbol, dtype=torch.long, device=input_ids.device)
+        done = torch.zeros_like(ys)
+        for _ in range(max_len):
+            out = self.decode(ys, enc, mask)
+            logits = _lin(out[:, -1:].to(self.compute_dtype), self.lm_head.weight, self.lm_head.bias).float()
+            nxt = logits[:, -1].argmax(-1)
+            done = torch.where((nxt == end_symbol)[:, None], torch.ones_like(done), done)
+            ys = torch.cat([ys, nxt.unsqueeze(1)], dim=1)
             if bool(done.all()):
                 break
         return ys

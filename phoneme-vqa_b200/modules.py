@@ -224,6 +224,25 @@ class T5LayerNorm(nn.Module):
 _BUCKET_CACHE: dict = {}
 
 
+def t5_bucket(rel, bidirectional=True, num_buckets=32, max_distance=128):
+    """HF T5Attention._relative_position_bucket (modeling_t5.py:190-235) on a LongTensor, evaluated with the
+    same torch float32 ops so bucket ids are bit-exact."""
+    nb = num_buckets
+    buckets = torch.zeros_like(rel)
+    if bidirectional:
+        nb //= 2
+        buckets = buckets + (rel > 0).long() * nb
+        rp = rel.abs()
+    else:
+        rp = -torch.min(rel, torch.zeros_like(rel))
+    max_exact = nb // 2
+    is_small = rp < max_exact
+    large = max_exact + (torch.log(rp.float() / max_exact) / math.log(max_distance / max_exact)
+                         * (nb - max_exact)).long()
+    large = torch.min(large, torch.full_like(large, nb - 1))
+    return buckets + torch.where(is_small, rp, large)
+
+
 def t5_bucket_lut(q_len, k_len, bidirectional, num_buckets, max_distance, device):
     """bucket id for every relative offset rel = j - i in [-(q_len-1), k_len-1] (HF formula,
     modeling_t5.py:190-235, evaluated with the same torch float32 ops so ids are bit-exact)."""
@@ -274,7 +293,7 @@ class T5Attention(nn.Module):
                             self.relative_attention_max_distance, self.relative_attention_bias.weight.device)
         return self.relative_attention_bias.weight.float()[lut].t().contiguous()
 
-    def forward(self, x, rel_bias, key_add, kv=None, causal=False, dense_bias=None):
+    def forward(self, x, rel_bias, key_add, kv=None, causal=False, scp=None):
         """x (B,S,d) compute dtype.  Self-attention when kv is None, else cross-attention on kv."""
         B, S, _ = x.shape
         H, D = self.n_heads, self.key_value_proj_dim
@@ -282,7 +301,7 @@ class T5Attention(nn.Module):
         if kv is None:
             qkv = _lin_multi(x, [self.q.weight, self.k.weight, self.v.weight]).view(B, S, 3, H, D)
             o = ops.attention_self(qkv, scale=1.0, rel_bias=rel_bias, key_add=key_add, causal=causal,
-                                   dropout_p=p_drop, dense_bias=dense_bias)
+                                   dropout_p=p_drop, scp=scp)
         else:
             q = _lin(x, self.q.weight).view(B, S, H, D)
             kvp = _lin_multi(kv, [self.k.weight, self.v.weight]).view(B, kv.shape[1], 2, H, D)
@@ -297,9 +316,9 @@ class T5LayerSelfAttention(nn.Module):
         self.layer_norm = T5LayerNorm(config.d_model, eps=config.layer_norm_epsilon)
         self.dropout = nn.Dropout(config.dropout_rate)
 
-    def forward(self, hidden, rel_bias, key_add, compute_dtype, causal=False, dense_bias=None):
+    def forward(self, hidden, rel_bias, key_add, compute_dtype, causal=False, scp=None):
         normed = self.layer_norm(hidden, out_dtype=compute_dtype)
-        attn = self.SelfAttention(normed, rel_bias, key_add, causal=causal, dense_bias=dense_bias)
+        attn = self.SelfAttention(normed, rel_bias, key_add, causal=causal, scp=scp)
         return ops.residual_dropout_add(hidden, attn, self.dropout.p, self.training)
 
 
@@ -375,8 +394,8 @@ class T5Block(nn.Module):
         self.layer.append(T5LayerFF(config))
 
     def forward(self, hidden, rel_bias, key_add, compute_dtype, memory=None, memory_key_add=None, causal=False,
-                dense_bias=None):
-        hidden = self.layer[0](hidden, rel_bias, key_add, compute_dtype, causal=causal, dense_bias=dense_bias)
+                scp=None):
+        hidden = self.layer[0](hidden, rel_bias, key_add, compute_dtype, causal=causal, scp=scp)
         if self.is_decoder:
             hidden = self.layer[1](hidden, memory, memory_key_add, compute_dtype)
         return self.layer[-1](hidden, compute_dtype)
@@ -430,10 +449,10 @@ class T5Stack(nn.Module):
         return torch.where(attention_mask != 0, 0.0, float("-inf")).to(torch.float32)
 
     def forward(self, inputs_embeds, attention_mask=None, compute_dtype=torch.float32, memory=None,
-                memory_mask=None, external_rel_bias=None, dense_bias=None):
+                memory_mask=None, external_rel_bias=None, scp=None):
         hidden = F.dropout(inputs_embeds.float(), self.dropout.p, self.training)
         S = hidden.shape[1]
-        if dense_bias is not None or external_rel_bias is not None:
+        if external_rel_bias is not None:
             rel_bias = external_rel_bias     # SaL: bias supplied by the caller, mask NOT added
             key_add = None
         else:
@@ -443,7 +462,7 @@ class T5Stack(nn.Module):
         mem_key_add = self.key_add_from_mask(memory_mask) if memory is not None else None
         for blk in self.block:
             hidden = blk(hidden, rel_bias, key_add, compute_dtype, memory=mem, memory_key_add=mem_key_add,
-                         causal=self.is_decoder, dense_bias=dense_bias)
+                         causal=self.is_decoder, scp=scp)
         hidden = self.final_layer_norm(hidden, out_dtype=torch.float32)
         return F.dropout(hidden, self.dropout.p, self.training)
 
@@ -583,3 +602,67 @@ class BaseDecoder(nn.Module):
         for layer in self.decoder.layers:
             x = layer(x, mem, tka, mka, compute_dtype, causal=causal)
         return x
+
+
+# ----------------------------------------------------------------------------------
+# SaL family: 1-D + spatial (SCP) relative position bias
+# reference: core/model/modules/SaL_utils.py:24-223.  The reference materialises (B,H,S,S) fp32 and makes a
+# GPU -> CPU -> numpy -> GPU round trip per forward (:161-168); here the 1-D part is the (H, 2S-1) relative
+# vector of the attention kernels and the SCP part is a uint8 bucket map (B, L_ocr, L_ocr) computed on the
+# device from a 121 x 121 cell-distance LUT, looked up inside the kernels.
+# ----------------------------------------------------------------------------------
+class _RelBiasTable(nn.Module):
+    def __init__(self, num_heads, num_buckets=32):
+        super().__init__()
+        self.relative_attention_bias = nn.Embedding(num_buckets, num_heads)
+
+
+class RelativePositionBias1D(_RelBiasTable):
+    def rel_vector(self, S):
+        lut = t5_bucket_lut(S, S, True, 32, 128, self.relative_attention_bias.weight.device)
+        return self.relative_attention_bias.weight.float()[lut].t().contiguous()
+
+
+class SCPRelativePositionBias(_RelBiasTable):
+    GRID = 11
+
+    def __init__(self, num_heads, num_buckets=32):
+        super().__init__(num_heads, num_buckets)
+        g = self.GRID
+        xs, ys = np.mgrid[0:g, 0:g]
+        cells = np.stack([xs.reshape(-1), ys.reshape(-1)], axis=1).astype(np.float64)       # cell id = x * 11 + y
+        dist = np.sqrt(((cells[:, None, :] - cells[None, :, :]) ** 2).sum(-1)) * 5           # SaL_utils.py:171-195
+        rel = torch.tensor(dist).to(torch.long)                                               # truncation, :166
+        lut = t5_bucket(rel, bidirectional=True, num_buckets=num_buckets, max_distance=100)   # :66-73 with :127
+        self.register_buffer("cell_bucket_lut", lut.to(torch.uint8), persistent=False)
+
+    def buckets(self, coordinates):
+        """coordinates (B,L,4) in [0,1) -> uint8 (B,L,L) bucket ids (SaL_utils.py:152-168, on the device)."""
+        g = self.GRID
+        xc = coordinates[:, :, [0, 2]].mean(dim=-1)
+        yc = coordinates[:, :, [1, 3]].mean(dim=-1)
+        cx = torch.floor(xc * g).to(torch.long).clamp_(0, g - 1)
+        cy = torch.floor(yc * g).to(torch.long).clamp_(0, g - 1)
+        cell = cx * g + cy
+        return self.cell_bucket_lut[cell[:, :, None], cell[:, None, :]].contiguous()
+
+
+class RelativePositionBiasAggregated(nn.Module):
+    def __init__(self, Relative1D, SCP):
+        super().__init__()
+        self.Relative1D = Relative1D
+        self.SCP = SCP
+
+    def forward(self, S, coordinates, max_ques, max_ocr):
+        """-> (rel_vector (H, 2S-1), (scp buckets u8 (B,L,L), scp table (32,H), q0))"""
+        return self.Relative1D.rel_vector(S), (self.SCP.buckets(coordinates[:, :max_ocr]),
+                                               self.SCP.relative_attention_bias.weight, int(max_ques))
+
+    def dense(self, S, coordinates, max_ques, max_ocr):
+        """the reference's materialised (B,H,S,S) tensor (tests / debugging only)"""
+        rel, (bk, tab, q0) = self.forward(S, coordinates, max_ques, max_ocr)
+        i = torch.arange(S, device=rel.device)
+        dense = rel[:, (i[None, :] - i[:, None] + S - 1)][None].repeat(coordinates.shape[0], 1, 1, 1)
+        L = bk.shape[-1]
+        dense[:, :, q0:q0 + L, q0:q0 + L] += tab.float()[bk.long()].permute(0, 3, 1, 2)
+        return dense

@@ -401,7 +401,15 @@ def _drop_args(dropout_p, B, H, Sq, Sk):
     return float(dropout_p), seed, off
 
 
-def attention_fwd_raw(q, k, v, scale, rel_bias=None, key_add=None, causal=False, drop=(0.0, 0, 0)):
+def _scp_args(scp):
+    """(bucket u8 (B,L,L), table_t fp32 (H,32), q0) -> ctypes args (bucket, table, q0, L)"""
+    if scp is None:
+        return None, None, 0, 0
+    bucket, table_t, q0 = scp
+    return _p(bucket), _p(table_t), int(q0), int(bucket.shape[-1])
+
+
+def attention_fwd_raw(q, k, v, scale, rel_bias=None, key_add=None, causal=False, drop=(0.0, 0, 0), scp=None):
     """Forward through the C-ABI.  q (B,Sq,H,D), k/v (B,Sk,H,D) strided views (bf16 or fp32).
     Returns (o (B,Sq,H,D) same dtype, lse (B,H,Sq) fp32)."""
     lib = _lib.load()
@@ -424,11 +432,12 @@ def attention_fwd_raw(q, k, v, scale, rel_bias=None, key_add=None, causal=False,
     with torch.cuda.device(dev), _prof(f"{name}[Sq={Sq},Sk={Sk}]"):
         check(fn(_p(q), _p(k), _p(v), _p(o), _p(lse), _p(rel_bias), _p(key_add), B, H, Sq, Sk, D,
                  *_st3(q), *_st3(k), *_st3(v), *_st3(o), float(scale), int(bool(causal)),
-                 float(drop[0]), int(drop[1]), int(drop[2]), _stream()), "pvqa_" + name)
+                 float(drop[0]), int(drop[1]), int(drop[2]), *_scp_args(scp), _stream()), "pvqa_" + name)
     return o, lse
 
 
-def attention_bwd_raw(q, k, v, o, d_o, lse, scale, rel_bias, key_add, causal, dk, dv, want_d_rel, drop=(0.0, 0, 0)):
+def attention_bwd_raw(q, k, v, o, d_o, lse, scale, rel_bias, key_add, causal, dk, dv, want_d_rel, drop=(0.0, 0, 0),
+                      scp=None, want_d_scp=False):
     """Backward through the C-ABI.  dk/dv are caller-provided (B,Sk,H,D) views (possibly into a packed
     buffer) in q's dtype.  Returns (dq fp32 (B,Sq,H,D), d_rel fp32 or None)."""
     lib = _lib.load()
@@ -436,6 +445,8 @@ def attention_bwd_raw(q, k, v, o, d_o, lse, scale, rel_bias, key_add, causal, dk
     Sk = k.shape[1]
     dev = q.device
     d_rel = torch.zeros((H, Sq + Sk - 1), dtype=torch.float32, device=dev) if want_d_rel else None
+    d_scp = torch.zeros((H, 32), dtype=torch.float32, device=dev) if (scp is not None and want_d_scp) else None
+    sb, st_, sq0, sL = _scp_args(scp)
     d_o = d_o.to(q.dtype)
     if d_o.stride(3) != 1:
         d_o = d_o.contiguous()
@@ -447,7 +458,7 @@ def attention_bwd_raw(q, k, v, o, d_o, lse, scale, rel_bias, key_add, causal, dk
                                     _p(dq), _p(dk), _p(dv), _p(d_rel), _p(ws), B, H, Sq, Sk, D,
                                     *_st3(q), *_st3(k), *_st3(v), *_st3(o), *_st3(d_o), *_st3(dk), *_st3(dv),
                                     float(scale), int(bool(causal)), float(drop[0]), int(drop[1]), int(drop[2]),
-                                    _stream()), "pvqa_attn_bwd")
+                                    sb, st_, _p(d_scp), sq0, sL, _stream()), "pvqa_attn_bwd")
     else:
         dq = torch.empty((B, Sq, H, D), dtype=torch.float32, device=dev)
         ws = torch.empty((B, H, Sq), dtype=torch.float32, device=dev)
@@ -456,8 +467,8 @@ def attention_bwd_raw(q, k, v, o, d_o, lse, scale, rel_bias, key_add, causal, dk
                                         _p(dq), _p(dk), _p(dv), _p(d_rel), _p(ws), B, H, Sq, Sk, D,
                                         *_st3(q), *_st3(k), *_st3(v), *_st3(o), *_st3(d_o), *_st3(dq), *_st3(dk),
                                         *_st3(dv), float(scale), int(bool(causal)), float(drop[0]), int(drop[1]),
-                                        int(drop[2]), _stream()), "pvqa_attn_f32_bwd")
-    return dq, d_rel
+                                        int(drop[2]), sb, st_, _p(d_scp), sq0, sL, _stream()), "pvqa_attn_f32_bwd")
+    return dq, d_rel, d_scp
 
 
 def _prep_bias(rel_bias, key_add):
@@ -470,26 +481,35 @@ class _AttnSelf(torch.autograd.Function):
     """packed (B,S,3,H,D) projection -> (B,S,H,D); d(qkv) comes back packed for the QKV GEMM backward."""
 
     @staticmethod
-    def forward(ctx, qkv, rel_bias, key_add, scale, causal, dropout_p):
+    def forward(ctx, qkv, rel_bias, key_add, scale, causal, dropout_p, scp_bucket, scp_table, scp_q0):
         rb, ka = _prep_bias(rel_bias, key_add)
         qkv = qkv.contiguous()
         B, S, _, H, _ = qkv.shape
         drop = _drop_args(dropout_p, B, H, S, S)
-        o, lse = attention_fwd_raw(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], scale, rb, ka, causal, drop)
-        ctx.save_for_backward(qkv, o, lse, rb, ka)
+        scp = None
+        if scp_bucket is not None:
+            if scp_bucket.dtype != torch.uint8 or scp_bucket.dim() != 3:
+                raise TypeError("scp_bucket must be uint8 (B,L,L)")
+            scp = (scp_bucket.contiguous(), scp_table.detach().to(torch.float32).t().contiguous(), int(scp_q0))
+        o, lse = attention_fwd_raw(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], scale, rb, ka, causal, drop, scp)
+        ctx.save_for_backward(qkv, o, lse, rb, ka, *(scp[:2] if scp else ()))
         ctx.meta = (float(scale), bool(causal), rel_bias is not None and ctx.needs_input_grad[1],
-                    None if rel_bias is None else rel_bias.dtype, drop)
+                    None if rel_bias is None else rel_bias.dtype, drop,
+                    None if scp is None else scp[2], scp is not None and ctx.needs_input_grad[7],
+                    None if scp_table is None else scp_table.dtype)
         return o
 
     @staticmethod
     def backward(ctx, d_o):
-        qkv, o, lse, rb, ka = ctx.saved_tensors
-        scale, causal, want_rel, rel_dtype, drop = ctx.meta
+        qkv, o, lse, rb, ka, *scp_t = ctx.saved_tensors
+        scale, causal, want_rel, rel_dtype, drop, scp_q0, want_scp, scp_dtype = ctx.meta
+        scp = (scp_t[0], scp_t[1], scp_q0) if scp_t else None
         dqkv = torch.empty_like(qkv)
-        dq, d_rel = attention_bwd_raw(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], o, d_o, lse, scale, rb, ka, causal,
-                                      dqkv[:, :, 1], dqkv[:, :, 2], want_rel, drop)
+        dq, d_rel, d_scp = attention_bwd_raw(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], o, d_o, lse, scale, rb, ka,
+                                             causal, dqkv[:, :, 1], dqkv[:, :, 2], want_rel, drop, scp, want_scp)
         dqkv[:, :, 0].copy_(dq)
-        return dqkv, (d_rel.to(rel_dtype) if want_rel else None), None, None, None, None
+        return (dqkv, (d_rel.to(rel_dtype) if want_rel else None), None, None, None, None, None,
+                (d_scp.t().to(scp_dtype) if want_scp else None), None)
 
 
 class _AttnCross(torch.autograd.Function):
@@ -512,17 +532,17 @@ class _AttnCross(torch.autograd.Function):
         q, kv, o, lse, rb, ka = ctx.saved_tensors
         scale, want_rel, rel_dtype, drop = ctx.meta
         dkv = torch.empty_like(kv)
-        dq, d_rel = attention_bwd_raw(q, kv[:, :, 0], kv[:, :, 1], o, d_o, lse, scale, rb, ka, False,
-                                      dkv[:, :, 0], dkv[:, :, 1], want_rel, drop)
+        dq, d_rel, _ = attention_bwd_raw(q, kv[:, :, 0], kv[:, :, 1], o, d_o, lse, scale, rb, ka, False,
+                                         dkv[:, :, 0], dkv[:, :, 1], want_rel, drop)
         return dq.to(q.dtype), dkv, (d_rel.to(rel_dtype) if want_rel else None), None, None, None
 
 
-def attention_self(qkv, scale, rel_bias=None, key_add=None, causal=False, dropout_p=0.0, dense_bias=None):
+def attention_self(qkv, scale, rel_bias=None, key_add=None, causal=False, dropout_p=0.0, scp=None):
     """qkv (B,S,3,H,D) packed projection output (bf16 or fp32).
-    scores = scale * q.k + rel_bias[h, j-i+S-1] + key_add[b, j] (+ -inf above the diagonal if causal)."""
-    if dense_bias is not None:
-        raise NotImplementedError("dense (B,H,S,S) position bias (SaL family) is not built yet — SURVEY §8f rank 2")
-    return _AttnSelf.apply(qkv, rel_bias, key_add, scale, causal, float(dropout_p))
+    scores = scale * q.k + rel_bias[h, j-i+S-1] + key_add[b, j] (+ -inf above the diagonal if causal)
+             (+ scp_table[bucket[b, i-q0, j-q0], h] on the OCR block when scp = (bucket u8 (B,L,L), table (32,H), q0))."""
+    sb, stab, sq0 = scp if scp is not None else (None, None, 0)
+    return _AttnSelf.apply(qkv, rel_bias, key_add, scale, causal, float(dropout_p), sb, stab, sq0)
 
 
 def attention_cross(q, kv, scale, rel_bias=None, key_add=None, dropout_p=0.0):

@@ -225,3 +225,35 @@ def test_attention_dropout_mask_is_consistent_between_fwd_and_bwd(dtype):
     assert torch.equal(o2, o.detach())
     o3 = ops.attention_self(qkv.to(DEV), 1.0, dropout_p=p)
     assert not torch.equal(o3 != 0, o2 != 0)
+
+
+# ------------------------------- SaL spatial (SCP) bias in-kernel ---------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_self_attention_with_scp_bias_fwd_bwd(dtype):
+    from phoneme_vqa_b200 import ops
+    B, S, H, q0, L = 2, 208, 2, 16, 128
+    g = torch.Generator().manual_seed(3)
+    qkv = (torch.randn(B, S, 3, H, 64, generator=g) * 0.4).to(dtype)
+    rel = torch.randn(H, 2 * S - 1, generator=g)
+    tab = torch.randn(32, H, generator=g)
+    bk = torch.randint(0, 32, (B, L, L), generator=g, dtype=torch.int64).to(torch.uint8)
+    go = torch.randn(B, S, H, 64, generator=g).to(dtype)
+    # reference math: dense (B,H,S,S) bias, no key mask (SaL passes the bias externally)
+    qf, kf, vf = [qkv[:, :, i].float().transpose(1, 2).clone().requires_grad_(True) for i in range(3)]
+    relp, tabp = rel.clone().requires_grad_(True), tab.clone().requires_grad_(True)
+    dense = _rel_dense(relp, S, S)[None].repeat(B, 1, 1, 1)
+    scp = tabp[bk.long()].permute(0, 3, 1, 2)
+    dense = torch.cat([dense[:, :, :q0], torch.cat([dense[:, :, q0:q0 + L, :q0], dense[:, :, q0:q0 + L, q0:q0 + L] + scp,
+                                                    dense[:, :, q0:q0 + L, q0 + L:]], dim=3), dense[:, :, q0 + L:]], dim=2)
+    o_ref = torch.matmul(torch.softmax(torch.matmul(qf, kf.transpose(-1, -2)) + dense, -1), vf)
+    o_ref.backward(go.float().transpose(1, 2))
+    qd = qkv.to(DEV).requires_grad_(True)
+    reld, tabd = rel.to(DEV).requires_grad_(True), tab.to(DEV).requires_grad_(True)
+    o = ops.attention_self(qd, 1.0, rel_bias=reld, scp=(bk.to(DEV), tabd, q0))
+    o.backward(go.to(DEV))
+    tol = 1e-4 if dtype == torch.float32 else 2e-2
+    _close(o.detach().transpose(1, 2), o_ref.detach(), tol)
+    for idx, r in ((0, qf), (1, kf), (2, vf)):
+        _close(qd.grad[:, :, idx], r.grad.transpose(1, 2), tol if dtype == torch.float32 else 3e-2)
+    _close(reld.grad, relp.grad, tol if dtype == torch.float32 else 3e-2)
+    _close(tabd.grad, tabp.grad, tol if dtype == torch.float32 else 3e-2)

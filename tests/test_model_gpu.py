@@ -183,3 +183,57 @@ def test_latr_loss_and_grads_match_oracle(dtype):
                 for k, p in oracle.named_parameters() if p.grad is not None}
         bad = {k: (errs[k], base[k]) for k in errs if errs[k] > 1.25 * base[k] + 1e-2}
         assert not bad, bad
+
+
+# ------------------------------- PhonemeSaL (external 1-D + SCP bias) ---------------------------------
+def _sal_call(model, b):
+    return model(b["input_ids"], b["src_attention_mask"], b["label_ids"], b["shifted_right_label_ids"],
+                 b["label_attention_mask"], b["tokenized_ocr"], b["ocr_attention_mask"], b["ocr_coordinates"],
+                 b["ocr_features"], b["tokenized_obj"], b["obj_attention_mask"], b["obj_coordinates"],
+                 b["obj_features"], b["max_ocr"], b["max_ques"])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_phoneme_sal_matches_oracle(dtype):
+    import phoneme_vqa_b200.models as M
+    cfg = ref_model.sal_config()
+    oracle = ref_model.PhonemeSaL(cfg, 253)
+    oracle.load_state_dict(ref_model.deterministic_state_dict(oracle), strict=True)
+    model = M.PhonemeSaL(cfg, 253)
+    model.load_state_dict(oracle.state_dict(), strict=True)
+    model = model.to(DEV).set_compute_dtype(dtype)
+    batch = ref_model.sal_batch(3, cfg)
+    bd = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    oracle.eval(); model.eval()
+    ref_logits, ref_loss = oracle(batch)
+    logits, loss = _sal_call(model, bd)
+    if dtype == torch.float32:
+        np.testing.assert_allclose(logits.detach().cpu().numpy(), ref_logits.detach().numpy(), rtol=2e-4, atol=2e-5)
+        ys_ref = oracle.generate(batch, 1, 2, max_len=5)
+        ys = model.generate(*[bd[k] for k in ("input_ids", "src_attention_mask", "tokenized_ocr", "ocr_attention_mask",
+                                              "ocr_coordinates", "ocr_features", "tokenized_obj", "obj_attention_mask",
+                                              "obj_coordinates", "obj_features", "max_ocr", "max_ques")], 1, 2, max_len=5)
+        assert torch.equal(ys.cpu(), ys_ref)
+    oracle.train(); model.train()
+    _no_dropout(oracle); _no_dropout(model)
+    _, ref_loss = oracle(batch)
+    ref_loss.backward()
+    _, loss = _sal_call(model, bd)
+    loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= (1e-3 if dtype == torch.float32 else 3e-3) * abs(ref_loss.item())
+    ref_grads = {k: p.grad.clone() for k, p in oracle.named_parameters() if p.grad is not None}
+    got = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+    assert set(ref_grads) == set(got)
+    errs = {k: float((got[k].float().cpu() - gr).norm() / (gr.norm() + 1e-12)) for k, gr in ref_grads.items()}
+    if dtype == torch.float32:
+        worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
+        assert worst[0][1] <= 1e-3, worst
+    else:
+        oracle.zero_grad(set_to_none=True)
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            _, l2 = oracle(batch)
+        l2.backward()
+        base = {k: float((p.grad.float() - ref_grads[k]).norm() / (ref_grads[k].norm() + 1e-12))
+                for k, p in oracle.named_parameters() if p.grad is not None}
+        bad = {k: (errs[k], base[k]) for k in errs if errs[k] > 1.25 * base[k] + 1e-2}
+        assert not bad, bad

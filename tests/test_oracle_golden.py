@@ -126,3 +126,34 @@ def test_product_latr_state_dict_layout_matches_reference():
     # tied weights stay tied after loading
     assert model.backbone.lm_head.weight is model.backbone.shared.weight
     assert model.backbone.decoder.embed_tokens.weight is model.backbone.shared.weight
+
+
+def test_sal_bias_oracle_and_product_match_reference_modules():
+    """the reference's RelativePositionBiasAggregated output (real modules, CPU) vs the oracle restatement and
+    vs the product's on-device formulation (relative vector + uint8 SCP bucket map), bit-exact."""
+    g = np.load(os.path.join(GOLD, "sal_bias.npz"))
+    S, q0, L = int(g["S"]), int(g["q0"]), int(g["L"])
+    coords = torch.from_numpy(g["coords"])
+    rel_t, scp_t = torch.from_numpy(g["rel_table"]), torch.from_numpy(g["scp_table"])
+    ora = ref_model.sal_position_bias(rel_t, scp_t, S, coords, q0, L)
+    assert np.array_equal(ora.numpy(), g["bias"])
+    import phoneme_vqa_b200.modules as PM
+    agg = PM.RelativePositionBiasAggregated(PM.RelativePositionBias1D(int(g["H"])), PM.SCPRelativePositionBias(int(g["H"])))
+    assert list(agg.state_dict().keys()) == list(g["state_dict_keys"])
+    agg.Relative1D.relative_attention_bias.weight.data.copy_(rel_t)
+    agg.SCP.relative_attention_bias.weight.data.copy_(scp_t)
+    dense = agg.dense(S, coords, q0, L)
+    assert np.array_equal(dense.detach().numpy(), g["bias"])
+    rel, (bk, tab, qq) = agg(S, coords, q0, L)
+    assert bk.dtype == torch.uint8 and bk.shape == (2, L, L) and rel.shape == (int(g["H"]), 2 * S - 1) and qq == q0
+
+
+def test_product_sal_state_dict_layout_matches_oracle():
+    import phoneme_vqa_b200.models as M
+    cfg = ref_model.sal_config()
+    oracle = ref_model.PhonemeSaL(cfg, 253)
+    model = M.PhonemeSaL(cfg, 253)
+    assert list(model.state_dict().keys()) == list(oracle.state_dict().keys())
+    assert [tuple(v.shape) for v in model.state_dict().values()] == [tuple(v.shape) for v in oracle.state_dict().values()]
+    model.load_state_dict(oracle.state_dict(), strict=True)
+    oracle.load_state_dict(model.state_dict(), strict=True)
