@@ -44,7 +44,7 @@ def test_argument_errors_are_reported_without_a_device():
     assert rc == 1
     assert b"multiple of 8" in lib.pvqa_last_error()
     rc = lib.pvqa_attn_fwd(None, None, None, None, None, None, None, 1, 1, 8, 8, 32,
-                           0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1.0, 0, 0.0, 0, 0, None)
+                           0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1.0, 0, 0.0, 0, 0, None, None, 0, 0, None)
     assert rc == 1 and b"head dim" in lib.pvqa_last_error()
     rc = lib.pvqa_embed_tgt_fwd(None, None, None, None, None, None, 1, 1, 10, 4, 4, 1, 1, 1, 0, 0, 0.0, 0, 0, None, None)
     assert rc == 1 and b"on_dim" in lib.pvqa_last_error()
