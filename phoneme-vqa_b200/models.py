@@ -84,13 +84,36 @@ def _load_pretrained_t5_encoder(encoder: T5EncoderModel, config):
 class _VisionMixin:
     """frozen-ViT handling shared by the LaTr / PreSTU families."""
 
+    def _vit_frozen(self):
+        return not any(p.requires_grad for p in self.vit.parameters())
+
+    def _vit_shadow(self):
+        """bf16 copy of the FROZEN ViT tower used for bf16 compute.  It is deliberately kept out of the module
+        tree (so `state_dict()` still holds exactly the reference's fp32 `vit.*` tensors) and is rebuilt when
+        the fp32 weights change (load_state_dict, .to(device))."""
+        sig = tuple((p.data_ptr(), p._version) for p in self.vit.parameters())
+        cache = self.__dict__.get("_vit_lp")
+        if cache is None or cache[0] != sig:
+            import copy
+            lp = copy.deepcopy(self.vit).to(torch.bfloat16)
+            lp.eval()
+            for p in lp.parameters():
+                p.requires_grad_(False)
+            cache = (sig, lp)
+            self.__dict__["_vit_lp"] = cache
+        return cache[1]
+
     def _vit_tokens(self, pixel_values):
-        frozen = not any(p.requires_grad for p in self.vit.parameters())
-        ctx = torch.no_grad() if frozen else contextlib.nullcontext()
+        # ViTModel.forward minus the pooler (never used by the reference: PhonemeLaTr.py:220)
+        if self._vit_frozen() and self.compute_dtype == torch.bfloat16:
+            vit = self._vit_shadow()
+            with torch.no_grad():
+                emb = vit.embeddings(pixel_values.to(torch.bfloat16))
+                return vit.layernorm(vit.encoder(emb).last_hidden_state)
+        ctx = torch.no_grad() if self._vit_frozen() else contextlib.nullcontext()
         amp = (torch.autocast("cuda", dtype=torch.bfloat16) if self.compute_dtype == torch.bfloat16
                else contextlib.nullcontext())
         with ctx, amp:
-            # ViTModel.forward minus the pooler (never used by the reference: PhonemeLaTr.py:220)
             emb = self.vit.embeddings(pixel_values)
             seq = self.vit.encoder(emb).last_hidden_state
             seq = self.vit.layernorm(seq)
