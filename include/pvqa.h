@@ -280,8 +280,9 @@ int pvqa_attn_f32_bwd(const float* q, const float* k, const float* v, const floa
  * ------------------------------------------------------------------------ */
 int pvqa_rms_norm_fwd(const void* x, const float* w, void* y, float* rstd, int64_t N, int64_t d, float eps,
                       int x_dtype, int y_dtype, void* stream);
-int pvqa_rms_norm_bwd(const void* dy, const void* x, const float* w, const float* rstd, void* dx, float* dw,
-                      int64_t N, int64_t d, int x_dtype, int y_dtype, void* stream);
+int pvqa_rms_norm_bwd(const void* dy, const void* x, const float* w, const float* rstd,
+                      const void* d_residual /* optional (x dtype): gradient of the residual path, added to dx */,
+                      void* dx, float* dw, int64_t N, int64_t d, int x_dtype, int y_dtype, void* stream);
 int pvqa_residual_dropout_add(const float* hidden, const void* update, float* out, int64_t n, int upd_dtype,
                               float dropout_p, uint64_t seed, uint64_t offset, void* stream);
 int pvqa_residual_dropout_bwd(const float* d_out, void* d_update, int64_t n, int upd_dtype, float dropout_p,

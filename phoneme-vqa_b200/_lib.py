@@ -77,7 +77,7 @@ _SIGNATURES = {
     "pvqa_attn_bwd": (c_int, [_vp] * 13 + _i64x(5) + _i64x(21) + [_f, c_int, _f, c_uint64, c_uint64, _vp, _vp, _vp, _i64, _i64, _vp]),
     "pvqa_attn_f32_fwd": (c_int, [_vp] * 7 + _i64x(5) + _i64x(12) + [_f, c_int, _f, c_uint64, c_uint64, _vp, _vp, _i64, _i64, _vp]),
     "pvqa_rms_norm_fwd": (c_int, [_vp] * 4 + _i64x(2) + [_f, c_int, c_int, _vp]),
-    "pvqa_rms_norm_bwd": (c_int, [_vp] * 6 + _i64x(2) + [c_int, c_int, _vp]),
+    "pvqa_rms_norm_bwd": (c_int, [_vp] * 7 + _i64x(2) + [c_int, c_int, _vp]),
     "pvqa_residual_dropout_add": (c_int, [_vp] * 3 + [_i64, c_int, _f, c_uint64, c_uint64, _vp]),
     "pvqa_residual_dropout_bwd": (c_int, [_vp] * 2 + [_i64, c_int, _f, c_uint64, c_uint64, _vp]),
     "pvqa_relu_dropout_fwd": (c_int, [_vp] * 2 + [_i64, c_int, _f, c_uint64, c_uint64, _vp]),

@@ -80,7 +80,8 @@ rms_norm_fwd_kernel(const XT* __restrict__ x, const float* __restrict__ w, YT* _
 template <typename XT, typename YT>
 __global__ void __launch_bounds__(kNormThreads)
 rms_norm_bwd_kernel(const YT* __restrict__ dy, const XT* __restrict__ x, const float* __restrict__ w,
-                    const float* __restrict__ rstd, XT* __restrict__ dx, float* __restrict__ dw, int N, int d) {
+                    const float* __restrict__ rstd, const XT* __restrict__ d_res, XT* __restrict__ dx,
+                    float* __restrict__ dw, int N, int d) {
   extern __shared__ float s_dw[];             // [d] block partial
   const int lane = threadIdx.x & 31;
   for (int c = threadIdx.x; c < d; c += kNormThreads) s_dw[c] = 0.f;
@@ -109,12 +110,17 @@ rms_norm_bwd_kernel(const YT* __restrict__ dy, const XT* __restrict__ x, const f
     }
     dot = warp_sum_n(dot) / (float)d;
     XT* dr = dx + (long long)row * d;
+    const XT* rr = d_res ? d_res + (long long)row * d : nullptr;
 #pragma unroll
     for (int c = 0; c < kMaxVec; ++c) {
       if ((c * 32 + lane) * 4 < d) {
         float4 o;
         o.x = r * (g[c].x - xh[c].x * dot); o.y = r * (g[c].y - xh[c].y * dot);
         o.z = r * (g[c].z - xh[c].z * dot); o.w = r * (g[c].w - xh[c].w * dot);
+        if (rr) {          // fused residual-gradient accumulation: dx = d_residual + d(norm branch)
+          const float4 e = load4<XT>(rr + (c * 32 + lane) * 4);
+          o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
+        }
         store4<XT>(dr + (c * 32 + lane) * 4, o);
       }
     }
@@ -235,7 +241,8 @@ extern "C" int pvqa_rms_norm_fwd(const void* x, const float* w, void* y, float* 
   return PVQA_OK;
 }
 
-extern "C" int pvqa_rms_norm_bwd(const void* dy, const void* x, const float* w, const float* rstd, void* dx,
+extern "C" int pvqa_rms_norm_bwd(const void* dy, const void* x, const float* w, const float* rstd,
+                                 const void* d_residual /* optional, x dtype: added to dx */, void* dx,
                                  float* dw /* accumulated */, int64_t N, int64_t d, int x_dtype, int y_dtype,
                                  void* stream) {
   PVQA_REQUIRE(N >= 0 && d > 0, PVQA_ERR_SHAPE, "rms_norm_bwd: bad dimension");
@@ -244,16 +251,16 @@ extern "C" int pvqa_rms_norm_bwd(const void* dy, const void* x, const float* w, 
   PVQA_REQUIRE(dy && x && w && rstd && dx && dw, PVQA_ERR_NULL, "rms_norm_bwd: NULL pointer");
   PVQA_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(w) && aligned16(dx), PVQA_ERR_ALIGN, "rms_norm_bwd: 16-byte alignment required");
   const int warps = kNormThreads / 32;
-  long long need = (N + warps - 1) / warps, cap = (long long)num_sms() * 2;
+  long long need = (N + warps - 1) / warps, cap = (long long)num_sms() * 6;
   const int grid = (int)(need < cap ? need : cap);
   const size_t smem = (size_t)d * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
   if (x_dtype == PVQA_F32 && y_dtype == PVQA_BF16)
-    rms_norm_bwd_kernel<float, __nv_bfloat16><<<grid, kNormThreads, smem, st>>>((const __nv_bfloat16*)dy, (const float*)x, w, rstd, (float*)dx, dw, (int)N, (int)d);
+    rms_norm_bwd_kernel<float, __nv_bfloat16><<<grid, kNormThreads, smem, st>>>((const __nv_bfloat16*)dy, (const float*)x, w, rstd, (const float*)d_residual, (float*)dx, dw, (int)N, (int)d);
   else if (x_dtype == PVQA_F32 && y_dtype == PVQA_F32)
-    rms_norm_bwd_kernel<float, float><<<grid, kNormThreads, smem, st>>>((const float*)dy, (const float*)x, w, rstd, (float*)dx, dw, (int)N, (int)d);
+    rms_norm_bwd_kernel<float, float><<<grid, kNormThreads, smem, st>>>((const float*)dy, (const float*)x, w, rstd, (const float*)d_residual, (float*)dx, dw, (int)N, (int)d);
   else if (x_dtype == PVQA_BF16 && y_dtype == PVQA_BF16)
-    rms_norm_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, kNormThreads, smem, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, w, rstd, (__nv_bfloat16*)dx, dw, (int)N, (int)d);
+    rms_norm_bwd_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, kNormThreads, smem, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, w, rstd, (const __nv_bfloat16*)d_residual, (__nv_bfloat16*)dx, dw, (int)N, (int)d);
   else
     return fail(PVQA_ERR_DTYPE, "rms_norm_bwd: unsupported dtype combination");
   count_launch();

@@ -220,6 +220,10 @@ class T5LayerNorm(nn.Module):
     def forward(self, x, out_dtype=None):
         return ops.rms_norm(x, self.weight, self.variance_epsilon, out_dtype or x.dtype)
 
+    def with_residual(self, x, out_dtype=None):
+        """-> (normed, x) with the residual gradient fused into the norm backward"""
+        return ops.rms_norm_residual(x, self.weight, self.variance_epsilon, out_dtype or x.dtype)
+
 
 _BUCKET_CACHE: dict = {}
 
@@ -317,7 +321,7 @@ class T5LayerSelfAttention(nn.Module):
         self.dropout = nn.Dropout(config.dropout_rate)
 
     def forward(self, hidden, rel_bias, key_add, compute_dtype, causal=False, scp=None):
-        normed = self.layer_norm(hidden, out_dtype=compute_dtype)
+        normed, hidden = self.layer_norm.with_residual(hidden, out_dtype=compute_dtype)
         attn = self.SelfAttention(normed, rel_bias, key_add, causal=causal, scp=scp)
         return ops.residual_dropout_add(hidden, attn, self.dropout.p, self.training)
 
@@ -330,7 +334,7 @@ class T5LayerCrossAttention(nn.Module):
         self.dropout = nn.Dropout(config.dropout_rate)
 
     def forward(self, hidden, memory, key_add, compute_dtype):
-        normed = self.layer_norm(hidden, out_dtype=compute_dtype)
+        normed, hidden = self.layer_norm.with_residual(hidden, out_dtype=compute_dtype)
         attn = self.EncDecAttention(normed, None, key_add, kv=memory)
         return ops.residual_dropout_add(hidden, attn, self.dropout.p, self.training)
 
@@ -379,7 +383,7 @@ class T5LayerFF(nn.Module):
         self.dropout = nn.Dropout(config.dropout_rate)
 
     def forward(self, hidden, compute_dtype):
-        normed = self.layer_norm(hidden, out_dtype=compute_dtype)
+        normed, hidden = self.layer_norm.with_residual(hidden, out_dtype=compute_dtype)
         ff = self.DenseReluDense(normed)
         return ops.residual_dropout_add(hidden, ff, self.dropout.p, self.training)
 

@@ -272,8 +272,12 @@ def embed_target(labels, onset_weight, rhyme_weight, tone_weight, pos_embedding,
 # Fused glue: RMS norm, residual + dropout, relu + dropout, bf16 linear with fp32 weight gradients
 # ----------------------------------------------------------------------------------
 class _RmsNorm(torch.autograd.Function):
+    """y = rms_norm(x) and, optionally, a pass-through copy of x for the residual path: the backward then
+    receives both gradients at once and emits dx = d_residual + d(norm branch) from ONE kernel instead of a
+    norm-backward kernel plus an autograd accumulation pass over the fp32 residual stream."""
+
     @staticmethod
-    def forward(ctx, x, weight, eps, out_dtype):
+    def forward(ctx, x, weight, eps, out_dtype, with_residual):
         lib = _lib.load()
         _need_cuda(x, weight)
         shape = x.shape
@@ -287,29 +291,41 @@ class _RmsNorm(torch.autograd.Function):
             check(lib.pvqa_rms_norm_fwd(_p(x2), _p(w), _p(y), _p(rstd), N, d, float(eps), _dt(x2.dtype), _dt(out_dtype),
                                         _stream()), "pvqa_rms_norm_fwd")
         ctx.save_for_backward(x2, w, rstd)
-        ctx.meta = (shape, weight.dtype)
+        ctx.meta = (shape, weight.dtype, with_residual)
+        if with_residual:
+            return y.view(shape), x.view_as(x)
         return y.view(shape)
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, d_res=None):
         lib = _lib.load()
         x2, w, rstd = ctx.saved_tensors
-        shape, w_dtype = ctx.meta
+        shape, w_dtype, with_residual = ctx.meta
         N, d = x2.shape
         dy2 = dy.reshape(N, d).contiguous()
+        if d_res is not None:
+            d_res = d_res.reshape(N, d).to(x2.dtype).contiguous()
         dx = torch.empty_like(x2)
         dw = torch.zeros(d, dtype=torch.float32, device=x2.device)
         with torch.cuda.device(x2.device), _prof("rms_norm_bwd"):
-            check(lib.pvqa_rms_norm_bwd(_p(dy2), _p(x2), _p(w), _p(rstd), _p(dx), _p(dw), N, d, _dt(x2.dtype),
-                                        _dt(dy2.dtype), _stream()), "pvqa_rms_norm_bwd")
-        return dx.view(shape), dw.to(w_dtype), None, None
+            check(lib.pvqa_rms_norm_bwd(_p(dy2), _p(x2), _p(w), _p(rstd), _p(d_res), _p(dx), _p(dw), N, d,
+                                        _dt(x2.dtype), _dt(dy2.dtype), _stream()), "pvqa_rms_norm_bwd")
+        return dx.view(shape), dw.to(w_dtype), None, None, None
 
 
 def rms_norm(x, weight, eps, out_dtype):
     """T5LayerNorm (modeling_t5.py:46-70): fp32 variance, no mean subtraction, no bias."""
     if x.dtype == torch.bfloat16:
         out_dtype = torch.bfloat16
-    return _RmsNorm.apply(x, weight, eps, out_dtype)
+    return _RmsNorm.apply(x, weight, eps, out_dtype, False)
+
+
+def rms_norm_residual(x, weight, eps, out_dtype):
+    """(rms_norm(x), x): use the second output for the residual add of a pre-norm block so the two gradient
+    paths into x are summed inside the norm-backward kernel."""
+    if x.dtype == torch.bfloat16:
+        out_dtype = torch.bfloat16
+    return _RmsNorm.apply(x, weight, eps, out_dtype, True)
 
 
 class _ResidualDropoutAdd(torch.autograd.Function):

@@ -85,3 +85,22 @@ def test_shadow_weight_linear_fp32_grads_and_refresh():
         lin_q.weight.add_(1.0)
     y2 = M._lin_multi(x, [lin_q.weight, lin_k.weight], [lin_q.bias, lin_k.bias])
     assert (y2[:, :32].float() - y[:, :32].float()).abs().max() > 0.1
+
+
+def test_rms_norm_with_fused_residual_gradient():
+    """(normed, x) variant: d x = d_residual + d(norm branch) from one kernel == plain autograd sum."""
+    from phoneme_vqa_b200 import ops
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(6, 50, 768, generator=g).to(DEV).requires_grad_(True)
+    w = (1 + 0.1 * torch.randn(768, generator=g)).to(DEV).requires_grad_(True)
+    proj = torch.randn(768, 768, generator=g).to(DEV) * 0.03
+    normed, xp = ops.rms_norm_residual(x, w, 1e-6, torch.bfloat16)
+    out = xp + (normed.float() @ proj)
+    go = torch.randn(6, 50, 768, generator=g).to(DEV)
+    out.backward(go)
+    xr = x.detach().clone().requires_grad_(True)
+    wr = w.detach().clone().requires_grad_(True)
+    nr = ops.rms_norm(xr, wr, 1e-6, torch.bfloat16)
+    (xr + (nr.float() @ proj)).backward(go)
+    torch.testing.assert_close(x.grad, xr.grad, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(w.grad, wr.grad, rtol=1e-4, atol=1e-4)
