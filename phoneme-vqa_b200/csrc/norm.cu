@@ -251,7 +251,7 @@ extern "C" int pvqa_rms_norm_bwd(const void* dy, const void* x, const float* w, 
   PVQA_REQUIRE(dy && x && w && rstd && dx && dw, PVQA_ERR_NULL, "rms_norm_bwd: NULL pointer");
   PVQA_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(w) && aligned16(dx), PVQA_ERR_ALIGN, "rms_norm_bwd: 16-byte alignment required");
   const int warps = kNormThreads / 32;
-  long long need = (N + warps - 1) / warps, cap = (long long)num_sms() * 6;
+  long long need = (N + warps - 1) / warps, cap = (long long)num_sms() * 2;   // 128 regs -> 2 CTAs/SM resident
   const int grid = (int)(need < cap ? need : cap);
   const size_t smem = (size_t)d * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
