@@ -165,6 +165,146 @@ phoneme_head_kernel(const HeadParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------
+// bf16 tensor-core variant (mma.sync m16n8k16, fp32 accumulate): one warp owns 16 rows; per head the A
+// fragments of the 16 x w_k slice stay in registers (w_k <= 256), W_k streams from L1/L2 as B fragments,
+// and the C fragments (16 x 8 logits per n-tile) feed an online log-sum-exp — logits still never reach HBM.
+// The GEMM is 1.2 GFLOP: far too small for a 128-row tcgen05 tile grid (64 CTAs on 148 SMs), while 16-row
+// warp tiles spread it over every SM; the kernel is bounded by reading h once (12.5 MB).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int kMmaMaxKSteps = 16;     // w_k <= 256
+
+template <int MODE>
+__global__ void __launch_bounds__(128)
+phoneme_head_mma_kernel(const HeadParams p) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int warps = 4;
+  const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(p.h);
+  const int tiles = (p.N + 15) / 16;
+  float loss_acc[3] = {0.f, 0.f, 0.f};
+  int cnt_acc[3] = {0, 0, 0};
+  float gl = 0.f;
+  if (MODE == 1) gl = *p.grad_loss;
+
+  for (int tile = blockIdx.x * warps + (threadIdx.x >> 5); tile < tiles; tile += gridDim.x * warps) {
+    const int r_lo = tile * 16 + g, r_hi = r_lo + 8;
+    const bool ok_lo = r_lo < p.N, ok_hi = r_hi < p.N;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int w = p.wdim[k], V = p.V[k], ksteps = w >> 4;
+      const __nv_bfloat16* W = reinterpret_cast<const __nv_bfloat16*>(p.W[k]);
+      const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(p.b[k]);
+      // A fragments of this head's column slice
+      uint32_t a[kMmaMaxKSteps][4];
+      const __nv_bfloat16* h_lo = h + (long long)r_lo * p.d + p.off[k] + 2 * t;
+      const __nv_bfloat16* h_hi = h + (long long)r_hi * p.d + p.off[k] + 2 * t;
+#pragma unroll
+      for (int ks = 0; ks < kMmaMaxKSteps; ++ks) {
+        if (ks < ksteps) {
+          a[ks][0] = ok_lo ? *reinterpret_cast<const uint32_t*>(h_lo + ks * 16) : 0u;
+          a[ks][1] = ok_hi ? *reinterpret_cast<const uint32_t*>(h_hi + ks * 16) : 0u;
+          a[ks][2] = ok_lo ? *reinterpret_cast<const uint32_t*>(h_lo + ks * 16 + 8) : 0u;
+          a[ks][3] = ok_hi ? *reinterpret_cast<const uint32_t*>(h_hi + ks * 16 + 8) : 0u;
+        }
+      }
+      const long long tg_lo = ok_lo ? p.tgt[(long long)r_lo * p.tgt_stride + k] : p.ignore_index;
+      const long long tg_hi = ok_hi ? p.tgt[(long long)r_hi * p.tgt_stride + k] : p.ignore_index;
+      const bool v_lo = tg_lo != p.ignore_index, v_hi = tg_hi != p.ignore_index;
+      float m_lo = -INFINITY, s_lo = 0.f, tl_lo = 0.f, m_hi = -INFINITY, s_hi = 0.f, tl_hi = 0.f;
+      float lse_lo = 0.f, lse_hi = 0.f, g_lo = 0.f, g_hi = 0.f;
+      if (MODE == 1) {
+        const int cnt = p.count[k];
+        if (ok_lo) lse_lo = p.lse[(long long)r_lo * 3 + k];
+        if (ok_hi) lse_hi = p.lse[(long long)r_hi * 3 + k];
+        g_lo = (v_lo && cnt > 0) ? gl / (float)cnt : 0.f;
+        g_hi = (v_hi && cnt > 0) ? gl / (float)cnt : 0.f;
+      }
+      for (int n0 = 0; n0 < V; n0 += 8) {
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+        const int nrow = n0 + g;                                  // vocabulary entry this thread feeds as B column
+        const __nv_bfloat16* wrow = W + (long long)min(nrow, V - 1) * w + 2 * t;
+        const bool nok = nrow < V;
+#pragma unroll
+        for (int ks = 0; ks < kMmaMaxKSteps; ++ks) {
+          if (ks < ksteps) {
+            const uint32_t b0 = nok ? __ldg(reinterpret_cast<const uint32_t*>(wrow + ks * 16)) : 0u;
+            const uint32_t b1 = nok ? __ldg(reinterpret_cast<const uint32_t*>(wrow + ks * 16 + 8)) : 0u;
+            mma_bf16_16816(c, a[ks], b0, b1);
+          }
+        }
+        const int c0 = n0 + 2 * t;                                // this thread's two logit columns
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = c0 + e;
+          if (col < V) {
+            const float bb = __bfloat162float(bias[col]);
+            const float l_lo = c[e] + bb, l_hi = c[2 + e] + bb;
+            if (MODE == 0) {
+              if (p.logits[k]) {
+                __nv_bfloat16* lg = reinterpret_cast<__nv_bfloat16*>(p.logits[k]);
+                if (ok_lo) lg[(long long)r_lo * V + col] = __float2bfloat16_rn(l_lo);
+                if (ok_hi) lg[(long long)r_hi * V + col] = __float2bfloat16_rn(l_hi);
+              }
+              float mn = fmaxf(m_lo, l_lo);
+              s_lo = s_lo * __expf(m_lo - mn) + __expf(l_lo - mn); m_lo = mn;
+              mn = fmaxf(m_hi, l_hi);
+              s_hi = s_hi * __expf(m_hi - mn) + __expf(l_hi - mn); m_hi = mn;
+              if (col == tg_lo) tl_lo = l_lo;
+              if (col == tg_hi) tl_hi = l_hi;
+            } else {
+              __nv_bfloat16* dl = reinterpret_cast<__nv_bfloat16*>(p.dlogits[k]);
+              if (ok_lo) dl[(long long)r_lo * V + col] =
+                  __float2bfloat16_rn(g_lo * (__expf(l_lo - lse_lo) - (col == tg_lo ? 1.f : 0.f)));
+              if (ok_hi) dl[(long long)r_hi * V + col] =
+                  __float2bfloat16_rn(g_hi * (__expf(l_hi - lse_hi) - (col == tg_hi ? 1.f : 0.f)));
+            }
+          }
+        }
+      }
+      if (MODE == 0) {
+        // combine the 4 threads of a quad (they hold different columns of the same two rows)
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+          float mo = __shfl_xor_sync(0xffffffffu, m_lo, o), so = __shfl_xor_sync(0xffffffffu, s_lo, o);
+          float mn = fmaxf(m_lo, mo);
+          s_lo = (m_lo == -INFINITY ? 0.f : s_lo * __expf(m_lo - mn)) + (mo == -INFINITY ? 0.f : so * __expf(mo - mn));
+          m_lo = mn;
+          mo = __shfl_xor_sync(0xffffffffu, m_hi, o); so = __shfl_xor_sync(0xffffffffu, s_hi, o);
+          mn = fmaxf(m_hi, mo);
+          s_hi = (m_hi == -INFINITY ? 0.f : s_hi * __expf(m_hi - mn)) + (mo == -INFINITY ? 0.f : so * __expf(mo - mn));
+          m_hi = mn;
+          tl_lo += __shfl_xor_sync(0xffffffffu, tl_lo, o);
+          tl_hi += __shfl_xor_sync(0xffffffffu, tl_hi, o);
+        }
+        if (t == 0) {
+          const float l1 = m_lo + __logf(s_lo), l2 = m_hi + __logf(s_hi);
+          if (ok_lo) { p.lse[(long long)r_lo * 3 + k] = l1; if (v_lo) { loss_acc[k] += l1 - tl_lo; cnt_acc[k] += 1; } }
+          if (ok_hi) { p.lse[(long long)r_hi * 3 + k] = l2; if (v_hi) { loss_acc[k] += l2 - tl_hi; cnt_acc[k] += 1; } }
+        }
+      }
+    }
+  }
+  if (MODE == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float la = loss_acc[k];
+      int ca = cnt_acc[k];
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        la += __shfl_xor_sync(0xffffffffu, la, o);
+        ca += __shfl_xor_sync(0xffffffffu, ca, o);
+      }
+      if (lane == 0 && ca) { atomicAdd(p.loss_sum + k, la); atomicAdd(p.count + k, ca); }
+    }
+  }
+}
+
 static int validate_head(const char* fn, int64_t N, int64_t d, int64_t on_dim, int64_t rt_dim, int64_t V_o,
                          int64_t V_r, int64_t V_t, int w_dtype, int act_dtype) {
   PVQA_REQUIRE(N >= 0 && d > 0 && on_dim > 0 && rt_dim > 0, PVQA_ERR_SHAPE, "%s: bad dimension", fn);
@@ -185,7 +325,13 @@ static void launch_head(const HeadParams& p, int w_dtype, int act_dtype, cudaStr
   long long need = ((long long)p.N + warps - 1) / warps;
   long long cap = (long long)num_sms() * 4;
   const int grid = (int)(need < cap ? (need < 1 ? 1 : need) : cap);
-  if (w_dtype == PVQA_BF16 && act_dtype == PVQA_BF16)
+  const bool mma_ok = w_dtype == PVQA_BF16 && act_dtype == PVQA_BF16 && p.wdim[0] % 16 == 0 && p.wdim[1] % 16 == 0 &&
+                      p.wdim[0] <= 16 * kMmaMaxKSteps && p.wdim[1] <= 16 * kMmaMaxKSteps && p.d % 2 == 0;
+  if (mma_ok) {
+    const long long tiles = ((long long)p.N + 15) / 16;
+    long long need_m = (tiles + 3) / 4, cap_m = (long long)num_sms() * 8;
+    phoneme_head_mma_kernel<MODE><<<(int)(need_m < cap_m ? need_m : cap_m), 128, 0, st>>>(p);
+  } else if (w_dtype == PVQA_BF16 && act_dtype == PVQA_BF16)
     phoneme_head_kernel<__nv_bfloat16, __nv_bfloat16, MODE><<<grid, kHeadThreads, 0, st>>>(p);
   else if (w_dtype == PVQA_F32 && act_dtype == PVQA_F32)
     phoneme_head_kernel<float, float, MODE><<<grid, kHeadThreads, 0, st>>>(p);
