@@ -192,14 +192,21 @@ phoneme_head_mma_kernel(const HeadParams p) {
   float gl = 0.f;
   if (MODE == 1) gl = *p.grad_loss;
 
-  for (int tile = blockIdx.x * warps + (threadIdx.x >> 5); tile < tiles; tile += gridDim.x * warps) {
+  // work item = (16-row tile, head): 3x more warps in flight than one warp per tile
+  for (int item = blockIdx.x * warps + (threadIdx.x >> 5); item < tiles * 3; item += gridDim.x * warps) {
+    const int tile = item / 3, k = item - tile * 3;
     const int r_lo = tile * 16 + g, r_hi = r_lo + 8;
     const bool ok_lo = r_lo < p.N, ok_hi = r_hi < p.N;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
+    {
       const int w = p.wdim[k], V = p.V[k], ksteps = w >> 4;
       const __nv_bfloat16* W = reinterpret_cast<const __nv_bfloat16*>(p.W[k]);
       const __nv_bfloat16* bias = reinterpret_cast<const __nv_bfloat16*>(p.b[k]);
+      const long long tg_lo = ok_lo ? p.tgt[(long long)r_lo * p.tgt_stride + k] : p.ignore_index;
+      const long long tg_hi = ok_hi ? p.tgt[(long long)r_hi * p.tgt_stride + k] : p.ignore_index;
+      const bool v_lo = tg_lo != p.ignore_index, v_hi = tg_hi != p.ignore_index;
+      // pad tails make most tiles all-ignored: they contribute no loss and a zero gradient (dlogits is
+      // pre-zeroed by the host), so the whole tile is skipped unless the caller wants the logits themselves
+      if (!__any_sync(0xffffffffu, v_lo || v_hi) && !(MODE == 0 && p.logits[k])) continue;
       // A fragments of this head's column slice
       uint32_t a[kMmaMaxKSteps][4];
       const __nv_bfloat16* h_lo = h + (long long)r_lo * p.d + p.off[k] + 2 * t;
@@ -213,9 +220,7 @@ phoneme_head_mma_kernel(const HeadParams p) {
           a[ks][3] = ok_hi ? *reinterpret_cast<const uint32_t*>(h_hi + ks * 16 + 8) : 0u;
         }
       }
-      const long long tg_lo = ok_lo ? p.tgt[(long long)r_lo * p.tgt_stride + k] : p.ignore_index;
-      const long long tg_hi = ok_hi ? p.tgt[(long long)r_hi * p.tgt_stride + k] : p.ignore_index;
-      const bool v_lo = tg_lo != p.ignore_index, v_hi = tg_hi != p.ignore_index;
+
       float m_lo = -INFINITY, s_lo = 0.f, tl_lo = 0.f, m_hi = -INFINITY, s_hi = 0.f, tl_hi = 0.f;
       float lse_lo = 0.f, lse_hi = 0.f, g_lo = 0.f, g_hi = 0.f;
       if (MODE == 1) {
@@ -284,8 +289,12 @@ phoneme_head_mma_kernel(const HeadParams p) {
         }
         if (t == 0) {
           const float l1 = m_lo + __logf(s_lo), l2 = m_hi + __logf(s_hi);
-          if (ok_lo) { p.lse[(long long)r_lo * 3 + k] = l1; if (v_lo) { loss_acc[k] += l1 - tl_lo; cnt_acc[k] += 1; } }
-          if (ok_hi) { p.lse[(long long)r_hi * 3 + k] = l2; if (v_hi) { loss_acc[k] += l2 - tl_hi; cnt_acc[k] += 1; } }
+          float dl = 0.f;
+          int dc = 0;
+          if (ok_lo) { p.lse[(long long)r_lo * 3 + k] = l1; if (v_lo) { dl += l1 - tl_lo; dc += 1; } }
+          if (ok_hi) { p.lse[(long long)r_hi * 3 + k] = l2; if (v_hi) { dl += l2 - tl_hi; dc += 1; } }
+#pragma unroll
+          for (int kk = 0; kk < 3; ++kk) if (kk == k) { loss_acc[kk] += dl; cnt_acc[kk] += dc; }
         }
       }
     }
@@ -329,7 +338,12 @@ static void launch_head(const HeadParams& p, int w_dtype, int act_dtype, cudaStr
                       p.wdim[0] <= 16 * kMmaMaxKSteps && p.wdim[1] <= 16 * kMmaMaxKSteps && p.d % 2 == 0;
   if (mma_ok) {
     const long long tiles = ((long long)p.N + 15) / 16;
-    long long need_m = (tiles + 3) / 4, cap_m = (long long)num_sms() * 8;
+    if (MODE == 1) {
+      for (int k = 0; k < 3; ++k) cudaMemsetAsync(p.dlogits[k], 0, (size_t)p.N * p.V[k] * 2, st);   // skipped tiles
+    } else {
+      cudaMemsetAsync(p.lse, 0, (size_t)p.N * 3 * sizeof(float), st);
+    }
+    long long need_m = (tiles * 3 + 3) / 4, cap_m = (long long)num_sms() * 8;
     phoneme_head_mma_kernel<MODE><<<(int)(need_m < cap_m ? need_m : cap_m), 128, 0, st>>>(p);
   } else if (w_dtype == PVQA_BF16 && act_dtype == PVQA_BF16)
     phoneme_head_kernel<__nv_bfloat16, __nv_bfloat16, MODE><<<grid, kHeadThreads, 0, st>>>(p);
