@@ -230,44 +230,57 @@ phoneme_head_mma_kernel(const HeadParams p) {
         g_lo = (v_lo && cnt > 0) ? gl / (float)cnt : 0.f;
         g_hi = (v_hi && cnt > 0) ? gl / (float)cnt : 0.f;
       }
-      for (int n0 = 0; n0 < V; n0 += 8) {
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-        const int nrow = n0 + g;                                  // vocabulary entry this thread feeds as B column
-        const __nv_bfloat16* wrow = W + (long long)min(nrow, V - 1) * w + 2 * t;
-        const bool nok = nrow < V;
+      // four n-tiles (32 vocabulary entries) per pass: four independent accumulator chains hide the mma latency
+      for (int n0 = 0; n0 < V; n0 += 32) {
+        float c[4][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { c[q][0] = c[q][1] = c[q][2] = c[q][3] = 0.f; }
+        const __nv_bfloat16* wrow[4];
+        bool nok[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int nrow = n0 + q * 8 + g;                      // vocabulary entry this thread feeds as B column
+          nok[q] = nrow < V;
+          wrow[q] = W + (long long)min(nrow, V - 1) * w + 2 * t;
+        }
 #pragma unroll
         for (int ks = 0; ks < kMmaMaxKSteps; ++ks) {
           if (ks < ksteps) {
-            const uint32_t b0 = nok ? __ldg(reinterpret_cast<const uint32_t*>(wrow + ks * 16)) : 0u;
-            const uint32_t b1 = nok ? __ldg(reinterpret_cast<const uint32_t*>(wrow + ks * 16 + 8)) : 0u;
-            mma_bf16_16816(c, a[ks], b0, b1);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t b0 = nok[q] ? __ldg(reinterpret_cast<const uint32_t*>(wrow[q] + ks * 16)) : 0u;
+              const uint32_t b1 = nok[q] ? __ldg(reinterpret_cast<const uint32_t*>(wrow[q] + ks * 16 + 8)) : 0u;
+              mma_bf16_16816(c[q], a[ks], b0, b1);
+            }
           }
         }
-        const int c0 = n0 + 2 * t;                                // this thread's two logit columns
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int col = c0 + e;
-          if (col < V) {
-            const float bb = __bfloat162float(bias[col]);
-            const float l_lo = c[e] + bb, l_hi = c[2 + e] + bb;
-            if (MODE == 0) {
-              if (p.logits[k]) {
-                __nv_bfloat16* lg = reinterpret_cast<__nv_bfloat16*>(p.logits[k]);
-                if (ok_lo) lg[(long long)r_lo * V + col] = __float2bfloat16_rn(l_lo);
-                if (ok_hi) lg[(long long)r_hi * V + col] = __float2bfloat16_rn(l_hi);
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = n0 + q * 8 + 2 * t + e;             // this thread's logit columns
+            if (col < V) {
+              const float bb = __bfloat162float(bias[col]);
+              const float l_lo = c[q][e] + bb, l_hi = c[q][2 + e] + bb;
+              if (MODE == 0) {
+                if (p.logits[k]) {
+                  __nv_bfloat16* lg = reinterpret_cast<__nv_bfloat16*>(p.logits[k]);
+                  if (ok_lo) lg[(long long)r_lo * V + col] = __float2bfloat16_rn(l_lo);
+                  if (ok_hi) lg[(long long)r_hi * V + col] = __float2bfloat16_rn(l_hi);
+                }
+                float mn = fmaxf(m_lo, l_lo);
+                s_lo = s_lo * __expf(m_lo - mn) + __expf(l_lo - mn); m_lo = mn;
+                mn = fmaxf(m_hi, l_hi);
+                s_hi = s_hi * __expf(m_hi - mn) + __expf(l_hi - mn); m_hi = mn;
+                if (col == tg_lo) tl_lo = l_lo;
+                if (col == tg_hi) tl_hi = l_hi;
+              } else {
+                __nv_bfloat16* dl = reinterpret_cast<__nv_bfloat16*>(p.dlogits[k]);
+                if (ok_lo) dl[(long long)r_lo * V + col] =
+                    __float2bfloat16_rn(g_lo * (__expf(l_lo - lse_lo) - (col == tg_lo ? 1.f : 0.f)));
+                if (ok_hi) dl[(long long)r_hi * V + col] =
+                    __float2bfloat16_rn(g_hi * (__expf(l_hi - lse_hi) - (col == tg_hi ? 1.f : 0.f)));
               }
-              float mn = fmaxf(m_lo, l_lo);
-              s_lo = s_lo * __expf(m_lo - mn) + __expf(l_lo - mn); m_lo = mn;
-              mn = fmaxf(m_hi, l_hi);
-              s_hi = s_hi * __expf(m_hi - mn) + __expf(l_hi - mn); m_hi = mn;
-              if (col == tg_lo) tl_lo = l_lo;
-              if (col == tg_hi) tl_hi = l_hi;
-            } else {
-              __nv_bfloat16* dl = reinterpret_cast<__nv_bfloat16*>(p.dlogits[k]);
-              if (ok_lo) dl[(long long)r_lo * V + col] =
-                  __float2bfloat16_rn(g_lo * (__expf(l_lo - lse_lo) - (col == tg_lo ? 1.f : 0.f)));
-              if (ok_hi) dl[(long long)r_hi * V + col] =
-                  __float2bfloat16_rn(g_hi * (__expf(l_hi - lse_hi) - (col == tg_hi ? 1.f : 0.f)));
             }
           }
         }
