@@ -280,8 +280,12 @@ def run_b200_arm(args):
             line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
         _emit(line)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # Every collective of the run has completed (the max-over-ranks reductions above were the last ones).
+        # Tearing NCCL down after CUDA-graph-captured collectives was observed to hang at exit on 8 ranks,
+        # so leave without the destroy/barrier handshake.
+        torch.cuda.synchronize()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def _measured_traffic():
