@@ -220,16 +220,24 @@ class PhonemeLaTr(nn.Module, _VisionMixin):
 
     @torch.no_grad()
     def greedy_generate(self, pixel_values, coordinates, input_ids, src_attention_mask, ocr_attention_mask,
-                        tokenized_ocr, start_symbol, end_symbol, max_len=100):
+                        tokenized_ocr, start_symbol, end_symbol, max_len=100, use_cache=True):
+        """reference :169-217.  `use_cache=True` decodes incrementally with a key/value cache (SURVEY §8f rank 1);
+        `use_cache=False` re-runs the decoder over the growing prefix exactly like the reference loop."""
         bz = input_ids.size(0)
         dev = input_ids.device
         enc, attention_mask = self._encode(pixel_values, coordinates, input_ids, ocr_attention_mask,
                                            src_attention_mask, tokenized_ocr)
         ys = torch.tensor([[[start_symbol, 0, 0]]], dtype=torch.long, device=dev).repeat(bz, 1, 1)
-        for _ in range(max_len):
-            out = self.decode(ys, enc, attention_mask)
+        cache = self.decoder.new_cache(enc, max_len + 1, self.compute_dtype) if use_cache else None
+        pe = self.positional_encoding.pos_embedding
+        for t in range(max_len):
+            if use_cache:
+                emb = self.tgt_tok_emb(ys[:, -1:], pe[:, t:t + 1], out_dtype=torch.float32)
+                out = self.decoder.step(emb, cache, attention_mask, self.compute_dtype)
+            else:
+                out = self.decode(ys, enc, attention_mask)[:, -1:]
             # NOTE: like the reference (:195-205) greedy decoding does NOT apply shared_lm_head
-            on, rh, to = self._heads(out[:, -1:].to(self.compute_dtype))
+            on, rh, to = self._heads(out.to(self.compute_dtype))
             nxt = torch.stack([on[:, -1].float().argmax(-1), rh[:, -1].float().argmax(-1),
                                to[:, -1].float().argmax(-1)], dim=-1)
             ys = torch.cat([ys, nxt.unsqueeze(1)], dim=1)

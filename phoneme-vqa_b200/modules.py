@@ -567,6 +567,25 @@ class TransformerDecoderLayer(nn.Module):
         return x
 
 
+class DecoderCache:
+    """Per-layer key/value cache for incremental (one new token per call) decoding: the cross-attention K/V of
+    the encoder memory are projected once, the self-attention K/V grow by one position per step.  The
+    reference re-runs the whole 4-layer decoder over the growing prefix every step (core/model/PhonemeLaTr.py
+    :193-215, O(T^2) layer passes); with the cache a step is O(1) layer passes and reads only the prefix K/V."""
+
+    def __init__(self, layers, memory, max_len, compute_dtype):
+        B, S, d = memory.shape
+        l0 = layers[0]
+        H, D = l0.self_attn.num_heads, l0.self_attn.head_dim
+        self.len = 0
+        self.max_len = max_len
+        self.self_kv = [torch.empty((B, max_len, 2, H, D), dtype=compute_dtype, device=memory.device) for _ in layers]
+        self.mem_kv = []
+        for layer in layers:
+            ca = layer.multihead_attn
+            self.mem_kv.append(_lin_rows(memory, ca.in_proj_weight, ca.in_proj_bias, d, 3 * d).view(B, S, 2, H, D))
+
+
 class _DecoderStack(nn.Module):
     def __init__(self, d_model, n_head, num_layers):
         super().__init__()
@@ -605,6 +624,40 @@ class BaseDecoder(nn.Module):
         mem = memory.to(compute_dtype)
         for layer in self.decoder.layers:
             x = layer(x, mem, tka, mka, compute_dtype, causal=causal)
+        return x
+
+    # ---- incremental decoding (inference only) ----
+    def new_cache(self, memory, max_len, compute_dtype):
+        return DecoderCache(self.decoder.layers, memory.to(compute_dtype), max_len, compute_dtype)
+
+    @torch.no_grad()
+    def step(self, x_t, cache, memory_key_padding_mask=None, compute_dtype=torch.float32):
+        """x_t (B,1,d): embedding (+PE) of the newest target position.  Returns the decoder output for that
+        position — identical (up to float reassociation) to row t of the full causal pass."""
+        mka = None if memory_key_padding_mask is None else memory_key_padding_mask.to(torch.float32).contiguous()
+        x = x_t.float()
+        B, _, d = x.shape
+        t = cache.len
+        assert t < cache.max_len, "decoder cache is full"
+        for li, layer in enumerate(self.decoder.layers):
+            sa, ca = layer.self_attn, layer.multihead_attn
+            H, D = sa.num_heads, sa.head_dim
+            scale = 1.0 / math.sqrt(D)
+            qkv = _lin(x.to(compute_dtype), sa.in_proj_weight, sa.in_proj_bias).view(B, 1, 3, H, D)
+            cache.self_kv[li][:, t] = qkv[:, 0, 1:]
+            kv = cache.self_kv[li][:, : t + 1]
+            a, _ = ops.attention_fwd_raw(qkv[:, :, 0].contiguous(), kv[:, :, 0], kv[:, :, 1], scale)
+            a = _lin(a.reshape(B, 1, d), sa.out_proj.weight, sa.out_proj.bias)
+            x = F.layer_norm(x + a.float(), (d,), layer.norm1.weight, layer.norm1.bias, layer.norm1.eps)
+            q = _lin_rows(x.to(compute_dtype), ca.in_proj_weight, ca.in_proj_bias, 0, d).view(B, 1, H, D)
+            mkv = cache.mem_kv[li]
+            c, _ = ops.attention_fwd_raw(q, mkv[:, :, 0], mkv[:, :, 1], scale, None, mka)
+            c = _lin(c.reshape(B, 1, d), ca.out_proj.weight, ca.out_proj.bias)
+            x = F.layer_norm(x + c.float(), (d,), layer.norm2.weight, layer.norm2.bias, layer.norm2.eps)
+            h = torch.relu(_lin(x.to(compute_dtype), layer.linear1.weight, layer.linear1.bias))
+            h = _lin(h, layer.linear2.weight, layer.linear2.bias)
+            x = F.layer_norm(x + h.float(), (d,), layer.norm3.weight, layer.norm3.bias, layer.norm3.eps)
+        cache.len = t + 1
         return x
 
 

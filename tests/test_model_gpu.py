@@ -237,3 +237,21 @@ def test_phoneme_sal_matches_oracle(dtype):
                 for k, p in oracle.named_parameters() if p.grad is not None}
         bad = {k: (errs[k], base[k]) for k in errs if errs[k] > 1.25 * base[k] + 1e-2}
         assert not bad, bad
+
+
+def test_greedy_decoding_with_kv_cache_matches_uncached_reference_loop():
+    """incremental decoding must give the same ids as the reference's O(T^2) loop."""
+    g = np.load(os.path.join(GOLD, "model_phonemelatr_tiny.npz"))
+    cfg = ref_model.tiny_config()
+    _, model = _pair(cfg)
+    model.eval()
+    batch = ref_model.synthetic_batch(3, cfg, T=9, L_ocr=12, L_q=6, V_sub=VOCAB, seed=7, image=32)
+    args = [batch[k].to(DEV) for k in ("pixel_values", "coordinates", "input_ids", "src_attention_mask",
+                                       "ocr_attention_mask", "tokenized_ocr")]
+    for dtype in (torch.float32, torch.bfloat16):
+        model.set_compute_dtype(dtype)
+        cached = model.greedy_generate(*args, start_symbol=3, end_symbol=4, max_len=12, use_cache=True)
+        plain = model.greedy_generate(*args, start_symbol=3, end_symbol=4, max_len=12, use_cache=False)
+        assert torch.equal(cached, plain), dtype
+        if dtype == torch.float32:
+            assert np.array_equal(cached[:, :7].cpu().numpy(), g["greedy_ids"])       # the reference's own ids
