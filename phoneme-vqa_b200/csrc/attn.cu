@@ -168,6 +168,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
 
   const int i = i0 + rowl;
+  const bool rows_dead = i0 + (warp & 3) * 32 >= p.Sq;      // all 32 query rows of this warp are past the end
   const float sl2 = p.scale * kLog2e;
   const uint32_t idesc_qk = tc05::idesc_bf16(kBM, kBN, 0, 0);
   const uint32_t idesc_pv = tc05::idesc_bf16(kBM, kD, 0, 1);      // B = V is MN-major (d contiguous)
@@ -221,6 +222,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
       const int jb = j0 + half * 64 + c * 32;
+      if (jb >= p.Sk || rows_dead) continue;        // warp-uniform: chunk beyond the last key / no live query row
       uint32_t r[32];
       tc05::tmem_ld_32x32(tmem_row + half * 64 + c * 32, r);
       tc05::tmem_ld_wait();
@@ -268,6 +270,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint8_t* prow = smem + kOffP + half * (kBM * 128) + rowl * 128;
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
+      if (j0 + half * 64 + c * 32 >= p.Sk || rows_dead) {      // dead chunk: P must still be zero for the PV MMA
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(prow + (((c * 4 + q) ^ (rowl & 7)) * 16)) = make_uint4(0u, 0u, 0u, 0u);
+        continue;
+      }
       uint32_t r[32];
       tc05::tmem_ld_32x32(tmem_row + half * 64 + c * 32, r);
       tc05::tmem_ld_wait();
@@ -548,7 +556,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc05::tc_fence_after_sync();
 
     // ---- P and dS for this thread's 32 columns ----
-    {
+    if (j0 + jl0 >= p.Sk || i0 + (warp & 3) * 32 >= p.Sq) {
+      // warp-uniform dead block (keys past Sk or query rows past Sq): P = dS = 0, nothing to compute
+      uint8_t* prow = smem + kBOffP + (qd >> 1) * (kBM * 128) + rowl * 128;
+      uint8_t* dsrow = smem + kBOffdS + (qd >> 1) * (kBM * 128) + rowl * 128;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int chunk = ((qd & 1) * 4 + q) ^ (rowl & 7);
+        *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(dsrow + chunk * 16) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    } else {
       uint32_t rs[32], rp[32];
       tc05::tmem_ld_32x32(tmem_row + jl0, rs);
       tc05::tmem_ld_32x32(tmem_row + kBN + jl0, rp);
