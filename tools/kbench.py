@@ -137,7 +137,7 @@ def bench_embed(B=64):
     return res
 
 
-def bench_attn(B=64, H=12, S=327, T=127, dropout=0.1, iters=10):
+def bench_attn(B=64, H=12, S=327, T=127, dropout=0.1, iters=10, only=None):
     """tcgen05 attention kernels at the PhonoLaTr-base shapes; TFLOP/s against the measured bf16 peak.
     flops: fwd 4*B*H*Sq*Sk*D, bwd 10*B*H*Sq*Sk*D (5 GEMMs), causal halves both."""
     import math
@@ -147,13 +147,15 @@ def bench_attn(B=64, H=12, S=327, T=127, dropout=0.1, iters=10):
     g = torch.Generator(device="cuda").manual_seed(0)
     for name, Sq, Sk, causal, rel, scale in [("enc_self", S, S, False, True, 1.0), ("dec_self", T, T, True, False, 0.125),
                                             ("dec_cross", T, S, False, False, 0.125)]:
+        if only and name != only:
+            continue
         q = (torch.randn(B, Sq, H, 64, device="cuda", generator=g) * 0.5).bfloat16()
         kv = (torch.randn(B, Sk, 2, H, 64, device="cuda", generator=g) * 0.5).bfloat16()
         k, v = kv[:, :, 0], kv[:, :, 1]
         rb = torch.randn(H, Sq + Sk - 1, device="cuda", generator=g) if rel else None
         ka = torch.zeros(B, Sk, device="cuda")
         go = torch.randn(B, Sq, H, 64, device="cuda", generator=g).bfloat16()
-        for p in (0.0, dropout):
+        for p in ((dropout,) if only else (0.0, dropout)):
             drop = (p, 1234, 0)
             fwd = lambda: ops.attention_fwd_raw(q, k, v, scale, rb, ka, causal, drop)  # noqa: E731
             o, lse = fwd()
@@ -186,6 +188,8 @@ if __name__ == "__main__":
         out.update(bench_embed())
     if which in ("attn", "all"):
         out.update(bench_attn())
+    if which == "attn_one":         # bench shape, encoder self-attention with dropout, one timed call (for ncu --set full)
+        out.update(bench_attn(B=64, iters=1, only="enc_self"))
     if which == "attn_small":       # short run for ncu
         out.update(bench_attn(B=8, iters=1))
     print(json.dumps(out, indent=1))
