@@ -106,7 +106,9 @@ __global__ void __launch_bounds__(kFwdThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnFwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment for SWIZZLE_128B, computed as an OFFSET into the __shared__ array so that the compiler
+  // keeps the shared address space (32-bit LDS/STS instead of generic 64-bit LD/ST for every smem access)
+  uint8_t* smem = smem_raw + ((1024u - (tc05::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bar_q = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* bar_k = bar_q + 1;            // [2] by tile parity
   uint64_t* bar_v = bar_q + 3;            // [2]
@@ -437,7 +439,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
                 const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment for SWIZZLE_128B, computed as an OFFSET into the __shared__ array so that the compiler
+  // keeps the shared address space (32-bit LDS/STS instead of generic 64-bit LD/ST for every smem access)
+  uint8_t* smem = smem_raw + ((1024u - (tc05::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bar_kv = reinterpret_cast<uint64_t*>(smem + kBOffBar);
   uint64_t* bar_ld = bar_kv + 1;          // [2]
   uint64_t* bar_s = bar_kv + 3;
