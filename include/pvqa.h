@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PVQA_ABI_VERSION 4
+#define PVQA_ABI_VERSION 5
 
 typedef enum {
   PVQA_OK = 0,
@@ -291,6 +291,29 @@ int pvqa_relu_dropout_fwd(const void* x, void* y, int64_t n, int dtype, float dr
                           uint64_t offset, void* stream);
 int pvqa_relu_dropout_bwd(const void* dy, const void* y, void* dx, int64_t n, int dtype, float dropout_p,
                           void* stream);
+
+/* Post-norm tail of the target decoder layer, one launch per sublayer:
+ *     y = LayerNorm(hidden + dropout(update))        (biased variance, eps inside the rsqrt)
+ * replaces the `x = self.normN(x + self.dropoutN(block(x)))` lines of torch's nn.TransformerDecoderLayer
+ * (norm_first=False), which the reference instantiates in core/model/modules/transformer_utils.py:47-64 and runs
+ * from core/model/PhonemeLaTr.py:134-144.  hidden/y/z are fp32 (N, d); update is bf16 or fp32; y_lp (optional)
+ * is the bf16 copy of y the next GEMM consumes; z (optional) is the pre-norm sum saved for the backward;
+ * mean/rstd are (N).  The dropout mask is the one pvqa_residual_dropout_add draws for the same (seed, offset).
+ * Backward: dy and/or dy_lp are the gradients of y / y_lp; d_hidden (fp32) is the residual-path gradient,
+ * d_update = mask * d_hidden / keep in the update's dtype; dgamma/dbeta (d) are ACCUMULATED. */
+int pvqa_add_dropout_ln_fwd(const float* hidden, const void* update /* may be NULL: plain LayerNorm */, int upd_dtype,
+                            const float* gamma, const float* beta, float* z, float* y, void* y_lp, int lp_dtype,
+                            float* mean, float* rstd, int64_t N, int64_t d, float eps, float dropout_p, uint64_t seed,
+                            uint64_t offset, void* stream);
+int pvqa_add_dropout_ln_bwd(const float* dy, const void* dy_lp, int lp_dtype, const float* z, const float* gamma,
+                            const float* mean, const float* rstd, float* d_hidden, void* d_update /* may be NULL */,
+                            int upd_dtype, float* dgamma, float* dbeta, int64_t N, int64_t d, float dropout_p,
+                            uint64_t seed, uint64_t offset, void* stream);
+
+/* out[c] (+)= sum_r x[r][c] in fp32: the bias gradient of every biased Linear on the decoder path
+ * (autograd's `grad_output.sum(0)` for nn.Linear / nn.MultiheadAttention in_proj/out_proj biases).
+ * x is (N, d) bf16 or fp32 row-major, d % 8 == 0; accumulate == 0 zeroes `out` first. */
+int pvqa_col_sum(const void* x, float* out, int64_t N, int64_t d, int dtype, int accumulate, void* stream);
 
 #ifdef __cplusplus
 }

@@ -50,6 +50,22 @@ __device__ __forceinline__ uint4 keep_bytes16(uint64_t seed, uint64_t offset, ui
 // byte `bb` of m replicated to a full-word mask
 #define PVQA_BYTE_MASK(m, bb) __byte_perm((m), 0u, 0x1111u * (bb))
 
+// Developer-only phase trace (tools/attn_trace.py builds a private copy of the library with -DPVQA_ATTN_TRACE):
+// CTAs (x=1, y=3, z<64) record clock64() at phase boundaries, thread 0 in slots [0,32), the first lane of the
+// last warp in [32,64).  Compiled out of the product library.
+#ifdef PVQA_ATTN_TRACE
+__device__ long long g_attn_trace[64 * 64];
+#define PVQA_TRACE(ev)                                                                              \
+  do {                                                                                              \
+    if (blockIdx.x == 1 && blockIdx.y == 3 && blockIdx.z < 64 && (ev) < 32) {                       \
+      if (threadIdx.x == 0) g_attn_trace[blockIdx.z * 64 + (ev)] = clock64();                       \
+      if (threadIdx.x == blockDim.x - 32) g_attn_trace[blockIdx.z * 64 + 32 + (ev)] = clock64();    \
+    }                                                                                               \
+  } while (0)
+#else
+#define PVQA_TRACE(ev)
+#endif
+
 // =================================================================================
 // forward
 // =================================================================================
@@ -127,6 +143,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rowl = (warp & 3) * 32 + lane;          // row in the tile == TMEM lane
   const int half = warp >> 2;                       // column half owned by this thread
+  PVQA_TRACE(0);
   const int i0 = blockIdx.x * kBM;
   const int h = blockIdx.y, b = blockIdx.z;
 
@@ -156,6 +173,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc05::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  PVQA_TRACE(1);
 
   int n_tiles = n_tiles_all;
   if (p.causal) n_tiles = min(n_tiles, min(i0 + kBM - 1, p.Sq - 1) / kBN + 1);
@@ -214,6 +232,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const bool diag = p.causal && (j0 + kBN - 1 > i0);     // tile touches the diagonal (CTA-uniform)
     tc05::mbar_wait(bar_s, ph);
     tc05::tc_fence_after_sync();
+    PVQA_TRACE(2 + 6 * t);
     if (tid == 0 && t + 1 < n_tiles) {   // K_j is consumed: its buffer takes V_{j+1}
       tc05::mbar_expect_tx(bar_v + ((t + 1) & 1), kKVBuf);
       tc05::tma_load_4d(smem + kOffKV + ((2 * t) % 3) * kKVBuf, &tmV, bar_v + ((t + 1) & 1), 0, h, j0 + kBN, b);
@@ -261,7 +280,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     tc05::tmem_st_wait();
     s_x[half * kBM + rowl] = mx;
+    PVQA_TRACE(3 + 6 * t);
     __syncthreads();
+    PVQA_TRACE(4 + 6 * t);
     mx = fmaxf(mx, s_x[(half ^ 1) * kBM + rowl]);
     const float m_new = fmaxf(m_run, mx);
     const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
@@ -310,6 +331,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     l_run = l_run * alpha + sum;
     m_run = m_new;
+    PVQA_TRACE(5 + 6 * t);
 
     tc05::fence_proxy_async_smem();
     tc05::tc_fence_before_sync();
@@ -328,6 +350,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     tc05::mbar_wait(bar_o, ph);
     tc05::tc_fence_after_sync();
+    PVQA_TRACE(6 + 6 * t);
     {
       uint32_t r[32];
       tc05::tmem_ld_32x32(tmem_row + kBN + half * 32, r);
@@ -338,6 +361,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc05::tc_fence_before_sync();
     __syncthreads();          // TMEM S/O_j and smem K/V/P are free for the next tile
     tc05::tc_fence_after_sync();
+    PVQA_TRACE(7 + 6 * t);
   }
 
   // ---- epilogue: combine the two half-row sums, normalise, write O (bf16) and lse (natural log) ----
@@ -356,8 +380,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       p.lse[((long long)b * p.H + h) * p.Sq + i] =
           l_tot > 0.f ? (m_run + log2f(l_tot) - m_shift) * (1.0f / kLog2e) : -INFINITY;
   }
+  PVQA_TRACE(30);
   tc05::tc_fence_before_sync();
   __syncthreads();
+  PVQA_TRACE(31);
   if (warp == 0) tc05::tmem_dealloc(tmem_base, kTmemCols);
 }
 
@@ -461,6 +487,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int qd = warp >> 2;                    // which quarter of the columns this thread owns
   const int j0 = blockIdx.x * kBN;
   const int h = blockIdx.y, b = blockIdx.z;
+  PVQA_TRACE(0);
 
   if (tid == 0) {
     tc05::prefetch_tmap(&tmQ); tc05::prefetch_tmap(&tmK); tc05::prefetch_tmap(&tmV); tc05::prefetch_tmap(&tmdO);
@@ -493,6 +520,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc05::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  PVQA_TRACE(1);
 
   const int m_tiles = (p.Sq + kBM - 1) / kBM;
   const int m_first = p.causal ? (j0 / kBM) : 0;      // query tiles entirely above the diagonal see nothing
@@ -558,6 +586,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float* relrow = s_rel + (p.Sq - 1 - i) + kRelPad;      // relrow[jl] = bias of local key jl for this row
     tc05::mbar_wait(bar_s, ph);
     tc05::tc_fence_after_sync();
+    PVQA_TRACE(2 + 5 * it);
 
     // ---- P and dS for this thread's 32 columns ----
     if (j0 + jl0 >= p.Sk || i0 + (warp & 3) * 32 >= p.Sq) {
@@ -654,9 +683,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         *reinterpret_cast<uint4*>(dsrow + chunk * 16) = pack8(dsv + q * 8);
       }
     }
+    PVQA_TRACE(3 + 5 * it);
     tc05::fence_proxy_async_smem();
     tc05::tc_fence_before_sync();
     __syncthreads();
+    PVQA_TRACE(4 + 5 * it);
     if (tid == 0) {
       tc05::tc_fence_after_sync();
 #pragma unroll
@@ -676,6 +707,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     tc05::mbar_wait(bar_dq, ph);
     tc05::tc_fence_after_sync();
+    PVQA_TRACE(5 + 5 * it);
     {
       uint32_t r[16];
       tc05::tmem_ld_32x16(tmem_row + qd * 16, r);
@@ -691,6 +723,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc05::tc_fence_before_sync();
     __syncthreads();
     tc05::tc_fence_after_sync();
+    PVQA_TRACE(6 + 5 * it);
   }
 
   if (it == 0 && tid == 0) tc05::mbar_wait(bar_kv, 0);     // never leave with a TMA write in flight
@@ -727,8 +760,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (r < n_rel && g != 0.f) atomicAdd(p.d_rel + (long long)h * n_rel + r, g * inv_scale);
     }
   }
+  PVQA_TRACE(30);
   tc05::tc_fence_before_sync();
   __syncthreads();
+  PVQA_TRACE(31);
   if (has_scp && p.d_scp && tid < 32) {
     float g = 0.f;
 #pragma unroll
@@ -778,6 +813,17 @@ static int make_tmap(CUtensorMap* m, const void* ptr, int64_t B, int64_t S, int6
 }  // namespace pvqa
 
 using namespace pvqa;
+
+#ifdef PVQA_ATTN_TRACE
+extern "C" int pvqa_debug_attn_trace(long long* host, int clear) {
+  if (host && cudaMemcpyFromSymbol(host, g_attn_trace, sizeof(long long) * 64 * 64) != cudaSuccess) return PVQA_ERR_CUDA;
+  if (clear) {
+    static long long zeros[64 * 64];
+    if (cudaMemcpyToSymbol(g_attn_trace, zeros, sizeof(zeros)) != cudaSuccess) return PVQA_ERR_CUDA;
+  }
+  return PVQA_OK;
+}
+#endif
 
 extern "C" int pvqa_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
                              const float* rel_bias, const float* key_add, int64_t B, int64_t H, int64_t Sq,

@@ -202,6 +202,211 @@ relu_dropout_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __
   }
 }
 
+// ---------------- y = LayerNorm(hidden + dropout(update)): post-norm tail of the target decoder layer ----------------
+// One warp per row, the row lives in registers (NV chunks of 8 elements per lane: d <= 256 * NV).  The dropout
+// mask uses the same flat element index (row * d + col) as residual_dropout_add, so the fused kernel is
+// bit-compatible with the unfused pair.  Outputs: z (pre-norm sum, saved for backward), y (fp32 residual
+// stream) and optionally y_lp (the low-precision copy the next GEMM reads).
+template <typename UT, typename LT, int NV>
+__global__ void __launch_bounds__(kNormThreads)
+add_dropout_ln_fwd_kernel(const float* __restrict__ hidden, const UT* __restrict__ upd, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, float* __restrict__ z, float* __restrict__ y,
+                          LT* __restrict__ y_lp, float* __restrict__ mean, float* __restrict__ rstd, int N, int d,
+                          float eps, uint32_t thr16, float scale, uint64_t seed, uint64_t offset,
+                          const unsigned long long* rng_base) {
+  if (thr16 && rng_base) offset += *rng_base;
+  const int lane = threadIdx.x & 31;
+  const float inv_d = 1.0f / (float)d;
+  for (int row = blockIdx.x * (kNormThreads / 32) + (threadIdx.x >> 5); row < N; row += gridDim.x * (kNormThreads / 32)) {
+    const long long base = (long long)row * d;
+    f8 v[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < d) {
+        v[c] = Vec8<float>::load_stream(hidden + base + col);
+        if (upd) {
+          const f8 u = Vec8<UT>::load_stream(upd + base + col);
+          if (thr16) {
+            const uint32_t m = dropout_keep8(seed, offset, (uint64_t)(base + col), thr16);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[c].v[j] += ((m >> j) & 1u) ? u.v[j] * scale : 0.f;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[c].v[j] += u.v[j];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[c].v[j];
+      }
+    }
+    const float mu = warp_sum_n(s) * inv_d;
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+      if ((c * 32 + lane) * 8 < d) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float t = v[c].v[j] - mu; ss += t * t; }
+      }
+    }
+    const float r = rsqrtf(warp_sum_n(ss) * inv_d + eps);
+    if (lane == 0) {
+      if (mean) mean[row] = mu;
+      if (rstd) rstd[row] = r;
+    }
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < d) {
+        if (z) Vec8<float>::store(z + base + col, v[c]);
+        const f8 g = Vec8<float>::load(gamma + col), bt = Vec8<float>::load(beta + col);
+        f8 o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o.v[j] = (v[c].v[j] - mu) * r * g.v[j] + bt.v[j];
+        if (y) Vec8<float>::store(y + base + col, o);
+        if (y_lp) Vec8<LT>::store(y_lp + base + col, o);
+      }
+    }
+  }
+}
+
+// backward of the fused tail.  g = dy (+ dy_lp), xhat = (z - mean) * rstd, wg = g * gamma:
+//   dz = rstd * (wg - mean(wg) - xhat * mean(wg * xhat));  d_hidden = dz;  d_update = mask * dz / keep
+//   dgamma += sum_rows g * xhat;  dbeta += sum_rows g      (register partials -> smem -> one global atomic per CTA column)
+template <typename UT, typename LT, int NV>
+__global__ void __launch_bounds__(kNormThreads)
+add_dropout_ln_bwd_kernel(const float* __restrict__ dy, const LT* __restrict__ dy_lp, const float* __restrict__ z,
+                          const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+                          float* __restrict__ d_hidden, UT* __restrict__ d_upd, float* __restrict__ dgamma,
+                          float* __restrict__ dbeta, int N, int d, uint32_t thr16, float scale, uint64_t seed,
+                          uint64_t offset, const unsigned long long* rng_base) {
+  extern __shared__ float s_part[];           // [2][d] block partials of dgamma, dbeta
+  if (thr16 && rng_base) offset += *rng_base;
+  const int lane = threadIdx.x & 31;
+  const float inv_d = 1.0f / (float)d;
+  for (int c = threadIdx.x; c < 2 * d; c += kNormThreads) s_part[c] = 0.f;
+  __syncthreads();
+  f8 acc_g[NV], acc_b[NV];
+#pragma unroll
+  for (int c = 0; c < NV; ++c) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc_g[c].v[j] = 0.f; acc_b[c].v[j] = 0.f; }
+  }
+  for (int row = blockIdx.x * (kNormThreads / 32) + (threadIdx.x >> 5); row < N; row += gridDim.x * (kNormThreads / 32)) {
+    const long long base = (long long)row * d;
+    const float mu = mean[row], r = rstd[row];
+    f8 xh[NV], wg[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < d) {
+        f8 g;
+        if (dy) g = Vec8<float>::load_stream(dy + base + col);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g.v[j] = 0.f;
+        }
+        if (dy_lp) {
+          const f8 g2 = Vec8<LT>::load_stream(dy_lp + base + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g.v[j] += g2.v[j];
+        }
+        const f8 zz = Vec8<float>::load_stream(z + base + col);
+        const f8 gm = Vec8<float>::load(gamma + col);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xhat = (zz.v[j] - mu) * r;
+          xh[c].v[j] = xhat;
+          acc_g[c].v[j] = fmaf(g.v[j], xhat, acc_g[c].v[j]);
+          acc_b[c].v[j] += g.v[j];
+          const float w = g.v[j] * gm.v[j];
+          wg[c].v[j] = w;
+          s1 += w;
+          s2 = fmaf(w, xhat, s2);
+        }
+      }
+    }
+    const float c1 = warp_sum_n(s1) * inv_d, c2 = warp_sum_n(s2) * inv_d;
+#pragma unroll
+    for (int c = 0; c < NV; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      if (col < d) {
+        f8 o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o.v[j] = r * (wg[c].v[j] - c1 - xh[c].v[j] * c2);
+        Vec8<float>::store(d_hidden + base + col, o);
+        if (d_upd) {
+          if (thr16) {
+            const uint32_t m = dropout_keep8(seed, offset, (uint64_t)(base + col), thr16);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o.v[j] = ((m >> j) & 1u) ? o.v[j] * scale : 0.f;
+          }
+          Vec8<UT>::store(d_upd + base + col, o);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NV; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    if (col < d) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(s_part + col + j, acc_g[c].v[j]);
+        atomicAdd(s_part + d + col + j, acc_b[c].v[j]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += kNormThreads) {
+    atomicAdd(dgamma + c, s_part[c]);
+    atomicAdd(dbeta + c, s_part[d + c]);
+  }
+}
+
+// ---------------- out[c] += sum_rows x[r][c]: bias gradient of a Linear (fp32 accumulation) ----------------
+// CTA = 32 column groups (8 columns each) x 8 row lanes; grid = (column slabs, row slabs).
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads)
+col_sum_kernel(const T* __restrict__ x, float* __restrict__ out, int N, int d, int rows_per_cta) {
+  __shared__ float s_acc[8][32 * 8 + 1];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int col = (blockIdx.x * 32 + cg) * 8;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(N, r0 + rows_per_cta);
+  f8 acc;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc.v[j] = 0.f;
+  if (col < d) {
+    int r = r0 + rl;
+    for (; r + 24 < r1; r += 32) {          // four independent loads in flight per thread
+      const f8 a = Vec8<T>::load_stream(x + (long long)r * d + col);
+      const f8 b = Vec8<T>::load_stream(x + (long long)(r + 8) * d + col);
+      const f8 c = Vec8<T>::load_stream(x + (long long)(r + 16) * d + col);
+      const f8 e = Vec8<T>::load_stream(x + (long long)(r + 24) * d + col);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc.v[j] += (a.v[j] + b.v[j]) + (c.v[j] + e.v[j]);
+    }
+    for (; r < r1; r += 8) {
+      const f8 a = Vec8<T>::load_stream(x + (long long)r * d + col);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc.v[j] += a.v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s_acc[rl][cg * 8 + j] = acc.v[j];
+  __syncthreads();
+  {
+    const int c = threadIdx.x;              // 256 threads == 256 columns of this slab
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += s_acc[k][c];
+    const int gc = blockIdx.x * 256 + c;
+    if (gc < d) atomicAdd(out + gc, t);
+  }
+}
+
 static int ew_grid(long long n8) {
   long long need = (n8 + kNormThreads - 1) / kNormThreads;
   long long cap = (long long)num_sms() * 8;
@@ -349,5 +554,116 @@ extern "C" int pvqa_relu_dropout_bwd(const void* dy, const void* y, void* dx, in
     return fail(PVQA_ERR_DTYPE, "relu_dropout_bwd: bad dtype");
   count_launch();
   PVQA_CHECK_LAUNCH("relu_dropout_bwd");
+  return PVQA_OK;
+}
+
+// ---- fused post-norm tail: y = LayerNorm(hidden + dropout(update)) ----
+template <typename UT, typename LT>
+static int launch_add_ln_fwd(int nv, int grid, cudaStream_t st, const float* hidden, const UT* upd, const float* gamma,
+                             const float* beta, float* z, float* y, LT* y_lp, float* mean, float* rstd, int N, int d,
+                             float eps, uint32_t thr, float sc, uint64_t seed, uint64_t offset) {
+#define PVQA_LN_FWD(NV) add_dropout_ln_fwd_kernel<UT, LT, NV><<<grid, kNormThreads, 0, st>>>( \
+    hidden, upd, gamma, beta, z, y, y_lp, mean, rstd, N, d, eps, thr, sc, seed, offset, g_rng_base)
+  switch (nv) { case 1: PVQA_LN_FWD(1); break; case 2: PVQA_LN_FWD(2); break; case 3: PVQA_LN_FWD(3); break; default: PVQA_LN_FWD(4); }
+#undef PVQA_LN_FWD
+  return PVQA_OK;
+}
+template <typename UT, typename LT>
+static int launch_add_ln_bwd(int nv, int grid, size_t smem, cudaStream_t st, const float* dy, const LT* dy_lp,
+                             const float* z, const float* gamma, const float* mean, const float* rstd, float* d_hidden,
+                             UT* d_upd, float* dgamma, float* dbeta, int N, int d, uint32_t thr, float sc, uint64_t seed,
+                             uint64_t offset) {
+#define PVQA_LN_BWD(NV) add_dropout_ln_bwd_kernel<UT, LT, NV><<<grid, kNormThreads, smem, st>>>( \
+    dy, dy_lp, z, gamma, mean, rstd, d_hidden, d_upd, dgamma, dbeta, N, d, thr, sc, seed, offset, g_rng_base)
+  switch (nv) { case 1: PVQA_LN_BWD(1); break; case 2: PVQA_LN_BWD(2); break; case 3: PVQA_LN_BWD(3); break; default: PVQA_LN_BWD(4); }
+#undef PVQA_LN_BWD
+  return PVQA_OK;
+}
+
+extern "C" int pvqa_add_dropout_ln_fwd(const float* hidden, const void* update, int upd_dtype, const float* gamma,
+                                       const float* beta, float* z, float* y, void* y_lp, int lp_dtype, float* mean,
+                                       float* rstd, int64_t N, int64_t d, float eps, float dropout_p, uint64_t seed,
+                                       uint64_t offset, void* stream) {
+  PVQA_REQUIRE(N >= 0 && d > 0, PVQA_ERR_SHAPE, "add_dropout_ln_fwd: bad dimension");
+  PVQA_REQUIRE(d % 8 == 0 && d <= 1024, PVQA_ERR_SHAPE, "add_dropout_ln_fwd: d=%lld must be a multiple of 8 and <= 1024", (long long)d);
+  PVQA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, PVQA_ERR_SHAPE, "add_dropout_ln_fwd: dropout_p must be in [0,1)");
+  if (N == 0) return PVQA_OK;
+  PVQA_REQUIRE(hidden && gamma && beta && (y || y_lp), PVQA_ERR_NULL, "add_dropout_ln_fwd: NULL pointer");
+  PVQA_REQUIRE(aligned16(hidden) && aligned16(update) && aligned16(gamma) && aligned16(beta) && aligned16(z) &&
+                   aligned16(y) && aligned16(y_lp), PVQA_ERR_ALIGN, "add_dropout_ln_fwd: 16-byte alignment required");
+  PVQA_REQUIRE(!y_lp || lp_dtype == PVQA_BF16, PVQA_ERR_DTYPE, "add_dropout_ln_fwd: the low-precision copy must be bf16");
+  uint32_t thr; float sc;
+  drop_consts(update ? dropout_p : 0.f, thr, sc);
+  const int warps = kNormThreads / 32, nv = (int)((d + 255) / 256);
+  long long need = (N + warps - 1) / warps, cap = (long long)num_sms() * 8;
+  const int grid = (int)(need < cap ? need : cap);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (upd_dtype == PVQA_BF16)
+    launch_add_ln_fwd<__nv_bfloat16, __nv_bfloat16>(nv, grid, st, hidden, (const __nv_bfloat16*)update, gamma, beta, z, y, (__nv_bfloat16*)y_lp, mean, rstd, (int)N, (int)d, eps, thr, sc, seed, offset);
+  else if (upd_dtype == PVQA_F32)
+    launch_add_ln_fwd<float, __nv_bfloat16>(nv, grid, st, hidden, (const float*)update, gamma, beta, z, y, (__nv_bfloat16*)y_lp, mean, rstd, (int)N, (int)d, eps, thr, sc, seed, offset);
+  else
+    return fail(PVQA_ERR_DTYPE, "add_dropout_ln_fwd: bad update dtype");
+  count_launch();
+  PVQA_CHECK_LAUNCH("add_dropout_ln_fwd");
+  return PVQA_OK;
+}
+
+extern "C" int pvqa_add_dropout_ln_bwd(const float* dy, const void* dy_lp, int lp_dtype, const float* z,
+                                       const float* gamma, const float* mean, const float* rstd, float* d_hidden,
+                                       void* d_update, int upd_dtype, float* dgamma, float* dbeta, int64_t N, int64_t d,
+                                       float dropout_p, uint64_t seed, uint64_t offset, void* stream) {
+  PVQA_REQUIRE(N >= 0 && d > 0, PVQA_ERR_SHAPE, "add_dropout_ln_bwd: bad dimension");
+  PVQA_REQUIRE(d % 8 == 0 && d <= 1024, PVQA_ERR_SHAPE, "add_dropout_ln_bwd: d must be a multiple of 8 and <= 1024");
+  PVQA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, PVQA_ERR_SHAPE, "add_dropout_ln_bwd: dropout_p must be in [0,1)");
+  if (N == 0) return PVQA_OK;
+  PVQA_REQUIRE((dy || dy_lp) && z && gamma && mean && rstd && d_hidden && dgamma && dbeta, PVQA_ERR_NULL, "add_dropout_ln_bwd: NULL pointer");
+  PVQA_REQUIRE(aligned16(dy) && aligned16(dy_lp) && aligned16(z) && aligned16(gamma) && aligned16(d_hidden) && aligned16(d_update),
+               PVQA_ERR_ALIGN, "add_dropout_ln_bwd: 16-byte alignment required");
+  PVQA_REQUIRE(!dy_lp || lp_dtype == PVQA_BF16, PVQA_ERR_DTYPE, "add_dropout_ln_bwd: the low-precision gradient must be bf16");
+  uint32_t thr; float sc;
+  drop_consts(dropout_p, thr, sc);
+  const int warps = kNormThreads / 32, nv = (int)((d + 255) / 256);
+  long long need = (N + warps - 1) / warps, cap = (long long)num_sms() * 2;
+  const int grid = (int)(need < cap ? need : cap);
+  const size_t smem = (size_t)2 * d * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (upd_dtype == PVQA_BF16)
+    launch_add_ln_bwd<__nv_bfloat16, __nv_bfloat16>(nv, grid, smem, st, dy, (const __nv_bfloat16*)dy_lp, z, gamma, mean, rstd, d_hidden, (__nv_bfloat16*)d_update, dgamma, dbeta, (int)N, (int)d, thr, sc, seed, offset);
+  else if (upd_dtype == PVQA_F32)
+    launch_add_ln_bwd<float, __nv_bfloat16>(nv, grid, smem, st, dy, (const __nv_bfloat16*)dy_lp, z, gamma, mean, rstd, d_hidden, (float*)d_update, dgamma, dbeta, (int)N, (int)d, thr, sc, seed, offset);
+  else
+    return fail(PVQA_ERR_DTYPE, "add_dropout_ln_bwd: bad update dtype");
+  count_launch();
+  PVQA_CHECK_LAUNCH("add_dropout_ln_bwd");
+  return PVQA_OK;
+}
+
+extern "C" int pvqa_col_sum(const void* x, float* out, int64_t N, int64_t d, int dtype, int accumulate, void* stream) {
+  PVQA_REQUIRE(N >= 0 && d > 0, PVQA_ERR_SHAPE, "col_sum: bad dimension");
+  PVQA_REQUIRE(d % 8 == 0, PVQA_ERR_SHAPE, "col_sum: d must be a multiple of 8");
+  PVQA_REQUIRE(out, PVQA_ERR_NULL, "col_sum: NULL pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(out, 0, (size_t)d * sizeof(float), st);
+    if (e != cudaSuccess) return fail(PVQA_ERR_CUDA, "col_sum: memset: %s", cudaGetErrorString(e));
+  }
+  if (N == 0) return PVQA_OK;
+  PVQA_REQUIRE(x, PVQA_ERR_NULL, "col_sum: NULL pointer");
+  PVQA_REQUIRE(aligned16(x), PVQA_ERR_ALIGN, "col_sum: 16-byte alignment required");
+  const int slabs = (int)((d + 255) / 256);
+  long long want = ((long long)num_sms() * 4 + slabs - 1) / slabs;      // ~4 CTAs per SM in total
+  long long rows_per = (N + want - 1) / want;
+  if (rows_per < 32) rows_per = 32;
+  rows_per = (rows_per + 7) / 8 * 8;
+  dim3 grid((unsigned)slabs, (unsigned)((N + rows_per - 1) / rows_per));
+  if (dtype == PVQA_BF16)
+    col_sum_kernel<__nv_bfloat16><<<grid, kNormThreads, 0, st>>>((const __nv_bfloat16*)x, out, (int)N, (int)d, (int)rows_per);
+  else if (dtype == PVQA_F32)
+    col_sum_kernel<float><<<grid, kNormThreads, 0, st>>>((const float*)x, out, (int)N, (int)d, (int)rows_per);
+  else
+    return fail(PVQA_ERR_DTYPE, "col_sum: bad dtype");
+  count_launch();
+  PVQA_CHECK_LAUNCH("col_sum");
   return PVQA_OK;
 }

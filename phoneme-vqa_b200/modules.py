@@ -103,7 +103,7 @@ class _LinearLP(torch.autograd.Function):
             grads.append(dW[off:off + r])
             off += r
         if ctx.has_bias:
-            db = dy2.sum(0, dtype=torch.float32)
+            db = ops.col_sum(dy2)
             off = 0
             for r in ctx.rows:
                 grads.append(db[off:off + r])
@@ -540,31 +540,33 @@ class TransformerDecoderLayer(nn.Module):
         self.dropout3 = nn.Dropout(dropout)
         self.p = dropout
 
-    def forward(self, x, memory, tgt_key_add, memory_key_add, compute_dtype, causal=True):
+    def _tail(self, x, update, norm, compute_dtype):
+        """x = norm(x + dropout(update)) in one launch; also returns the compute-dtype copy the next GEMM reads."""
+        y, y_lp = ops.add_dropout_layer_norm(x, update, norm.weight, norm.bias, norm.eps, self.p, self.training,
+                                             want_lp=(compute_dtype == torch.bfloat16))
+        return y, (y_lp if y_lp is not None else y.to(compute_dtype))
+
+    def forward(self, x, memory, tgt_key_add, memory_key_add, compute_dtype, causal=True, xc=None):
+        """-> (x fp32 residual stream, xc = x in compute_dtype for the next layer's first GEMM)"""
         B, T, d = x.shape
         sa, ca = self.self_attn, self.multihead_attn
         H, D = sa.num_heads, sa.head_dim
         p_attn = self.p if self.training else 0.0
         scale = 1.0 / math.sqrt(D)
-        xc = x.to(compute_dtype)
+        if xc is None:
+            xc = x.to(compute_dtype)
         qkv = _lin(xc, sa.in_proj_weight, sa.in_proj_bias).view(B, T, 3, H, D)
         a = ops.attention_self(qkv, scale=scale, rel_bias=None, key_add=tgt_key_add, causal=causal, dropout_p=p_attn)
         a = _lin(a.reshape(B, T, d), sa.out_proj.weight, sa.out_proj.bias)
-        x = F.layer_norm(ops.residual_dropout_add(x, a, self.p, self.training), (d,), self.norm1.weight,
-                         self.norm1.bias, self.norm1.eps)
-        xc = x.to(compute_dtype)
+        x, xc = self._tail(x, a, self.norm1, compute_dtype)
         q = _lin_rows(xc, ca.in_proj_weight, ca.in_proj_bias, 0, d).view(B, T, H, D)
         kv = _lin_rows(memory, ca.in_proj_weight, ca.in_proj_bias, d, 3 * d).view(B, memory.shape[1], 2, H, D)
         c = ops.attention_cross(q, kv, scale=scale, rel_bias=None, key_add=memory_key_add, dropout_p=p_attn)
         c = _lin(c.reshape(B, T, d), ca.out_proj.weight, ca.out_proj.bias)
-        x = F.layer_norm(ops.residual_dropout_add(x, c, self.p, self.training), (d,), self.norm2.weight,
-                         self.norm2.bias, self.norm2.eps)
-        xc = x.to(compute_dtype)
+        x, xc = self._tail(x, c, self.norm2, compute_dtype)
         h = ops.relu_dropout(_lin(xc, self.linear1.weight, self.linear1.bias), self.p, self.training)
         h = _lin(h, self.linear2.weight, self.linear2.bias)
-        x = F.layer_norm(ops.residual_dropout_add(x, h, self.p, self.training), (d,), self.norm3.weight,
-                         self.norm3.bias, self.norm3.eps)
-        return x
+        return self._tail(x, h, self.norm3, compute_dtype)
 
 
 class DecoderCache:
@@ -622,8 +624,9 @@ class BaseDecoder(nn.Module):
         tka, mka = as_add(tgt_key_padding_mask), as_add(memory_key_padding_mask)
         x = tgt.float()
         mem = memory.to(compute_dtype)
+        xc = None
         for layer in self.decoder.layers:
-            x = layer(x, mem, tka, mka, compute_dtype, causal=causal)
+            x, xc = layer(x, mem, tka, mka, compute_dtype, causal=causal, xc=xc)
         return x
 
     # ---- incremental decoding (inference only) ----

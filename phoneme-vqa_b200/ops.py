@@ -364,6 +364,80 @@ def residual_dropout_add(hidden, update, p, training):
     return _ResidualDropoutAdd.apply(hidden, update, p)
 
 
+class _AddDropoutLN(torch.autograd.Function):
+    """y = LayerNorm(hidden + dropout(update)); returns (y fp32, y_lp) where y_lp is the bf16 copy the next
+    GEMM reads (or None).  One launch forward, one backward (include/pvqa.h: pvqa_add_dropout_ln_*)."""
+
+    @staticmethod
+    def forward(ctx, hidden, update, gamma, beta, eps, p, want_lp):
+        lib = _lib.load()
+        _need_cuda(hidden, update, gamma, beta)
+        hidden = hidden.contiguous()
+        update = update.contiguous()
+        d = hidden.shape[-1]
+        N = hidden.numel() // d
+        dev = hidden.device
+        need_grad = any(ctx.needs_input_grad)
+        y = torch.empty_like(hidden)
+        y_lp = torch.empty(hidden.shape, dtype=torch.bfloat16, device=dev) if want_lp else None
+        z = torch.empty_like(hidden) if need_grad else None
+        mean = torch.empty(N, dtype=torch.float32, device=dev) if need_grad else None
+        rstd = torch.empty(N, dtype=torch.float32, device=dev) if need_grad else None
+        seed, off = _Rng.next(hidden.numel()) if p > 0 else (0, 0)
+        with torch.cuda.device(dev), _prof("add_dropout_ln_fwd"):
+            check(lib.pvqa_add_dropout_ln_fwd(_p(hidden), _p(update), _dt(update.dtype), _p(gamma), _p(beta), _p(z), _p(y),
+                                              _p(y_lp), _lib.PVQA_BF16, _p(mean), _p(rstd), N, d, float(eps), float(p),
+                                              seed, off, _stream()), "pvqa_add_dropout_ln_fwd")
+        ctx.save_for_backward(z, gamma, mean, rstd)
+        ctx.meta = (float(p), seed, off, update.dtype, update.shape, N, d)
+        ctx.set_materialize_grads(False)
+        if want_lp:
+            return y, y_lp
+        return y, None
+
+    @staticmethod
+    def backward(ctx, dy, dy_lp):
+        lib = _lib.load()
+        z, gamma, mean, rstd = ctx.saved_tensors
+        p, seed, off, udt, ushape, N, d = ctx.meta
+        dev = z.device
+        if dy is None and dy_lp is None:
+            return None, None, None, None, None, None, None
+        dy = dy.contiguous() if dy is not None else None
+        dy_lp = dy_lp.contiguous() if dy_lp is not None else None
+        d_hidden = torch.empty_like(z)
+        d_upd = torch.empty(ushape, dtype=udt, device=dev)
+        dgb = torch.zeros(2, d, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev), _prof("add_dropout_ln_bwd"):
+            check(lib.pvqa_add_dropout_ln_bwd(_p(dy), _p(dy_lp), _lib.PVQA_BF16, _p(z), _p(gamma), _p(mean), _p(rstd),
+                                              _p(d_hidden), _p(d_upd), _dt(udt), _p(dgb[0]), _p(dgb[1]), N, d, p, seed,
+                                              off, _stream()), "pvqa_add_dropout_ln_bwd")
+        return d_hidden, d_upd, dgb[0], dgb[1], None, None, None
+
+
+def add_dropout_layer_norm(hidden, update, weight, bias, eps, p, training, want_lp=False):
+    """LayerNorm(hidden + dropout(update)) of the post-norm decoder layer; returns (y, y_lp or None)."""
+    p = float(p) if training else 0.0
+    d = hidden.shape[-1]
+    if hidden.dtype != torch.float32 or d % 8 != 0 or d > 1024 or hidden.shape != update.shape:
+        raise TypeError("add_dropout_layer_norm expects an fp32 residual stream with d % 8 == 0 and d <= 1024")
+    return _AddDropoutLN.apply(hidden, update, weight, bias, float(eps), p, bool(want_lp))
+
+
+def col_sum(x2d, out=None):
+    """fp32 column sums of a (N, d) bf16/fp32 matrix (bias gradients)."""
+    lib = _lib.load()
+    _need_cuda(x2d)
+    x2d = x2d.contiguous()
+    N, d = x2d.shape
+    if d % 8 != 0:
+        return x2d.sum(0, dtype=torch.float32)
+    res = torch.empty(d, dtype=torch.float32, device=x2d.device) if out is None else out
+    with torch.cuda.device(x2d.device), _prof("col_sum"):
+        check(lib.pvqa_col_sum(_p(x2d), _p(res), N, d, _dt(x2d.dtype), 0, _stream()), "pvqa_col_sum")
+    return res
+
+
 class _ReluDropout(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, p):

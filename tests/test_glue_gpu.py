@@ -104,3 +104,73 @@ def test_rms_norm_with_fused_residual_gradient():
     (xr + (nr.float() @ proj)).backward(go)
     torch.testing.assert_close(x.grad, xr.grad, rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(w.grad, wr.grad, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("N,d,udt,p", [(37, 768, torch.bfloat16, 0.1), (8128, 768, torch.bfloat16, 0.1),
+                                       (5, 192, torch.float32, 0.0), (300, 1024, torch.float32, 0.1),
+                                       (9, 8, torch.bfloat16, 0.0)])
+def test_add_dropout_layer_norm_matches_unfused_pair(N, d, udt, p):
+    """fused LayerNorm(hidden + dropout(update)) == residual_dropout_add (same Philox mask) + torch layer_norm,
+    forward and backward, including the bf16 side output and its gradient."""
+    from phoneme_vqa_b200 import ops
+    g = torch.Generator().manual_seed(N + d)
+    h0 = torch.randn(N, d, generator=g).to(DEV)
+    u0 = (torch.randn(N, d, generator=g) * 2).to(DEV).to(udt)
+    w0 = (1 + 0.1 * torch.randn(d, generator=g)).to(DEV)
+    b0 = (0.1 * torch.randn(d, generator=g)).to(DEV)
+    gy = torch.randn(N, d, generator=g).to(DEV)
+    gy_lp = torch.randn(N, d, generator=g).to(DEV).bfloat16()
+    outs = []
+    for fused in (True, False):
+        h, u, w, b = (t.clone().requires_grad_(True) for t in (h0, u0, w0, b0))
+        ops.manual_seed(11)
+        if fused:
+            y, y_lp = ops.add_dropout_layer_norm(h, u, w, b, 1e-5, p, training=True, want_lp=True)
+            assert y_lp.dtype == torch.bfloat16
+        else:
+            z = ops.residual_dropout_add(h, u, p, training=True)
+            y = torch.nn.functional.layer_norm(z, (d,), w, b, 1e-5)
+            y_lp = y.bfloat16()
+        torch.autograd.backward([y, y_lp], [gy, gy_lp])
+        outs.append((y.detach(), y_lp.detach().float(), h.grad, u.grad.float(), w.grad, b.grad))
+    names = ("y", "y_lp", "d_hidden", "d_update", "d_gamma", "d_beta")
+    lp_u = udt == torch.bfloat16
+    tols = {"y": 2e-5, "y_lp": 2e-2, "d_hidden": 2e-4, "d_update": 2e-2 if lp_u else 2e-4, "d_gamma": 2e-3, "d_beta": 2e-3}
+    for n, a, r in zip(names, outs[0], outs[1]):
+        torch.testing.assert_close(a, r, rtol=tols[n], atol=tols[n] * max(1.0, float(r.abs().max()) if "gamma" in n or "beta" in n else 1.0),
+                                   msg=lambda m, n=n: f"{n}: {m}")
+
+
+def test_add_dropout_layer_norm_eval_and_single_consumer():
+    from phoneme_vqa_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    h = torch.randn(6, 10, 768, generator=g).to(DEV).requires_grad_(True)
+    u = torch.randn(6, 10, 768, generator=g).to(DEV).bfloat16().requires_grad_(True)
+    w = torch.ones(768, device=DEV, requires_grad=True)
+    b = torch.zeros(768, device=DEV, requires_grad=True)
+    y, y_lp = ops.add_dropout_layer_norm(h, u, w, b, 1e-5, 0.3, training=False, want_lp=False)
+    assert y_lp is None
+    ref = torch.nn.functional.layer_norm(h.detach() + u.detach().float(), (768,), w.detach(), b.detach(), 1e-5)
+    torch.testing.assert_close(y, ref, rtol=2e-5, atol=2e-5)
+    # only the bf16 copy is consumed downstream: the fp32 gradient arrives as None
+    y, y_lp = ops.add_dropout_layer_norm(h, u, w, b, 1e-5, 0.0, training=True, want_lp=True)
+    y_lp.float().pow(2).sum().backward()
+    hr = h.detach().clone().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(hr + u.detach().float(), (768,), w.detach(), b.detach(), 1e-5)
+    yr.bfloat16().float().pow(2).sum().backward()
+    torch.testing.assert_close(h.grad, hr.grad, rtol=2e-2, atol=2e-2)
+    with torch.no_grad():
+        y2, _ = ops.add_dropout_layer_norm(h, u, w, b, 1e-5, 0.0, training=False)
+    torch.testing.assert_close(y2, ref, rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("N,d,dt", [(8128, 2304, torch.bfloat16), (1, 8, torch.float32), (333, 768, torch.float32),
+                                    (20928, 3072, torch.bfloat16), (31, 2048, torch.bfloat16)])
+def test_col_sum(N, d, dt):
+    from phoneme_vqa_b200 import ops
+    g = torch.Generator().manual_seed(d)
+    x = torch.randn(N, d, generator=g).to(DEV).to(dt)
+    out = ops.col_sum(x)
+    ref = x.double().sum(0).float()
+    assert out.dtype == torch.float32
+    torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-3 * max(1.0, N ** 0.5 / 10))
