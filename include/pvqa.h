@@ -299,16 +299,34 @@ int pvqa_relu_dropout_bwd(const void* dy, const void* y, void* dx, int64_t n, in
  * from core/model/PhonemeLaTr.py:134-144.  hidden/y/z are fp32 (N, d); update is bf16 or fp32; y_lp (optional)
  * is the bf16 copy of y the next GEMM consumes; z (optional) is the pre-norm sum saved for the backward;
  * mean/rstd are (N).  The dropout mask is the one pvqa_residual_dropout_add draws for the same (seed, offset).
+ * With a bf16 hidden stream (and y == NULL) the same kernel is the `x = x + sublayer; y = layernorm(x)` step of
+ * the frozen ViT tower (HF ViTLayer.forward, called from core/model/PhonemeLaTr.py:220).
  * Backward: dy and/or dy_lp are the gradients of y / y_lp; d_hidden (fp32) is the residual-path gradient,
  * d_update = mask * d_hidden / keep in the update's dtype; dgamma/dbeta (d) are ACCUMULATED. */
-int pvqa_add_dropout_ln_fwd(const float* hidden, const void* update /* may be NULL: plain LayerNorm */, int upd_dtype,
-                            const float* gamma, const float* beta, float* z, float* y, void* y_lp, int lp_dtype,
+int pvqa_add_dropout_ln_fwd(const void* hidden, int hidden_dtype /* fp32, or bf16 with a bf16 update */,
+                            const void* update /* may be NULL: plain LayerNorm */, int upd_dtype, const float* gamma,
+                            const float* beta, void* z /* hidden dtype */, float* y, void* y_lp, int lp_dtype,
                             float* mean, float* rstd, int64_t N, int64_t d, float eps, float dropout_p, uint64_t seed,
                             uint64_t offset, void* stream);
 int pvqa_add_dropout_ln_bwd(const float* dy, const void* dy_lp, int lp_dtype, const float* z, const float* gamma,
                             const float* mean, const float* rstd, float* d_hidden, void* d_update /* may be NULL */,
                             int upd_dtype, float* dgamma, float* dbeta, int64_t N, int64_t d, float dropout_p,
                             uint64_t seed, uint64_t offset, void* stream);
+
+/* Pre-norm step between two sublayers of a T5 block, one launch:
+ *     hidden_out = hidden + dropout(update);   y = T5LayerNorm(hidden_out) * weight
+ * i.e. the tail of T5LayerSelfAttention/T5LayerFF.forward (`hidden_states + self.dropout(...)`) fused with the
+ * `self.layer_norm(hidden_states)` that opens the next sublayer (transformers modeling_t5.py:46-70 and the
+ * T5Layer* classes; reached from core/model/PhonemeLaTr.py:111-114).  hidden/hidden_out fp32, y bf16 or fp32.
+ * Backward: dy = gradient of y, d_residual (optional) = gradient reaching hidden_out past the norm;
+ * d_hidden = d_residual + d(norm); d_update = mask * d_hidden / keep; dweight (d) is ACCUMULATED. */
+int pvqa_add_dropout_rms_fwd(const float* hidden, const void* update, int upd_dtype, const float* weight,
+                             float* hidden_out, void* y, int y_dtype, float* rstd, int64_t N, int64_t d, float eps,
+                             float dropout_p, uint64_t seed, uint64_t offset, void* stream);
+int pvqa_add_dropout_rms_bwd(const void* dy, int y_dtype, const float* d_residual, const float* hidden_out,
+                             const float* weight, const float* rstd, float* d_hidden, void* d_update, int upd_dtype,
+                             float* dweight, int64_t N, int64_t d, float dropout_p, uint64_t seed, uint64_t offset,
+                             void* stream);
 
 /* out[c] (+)= sum_r x[r][c] in fp32: the bias gradient of every biased Linear on the decoder path
  * (autograd's `grad_output.sum(0)` for nn.Linear / nn.MultiheadAttention in_proj/out_proj biases).

@@ -207,13 +207,13 @@ relu_dropout_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __
 // mask uses the same flat element index (row * d + col) as residual_dropout_add, so the fused kernel is
 // bit-compatible with the unfused pair.  Outputs: z (pre-norm sum, saved for backward), y (fp32 residual
 // stream) and optionally y_lp (the low-precision copy the next GEMM reads).
-template <typename UT, typename LT, int NV>
+template <typename HT, typename UT, typename LT, int NV>
 __global__ void __launch_bounds__(kNormThreads)
-add_dropout_ln_fwd_kernel(const float* __restrict__ hidden, const UT* __restrict__ upd, const float* __restrict__ gamma,
-                          const float* __restrict__ beta, float* __restrict__ z, float* __restrict__ y,
+add_dropout_ln_fwd_kernel(const HT* __restrict__ hidden, const UT* __restrict__ upd, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, HT* __restrict__ z, float* __restrict__ y,
                           LT* __restrict__ y_lp, float* __restrict__ mean, float* __restrict__ rstd, int N, int d,
                           float eps, uint32_t thr16, float scale, uint64_t seed, uint64_t offset,
-                          const unsigned long long* rng_base) {
+                          const unsigned long long* rng_base, int rms) {
   if (thr16 && rng_base) offset += *rng_base;
   const int lane = threadIdx.x & 31;
   const float inv_d = 1.0f / (float)d;
@@ -225,7 +225,7 @@ add_dropout_ln_fwd_kernel(const float* __restrict__ hidden, const UT* __restrict
     for (int c = 0; c < NV; ++c) {
       const int col = (c * 32 + lane) * 8;
       if (col < d) {
-        v[c] = Vec8<float>::load_stream(hidden + base + col);
+        v[c] = Vec8<HT>::load_stream(hidden + base + col);
         if (upd) {
           const f8 u = Vec8<UT>::load_stream(upd + base + col);
           if (thr16) {
@@ -241,7 +241,7 @@ add_dropout_ln_fwd_kernel(const float* __restrict__ hidden, const UT* __restrict
         for (int j = 0; j < 8; ++j) s += v[c].v[j];
       }
     }
-    const float mu = warp_sum_n(s) * inv_d;
+    const float mu = rms ? 0.f : warp_sum_n(s) * inv_d;      // rms: T5LayerNorm (no mean, no bias)
     float ss = 0.f;
 #pragma unroll
     for (int c = 0; c < NV; ++c) {
@@ -259,11 +259,17 @@ add_dropout_ln_fwd_kernel(const float* __restrict__ hidden, const UT* __restrict
     for (int c = 0; c < NV; ++c) {
       const int col = (c * 32 + lane) * 8;
       if (col < d) {
-        if (z) Vec8<float>::store(z + base + col, v[c]);
-        const f8 g = Vec8<float>::load(gamma + col), bt = Vec8<float>::load(beta + col);
+        if (z) Vec8<HT>::store(z + base + col, v[c]);
+        const f8 g = Vec8<float>::load(gamma + col);
         f8 o;
+        if (beta) {
+          const f8 bt = Vec8<float>::load(beta + col);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o.v[j] = (v[c].v[j] - mu) * r * g.v[j] + bt.v[j];
+          for (int j = 0; j < 8; ++j) o.v[j] = (v[c].v[j] - mu) * r * g.v[j] + bt.v[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o.v[j] = g.v[j] * ((v[c].v[j] - mu) * r);
+        }
         if (y) Vec8<float>::store(y + base + col, o);
         if (y_lp) Vec8<LT>::store(y_lp + base + col, o);
       }
@@ -276,7 +282,8 @@ add_dropout_ln_fwd_kernel(const float* __restrict__ hidden, const UT* __restrict
 //   dgamma += sum_rows g * xhat;  dbeta += sum_rows g      (register partials -> smem -> one global atomic per CTA column)
 template <typename UT, typename LT, int NV>
 __global__ void __launch_bounds__(kNormThreads)
-add_dropout_ln_bwd_kernel(const float* __restrict__ dy, const LT* __restrict__ dy_lp, const float* __restrict__ z,
+add_dropout_ln_bwd_kernel(const float* __restrict__ dy, const LT* __restrict__ dy_lp, const float* __restrict__ d_res,
+                          const float* __restrict__ z,
                           const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
                           float* __restrict__ d_hidden, UT* __restrict__ d_upd, float* __restrict__ dgamma,
                           float* __restrict__ dbeta, int N, int d, uint32_t thr16, float scale, uint64_t seed,
@@ -295,7 +302,7 @@ add_dropout_ln_bwd_kernel(const float* __restrict__ dy, const LT* __restrict__ d
   }
   for (int row = blockIdx.x * (kNormThreads / 32) + (threadIdx.x >> 5); row < N; row += gridDim.x * (kNormThreads / 32)) {
     const long long base = (long long)row * d;
-    const float mu = mean[row], r = rstd[row];
+    const float mu = mean ? mean[row] : 0.f, r = rstd[row];
     f8 xh[NV], wg[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -328,7 +335,7 @@ add_dropout_ln_bwd_kernel(const float* __restrict__ dy, const LT* __restrict__ d
         }
       }
     }
-    const float c1 = warp_sum_n(s1) * inv_d, c2 = warp_sum_n(s2) * inv_d;
+    const float c1 = mean ? warp_sum_n(s1) * inv_d : 0.f, c2 = warp_sum_n(s2) * inv_d;
 #pragma unroll
     for (int c = 0; c < NV; ++c) {
       const int col = (c * 32 + lane) * 8;
@@ -336,6 +343,11 @@ add_dropout_ln_bwd_kernel(const float* __restrict__ dy, const LT* __restrict__ d
         f8 o;
 #pragma unroll
         for (int j = 0; j < 8; ++j) o.v[j] = r * (wg[c].v[j] - c1 - xh[c].v[j] * c2);
+        if (d_res) {         // pre-norm residual path: the gradient that bypasses the norm
+          const f8 e = Vec8<float>::load_stream(d_res + base + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o.v[j] += e.v[j];
+        }
         Vec8<float>::store(d_hidden + base + col, o);
         if (d_upd) {
           if (thr16) {
@@ -355,14 +367,14 @@ add_dropout_ln_bwd_kernel(const float* __restrict__ dy, const LT* __restrict__ d
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         atomicAdd(s_part + col + j, acc_g[c].v[j]);
-        atomicAdd(s_part + d + col + j, acc_b[c].v[j]);
+        if (dbeta) atomicAdd(s_part + d + col + j, acc_b[c].v[j]);
       }
     }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < d; c += kNormThreads) {
     atomicAdd(dgamma + c, s_part[c]);
-    atomicAdd(dbeta + c, s_part[d + c]);
+    if (dbeta) atomicAdd(dbeta + c, s_part[d + c]);
   }
 }
 
@@ -558,37 +570,37 @@ extern "C" int pvqa_relu_dropout_bwd(const void* dy, const void* y, void* dx, in
 }
 
 // ---- fused post-norm tail: y = LayerNorm(hidden + dropout(update)) ----
-template <typename UT, typename LT>
-static int launch_add_ln_fwd(int nv, int grid, cudaStream_t st, const float* hidden, const UT* upd, const float* gamma,
-                             const float* beta, float* z, float* y, LT* y_lp, float* mean, float* rstd, int N, int d,
-                             float eps, uint32_t thr, float sc, uint64_t seed, uint64_t offset) {
-#define PVQA_LN_FWD(NV) add_dropout_ln_fwd_kernel<UT, LT, NV><<<grid, kNormThreads, 0, st>>>( \
-    hidden, upd, gamma, beta, z, y, y_lp, mean, rstd, N, d, eps, thr, sc, seed, offset, g_rng_base)
+template <typename HT, typename UT, typename LT>
+static int launch_add_ln_fwd(int nv, int grid, cudaStream_t st, const HT* hidden, const UT* upd, const float* gamma,
+                             const float* beta, HT* z, float* y, LT* y_lp, float* mean, float* rstd, int N, int d,
+                             float eps, uint32_t thr, float sc, uint64_t seed, uint64_t offset, int rms = 0) {
+#define PVQA_LN_FWD(NV) add_dropout_ln_fwd_kernel<HT, UT, LT, NV><<<grid, kNormThreads, 0, st>>>( \
+    hidden, upd, gamma, beta, z, y, y_lp, mean, rstd, N, d, eps, thr, sc, seed, offset, g_rng_base, rms)
   switch (nv) { case 1: PVQA_LN_FWD(1); break; case 2: PVQA_LN_FWD(2); break; case 3: PVQA_LN_FWD(3); break; default: PVQA_LN_FWD(4); }
 #undef PVQA_LN_FWD
   return PVQA_OK;
 }
 template <typename UT, typename LT>
 static int launch_add_ln_bwd(int nv, int grid, size_t smem, cudaStream_t st, const float* dy, const LT* dy_lp,
-                             const float* z, const float* gamma, const float* mean, const float* rstd, float* d_hidden,
+                             const float* d_res, const float* z, const float* gamma, const float* mean, const float* rstd, float* d_hidden,
                              UT* d_upd, float* dgamma, float* dbeta, int N, int d, uint32_t thr, float sc, uint64_t seed,
                              uint64_t offset) {
 #define PVQA_LN_BWD(NV) add_dropout_ln_bwd_kernel<UT, LT, NV><<<grid, kNormThreads, smem, st>>>( \
-    dy, dy_lp, z, gamma, mean, rstd, d_hidden, d_upd, dgamma, dbeta, N, d, thr, sc, seed, offset, g_rng_base)
+    dy, dy_lp, d_res, z, gamma, mean, rstd, d_hidden, d_upd, dgamma, dbeta, N, d, thr, sc, seed, offset, g_rng_base)
   switch (nv) { case 1: PVQA_LN_BWD(1); break; case 2: PVQA_LN_BWD(2); break; case 3: PVQA_LN_BWD(3); break; default: PVQA_LN_BWD(4); }
 #undef PVQA_LN_BWD
   return PVQA_OK;
 }
 
-extern "C" int pvqa_add_dropout_ln_fwd(const float* hidden, const void* update, int upd_dtype, const float* gamma,
-                                       const float* beta, float* z, float* y, void* y_lp, int lp_dtype, float* mean,
+extern "C" int pvqa_add_dropout_ln_fwd(const void* hidden, int hidden_dtype, const void* update, int upd_dtype,
+                                       const float* gamma, const float* beta, void* z, float* y, void* y_lp, int lp_dtype, float* mean,
                                        float* rstd, int64_t N, int64_t d, float eps, float dropout_p, uint64_t seed,
                                        uint64_t offset, void* stream) {
   PVQA_REQUIRE(N >= 0 && d > 0, PVQA_ERR_SHAPE, "add_dropout_ln_fwd: bad dimension");
   PVQA_REQUIRE(d % 8 == 0 && d <= 1024, PVQA_ERR_SHAPE, "add_dropout_ln_fwd: d=%lld must be a multiple of 8 and <= 1024", (long long)d);
   PVQA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, PVQA_ERR_SHAPE, "add_dropout_ln_fwd: dropout_p must be in [0,1)");
   if (N == 0) return PVQA_OK;
-  PVQA_REQUIRE(hidden && gamma && beta && (y || y_lp), PVQA_ERR_NULL, "add_dropout_ln_fwd: NULL pointer");
+  PVQA_REQUIRE(hidden && gamma && beta && (y || y_lp), PVQA_ERR_NULL, "add_dropout_ln_fwd: NULL pointer");  // beta required: LayerNorm
   PVQA_REQUIRE(aligned16(hidden) && aligned16(update) && aligned16(gamma) && aligned16(beta) && aligned16(z) &&
                    aligned16(y) && aligned16(y_lp), PVQA_ERR_ALIGN, "add_dropout_ln_fwd: 16-byte alignment required");
   PVQA_REQUIRE(!y_lp || lp_dtype == PVQA_BF16, PVQA_ERR_DTYPE, "add_dropout_ln_fwd: the low-precision copy must be bf16");
@@ -598,12 +610,15 @@ extern "C" int pvqa_add_dropout_ln_fwd(const float* hidden, const void* update, 
   long long need = (N + warps - 1) / warps, cap = (long long)num_sms() * 8;
   const int grid = (int)(need < cap ? need : cap);
   cudaStream_t st = (cudaStream_t)stream;
-  if (upd_dtype == PVQA_BF16)
-    launch_add_ln_fwd<__nv_bfloat16, __nv_bfloat16>(nv, grid, st, hidden, (const __nv_bfloat16*)update, gamma, beta, z, y, (__nv_bfloat16*)y_lp, mean, rstd, (int)N, (int)d, eps, thr, sc, seed, offset);
-  else if (upd_dtype == PVQA_F32)
-    launch_add_ln_fwd<float, __nv_bfloat16>(nv, grid, st, hidden, (const float*)update, gamma, beta, z, y, (__nv_bfloat16*)y_lp, mean, rstd, (int)N, (int)d, eps, thr, sc, seed, offset);
+  typedef __nv_bfloat16 bf;
+  if (hidden_dtype == PVQA_F32 && upd_dtype == PVQA_BF16)
+    launch_add_ln_fwd<float, bf, bf>(nv, grid, st, (const float*)hidden, (const bf*)update, gamma, beta, (float*)z, y, (bf*)y_lp, mean, rstd, (int)N, (int)d, eps, thr, sc, seed, offset);
+  else if (hidden_dtype == PVQA_F32 && upd_dtype == PVQA_F32)
+    launch_add_ln_fwd<float, float, bf>(nv, grid, st, (const float*)hidden, (const float*)update, gamma, beta, (float*)z, y, (bf*)y_lp, mean, rstd, (int)N, (int)d, eps, thr, sc, seed, offset);
+  else if (hidden_dtype == PVQA_BF16 && upd_dtype == PVQA_BF16)     // frozen bf16 ViT tower (pre-norm, no dropout)
+    launch_add_ln_fwd<bf, bf, bf>(nv, grid, st, (const bf*)hidden, (const bf*)update, gamma, beta, (bf*)z, y, (bf*)y_lp, mean, rstd, (int)N, (int)d, eps, thr, sc, seed, offset);
   else
-    return fail(PVQA_ERR_DTYPE, "add_dropout_ln_fwd: bad update dtype");
+    return fail(PVQA_ERR_DTYPE, "add_dropout_ln_fwd: unsupported hidden/update dtype combination");
   count_launch();
   PVQA_CHECK_LAUNCH("add_dropout_ln_fwd");
   return PVQA_OK;
@@ -629,9 +644,9 @@ extern "C" int pvqa_add_dropout_ln_bwd(const float* dy, const void* dy_lp, int l
   const size_t smem = (size_t)2 * d * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
   if (upd_dtype == PVQA_BF16)
-    launch_add_ln_bwd<__nv_bfloat16, __nv_bfloat16>(nv, grid, smem, st, dy, (const __nv_bfloat16*)dy_lp, z, gamma, mean, rstd, d_hidden, (__nv_bfloat16*)d_update, dgamma, dbeta, (int)N, (int)d, thr, sc, seed, offset);
+    launch_add_ln_bwd<__nv_bfloat16, __nv_bfloat16>(nv, grid, smem, st, dy, (const __nv_bfloat16*)dy_lp, nullptr, z, gamma, mean, rstd, d_hidden, (__nv_bfloat16*)d_update, dgamma, dbeta, (int)N, (int)d, thr, sc, seed, offset);
   else if (upd_dtype == PVQA_F32)
-    launch_add_ln_bwd<float, __nv_bfloat16>(nv, grid, smem, st, dy, (const __nv_bfloat16*)dy_lp, z, gamma, mean, rstd, d_hidden, (float*)d_update, dgamma, dbeta, (int)N, (int)d, thr, sc, seed, offset);
+    launch_add_ln_bwd<float, __nv_bfloat16>(nv, grid, smem, st, dy, (const __nv_bfloat16*)dy_lp, nullptr, z, gamma, mean, rstd, d_hidden, (float*)d_update, dgamma, dbeta, (int)N, (int)d, thr, sc, seed, offset);
   else
     return fail(PVQA_ERR_DTYPE, "add_dropout_ln_bwd: bad update dtype");
   count_launch();
@@ -665,5 +680,70 @@ extern "C" int pvqa_col_sum(const void* x, float* out, int64_t N, int64_t d, int
     return fail(PVQA_ERR_DTYPE, "col_sum: bad dtype");
   count_launch();
   PVQA_CHECK_LAUNCH("col_sum");
+  return PVQA_OK;
+}
+
+// ---- fused pre-norm step of the T5 block: hidden_out = hidden + dropout(update); y = T5LayerNorm(hidden_out) ----
+extern "C" int pvqa_add_dropout_rms_fwd(const float* hidden, const void* update, int upd_dtype, const float* weight,
+                                        float* hidden_out, void* y, int y_dtype, float* rstd, int64_t N, int64_t d,
+                                        float eps, float dropout_p, uint64_t seed, uint64_t offset, void* stream) {
+  PVQA_REQUIRE(N >= 0 && d > 0, PVQA_ERR_SHAPE, "add_dropout_rms_fwd: bad dimension");
+  PVQA_REQUIRE(d % 8 == 0 && d <= 1024, PVQA_ERR_SHAPE, "add_dropout_rms_fwd: d=%lld must be a multiple of 8 and <= 1024", (long long)d);
+  PVQA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, PVQA_ERR_SHAPE, "add_dropout_rms_fwd: dropout_p must be in [0,1)");
+  if (N == 0) return PVQA_OK;
+  PVQA_REQUIRE(hidden && update && weight && hidden_out && y, PVQA_ERR_NULL, "add_dropout_rms_fwd: NULL pointer");
+  PVQA_REQUIRE(aligned16(hidden) && aligned16(update) && aligned16(weight) && aligned16(hidden_out) && aligned16(y),
+               PVQA_ERR_ALIGN, "add_dropout_rms_fwd: 16-byte alignment required");
+  PVQA_REQUIRE(y_dtype == PVQA_BF16 || y_dtype == PVQA_F32, PVQA_ERR_DTYPE, "add_dropout_rms_fwd: bad output dtype");
+  uint32_t thr; float sc;
+  drop_consts(dropout_p, thr, sc);
+  const int warps = kNormThreads / 32, nv = (int)((d + 255) / 256);
+  long long need = (N + warps - 1) / warps, cap = (long long)num_sms() * 8;
+  const int grid = (int)(need < cap ? need : cap);
+  cudaStream_t st = (cudaStream_t)stream;
+  typedef __nv_bfloat16 bf;
+  float* yf = y_dtype == PVQA_F32 ? (float*)y : nullptr;
+  bf* yl = y_dtype == PVQA_BF16 ? (bf*)y : nullptr;
+  if (upd_dtype == PVQA_BF16)
+    launch_add_ln_fwd<float, bf, bf>(nv, grid, st, hidden, (const bf*)update, weight, nullptr, hidden_out, yf, yl, nullptr, rstd, (int)N, (int)d, eps, thr, sc, seed, offset, 1);
+  else if (upd_dtype == PVQA_F32)
+    launch_add_ln_fwd<float, float, bf>(nv, grid, st, hidden, (const float*)update, weight, nullptr, hidden_out, yf, yl, nullptr, rstd, (int)N, (int)d, eps, thr, sc, seed, offset, 1);
+  else
+    return fail(PVQA_ERR_DTYPE, "add_dropout_rms_fwd: bad update dtype");
+  count_launch();
+  PVQA_CHECK_LAUNCH("add_dropout_rms_fwd");
+  return PVQA_OK;
+}
+
+extern "C" int pvqa_add_dropout_rms_bwd(const void* dy, int y_dtype, const float* d_residual, const float* hidden_out,
+                                        const float* weight, const float* rstd, float* d_hidden, void* d_update,
+                                        int upd_dtype, float* dweight, int64_t N, int64_t d, float dropout_p,
+                                        uint64_t seed, uint64_t offset, void* stream) {
+  PVQA_REQUIRE(N >= 0 && d > 0, PVQA_ERR_SHAPE, "add_dropout_rms_bwd: bad dimension");
+  PVQA_REQUIRE(d % 8 == 0 && d <= 1024, PVQA_ERR_SHAPE, "add_dropout_rms_bwd: d must be a multiple of 8 and <= 1024");
+  PVQA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, PVQA_ERR_SHAPE, "add_dropout_rms_bwd: dropout_p must be in [0,1)");
+  if (N == 0) return PVQA_OK;
+  PVQA_REQUIRE(dy && hidden_out && weight && rstd && d_hidden && d_update && dweight, PVQA_ERR_NULL, "add_dropout_rms_bwd: NULL pointer");
+  PVQA_REQUIRE(aligned16(dy) && aligned16(d_residual) && aligned16(hidden_out) && aligned16(weight) && aligned16(d_hidden) &&
+                   aligned16(d_update), PVQA_ERR_ALIGN, "add_dropout_rms_bwd: 16-byte alignment required");
+  PVQA_REQUIRE(y_dtype == PVQA_BF16 || y_dtype == PVQA_F32, PVQA_ERR_DTYPE, "add_dropout_rms_bwd: bad gradient dtype");
+  uint32_t thr; float sc;
+  drop_consts(dropout_p, thr, sc);
+  const int warps = kNormThreads / 32, nv = (int)((d + 255) / 256);
+  long long need = (N + warps - 1) / warps, cap = (long long)num_sms() * 2;
+  const int grid = (int)(need < cap ? need : cap);
+  const size_t smem = (size_t)2 * d * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  typedef __nv_bfloat16 bf;
+  const float* gf = y_dtype == PVQA_F32 ? (const float*)dy : nullptr;
+  const bf* gl = y_dtype == PVQA_BF16 ? (const bf*)dy : nullptr;
+  if (upd_dtype == PVQA_BF16)
+    launch_add_ln_bwd<bf, bf>(nv, grid, smem, st, gf, gl, d_residual, hidden_out, weight, nullptr, rstd, d_hidden, (bf*)d_update, dweight, nullptr, (int)N, (int)d, thr, sc, seed, offset);
+  else if (upd_dtype == PVQA_F32)
+    launch_add_ln_bwd<float, bf>(nv, grid, smem, st, gf, gl, d_residual, hidden_out, weight, nullptr, rstd, d_hidden, (float*)d_update, dweight, nullptr, (int)N, (int)d, thr, sc, seed, offset);
+  else
+    return fail(PVQA_ERR_DTYPE, "add_dropout_rms_bwd: bad update dtype");
+  count_launch();
+  PVQA_CHECK_LAUNCH("add_dropout_rms_bwd");
   return PVQA_OK;
 }

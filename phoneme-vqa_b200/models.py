@@ -9,10 +9,12 @@ Selecting them from the reference's YAML is ``MODEL_CLASS: "PhonemeLaTr"`` after
 from __future__ import annotations
 
 import contextlib
+import math
 import os
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from . import ops
 from .modules import (SHADOWS, BaseDecoder, RelativePositionBias1D, RelativePositionBiasAggregated,
@@ -81,6 +83,66 @@ def _load_pretrained_t5_encoder(encoder: T5EncoderModel, config):
     encoder.load_state_dict(sd, strict=True)
 
 
+class _FrozenVitLP:
+    """bf16 forward of the frozen ViT tower (HF ViTModel semantics: pre-norm blocks, exact GELU, final layernorm;
+    transformers models/vit/modeling_vit.py, run by the reference at core/model/PhonemeLaTr.py:220).  Weights are
+    bf16 copies of the fp32 `vit.*` parameters (q/k/v fused into one projection), LayerNorm parameters stay fp32.
+    Per block: 4 GEMMs, the tcgen05 attention kernel on the packed (B,S,3,H,D) projection (no transposes or
+    copies), and two fused `x += sublayer; y = LayerNorm(x)` launches."""
+
+    def __init__(self, vit):
+        import copy
+        cfg = vit.config
+        self.eps = float(cfg.layer_norm_eps)
+        self.heads = int(cfg.num_attention_heads)
+        self.lean = (cfg.hidden_size // self.heads == 64 and cfg.hidden_size % 8 == 0 and cfg.hidden_size <= 1024
+                     and cfg.hidden_act == "gelu")
+        bf = torch.bfloat16
+        if not self.lean:                        # unusual geometry: the HF modules in bf16
+            self.full = copy.deepcopy(vit).to(bf).eval()
+            for p in self.full.parameters():
+                p.requires_grad_(False)
+            return
+        self.embeddings = copy.deepcopy(vit.embeddings).to(bf).eval()
+        for p in self.embeddings.parameters():
+            p.requires_grad_(False)
+        self.layers = []
+        for blk in vit.encoder.layer:
+            att = blk.attention.attention
+            self.layers.append(dict(
+                ln1=(blk.layernorm_before.weight.detach().float(), blk.layernorm_before.bias.detach().float()),
+                ln2=(blk.layernorm_after.weight.detach().float(), blk.layernorm_after.bias.detach().float()),
+                wqkv=torch.cat([att.query.weight, att.key.weight, att.value.weight]).detach().to(bf),
+                bqkv=torch.cat([att.query.bias, att.key.bias, att.value.bias]).detach().to(bf),
+                wo=blk.attention.output.dense.weight.detach().to(bf), bo=blk.attention.output.dense.bias.detach().to(bf),
+                w1=blk.intermediate.dense.weight.detach().to(bf), b1=blk.intermediate.dense.bias.detach().to(bf),
+                w2=blk.output.dense.weight.detach().to(bf), b2=blk.output.dense.bias.detach().to(bf)))
+        self.final_ln = (vit.layernorm.weight.detach().float(), vit.layernorm.bias.detach().float())
+
+    @torch.no_grad()
+    def __call__(self, pixel_values):
+        bf = torch.bfloat16
+        if not self.lean:
+            emb = self.full.embeddings(pixel_values.to(bf))
+            return self.full.layernorm(self.full.encoder(emb).last_hidden_state)
+        x = self.embeddings(pixel_values.to(bf)).contiguous()
+        B, S, d = x.shape
+        H, D = self.heads, d // self.heads
+        scale = 1.0 / math.sqrt(D)
+        n = len(self.layers)
+        _, y = ops.add_layer_norm_lp(x, None, *self.layers[0]["ln1"], self.eps) if n else (x, x)
+        for i, L in enumerate(self.layers):
+            qkv = F.linear(y, L["wqkv"], L["bqkv"]).view(B, S, 3, H, D)
+            a, _ = ops.attention_fwd_raw(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], scale)
+            x, y = ops.add_layer_norm_lp(x, F.linear(a.view(B, S, d), L["wo"], L["bo"]), *L["ln2"], self.eps)
+            m = F.linear(F.gelu(F.linear(y, L["w1"], L["b1"])), L["w2"], L["b2"])
+            nxt = self.layers[i + 1]["ln1"] if i + 1 < n else self.final_ln
+            x, y = ops.add_layer_norm_lp(x, m, *nxt, self.eps)
+        if n == 0:
+            _, y = ops.add_layer_norm_lp(x, None, *self.final_ln, self.eps)
+        return y
+
+
 class _VisionMixin:
     """frozen-ViT handling shared by the LaTr / PreSTU families."""
 
@@ -94,22 +156,14 @@ class _VisionMixin:
         sig = tuple((p.data_ptr(), p._version) for p in self.vit.parameters())
         cache = self.__dict__.get("_vit_lp")
         if cache is None or cache[0] != sig:
-            import copy
-            lp = copy.deepcopy(self.vit).to(torch.bfloat16)
-            lp.eval()
-            for p in lp.parameters():
-                p.requires_grad_(False)
-            cache = (sig, lp)
+            cache = (sig, _FrozenVitLP(self.vit))
             self.__dict__["_vit_lp"] = cache
         return cache[1]
 
     def _vit_tokens(self, pixel_values):
         # ViTModel.forward minus the pooler (never used by the reference: PhonemeLaTr.py:220)
-        if self._vit_frozen() and self.compute_dtype == torch.bfloat16:
-            vit = self._vit_shadow()
-            with torch.no_grad():
-                emb = vit.embeddings(pixel_values.to(torch.bfloat16))
-                return vit.layernorm(vit.encoder(emb).last_hidden_state)
+        if self._vit_frozen() and self.compute_dtype == torch.bfloat16 and pixel_values.is_cuda:
+            return self._vit_shadow()(pixel_values)
         ctx = torch.no_grad() if self._vit_frozen() else contextlib.nullcontext()
         amp = (torch.autocast("cuda", dtype=torch.bfloat16) if self.compute_dtype == torch.bfloat16
                else contextlib.nullcontext())

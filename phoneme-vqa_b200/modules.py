@@ -320,9 +320,13 @@ class T5LayerSelfAttention(nn.Module):
         self.layer_norm = T5LayerNorm(config.d_model, eps=config.layer_norm_epsilon)
         self.dropout = nn.Dropout(config.dropout_rate)
 
+    def core(self, normed, rel_bias, key_add, causal=False, scp=None):
+        """the sublayer between its norm and its residual add (T5Stack fuses those two with the neighbours)"""
+        return self.SelfAttention(normed, rel_bias, key_add, causal=causal, scp=scp)
+
     def forward(self, hidden, rel_bias, key_add, compute_dtype, causal=False, scp=None):
         normed, hidden = self.layer_norm.with_residual(hidden, out_dtype=compute_dtype)
-        attn = self.SelfAttention(normed, rel_bias, key_add, causal=causal, scp=scp)
+        attn = self.core(normed, rel_bias, key_add, causal=causal, scp=scp)
         return ops.residual_dropout_add(hidden, attn, self.dropout.p, self.training)
 
 
@@ -333,9 +337,12 @@ class T5LayerCrossAttention(nn.Module):
         self.layer_norm = T5LayerNorm(config.d_model, eps=config.layer_norm_epsilon)
         self.dropout = nn.Dropout(config.dropout_rate)
 
+    def core(self, normed, memory, key_add):
+        return self.EncDecAttention(normed, None, key_add, kv=memory)
+
     def forward(self, hidden, memory, key_add, compute_dtype):
         normed, hidden = self.layer_norm.with_residual(hidden, out_dtype=compute_dtype)
-        attn = self.EncDecAttention(normed, None, key_add, kv=memory)
+        attn = self.core(normed, memory, key_add)
         return ops.residual_dropout_add(hidden, attn, self.dropout.p, self.training)
 
 
@@ -382,9 +389,12 @@ class T5LayerFF(nn.Module):
         self.layer_norm = T5LayerNorm(config.d_model, eps=config.layer_norm_epsilon)
         self.dropout = nn.Dropout(config.dropout_rate)
 
+    def core(self, normed):
+        return self.DenseReluDense(normed)
+
     def forward(self, hidden, compute_dtype):
         normed, hidden = self.layer_norm.with_residual(hidden, out_dtype=compute_dtype)
-        ff = self.DenseReluDense(normed)
+        ff = self.core(normed)
         return ops.residual_dropout_add(hidden, ff, self.dropout.p, self.training)
 
 
@@ -464,11 +474,31 @@ class T5Stack(nn.Module):
             key_add = self.key_add_from_mask(attention_mask)
         mem = None if memory is None else memory.to(compute_dtype)
         mem_key_add = self.key_add_from_mask(memory_mask) if memory is not None else None
+        d = hidden.shape[-1]
+        if len(self.block) == 0 or d % 8 != 0 or d > 1024:
+            for blk in self.block:
+                hidden = blk(hidden, rel_bias, key_add, compute_dtype, memory=mem, memory_key_add=mem_key_add,
+                             causal=self.is_decoder, scp=scp)
+            hidden = self.final_layer_norm(hidden, out_dtype=torch.float32)
+            return F.dropout(hidden, self.dropout.p, self.training)
+        # Pre-norm chain: every `hidden + dropout(sublayer)` is fused with the T5LayerNorm that opens the NEXT
+        # sublayer (the last one with final_layer_norm): one launch instead of two per sublayer, forward and backward.
+        subs = []
         for blk in self.block:
-            hidden = blk(hidden, rel_bias, key_add, compute_dtype, memory=mem, memory_key_add=mem_key_add,
-                         causal=self.is_decoder, scp=scp)
-        hidden = self.final_layer_norm(hidden, out_dtype=torch.float32)
-        return F.dropout(hidden, self.dropout.p, self.training)
+            sa = blk.layer[0]
+            subs.append((sa, lambda n, sa=sa: sa.core(n, rel_bias, key_add, causal=self.is_decoder, scp=scp)))
+            if blk.is_decoder:
+                ca = blk.layer[1]
+                subs.append((ca, lambda n, ca=ca: ca.core(n, mem, mem_key_add)))
+            subs.append((blk.layer[-1], blk.layer[-1].core))
+        normed, hidden = subs[0][0].layer_norm.with_residual(hidden, out_dtype=compute_dtype)
+        for i, (sub, core) in enumerate(subs):
+            last = i + 1 == len(subs)
+            nrm = self.final_layer_norm if last else subs[i + 1][0].layer_norm
+            hidden, normed = ops.add_dropout_rms_norm(hidden, core(normed), nrm.weight, nrm.variance_epsilon,
+                                                      sub.dropout.p, self.training,
+                                                      torch.float32 if last else compute_dtype)
+        return F.dropout(normed, self.dropout.p, self.training)
 
 
 class T5ForConditionalGeneration(nn.Module):

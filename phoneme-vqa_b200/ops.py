@@ -385,7 +385,7 @@ class _AddDropoutLN(torch.autograd.Function):
         rstd = torch.empty(N, dtype=torch.float32, device=dev) if need_grad else None
         seed, off = _Rng.next(hidden.numel()) if p > 0 else (0, 0)
         with torch.cuda.device(dev), _prof("add_dropout_ln_fwd"):
-            check(lib.pvqa_add_dropout_ln_fwd(_p(hidden), _p(update), _dt(update.dtype), _p(gamma), _p(beta), _p(z), _p(y),
+            check(lib.pvqa_add_dropout_ln_fwd(_p(hidden), PVQA_F32, _p(update), _dt(update.dtype), _p(gamma), _p(beta), _p(z), _p(y),
                                               _p(y_lp), _lib.PVQA_BF16, _p(mean), _p(rstd), N, d, float(eps), float(p),
                                               seed, off, _stream()), "pvqa_add_dropout_ln_fwd")
         ctx.save_for_backward(z, gamma, mean, rstd)
@@ -422,6 +422,92 @@ def add_dropout_layer_norm(hidden, update, weight, bias, eps, p, training, want_
     if hidden.dtype != torch.float32 or d % 8 != 0 or d > 1024 or hidden.shape != update.shape:
         raise TypeError("add_dropout_layer_norm expects an fp32 residual stream with d % 8 == 0 and d <= 1024")
     return _AddDropoutLN.apply(hidden, update, weight, bias, float(eps), p, bool(want_lp))
+
+
+class _AddDropoutRms(torch.autograd.Function):
+    """(hidden_out, y) = (hidden + dropout(update), T5LayerNorm(hidden_out)): the residual add that closes one
+    T5 sublayer fused with the norm that opens the next (include/pvqa.h: pvqa_add_dropout_rms_*)."""
+
+    @staticmethod
+    def forward(ctx, hidden, update, weight, eps, p, out_dtype):
+        lib = _lib.load()
+        _need_cuda(hidden, update, weight)
+        hidden = hidden.contiguous()
+        update = update.contiguous()
+        d = hidden.shape[-1]
+        N = hidden.numel() // d
+        dev = hidden.device
+        w = weight.to(torch.float32).contiguous()
+        hidden_out = torch.empty_like(hidden)
+        y = torch.empty(hidden.shape, dtype=out_dtype, device=dev)
+        rstd = torch.empty(N, dtype=torch.float32, device=dev)
+        seed, off = _Rng.next(hidden.numel()) if p > 0 else (0, 0)
+        with torch.cuda.device(dev), _prof("add_dropout_rms_fwd"):
+            check(lib.pvqa_add_dropout_rms_fwd(_p(hidden), _p(update), _dt(update.dtype), _p(w), _p(hidden_out), _p(y),
+                                               _dt(out_dtype), _p(rstd), N, d, float(eps), float(p), seed, off, _stream()),
+                  "pvqa_add_dropout_rms_fwd")
+        ctx.save_for_backward(hidden_out, w, rstd)
+        ctx.meta = (float(p), seed, off, update.dtype, update.shape, N, d, weight.dtype)
+        ctx.set_materialize_grads(False)
+        return hidden_out, y
+
+    @staticmethod
+    def backward(ctx, d_res, dy):
+        lib = _lib.load()
+        hidden_out, w, rstd = ctx.saved_tensors
+        p, seed, off, udt, ushape, N, d, w_dtype = ctx.meta
+        dev = hidden_out.device
+        if dy is None:           # the normed output was not used: plain residual add backward
+            if d_res is None:
+                return None, None, None, None, None, None
+            d_res = d_res.contiguous()
+            d_upd = torch.empty(ushape, dtype=udt, device=dev)
+            with torch.cuda.device(dev), _prof("residual_dropout_bwd"):
+                check(lib.pvqa_residual_dropout_bwd(_p(d_res), _p(d_upd), d_res.numel(), _dt(udt), p, seed, off, _stream()),
+                      "pvqa_residual_dropout_bwd")
+            return d_res, d_upd, None, None, None, None
+        dy = dy.contiguous()
+        d_res = d_res.to(torch.float32).contiguous() if d_res is not None else None
+        d_hidden = torch.empty_like(hidden_out)
+        d_upd = torch.empty(ushape, dtype=udt, device=dev)
+        dw = torch.zeros(d, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev), _prof("add_dropout_rms_bwd"):
+            check(lib.pvqa_add_dropout_rms_bwd(_p(dy), _dt(dy.dtype), _p(d_res), _p(hidden_out), _p(w), _p(rstd), _p(d_hidden),
+                                               _p(d_upd), _dt(udt), _p(dw), N, d, p, seed, off, _stream()),
+                  "pvqa_add_dropout_rms_bwd")
+        return d_hidden, d_upd, dw.to(w_dtype), None, None, None
+
+
+def add_dropout_rms_norm(hidden, update, weight, eps, p, training, out_dtype):
+    """-> (hidden + dropout(update), T5LayerNorm of that sum in out_dtype); fp32 residual stream."""
+    p = float(p) if training else 0.0
+    d = hidden.shape[-1]
+    if hidden.dtype != torch.float32 or d % 8 != 0 or d > 1024 or hidden.shape != update.shape:
+        raise TypeError("add_dropout_rms_norm expects an fp32 residual stream with d % 8 == 0 and d <= 1024")
+    return _AddDropoutRms.apply(hidden, update, weight, float(eps), p, out_dtype)
+
+
+@torch.no_grad()
+def add_layer_norm_lp(hidden, update, weight, bias, eps):
+    """Inference-only bf16 stream: x = hidden + update (or hidden itself when update is None), y = LayerNorm(x);
+    returns (x, y), both bf16.  The pre-norm step of the frozen ViT tower."""
+    lib = _lib.load()
+    _need_cuda(hidden, update, weight, bias)
+    d = hidden.shape[-1]
+    if hidden.dtype != torch.bfloat16 or d % 8 != 0 or d > 1024 or (update is not None and update.dtype != torch.bfloat16):
+        raise TypeError("add_layer_norm_lp expects bf16 operands with d % 8 == 0 and d <= 1024")
+    hidden = hidden.contiguous()
+    N = hidden.numel() // d
+    y = torch.empty_like(hidden)
+    x = hidden
+    if update is not None:
+        update = update.contiguous()
+        x = torch.empty_like(hidden)
+    with torch.cuda.device(hidden.device), _prof("add_ln_lp"):
+        check(lib.pvqa_add_dropout_ln_fwd(_p(hidden), PVQA_BF16, _p(update), PVQA_BF16, _p(weight), _p(bias),
+                                          _p(x) if update is not None else None, None, _p(y), PVQA_BF16, None, None, N, d,
+                                          float(eps), 0.0, 0, 0, _stream()), "pvqa_add_dropout_ln_fwd")
+    return x, y
 
 
 def col_sum(x2d, out=None):

@@ -174,3 +174,45 @@ def test_col_sum(N, d, dt):
     ref = x.double().sum(0).float()
     assert out.dtype == torch.float32
     torch.testing.assert_close(out, ref, rtol=1e-4, atol=1e-3 * max(1.0, N ** 0.5 / 10))
+
+
+@pytest.mark.parametrize("N,d,udt,ydt,p", [(37, 768, torch.bfloat16, torch.bfloat16, 0.1),
+                                           (2048, 768, torch.bfloat16, torch.float32, 0.1),
+                                           (5, 64, torch.float32, torch.float32, 0.0),
+                                           (100, 1024, torch.float32, torch.float32, 0.2)])
+def test_add_dropout_rms_norm_matches_unfused_pair(N, d, udt, ydt, p):
+    """fused (hidden + dropout(update), T5LayerNorm(sum)) == residual_dropout_add + rms_norm_residual with the
+    same Philox mask; both outputs carry gradients (residual path and norm path)."""
+    from phoneme_vqa_b200 import ops
+    g = torch.Generator().manual_seed(N * d)
+    h0 = torch.randn(N, d, generator=g).to(DEV)
+    u0 = (torch.randn(N, d, generator=g) * 2).to(DEV).to(udt)
+    w0 = (1 + 0.1 * torch.randn(d, generator=g)).to(DEV)
+    g_res = torch.randn(N, d, generator=g).to(DEV)
+    g_y = torch.randn(N, d, generator=g).to(DEV).to(ydt)
+    outs = []
+    for fused in (True, False):
+        h, u, w = (t.clone().requires_grad_(True) for t in (h0, u0, w0))
+        ops.manual_seed(21)
+        if fused:
+            ho, y = ops.add_dropout_rms_norm(h, u, w, 1e-6, p, True, ydt)
+        else:
+            ho = ops.residual_dropout_add(h, u, p, training=True)
+            y, ho = ops.rms_norm_residual(ho, w, 1e-6, ydt)
+        assert y.dtype == ydt and ho.dtype == torch.float32
+        torch.autograd.backward([ho, y], [g_res, g_y])
+        outs.append((ho.detach(), y.detach().float(), h.grad, u.grad.float(), w.grad))
+    lp = udt == torch.bfloat16
+    tols = {"hidden_out": 1e-6, "y": 2e-2 if ydt == torch.bfloat16 else 2e-5, "d_hidden": 2e-4,
+            "d_update": 2e-2 if lp else 2e-4, "d_weight": 2e-3}
+    for (n, tol), a, r in zip(tols.items(), outs[0], outs[1]):
+        scale = max(1.0, float(r.abs().max())) if n == "d_weight" else 1.0
+        torch.testing.assert_close(a, r, rtol=tol, atol=tol * scale, msg=lambda m, n=n: f"{n}: {m}")
+    # residual-only consumer (normed output unused) still back-propagates through the dropout mask
+    h, u, w = (t.clone().requires_grad_(True) for t in (h0, u0, w0))
+    ops.manual_seed(21)
+    ho, _ = ops.add_dropout_rms_norm(h, u, w, 1e-6, p, True, ydt)
+    ho.backward(g_res)
+    torch.testing.assert_close(h.grad, g_res)
+    kept = (outs[0][0] - h0) != 0
+    torch.testing.assert_close(u.grad.float()[kept], (g_res / (1 - p))[kept], rtol=2e-2, atol=2e-2)

@@ -255,3 +255,32 @@ def test_greedy_decoding_with_kv_cache_matches_uncached_reference_loop():
         assert torch.equal(cached, plain), dtype
         if dtype == torch.float32:
             assert np.array_equal(cached[:, :7].cpu().numpy(), g["greedy_ids"])       # the reference's own ids
+
+
+def test_frozen_vit_bf16_forward_matches_hf_tower():
+    """the lean bf16 ViT forward (fused qkv, tcgen05 attention, fused add+LayerNorm) against the HF ViTModel
+    it restates: fp32 HF output as the truth, HF-in-bf16 as the yardstick for the allowed error."""
+    from transformers import ViTConfig, ViTModel
+    from phoneme_vqa_b200.models import _FrozenVitLP
+    torch.manual_seed(0)
+    cfg = ViTConfig(hidden_size=256, num_hidden_layers=3, num_attention_heads=4, intermediate_size=512)
+    cfg._attn_implementation = "sdpa"
+    vit = ViTModel(cfg, add_pooling_layer=False).to(DEV).eval()
+    px = torch.randn(3, 3, 224, 224, device=DEV)
+    with torch.no_grad():
+        ref = vit.layernorm(vit.encoder(vit.embeddings(px)).last_hidden_state)
+        import copy
+        hf16 = copy.deepcopy(vit).bfloat16()
+        yard = hf16.layernorm(hf16.encoder(hf16.embeddings(px.bfloat16())).last_hidden_state).float()
+    lean = _FrozenVitLP(vit)
+    assert lean.lean
+    out = lean(px)
+    assert out.dtype == torch.bfloat16 and out.shape == ref.shape
+    err = (out.float() - ref).abs().max().item()
+    yard_err = (yard - ref).abs().max().item()
+    assert err <= 1.5 * yard_err + 1e-2, (err, yard_err)
+    # unusual head size: falls back to the HF modules in bf16, same interface
+    cfg2 = ViTConfig(hidden_size=96, num_hidden_layers=1, num_attention_heads=3, intermediate_size=128)
+    vit2 = ViTModel(cfg2, add_pooling_layer=False).to(DEV).eval()
+    other = _FrozenVitLP(vit2)
+    assert not other.lean and other(px).shape == (3, 197, 96)

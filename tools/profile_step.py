@@ -36,4 +36,18 @@ torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     step()
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
+from collections import defaultdict  # noqa: E402
+from torch.autograd import DeviceType  # noqa: E402
+
+agg = defaultdict(lambda: [0, 0.0])
+for e in prof.events():
+    if e.device_type == DeviceType.CUDA:
+        a = agg[e.name]
+        a[0] += 1
+        a[1] += e.device_time_total if hasattr(e, "device_time_total") else e.cuda_time_total
+tot = sum(v[1] for v in agg.values())
+mine = sum(v[1] for k, v in agg.items() if "pvqa::" in k)
+print(f"GPU busy {tot / 1e3:.3f} ms over {sum(v[0] for v in agg.values())} launches; libpvqa kernels {mine / 1e3:.3f} ms "
+      f"({100 * mine / tot:.1f}%)")
+for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:70]:
+    print(f"{t:10.1f} us {100 * t / tot:5.1f}%  n={n:3d}  {name[:110]}")
