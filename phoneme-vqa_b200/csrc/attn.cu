@@ -391,21 +391,30 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // backward
 //   prep kernel: delta[b,h,i] = rowsum(dO * O)
 //   main kernel: one CTA = one (batch, head, 128-key tile), 512 threads (row = TMEM lane, a quarter of the
-//   columns per thread); loop over 128-query tiles with double-buffered TMA loads of Q / dO:
+//   columns per thread); loop over 128-query tiles with a 3-stage TMA ring of Q / dO:
 //     S = Q K^T, dP = dO V^T                  (TMEM [0,128) and [128,256))
 //     P = exp2(s - lse), dS = P * (dP - delta) * scale   -> bf16 [query][key] tiles in smem
 //     dV += P^T dO, dK += dS^T Q               (A operands read MN-major from those tiles; TMEM [256,320), [320,384))
-//     dQ_m = dS K -> TMEM (aliasing S) -> fp32 RED into the dq accumulator (other key tiles add to it)
-//     d_rel[j-i] += dS: diagonal sums of the bf16 dS tile, half a diagonal per thread, overlapped with the MMAs
+//     dQ_m = dS K -> TMEM [384,448) / [448,512) by tile parity -> fp32 RED into the dq accumulator
+//   Software pipeline: after the P/dS tile of query tile m is in smem, one thread issues the three accumulating
+//   GEMMs of tile m AND S/dP of tile m+1 behind them, one commit for the lot; while the tensor pipe works the
+//   512 threads drain dQ of tile m-1 (TMEM -> RED.v4), so the reduction traffic and the MMAs overlap and the
+//   next tile's scores are ready when the threads come back.
+//     d_rel[j-i] += dS: per-warp diagonal sums by lane shuffles, accumulated in smem, one global atomic per offset
 // =================================================================================
-constexpr int kBwdThreads2 = 512;
-constexpr uint32_t kBwdTmemCols = 512;   // S/dQ [0,128) | dP [128,256) | dV [256,320) | dK [320,384)
+constexpr int kBwdComputeWarps = 16;
+constexpr int kBwdComputeThreads = kBwdComputeWarps * 32;
+constexpr int kBwdThreads2 = kBwdComputeThreads + 32;     // + the issuer warp
+constexpr uint32_t kBwdTmemCols = 512;   // S [0,128) | dP [128,256) | dV [256,320) | dK [320,384) | dQ [384,448), [448,512)
+constexpr int kBwdStages = 2;            // Q / dO ring
+constexpr int kBwdStageBytes = 2 * kBM * kD * 2;
 constexpr int kBOffK = 0;
 constexpr int kBOffV = kBOffK + kBN * kD * 2;             // 16 KB
 constexpr int kBOffQ = kBOffV + kBN * kD * 2;             // 32 KB: 2 stages x (Q 16 KB, dO 16 KB)
-constexpr int kBOffP = kBOffQ + 2 * 2 * kBM * kD * 2;     // 96 KB
+constexpr int kBOffP = kBOffQ + kBwdStages * kBwdStageBytes;   // 96 KB
 constexpr int kBOffdS = kBOffP + kBM * kBN * 2;           // 128 KB
-constexpr int kBOffBar = kBOffdS + kBM * kBN * 2;         // 160 KB
+constexpr int kBOffStg = kBOffdS + kBM * kBN * 2;         // 160 KB: fp32 dQ staging, two [128][32] SW128 halves
+constexpr int kBOffBar = kBOffStg + kBM * kD * 4;         // 192 KB
 constexpr int kBOffFloats = kBOffBar + 64;
 
 struct AttnBwdParams {
@@ -463,16 +472,17 @@ template <bool HAS_REL, bool DROP>
 __global__ void __launch_bounds__(kBwdThreads2, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
-                const AttnBwdParams p) {
+                const __grid_constant__ CUtensorMap tmdQ, const AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for SWIZZLE_128B, computed as an OFFSET into the __shared__ array so that the compiler
   // keeps the shared address space (32-bit LDS/STS instead of generic 64-bit LD/ST for every smem access)
   uint8_t* smem = smem_raw + ((1024u - (tc05::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bar_kv = reinterpret_cast<uint64_t*>(smem + kBOffBar);
-  uint64_t* bar_ld = bar_kv + 1;          // [2]
-  uint64_t* bar_s = bar_kv + 3;
-  uint64_t* bar_dq = bar_kv + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 5);
+  uint64_t* bar_ld = bar_kv + 1;          // [kBwdStages] Q/dO ring
+  uint64_t* bar_s = bar_kv + 3;           // S/dP of a query tile are in TMEM
+  uint64_t* bar_g = bar_kv + 4;           // the three accumulating GEMMs of a query tile are done
+  uint64_t* bar_stg = bar_kv + 5;         // the dQ staging tile has been read by its reduce
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_kv + 6);
   const int n_rel = p.Sq + p.Sk - 1;
   const int n_win = p.Sq + kBN - 1;                              // rel offsets this key tile can see
   float* s_kadd = reinterpret_cast<float*>(smem + kBOffFloats);  // [kBN], -inf beyond Sk
@@ -483,36 +493,54 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const bool has_scp = HAS_REL && p.scp_bucket != nullptr;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool is_issuer = warp == kBwdComputeWarps;       // warp 16: TMA, tcgen05.mma and the dQ reduce, nothing else
   const int rowl = (warp & 3) * 32 + lane;     // row inside the 128-row tile == TMEM lane
-  const int qd = warp >> 2;                    // which quarter of the columns this thread owns
+  const int qd = warp >> 2;                    // which quarter of the columns this thread owns (compute warps)
   const int j0 = blockIdx.x * kBN;
   const int h = blockIdx.y, b = blockIdx.z;
   PVQA_TRACE(0);
 
-  if (tid == 0) {
-    tc05::prefetch_tmap(&tmQ); tc05::prefetch_tmap(&tmK); tc05::prefetch_tmap(&tmV); tc05::prefetch_tmap(&tmdO);
-    tc05::mbar_init(bar_kv, 1); tc05::mbar_init(bar_ld, 1); tc05::mbar_init(bar_ld + 1, 1);
-    tc05::mbar_init(bar_s, 1); tc05::mbar_init(bar_dq, 1);
-    tc05::fence_barrier_init();
-  }
-  if (warp == 0) {
+  const int m_tiles = (p.Sq + kBM - 1) / kBM;
+  const int m_first = p.causal ? (j0 / kBM) : 0;      // query tiles entirely above the diagonal see nothing
+  const int n_it = m_tiles > m_first ? m_tiles - m_first : 0;
+  if (is_issuer) {
+    if (lane == 0) {
+      tc05::prefetch_tmap(&tmQ); tc05::prefetch_tmap(&tmK); tc05::prefetch_tmap(&tmV); tc05::prefetch_tmap(&tmdO);
+      tc05::prefetch_tmap(&tmdQ);
+      tc05::mbar_init(bar_kv, 1);
+      for (int st = 0; st < kBwdStages; ++st) tc05::mbar_init(bar_ld + st, 1);
+      tc05::mbar_init(bar_s, 1); tc05::mbar_init(bar_g, 1); tc05::mbar_init(bar_stg, 1);
+      tc05::fence_barrier_init();
+      // the loads go out before anything else: K, V and the first two query tiles
+      tc05::mbar_expect_tx(bar_kv, 2 * kBN * kD * 2);
+      tc05::tma_load_4d(smem + kBOffK, &tmK, bar_kv, 0, h, j0, b);
+      tc05::tma_load_4d(smem + kBOffV, &tmV, bar_kv, 0, h, j0, b);
+      for (int st = 0; st < kBwdStages && st < n_it; ++st) {
+        uint8_t* dst = smem + kBOffQ + st * kBwdStageBytes;
+        tc05::mbar_expect_tx(bar_ld + st, kBwdStageBytes);
+        tc05::tma_load_4d(dst, &tmQ, bar_ld + st, 0, h, (m_first + st) * kBM, b);
+        tc05::tma_load_4d(dst + kBM * kD * 2, &tmdO, bar_ld + st, 0, h, (m_first + st) * kBM, b);
+      }
+    }
+    __syncwarp();
     tc05::tmem_alloc(tmem_slot, kBwdTmemCols);
     tc05::tmem_relinquish();
-  }
-  if (tid < kBN) {
-    const int j = j0 + tid;
-    s_kadd[tid] = (j < p.Sk) ? (p.key_add ? p.key_add[(long long)b * p.Sk + j] * kLog2e : 0.f) : -INFINITY;
-  }
-  if (HAS_REL) {
-    // window of relative offsets: global rel index r = j - i + Sq - 1 = j0 + w, w in [0, n_win)
-    for (int x = tid; x < kRelPad + n_win; x += kBwdThreads2) {
-      const int r = j0 + x - kRelPad;
-      s_rel[x] = (x >= kRelPad && r < n_rel) ? p.rel_bias[(long long)h * n_rel + r] * kLog2e : 0.f;
+  } else {
+    if (tid < kBN) {
+      const int j = j0 + tid;
+      s_kadd[tid] = (j < p.Sk) ? (p.key_add ? p.key_add[(long long)b * p.Sk + j] * kLog2e : 0.f) : -INFINITY;
     }
-    for (int x = tid; x < n_win; x += kBwdThreads2) s_drel[x] = 0.f;
-    if (has_scp) {
-      if (tid < 32) s_scp[tid] = p.scp_tab[h * 32 + tid] * kLog2e;
-      s_dscp[tid] = 0.f;                       // 512 threads == 16 x 32 bins
+    if (HAS_REL) {
+      // window of relative offsets: global rel index r = j - i + Sq - 1 = j0 + w, w in [0, n_win)
+      for (int x = tid; x < kRelPad + n_win; x += kBwdComputeThreads) {
+        const int r = j0 + x - kRelPad;
+        s_rel[x] = (x >= kRelPad && r < n_rel) ? p.rel_bias[(long long)h * n_rel + r] * kLog2e : 0.f;
+      }
+      for (int x = tid; x < n_win; x += kBwdComputeThreads) s_drel[x] = 0.f;
+      if (has_scp) {
+        if (tid < 32) s_scp[tid] = p.scp_tab[h * 32 + tid] * kLog2e;
+        s_dscp[tid] = 0.f;                       // 512 threads == 16 x 32 bins
+      }
     }
   }
   tc05::tc_fence_before_sync();
@@ -522,242 +550,302 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   PVQA_TRACE(1);
 
-  const int m_tiles = (p.Sq + kBM - 1) / kBM;
-  const int m_first = p.causal ? (j0 / kBM) : 0;      // query tiles entirely above the diagonal see nothing
-  if (tid == 0) {
-    tc05::mbar_expect_tx(bar_kv, 2 * kBN * kD * 2);
-    tc05::tma_load_4d(smem + kBOffK, &tmK, bar_kv, 0, h, j0, b);
-    tc05::tma_load_4d(smem + kBOffV, &tmV, bar_kv, 0, h, j0, b);
-    if (m_first < m_tiles) {
-      tc05::mbar_expect_tx(bar_ld, 2 * kBM * kD * 2);
-      tc05::tma_load_4d(smem + kBOffQ, &tmQ, bar_ld, 0, h, m_first * kBM, b);
-      tc05::tma_load_4d(smem + kBOffQ + kBM * kD * 2, &tmdO, bar_ld, 0, h, m_first * kBM, b);
-    }
-  }
-
-  const float sl2 = p.scale * kLog2e;
-  const uint32_t idesc_s = tc05::idesc_bf16(kBM, kBN, 0, 0);
-  const uint32_t idesc_dkv = tc05::idesc_bf16(kBN, kD, 1, 1);   // A = P^T / dS^T (MN-major), B = dO / Q (MN-major)
-  const uint32_t idesc_dq = tc05::idesc_bf16(kBM, kD, 0, 1);    // A = dS (K-major), B = K (MN-major)
-  const uint32_t k_addr = tc05::smem_u32(smem + kBOffK), v_addr = tc05::smem_u32(smem + kBOffV);
-  const uint32_t p_addr = tc05::smem_u32(smem + kBOffP), ds_addr = tc05::smem_u32(smem + kBOffdS);
-  const uint32_t thr4 = p.drop_thr8 * 0x01010101u;
-  const int jl0 = qd * 32;                      // first local key column of this thread
-  const uint64_t rng_off = p.offset + ((DROP && p.rng_base) ? *p.rng_base : 0ull);
-
-  int it = 0;
-  for (int mt = m_first; mt < m_tiles; ++mt, ++it) {
-    const int i0 = mt * kBM;
-    const int stg = it & 1;
-    const uint32_t ph = it & 1;
-    const uint32_t q_addr = tc05::smem_u32(smem + kBOffQ + stg * (2 * kBM * kD * 2));
-    const uint32_t do_addr = q_addr + kBM * kD * 2;
-    if (tid == 0) {
-      if (mt + 1 < m_tiles) {                   // prefetch the next query tile into the other stage
-        uint8_t* nq = smem + kBOffQ + (stg ^ 1) * (2 * kBM * kD * 2);
-        tc05::mbar_expect_tx(bar_ld + (stg ^ 1), 2 * kBM * kD * 2);
-        tc05::tma_load_4d(nq, &tmQ, bar_ld + (stg ^ 1), 0, h, i0 + kBM, b);
-        tc05::tma_load_4d(nq + kBM * kD * 2, &tmdO, bar_ld + (stg ^ 1), 0, h, i0 + kBM, b);
-      }
-      if (it == 0) tc05::mbar_wait(bar_kv, 0);
-      tc05::mbar_wait(bar_ld + stg, (it >> 1) & 1);
-      tc05::tc_fence_after_sync();
+  if (is_issuer) {
+    // ================= issuer warp =================
+    const uint32_t idesc_s = tc05::idesc_bf16(kBM, kBN, 0, 0);
+    const uint32_t idesc_dkv = tc05::idesc_bf16(kBN, kD, 1, 1);   // A = P^T / dS^T (MN-major), B = dO / Q (MN-major)
+    const uint32_t idesc_dq = tc05::idesc_bf16(kBM, kD, 0, 1);    // A = dS (K-major), B = K (MN-major)
+    const uint32_t k_addr = tc05::smem_u32(smem + kBOffK), v_addr = tc05::smem_u32(smem + kBOffV);
+    const uint32_t p_addr = tc05::smem_u32(smem + kBOffP), ds_addr = tc05::smem_u32(smem + kBOffdS);
+    const uint32_t q_base = tc05::smem_u32(smem + kBOffQ);
+    auto issue_s_dp = [&](int st) {           // S = Q K^T and dP = dO V^T of the query tile in ring stage st
+      const uint32_t qa = q_base + st * kBwdStageBytes, da = qa + kBM * kD * 2;
 #pragma unroll
-      for (int ks = 0; ks < kD / 16; ++ks)      // S = Q K^T
-        tc05::mma_bf16_ss(tmem_base, tc05::smem_desc_sw128(q_addr + ks * 32, 16, 1024),
+      for (int ks = 0; ks < kD / 16; ++ks)
+        tc05::mma_bf16_ss(tmem_base, tc05::smem_desc_sw128(qa + ks * 32, 16, 1024),
                           tc05::smem_desc_sw128(k_addr + ks * 32, 16, 1024), idesc_s, ks > 0);
 #pragma unroll
-      for (int ks = 0; ks < kD / 16; ++ks)      // dP = dO V^T
-        tc05::mma_bf16_ss(tmem_base + kBN, tc05::smem_desc_sw128(do_addr + ks * 32, 16, 1024),
+      for (int ks = 0; ks < kD / 16; ++ks)
+        tc05::mma_bf16_ss(tmem_base + kBN, tc05::smem_desc_sw128(da + ks * 32, 16, 1024),
                           tc05::smem_desc_sw128(v_addr + ks * 32, 16, 1024), idesc_s, ks > 0);
+    };
+    auto reduce_dq = [&](int itp) {           // staging tile (fp32, two [128][32] SW128 halves) += into dq_accum
+      tc05::tma_reduce_add_4d(&tmdQ, smem + kBOffStg, 0, h, (m_first + itp) * kBM, b);
+      tc05::tma_reduce_add_4d(&tmdQ, smem + kBOffStg + kBM * 128, 32, h, (m_first + itp) * kBM, b);
+      tc05::bulk_commit_group();
+    };
+    if (lane == 0 && n_it > 0) {
+      tc05::mbar_wait(bar_kv, 0);
+      tc05::mbar_wait(bar_ld, 0);
+      tc05::tc_fence_after_sync();
+      issue_s_dp(0);
       tc05::mma_commit(bar_s);
     }
-    // ---- per-row statistics (overlaps the MMAs) ----
-    const int i = i0 + rowl;
-    const bool row_ok = i < p.Sq;
-    float lse2 = INFINITY, delta = 0.f;          // +inf => p = exp2(s - inf) = 0 for dead rows
-    if (row_ok) {
-      const long long ri = ((long long)b * p.H + h) * p.Sq + i;
-      const float l = p.lse[ri];
-      if (l != -INFINITY) lse2 = l * kLog2e;
-      delta = p.delta[ri];
+    for (int it = 0; it < n_it; ++it) {
+      // (1) every compute thread holds S/dP of tile it in registers: TMEM S/dP can take the next tile's scores
+      tc05::named_bar_sync(1, kBwdThreads2);
+      if (lane == 0 && it + 1 < n_it) {
+        tc05::tc_fence_after_sync();
+        const int st1 = (it + 1) % kBwdStages;
+        tc05::mbar_wait(bar_ld + st1, ((it + 1) / kBwdStages) & 1);
+        tc05::tc_fence_after_sync();
+        issue_s_dp(st1);
+        tc05::mma_commit(bar_s);
+      }
+      __syncwarp();
+      // (2) P/dS of tile it are in smem and dQ(it-1) is staged
+      tc05::named_bar_sync(3, kBwdThreads2);
+      if (lane == 0) {
+        tc05::tc_fence_after_sync();
+        const int stg = it % kBwdStages;
+        const uint32_t q_addr = q_base + stg * kBwdStageBytes, do_addr = q_addr + kBM * kD * 2;
+        if (it > 0) reduce_dq(it - 1);
+        const uint32_t dq_col = tmem_base + 384 + (it & 1) * 64;
+#pragma unroll
+        for (int ks = 0; ks < kBM / 16; ++ks)     // dV += P^T dO   (K = 128 query rows, 16 per step)
+          tc05::mma_bf16_ss(tmem_base + 256, tc05::smem_desc_sw128(p_addr + ks * 2048, kBM * 128, 1024),
+                            tc05::smem_desc_sw128(do_addr + ks * 2048, 16, 1024), idesc_dkv, (it > 0) || (ks > 0));
+#pragma unroll
+        for (int ks = 0; ks < kBM / 16; ++ks)     // dK += dS^T Q
+          tc05::mma_bf16_ss(tmem_base + 320, tc05::smem_desc_sw128(ds_addr + ks * 2048, kBM * 128, 1024),
+                            tc05::smem_desc_sw128(q_addr + ks * 2048, 16, 1024), idesc_dkv, (it > 0) || (ks > 0));
+#pragma unroll
+        for (int ks = 0; ks < kBN / 16; ++ks)     // dQ_m = dS K    (K = 128 keys)
+          tc05::mma_bf16_ss(dq_col,
+                            tc05::smem_desc_sw128(ds_addr + (ks >> 2) * (kBM * 128) + (ks & 3) * 32, 16, 1024),
+                            tc05::smem_desc_sw128(k_addr + ks * 2048, 16, 1024), idesc_dq, ks > 0);
+        tc05::mma_commit(bar_g);
+        PVQA_TRACE(3 + 5 * it);
+        if (it > 0) {                             // the reduce has read the staging tile: hand it back
+          tc05::bulk_wait_group_read0();
+          tc05::mbar_arrive(bar_stg);
+        }
+        if (it + kBwdStages < n_it) {             // this tile's ring stage is free once its GEMMs are done
+          tc05::mbar_wait(bar_g, it & 1);
+          uint8_t* dst = smem + kBOffQ + stg * kBwdStageBytes;
+          const int i_next = (m_first + it + kBwdStages) * kBM;
+          tc05::mbar_expect_tx(bar_ld + stg, kBwdStageBytes);
+          tc05::tma_load_4d(dst, &tmQ, bar_ld + stg, 0, h, i_next, b);
+          tc05::tma_load_4d(dst + kBM * kD * 2, &tmdO, bar_ld + stg, 0, h, i_next, b);
+        }
+        PVQA_TRACE(4 + 5 * it);
+      }
+      __syncwarp();
     }
-    const bool diag = p.causal && (j0 + kBN - 1 > i0);
-    const float* relrow = s_rel + (p.Sq - 1 - i) + kRelPad;      // relrow[jl] = bias of local key jl for this row
-    tc05::mbar_wait(bar_s, ph);
-    tc05::tc_fence_after_sync();
-    PVQA_TRACE(2 + 5 * it);
-
-    // ---- P and dS for this thread's 32 columns ----
-    if (j0 + jl0 >= p.Sk || i0 + (warp & 3) * 32 >= p.Sq) {
-      // warp-uniform dead block (keys past Sk or query rows past Sq): P = dS = 0, nothing to compute
-      uint8_t* prow = smem + kBOffP + (qd >> 1) * (kBM * 128) + rowl * 128;
-      uint8_t* dsrow = smem + kBOffdS + (qd >> 1) * (kBM * 128) + rowl * 128;
+    if (n_it > 0) {
+      tc05::named_bar_sync(3, kBwdThreads2);      // dQ of the last tile is staged
+      if (lane == 0) {
+        reduce_dq(n_it - 1);
+        tc05::bulk_wait_group0();                 // all reductions performed before the CTA retires
+      }
+      __syncwarp();
+    } else if (lane == 0) {
+      tc05::mbar_wait(bar_kv, 0);                 // never leave with a TMA write in flight
+    }
+  } else {
+    // ================= 16 compute warps =================
+    const float sl2 = p.scale * kLog2e;
+    const uint32_t thr4 = p.drop_thr8 * 0x01010101u;
+    const int jl0 = qd * 32;                      // first local key column of this thread
+    const uint64_t rng_off = p.offset + ((DROP && p.rng_base) ? *p.rng_base : 0ull);
+    uint8_t* stg_row = smem + kBOffStg + (qd >> 1) * (kBM * 128) + rowl * 128;
+    // dQ of query tile itp (complete in TMEM) -> fp32 staging tile in smem (the issuer reduces it into dq_accum)
+    auto stage_dq = [&](int itp) {
+      if (itp > 0) tc05::mbar_wait(bar_stg, (itp - 1) & 1);       // reduce of tile itp-1 has read the buffer
+      uint32_t r[16];
+      tc05::tmem_ld_32x16(tmem_row + 384 + (itp & 1) * 64 + qd * 16, r);
+      tc05::tmem_ld_wait();
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int chunk = ((qd & 1) * 4 + q) ^ (rowl & 7);
-        *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(0u, 0u, 0u, 0u);
-        *reinterpret_cast<uint4*>(dsrow + chunk * 16) = make_uint4(0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(stg_row + chunk * 16) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
       }
-    } else {
-      uint32_t rs[32], rp[32];
-      tc05::tmem_ld_32x32(tmem_row + jl0, rs);
-      tc05::tmem_ld_32x32(tmem_row + kBN + jl0, rp);
-      tc05::tmem_ld_wait();
-      float pv[32], dsv[32];
-      const uint8_t* scp_row = nullptr;
-      const int jj0 = j0 + jl0 - p.scp_q0;           // this chunk's first column inside the OCR block
-      if (has_scp && row_ok && i >= p.scp_q0 && i < p.scp_q0 + p.scp_L && jj0 + 32 > 0 && jj0 < p.scp_L)
-        scp_row = p.scp_bucket + ((long long)b * p.scp_L + (i - p.scp_q0)) * p.scp_L;
-      if (scp_row) {
-        float sb[32];
-        load_scp32(scp_row, jj0, p.scp_L, s_scp, sb);
+    };
+    // per-row statistics of a query tile, fetched one tile ahead so the global-load latency hides behind the math
+    auto load_stats = [&](int itn, float& l_out, float& d_out) {
+      const int in = (m_first + itn) * kBM + rowl;
+      l_out = -INFINITY; d_out = 0.f;
+      if (itn < n_it && in < p.Sq) {
+        const long long ri = ((long long)b * p.H + h) * p.Sq + in;
+        l_out = p.lse[ri];
+        d_out = p.delta[ri];
+      }
+    };
+    float lse_nx, delta_nx;
+    load_stats(0, lse_nx, delta_nx);
+    for (int it = 0; it < n_it; ++it) {
+      const int i0 = (m_first + it) * kBM;
+      const int i = i0 + rowl;
+      const bool row_ok = i < p.Sq;
+      // +inf => p = exp2(s - inf) = 0 for dead rows and for rows whose softmax was empty (lse = -inf)
+      const float lse2 = (lse_nx != -INFINITY) ? lse_nx * kLog2e : INFINITY;
+      const float delta = delta_nx;
+      load_stats(it + 1, lse_nx, delta_nx);
+      const bool diag = p.causal && (j0 + kBN - 1 > i0);
+      const float* relrow = s_rel + (p.Sq - 1 - i) + kRelPad;      // relrow[jl] = bias of local key jl for this row
+      // P/dS smem is still read by the GEMMs of tile it-1: wait for them right before the stores (long done by then)
+      auto wait_prev_gemms = [&]() {
+        if (it > 0) {
+          tc05::mbar_wait(bar_g, (it - 1) & 1);
+          tc05::tc_fence_after_sync();
+        }
+      };
+      tc05::mbar_wait(bar_s, it & 1);
+      tc05::tc_fence_after_sync();
+      PVQA_TRACE(2 + 5 * it);
+
+      // ---- P and dS for this thread's 32 columns ----
+      const bool dead = j0 + jl0 >= p.Sk || i0 + (warp & 3) * 32 >= p.Sq;   // warp-uniform: keys past Sk / rows past Sq
+      uint8_t* prow = smem + kBOffP + (qd >> 1) * (kBM * 128) + rowl * 128;
+      uint8_t* dsrow = smem + kBOffdS + (qd >> 1) * (kBM * 128) + rowl * 128;
+      if (dead) {
+        tc05::tc_fence_before_sync();
+        tc05::named_bar_arrive(1, kBwdThreads2);
+        wait_prev_gemms();
 #pragma unroll
-        for (int x = 0; x < 32; ++x)
-          pv[x] = fast_exp2(fmaf(__uint_as_float(rs[x]), sl2, s_kadd[jl0 + x] + relrow[jl0 + x] + sb[x]) - lse2);
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = ((qd & 1) * 4 + q) ^ (rowl & 7);
+          *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(dsrow + chunk * 16) = make_uint4(0u, 0u, 0u, 0u);
+        }
       } else {
+        uint32_t rs[32], rp[32];
+        tc05::tmem_ld_32x32(tmem_row + jl0, rs);
+        tc05::tmem_ld_32x32(tmem_row + kBN + jl0, rp);
+        tc05::tmem_ld_wait();
+        // S/dP of this tile now live in registers: the issuer may overwrite TMEM with the next tile's
+        tc05::tc_fence_before_sync();
+        tc05::named_bar_arrive(1, kBwdThreads2);
+        // SCP bucket ids of the 32 columns (two 16-byte halves, each inside or outside the OCR block)
+        const int jj0 = j0 + jl0 - p.scp_q0;
+        uint32_t bkw[8];
+        bool scp_h[2] = {false, false};
+        if (has_scp) {
+          const bool row_in = row_ok && i >= p.scp_q0 && i < p.scp_q0 + p.scp_L;
+          const uint8_t* scp_row = p.scp_bucket + ((long long)b * p.scp_L + (i - p.scp_q0)) * p.scp_L;
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int jj = jj0 + hf * 16;
+            scp_h[hf] = row_in && jj >= 0 && jj < p.scp_L;
+            uint4 u = make_uint4(0u, 0u, 0u, 0u);
+            if (scp_h[hf]) u = __ldg(reinterpret_cast<const uint4*>(scp_row + jj));
+            bkw[hf * 4] = u.x; bkw[hf * 4 + 1] = u.y; bkw[hf * 4 + 2] = u.z; bkw[hf * 4 + 3] = u.w;
+          }
+        }
+        // dropout: the 1/keep factor rides in the exponent (pv = P/keep), so P_drop = pv & mask and
+        // dS = P (M/keep dP - delta) scale = pv (M dP - keep delta) scale = pv * fma(M*scale, dP, -keep*delta*scale)
+        const float lse_k = DROP ? lse2 - log2f(p.drop_scale) : lse2;
+        const float nds = -(DROP ? delta / p.drop_scale : delta) * p.scale;
+        float pv[32], dsv[32];
 #pragma unroll
         for (int x = 0; x < 32; ++x) {
-          float bias = s_kadd[jl0 + x];
+          // key term: one 16-byte broadcast load per 4 columns (every lane reads the same address)
+          const float4 ka4 = *reinterpret_cast<const float4*>(s_kadd + jl0 + (x & ~3));
+          float bias = (x & 3) == 0 ? ka4.x : (x & 3) == 1 ? ka4.y : (x & 3) == 2 ? ka4.z : ka4.w;
           if (HAS_REL) bias += relrow[jl0 + x];
-          float s = fmaf(__uint_as_float(rs[x]), sl2, bias);
-          if (diag && (j0 + jl0 + x > i)) s = -INFINITY;
-          pv[x] = fast_exp2(s - lse2);
+          if (has_scp && scp_h[x >> 4]) bias += s_scp[(bkw[x >> 2] >> (8 * (x & 3))) & 31u];
+          float sc = fmaf(__uint_as_float(rs[x]), sl2, bias);
+          if (diag && (j0 + jl0 + x > i)) sc = -INFINITY;
+          pv[x] = fast_exp2(sc - lse_k);
         }
-      }
-      if (DROP) {      // P_drop = P*M/keep feeds dV; dP = M/keep * dP_drop feeds dS
-        const uint64_t drop_row = ((uint64_t)(b * p.H + h) * p.Sq + min(i, p.Sq - 1)) * (uint64_t)((p.Sk + 15) >> 4);
+        if (DROP) {
+          const uint64_t drop_row = ((uint64_t)(b * p.H + h) * p.Sq + min(i, p.Sq - 1)) * (uint64_t)((p.Sk + 15) >> 4);
 #pragma unroll
-        for (int g2 = 0; g2 < 2; ++g2) {
-          const uint4 kb = keep_bytes16(p.seed, rng_off, drop_row + ((j0 + jl0) >> 4) + g2, thr4);
-          const uint32_t kw[4] = {kb.x, kb.y, kb.z, kb.w};
+          for (int g2 = 0; g2 < 2; ++g2) {
+            const uint4 kb = keep_bytes16(p.seed, rng_off, drop_row + ((j0 + jl0) >> 4) + g2, thr4);
+            const uint32_t kw[4] = {kb.x, kb.y, kb.z, kb.w};
 #pragma unroll
-          for (int w = 0; w < 4; ++w) {
-#pragma unroll
-            for (int bb = 0; bb < 4; ++bb) {
-              const int x = g2 * 16 + w * 4 + bb;
-              const float mk = __uint_as_float(__float_as_uint(p.drop_scale) & PVQA_BYTE_MASK(kw[w], bb));
-              dsv[x] = pv[x] * fmaf(mk, __uint_as_float(rp[x]), -delta) * p.scale;
-              pv[x] *= mk;
+            for (int xx = 0; xx < 16; ++xx) {
+              const int x = g2 * 16 + xx;
+              const uint32_t m = PVQA_BYTE_MASK(kw[xx >> 2], xx & 3);
+              dsv[x] = pv[x] * fmaf(__uint_as_float(__float_as_uint(p.scale) & m), __uint_as_float(rp[x]), nds);
+              pv[x] = __uint_as_float(__float_as_uint(pv[x]) & m);
             }
           }
+        } else {
+#pragma unroll
+          for (int x = 0; x < 32; ++x) dsv[x] = pv[x] * fmaf(p.scale, __uint_as_float(rp[x]), nds);
         }
+        if (has_scp && p.d_scp) {
+          // d_scp[bucket] += dS on the OCR x OCR block: per-warp shared-memory bins (conflicting lanes serialise)
+#pragma unroll
+          for (int x = 0; x < 32; ++x)
+            if (scp_h[x >> 4]) atomicAdd(s_dscp + warp * 32 + ((bkw[x >> 2] >> (8 * (x & 3))) & 31u), dsv[x]);
+        }
+        if (HAS_REL && p.d_rel) {
+          // d_rel[j-i] += dS: this warp holds a 32x32 block (lane = row, register = column).  Lane L collects the
+          // diagonals d' = col - row == L (mod 32): one shuffle per column, two accumulators for the wrap.
+          float accp = 0.f, accn = 0.f;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const float vsh = __shfl_sync(0xffffffffu, dsv[c], c - lane);   // source lane taken mod 32
+            if (lane <= c) accp += vsh; else accn += vsh;
+          }
+          // window index of rel = (j0+jl) - (i0+il) + Sq-1, minus j0;  jl - il = (jl0 - 32*(warp&3)) + d'
+          const int wpos = jl0 - (warp & 3) * 32 + lane - i0 + p.Sq - 1;
+          if (wpos >= 0 && wpos < n_win) atomicAdd(s_drel + wpos, accp);
+          if (lane > 0 && wpos - 32 >= 0 && wpos - 32 < n_win) atomicAdd(s_drel + wpos - 32, accn);
+        }
+        wait_prev_gemms();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = ((qd & 1) * 4 + q) ^ (rowl & 7);
+          *reinterpret_cast<uint4*>(prow + chunk * 16) = pack8(pv + q * 8);
+          *reinterpret_cast<uint4*>(dsrow + chunk * 16) = pack8(dsv + q * 8);
+        }
+      }
+      PVQA_TRACE(3 + 5 * it);
+      if (it > 0) stage_dq(it - 1);               // complete since bar_g(it-1)
+      tc05::fence_proxy_async_smem();
+      tc05::tc_fence_before_sync();
+      tc05::named_bar_arrive(3, kBwdThreads2);
+      PVQA_TRACE(4 + 5 * it);
+    }
+    if (n_it > 0) {
+      tc05::mbar_wait(bar_g, (n_it - 1) & 1);
+      tc05::tc_fence_after_sync();
+      PVQA_TRACE(25);
+      stage_dq(n_it - 1);
+      tc05::fence_proxy_async_smem();
+      tc05::tc_fence_before_sync();
+      tc05::named_bar_arrive(3, kBwdThreads2);
+      PVQA_TRACE(26);
+    }
+    // ---- epilogue: dV, dK rows (key j0 + rowl), columns [16*qd, +16) ----
+    {
+      const int j = j0 + rowl;
+      uint32_t rv[16], rk[16];
+      if (n_it > 0) {
+        tc05::tmem_ld_32x16(tmem_row + 256 + qd * 16, rv);
+        tc05::tmem_ld_32x16(tmem_row + 320 + qd * 16, rk);
+        tc05::tmem_ld_wait();
       } else {
 #pragma unroll
-        for (int x = 0; x < 32; ++x) dsv[x] = pv[x] * (__uint_as_float(rp[x]) - delta) * p.scale;
+        for (int x = 0; x < 16; ++x) { rv[x] = 0u; rk[x] = 0u; }
       }
-      if (scp_row && p.d_scp) {
-        // d_scp[bucket] += dS on the OCR x OCR block: per-warp shared-memory bins (conflicting lanes serialise)
+      if (j < p.Sk) {
+        __nv_bfloat16* dvrow = p.dv + b * p.dv_stride_b + j * p.dv_stride_s + h * p.dv_stride_h + qd * 16;
+        __nv_bfloat16* dkrow = p.dk + b * p.dk_stride_b + j * p.dk_stride_s + h * p.dk_stride_h + qd * 16;
+        float fv[16], fk[16];
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          const int jj = jj0 + hf * 16;
-          if (jj >= 0 && jj < p.scp_L) {
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(scp_row + jj));
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        for (int x = 0; x < 16; ++x) { fv[x] = __uint_as_float(rv[x]); fk[x] = __uint_as_float(rk[x]); }
 #pragma unroll
-            for (int k = 0; k < 16; ++k)
-              atomicAdd(s_dscp + warp * 32 + ((w[k >> 2] >> (8 * (k & 3))) & 31u), dsv[hf * 16 + k]);
-          }
+        for (int c = 0; c < 2; ++c) {
+          *reinterpret_cast<uint4*>(dvrow + c * 8) = pack8(fv + c * 8);
+          *reinterpret_cast<uint4*>(dkrow + c * 8) = pack8(fk + c * 8);
         }
       }
-      if (HAS_REL && p.d_rel) {
-        // d_rel[j-i] += dS: this warp holds a 32x32 block (lane = row, register = column).  Lane L collects the
-        // diagonals d' = col - row == L (mod 32): one shuffle per column, two accumulators for the wrap.
-        float accp = 0.f, accn = 0.f;
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float vsh = __shfl_sync(0xffffffffu, dsv[c], (c - lane) & 31);
-          if (lane <= c) accp += vsh; else accn += vsh;
-        }
-        // window index of rel = (j0+jl) - (i0+il) + Sq-1, minus j0;  jl - il = (jl0 - 32*(warp&3)) + d'
-        const int wpos = jl0 - (warp & 3) * 32 + lane - i0 + p.Sq - 1;
-        if (wpos >= 0 && wpos < n_win) atomicAdd(s_drel + wpos, accp);
-        if (lane > 0 && wpos - 32 >= 0 && wpos - 32 < n_win) atomicAdd(s_drel + wpos - 32, accn);
+    }
+    PVQA_TRACE(27);
+    tc05::named_bar_sync(2, kBwdComputeThreads);       // every warp's smem bins are final
+    PVQA_TRACE(28);
+    if (HAS_REL && p.d_rel) {
+      const float inv_scale = 1.0f / p.scale;          // the smem tile holds scale * dS
+      for (int w = tid; w < n_win; w += kBwdComputeThreads) {
+        const int r = j0 + w;
+        const float g = s_drel[w];
+        if (r < n_rel && g != 0.f) atomicAdd(p.d_rel + (long long)h * n_rel + r, g * inv_scale);
       }
-      uint8_t* prow = smem + kBOffP + (qd >> 1) * (kBM * 128) + rowl * 128;
-      uint8_t* dsrow = smem + kBOffdS + (qd >> 1) * (kBM * 128) + rowl * 128;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int chunk = ((qd & 1) * 4 + q) ^ (rowl & 7);
-        *reinterpret_cast<uint4*>(prow + chunk * 16) = pack8(pv + q * 8);
-        *reinterpret_cast<uint4*>(dsrow + chunk * 16) = pack8(dsv + q * 8);
-      }
-    }
-    PVQA_TRACE(3 + 5 * it);
-    tc05::fence_proxy_async_smem();
-    tc05::tc_fence_before_sync();
-    __syncthreads();
-    PVQA_TRACE(4 + 5 * it);
-    if (tid == 0) {
-      tc05::tc_fence_after_sync();
-#pragma unroll
-      for (int ks = 0; ks < kBM / 16; ++ks)     // dV += P^T dO   (K = 128 query rows, 16 per step)
-        tc05::mma_bf16_ss(tmem_base + 256, tc05::smem_desc_sw128(p_addr + ks * 2048, kBM * 128, 1024),
-                          tc05::smem_desc_sw128(do_addr + ks * 2048, 16, 1024), idesc_dkv, (it > 0) || (ks > 0));
-#pragma unroll
-      for (int ks = 0; ks < kBM / 16; ++ks)     // dK += dS^T Q
-        tc05::mma_bf16_ss(tmem_base + 320, tc05::smem_desc_sw128(ds_addr + ks * 2048, kBM * 128, 1024),
-                          tc05::smem_desc_sw128(q_addr + ks * 2048, 16, 1024), idesc_dkv, (it > 0) || (ks > 0));
-#pragma unroll
-      for (int ks = 0; ks < kBN / 16; ++ks)     // dQ_m = dS K    (K = 128 keys)
-        tc05::mma_bf16_ss(tmem_base,
-                          tc05::smem_desc_sw128(ds_addr + (ks >> 2) * (kBM * 128) + (ks & 3) * 32, 16, 1024),
-                          tc05::smem_desc_sw128(k_addr + ks * 2048, 16, 1024), idesc_dq, ks > 0);
-      tc05::mma_commit(bar_dq);
-    }
-    tc05::mbar_wait(bar_dq, ph);
-    tc05::tc_fence_after_sync();
-    PVQA_TRACE(5 + 5 * it);
-    {
-      uint32_t r[16];
-      tc05::tmem_ld_32x16(tmem_row + qd * 16, r);
-      tc05::tmem_ld_wait();
-      if (row_ok) {
-        float* dst = p.dq_accum + (((long long)b * p.Sq + i) * p.H + h) * kD + qd * 16;
-#pragma unroll
-        for (int x = 0; x < 16; x += 4)
-          red_add_v4(dst + x, __uint_as_float(r[x]), __uint_as_float(r[x + 1]), __uint_as_float(r[x + 2]),
-                     __uint_as_float(r[x + 3]));
-      }
-    }
-    tc05::tc_fence_before_sync();
-    __syncthreads();
-    tc05::tc_fence_after_sync();
-    PVQA_TRACE(6 + 5 * it);
-  }
-
-  if (it == 0 && tid == 0) tc05::mbar_wait(bar_kv, 0);     // never leave with a TMA write in flight
-  // ---- epilogue: dV, dK rows (key j0 + rowl), columns [16*qd, +16) ----
-  {
-    const int j = j0 + rowl;
-    uint32_t rv[16], rk[16];
-    if (it > 0) {
-      tc05::tmem_ld_32x16(tmem_row + 256 + qd * 16, rv);
-      tc05::tmem_ld_32x16(tmem_row + 320 + qd * 16, rk);
-      tc05::tmem_ld_wait();
-    } else {
-#pragma unroll
-      for (int x = 0; x < 16; ++x) { rv[x] = 0u; rk[x] = 0u; }
-    }
-    if (j < p.Sk) {
-      __nv_bfloat16* dvrow = p.dv + b * p.dv_stride_b + j * p.dv_stride_s + h * p.dv_stride_h + qd * 16;
-      __nv_bfloat16* dkrow = p.dk + b * p.dk_stride_b + j * p.dk_stride_s + h * p.dk_stride_h + qd * 16;
-      float fv[16], fk[16];
-#pragma unroll
-      for (int x = 0; x < 16; ++x) { fv[x] = __uint_as_float(rv[x]); fk[x] = __uint_as_float(rk[x]); }
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        *reinterpret_cast<uint4*>(dvrow + c * 8) = pack8(fv + c * 8);
-        *reinterpret_cast<uint4*>(dkrow + c * 8) = pack8(fk + c * 8);
-      }
-    }
-  }
-  if (HAS_REL && p.d_rel) {
-    const float inv_scale = 1.0f / p.scale;          // the smem tile holds scale * dS
-    for (int w = tid; w < n_win; w += kBwdThreads2) {
-      const int r = j0 + w;
-      const float g = s_drel[w];
-      if (r < n_rel && g != 0.f) atomicAdd(p.d_rel + (long long)h * n_rel + r, g * inv_scale);
     }
   }
   PVQA_TRACE(30);
@@ -767,10 +855,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (has_scp && p.d_scp && tid < 32) {
     float g = 0.f;
 #pragma unroll
-    for (int w = 0; w < kBwdThreads2 / 32; ++w) g += s_dscp[w * 32 + tid];
+    for (int w = 0; w < kBwdComputeWarps; ++w) g += s_dscp[w * 32 + tid];
     if (g != 0.f) atomicAdd(p.d_scp + h * 32 + tid, g / p.scale);
   }
-  if (warp == 0) tc05::tmem_dealloc(tmem_base, kBwdTmemCols);
+  if (is_issuer) tc05::tmem_dealloc(tmem_base, kBwdTmemCols);
 }
 
 // ---------------------------------------------------------------------------------
@@ -929,6 +1017,19 @@ extern "C" int pvqa_attn_bwd(const void* q, const void* k, const void* v, const 
   if ((rc = make_tmap(&tk, k, B, Sk, H, k_stride_b, k_stride_s, k_stride_h, kBN, "k"))) return rc;
   if ((rc = make_tmap(&tv, v, B, Sk, H, v_stride_b, v_stride_s, v_stride_h, kBN, "v"))) return rc;
   if ((rc = make_tmap(&tdo, d_o, B, Sq, H, do_stride_b, do_stride_s, do_stride_h, kBM, "d_o"))) return rc;
+  CUtensorMap tdq;          // fp32 (B,Sq,H,64) contiguous accumulator, reduced into by 32-column half tiles
+  {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return fail(PVQA_ERR_CUDA, "attn_bwd: cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[4] = {(cuuint64_t)kD, (cuuint64_t)H, (cuuint64_t)Sq, (cuuint64_t)B};
+    cuuint64_t gstr[3] = {(cuuint64_t)kD * 4, (cuuint64_t)H * kD * 4, (cuuint64_t)Sq * H * kD * 4};
+    cuuint32_t box[4] = {32, 1, (cuuint32_t)kBM, 1};
+    cuuint32_t est[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tdq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dq_accum, gdim, gstr, box, est,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PVQA_ERR_CUDA, "attn_bwd: cuTensorMapEncodeTiled(dq_accum) failed with %d", (int)r);
+  }
   cudaStream_t st = (cudaStream_t)stream;
   AttnPrepParams pp{};
   pp.o = reinterpret_cast<const __nv_bfloat16*>(o); pp.d_o = reinterpret_cast<const __nv_bfloat16*>(d_o);
@@ -964,7 +1065,7 @@ extern "C" int pvqa_attn_bwd(const void* q, const void* k, const void* v, const 
     attr_set[vi] = true;
   }
   dim3 grid((unsigned)((Sk + kBN - 1) / kBN), (unsigned)H, (unsigned)B);
-  kern<<<grid, kBwdThreads2, smem_bytes, st>>>(tq, tk, tv, tdo, p);
+  kern<<<grid, kBwdThreads2, smem_bytes, st>>>(tq, tk, tv, tdo, tdq, p);
   count_launch();
   PVQA_CHECK_LAUNCH("attn_bwd");
   return PVQA_OK;

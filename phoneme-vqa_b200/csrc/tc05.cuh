@@ -156,3 +156,28 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16])
       : "r"(taddr) : "memory");
 }
 }  // namespace tc05
+
+// ---------------- TMA reduce (smem tile += into global), bulk async groups, named barriers ----------------
+namespace tc05 {
+// 4-D tiled element-wise ADD of a shared-memory box into global memory (performed at L2 by the TMA unit;
+// out-of-bounds rows of the box are clipped).  Completion is tracked by the issuing thread's bulk async-group.
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2,
+                                                  int c3) {
+  asm volatile(
+      "cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+      :: "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk groups of this thread have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... have completed entirely (global writes performed)
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// hardware named barrier `id` over `nthreads` threads (a multiple of 32): arrive does not block
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+  asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+}
+}  // namespace tc05

@@ -18,10 +18,13 @@ FWD_EV = {0: "start", 1: "prologue done", 30: "epilogue stores issued", 31: "end
 for t in range(4):
     FWD_EV.update({2 + 6 * t: f"t{t} S ready", 3 + 6 * t: f"t{t} pass A done", 4 + 6 * t: f"t{t} max exchanged",
                    5 + 6 * t: f"t{t} pass B done", 6 + 6 * t: f"t{t} O_j ready", 7 + 6 * t: f"t{t} tile end"})
-BWD_EV = {0: "start", 1: "prologue done", 30: "epilogue stores issued", 31: "end"}
+BWD_EV = {0: "start", 1: "prologue done", 25: "last GEMMs done", 26: "last dQ staged", 27: "dK/dV stored", 28: "bins synced",
+          30: "epilogue stores issued", 31: "end"}
 for t in range(5):
-    BWD_EV.update({2 + 5 * t: f"t{t} S,dP ready", 3 + 5 * t: f"t{t} P,dS done", 4 + 5 * t: f"t{t} synced",
-                   5 + 5 * t: f"t{t} dQ ready", 6 + 5 * t: f"t{t} tile end"})
+    # thread 0 (compute): S/dP ready -> P/dS stored -> dQ(t-1) staged + arrived;  issuer: barrier passed -> all MMAs
+    # issued -> ring refilled
+    BWD_EV.update({2 + 5 * t: f"t{t} S,dP ready | P/dS full", 3 + 5 * t: f"t{t} P,dS stored | MMAs issued",
+                   4 + 5 * t: f"t{t} dQ(t-1) staged | refilled"})
 
 
 def build():
@@ -47,7 +50,7 @@ def report(tr, names, title):
             if e == 0 or not (ev[:, e] > 0).all():
                 continue
             d = ev[:, e] - ev[:, prev]
-            print(f"    {names[e]:26s} +{d.mean():8.0f}  (min {d.min():6d} max {d.max():6d})   @{np.mean(ev[:, e] - ev[:, 0]):8.0f}")
+            print(f"    {names[e]:34s} +{d.mean():8.0f}  (min {d.min():6d} max {d.max():6d})   @{np.mean(ev[:, e] - ev[:, 0]):8.0f}")
             prev = e
 
 
