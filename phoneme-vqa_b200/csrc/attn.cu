@@ -152,19 +152,45 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     tc05::mbar_init(bar_q, 1); tc05::mbar_init(bar_k, 1); tc05::mbar_init(bar_k + 1, 1);
     tc05::mbar_init(bar_v, 1); tc05::mbar_init(bar_v + 1, 1); tc05::mbar_init(bar_s, 1); tc05::mbar_init(bar_o, 1);
     tc05::fence_barrier_init();
+    // the first loads go out before anything else so that they overlap the bias staging below
+    // (K_j lives in buffer (2j) % 3, V_j in (2j+1) % 3: K_{j+1} reuses V_{j-1}'s buffer, V_{j+1} reuses K_j's)
+    tc05::mbar_expect_tx(bar_q, kBM * kD * 2);
+    tc05::tma_load_4d(smem + kOffQ, &tmQ, bar_q, 0, h, i0, b);
+    tc05::mbar_expect_tx(bar_k, kKVBuf);
+    tc05::tma_load_4d(smem + kOffKV, &tmK, bar_k, 0, h, 0, b);
+    tc05::mbar_expect_tx(bar_v, kKVBuf);
+    tc05::tma_load_4d(smem + kOffKV + kKVBuf, &tmV, bar_v, 0, h, 0, b);
   }
+  __syncwarp();
   if (warp == 0) {
     tc05::tmem_alloc(tmem_slot, kTmemCols);
     tc05::tmem_relinquish();
   }
-  // stage the additive vectors, pre-multiplied by log2(e): the softmax runs in the exp2 domain
-  for (int j = tid; j < n_kpad; j += kFwdThreads)
-    s_kadd[j] = (j < p.Sk) ? (p.key_add ? p.key_add[(long long)b * p.Sk + j] * kLog2e : 0.f) : -INFINITY;
+  // stage the additive vectors, pre-multiplied by log2(e): the softmax runs in the exp2 domain.
+  // Four independent global loads per thread and trip (the loops are latency-, not bandwidth-bound).
+  for (int j0s = tid; j0s < n_kpad; j0s += 4 * kFwdThreads) {
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0s + u * kFwdThreads;
+      v[u] = (j < p.Sk) ? (p.key_add ? p.key_add[(long long)b * p.Sk + j] * kLog2e : 0.f) : -INFINITY;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (j0s + u * kFwdThreads < n_kpad) s_kadd[j0s + u * kFwdThreads] = v[u];
+  }
   if (HAS_REL) {
     const int n = kRelPad + p.Sq + n_kpad;
-    for (int x = tid; x < n; x += kFwdThreads) {
-      const int r = x - kRelPad;
-      s_rel[x] = (r >= 0 && r < n_rel) ? p.rel_bias[(long long)h * n_rel + r] * kLog2e : 0.f;
+    for (int x0 = tid; x0 < n; x0 += 4 * kFwdThreads) {
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = x0 + u * kFwdThreads - kRelPad;
+        v[u] = (r >= 0 && r < n_rel) ? p.rel_bias[(long long)h * n_rel + r] * kLog2e : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (x0 + u * kFwdThreads < n) s_rel[x0 + u * kFwdThreads] = v[u];
     }
     if (has_scp && tid < 32) s_scp[tid] = p.scp_tab[h * 32 + tid] * kLog2e;
   }
@@ -177,15 +203,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   int n_tiles = n_tiles_all;
   if (p.causal) n_tiles = min(n_tiles, min(i0 + kBM - 1, p.Sq - 1) / kBN + 1);
-  // K_j lives in buffer (2j) % 3, V_j in (2j+1) % 3: K_{j+1} reuses V_{j-1}'s buffer, V_{j+1} reuses K_j's
-  if (tid == 0) {
-    tc05::mbar_expect_tx(bar_q, kBM * kD * 2);
-    tc05::tma_load_4d(smem + kOffQ, &tmQ, bar_q, 0, h, i0, b);
-    tc05::mbar_expect_tx(bar_k, kKVBuf);
-    tc05::tma_load_4d(smem + kOffKV, &tmK, bar_k, 0, h, 0, b);
-    tc05::mbar_expect_tx(bar_v, kKVBuf);
-    tc05::tma_load_4d(smem + kOffKV + kKVBuf, &tmV, bar_v, 0, h, 0, b);
-  }
 
   const int i = i0 + rowl;
   const bool rows_dead = i0 + (warp & 3) * 32 >= p.Sq;      // all 32 query rows of this warp are past the end
