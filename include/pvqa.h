@@ -333,6 +333,13 @@ int pvqa_add_dropout_rms_bwd(const void* dy, int y_dtype, const float* d_residua
  * x is (N, d) bf16 or fp32 row-major, d % 8 == 0; accumulate == 0 zeroes `out` first. */
 int pvqa_col_sum(const void* x, float* out, int64_t N, int64_t d, int dtype, int accumulate, void* stream);
 
+/* dst[r][0:d] = src[r][0:d] with src fp32 contiguous (N, d) and dst bf16/fp32 rows `dst_row_stride` elements
+ * apart: drops the fp32 dQ accumulator of pvqa_attn_bwd into the q slot of the packed (B,S,3,H,D) gradient that
+ * the fused q/k/v projection backward consumes (the reference gets three separate .grad tensors from autograd:
+ * transformers modeling_t5.py:312-336). */
+int pvqa_cast_rows(const float* src, void* dst, int64_t N, int64_t d, int64_t dst_row_stride, int dst_dtype,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,6 +89,7 @@ _SIGNATURES = {
     "pvqa_add_dropout_rms_fwd": (c_int, [_vp, _vp, c_int, _vp, _vp, _vp, c_int, _vp, _i64, _i64, _f, _f, c_uint64, c_uint64, _vp]),
     "pvqa_add_dropout_rms_bwd": (c_int, [_vp, c_int, _vp, _vp, _vp, _vp, _vp, _vp, c_int, _vp, _i64, _i64, _f, c_uint64,
                                          c_uint64, _vp]),
+    "pvqa_cast_rows": (c_int, [_vp, _vp, _i64, _i64, _i64, c_int, _vp]),
     "pvqa_col_sum": (c_int, [_vp, _vp, _i64, _i64, c_int, c_int, _vp]),
     "pvqa_attn_f32_bwd": (c_int, [_vp] * 13 + _i64x(5) + _i64x(24) + [_f, c_int, _f, c_uint64, c_uint64, _vp, _vp, _vp, _i64, _i64, _vp]),
 }

@@ -419,6 +419,18 @@ col_sum_kernel(const T* __restrict__ x, float* __restrict__ out, int N, int d, i
   }
 }
 
+// ---------------- dst[r][0:d] (row stride ld elements, T) = src[r][0:d] (fp32 contiguous) ----------------
+// the fp32 dQ accumulator of the attention backward cast into the q slot of the packed (B,S,3,H,D) gradient
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads)
+cast_rows_kernel(const float* __restrict__ src, T* __restrict__ dst, long long n8, int d8, long long ld) {
+  for (long long i = (long long)blockIdx.x * kNormThreads + threadIdx.x; i < n8; i += (long long)gridDim.x * kNormThreads) {
+    const long long r = i / d8;
+    const int c = (int)(i - r * d8) * 8;
+    Vec8<T>::store(dst + r * ld + c, Vec8<float>::load_stream(src + i * 8));
+  }
+}
+
 static int ew_grid(long long n8) {
   long long need = (n8 + kNormThreads - 1) / kNormThreads;
   long long cap = (long long)num_sms() * 8;
@@ -745,5 +757,25 @@ extern "C" int pvqa_add_dropout_rms_bwd(const void* dy, int y_dtype, const float
     return fail(PVQA_ERR_DTYPE, "add_dropout_rms_bwd: bad update dtype");
   count_launch();
   PVQA_CHECK_LAUNCH("add_dropout_rms_bwd");
+  return PVQA_OK;
+}
+
+extern "C" int pvqa_cast_rows(const float* src, void* dst, int64_t N, int64_t d, int64_t dst_row_stride, int dst_dtype,
+                              void* stream) {
+  PVQA_REQUIRE(N >= 0 && d > 0 && d % 8 == 0 && dst_row_stride >= d && dst_row_stride % 8 == 0, PVQA_ERR_SHAPE,
+               "cast_rows: d and the destination row stride must be multiples of 8, stride >= d");
+  if (N == 0) return PVQA_OK;
+  PVQA_REQUIRE(src && dst, PVQA_ERR_NULL, "cast_rows: NULL pointer");
+  PVQA_REQUIRE(aligned16(src) && aligned16(dst), PVQA_ERR_ALIGN, "cast_rows: 16-byte alignment required");
+  const long long n8 = (long long)N * (d / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dst_dtype == PVQA_BF16)
+    cast_rows_kernel<__nv_bfloat16><<<ew_grid(n8), kNormThreads, 0, st>>>(src, (__nv_bfloat16*)dst, n8, (int)(d / 8), dst_row_stride);
+  else if (dst_dtype == PVQA_F32)
+    cast_rows_kernel<float><<<ew_grid(n8), kNormThreads, 0, st>>>(src, (float*)dst, n8, (int)(d / 8), dst_row_stride);
+  else
+    return fail(PVQA_ERR_DTYPE, "cast_rows: bad dtype");
+  count_launch();
+  PVQA_CHECK_LAUNCH("cast_rows");
   return PVQA_OK;
 }

@@ -683,7 +683,13 @@ class _AttnSelf(torch.autograd.Function):
         dqkv = torch.empty_like(qkv)
         dq, d_rel, d_scp = attention_bwd_raw(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], o, d_o, lse, scale, rb, ka,
                                              causal, dqkv[:, :, 1], dqkv[:, :, 2], want_rel, drop, scp, want_scp)
-        dqkv[:, :, 0].copy_(dq)
+        B_, S_, _, H_, D_ = dqkv.shape
+        if (H_ * D_) % 8 == 0:          # fp32 accumulator -> q slot of the packed gradient, one vectorised pass
+            with torch.cuda.device(dqkv.device), _prof("cast_rows"):
+                check(_lib.load().pvqa_cast_rows(_p(dq), _p(dqkv), B_ * S_, H_ * D_, 3 * H_ * D_, _dt(dqkv.dtype), _stream()),
+                      "pvqa_cast_rows")
+        else:
+            dqkv[:, :, 0].copy_(dq)
         return (dqkv, (d_rel.to(rel_dtype) if want_rel else None), None, None, None, None, None,
                 (d_scp.t().to(scp_dtype) if want_scp else None), None)
 
