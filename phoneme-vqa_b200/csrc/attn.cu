@@ -466,22 +466,29 @@ struct AttnPrepParams {
 
 __global__ void __launch_bounds__(256)
 attn_bwd_prep_kernel(const AttnPrepParams p) {
+  // 8 lanes per (b, i, h) row of 64 elements, rows enumerated in memory order (h fastest): every warp reads
+  // four whole 128-byte rows of O and of dO per step
   const long long n = (long long)p.B * p.H * p.Sq;
-  for (long long t = (long long)blockIdx.x * 256 + threadIdx.x; t < n; t += (long long)gridDim.x * 256) {
-    const int i = (int)(t % p.Sq);
-    const int h = (int)((t / p.Sq) % p.H);
-    const int b = (int)(t / ((long long)p.Sq * p.H));
-    const __nv_bfloat16* orow = p.o + b * p.o_stride_b + i * p.o_stride_s + h * p.o_stride_h;
-    const __nv_bfloat16* grow = p.d_o + b * p.do_stride_b + i * p.do_stride_s + h * p.do_stride_h;
+  const int sub = threadIdx.x & 7;
+  // warp-uniform trip count (the shuffles below need all 32 lanes): t0 = first row of this warp's group of four
+  for (long long t0 = ((long long)blockIdx.x * 256 + (threadIdx.x & ~31)) >> 3; t0 < n; t0 += ((long long)gridDim.x * 256) >> 3) {
+    const long long t = t0 + ((threadIdx.x & 31) >> 3);
+    const bool valid = t < n;
+    const long long tc = valid ? t : 0;
+    const int h = (int)(tc % p.H);
+    const int i = (int)((tc / p.H) % p.Sq);
+    const int b = (int)(tc / ((long long)p.H * p.Sq));
+    const __nv_bfloat16* orow = p.o + b * p.o_stride_b + i * p.o_stride_s + h * p.o_stride_h + sub * 8;
+    const __nv_bfloat16* grow = p.d_o + b * p.do_stride_b + i * p.do_stride_s + h * p.do_stride_h + sub * 8;
+    const f8 a = Vec8<__nv_bfloat16>::load(orow);
+    const f8 g = Vec8<__nv_bfloat16>::load(grow);
     float acc = 0.f;
 #pragma unroll
-    for (int c = 0; c < kD / 8; ++c) {
-      const f8 a = Vec8<__nv_bfloat16>::load(orow + c * 8);
-      const f8 g = Vec8<__nv_bfloat16>::load(grow + c * 8);
-#pragma unroll
-      for (int x = 0; x < 8; ++x) acc = fmaf(a.v[x], g.v[x], acc);
-    }
-    p.delta[t] = acc;          // t == (b*H + h)*Sq + i
+    for (int x = 0; x < 8; ++x) acc = fmaf(a.v[x], g.v[x], acc);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (sub == 0 && valid) p.delta[((long long)b * p.H + h) * p.Sq + i] = acc;
   }
 }
 
@@ -1054,7 +1061,7 @@ extern "C" int pvqa_attn_bwd(const void* q, const void* k, const void* v, const 
   pp.o_stride_b = o_stride_b; pp.o_stride_s = o_stride_s; pp.o_stride_h = o_stride_h;
   pp.do_stride_b = do_stride_b; pp.do_stride_s = do_stride_s; pp.do_stride_h = do_stride_h;
   {
-    const long long n = (long long)B * H * Sq;
+    const long long n = (long long)B * H * Sq * 8;         // 8 lanes per row
     long long need = (n + 255) / 256, cap = (long long)num_sms() * 8;
     attn_bwd_prep_kernel<<<(int)(need < cap ? need : cap), 256, 0, st>>>(pp);
     count_launch();

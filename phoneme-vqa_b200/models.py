@@ -103,9 +103,20 @@ class _FrozenVitLP:
             for p in self.full.parameters():
                 p.requires_grad_(False)
             return
-        self.embeddings = copy.deepcopy(vit.embeddings).to(bf).eval()
+        self.embeddings = copy.deepcopy(vit.embeddings).to(bf).eval()     # only for unexpected image sizes
         for p in self.embeddings.parameters():
             p.requires_grad_(False)
+        # patch embedding as unfold + GEMM (the stride-16 16x16 convolution is exactly that; cuDNN's conv path
+        # spends 10x longer in layout conversions), [CLS] and the position table folded in
+        pe = vit.embeddings.patch_embeddings
+        self.patch = tuple(pe.patch_size) if hasattr(pe.patch_size, "__len__") else (pe.patch_size, pe.patch_size)
+        self.image = tuple(pe.image_size) if hasattr(pe.image_size, "__len__") else (pe.image_size, pe.image_size)
+        w = pe.projection.weight.detach()
+        self.w_patch = w.reshape(w.shape[0], -1).to(bf).contiguous()
+        self.b_patch = pe.projection.bias.detach().to(bf)
+        pos = vit.embeddings.position_embeddings.detach()
+        self.cls_pos = (vit.embeddings.cls_token.detach() + pos[:, :1]).to(bf)
+        self.pos = pos[:, 1:].to(bf).contiguous()
         self.layers = []
         for blk in vit.encoder.layer:
             att = blk.attention.attention
@@ -119,13 +130,28 @@ class _FrozenVitLP:
                 w2=blk.output.dense.weight.detach().to(bf), b2=blk.output.dense.bias.detach().to(bf)))
         self.final_ln = (vit.layernorm.weight.detach().float(), vit.layernorm.bias.detach().float())
 
+    def _embed(self, px):
+        """HF ViTEmbeddings.forward (patch projection, [CLS], position table; dropout is 0 in eval) -> (B, 1+N, d)"""
+        bf = torch.bfloat16
+        B, C, Hh, Ww = px.shape
+        (ph, pw), d = self.patch, self.w_patch.shape[0]
+        if (Hh, Ww) != self.image or C * ph * pw != self.w_patch.shape[1]:
+            return self.embeddings(px.to(bf)).contiguous()
+        gh, gw = Hh // ph, Ww // pw
+        patches = torch.empty((B, gh, gw, C, ph, pw), dtype=bf, device=px.device)
+        patches.copy_(px.view(B, C, gh, ph, gw, pw).permute(0, 2, 4, 1, 3, 5))       # unfold + cast, one pass
+        x = torch.empty((B, 1 + gh * gw, d), dtype=bf, device=px.device)
+        x[:, :1] = self.cls_pos
+        torch.add(F.linear(patches.view(B, gh * gw, C * ph * pw), self.w_patch, self.b_patch), self.pos, out=x[:, 1:])
+        return x
+
     @torch.no_grad()
     def __call__(self, pixel_values):
         bf = torch.bfloat16
         if not self.lean:
             emb = self.full.embeddings(pixel_values.to(bf))
             return self.full.layernorm(self.full.encoder(emb).last_hidden_state)
-        x = self.embeddings(pixel_values.to(bf)).contiguous()
+        x = self._embed(pixel_values)
         B, S, d = x.shape
         H, D = self.heads, d // self.heads
         scale = 1.0 / math.sqrt(D)
