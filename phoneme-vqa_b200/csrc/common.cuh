@@ -36,6 +36,9 @@ extern const unsigned long long* g_rng_base;
   } while (0)
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+// streaming fp32 rows move as 256-bit accesses (Vec8<float>::load_stream / store): 32-byte alignment
+inline bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
+inline bool aligned_for(const void* p, int dtype) { return dtype == PVQA_F32 ? aligned32(p) : aligned16(p); }
 
 // ---- 8-element vector load/store in fp32 registers -------------------------
 // One "chunk" = 8 consecutive elements: 16 B for bf16, 32 B for fp32.
@@ -107,23 +110,20 @@ template <> struct Vec8<float> {
     r.v[6] = __uint_as_float(b.z); r.v[7] = __uint_as_float(b.w);
     return r;
   }
+  // One 256-bit access per lane (sm_100: LDG/STG.256): a warp covers 1 KB of contiguous sectors.  Two 128-bit
+  // accesses per lane would interleave the lanes at a 32-byte stride, every instruction touching only half of each
+  // sector it requests, which doubles the L2 -> SM traffic of the un-cached (L1::no_allocate) streaming path.
   static __device__ __forceinline__ f8 load_stream(const float* p) {
-    uint4 a = ldg16_stream(p), b = ldg16_stream(p + 4);
     f8 r;
-    r.v[0] = __uint_as_float(a.x); r.v[1] = __uint_as_float(a.y);
-    r.v[2] = __uint_as_float(a.z); r.v[3] = __uint_as_float(a.w);
-    r.v[4] = __uint_as_float(b.x); r.v[5] = __uint_as_float(b.y);
-    r.v[6] = __uint_as_float(b.z); r.v[7] = __uint_as_float(b.w);
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]),
+                   "=f"(r.v[7]) : "l"(p));
     return r;
   }
   static __device__ __forceinline__ void store(float* p, const f8& a) {
-    uint4 x, y;
-    x.x = __float_as_uint(a.v[0]); x.y = __float_as_uint(a.v[1]);
-    x.z = __float_as_uint(a.v[2]); x.w = __float_as_uint(a.v[3]);
-    y.x = __float_as_uint(a.v[4]); y.y = __float_as_uint(a.v[5]);
-    y.z = __float_as_uint(a.v[6]); y.w = __float_as_uint(a.v[7]);
-    stg16_stream(p, x);
-    stg16_stream(p + 4, y);
+    asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "l"(p), "f"(a.v[0]), "f"(a.v[1]), "f"(a.v[2]), "f"(a.v[3]), "f"(a.v[4]), "f"(a.v[5]), "f"(a.v[6]),
+                    "f"(a.v[7]) : "memory");
   }
 };
 

@@ -486,7 +486,7 @@ extern "C" int pvqa_embed_mm_fwd(const void* img_feat, const int64_t* coords, co
   EmbedMMParams p{};
   p.img = img_feat; p.coords = coords; p.ocr_ids = ocr_ids; p.q_ids = q_ids;
   p.ocr_mask = ocr_mask; p.q_mask = q_mask; p.shared_tab = shared_tab;
-  PVQA_REQUIRE(aligned16(out) && aligned16(shared_tab) && aligned16(img_feat), PVQA_ERR_ALIGN,
+  PVQA_REQUIRE(aligned32(out) && aligned16(shared_tab) && aligned32(img_feat), PVQA_ERR_ALIGN,
                "embed_mm_fwd: pointers must be 16-byte aligned");
   for (int t = 0; t < 6; ++t) {
     p.layout[t] = L_ocr ? layout_tabs[t] : nullptr;
@@ -523,7 +523,7 @@ extern "C" int pvqa_embed_mm_bwd(const void* d_out, const int64_t* coords, const
   PVQA_REQUIRE(d_out && d_shared, PVQA_ERR_NULL, "embed_mm_bwd: d_out/d_shared is NULL");
   PVQA_REQUIRE(L_ocr == 0 || (coords && ocr_ids && d_layout_tabs), PVQA_ERR_NULL, "embed_mm_bwd: OCR inputs NULL");
   PVQA_REQUIRE(L_q == 0 || q_ids, PVQA_ERR_NULL, "embed_mm_bwd: q_ids NULL");
-  PVQA_REQUIRE(aligned16(d_out) && aligned16(d_shared), PVQA_ERR_ALIGN, "embed_mm_bwd: pointers must be 16-byte aligned");
+  PVQA_REQUIRE(aligned32(d_out) && aligned16(d_shared), PVQA_ERR_ALIGN, "embed_mm_bwd: pointers must be 16-byte (d_out: 32-byte) aligned");
   EmbedMMBwdParams p{};
   p.d_out = d_out; p.coords = coords; p.ocr_ids = ocr_ids; p.q_ids = q_ids; p.d_shared = d_shared;
   for (int t = 0; t < 6; ++t) {
@@ -567,7 +567,7 @@ extern "C" int pvqa_embed_tgt_fwd(const int64_t* labels, const void* onset_tab, 
   p.dropout_p = dropout_p; p.seed = seed; p.offset = offset; p.rng_base = g_rng_base; p.err_flag = err_flag;
   cudaStream_t st = (cudaStream_t)stream;
   const bool vec = (on_dim % 8 == 0) && (rt_dim % 8 == 0) && aligned16(onset_tab) && aligned16(rhyme_tab) &&
-                   aligned16(tone_tab) && aligned16(pe) && aligned16(out);
+                   aligned16(tone_tab) && aligned16(pe) && aligned32(out);
   if (vec) {
     const int grid = grid_for(B * T * (d / 8), 256, 8);
 #define LAUNCH_TGT_VEC(TT, AT) embed_tgt_fwd_vec_kernel<TT, AT><<<grid, 256, 0, st>>>(p)

@@ -280,8 +280,8 @@ add_dropout_ln_fwd_kernel(const HT* __restrict__ hidden, const UT* __restrict__ 
 // backward of the fused tail.  g = dy (+ dy_lp), xhat = (z - mean) * rstd, wg = g * gamma:
 //   dz = rstd * (wg - mean(wg) - xhat * mean(wg * xhat));  d_hidden = dz;  d_update = mask * dz / keep
 //   dgamma += sum_rows g * xhat;  dbeta += sum_rows g      (register partials -> smem -> one global atomic per CTA column)
-template <typename UT, typename LT, int NV>
-__global__ void __launch_bounds__(kNormThreads)
+template <typename UT, typename LT, int NV, bool LN>      // LN: LayerNorm (mean, beta); otherwise T5 RMS norm
+__global__ void __launch_bounds__(kNormThreads, 2)
 add_dropout_ln_bwd_kernel(const float* __restrict__ dy, const LT* __restrict__ dy_lp, const float* __restrict__ d_res,
                           const float* __restrict__ z,
                           const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -294,15 +294,18 @@ add_dropout_ln_bwd_kernel(const float* __restrict__ dy, const LT* __restrict__ d
   const float inv_d = 1.0f / (float)d;
   for (int c = threadIdx.x; c < 2 * d; c += kNormThreads) s_part[c] = 0.f;
   __syncthreads();
-  f8 acc_g[NV], acc_b[NV];
+  f8 acc_g[NV], acc_b[LN ? NV : 1];
 #pragma unroll
   for (int c = 0; c < NV; ++c) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { acc_g[c].v[j] = 0.f; acc_b[c].v[j] = 0.f; }
+    for (int j = 0; j < 8; ++j) {
+      acc_g[c].v[j] = 0.f;
+      if (LN) acc_b[c].v[j] = 0.f;
+    }
   }
   for (int row = blockIdx.x * (kNormThreads / 32) + (threadIdx.x >> 5); row < N; row += gridDim.x * (kNormThreads / 32)) {
     const long long base = (long long)row * d;
-    const float mu = mean ? mean[row] : 0.f, r = rstd[row];
+    const float mu = LN ? mean[row] : 0.f, r = rstd[row];
     f8 xh[NV], wg[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -327,15 +330,15 @@ add_dropout_ln_bwd_kernel(const float* __restrict__ dy, const LT* __restrict__ d
           const float xhat = (zz.v[j] - mu) * r;
           xh[c].v[j] = xhat;
           acc_g[c].v[j] = fmaf(g.v[j], xhat, acc_g[c].v[j]);
-          acc_b[c].v[j] += g.v[j];
+          if (LN) acc_b[c].v[j] += g.v[j];
           const float w = g.v[j] * gm.v[j];
           wg[c].v[j] = w;
-          s1 += w;
+          if (LN) s1 += w;
           s2 = fmaf(w, xhat, s2);
         }
       }
     }
-    const float c1 = mean ? warp_sum_n(s1) * inv_d : 0.f, c2 = warp_sum_n(s2) * inv_d;
+    const float c1 = LN ? warp_sum_n(s1) * inv_d : 0.f, c2 = warp_sum_n(s2) * inv_d;
 #pragma unroll
     for (int c = 0; c < NV; ++c) {
       const int col = (c * 32 + lane) * 8;
@@ -367,14 +370,14 @@ add_dropout_ln_bwd_kernel(const float* __restrict__ dy, const LT* __restrict__ d
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         atomicAdd(s_part + col + j, acc_g[c].v[j]);
-        if (dbeta) atomicAdd(s_part + d + col + j, acc_b[c].v[j]);
+        if (LN) atomicAdd(s_part + d + col + j, acc_b[c].v[j]);
       }
     }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < d; c += kNormThreads) {
     atomicAdd(dgamma + c, s_part[c]);
-    if (dbeta) atomicAdd(dbeta + c, s_part[d + c]);
+    if (LN) atomicAdd(dbeta + c, s_part[d + c]);
   }
 }
 
@@ -452,7 +455,7 @@ extern "C" int pvqa_rms_norm_fwd(const void* x, const float* w, void* y, float* 
                "rms_norm_fwd: d=%lld must be a multiple of 4 and <= %d", (long long)d, 128 * kMaxVec);
   if (N == 0) return PVQA_OK;
   PVQA_REQUIRE(x && w && y, PVQA_ERR_NULL, "rms_norm_fwd: NULL pointer");
-  PVQA_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y), PVQA_ERR_ALIGN, "rms_norm_fwd: 16-byte alignment required");
+  PVQA_REQUIRE(aligned32(x) && aligned32(w) && aligned32(y), PVQA_ERR_ALIGN, "rms_norm_fwd: 32-byte alignment required");
   const int warps = kNormThreads / 32;
   long long need = (N + warps - 1) / warps, cap = (long long)num_sms() * 8;
   const int grid = (int)(need < cap ? need : cap);
@@ -478,7 +481,7 @@ extern "C" int pvqa_rms_norm_bwd(const void* dy, const void* x, const float* w, 
   PVQA_REQUIRE(d % 4 == 0 && d <= 128 * kMaxVec, PVQA_ERR_SHAPE, "rms_norm_bwd: d must be a multiple of 4 and <= %d", 128 * kMaxVec);
   if (N == 0) return PVQA_OK;
   PVQA_REQUIRE(dy && x && w && rstd && dx && dw, PVQA_ERR_NULL, "rms_norm_bwd: NULL pointer");
-  PVQA_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(w) && aligned16(dx), PVQA_ERR_ALIGN, "rms_norm_bwd: 16-byte alignment required");
+  PVQA_REQUIRE(aligned32(dy) && aligned32(x) && aligned32(w) && aligned32(dx), PVQA_ERR_ALIGN, "rms_norm_bwd: 32-byte alignment required");
   const int warps = kNormThreads / 32;
   long long need = (N + warps - 1) / warps, cap = (long long)num_sms() * 2;   // 128 regs -> 2 CTAs/SM resident
   const int grid = (int)(need < cap ? need : cap);
@@ -503,7 +506,7 @@ extern "C" int pvqa_residual_dropout_add(const float* hidden, const void* update
   PVQA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, PVQA_ERR_SHAPE, "residual_dropout_add: dropout_p must be in [0,1)");
   if (n == 0) return PVQA_OK;
   PVQA_REQUIRE(hidden && update && out, PVQA_ERR_NULL, "residual_dropout_add: NULL pointer");
-  PVQA_REQUIRE(aligned16(hidden) && aligned16(update) && aligned16(out), PVQA_ERR_ALIGN, "residual_dropout_add: 16-byte alignment required");
+  PVQA_REQUIRE(aligned32(hidden) && aligned32(update) && aligned32(out), PVQA_ERR_ALIGN, "residual_dropout_add: 32-byte alignment required");
   uint32_t thr; float sc;
   drop_consts(dropout_p, thr, sc);
   cudaStream_t st = (cudaStream_t)stream;
@@ -524,7 +527,7 @@ extern "C" int pvqa_residual_dropout_bwd(const float* d_out, void* d_update, int
   PVQA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, PVQA_ERR_SHAPE, "residual_dropout_bwd: dropout_p must be in [0,1)");
   if (n == 0) return PVQA_OK;
   PVQA_REQUIRE(d_out && d_update, PVQA_ERR_NULL, "residual_dropout_bwd: NULL pointer");
-  PVQA_REQUIRE(aligned16(d_out) && aligned16(d_update), PVQA_ERR_ALIGN, "residual_dropout_bwd: 16-byte alignment required");
+  PVQA_REQUIRE(aligned32(d_out) && aligned32(d_update), PVQA_ERR_ALIGN, "residual_dropout_bwd: 32-byte alignment required");
   uint32_t thr; float sc;
   drop_consts(dropout_p, thr, sc);
   cudaStream_t st = (cudaStream_t)stream;
@@ -545,7 +548,7 @@ extern "C" int pvqa_relu_dropout_fwd(const void* x, void* y, int64_t n, int dtyp
   PVQA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, PVQA_ERR_SHAPE, "relu_dropout_fwd: dropout_p must be in [0,1)");
   if (n == 0) return PVQA_OK;
   PVQA_REQUIRE(x && y, PVQA_ERR_NULL, "relu_dropout_fwd: NULL pointer");
-  PVQA_REQUIRE(aligned16(x) && aligned16(y), PVQA_ERR_ALIGN, "relu_dropout_fwd: 16-byte alignment required");
+  PVQA_REQUIRE(aligned32(x) && aligned32(y), PVQA_ERR_ALIGN, "relu_dropout_fwd: 32-byte alignment required");
   uint32_t thr; float sc;
   drop_consts(dropout_p, thr, sc);
   cudaStream_t st = (cudaStream_t)stream;
@@ -566,7 +569,7 @@ extern "C" int pvqa_relu_dropout_bwd(const void* dy, const void* y, void* dx, in
   PVQA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, PVQA_ERR_SHAPE, "relu_dropout_bwd: dropout_p must be in [0,1)");
   if (n == 0) return PVQA_OK;
   PVQA_REQUIRE(dy && y && dx, PVQA_ERR_NULL, "relu_dropout_bwd: NULL pointer");
-  PVQA_REQUIRE(aligned16(dy) && aligned16(y) && aligned16(dx), PVQA_ERR_ALIGN, "relu_dropout_bwd: 16-byte alignment required");
+  PVQA_REQUIRE(aligned32(dy) && aligned32(y) && aligned32(dx), PVQA_ERR_ALIGN, "relu_dropout_bwd: 32-byte alignment required");
   uint32_t thr; float sc;
   drop_consts(dropout_p, thr, sc);
   cudaStream_t st = (cudaStream_t)stream;
@@ -597,9 +600,13 @@ static int launch_add_ln_bwd(int nv, int grid, size_t smem, cudaStream_t st, con
                              const float* d_res, const float* z, const float* gamma, const float* mean, const float* rstd, float* d_hidden,
                              UT* d_upd, float* dgamma, float* dbeta, int N, int d, uint32_t thr, float sc, uint64_t seed,
                              uint64_t offset) {
-#define PVQA_LN_BWD(NV) add_dropout_ln_bwd_kernel<UT, LT, NV><<<grid, kNormThreads, smem, st>>>( \
+#define PVQA_LN_BWD(NV, LN) add_dropout_ln_bwd_kernel<UT, LT, NV, LN><<<grid, kNormThreads, smem, st>>>( \
     dy, dy_lp, d_res, z, gamma, mean, rstd, d_hidden, d_upd, dgamma, dbeta, N, d, thr, sc, seed, offset, g_rng_base)
-  switch (nv) { case 1: PVQA_LN_BWD(1); break; case 2: PVQA_LN_BWD(2); break; case 3: PVQA_LN_BWD(3); break; default: PVQA_LN_BWD(4); }
+  if (mean != nullptr && dbeta != nullptr) {
+    switch (nv) { case 1: PVQA_LN_BWD(1, true); break; case 2: PVQA_LN_BWD(2, true); break; case 3: PVQA_LN_BWD(3, true); break; default: PVQA_LN_BWD(4, true); }
+  } else {
+    switch (nv) { case 1: PVQA_LN_BWD(1, false); break; case 2: PVQA_LN_BWD(2, false); break; case 3: PVQA_LN_BWD(3, false); break; default: PVQA_LN_BWD(4, false); }
+  }
 #undef PVQA_LN_BWD
   return PVQA_OK;
 }
@@ -613,8 +620,8 @@ extern "C" int pvqa_add_dropout_ln_fwd(const void* hidden, int hidden_dtype, con
   PVQA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, PVQA_ERR_SHAPE, "add_dropout_ln_fwd: dropout_p must be in [0,1)");
   if (N == 0) return PVQA_OK;
   PVQA_REQUIRE(hidden && gamma && beta && (y || y_lp), PVQA_ERR_NULL, "add_dropout_ln_fwd: NULL pointer");  // beta required: LayerNorm
-  PVQA_REQUIRE(aligned16(hidden) && aligned16(update) && aligned16(gamma) && aligned16(beta) && aligned16(z) &&
-                   aligned16(y) && aligned16(y_lp), PVQA_ERR_ALIGN, "add_dropout_ln_fwd: 16-byte alignment required");
+  PVQA_REQUIRE(aligned32(hidden) && aligned32(update) && aligned32(gamma) && aligned32(beta) && aligned32(z) &&
+                   aligned32(y) && aligned32(y_lp), PVQA_ERR_ALIGN, "add_dropout_ln_fwd: 32-byte alignment required");
   PVQA_REQUIRE(!y_lp || lp_dtype == PVQA_BF16, PVQA_ERR_DTYPE, "add_dropout_ln_fwd: the low-precision copy must be bf16");
   uint32_t thr; float sc;
   drop_consts(update ? dropout_p : 0.f, thr, sc);
@@ -645,7 +652,7 @@ extern "C" int pvqa_add_dropout_ln_bwd(const float* dy, const void* dy_lp, int l
   PVQA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, PVQA_ERR_SHAPE, "add_dropout_ln_bwd: dropout_p must be in [0,1)");
   if (N == 0) return PVQA_OK;
   PVQA_REQUIRE((dy || dy_lp) && z && gamma && mean && rstd && d_hidden && dgamma && dbeta, PVQA_ERR_NULL, "add_dropout_ln_bwd: NULL pointer");
-  PVQA_REQUIRE(aligned16(dy) && aligned16(dy_lp) && aligned16(z) && aligned16(gamma) && aligned16(d_hidden) && aligned16(d_update),
+  PVQA_REQUIRE(aligned32(dy) && aligned32(dy_lp) && aligned32(z) && aligned32(gamma) && aligned32(d_hidden) && aligned32(d_update),
                PVQA_ERR_ALIGN, "add_dropout_ln_bwd: 16-byte alignment required");
   PVQA_REQUIRE(!dy_lp || lp_dtype == PVQA_BF16, PVQA_ERR_DTYPE, "add_dropout_ln_bwd: the low-precision gradient must be bf16");
   uint32_t thr; float sc;
@@ -677,7 +684,7 @@ extern "C" int pvqa_col_sum(const void* x, float* out, int64_t N, int64_t d, int
   }
   if (N == 0) return PVQA_OK;
   PVQA_REQUIRE(x, PVQA_ERR_NULL, "col_sum: NULL pointer");
-  PVQA_REQUIRE(aligned16(x), PVQA_ERR_ALIGN, "col_sum: 16-byte alignment required");
+  PVQA_REQUIRE(aligned32(x), PVQA_ERR_ALIGN, "col_sum: 32-byte alignment required");
   const int slabs = (int)((d + 255) / 256);
   long long want = ((long long)num_sms() * 4 + slabs - 1) / slabs;      // ~4 CTAs per SM in total
   long long rows_per = (N + want - 1) / want;
@@ -704,7 +711,7 @@ extern "C" int pvqa_add_dropout_rms_fwd(const float* hidden, const void* update,
   PVQA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, PVQA_ERR_SHAPE, "add_dropout_rms_fwd: dropout_p must be in [0,1)");
   if (N == 0) return PVQA_OK;
   PVQA_REQUIRE(hidden && update && weight && hidden_out && y, PVQA_ERR_NULL, "add_dropout_rms_fwd: NULL pointer");
-  PVQA_REQUIRE(aligned16(hidden) && aligned16(update) && aligned16(weight) && aligned16(hidden_out) && aligned16(y),
+  PVQA_REQUIRE(aligned32(hidden) && aligned32(update) && aligned32(weight) && aligned32(hidden_out) && aligned32(y),
                PVQA_ERR_ALIGN, "add_dropout_rms_fwd: 16-byte alignment required");
   PVQA_REQUIRE(y_dtype == PVQA_BF16 || y_dtype == PVQA_F32, PVQA_ERR_DTYPE, "add_dropout_rms_fwd: bad output dtype");
   uint32_t thr; float sc;
@@ -736,8 +743,8 @@ extern "C" int pvqa_add_dropout_rms_bwd(const void* dy, int y_dtype, const float
   PVQA_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, PVQA_ERR_SHAPE, "add_dropout_rms_bwd: dropout_p must be in [0,1)");
   if (N == 0) return PVQA_OK;
   PVQA_REQUIRE(dy && hidden_out && weight && rstd && d_hidden && d_update && dweight, PVQA_ERR_NULL, "add_dropout_rms_bwd: NULL pointer");
-  PVQA_REQUIRE(aligned16(dy) && aligned16(d_residual) && aligned16(hidden_out) && aligned16(weight) && aligned16(d_hidden) &&
-                   aligned16(d_update), PVQA_ERR_ALIGN, "add_dropout_rms_bwd: 16-byte alignment required");
+  PVQA_REQUIRE(aligned32(dy) && aligned32(d_residual) && aligned32(hidden_out) && aligned32(weight) && aligned32(d_hidden) &&
+                   aligned32(d_update), PVQA_ERR_ALIGN, "add_dropout_rms_bwd: 32-byte alignment required");
   PVQA_REQUIRE(y_dtype == PVQA_BF16 || y_dtype == PVQA_F32, PVQA_ERR_DTYPE, "add_dropout_rms_bwd: bad gradient dtype");
   uint32_t thr; float sc;
   drop_consts(dropout_p, thr, sc);
@@ -766,7 +773,7 @@ extern "C" int pvqa_cast_rows(const float* src, void* dst, int64_t N, int64_t d,
                "cast_rows: d and the destination row stride must be multiples of 8, stride >= d");
   if (N == 0) return PVQA_OK;
   PVQA_REQUIRE(src && dst, PVQA_ERR_NULL, "cast_rows: NULL pointer");
-  PVQA_REQUIRE(aligned16(src) && aligned16(dst), PVQA_ERR_ALIGN, "cast_rows: 16-byte alignment required");
+  PVQA_REQUIRE(aligned32(src) && aligned32(dst), PVQA_ERR_ALIGN, "cast_rows: 32-byte alignment required");
   const long long n8 = (long long)N * (d / 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (dst_dtype == PVQA_BF16)

@@ -137,6 +137,41 @@ def bench_embed(B=64):
     return res
 
 
+def bench_norm(N=64 * 327, d=768, iters=10):
+    """fused pre-norm glue at the encoder shape: algorithmic bytes / time against the measured HBM peak.
+    fwd: read fp32 stream + bf16 update, write stream + bf16 normed; bwd: read dy(bf16) + d_res + z, write d_hidden + d_upd."""
+    from phoneme_vqa_b200 import ops
+    pk = peaks()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    res = {}
+    w = torch.ones(d, device="cuda", requires_grad=True)
+    # rotate over several operand sets so no call finds its inputs in L2 (5 sets x ~260 MB >> 126 MB)
+    sets = []
+    for _ in range(5):
+        h = torch.randn(N, d, device="cuda", generator=g).requires_grad_(True)
+        u = torch.randn(N, d, device="cuda", generator=g).bfloat16().requires_grad_(True)
+        sets.append((h, u, torch.randn(N, d, device="cuda", generator=g), torch.randn(N, d, device="cuda", generator=g).bfloat16()))
+    ops.KernelTimer.reset(True)
+    for it in range(3 + iters):
+        if it == 3:
+            torch.cuda.synchronize()
+            ops.KernelTimer.reset(True)
+        h, u, g_res, g_y = sets[it % len(sets)]
+        ho, y = ops.add_dropout_rms_norm(h, u, w, 1e-6, 0.1, True, torch.bfloat16)
+        torch.autograd.backward([ho, y], [g_res, g_y])
+        h.grad = u.grad = None
+    torch.cuda.synchronize()
+    summ = ops.KernelTimer.summary()
+    ops.KernelTimer.reset(False)
+    alg = {"add_dropout_rms_fwd": N * d * (4 + 2 + 4 + 2), "add_dropout_rms_bwd": N * d * (2 + 4 + 4 + 4 + 2)}
+    for kname, (n, tot) in summ.items():
+        ms = tot / n
+        b = alg.get(kname.split("[")[0])
+        if b:
+            res[kname] = {"ms": ms, "alg_MB": b / 1e6, "GBs": b / ms / 1e6, "frac_of_hbm": b / ms / 1e6 / pk["hbm_gbs"]}
+    return res
+
+
 def bench_attn(B=64, H=12, S=327, T=127, dropout=0.1, iters=10, only=None):
     """tcgen05 attention kernels at the PhonoLaTr-base shapes; TFLOP/s against the measured bf16 peak.
     flops: fwd 4*B*H*Sq*Sk*D, bwd 10*B*H*Sq*Sk*D (5 GEMMs), causal halves both."""
@@ -186,6 +221,8 @@ if __name__ == "__main__":
     out = {"peaks": peaks()}
     if which in ("embed", "all"):
         out.update(bench_embed())
+    if which in ("norm", "all"):
+        out.update(bench_norm())
     if which in ("attn", "all"):
         out.update(bench_attn())
     if which == "attn_one":         # bench shape, encoder self-attention with dropout, one timed call (for ncu --set full)
