@@ -25,29 +25,35 @@ from oracle.stub_tokenizer import StubT5Tokenizer  # noqa: E402
 from oracle.data_cases import build_case, phoneme_tokenizer, write_case  # noqa: E402
 
 
+def dump_items(ds):
+    items = []
+    for i in range(len(ds)):
+        it = ds[i]
+        items.append({k: {"dtype": str(v.dtype), "shape": list(v.shape), "data": v.flatten().tolist()} for k, v in it.items()})
+    return items
+
+
 def main():
-    from core.data import PhonemeLaTrDataset, textlayout_ocr_adapt      # the real reference
+    from core.data import PhonemeLaTrDataset, PhonemePreSTUDataset, textlayout_ocr_adapt      # the real reference
     case = build_case()
     case["images"] = {str(k): v for k, v in case["images"].items()}
     with tempfile.TemporaryDirectory() as tmp:
         ocr_root, feat_root, qa_df = write_case(case, tmp)
         ocr_df = textlayout_ocr_adapt(ocr_root).sort_values("image_id").reset_index(drop=True)
         p = case["params"]
-        ds = PhonemeLaTrDataset(qa_df, ocr_df, StubT5Tokenizer(), phoneme_tokenizer(case, tmp), feat_root,
-                                max_ocr_element=p["max_ocr_element"], max_ocr_length=p["max_ocr_length"],
-                                max_input_length=p["max_input_length"], max_output_length=p["max_output_length"])
-        items = []
-        for i in range(len(ds)):
-            it = ds[i]
-            items.append({k: {"dtype": str(v.dtype), "shape": list(v.shape), "data": v.flatten().tolist()} for k, v in it.items()})
+        kw = dict(max_ocr_element=p["max_ocr_element"], max_ocr_length=p["max_ocr_length"],
+                  max_input_length=p["max_input_length"], max_output_length=p["max_output_length"])
+        ds = PhonemeLaTrDataset(qa_df, ocr_df, StubT5Tokenizer(), phoneme_tokenizer(case, tmp), feat_root, **kw)
+        items = dump_items(ds)
+        prestu = dump_items(PhonemePreSTUDataset(qa_df, ocr_df, StubT5Tokenizer(), phoneme_tokenizer(case, tmp), feat_root, **kw))
         ocr_rows = [{"image_id": float(r.image_id), "texts": list(r.texts), "bboxes": [list(map(float, b)) for b in r.bboxes]}
                     for r in ocr_df.itertuples()]
     out = {"case": case, "n_items": len(items), "image_ids": [float(x) for x in ds.data["image_id"]], "items": items,
-           "ocr_table": ocr_rows}
+           "items_prestu": prestu, "ocr_table": ocr_rows}
     path = os.path.join(ROOT, "tests", "golden", "data_phonemelatr.json")
     with open(path, "w", encoding="utf-8") as f:
         json.dump(out, f, ensure_ascii=False)
-    print("wrote", path, "items", len(items), "bytes", os.path.getsize(path))
+    print("wrote", path, "items", len(items), "+", len(prestu), "bytes", os.path.getsize(path))
 
 
 if __name__ == "__main__":
