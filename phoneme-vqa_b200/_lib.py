@@ -11,7 +11,7 @@ import ctypes
 import os
 import shutil
 import subprocess
-from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p, POINTER
+from ctypes import c_char_p, c_float, c_int, c_int64, c_uint64, c_void_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")

@@ -19,7 +19,7 @@ import torch.nn.functional as F
 from . import ops
 from .modules import (SHADOWS, BaseDecoder, RelativePositionBias1D, RelativePositionBiasAggregated,
                       SCPRelativePositionBias, T5LayerNorm, PhonemeEmbedding, SinusoidalPositionalEncoding, SpatialModule, T5EncoderModel,
-                      T5ForConditionalGeneration, T5Stack, _lin, _t5_init)
+                      T5ForConditionalGeneration, _lin)
 
 __all__ = ["LaTr_config", "CustomizedLaTr_config", "CustomizedPreSTU_config", "PhonemeLaTr", "PhonemePreSTU", "LaTr", "PhonemeSaL", "CustomizedSaL_config"]
 

@@ -7,7 +7,6 @@ tensor is not on a CUDA device — there is deliberately no PyTorch/CPU fallback
 """
 from __future__ import annotations
 
-import ctypes
 from ctypes import c_void_p
 
 import torch

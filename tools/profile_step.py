@@ -7,7 +7,7 @@ from torch.profiler import ProfilerActivity, profile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from phoneme_vqa_b200 import models, ops, synthetic  # noqa: E402
+from phoneme_vqa_b200 import models, synthetic  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 dev = torch.device("cuda:0")
