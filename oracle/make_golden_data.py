@@ -22,7 +22,7 @@ sys.path.insert(0, "/root/reference")
 
 from oracle.stub_tokenizer import StubT5Tokenizer  # noqa: E402
 
-from oracle.data_cases import build_case, phoneme_tokenizer, write_case  # noqa: E402
+from oracle.data_cases import build_case, build_sal_case, phoneme_tokenizer, write_case, write_sal_case  # noqa: E402
 
 
 def dump_items(ds):
@@ -54,6 +54,34 @@ def main():
     with open(path, "w", encoding="utf-8") as f:
         json.dump(out, f, ensure_ascii=False)
     print("wrote", path, "items", len(items), "+", len(prestu), "bytes", os.path.getsize(path))
+    main_sal()
+
+
+def main_sal():
+    """PhonemeSaLDataset of the real reference on the SaL case -> tests/golden/data_phonemesal.json"""
+    from importlib import import_module
+    from core.data import PhonemeSaLDataset, textlayout_obj_adapt, textlayout_ocr_adapt
+    text = import_module("phoneme_vqa_b200.text")
+    case = build_sal_case()
+    with tempfile.TemporaryDirectory() as tmp:
+        ocr_root, obj_root, qa_df = write_sal_case(case, tmp)
+        ocr_df = textlayout_ocr_adapt(ocr_root, h_scale=1, w_scale=1).sort_values("image_id").reset_index(drop=True)
+        obj_df = textlayout_obj_adapt(obj_root, h_scale=1, w_scale=1).sort_values("image_id").reset_index(drop=True)
+        p = case["params"]
+        ds = PhonemeSaLDataset(qa_df, ocr_df, obj_df, StubT5Tokenizer(), text.FlatPhonemeTokenizer(), ocr_root, obj_root,
+                               p["ocr_hidden"], p["obj_hidden"], max_ocr_element=p["max_ocr_element"],
+                               max_ocr_length=p["max_ocr_length"], max_obj_element=p["max_obj_element"],
+                               max_obj_length=p["max_obj_length"], max_input_length=p["max_input_length"],
+                               max_output_length=p["max_output_length"])
+        items = dump_items(ds)
+        obj_rows = [{"image_id": float(r.image_id), "obj_labels": list(r.obj_labels),
+                     "obj_bboxes": [list(map(float, b)) for b in r.obj_bboxes]} for r in obj_df.itertuples()]
+    out = {"case": case, "n_items": len(items), "image_ids": [float(x) for x in ds.data["image_id"]], "items": items,
+           "obj_table": obj_rows}
+    path = os.path.join(ROOT, "tests", "golden", "data_phonemesal.json")
+    with open(path, "w", encoding="utf-8") as f:
+        json.dump(out, f, ensure_ascii=False)
+    print("wrote", path, "items", len(items), "bytes", os.path.getsize(path))
 
 
 if __name__ == "__main__":
