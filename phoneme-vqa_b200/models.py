@@ -294,19 +294,23 @@ class PhonemeLaTr(nn.Module, _VisionMixin):
 
     # -- reference :146-217 ---------------------------------------------------------
     def generate(self, pixel_values, coordinates, input_ids, src_attention_mask, ocr_attention_mask, tokenized_ocr,
-                 start_symbol, end_symbol, max_length=20, isgreedy=True, num_beam=2):
+                 start_symbol, end_symbol, max_length=20, isgreedy=True, num_beam=2, use_graph=False):
         return self.greedy_generate(pixel_values, coordinates, input_ids, src_attention_mask, ocr_attention_mask,
-                                    tokenized_ocr, start_symbol, end_symbol, max_length)
+                                    tokenized_ocr, start_symbol, end_symbol, max_length, use_graph=use_graph)
 
     @torch.no_grad()
     def greedy_generate(self, pixel_values, coordinates, input_ids, src_attention_mask, ocr_attention_mask,
-                        tokenized_ocr, start_symbol, end_symbol, max_len=100, use_cache=True):
+                        tokenized_ocr, start_symbol, end_symbol, max_len=100, use_cache=True, use_graph=False):
         """reference :169-217.  `use_cache=True` decodes incrementally with a key/value cache (SURVEY §8f rank 1);
-        `use_cache=False` re-runs the decoder over the growing prefix exactly like the reference loop."""
+        `use_cache=False` re-runs the decoder over the growing prefix exactly like the reference loop;
+        `use_graph=True` (with the cache) replays one captured CUDA graph per target position — a decode step is
+        ~100 small launches, i.e. launch-bound when issued from Python."""
         bz = input_ids.size(0)
         dev = input_ids.device
         enc, attention_mask = self._encode(pixel_values, coordinates, input_ids, ocr_attention_mask,
                                            src_attention_mask, tokenized_ocr)
+        if use_graph and use_cache and dev.type == "cuda":
+            return self._greedy_graphed(enc, attention_mask, start_symbol, end_symbol, max_len)
         ys = torch.tensor([[[start_symbol, 0, 0]]], dtype=torch.long, device=dev).repeat(bz, 1, 1)
         cache = self.decoder.new_cache(enc, max_len + 1, self.compute_dtype) if use_cache else None
         pe = self.positional_encoding.pos_embedding
@@ -324,6 +328,71 @@ class PhonemeLaTr(nn.Module, _VisionMixin):
             if torch.any(ys[:, :, 0] == end_symbol, dim=1).sum() == bz:
                 break
         return ys
+
+    def _decode_step_ids(self, tok, t, cache, attention_mask):
+        """one cached greedy step: last emitted triples (B,1,3) at target position t -> next triples (B,3)"""
+        emb = self.tgt_tok_emb(tok, self.positional_encoding.pos_embedding[:, t:t + 1], out_dtype=torch.float32)
+        cache.len = t
+        out = self.decoder.step(emb, cache, attention_mask, self.compute_dtype)
+        on, rh, to = self._heads(out.to(self.compute_dtype))      # like the reference, no shared_lm_head here
+        return torch.stack([on[:, -1].float().argmax(-1), rh[:, -1].float().argmax(-1), to[:, -1].float().argmax(-1)], dim=-1)
+
+    @torch.no_grad()
+    def _greedy_graphed(self, enc, attention_mask, start_symbol, end_symbol, max_len, check_every=4):
+        """Cached greedy decoding with one CUDA graph per target position.  The workspace (token buffer, id
+        buffer, K/V caches, mask) is address-stable and kept on the model object per (batch, memory length,
+        max_len, dtype, parameter storage); graphs are captured the first time a position is reached and replayed
+        afterwards.  Termination is checked every `check_every` positions and the result is cut where the
+        reference loop would have stopped, so the returned ids are the reference's."""
+        bz, S, _ = enc.shape
+        dev = enc.device
+        key = (bz, S, max_len, self.compute_dtype, str(dev), next(self.decoder.parameters()).data_ptr())
+        ws = self.__dict__.get("_decode_ws")
+        if ws is None or ws["key"] != key:
+            ws = {"key": key, "graphs": {}, "pool": torch.cuda.graph_pool_handle(),
+                  "tok": torch.zeros((bz, 1, 3), dtype=torch.long, device=dev),
+                  "ys": torch.zeros((bz, max_len + 1, 3), dtype=torch.long, device=dev),
+                  "mask": torch.zeros((bz, S), dtype=torch.float32, device=dev),
+                  "cache": self.decoder.new_cache(enc, max_len + 1, self.compute_dtype)}
+            self.__dict__["_decode_ws"] = ws
+        else:
+            ws["cache"].set_memory(enc.to(self.compute_dtype))
+        ws["mask"].copy_(attention_mask.to(torch.float32))
+        start = torch.tensor([start_symbol, 0, 0], dtype=torch.long, device=dev)
+        ws["tok"].copy_(start.expand(bz, 1, 3))
+        ws["ys"].zero_()
+        ws["ys"][:, 0] = start
+
+        def body(t):
+            nxt = self._decode_step_ids(ws["tok"], t, ws["cache"], ws["mask"])
+            ws["ys"][:, t + 1].copy_(nxt)
+            ws["tok"].copy_(nxt.view(bz, 1, 3))
+
+        n_done = max_len
+        for t in range(max_len):
+            g = ws["graphs"].get(t)
+            if g is None:
+                # eager once (lazy initialisations, kernel attributes) on a side stream, rewind, then capture
+                tok0 = ws["tok"].clone()
+                side = torch.cuda.Stream(dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    body(t)
+                torch.cuda.current_stream(dev).wait_stream(side)
+                ws["tok"].copy_(tok0)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=ws["pool"]):
+                    body(t)
+                ws["graphs"][t] = g
+            g.replay()
+            if (t + 1) % check_every == 0 or t + 1 == max_len:
+                ended = ws["ys"][:, :t + 2, 0] == end_symbol
+                if bool(ended.any(dim=1).all()):
+                    # the reference stops after the first position at which every row has emitted <eos>
+                    first = torch.where(ended, torch.arange(t + 2, device=dev)[None], t + 2).min(dim=1).values
+                    n_done = int(first.max())
+                    break
+        return ws["ys"][:, :n_done + 1].clone()
 
 
 class PhonemePreSTU(nn.Module, _VisionMixin):

@@ -609,13 +609,21 @@ class DecoderCache:
         B, S, d = memory.shape
         l0 = layers[0]
         H, D = l0.self_attn.num_heads, l0.self_attn.head_dim
+        self.layers = layers
         self.len = 0
         self.max_len = max_len
         self.self_kv = [torch.empty((B, max_len, 2, H, D), dtype=compute_dtype, device=memory.device) for _ in layers]
-        self.mem_kv = []
-        for layer in layers:
+        self.mem_kv = [torch.empty((B, S, 2, H, D), dtype=compute_dtype, device=memory.device) for _ in layers]
+        self.set_memory(memory)
+
+    @torch.no_grad()
+    def set_memory(self, memory):
+        """project a new encoder memory into the (address-stable) cross-attention K/V buffers and rewind"""
+        B, S, d = memory.shape
+        for buf, layer in zip(self.mem_kv, self.layers):
             ca = layer.multihead_attn
-            self.mem_kv.append(_lin_rows(memory, ca.in_proj_weight, ca.in_proj_bias, d, 3 * d).view(B, S, 2, H, D))
+            buf.copy_(_lin_rows(memory.to(buf.dtype), ca.in_proj_weight, ca.in_proj_bias, d, 3 * d).view(buf.shape))
+        self.len = 0
 
 
 class _DecoderStack(nn.Module):
@@ -672,24 +680,36 @@ class BaseDecoder(nn.Module):
         B, _, d = x.shape
         t = cache.len
         assert t < cache.max_len, "decoder cache is full"
+        fused = d % 8 == 0 and d <= 1024
+        lp = compute_dtype == torch.bfloat16
+
+        def tail(x, upd, norm):
+            """norm(x + upd) -> (fp32 stream, compute-dtype copy): the same fused launch the full layer pass uses"""
+            if fused:
+                y, y_lp = ops.add_dropout_layer_norm(x, upd, norm.weight, norm.bias, norm.eps, 0.0, False, want_lp=lp)
+                return y, (y_lp if lp else y)
+            y = F.layer_norm(x + upd.float(), (d,), norm.weight, norm.bias, norm.eps)
+            return y, y.to(compute_dtype)
+
+        xc = x.to(compute_dtype)
         for li, layer in enumerate(self.decoder.layers):
             sa, ca = layer.self_attn, layer.multihead_attn
             H, D = sa.num_heads, sa.head_dim
             scale = 1.0 / math.sqrt(D)
-            qkv = _lin(x.to(compute_dtype), sa.in_proj_weight, sa.in_proj_bias).view(B, 1, 3, H, D)
+            qkv = _lin(xc, sa.in_proj_weight, sa.in_proj_bias).view(B, 1, 3, H, D)
             cache.self_kv[li][:, t] = qkv[:, 0, 1:]
             kv = cache.self_kv[li][:, : t + 1]
             a, _ = ops.attention_fwd_raw(qkv[:, :, 0].contiguous(), kv[:, :, 0], kv[:, :, 1], scale)
             a = _lin(a.reshape(B, 1, d), sa.out_proj.weight, sa.out_proj.bias)
-            x = F.layer_norm(x + a.float(), (d,), layer.norm1.weight, layer.norm1.bias, layer.norm1.eps)
-            q = _lin_rows(x.to(compute_dtype), ca.in_proj_weight, ca.in_proj_bias, 0, d).view(B, 1, H, D)
+            x, xc = tail(x, a, layer.norm1)
+            q = _lin_rows(xc, ca.in_proj_weight, ca.in_proj_bias, 0, d).view(B, 1, H, D)
             mkv = cache.mem_kv[li]
             c, _ = ops.attention_fwd_raw(q, mkv[:, :, 0], mkv[:, :, 1], scale, None, mka)
             c = _lin(c.reshape(B, 1, d), ca.out_proj.weight, ca.out_proj.bias)
-            x = F.layer_norm(x + c.float(), (d,), layer.norm2.weight, layer.norm2.bias, layer.norm2.eps)
-            h = torch.relu(_lin(x.to(compute_dtype), layer.linear1.weight, layer.linear1.bias))
+            x, xc = tail(x, c, layer.norm2)
+            h = torch.relu(_lin(xc, layer.linear1.weight, layer.linear1.bias))
             h = _lin(h, layer.linear2.weight, layer.linear2.bias)
-            x = F.layer_norm(x + h.float(), (d,), layer.norm3.weight, layer.norm3.bias, layer.norm3.eps)
+            x, xc = tail(x, h, layer.norm3)
         cache.len = t + 1
         return x
 

@@ -257,6 +257,40 @@ def test_greedy_decoding_with_kv_cache_matches_uncached_reference_loop():
             assert np.array_equal(cached[:, :7].cpu().numpy(), g["greedy_ids"])       # the reference's own ids
 
 
+def test_graphed_greedy_decoding_matches_eager_and_reference_ids():
+    """one CUDA graph per target position: same ids as the eager cached loop (and, in fp32, as the reference's own
+    greedy ids), including the early stop; the graphs are reused for later batches (new memory, same shapes)."""
+    g = np.load(os.path.join(GOLD, "model_phonemelatr_tiny.npz"))
+    cfg = ref_model.tiny_config()
+    _, model = _pair(cfg)
+    model.eval()
+    keys = ("pixel_values", "coordinates", "input_ids", "src_attention_mask", "ocr_attention_mask", "tokenized_ocr")
+    batches = [[ref_model.synthetic_batch(3, cfg, T=9, L_ocr=12, L_q=6, V_sub=VOCAB, seed=sd, image=32)[k].to(DEV) for k in keys]
+               for sd in (7, 8, 7)]
+    for dtype in (torch.float32, torch.bfloat16):
+        model.set_compute_dtype(dtype)
+        # (a) with the <eos> stop: cut exactly where the reference loop stops
+        for i, args in enumerate(batches):
+            eager = model.greedy_generate(*args, start_symbol=3, end_symbol=4, max_len=12, use_cache=True)
+            graphed = model.greedy_generate(*args, start_symbol=3, end_symbol=4, max_len=12, use_cache=True, use_graph=True)
+            assert graphed.shape == eager.shape and torch.equal(graphed, eager), (dtype, i)
+            if dtype == torch.float32 and i == 0:
+                assert np.array_equal(graphed[:, :7].cpu().numpy(), g["greedy_ids"])
+        ws = model._decode_ws
+        n_graphs = len(ws["graphs"])
+        assert 0 < n_graphs <= 12
+        # (b) never-ending case: every position comes out of a graph; the workspace of (a) is replaced (max_len differs)
+        for i, args in enumerate(batches):
+            full_e = model.greedy_generate(*args, start_symbol=3, end_symbol=-1, max_len=10, use_cache=True)
+            full_g = model.greedy_generate(*args, start_symbol=3, end_symbol=-1, max_len=10, use_cache=True, use_graph=True)
+            assert full_g.shape == (3, 11, 3) and torch.equal(full_g, full_e), (dtype, i)
+            if i == 0:
+                ws10 = model._decode_ws
+                assert ws10 is not ws and len(ws10["graphs"]) == 10
+            else:
+                assert model._decode_ws is ws10 and len(ws10["graphs"]) == 10      # replayed, not re-captured
+
+
 def test_frozen_vit_bf16_forward_matches_hf_tower():
     """the lean bf16 ViT forward (fused qkv, tcgen05 attention, fused add+LayerNorm) against the HF ViTModel
     it restates: fp32 HF output as the truth, HF-in-bf16 as the yardstick for the allowed error."""

@@ -22,14 +22,14 @@ b = synthetic.phoneme_latr_batch(B, cfg.vocab_size, device=dev)
 args = (b["pixel_values"], b["coordinates"], b["input_ids"], b["src_attention_mask"], b["ocr_attention_mask"],
         b["tokenized_ocr"], synthetic.BOS_ID, -1)
 out = {"B": B, "max_len": L}
-for name, use_cache in (("kv_cache", True), ("reference_loop", False)):
+for name, use_cache, use_graph in (("kv_cache_graphs", True, True), ("kv_cache", True, False), ("reference_loop", False, False)):
     for _ in range(2):
-        ys = model.greedy_generate(*args, max_len=L, use_cache=use_cache)
+        ys = model.greedy_generate(*args, max_len=L, use_cache=use_cache, use_graph=use_graph)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(3):
-        ys = model.greedy_generate(*args, max_len=L, use_cache=use_cache)
+        ys = model.greedy_generate(*args, max_len=L, use_cache=use_cache, use_graph=use_graph)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
