@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, "/root/reference")
 
-from oracle.stub_tokenizer import StubT5Tokenizer  # noqa: E402
+from oracle.stub_tokenizer import StubFlatTokenizer, StubT5Tokenizer  # noqa: E402
 
 from oracle.data_cases import build_case, build_sal_case, phoneme_tokenizer, write_case, write_sal_case  # noqa: E402
 
@@ -34,7 +34,8 @@ def dump_items(ds):
 
 
 def main():
-    from core.data import PhonemeLaTrDataset, PhonemePreSTUDataset, textlayout_ocr_adapt      # the real reference
+    from core.data import (CustomizedLaTrDataset, CustomizedPreSTUDataset, LaTrDataset, PhonemeLaTrDataset,      # the real
+                           PhonemePreSTUDataset, textlayout_ocr_adapt)                                           # reference
     case = build_case()
     case["images"] = {str(k): v for k, v in case["images"].items()}
     with tempfile.TemporaryDirectory() as tmp:
@@ -46,10 +47,21 @@ def main():
         ds = PhonemeLaTrDataset(qa_df, ocr_df, StubT5Tokenizer(), phoneme_tokenizer(case, tmp), feat_root, **kw)
         items = dump_items(ds)
         prestu = dump_items(PhonemePreSTUDataset(qa_df, ocr_df, StubT5Tokenizer(), phoneme_tokenizer(case, tmp), feat_root, **kw))
+        variants = {
+            "LaTrDataset": dump_items(LaTrDataset(qa_df, ocr_df, StubT5Tokenizer(), feat_root, **kw)),
+            "CustomizedLaTrDataset": dump_items(CustomizedLaTrDataset(qa_df, ocr_df, StubT5Tokenizer(), StubFlatTokenizer(), feat_root, **kw)),
+            # PreSTUDataset cannot be instantiated in the snapshot: data_processing calls create_properties but the
+            # class defines create_features (core/data/PreSTUDataset.py:69,87) -> no golden, parity unpinned
+            "CustomizedPreSTUDataset": dump_items(CustomizedPreSTUDataset(qa_df, ocr_df, StubT5Tokenizer(), StubFlatTokenizer(), feat_root, **kw)),
+        }
         ocr_rows = [{"image_id": float(r.image_id), "texts": list(r.texts), "bboxes": [list(map(float, b)) for b in r.bboxes]}
                     for r in ocr_df.itertuples()]
     out = {"case": case, "n_items": len(items), "image_ids": [float(x) for x in ds.data["image_id"]], "items": items,
            "items_prestu": prestu, "ocr_table": ocr_rows}
+    vpath = os.path.join(ROOT, "tests", "golden", "data_variants.json")
+    with open(vpath, "w", encoding="utf-8") as f:
+        json.dump(variants, f, ensure_ascii=False)
+    print("wrote", vpath, {k: len(v) for k, v in variants.items()}, "bytes", os.path.getsize(vpath))
     path = os.path.join(ROOT, "tests", "golden", "data_phonemelatr.json")
     with open(path, "w", encoding="utf-8") as f:
         json.dump(out, f, ensure_ascii=False)

@@ -70,3 +70,18 @@ class StubT5Tokenizer:
             ids = ids + [self.pad_token_id] * n
             mask = mask + [0] * n
         return _Encoding(input_ids=ids, attention_mask=mask)
+
+
+class StubFlatTokenizer:
+    """call contract of the reference's char / byte / BPE decode tokenizers (core/tokenizer/byte_tokenizer.py:1-46):
+    `tok(text, max_length=None)` -> [bos] + ids + [eos] + [pad]*, attribute `pad_id`.  UTF-8 bytes as ids."""
+    pad_id, bos_id, eos_id = 256, 257, 258
+
+    def __call__(self, text, max_length=None, padding=True, add_special_tokens=True):
+        ids = list(text.encode("utf-8"))
+        if max_length is not None:
+            ids = ids[:max_length - 2]
+        ids = [self.bos_id] + ids + [self.eos_id]
+        if max_length is not None and padding:
+            ids += [self.pad_id] * (max_length - len(ids))
+        return ids
