@@ -72,7 +72,7 @@ def main():
 def main_sal():
     """PhonemeSaLDataset of the real reference on the SaL case -> tests/golden/data_phonemesal.json"""
     from importlib import import_module
-    from core.data import PhonemeSaLDataset, textlayout_obj_adapt, textlayout_ocr_adapt
+    from core.data import CustomizedSaLDataset, PhonemeSaLDataset, SaLDataset, textlayout_obj_adapt, textlayout_ocr_adapt
     text = import_module("phoneme_vqa_b200.text")
     case = build_sal_case()
     with tempfile.TemporaryDirectory() as tmp:
@@ -86,10 +86,19 @@ def main_sal():
                                max_obj_length=p["max_obj_length"], max_input_length=p["max_input_length"],
                                max_output_length=p["max_output_length"])
         items = dump_items(ds)
+        skw = dict(max_ocr_element=p["max_ocr_element"], max_ocr_length=p["max_ocr_length"], max_obj_element=p["max_obj_element"],
+                   max_obj_length=p["max_obj_length"], max_input_length=p["max_input_length"],
+                   max_output_length=p["max_output_length"])
+        sal_variants = {
+            "SaLDataset": dump_items(SaLDataset(qa_df, ocr_df, obj_df, StubT5Tokenizer(), ocr_root, obj_root,
+                                                p["ocr_hidden"], p["obj_hidden"], **skw)),
+            "CustomizedSaLDataset": dump_items(CustomizedSaLDataset(qa_df, ocr_df, obj_df, StubT5Tokenizer(), StubFlatTokenizer(),
+                                                                    ocr_root, obj_root, p["ocr_hidden"], p["obj_hidden"], **skw)),
+        }
         obj_rows = [{"image_id": float(r.image_id), "obj_labels": list(r.obj_labels),
                      "obj_bboxes": [list(map(float, b)) for b in r.obj_bboxes]} for r in obj_df.itertuples()]
     out = {"case": case, "n_items": len(items), "image_ids": [float(x) for x in ds.data["image_id"]], "items": items,
-           "obj_table": obj_rows}
+           "obj_table": obj_rows, "variants": sal_variants}
     path = os.path.join(ROOT, "tests", "golden", "data_phonemesal.json")
     with open(path, "w", encoding="utf-8") as f:
         json.dump(out, f, ensure_ascii=False)
