@@ -483,3 +483,198 @@ def synthetic_batch(B, cfg, T=127, L_ocr=100, L_q=30, V_sub=(84, 187, 7), seed=1
     pix = torch.randn(B, 3, image, image, generator=g)
     return {"pixel_values": pix, "coordinates": coords, "input_ids": q, "src_attention_mask": qm,
             "label_ids": labels, "label_attention_mask": lmask, "tokenized_ocr": ocr, "ocr_attention_mask": om}
+
+
+# ----------------------------------------------------------------------------------
+# flat-vocabulary (Customized*) batches and the executors' loss: CrossEntropyLoss(ignore_index=pad) on
+# logits[:, :-1] vs labels[:, 1:]  (core/executor/CustomizedLaTr_Executor.py:160-182, PreSTU_Executor.py:135-153)
+# ----------------------------------------------------------------------------------
+def flat_batch(B, cfg, T=13, L_ocr=12, L_q=6, vocab=50, seed=21, image=32, pad_id=0, bos_id=1, eos_id=2):
+    """CustomizedLaTrDataset fields (core/data/CustomizedLaTrDataset.py:40-58): int64 src / ocr masks, flat label
+    ids, label mask = (ids == pad) as bool."""
+    b = synthetic_batch(B, cfg, T=T, L_ocr=L_ocr, L_q=L_q, seed=seed, image=image)
+    g = torch.Generator().manual_seed(seed + 1)
+    labels = torch.full((B, T + 1), pad_id, dtype=torch.long)
+    for i in range(B):
+        n = int(torch.randint(2, T, (1,), generator=g))
+        labels[i, 0] = bos_id
+        labels[i, 1:n] = torch.randint(3, vocab, (n - 1,), generator=g)
+        labels[i, n] = eos_id
+    b["label_ids"], b["label_attention_mask"] = labels, labels == pad_id
+    b["src_attention_mask"] = b["src_attention_mask"].long()
+    b["ocr_attention_mask"] = b["ocr_attention_mask"].long()
+    return b
+
+
+LATR_KEYS = ("pixel_values", "coordinates", "input_ids", "src_attention_mask", "ocr_attention_mask", "tokenized_ocr")
+PRESTU_KEYS = ("pixel_values", "input_ids", "src_attention_mask")
+
+
+def flat_loss(model, batch, keys, pad_id=0):
+    labels = batch["label_ids"]
+    logits = model(labels=labels[:, :-1], label_attention_mask=batch["label_attention_mask"][:, :-1],
+                   **{k: batch[k] for k in keys})
+    return nn.functional.cross_entropy(logits.reshape(-1, logits.shape[-1]), labels[:, 1:].reshape(-1),
+                                       ignore_index=pad_id)
+
+
+def prestu_batch(B, cfg, T=19, L_q=14, seed=9, image=32):
+    """PreSTUDataset fields: question + OCR text packed into input_ids, int64 masks, T5 labels (1 = valid)."""
+    b = latr_batch(B, cfg, T=T, L_ocr=4, L_q=L_q, seed=seed, image=image)
+    b["src_attention_mask"] = b["src_attention_mask"].long()
+    return {k: b[k] for k in PRESTU_KEYS + ("label_ids", "label_attention_mask")}
+
+
+# ----------------------------------------------------------------------------------
+# SaL (core/model/SaL.py:24-140) and CustomizedSaL (core/model/CustomizedSaL.py:29-335) restated like PhonemeSaL
+# above: HF modules composed as the reference composes them, the T52DStack encoder as a loop over HF T5Block with the
+# external bias.  State_dict layouts are pinned to the reference's constructed modules (tests/golden/
+# sal_family_layouts.npz); the forward cannot be run from the reference under transformers 5.5 (SURVEY D8).
+# ----------------------------------------------------------------------------------
+def _sal_encoder_inputs(m, shared, b):
+    obj = (m.obj_feature_layer_norm(m.obj_feature_projector(b["obj_features"]))
+           + m.obj_feature_layer_norm(m.obj_bbox_projector(b["obj_coordinates"])) + shared(b["tokenized_obj"]))
+    ocr = (m.ocr_feature_layer_norm(m.ocr_feature_projector(b["ocr_features"]))
+           + m.ocr_feature_layer_norm(m.ocr_bbox_projector(b["ocr_coordinates"])) + shared(b["tokenized_ocr"]))
+    feat = torch.cat([shared(b["input_ids"]), ocr, obj], dim=1)
+    mask = torch.cat([b["src_attention_mask"], b["ocr_attention_mask"], b["obj_attention_mask"]], dim=1)
+    bias = sal_position_bias(m.rel2Dbias.Relative1D.relative_attention_bias.weight,
+                             m.rel2Dbias.SCP.relative_attention_bias.weight, feat.shape[1],
+                             b["ocr_coordinates"], b["max_ques"], b["max_ocr"])
+    return feat, mask, bias
+
+
+def _external_bias_stack(stack, feat, bias):
+    h = stack.dropout(feat)
+    for blk in stack.block:
+        h = blk(h, attention_mask=None, position_bias=bias)[0]
+    return stack.dropout(stack.final_layer_norm(h))
+
+
+def _sal_projectors(m, config, obj_dropout, ocr_dropout):
+    from transformers.models.t5.modeling_t5 import T5LayerNorm
+    d = config.d_model
+    m.rel2Dbias = _BiasAggregated(config.num_heads)
+    m.obj_dropout = nn.Dropout(obj_dropout)
+    m.obj_feature_projector = nn.Linear(config.obj_hidden, d)
+    m.obj_bbox_projector = nn.Linear(4, d)
+    m.obj_feature_layer_norm = T5LayerNorm(d)
+    m.ocr_dropout = nn.Dropout(ocr_dropout)
+    m.ocr_feature_projector = nn.Linear(config.ocr_hidden, d)
+    m.ocr_bbox_projector = nn.Linear(4, d)
+    m.ocr_feature_layer_norm = T5LayerNorm(d)
+
+
+class SaL(nn.Module):
+    def __init__(self, config, obj_dropout=0.1, ocr_dropout=0.1):
+        super().__init__()
+        self.config = config
+        self.backbone = T5ForConditionalGeneration(config)
+        self.backbone.resize_token_embeddings(config.new_token_embedding_size)
+        _sal_projectors(self, config, obj_dropout, ocr_dropout)
+
+    def _encode(self, b):
+        feat, _, bias = _sal_encoder_inputs(self, self.backbone.shared, b)
+        return _external_bias_stack(self.backbone.encoder, feat, bias)
+
+    def forward(self, b):
+        enc = self._encode(b)
+        dec = self.backbone.decoder(encoder_hidden_states=enc, inputs_embeds=self.backbone.shared(b["label_ids"]),
+                                    attention_mask=b["label_attention_mask"]).last_hidden_state
+        return self.backbone.lm_head(dec)
+
+    @torch.no_grad()
+    def generate(self, b, max_length=20):
+        """HF greedy search from the encoder output (what `backbone.generate(inputs_embeds=..., position_bias=...)`
+        does in the reference: SaL.py:136-140)."""
+        from transformers.modeling_outputs import BaseModelOutput
+        feat, _, bias = _sal_encoder_inputs(self, self.backbone.shared, b)
+        enc = _external_bias_stack(self.backbone.encoder, feat, bias)
+        return self.backbone.generate(inputs_embeds=feat, encoder_outputs=BaseModelOutput(last_hidden_state=enc),
+                                      max_length=max_length, do_sample=False, num_beams=1)
+
+
+def sal_t5_batch(B, cfg, T=11, seed=5, **kw):
+    """SaLDataset fields (core/data/SaLDataset.py): T5 labels "<pad> answer </s>" with an int64 1 = valid mask."""
+    b = sal_batch(B, cfg, T=T, seed=seed, **kw)
+    g = torch.Generator().manual_seed(seed + 100)
+    labels = torch.zeros(B, T + 1, dtype=torch.long)
+    mask = torch.zeros(B, T + 1, dtype=torch.long)
+    for i in range(B):
+        n = int(torch.randint(2, T, (1,), generator=g))
+        labels[i, 1:n] = torch.randint(3, cfg.new_token_embedding_size, (n - 1,), generator=g)
+        labels[i, n] = 1
+        mask[i, : n + 1] = 1
+    b.pop("shifted_right_label_ids")
+    b["label_ids_full"], b["label_mask_full"] = labels, mask
+    b["label_ids"], b["label_attention_mask"] = labels[:, :-1], mask[:, :-1]
+    return b
+
+
+def sal_t5_loss(model, b, pad_id=0, as_kwargs=False):
+    """core/executor/SaL_Executor.py:190-221"""
+    if as_kwargs:
+        logits = model(**{k: v for k, v in b.items() if not k.endswith("_full")})
+    else:
+        logits = model(b)
+    return nn.functional.cross_entropy(logits.reshape(-1, logits.shape[-1]), b["label_ids_full"][:, 1:].reshape(-1),
+                                       ignore_index=pad_id)
+
+
+class _RefTokenEmbedding(nn.Module):
+    # core/model/modules/transformer_utils.py:27-36
+    def __init__(self, vocab_size, emb_size):
+        super().__init__()
+        self.embedding = nn.Embedding(vocab_size, emb_size)
+        self.emb_size = emb_size
+
+    def forward(self, tokens):
+        return self.embedding(tokens.long()) * math.sqrt(self.emb_size)
+
+
+class CustomizedSaL(nn.Module):
+    def __init__(self, config, tgt_vocab_size, obj_dropout=0.1, ocr_dropout=0.1):
+        super().__init__()
+        self.config = config
+        self.encoder = T5EncoderModel(config)
+        self.encoder.resize_token_embeddings(config.new_token_embedding_size)
+        _sal_projectors(self, config, obj_dropout, ocr_dropout)
+        d = config.d_model
+        self.tgt_tok_emb = _RefTokenEmbedding(tgt_vocab_size, d)
+        self.positional_encoding = SinusoidalPositionalEncoding(d, dropout=0.1)
+        self.decoder = BaseDecoder(d, config.num_decoder_layers, config.n_head)
+        self.lm_head = nn.Linear(d, tgt_vocab_size)
+
+    def _encode(self, b):
+        feat, mask, bias = _sal_encoder_inputs(self, self.encoder.shared, b)
+        return _external_bias_stack(self.encoder.encoder, feat, bias), mask
+
+    def decode(self, labels, enc, enc_mask, label_mask=None):
+        emb = self.positional_encoding(self.tgt_tok_emb(labels))
+        return self.decoder(emb, enc, tgt_mask=PhonemeLaTr._square_mask(labels.size(1), labels.device),
+                            memory_key_padding_mask=enc_mask, tgt_key_padding_mask=label_mask)
+
+    def forward(self, b):
+        enc, mask = self._encode(b)
+        return self.lm_head(self.decode(b["label_ids"], enc, mask, b["label_attention_mask"]))
+
+    @torch.no_grad()
+    def greedy_generate(self, b, start_symbol, end_symbol, max_len=100):
+        enc, mask = self._encode(b)
+        bz = b["input_ids"].size(0)
+        ys = torch.ones(bz, 1).fill_(start_symbol).type(torch.long)
+        for _ in range(max_len):
+            prob = self.lm_head(self.decode(ys, enc, mask)[:, -1])
+            ys = torch.cat([ys, torch.argmax(prob, dim=-1).view(bz, -1)], dim=1)
+            if torch.any(ys == end_symbol, dim=1).sum() == bz:
+                break
+        return ys
+
+
+def customized_sal_batch(B, cfg, T=11, vocab=50, seed=5, **kw):
+    """CustomizedSaLDataset fields: flat label ids, label mask = pad positions (bool), float encoder masks."""
+    b = sal_batch(B, cfg, T=T, vocab=vocab, seed=seed, **kw)
+    full = torch.cat([b["label_ids"], b.pop("shifted_right_label_ids")[:, -1:]], dim=1)
+    b["label_ids_full"] = full
+    b["label_ids"], b["label_attention_mask"] = full[:, :-1], full[:, :-1] == 0
+    return b

@@ -19,9 +19,11 @@ import torch.nn.functional as F
 from . import ops
 from .modules import (SHADOWS, BaseDecoder, RelativePositionBias1D, RelativePositionBiasAggregated,
                       SCPRelativePositionBias, T5LayerNorm, PhonemeEmbedding, SinusoidalPositionalEncoding, SpatialModule, T5EncoderModel,
-                      T5ForConditionalGeneration, _lin)
+                      T5ForConditionalGeneration, TokenEmbedding, _lin)
 
-__all__ = ["LaTr_config", "CustomizedLaTr_config", "CustomizedPreSTU_config", "PhonemeLaTr", "PhonemePreSTU", "LaTr", "PhonemeSaL", "CustomizedSaL_config"]
+__all__ = ["LaTr_config", "PreSTU_config", "SaL_config", "CustomizedLaTr_config", "CustomizedPreSTU_config",
+           "CustomizedSaL_config", "LaTr", "PreSTU", "SaL", "CustomizedLaTr", "CustomizedPreSTU", "CustomizedSaL",
+           "PhonemeLaTr", "PhonemePreSTU", "PhonemeSaL"]
 
 
 def _random_init(config) -> bool:
@@ -42,6 +44,23 @@ class LaTr_config:
         return model_config
 
 
+# reference: core/model/PreSTU.py:5-11
+class PreSTU_config:
+    def build(self, config):
+        model_config = _auto_config(config.backbone_name)
+        model_config.update({"vit_model": config.vit_model_name})
+        return model_config
+
+
+# reference: core/model/SaL.py:13-21
+class SaL_config:
+    def build(self, config, new_token_embedding_size):
+        model_config = _auto_config(config.backbone_name)
+        model_config.update({"ocr_hidden": config.ocr_hidden, "obj_hidden": config.obj_hidden,
+                             "new_token_embedding_size": new_token_embedding_size})
+        return model_config
+
+
 # reference: core/model/PhonemeLaTr.py:6-15 (same class in CustomizedLaTr.py)
 class CustomizedLaTr_config:
     def build(self, config):
@@ -53,10 +72,11 @@ class CustomizedLaTr_config:
         return model_config
 
 
-# reference: core/model/PhonemePreSTU.py:6-14
+# reference: core/model/CustomizedPreSTU.py:6-14 (backbone_name) / core/model/PhonemePreSTU.py:6-14 (encoder_name);
+# every YAML that selects these models carries both keys with the same value
 class CustomizedPreSTU_config:
     def build(self, config):
-        model_config = _auto_config(config.encoder_name)
+        model_config = _auto_config(getattr(config, "backbone_name", None) or config.encoder_name)
         model_config.update({"vit_model": config.vit_model_name,
                              "num_decoder_layers": config.num_decoder_layers,
                              "n_head": config.n_head})
@@ -438,6 +458,36 @@ class PhonemePreSTU(nn.Module, _VisionMixin):
         on, rh, to = self._heads(h)
         return on.float(), rh.float(), to.float()
 
+    # The call the executor makes (core/executor/PhonemePreSTU_Executor.py:41-49): the class's own `generate`
+    # (PhonemePreSTU.py:103-199) still carries PhonemeLaTr's argument list and cannot run, so the
+    # intended behaviour is PhonemeLaTr's greedy loop on this model's encoder; isgreedy / num_beam are ignored there.
+    def generate(self, pixel_values, input_ids, src_attention_mask, start_symbol, end_symbol, max_length=20,
+                 isgreedy=True, num_beam=2):
+        return self.greedy_generate(pixel_values, input_ids, src_attention_mask, start_symbol, end_symbol, max_length)
+
+    @torch.no_grad()
+    def greedy_generate(self, pixel_values, input_ids, src_attention_mask, start_symbol, end_symbol, max_len=100,
+                        use_cache=True):
+        bz, dev = input_ids.size(0), input_ids.device
+        inputs_embeds, attention_mask = self._calculate_embedding(pixel_values, input_ids, src_attention_mask)
+        enc = self.encoder.encoder(inputs_embeds, attention_mask, compute_dtype=self.compute_dtype)
+        ys = torch.tensor([[[start_symbol, 0, 0]]], dtype=torch.long, device=dev).repeat(bz, 1, 1)
+        cache = self.decoder.new_cache(enc, max_len + 1, self.compute_dtype) if use_cache else None
+        pe = self.positional_encoding.pos_embedding
+        for t in range(max_len):
+            if use_cache:
+                emb = self.tgt_tok_emb(ys[:, -1:], pe[:, t:t + 1], out_dtype=torch.float32)
+                out = self.decoder.step(emb, cache, attention_mask, self.compute_dtype)
+            else:
+                out = self.decode(ys, enc, attention_mask)[:, -1:]
+            on, rh, to = self._heads(out.to(self.compute_dtype))       # no shared_lm_head, like PhonemeLaTr.py:195-205
+            nxt = torch.stack([on[:, -1].float().argmax(-1), rh[:, -1].float().argmax(-1),
+                               to[:, -1].float().argmax(-1)], dim=-1)
+            ys = torch.cat([ys, nxt.unsqueeze(1)], dim=1)
+            if torch.any(ys[:, :, 0] == end_symbol, dim=1).sum() == bz:
+                break
+        return ys
+
 
 def _load_pretrained_t5(backbone: T5ForConditionalGeneration, config):
     if _random_init(config):
@@ -506,22 +556,28 @@ class LaTr(nn.Module, _VisionMixin):
         inputs_embeds, _ = self.calculate_embedding(pixel_values, coordinates, input_ids, ocr_attention_mask,
                                                     src_attention_mask, tokenized_ocr)
         enc = self.backbone.encoder(inputs_embeds, None, compute_dtype=self.compute_dtype)
-        cfg = self.config
-        start = cfg.decoder_start_token_id if cfg.decoder_start_token_id is not None else cfg.pad_token_id
-        B = inputs_embeds.shape[0]
-        ys = torch.full((B, 1), start, dtype=torch.long, device=inputs_embeds.device)
-        done = torch.zeros(B, dtype=torch.bool, device=ys.device)
-        for _ in range(max_length - 1):
-            tgt = torch.nn.functional.embedding(ys, self.backbone.shared.weight)
-            dec = self.backbone.decoder(tgt, None, compute_dtype=self.compute_dtype, memory=enc, memory_mask=None)
-            logits = _lin(dec[:, -1:].to(self.compute_dtype), self.backbone.lm_head.weight).float()
-            nxt = logits[:, -1].argmax(-1)
-            nxt = torch.where(done, torch.full_like(nxt, cfg.pad_token_id), nxt)
-            ys = torch.cat([ys, nxt[:, None]], dim=1)
-            done = done | (nxt == cfg.eos_token_id)
-            if bool(done.all()):
-                break
-        return ys
+        return _t5_greedy(self.backbone, self.config, enc, max_length, self.compute_dtype)
+
+
+def _t5_greedy(backbone, cfg, enc, max_length, compute_dtype):
+    """HF `generate(inputs_embeds=..., max_length=...)` with the default greedy settings: start from
+    decoder_start_token_id, at most max_length ids per row, finished rows are padded with pad_token_id, stop when
+    every row has emitted eos_token_id.  The decoder gets no encoder mask (the reference passes none)."""
+    start = cfg.decoder_start_token_id if cfg.decoder_start_token_id is not None else cfg.pad_token_id
+    B = enc.shape[0]
+    ys = torch.full((B, 1), start, dtype=torch.long, device=enc.device)
+    done = torch.zeros(B, dtype=torch.bool, device=ys.device)
+    for _ in range(max_length - 1):
+        tgt = torch.nn.functional.embedding(ys, backbone.shared.weight)
+        dec = backbone.decoder(tgt, None, compute_dtype=compute_dtype, memory=enc, memory_mask=None)
+        logits = _lin(dec[:, -1:].to(compute_dtype), backbone.lm_head.weight).float()
+        nxt = logits[:, -1].argmax(-1)
+        nxt = torch.where(done, torch.full_like(nxt, cfg.pad_token_id), nxt)
+        ys = torch.cat([ys, nxt[:, None]], dim=1)
+        done = done | (nxt == cfg.eos_token_id)
+        if bool(done.all()):
+            break
+    return ys
 
 
 # reference: core/model/PhonemeSaL.py:15-25
@@ -646,3 +702,437 @@ class PhonemeSaL(nn.Module):
             if bool(done.all()):
                 break
         return ys
+
+
+# ----------------------------------------------------------------------------------
+# the rest of the family: PreSTU / SaL (T5 encoder-decoder over the T5 vocabulary) and the Customized* classes
+# (T5 encoder + 4-layer target decoder over a flat char / byte / BPE vocabulary).  They are compositions of the
+# same kernels: K1 (fused multimodal embedding), K2 (T5 attention, with the in-kernel SCP bias for SaL), K3
+# (target decoder attention with additive float masks), the fused norm chains, and cuBLAS linears.
+# ----------------------------------------------------------------------------------
+def _resize_shared(holder, stack_owner, n, config):
+    """HF resize_token_embeddings on a model whose `shared` table is tied to the stacks' embed_tokens
+    (core/model/SaL.py:30, PhonemeSaL.py:41): first min(n, old) rows kept, new rows drawn like HF's init."""
+    old = holder.shared
+    if n is None or n == old.num_embeddings:
+        return
+    new = nn.Embedding(n, old.embedding_dim)
+    nn.init.normal_(new.weight, mean=0.0, std=config.initializer_factor)
+    k = min(n, old.num_embeddings)
+    new.weight.data[:k] = old.weight.data[:k]
+    holder.shared = new
+    for st in stack_owner:
+        st.embed_tokens = new
+
+
+class PreSTU(nn.Module, _VisionMixin):
+    """reference: core/model/PreSTU.py:13-66 — ViT tokens ‖ (question + OCR text) -> T5 encoder-decoder -> lm_head.
+    No layout branch; the ViT is NOT frozen (no freeze loop in the reference)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.compute_dtype = torch.float32
+        self.backbone = T5ForConditionalGeneration(config)
+        _load_pretrained_t5(self.backbone, config)
+        self.vit = _build_vit(config)
+        self.visual_projector = nn.Linear(self.vit.config.hidden_size, config.d_model)
+
+    # reference :48-56
+    def calculate_embedding(self, pixel_values, input_ids, src_attention_mask):
+        vit_tokens = self._vit_tokens(pixel_values)
+        img_feat = _lin(vit_tokens.to(self.compute_dtype), self.visual_projector.weight, self.visual_projector.bias)
+        return ops.embed_multimodal(img_feat, None, None, input_ids, None, src_attention_mask,
+                                    self.backbone.shared.weight, (), out_dtype=self.compute_dtype)
+
+    def _decoder_hidden(self, pixel_values, input_ids, labels, src_attention_mask, label_attention_mask):
+        inputs_embeds, attention_mask = self.calculate_embedding(pixel_values, input_ids, src_attention_mask)
+        enc = self.backbone.encoder(inputs_embeds, attention_mask, compute_dtype=self.compute_dtype)
+        tgt = torch.nn.functional.embedding(labels, self.backbone.shared.weight)
+        return self.backbone.decoder(tgt, label_attention_mask, compute_dtype=self.compute_dtype, memory=enc,
+                                     memory_mask=None)
+
+    # reference :24-46
+    def forward(self, pixel_values, input_ids, labels, src_attention_mask, label_attention_mask):
+        dec = self._decoder_hidden(pixel_values, input_ids, labels, src_attention_mask, label_attention_mask)
+        return _lin(dec.to(self.compute_dtype), self.backbone.lm_head.weight).float()
+
+    def forward_loss(self, pixel_values, input_ids, labels, src_attention_mask, label_attention_mask, targets,
+                     ignore_index):
+        """model forward + CrossEntropyLoss(ignore_index=pad) of core/executor/PreSTU_Executor.py without the
+        (N, V) logits (chunked lm_head + fused softmax / CE / dlogits)."""
+        dec = self._decoder_hidden(pixel_values, input_ids, labels, src_attention_mask, label_attention_mask)
+        h = dec.to(self.compute_dtype).reshape(-1, dec.shape[-1])
+        w = self.backbone.lm_head.weight
+        w_lp = SHADOWS.get([w], h.dtype) if h.dtype != w.dtype else None
+        return ops.vocab_head_ce(h, w, targets, ignore_index, w_lp=w_lp)
+
+    # reference :58-66
+    @torch.no_grad()
+    def generate(self, pixel_values, input_ids, src_attention_mask, max_length=20):
+        inputs_embeds, _ = self.calculate_embedding(pixel_values, input_ids, src_attention_mask)
+        enc = self.backbone.encoder(inputs_embeds, None, compute_dtype=self.compute_dtype)
+        return _t5_greedy(self.backbone, self.config, enc, max_length, self.compute_dtype)
+
+
+class _FlatTargetMixin:
+    """Target side shared by CustomizedLaTr / CustomizedPreSTU / CustomizedSaL: TokenEmbedding (x sqrt(d)) ->
+    sinusoidal PE + dropout -> BaseDecoder -> lm_head (with bias) over a flat vocabulary; greedy decoding (with a
+    key/value cache) and the reference's beam routine."""
+
+    def _init_flat_target(self, config, tgt_vocab_size):
+        d = config.d_model
+        self.tgt_tok_emb = TokenEmbedding(tgt_vocab_size, d)
+        self.positional_encoding = SinusoidalPositionalEncoding(d, dropout=0.1)
+        self.decoder = BaseDecoder(emb_size=d, num_layers=config.num_decoder_layers, n_head=config.n_head)
+        self.lm_head = nn.Linear(d, tgt_vocab_size)
+
+    # CustomizedLaTr.py:99-110, CustomizedPreSTU.py:60-70, CustomizedSaL.py:108-118
+    def decode(self, labels, encoder_outputs, encoder_attention_mask, label_attention_mask=None):
+        emb = self.positional_encoding(self.tgt_tok_emb(labels))
+        return self.decoder(emb, encoder_outputs, tgt_mask=None, memory_key_padding_mask=encoder_attention_mask,
+                            tgt_key_padding_mask=label_attention_mask, compute_dtype=self.compute_dtype, causal=True)
+
+    def _logits(self, dec):
+        return _lin(dec.to(self.compute_dtype), self.lm_head.weight, self.lm_head.bias).float()
+
+    @staticmethod
+    def _memory_mask_for_step(mask):
+        if mask is not None and mask.dtype == torch.bool:        # bool masks mask, float masks are additive (D14)
+            return torch.where(mask, float("-inf"), 0.0).to(torch.float32)
+        return mask
+
+    # CustomizedLaTr.py:146-183 — `use_cache=False` is the reference's O(T^2) loop, token for token
+    @torch.no_grad()
+    def _greedy(self, enc, attention_mask, start_symbol, end_symbol, max_len, use_cache=True):
+        bz, dev = enc.shape[0], enc.device
+        ys = torch.full((bz, 1), start_symbol, dtype=torch.long, device=dev)
+        cache = self.decoder.new_cache(enc, max_len + 1, self.compute_dtype) if use_cache else None
+        step_mask = self._memory_mask_for_step(attention_mask)
+        pe = self.positional_encoding.pos_embedding
+        for t in range(max_len):
+            if use_cache:
+                emb = self.tgt_tok_emb(ys[:, -1:]) + pe[:, t:t + 1]
+                out = self.decoder.step(emb, cache, step_mask, self.compute_dtype)
+            else:
+                out = self.decode(ys, enc, attention_mask)[:, -1:]
+            nxt = self._logits(out)[:, -1].argmax(-1).view(bz, 1)
+            ys = torch.cat([ys, nxt], dim=1)
+            if torch.any(ys == end_symbol, dim=1).sum() == bz:
+                break
+        return ys
+
+    # CustomizedLaTr.py:185-249, CustomizedSaL.py:235-320
+    @torch.no_grad()
+    def _beam(self, enc, attention_mask, start_symbol, end_symbol, max_len, num_beam):
+        ys = torch.full((enc.shape[0], 1), start_symbol, dtype=torch.long, device=enc.device)
+        prob = self._logits(self.decode(ys, enc, attention_mask)[:, -1:])[:, -1]
+        return reference_beam_select(prob, ys, end_symbol, max_len, num_beam)
+
+
+def reference_beam_select(prob, ys, end_symbol, max_len, num_beam):
+    """The reference's `beam_generate` after its first decoder call, restated on that call's scores `prob` (B, V).
+    The routine re-decodes the ONE-token prefix `ys` for every beam and every step (`self.decode(ys, ...)`, never
+    `beams[b]`), so every later score equals `prob`: each beam is its first-step candidate followed by the arg-max
+    token repeated.  Kept as the reference computes it — `log` of raw scores (NaN for negative ones, and torch's
+    argmax picks a NaN entry), one `eos_mask` tensor shared by all beams (`[mask] * num_beam`), per-beam early
+    exit — because the returned ids are the contract; the invariant decoder call is simply done once."""
+    bz = ys.shape[0]
+    values, indices = torch.topk(prob, num_beam, dim=-1)
+    beams = [torch.cat([ys, indices[:, i:i + 1]], dim=1) for i in range(num_beam)]
+    beam_probs = [torch.log(values[:, i:i + 1]) for i in range(num_beam)]
+    vals, inds = values[:, :1], indices[:, :1]           # topk(prob, 1) of the re-decoded one-token prefix
+    log_vals = torch.log(vals)
+    done = [False] * num_beam
+    eos_mask = torch.ones((bz, 1), dtype=torch.long, device=prob.device)      # shared by every beam
+    for _ in range(max_len - 1):
+        for b in range(num_beam):
+            eos_mask = eos_mask * (inds != end_symbol)
+            beams[b] = torch.cat([beams[b], inds], dim=1)
+            if eos_mask.sum() == 0:
+                done[b] = True
+                continue
+            beam_probs[b] = beam_probs[b] + log_vals * eos_mask
+        if all(done):
+            break
+    beam_probs = torch.cat(beam_probs, dim=-1)
+    beams = torch.stack(beams, dim=1)
+    beam_idx = torch.argmax(beam_probs, dim=-1)
+    return beams[torch.arange(bz, device=beams.device), beam_idx.flatten(), :].cpu()
+
+
+class CustomizedLaTr(nn.Module, _VisionMixin, _FlatTargetMixin):
+    """reference: core/model/CustomizedLaTr.py:45-271"""
+
+    def __init__(self, config, tgt_vocab_size=300):
+        super().__init__()
+        self.config = config
+        self.compute_dtype = torch.float32
+        self.encoder = T5EncoderModel(config)
+        _load_pretrained_t5_encoder(self.encoder, config)
+        self.spatial_feat_extractor = SpatialModule(config)
+        self.vit = _build_vit(config)
+        self.visual_projector = nn.Linear(self.vit.config.hidden_size, config.d_model)
+        for _, child in self.vit.named_children():                 # reference :56-59
+            for param in child.parameters():
+                param.requires_grad = False
+        self._init_flat_target(config, tgt_vocab_size)
+
+    _calculate_embedding = PhonemeLaTr._calculate_embedding       # reference :251-264, same body
+    _encode = PhonemeLaTr._encode
+
+    # reference :73-97
+    def forward(self, pixel_values, coordinates, input_ids, labels, src_attention_mask, label_attention_mask,
+                ocr_attention_mask, tokenized_ocr):
+        enc, attention_mask = self._encode(pixel_values, coordinates, input_ids, ocr_attention_mask,
+                                           src_attention_mask, tokenized_ocr)
+        return self._logits(self.decode(labels, enc, attention_mask, label_attention_mask))
+
+    # reference :112-144
+    def generate(self, pixel_values, coordinates, input_ids, src_attention_mask, ocr_attention_mask, tokenized_ocr,
+                 start_symbol, end_symbol, max_length=20, isgreedy=True, num_beam=2):
+        if isgreedy:
+            return self.greedy_generate(pixel_values, coordinates, input_ids, src_attention_mask, ocr_attention_mask,
+                                        tokenized_ocr, start_symbol, end_symbol, max_length)
+        return self.beam_generate(pixel_values, coordinates, input_ids, src_attention_mask, ocr_attention_mask,
+                                  tokenized_ocr, start_symbol, end_symbol, max_length, num_beam)
+
+    @torch.no_grad()
+    def greedy_generate(self, pixel_values, coordinates, input_ids, src_attention_mask, ocr_attention_mask,
+                        tokenized_ocr, start_symbol, end_symbol, max_len=100, use_cache=True):
+        enc, attention_mask = self._encode(pixel_values, coordinates, input_ids, ocr_attention_mask,
+                                           src_attention_mask, tokenized_ocr)
+        return self._greedy(enc, attention_mask, start_symbol, end_symbol, max_len, use_cache)
+
+    @torch.no_grad()
+    def beam_generate(self, pixel_values, coordinates, input_ids, src_attention_mask, ocr_attention_mask,
+                      tokenized_ocr, start_symbol, end_symbol, max_len=100, num_beam=2):
+        enc, attention_mask = self._encode(pixel_values, coordinates, input_ids, ocr_attention_mask,
+                                           src_attention_mask, tokenized_ocr)
+        return self._beam(enc, attention_mask, start_symbol, end_symbol, max_len, num_beam)
+
+
+class CustomizedPreSTU(nn.Module, _VisionMixin, _FlatTargetMixin):
+    """reference: core/model/CustomizedPreSTU.py:16-143.  No layout branch, ViT NOT frozen."""
+
+    def __init__(self, config, tgt_vocab_size):
+        super().__init__()
+        self.config = config
+        self.compute_dtype = torch.float32
+        self.encoder = T5EncoderModel(config)
+        _load_pretrained_t5_encoder(self.encoder, config)
+        self.vit = _build_vit(config)
+        self.visual_projector = nn.Linear(self.vit.config.hidden_size, config.d_model)
+        self._init_flat_target(config, tgt_vocab_size)
+
+    _calculate_embedding = PhonemePreSTU._calculate_embedding     # reference :127-136, same body
+
+    def _encode(self, pixel_values, input_ids, src_attention_mask):
+        inputs_embeds, attention_mask = self._calculate_embedding(pixel_values, input_ids, src_attention_mask)
+        return self.encoder.encoder(inputs_embeds, attention_mask, compute_dtype=self.compute_dtype), attention_mask
+
+    # reference :37-58
+    def forward(self, pixel_values, input_ids, labels, src_attention_mask, label_attention_mask):
+        enc, attention_mask = self._encode(pixel_values, input_ids, src_attention_mask)
+        return self._logits(self.decode(labels, enc, attention_mask, label_attention_mask))
+
+    # reference :72-87 (isgreedy / num_beam are accepted and ignored there too)
+    def generate(self, pixel_values, input_ids, src_attention_mask, start_symbol, end_symbol, max_length=20,
+                 isgreedy=True, num_beam=2):
+        return self.greedy_generate(pixel_values, input_ids, src_attention_mask, start_symbol, end_symbol, max_length)
+
+    @torch.no_grad()
+    def greedy_generate(self, pixel_values, input_ids, src_attention_mask, start_symbol, end_symbol, max_len=100,
+                        use_cache=True):
+        enc, attention_mask = self._encode(pixel_values, input_ids, src_attention_mask)
+        return self._greedy(enc, attention_mask, start_symbol, end_symbol, max_len, use_cache)
+
+
+class _SaLInputs:
+    """question ‖ OCR ‖ object embedding of the SaL family (SaL.py:93-101, CustomizedSaL.py:323-331): the same
+    T5LayerNorm normalises the region-feature projection and the box projection, the token embedding is added."""
+
+    def _init_sal_inputs(self, config, num_heads, obj_dropout, ocr_dropout):
+        d = config.d_model
+        self.rel2Dbias = RelativePositionBiasAggregated(Relative1D=RelativePositionBias1D(num_heads=num_heads),
+                                                        SCP=SCPRelativePositionBias(num_heads=num_heads))
+        self.obj_dropout = nn.Dropout(obj_dropout)          # declared by the reference, never applied
+        self.obj_feature_projector = nn.Linear(config.obj_hidden, d)
+        self.obj_bbox_projector = nn.Linear(4, d)
+        self.obj_feature_layer_norm = T5LayerNorm(d)
+        self.ocr_dropout = nn.Dropout(ocr_dropout)
+        self.ocr_feature_projector = nn.Linear(config.ocr_hidden, d)
+        self.ocr_bbox_projector = nn.Linear(4, d)
+        self.ocr_feature_layer_norm = T5LayerNorm(d)
+
+    def _modality_embedding(self, shared, tokens, coords, feats, feat_proj, box_proj, norm):
+        cd = self.compute_dtype
+        a = norm(_lin(feats.to(cd), feat_proj.weight, feat_proj.bias).float(), out_dtype=torch.float32)
+        b = norm(_lin(coords.to(cd), box_proj.weight, box_proj.bias).float(), out_dtype=torch.float32)
+        return a + b + torch.nn.functional.embedding(tokens, shared.weight)
+
+    def _sal_features(self, shared, input_ids, src_attention_mask, tokenized_ocr, ocr_attention_mask, ocr_coordinates,
+                      ocr_features, tokenized_obj, obj_attention_mask, obj_coordinates, obj_features, max_ocr,
+                      max_ques):
+        obj = self._modality_embedding(shared, tokenized_obj, obj_coordinates, obj_features,
+                                       self.obj_feature_projector, self.obj_bbox_projector,
+                                       self.obj_feature_layer_norm)
+        ocr = self._modality_embedding(shared, tokenized_ocr, ocr_coordinates, ocr_features,
+                                       self.ocr_feature_projector, self.ocr_bbox_projector,
+                                       self.ocr_feature_layer_norm)
+        ques = torch.nn.functional.embedding(input_ids, shared.weight)
+        feat = torch.cat([ques, ocr, obj], dim=1)
+        mask = torch.cat([src_attention_mask, ocr_attention_mask, obj_attention_mask], dim=1)
+        rel, scp = self.rel2Dbias(feat.shape[1], ocr_coordinates, int(max_ques), int(max_ocr))
+        return feat, mask, rel, scp
+
+
+class SaL(nn.Module, _SaLInputs):
+    """reference: core/model/SaL.py:24-140 — T5 encoder-decoder (`T52dForConditionalGeneration`) whose encoder takes
+    the EXTERNAL 1-D + SCP position bias (so the attention mask is not applied there — SURVEY D14), T5 decoder
+    without an encoder mask, lm_head over the (resized) T5 vocabulary."""
+
+    def __init__(self, config, obj_dropout=0.1, ocr_dropout=0.1):
+        super().__init__()
+        self.config = config
+        self.compute_dtype = torch.float32
+        self.backbone = T5ForConditionalGeneration(config)
+        _load_pretrained_t5(self.backbone, config)
+        self._resize_token_embeddings(getattr(config, "new_token_embedding_size", None))
+        self._init_sal_inputs(config, config.num_heads, obj_dropout, ocr_dropout)
+
+    def set_compute_dtype(self, dtype):
+        assert dtype in (torch.float32, torch.bfloat16)
+        self.compute_dtype = dtype
+        return self
+
+    def _resize_token_embeddings(self, n):
+        bb = self.backbone
+        if n is None or n == bb.shared.num_embeddings:
+            return
+        tied = bb.lm_head.weight is bb.shared.weight
+        _resize_shared(bb, (bb.encoder, bb.decoder), n, self.config)
+        if tied:
+            bb.lm_head = nn.Linear(bb.shared.embedding_dim, n, bias=False)
+            bb.lm_head.weight = bb.shared.weight
+        else:
+            old = bb.lm_head
+            bb.lm_head = nn.Linear(old.in_features, n, bias=False)
+            nn.init.normal_(bb.lm_head.weight, mean=0.0, std=self.config.initializer_factor)
+            k = min(n, old.out_features)
+            bb.lm_head.weight.data[:k] = old.weight.data[:k]
+        self.config.vocab_size = n
+
+    # reference :93-101
+    def calculate_obj_embedding(self, tokenized_obj, obj_coordinates, obj_features):
+        return self._modality_embedding(self.backbone.shared, tokenized_obj, obj_coordinates, obj_features,
+                                        self.obj_feature_projector, self.obj_bbox_projector,
+                                        self.obj_feature_layer_norm)
+
+    def calculate_ocr_embedding(self, tokenized_ocr, ocr_coordinates, ocr_features):
+        return self._modality_embedding(self.backbone.shared, tokenized_ocr, ocr_coordinates, ocr_features,
+                                        self.ocr_feature_projector, self.ocr_bbox_projector,
+                                        self.ocr_feature_layer_norm)
+
+    def _encode(self, *inputs):
+        feat, mask, rel, scp = self._sal_features(self.backbone.shared, *inputs)
+        return self.backbone.encoder(feat, None, compute_dtype=self.compute_dtype, external_rel_bias=rel, scp=scp)
+
+    def _decoder_hidden(self, input_ids, src_attention_mask, label_ids, label_attention_mask, tokenized_ocr,
+                        ocr_attention_mask, ocr_coordinates, ocr_features, tokenized_obj, obj_attention_mask,
+                        obj_coordinates, obj_features, max_ocr, max_ques):
+        enc = self._encode(input_ids, src_attention_mask, tokenized_ocr, ocr_attention_mask, ocr_coordinates,
+                           ocr_features, tokenized_obj, obj_attention_mask, obj_coordinates, obj_features, max_ocr,
+                           max_ques)
+        tgt = torch.nn.functional.embedding(label_ids, self.backbone.shared.weight)
+        return self.backbone.decoder(tgt, label_attention_mask, compute_dtype=self.compute_dtype, memory=enc,
+                                     memory_mask=None)
+
+    # reference :44-91
+    def forward(self, input_ids, src_attention_mask, label_ids, label_attention_mask, tokenized_ocr,
+                ocr_attention_mask, ocr_coordinates, ocr_features, tokenized_obj, obj_attention_mask,
+                obj_coordinates, obj_features, max_ocr, max_ques):
+        dec = self._decoder_hidden(input_ids, src_attention_mask, label_ids, label_attention_mask, tokenized_ocr,
+                                   ocr_attention_mask, ocr_coordinates, ocr_features, tokenized_obj,
+                                   obj_attention_mask, obj_coordinates, obj_features, max_ocr, max_ques)
+        return _lin(dec.to(self.compute_dtype), self.backbone.lm_head.weight).float()
+
+    # reference :104-140
+    @torch.no_grad()
+    def generate(self, input_ids, src_attention_mask, tokenized_ocr, ocr_attention_mask, ocr_coordinates,
+                 ocr_features, tokenized_obj, obj_attention_mask, obj_coordinates, obj_features, max_ocr, max_ques,
+                 max_length=20):
+        enc = self._encode(input_ids, src_attention_mask, tokenized_ocr, ocr_attention_mask, ocr_coordinates,
+                           ocr_features, tokenized_obj, obj_attention_mask, obj_coordinates, obj_features, max_ocr,
+                           max_ques)
+        return _t5_greedy(self.backbone, self.config, enc, max_length, self.compute_dtype)
+
+
+class CustomizedSaL(nn.Module, _SaLInputs, _FlatTargetMixin):
+    """reference: core/model/CustomizedSaL.py:29-335 — the PhonemeSaL encoder side with the flat-vocabulary
+    target decoder; forward returns logits only (the executor owns the loss)."""
+
+    def __init__(self, config, tgt_vocab_size, obj_dropout=0.1, ocr_dropout=0.1):
+        super().__init__()
+        self.config = config
+        self.compute_dtype = torch.float32
+        self.encoder = T5EncoderModel(config)
+        _load_pretrained_t5_encoder(self.encoder, config)
+        _resize_shared(self.encoder, (self.encoder.encoder,), getattr(config, "new_token_embedding_size", None),
+                       config)
+        self._init_sal_inputs(config, config.num_heads, obj_dropout, ocr_dropout)
+        self._init_flat_target(config, tgt_vocab_size)
+
+    set_compute_dtype = SaL.set_compute_dtype
+
+    def _calculate_obj_embedding(self, tokenized_obj, obj_coordinates, obj_features):
+        return self._modality_embedding(self.encoder.shared, tokenized_obj, obj_coordinates, obj_features,
+                                        self.obj_feature_projector, self.obj_bbox_projector,
+                                        self.obj_feature_layer_norm)
+
+    def _calculate_ocr_embedding(self, tokenized_ocr, ocr_coordinates, ocr_features):
+        return self._modality_embedding(self.encoder.shared, tokenized_ocr, ocr_coordinates, ocr_features,
+                                        self.ocr_feature_projector, self.ocr_bbox_projector,
+                                        self.ocr_feature_layer_norm)
+
+    def _encode(self, *inputs):
+        feat, mask, rel, scp = self._sal_features(self.encoder.shared, *inputs)
+        enc = self.encoder.encoder(feat, None, compute_dtype=self.compute_dtype, external_rel_bias=rel, scp=scp)
+        return enc, mask
+
+    # reference :62-106
+    def forward(self, input_ids, src_attention_mask, label_ids, label_attention_mask, tokenized_ocr,
+                ocr_attention_mask, ocr_coordinates, ocr_features, tokenized_obj, obj_attention_mask,
+                obj_coordinates, obj_features, max_ocr, max_ques):
+        enc, mask = self._encode(input_ids, src_attention_mask, tokenized_ocr, ocr_attention_mask, ocr_coordinates,
+                                 ocr_features, tokenized_obj, obj_attention_mask, obj_coordinates, obj_features,
+                                 max_ocr, max_ques)
+        return self._logits(self.decode(label_ids, enc, mask, label_attention_mask))
+
+    # reference :121-173
+    def generate(self, input_ids, src_attention_mask, tokenized_ocr, ocr_attention_mask, ocr_coordinates,
+                 ocr_features, tokenized_obj, obj_attention_mask, obj_coordinates, obj_features, max_ocr, max_ques,
+                 start_symbol, end_symbol, max_length=20, isgreedy=True, num_beam=2):
+        fn = self.greedy_generate if isgreedy else self.beam_generate
+        extra = () if isgreedy else (num_beam,)
+        return fn(input_ids, src_attention_mask, tokenized_ocr, ocr_attention_mask, ocr_coordinates, ocr_features,
+                  tokenized_obj, obj_attention_mask, obj_coordinates, obj_features, max_ocr, max_ques, start_symbol,
+                  end_symbol, max_length, *extra)
+
+    @torch.no_grad()
+    def greedy_generate(self, input_ids, src_attention_mask, tokenized_ocr, ocr_attention_mask, ocr_coordinates,
+                        ocr_features, tokenized_obj, obj_attention_mask, obj_coordinates, obj_features, max_ocr,
+                        max_ques, start_symbol, end_symbol, max_len=100, use_cache=True):
+        enc, mask = self._encode(input_ids, src_attention_mask, tokenized_ocr, ocr_attention_mask, ocr_coordinates,
+                                 ocr_features, tokenized_obj, obj_attention_mask, obj_coordinates, obj_features,
+                                 max_ocr, max_ques)
+        return self._greedy(enc, mask, start_symbol, end_symbol, max_len, use_cache)
+
+    @torch.no_grad()
+    def beam_generate(self, input_ids, src_attention_mask, tokenized_ocr, ocr_attention_mask, ocr_coordinates,
+                      ocr_features, tokenized_obj, obj_attention_mask, obj_coordinates, obj_features, max_ocr,
+                      max_ques, start_symbol, end_symbol, max_len=100, num_beam=2):
+        enc, mask = self._encode(input_ids, src_attention_mask, tokenized_ocr, ocr_attention_mask, ocr_coordinates,
+                                 ocr_features, tokenized_obj, obj_attention_mask, obj_coordinates, obj_features,
+                                 max_ocr, max_ques)
+        return self._beam(enc, mask, start_symbol, end_symbol, max_len, num_beam)

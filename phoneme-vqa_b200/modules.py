@@ -191,6 +191,19 @@ class PhonemeEmbedding(nn.Module):
                                 training=training, out_dtype=out_dtype)
 
 
+# reference: core/model/modules/transformer_utils.py:27-36
+class TokenEmbedding(nn.Module):
+    """flat target vocabulary (char / byte / BPE ids): embedding * sqrt(d)"""
+
+    def __init__(self, vocab_size: int, emb_size):
+        super().__init__()
+        self.embedding = nn.Embedding(vocab_size, emb_size)
+        self.emb_size = emb_size
+
+    def forward(self, tokens):
+        return F.embedding(tokens.long(), self.embedding.weight) * math.sqrt(self.emb_size)
+
+
 # reference: core/model/modules/transformer_utils.py:6-25
 class SinusoidalPositionalEncoding(nn.Module):
     def __init__(self, emb_size: int, dropout: float, maxlen: int = 5000):
