@@ -1,16 +1,10 @@
 """GradReducer (bucketed gradient all-reduce overlapped with backward) on 2 gloo ranks, CPU."""
 import os
-import socket
+import tempfile
 
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
-
-
-def _free_port():
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        return s.getsockname()[1]
 
 
 def _make_model():
@@ -23,9 +17,10 @@ def _make_model():
     return m
 
 
-def _worker(rank, world, port, q):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+def _worker(rank, world, store_path, q):
+    # file rendezvous: no port to race for when several test sessions share the machine
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), GLOO_SOCKET_IFNAME="lo")
+    dist.init_process_group("gloo", init_method="file://" + store_path, rank=rank, world_size=world)
     import phoneme_vqa_b200.parallel as par
     model = _make_model()
     if rank == 1:                                    # ranks start different: broadcast must fix it
@@ -59,16 +54,16 @@ def _worker(rank, world, port, q):
 
 
 def test_two_rank_gradients_equal_single_process_global_batch():
-    port = _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    grads, grads2 = q.get(timeout=120)
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    with tempfile.TemporaryDirectory() as tmp:
+        procs = [ctx.Process(target=_worker, args=(r, 2, os.path.join(tmp, "store"), q)) for r in range(2)]
+        for p in procs:
+            p.start()
+        grads, grads2 = q.get(timeout=300)
+        for p in procs:
+            p.join(timeout=120)
+            assert p.exitcode == 0
     model = _make_model()
     g = torch.Generator().manual_seed(100)
     x = torch.randn(8, 16, generator=g)
