@@ -160,20 +160,46 @@ def run_b200_arm(args):
     B = args.batch
     cfg = synthetic.t5_config("base")
     torch.manual_seed(0)
+    loss_fn, ignore_index = None, synthetic.PAD_ID
+    shape = {}                            # sequence geometry for the algorithmic-bytes table (default: PhonoLaTr)
+    metric = {"phonolatr": "train samples/sec (PhonoLaTr-base)", "latr": "train samples/sec (LaTr-base)",
+              "phonoprestu": "train samples/sec (PhonoPreSTU-base)", "phonosal": "train samples/sec (PhonoSaL-large)"}[args.workload]
     if args.workload == "latr":          # BASELINE config 2 (not the headline metric; kept for completeness)
         cfg = synthetic.t5_config("base", num_decoder_layers=12)
         model = models.LaTr(cfg).to(dev)
+        make_batch, ignore_index = synthetic.latr_batch, 0
+        workload = f"LaTr T5-base (12+12 layers, 36096-way vocabulary head), per-GPU batch {B}, S=327, T=127"
+    elif args.workload == "phonoprestu":  # BASELINE config 4: trainable ViT-B/16, question+OCR text in one sequence
+        vit = None if args.image == 224 else dict(image_size=args.image)
+        cfg = synthetic.t5_config("base", vit_config=vit)
+        model = models.PhonemePreSTU(cfg, *synthetic.PHONEME_VOCAB).to(dev)
+        make_batch = lambda B_, V, **kw: synthetic.phoneme_prestu_batch(B_, V, image=args.image, **kw)  # noqa: E731
+        loss_fn = synthetic.phoneme_prestu_loss
+        s_img = (args.image // 16) ** 2 + 1
+        shape = dict(S_img=s_img, L_ocr=0, L_q=130)
+        workload = (f"PhonemePreSTU T5-base, trainable ViT-B/16 at {args.image}px, per-GPU batch {B}, "
+                    f"S={s_img + 130} ({s_img} ViT + 130 text), T=127, phoneme vocab 84/187/7")
+    elif args.workload == "phonosal":     # BASELINE config 5: T5-large dims, 80 question + 256 OCR + 128 object tokens
+        cfg = synthetic.t5_config("large")
+        cfg.update({"ocr_hidden": 512, "obj_hidden": 2048, "new_token_embedding_size": cfg.vocab_size})
+        model = models.PhonemeSaL(cfg, 253).to(dev)
+        make_batch = synthetic.phoneme_sal_batch
+        loss_fn = synthetic.phoneme_sal_loss(256, 80)
+        shape = dict(S_img=0, L_ocr=256, L_q=80, T=39)
+        workload = (f"PhonemeSaL T5-large (24 layers, 16 heads, 1-D + SCP bias in-kernel), per-GPU batch {B}, "
+                    "S=464 (80 question + 256 OCR + 128 objects), T=39, 253-way phoneme vocabulary")
     else:
         model = models.PhonemeLaTr(cfg, *synthetic.PHONEME_VOCAB).to(dev)
+        make_batch = synthetic.phoneme_latr_batch
+        workload = WORKLOAD.format(B=B)
     model.set_compute_dtype(torch.bfloat16 if args.dtype == "bf16" else torch.float32)
     model.train()
     ops.manual_seed(1234 + rank)
     reducer = parallel.GradReducer(model, bucket_mb=32.0)
     reducer.broadcast_parameters(0)
     trainer = train.TrainStep(model, reducer if world > 1 else None, lr=5e-5, betas=(0.9, 0.98), eps=1e-9,
-                              warmup_iters=2000, ignore_index=0 if args.workload == "latr" else synthetic.PAD_ID,
-                              use_graph=not args.no_graph)
-    make_batch = synthetic.latr_batch if args.workload == "latr" else synthetic.phoneme_latr_batch
+                              warmup_iters=2000, ignore_index=ignore_index, use_graph=not args.no_graph,
+                              loss_fn=loss_fn)
 
     n_distinct = 4
     host = [make_batch(B, cfg.vocab_size, seed=1234 + rank * 1000 + i, pin=True)
@@ -233,7 +259,7 @@ def run_b200_arm(args):
 
     if rank == 0:
         hbm, tf, src = _peaks()
-        alg = kernel_algorithmic(B, cfg)
+        alg = kernel_algorithmic(B, cfg, **shape)
         traffic = _measured_traffic()
         kernels = {}
         for name, (n, total_ms) in ksum.items():
@@ -260,11 +286,10 @@ def run_b200_arm(args):
                                      "launch inside the step; traffic = ncu dram bytes per launch (profiles/)"})
         value = world * B * args.steps / (ms / 1e3)
         line = {
-            "metric": "train samples/sec (PhonoLaTr-base)", "value": value, "unit": "samples/s", "n_gpus": world,
+            "metric": metric, "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": (WORKLOAD.format(B=B) if args.workload == "phonolatr" else
-                                    f"LaTr T5-base (12+12 layers, 36096-way vocabulary head), per-GPU batch {B}, S=327, T=127"),
+            "config": {"workload": workload,
                        "global_batch": world * B,
                        "parallelism": f"dp{world}", "weights": "random-init",
                        "launch": "eager" if args.no_graph else "one CUDA graph per step",
@@ -353,7 +378,10 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=4, help="batch of the bounded CPU sample")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="phonolatr", choices=["phonolatr", "latr"])
+    ap.add_argument("--workload", default="phonolatr", choices=["phonolatr", "latr", "phonoprestu", "phonosal"],
+                    help="phonolatr = the headline metric (BASELINE config 3's per-GPU shard); the others are the "
+                         "sibling configs 2, 4 and 5")
+    ap.add_argument("--image", type=int, default=224, choices=[224, 384], help="phonoprestu: ViT input size")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of one CUDA graph")
     args = ap.parse_args()
     _quiet_stdout()

@@ -458,6 +458,19 @@ class PhonemePreSTU(nn.Module, _VisionMixin):
         on, rh, to = self._heads(h)
         return on.float(), rh.float(), to.float()
 
+    def forward_loss(self, pixel_values, input_ids, labels, src_attention_mask, label_attention_mask, targets,
+                     ignore_index):
+        """model forward + the executor's 3x CrossEntropyLoss (core/executor/PhonemePreSTU_Executor.py:160-180)
+        through the fused phoneme head kernel; `targets` = labels[:, 1:, :] of the executor."""
+        inputs_embeds, attention_mask = self._calculate_embedding(pixel_values, input_ids, src_attention_mask)
+        enc = self.encoder.encoder(inputs_embeds, attention_mask, compute_dtype=self.compute_dtype)
+        dec = self.decode(labels, enc, attention_mask, label_attention_mask)
+        h = _lin(dec.to(self.compute_dtype), self.shared_lm_head.weight, self.shared_lm_head.bias)
+        return ops.phoneme_head_ce(h.reshape(-1, h.shape[-1]), targets.reshape(-1, 3),
+                                   self.onset_lm_head.weight, self.onset_lm_head.bias,
+                                   self.rhyme_lm_head.weight, self.rhyme_lm_head.bias,
+                                   self.tone_lm_head.weight, self.tone_lm_head.bias, ignore_index)
+
     # The call the executor makes (core/executor/PhonemePreSTU_Executor.py:41-49): the class's own `generate`
     # (PhonemePreSTU.py:103-199) still carries PhonemeLaTr's argument list and cannot run (SURVEY D5), so the
     # intended behaviour is PhonemeLaTr's greedy loop on this model's encoder; isgreedy / num_beam are ignored there.

@@ -93,3 +93,75 @@ def latr_batch(B, vocab_size, T=127, L_ocr=100, L_q=30, seed=1234, image=224, de
     if device != "cpu":
         batch = {k: v.to(device) for k, v in batch.items()}
     return batch
+
+
+def phoneme_prestu_batch(B, vocab_size, T=127, L_in=130, V_sub=PHONEME_VOCAB, seed=1234, image=224, device="cpu",
+                         pin=False):
+    """PhonemePreSTUDataset fields (core/data/PhonemePreSTUDataset.py): question and OCR text share one
+    `input_ids` sequence of max_q_length + max_ocr_length = 130 (config/phonemeprestu.yaml:37-38), no boxes."""
+    b = phoneme_latr_batch(B, vocab_size, T=T, L_ocr=4, L_q=L_in, V_sub=V_sub, seed=seed, image=image)
+    batch = {k: b[k] for k in ("pixel_values", "input_ids", "src_attention_mask", "label_ids", "label_attention_mask")}
+    if pin:
+        batch = {k: v.pin_memory() for k, v in batch.items()}
+    if device != "cpu":
+        batch = {k: v.to(device) for k, v in batch.items()}
+    return batch
+
+
+def phoneme_prestu_loss(model, b, ignore_index=PAD_ID):
+    """step body of core/executor/PhonemePreSTU_Executor.py:150-185 on the fused head"""
+    labels = b["label_ids"]
+    return model.forward_loss(b["pixel_values"], b["input_ids"], labels[:, :-1], b["src_attention_mask"],
+                              b["label_attention_mask"][:, :-1], targets=labels[:, 1:], ignore_index=ignore_index)
+
+
+SAL_FIELDS = ("input_ids", "src_attention_mask", "label_ids", "shifted_right_label_ids", "label_attention_mask",
+              "tokenized_ocr", "ocr_attention_mask", "ocr_coordinates", "ocr_features", "tokenized_obj",
+              "obj_attention_mask", "obj_coordinates", "obj_features")
+
+
+def phoneme_sal_batch(B, vocab_size, T=39, L_q=80, L_ocr=256, L_obj=128, ocr_hidden=512, obj_hidden=2048,
+                      tgt_vocab=253, seed=1234, device="cpu", pin=False):
+    """PhonemeSaLDataset fields (core/data/PhonemeSaLDataset.py:78-92): float masks, boxes in
+    [0, 0.99), region features, flat 253-phoneme labels (pad 0, bos 1, eos 2), bool label mask = pad positions."""
+    g = torch.Generator().manual_seed(seed)
+
+    def toks(L, lo):
+        n = torch.randint(lo, L, (B,), generator=g)
+        pos = torch.arange(L)[None, :]
+        ids = torch.randint(3, vocab_size, (B, L), generator=g)
+        ids = torch.where(pos < n[:, None], ids, torch.zeros_like(ids))
+        ids = torch.where(pos == n[:, None], torch.ones_like(ids), ids)
+        return ids, (pos <= n[:, None]).float()
+
+    def boxes(L):
+        xy = torch.rand(B, L, 2, generator=g) * 0.8
+        return torch.cat([xy, xy + torch.rand(B, L, 2, generator=g) * 0.19], dim=-1)
+
+    q, qm = toks(L_q, min(8, L_q - 1))
+    ocr, om = toks(L_ocr, min(20, L_ocr - 1))
+    obj, bm = toks(L_obj, min(10, L_obj - 1))
+    ln = torch.randint(min(4, T), T, (B,), generator=g)
+    tpos = torch.arange(T + 1)[None, :]
+    lab = torch.randint(4, tgt_vocab, (B, T + 1), generator=g)
+    lab = torch.where(tpos == 0, torch.ones_like(lab), lab)
+    lab = torch.where(tpos == ln[:, None], torch.full_like(lab, 2), lab)
+    lab = torch.where(tpos > ln[:, None], torch.zeros_like(lab), lab)
+    batch = {"input_ids": q, "src_attention_mask": qm, "label_ids": lab[:, :-1].contiguous(),
+             "shifted_right_label_ids": lab[:, 1:].contiguous(), "label_attention_mask": lab[:, :-1] == 0,
+             "tokenized_ocr": ocr, "ocr_attention_mask": om, "ocr_coordinates": boxes(L_ocr),
+             "ocr_features": torch.randn(B, L_ocr, ocr_hidden, generator=g),
+             "tokenized_obj": obj, "obj_attention_mask": bm, "obj_coordinates": boxes(L_obj),
+             "obj_features": torch.randn(B, L_obj, obj_hidden, generator=g)}
+    if pin:
+        batch = {k: v.pin_memory() for k, v in batch.items()}
+    if device != "cpu":
+        batch = {k: v.to(device) for k, v in batch.items()}
+    return batch
+
+
+def phoneme_sal_loss(L_ocr, L_q):
+    """step body of core/executor/PhonemeSaL_Executor.py (the model returns (logits, loss) itself)"""
+    def loss_fn(model, b):
+        return model(*[b[k] for k in SAL_FIELDS], L_ocr, L_q)[1]
+    return loss_fn

@@ -20,8 +20,10 @@ from .modules import SHADOWS
 
 class TrainStep:
     def __init__(self, model, reducer=None, lr=5e-5, betas=(0.9, 0.98), eps=1e-9, warmup_iters=2000,
-                 start_factor=1.0 / 3.0, ignore_index=2, use_graph=True):
+                 start_factor=1.0 / 3.0, ignore_index=2, use_graph=True, loss_fn=None):
+        """`loss_fn(model, batch) -> scalar loss` replaces the LaTr-family step body (PreSTU / SaL argument lists)."""
         self.model, self.reducer = model, reducer
+        self.loss_fn = loss_fn
         self.base_lr, self.warmup_iters, self.start_factor = lr, warmup_iters, start_factor
         self.ignore_index = ignore_index
         dev = next(model.parameters()).device
@@ -45,11 +47,14 @@ class TrainStep:
         return self.base_lr * f
 
     def _body(self, b):
-        labels = b["label_ids"]
-        loss = self.model.forward_loss(b["pixel_values"], b["coordinates"], b["input_ids"], labels[:, :-1],
-                                       b["src_attention_mask"], b["label_attention_mask"][:, :-1],
-                                       b["ocr_attention_mask"], b["tokenized_ocr"], targets=labels[:, 1:],
-                                       ignore_index=self.ignore_index)
+        if self.loss_fn is not None:
+            loss = self.loss_fn(self.model, b)
+        else:
+            labels = b["label_ids"]
+            loss = self.model.forward_loss(b["pixel_values"], b["coordinates"], b["input_ids"], labels[:, :-1],
+                                           b["src_attention_mask"], b["label_attention_mask"][:, :-1],
+                                           b["ocr_attention_mask"], b["tokenized_ocr"], targets=labels[:, 1:],
+                                           ignore_index=self.ignore_index)
         self.optim.zero_grad(set_to_none=True)
         loss.backward()
         if self.reducer is not None:
