@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PVQA_ABI_VERSION 5
+#define PVQA_ABI_VERSION 6
 
 typedef enum {
   PVQA_OK = 0,
@@ -208,6 +208,23 @@ int pvqa_attn_fwd(const void* q, const void* k, const void* v, void* o, float* l
                   float dropout_p, uint64_t seed, uint64_t offset,
                   const uint8_t* scp_bucket, const float* scp_table, int64_t scp_q0, int64_t scp_L,
                   void* stream);
+
+/* Second-generation forward, same contract, arguments, outputs and dropout stream as pvqa_attn_fwd (so
+ * pvqa_attn_bwd consumes its lse / o unchanged).  One thread per query row: the score tile is read from TMEM once,
+ * O accumulates in TMEM across key tiles, the next tile's QK^T is issued while the current softmax runs, the T5
+ * bias is read with 128-bit shared loads (phoneme-vqa_b200/csrc/attn_fwd2.cuh).  OPT-IN (host: PVQA_ATTN_FWD_V2=1):
+ * written after round 1's GPU budget was spent, compiled and host-checked but not yet validated on a device. */
+int pvqa_attn_fwd_v2(const void* q, const void* k, const void* v, void* o, float* lse,
+                     const float* rel_bias, const float* key_add,
+                     int64_t B, int64_t H, int64_t Sq, int64_t Sk, int64_t D,
+                     int64_t q_stride_b, int64_t q_stride_s, int64_t q_stride_h,
+                     int64_t k_stride_b, int64_t k_stride_s, int64_t k_stride_h,
+                     int64_t v_stride_b, int64_t v_stride_s, int64_t v_stride_h,
+                     int64_t o_stride_b, int64_t o_stride_s, int64_t o_stride_h,
+                     float scale, int causal,
+                     float dropout_p, uint64_t seed, uint64_t offset,
+                     const uint8_t* scp_bucket, const float* scp_table, int64_t scp_q0, int64_t scp_L,
+                     void* stream);
 
 /* backward.  dk, dv: bf16 with explicit strides (may point into a packed d(qkv) buffer).
  * dq_accum: fp32 (B,Sq,H,64) contiguous, ZERO-INITIALISED by the caller — every 128-key tile

@@ -1094,3 +1094,5 @@ extern "C" int pvqa_attn_bwd(const void* q, const void* k, const void* v, const 
   PVQA_CHECK_LAUNCH("attn_bwd");
   return PVQA_OK;
 }
+
+#include "attn_fwd2.cuh"

@@ -7,6 +7,7 @@ tensor is not on a CUDA device — there is deliberately no PyTorch/CPU fallback
 """
 from __future__ import annotations
 
+import os
 from ctypes import c_void_p
 
 import torch
@@ -560,6 +561,11 @@ def relu_dropout(x, p, training):
 # ----------------------------------------------------------------------------------
 # K2 / K3: attention.  bf16 -> tcgen05/TMA flash kernels; fp32 (parity mode) -> fp32 CUDA-core kernels.
 # ----------------------------------------------------------------------------------
+# Opt-in second-generation forward kernel (csrc/attn_fwd2.cuh).  Off by default until it has passed the parity
+# tests on a device; both entry points have the same contract, so this is a switch, not a fallback.
+ATTN_FWD_V2 = os.environ.get("PVQA_ATTN_FWD_V2", "0") == "1"
+
+
 def _check_attn_operand(t, name, dtype):
     if t.dtype != dtype or t.dim() != 4 or t.stride(3) != 1:
         raise TypeError(f"attention {name} must be a {dtype} (B,S,H,D) view with unit stride on D")
@@ -603,7 +609,12 @@ def attention_fwd_raw(q, k, v, scale, rel_bias=None, key_add=None, causal=False,
         raise ValueError(f"rel_bias must be (H, Sq+Sk-1) = {(H, Sq + Sk - 1)}, got {tuple(rel_bias.shape)}")
     if key_add is not None and tuple(key_add.shape) != (B, Sk):
         raise ValueError(f"key_add must be (B, Sk) = {(B, Sk)}, got {tuple(key_add.shape)}")
-    fn, name = (lib.pvqa_attn_fwd, "attn_fwd") if dtype == torch.bfloat16 else (lib.pvqa_attn_f32_fwd, "attn_f32_fwd")
+    if dtype != torch.bfloat16:
+        fn, name = lib.pvqa_attn_f32_fwd, "attn_f32_fwd"
+    elif ATTN_FWD_V2:
+        fn, name = lib.pvqa_attn_fwd_v2, "attn_fwd_v2"
+    else:
+        fn, name = lib.pvqa_attn_fwd, "attn_fwd"
     with torch.cuda.device(dev), _prof(f"{name}[Sq={Sq},Sk={Sk}]"):
         check(fn(_p(q), _p(k), _p(v), _p(o), _p(lse), _p(rel_bias), _p(key_add), B, H, Sq, Sk, D,
                  *_st3(q), *_st3(k), *_st3(v), *_st3(o), float(scale), int(bool(causal)),

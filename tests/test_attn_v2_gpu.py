@@ -1,0 +1,78 @@
+"""The opt-in second-generation forward kernel (pvqa_attn_fwd_v2, csrc/attn_fwd2.cuh) against the same oracle cases
+as the product kernel, plus bit-level agreement with it.
+
+Skipped unless PVQA_TEST_ATTN_V2=1: the kernel was written after round 1's GPU budget was spent and has not run on a
+device yet; `PVQA_TEST_ATTN_V2=1 python -m pytest tests/test_attn_v2_gpu.py -m gpu` is the first thing to run before
+flipping ops.ATTN_FWD_V2 on."""
+import math
+import os
+
+import pytest
+import torch
+
+import test_attn_gpu as base
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
+              pytest.mark.skipif(os.environ.get("PVQA_TEST_ATTN_V2", "0") != "1",
+                                 reason="opt-in kernel: set PVQA_TEST_ATTN_V2=1 (not yet validated on a device)")]
+DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True)
+def v2(monkeypatch):
+    from phoneme_vqa_b200 import ops
+    monkeypatch.setattr(ops, "ATTN_FWD_V2", True)
+    c0 = ops._lib.launch_count()
+    yield
+    assert ops._lib.launch_count() > c0
+
+
+@pytest.mark.parametrize("B,Sq,Sk,H", base.T5_CASES)
+def test_t5_attention_fwd(B, Sq, Sk, H):
+    base.test_t5_attention_fwd(B, Sq, Sk, H)
+
+
+@pytest.mark.parametrize("B,T,S,H", [(2, 127, 327, 3), (1, 40, 64, 2), (2, 9, 17, 1)])
+def test_cross_attention_fwd(B, T, S, H):
+    base.test_mha_cross_attention_fwd_float_masks(B, T, S, H)
+
+
+@pytest.mark.parametrize("B,T,H", [(2, 127, 3), (1, 128, 1), (1, 300, 2), (2, 1, 1)])
+def test_causal_self_attention_fwd(B, T, H):
+    base.test_mha_causal_self_attention_fwd_packed_qkv(B, T, H)
+
+
+@pytest.mark.parametrize("B,S,H", [(1, 128, 1), (2, 327, 3), (1, 100, 2), (1, 464, 2), (2, 5, 1)])
+def test_backward_consumes_v2_forward_state(B, S, H):
+    """autograd wrappers: forward by v2 (o, lse), backward by the product kernel"""
+    base.test_t5_self_attention_bwd_packed(B, S, H)
+
+
+def test_dropout_stream_and_scp_bias():
+    base.test_attention_dropout_mask_is_consistent_between_fwd_and_bwd(torch.bfloat16)
+    base.test_self_attention_with_scp_bias_fwd_bwd(torch.bfloat16)
+
+
+@pytest.mark.parametrize("B,Sq,Sk,H,causal,p", [(2, 327, 327, 3, False, 0.0), (2, 327, 327, 2, False, 0.1),
+                                                (2, 127, 127, 2, True, 0.1), (1, 197, 197, 4, False, 0.0),
+                                                (2, 127, 327, 2, False, 0.1), (1, 707, 707, 1, False, 0.0)])
+def test_v2_agrees_with_the_product_kernel(B, Sq, Sk, H, causal, p, monkeypatch):
+    """same inputs, same dropout triple: identical keep-masks, lse within fp32 rounding, o within one bf16 ulp-ish"""
+    from phoneme_vqa_b200 import ops
+    g = torch.Generator().manual_seed(Sq + Sk)
+    q = (torch.randn(B, Sq, H, 64, generator=g) * 0.4).bfloat16().to(DEV)
+    k = (torch.randn(B, Sk, H, 64, generator=g) * 0.4).bfloat16().to(DEV)
+    v = torch.randn(B, Sk, H, 64, generator=g).bfloat16().to(DEV)
+    rel = None if (causal or Sq != Sk) else torch.randn(H, Sq + Sk - 1, generator=g).to(DEV)
+    key_add = torch.where(torch.rand(B, Sk, generator=g) > 0.2, 0.0, float("-inf"))
+    key_add[:, 0] = 0.0
+    key_add = key_add.to(DEV)
+    drop = (p, 1234, 77) if p > 0 else (0.0, 0, 0)
+    scale = 1.0 if rel is not None else 1.0 / math.sqrt(64)
+    o2, lse2 = ops.attention_fwd_raw(q, k, v, scale, rel, key_add, causal, drop)
+    monkeypatch.setattr(ops, "ATTN_FWD_V2", False)
+    o1, lse1 = ops.attention_fwd_raw(q, k, v, scale, rel, key_add, causal, drop)
+    torch.testing.assert_close(lse2, lse1, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(o2.float(), o1.float(), rtol=2e-2, atol=2e-3)
+    if p > 0:   # V = identity trick is in the dropout test; here: the same entries of o are exactly zero-contribution
+        assert (o2.float() - o1.float()).abs().max().item() < 5e-2
