@@ -16,6 +16,7 @@ with fp32 master weights / residual stream; random-init weights, synthetic data 
            of the same steps (events around every C-ABI launch), against MEASURED_PEAKS.json
   cpu_baseline : the oracle port of the reference model on the host cores, bounded sample
   --impl reference : the reference arm = that same CPU port, K steps (rank 0 only)
+  --impl eager-gpu : the same port run eagerly by PyTorch on one B200 (fp32 and bf16 autocast) — "what you get today"
 """
 from __future__ import annotations
 
@@ -123,6 +124,48 @@ def cpu_reference_run(batch_size, steps, warmup, threads=None):
             "sample": f"{len(times)} fwd+loss+bwd+Adam step(s) of the oracle port (HF T5/ViT + nn.TransformerDecoder, "
                       f"fp32) at batch {batch_size} of the same PhonoLaTr-base workload, after {warmup} warm-up",
             "ms_per_step": 1e3 * total / len(times)}
+
+
+def run_eager_gpu_arm(args):
+    """SURVEY §8d's "what you get today" number: the oracle port of the reference model (HF T5 / ViT modules +
+    nn.TransformerDecoder, i.e. the reference's own module graph) run eagerly by PyTorch on ONE B200, fp32 and
+    under torch.autocast(bfloat16), same batch shape as the B200 arm.  Not part of the driver's contract (it runs
+    `--impl b200` and `--impl reference`); kept so the comparison can be re-measured with one command."""
+    from oracle import ref_model
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    cfg = ref_model.make_config()
+    torch.manual_seed(0)
+    model = ref_model.PhonemeLaTr(cfg, 84, 187, 7).to(dev).train()
+    optim = torch.optim.Adam(model.parameters(), lr=5e-5, betas=(0.9, 0.98), eps=1e-9)
+    sched = torch.optim.lr_scheduler.LinearLR(optim, total_iters=2000)
+    batch = {k: v.to(dev) for k, v in ref_model.synthetic_batch(args.batch, cfg, seed=1234).items()}
+    out = {}
+    for name, amp in (("f32", False), ("bf16_autocast", True)):
+        def step():
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+                loss = ref_model.phoneme_latr_loss(model, batch, 2)
+            optim.zero_grad()
+            loss.backward()
+            optim.step()
+            sched.step()
+            return loss
+        for _ in range(max(args.warmup, 1)):
+            step()
+        torch.cuda.synchronize()
+        a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.steps):
+            last = step()
+        e.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(e) / args.steps
+        out[name] = {"samples_per_s": args.batch / (ms / 1e3), "ms_per_step": ms, "final_loss": float(last.item())}
+    _emit({"impl": "eager-gpu", "metric": "train samples/sec (PhonoLaTr-base)", "unit": "samples/s", "n_gpus": 1,
+           "steps": args.steps, "warmup": max(args.warmup, 1), "data": "synthetic",
+           "config": {"workload": WORKLOAD.format(B=args.batch) + " — reference module graph, PyTorch eager"},
+           "value": out["bf16_autocast"]["samples_per_s"], "dtype": "bf16 autocast", "variants": out})
 
 
 def run_reference_arm(args):
@@ -373,7 +416,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "eager-gpu"])
     ap.add_argument("--batch", type=int, default=64, help="per-GPU batch")
     ap.add_argument("--cpu-batch", type=int, default=4, help="batch of the bounded CPU sample")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
@@ -387,6 +430,10 @@ def main():
     _quiet_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.impl == "eager-gpu":
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py --impl eager-gpu needs a CUDA device")
+        run_eager_gpu_arm(args)
     else:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py --impl b200 needs a CUDA device; there is no CPU fallback "
