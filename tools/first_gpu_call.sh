@@ -1,0 +1,25 @@
+#!/usr/bin/env bash
+# One gpurun call that validates everything written after round 1's GPU budget ran out, in the order that matters:
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- bash tools/first_gpu_call.sh
+# Every step writes its own log under gpurun_out/; a failing step does not stop the later ones.
+set -u
+mkdir -p gpurun_out
+run() { local name=$1; shift; echo "== $name"; timeout 600 "$@" > "gpurun_out/$name.log" 2>&1; echo "   rc=$? ($(tail -n 1 "gpurun_out/$name.log" | cut -c1-150))"; }
+
+python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1
+# 1. the product path: full GPU suite (the model-family tests in test_variants_gpu.py are new), smoke, default bench
+run tests_gpu            python -m pytest tests -m gpu -q -x --deselect tests/test_variants_gpu.py
+run tests_variants       python -m pytest tests/test_variants_gpu.py -m gpu -q
+run smoke                python -c "import __graft_entry__ as g; g.smoke()"
+python bench.py --steps 10 --warmup 3 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
+# 2. the opt-in forward kernel: parity first, then its timing alone and inside the step
+PVQA_TEST_ATTN_V2=1 run tests_attn_v2 python -m pytest tests/test_attn_v2_gpu.py -m gpu -q
+run kbench_attn_v1       python tools/kbench.py attn
+PVQA_ATTN_FWD_V2=1 run kbench_attn_v2 python tools/kbench.py attn
+PVQA_ATTN_FWD_V2=1 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_attn_v2.json 2> gpurun_out/bench_attn_v2.err
+# 3. sibling workloads and the eager-PyTorch comparison (not yet measured)
+python bench.py --workload phonoprestu --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_prestu224.json 2> gpurun_out/bench_prestu224.err
+python bench.py --workload phonoprestu --image 384 --batch 32 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_prestu384.json 2> gpurun_out/bench_prestu384.err
+python bench.py --workload phonosal --batch 32 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_sal.json 2> gpurun_out/bench_sal.err
+python bench.py --impl eager-gpu --batch 64 --steps 5 --warmup 2 > gpurun_out/bench_eager_gpu.json 2> gpurun_out/bench_eager_gpu.err
+ls -la gpurun_out | tail -n 20
