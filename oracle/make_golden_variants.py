@@ -4,9 +4,16 @@
 
 CustomizedLaTr, CustomizedPreSTU and PreSTU run from the reference as they are once `from_pretrained` is replaced by
 config-init (no network); their logits, loss, gradient norms, greedy / beam ids and state_dict layout go to
-tests/golden/model_<name>_tiny.npz.  SaL / CustomizedSaL cannot run here (their T52DStack is written against
-transformers 4.x — SURVEY D8); for those only the state_dict layout of the constructed reference modules is
-recorded when construction succeeds, the numerics are checked against the oracle restatement.
+tests/golden/model_<name>_tiny.npz.
+
+The SaL family (SaL, CustomizedSaL, PhonemeSaL) is written against transformers 4.x: its `T52DStack`
+(core/model/modules/SaL_utils.py:226-500, a copy of the 4.x `T5Stack.forward` with `position_bias` injected) calls
+`self.get_head_mask` (gone in 5.x) and invokes `T5Block` with 4.x keyword names.  `adapt_t52d_stack` below bridges
+exactly those two call conventions — `get_head_mask -> [None] * n`, and a per-block `forward` that drops the 4.x-only
+keywords and passes the rest through — so that the reference's OWN classes run: its embedding composition, its bias
+modules, its `T52DStack.forward` loop, its decoders, heads and losses.  Their outputs go to
+tests/golden/model_{sal,customizedsal,phonemesal}_tiny.npz and pin the oracle restatement (oracle/ref_model.py), which
+reproduces them bit for bit.
 """
 import importlib
 import json
@@ -157,43 +164,115 @@ def golden_phoneme_prestu():
           sum(k.startswith("vit.") for k in out["grad_keys"]))
 
 
-def golden_sal_layouts():
-    """state_dict layout of the reference SaL / CustomizedSaL / PhonemeSaL modules (construction only)."""
-    import transformers
-    out = {}
-    cfg = ref_model.sal_config()
-    for name, args in (("SaL", ()), ("CustomizedSaL", (50,)), ("PhonemeSaL", (253,))):
-        try:
-            mod = importlib.import_module("core.model." + name)
-            if name == "SaL":
-                # transformers 5.x: T5Stack(config) no longer takes the embedding table; give the reference's
-                # `T5Stack(config, shared)` call (SaL_utils.py:513) the 4.x behaviour for construction
-                su = importlib.import_module("core.model.modules.SaL_utils")
-                hf_stack = transformers.models.t5.modeling_t5.T5Stack
+def adapt_t52d_stack(stack):
+    """transformers 4.x -> 5.x call conventions for the reference's T52DStack (see module docstring)."""
+    stack.get_head_mask = lambda head_mask, n, *a, **k: [None] * n
+    for blk in stack.block:
+        def fwd(hidden_states, attention_mask=None, position_bias=None, encoder_hidden_states=None,
+                encoder_attention_mask=None, encoder_decoder_position_bias=None, layer_head_mask=None,
+                cross_attn_layer_head_mask=None, past_key_value=None, use_cache=False, output_attentions=False,
+                hf_forward=blk.forward):
+            # 5.x returns (hidden, position_bias); the stack re-inserts the key/value slot itself when use_cache is False
+            return hf_forward(hidden_states, attention_mask=attention_mask, position_bias=position_bias,
+                              encoder_hidden_states=encoder_hidden_states,
+                              encoder_attention_mask=encoder_attention_mask,
+                              encoder_decoder_position_bias=encoder_decoder_position_bias, use_cache=False,
+                              output_attentions=False)
+        blk.forward = fwd
 
-                def stack_4x(config, embed_tokens=None, hf_stack=hf_stack):
-                    st = hf_stack(config)
-                    if embed_tokens is not None:
-                        st.embed_tokens = embed_tokens
-                    return st
-                su.T5Stack = stack_4x
-                base = mod.T52dForConditionalGeneration
-                mod.T52dForConditionalGeneration = type("T5", (), {"from_pretrained": staticmethod(lambda n, base=base: base(cfg))})
-            else:
-                mod.T52DEncoderModel = type("T5", (), {"from_pretrained": staticmethod(
-                    lambda n, base=mod.T52DEncoderModel: base(cfg))})
-            import functools
-            for cls in ("RelativePositionBias1D", "SCPRelativePositionBias"):      # default device is "cuda"
-                setattr(mod, cls, functools.partial(getattr(mod, cls), device="cpu"))
-            model = getattr(mod, name)(cfg, *args)
-            sd = model.state_dict()
-            out[name + "_keys"] = np.array(list(sd.keys()))
-            out[name + "_shapes"] = np.array([json.dumps(list(v.shape)) for v in sd.values()])
-            print(name, "constructed:", len(sd), "tensors")
-        except Exception as e:                                       # noqa: BLE001
-            print(name, "cannot be constructed here:", type(e).__name__, e)
-    if out:
-        np.savez_compressed(os.path.join(GOLD, "sal_family_layouts.npz"), **out)
+
+def _build_sal_reference(name, cfg, args):
+    import functools
+    import transformers
+    mod = importlib.import_module("core.model." + name)
+    if name == "SaL":
+        su = importlib.import_module("core.model.modules.SaL_utils")
+        hf_stack = transformers.models.t5.modeling_t5.T5Stack
+
+        def stack_4x(config, embed_tokens=None, hf_stack=hf_stack):     # 4.x: T5Stack(config, shared)
+            st = hf_stack(config)
+            if embed_tokens is not None:
+                st.embed_tokens = embed_tokens
+            return st
+        su.T5Stack = stack_4x
+        if not hasattr(mod, "_real_t52d"):
+            mod._real_t52d = mod.T52dForConditionalGeneration
+        mod.T52dForConditionalGeneration = type("T5", (), {"from_pretrained": staticmethod(lambda n: mod._real_t52d(cfg))})
+    else:
+        if not hasattr(mod, "_real_t52d"):
+            mod._real_t52d = mod.T52DEncoderModel
+        mod.T52DEncoderModel = type("T5", (), {"from_pretrained": staticmethod(lambda n: mod._real_t52d(cfg))})
+    for cls in ("RelativePositionBias1D", "SCPRelativePositionBias"):      # default device is "cuda"
+        real = getattr(mod, cls)
+        real = getattr(real, "func", real)
+        setattr(mod, cls, functools.partial(real, device="cpu"))
+    torch.manual_seed(0)
+    model = getattr(mod, name)(cfg, *args)
+    adapt_t52d_stack(model.backbone.encoder if name == "SaL" else model.encoder.encoder)
+    model.load_state_dict(ref_model.deterministic_state_dict(model), strict=True)
+    return model
+
+
+SAL_KEYS = ("input_ids", "src_attention_mask", "tokenized_ocr", "ocr_attention_mask", "ocr_coordinates", "ocr_features",
+            "tokenized_obj", "obj_attention_mask", "obj_coordinates", "obj_features", "max_ocr", "max_ques")
+
+
+def golden_sal_family():
+    """logits / loss / gradient norms / greedy ids of the REAL reference SaL-family classes (adapter above)."""
+    # PhonemeSaL: (logits, loss) from the model itself
+    cfg = ref_model.sal_config()
+    model = _build_sal_reference("PhonemeSaL", cfg, (253,))
+    b = ref_model.sal_batch(3, ref_model.sal_config())
+    fkeys = ("input_ids", "src_attention_mask", "label_ids", "shifted_right_label_ids", "label_attention_mask") + SAL_KEYS[2:]
+    model.eval()
+    out = {"logits": model(**{k: b[k] for k in fkeys})[0].detach().numpy()}
+    _record(model, lambda m: m(**{k: b[k] for k in fkeys})[1], out)
+    with torch.no_grad():
+        out["greedy_ids"] = model.generate(*[b[k] for k in SAL_KEYS], 1, 2, max_len=5).numpy()
+    np.savez_compressed(os.path.join(GOLD, "model_phonemesal_tiny.npz"), **out)
+    print("PhonemeSaL: loss", float(out["loss"]), "greedy", out["greedy_ids"].tolist())
+
+    # CustomizedSaL: logits; the executor owns the loss (CustomizedSaL_Executor.py:255)
+    cfg = ref_model.sal_config()
+    model = _build_sal_reference("CustomizedSaL", cfg, (50,))
+    b = ref_model.customized_sal_batch(3, ref_model.sal_config())
+    fkeys = ("input_ids", "src_attention_mask", "label_ids", "label_attention_mask") + SAL_KEYS[2:]
+    model.eval()
+    out = {"logits": model(**{k: b[k] for k in fkeys}).detach().numpy()}
+    _record(model, lambda m: ref_model.sal_t5_loss(m, b, as_kwargs=True), out)
+    with torch.no_grad():
+        out["greedy_ids"] = model.generate(*[b[k] for k in SAL_KEYS], start_symbol=1, end_symbol=2, max_length=6).numpy()
+        out["beam2_ids"] = model.generate(*[b[k] for k in SAL_KEYS], start_symbol=1, end_symbol=2, max_length=4,
+                                          isgreedy=False, num_beam=2).numpy()
+    np.savez_compressed(os.path.join(GOLD, "model_customizedsal_tiny.npz"), **out)
+    print("CustomizedSaL: loss", float(out["loss"]), "greedy", out["greedy_ids"].tolist(), "beam2", out["beam2_ids"].tolist())
+
+    # SaL: logits over the resized T5 vocabulary; loss in the executor (SaL_Executor.py:221)
+    cfg = ref_model.sal_config()
+    model = _build_sal_reference("SaL", cfg, ())
+    b = ref_model.sal_t5_batch(3, ref_model.sal_config())
+    model.eval()
+    out = {"logits": model(**{k: b[k] for k in fkeys}).detach().numpy()}
+    _record(model, lambda m: ref_model.sal_t5_loss(m, b, as_kwargs=True), out)
+    try:
+        with torch.no_grad():
+            out["generate_ids"] = model.generate(*[b[k] for k in SAL_KEYS], max_length=6).numpy()
+    except Exception as e:                                           # noqa: BLE001
+        print("SaL.generate cannot run under transformers", __import__("transformers").__version__, "->", type(e).__name__,
+              str(e)[:120])
+    np.savez_compressed(os.path.join(GOLD, "model_sal_tiny.npz"), **out)
+    print("SaL: loss", float(out["loss"]), "generate", out.get("generate_ids", np.zeros(0)).tolist())
+
+
+def golden_sal_layouts():
+    """state_dict layout of the reference SaL / CustomizedSaL / PhonemeSaL modules."""
+    out = {}
+    for name, args in (("SaL", ()), ("CustomizedSaL", (50,)), ("PhonemeSaL", (253,))):
+        sd = _build_sal_reference(name, ref_model.sal_config(), args).state_dict()
+        out[name + "_keys"] = np.array(list(sd.keys()))
+        out[name + "_shapes"] = np.array([json.dumps(list(v.shape)) for v in sd.values()])
+        print(name, "constructed:", len(sd), "tensors")
+    np.savez_compressed(os.path.join(GOLD, "sal_family_layouts.npz"), **out)
 
 
 if __name__ == "__main__":
@@ -202,3 +281,4 @@ if __name__ == "__main__":
     golden_prestu()
     golden_phoneme_prestu()
     golden_sal_layouts()
+    golden_sal_family()

@@ -250,10 +250,12 @@ def latr_batch(B, cfg, T=19, L_ocr=12, L_q=6, seed=3, image=32):
 
 # ----------------------------------------------------------------------------------
 # SaL family.  The reference's T52DStack (a copy of HF-4.x T5Stack.forward with `position_bias` injected,
-# core/model/modules/SaL_utils.py:226-500) does not run under transformers 5.5, so the encoder is
+# core/model/modules/SaL_utils.py:226-500) does not run as-is under transformers 5.5, so the encoder is
 # restated as a loop over HF T5Block with the external bias: no attention mask is added when the
-# bias is external, and layer 0's own relative_attention_bias stays an unused parameter.  The bias modules DO
-# import; tests/golden/sal_bias.npz holds their real outputs.
+# bias is external, and layer 0's own relative_attention_bias stays an unused parameter.  Pinning: the real
+# classes DO run through the call-convention adapter of oracle/make_golden_variants.py; their outputs
+# (tests/golden/model_{sal,customizedsal,phonemesal}_tiny.npz, sal_bias.npz) are reproduced bit for bit by these
+# restatements (tests/test_variants_cpu.py).
 # ----------------------------------------------------------------------------------
 def scp_distance_lut(grid=11):
     """core/model/modules/SaL_utils.py:171-195: 5 * Euclidean cell distance, (x, y, x', y')."""
@@ -528,8 +530,8 @@ def prestu_batch(B, cfg, T=19, L_q=14, seed=9, image=32):
 # ----------------------------------------------------------------------------------
 # SaL (core/model/SaL.py:24-140) and CustomizedSaL (core/model/CustomizedSaL.py:29-335) restated like PhonemeSaL
 # above: HF modules composed as the reference composes them, the T52DStack encoder as a loop over HF T5Block with the
-# external bias.  State_dict layouts are pinned to the reference's constructed modules (tests/golden/
-# sal_family_layouts.npz); the forward cannot be run from the reference under transformers 5.5.
+# external bias.  Pinned to the real classes' outputs and layouts (tests/golden/model_{sal,customizedsal}_tiny.npz,
+# sal_family_layouts.npz).
 # ----------------------------------------------------------------------------------
 def _sal_encoder_inputs(m, shared, b):
     obj = (m.obj_feature_layer_norm(m.obj_feature_projector(b["obj_features"]))

@@ -94,3 +94,68 @@ def test_token_embedding_scales_by_sqrt_d():
     ids = torch.tensor([[1, 5, 10]], dtype=torch.int32)
     assert torch.equal(te(ids), te.embedding.weight[ids.long()] * 4.0)
     assert list(te.state_dict().keys()) == ["embedding.weight"]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SaL family: the oracle restatement against outputs of the REAL reference classes (tests/golden/model_{sal,
+# customizedsal,phonemesal}_tiny.npz; the reference runs through the two-line call-convention adapter documented in
+# oracle/make_golden_variants.py)
+# ---------------------------------------------------------------------------------------------------------------
+def _sal_oracle_case(name):
+    cfg = ref_model.sal_config()
+    if name == "PhonemeSaL":
+        model, batch = ref_model.PhonemeSaL(ref_model.sal_config(), 253), ref_model.sal_batch(3, cfg)
+        fwd = lambda m: m(batch)[0]                    # noqa: E731
+        loss = lambda m: m(batch)[1]                   # noqa: E731
+    elif name == "CustomizedSaL":
+        model, batch = ref_model.CustomizedSaL(ref_model.sal_config(), 50), ref_model.customized_sal_batch(3, cfg)
+        fwd = lambda m: m(batch)                       # noqa: E731
+        loss = lambda m: ref_model.sal_t5_loss(m, batch)   # noqa: E731
+    else:
+        model, batch = ref_model.SaL(ref_model.sal_config()), ref_model.sal_t5_batch(3, cfg)
+        fwd = lambda m: m(batch)                       # noqa: E731
+        loss = lambda m: ref_model.sal_t5_loss(m, batch)   # noqa: E731
+    model.load_state_dict(ref_model.deterministic_state_dict(model), strict=True)
+    return model, batch, fwd, loss
+
+
+@pytest.mark.parametrize("name", ["PhonemeSaL", "CustomizedSaL", "SaL"])
+def test_sal_family_oracle_matches_reference_golden(name):
+    g = np.load(os.path.join(GOLD, f"model_{name.lower()}_tiny.npz"))
+    model, batch, fwd, loss_fn = _sal_oracle_case(name)
+    assert list(model.state_dict().keys()) == list(g["state_dict_keys"])
+    model.eval()
+    with torch.no_grad():
+        np.testing.assert_allclose(fwd(model).numpy(), g["logits"], rtol=1e-5, atol=1e-6)
+        if name == "PhonemeSaL":
+            assert np.array_equal(model.generate(batch, 1, 2, max_len=5).numpy(), g["greedy_ids"])
+        elif name == "CustomizedSaL":
+            assert np.array_equal(model.greedy_generate(batch, 1, 2, 6).numpy(), g["greedy_ids"])
+        else:
+            assert np.array_equal(model.generate(batch, max_length=6).numpy(), g["generate_ids"])
+    model.train()
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+        if hasattr(m, "dropout") and isinstance(getattr(m, "dropout"), float):
+            m.dropout = 0.0
+    loss = loss_fn(model)
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), float(g["loss"]), rtol=1e-6)
+    grads = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+    assert sorted(grads) == list(g["grad_keys"])
+    norms = np.array([grads[k].double().norm().item() for k in sorted(grads)])
+    np.testing.assert_allclose(norms, g["grad_norms"], rtol=1e-4, atol=1e-9)
+
+
+def test_customized_sal_beam_ids_follow_the_reference_rule():
+    """the reference's CustomizedSaL.beam_generate output, replayed from the oracle's first-step scores"""
+    from phoneme_vqa_b200.models import reference_beam_select
+    g = np.load(os.path.join(GOLD, "model_customizedsal_tiny.npz"))
+    model, batch, _, _ = _sal_oracle_case("CustomizedSaL")
+    model.eval()
+    with torch.no_grad():
+        enc, mask = model._encode(batch)
+        ys = torch.ones(3, 1, dtype=torch.long)
+        prob = model.lm_head(model.decode(ys, enc, mask)[:, -1])
+    assert np.array_equal(reference_beam_select(prob, ys, 2, 4, 2).numpy(), g["beam2_ids"])
