@@ -492,7 +492,11 @@ attn_bwd_prep_kernel(const AttnPrepParams p) {
   }
 }
 
-template <bool HAS_REL, bool DROP>
+// SCP = false compiles the SaL spatial-bias code out (it sits in the per-element loops: with a run-time flag every
+// score pays its predicated-off bucket extraction, table load and add).  The launcher uses that variant for launches
+// without an SCP bias only when PVQA_ATTN_BWD_LEAN=1 (opt-in until it has been validated on a device; SCP = true is,
+// instruction for instruction, the kernel that was validated).
+template <bool HAS_REL, bool DROP, bool SCP = true>
 __global__ void __launch_bounds__(kBwdThreads2, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
@@ -514,7 +518,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   float* s_drel = s_rel + kRelPad + n_win;                       // [n_win] gradient accumulator (smem atomics)
   float* s_scp = s_drel + n_win;                                 // [32] SCP table of this head
   float* s_dscp = s_scp + 32;                                    // [16 warps][32] SCP gradient bins
-  const bool has_scp = HAS_REL && p.scp_bucket != nullptr;
+  const bool has_scp = SCP && HAS_REL && p.scp_bucket != nullptr;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool is_issuer = warp == kBwdComputeWarps;       // warp 16: TMA, tcgen05.mma and the dQ reduce, nothing else
@@ -1081,8 +1085,11 @@ extern "C" int pvqa_attn_bwd(const void* q, const void* k, const void* v, const 
   const bool rel = rel_bias != nullptr, drop = p.drop_thr8 != 0;
   auto kern = rel ? (drop ? attn_bwd_kernel<true, true> : attn_bwd_kernel<true, false>)
                   : (drop ? attn_bwd_kernel<false, true> : attn_bwd_kernel<false, false>);
-  static bool attr_set[4] = {false, false, false, false};
-  const int vi = (rel ? 2 : 0) + (drop ? 1 : 0);
+  static const bool lean_opt_in = [] { const char* e = getenv("PVQA_ATTN_BWD_LEAN"); return e && e[0] == '1'; }();
+  const bool lean = lean_opt_in && rel && scp_bucket == nullptr;
+  if (lean) kern = drop ? attn_bwd_kernel<true, true, false> : attn_bwd_kernel<true, false, false>;
+  static bool attr_set[6] = {false, false, false, false, false, false};
+  const int vi = lean ? 4 + (drop ? 1 : 0) : (rel ? 2 : 0) + (drop ? 1 : 0);
   if (!attr_set[vi]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
     if (e != cudaSuccess) return fail(PVQA_ERR_CUDA, "attn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));

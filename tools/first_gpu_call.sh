@@ -17,6 +17,11 @@ PVQA_TEST_ATTN_V2=1 run tests_attn_v2 python -m pytest tests/test_attn_v2_gpu.py
 run kbench_attn_v1       python tools/kbench.py attn
 PVQA_ATTN_FWD_V2=1 run kbench_attn_v2 python tools/kbench.py attn
 PVQA_ATTN_FWD_V2=1 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_attn_v2.json 2> gpurun_out/bench_attn_v2.err
+# 2b. the lean backward variant (SCP code compiled out of non-SaL launches): same tests in a process that opts in
+PVQA_ATTN_BWD_LEAN=1 run tests_bwd_lean python -m pytest tests/test_attn_gpu.py tests/test_model_gpu.py -m gpu -q
+PVQA_ATTN_BWD_LEAN=1 run kbench_attn_lean python tools/kbench.py attn
+PVQA_ATTN_BWD_LEAN=1 PVQA_ATTN_FWD_V2=1 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_v2_lean.json 2> gpurun_out/bench_v2_lean.err
+PVQA_ATTN_BWD_LEAN=1 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_lean.json 2> gpurun_out/bench_lean.err
 # 3. sibling workloads and the eager-PyTorch comparison (not yet measured)
 python bench.py --workload phonoprestu --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_prestu224.json 2> gpurun_out/bench_prestu224.err
 python bench.py --workload phonoprestu --image 384 --batch 32 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_prestu384.json 2> gpurun_out/bench_prestu384.err
