@@ -492,11 +492,12 @@ attn_bwd_prep_kernel(const AttnPrepParams p) {
   }
 }
 
-// SCP = false compiles the SaL spatial-bias code out (it sits in the per-element loops: with a run-time flag every
-// score pays its predicated-off bucket extraction, table load and add).  The launcher uses that variant for launches
-// without an SCP bias only when PVQA_ATTN_BWD_LEAN=1 (opt-in until it has been validated on a device; SCP = true is,
+// FULL = false compiles the SaL spatial-bias code and the causal test out.  Both sit in the per-element loops as
+// run-time flags, so every score of a plain bidirectional launch pays their predicated-off bucket extraction, table
+// load and add, and a compare + select for the diagonal.  The launcher uses that variant for non-causal launches
+// without an SCP bias only when PVQA_ATTN_BWD_LEAN=1 (opt-in until it has been validated on a device; FULL = true is,
 // instruction for instruction, the kernel that was validated).
-template <bool HAS_REL, bool DROP, bool SCP = true>
+template <bool HAS_REL, bool DROP, bool FULL = true>
 __global__ void __launch_bounds__(kBwdThreads2, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
@@ -518,7 +519,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   float* s_drel = s_rel + kRelPad + n_win;                       // [n_win] gradient accumulator (smem atomics)
   float* s_scp = s_drel + n_win;                                 // [32] SCP table of this head
   float* s_dscp = s_scp + 32;                                    // [16 warps][32] SCP gradient bins
-  const bool has_scp = SCP && HAS_REL && p.scp_bucket != nullptr;
+  const bool has_scp = FULL && HAS_REL && p.scp_bucket != nullptr;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool is_issuer = warp == kBwdComputeWarps;       // warp 16: TMA, tcgen05.mma and the dQ reduce, nothing else
@@ -709,7 +710,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const float lse2 = (lse_nx != -INFINITY) ? lse_nx * kLog2e : INFINITY;
       const float delta = delta_nx;
       load_stats(it + 1, lse_nx, delta_nx);
-      const bool diag = p.causal && (j0 + kBN - 1 > i0);
+      const bool diag = FULL && p.causal && (j0 + kBN - 1 > i0);
       const float* relrow = s_rel + (p.Sq - 1 - i) + kRelPad;      // relrow[jl] = bias of local key jl for this row
       // P/dS smem is still read by the GEMMs of tile it-1: wait for them right before the stores (long done by then)
       auto wait_prev_gemms = [&]() {
@@ -1086,7 +1087,7 @@ extern "C" int pvqa_attn_bwd(const void* q, const void* k, const void* v, const 
   auto kern = rel ? (drop ? attn_bwd_kernel<true, true> : attn_bwd_kernel<true, false>)
                   : (drop ? attn_bwd_kernel<false, true> : attn_bwd_kernel<false, false>);
   static const bool lean_opt_in = [] { const char* e = getenv("PVQA_ATTN_BWD_LEAN"); return e && e[0] == '1'; }();
-  const bool lean = lean_opt_in && rel && scp_bucket == nullptr;
+  const bool lean = lean_opt_in && rel && scp_bucket == nullptr && !causal;
   if (lean) kern = drop ? attn_bwd_kernel<true, true, false> : attn_bwd_kernel<true, false, false>;
   static bool attr_set[6] = {false, false, false, false, false, false};
   const int vi = lean ? 4 + (drop ? 1 : 0) : (rel ? 2 : 0) + (drop ? 1 : 0);
