@@ -49,6 +49,20 @@ constexpr int kF2OffFloats = kF2OffBar + 128;             // key_add[n_kpad], th
 static_assert(pvqa_f2::kRelPadF2 == kRelPad, "attn_fwd2_layout.h must use the padding of attn.cu");
 using pvqa_f2::rel_copy_stride;
 
+// phase trace (tools/attn_trace.py, private -DPVQA_ATTN_TRACE build only): softmax thread 0 in slots [0,32), the
+// issuer thread in [32,64)
+#ifdef PVQA_ATTN_TRACE
+#define PVQA_TRACE2(ev)                                                                             \
+  do {                                                                                              \
+    if (blockIdx.x == 1 && blockIdx.y == 3 && blockIdx.z < 64 && (ev) < 32) {                       \
+      if (threadIdx.x == 0) g_attn_trace[blockIdx.z * 64 + (ev)] = clock64();                       \
+      if (threadIdx.x == kF2SoftmaxThreads) g_attn_trace[blockIdx.z * 64 + 32 + (ev)] = clock64();  \
+    }                                                                                               \
+  } while (0)
+#else
+#define PVQA_TRACE2(ev)
+#endif
+
 template <bool HAS_REL, bool DROP>
 __global__ void __launch_bounds__(kF2Threads, 2)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -77,6 +91,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int h = blockIdx.y, b = blockIdx.z;
   const bool is_issuer_wg = warp >= kF2SoftmaxThreads / 32;       // warpgroup-uniform
   const bool is_issuer_warp = warp == kF2SoftmaxThreads / 32;
+  PVQA_TRACE2(0);
 
   int n_tiles = n_tiles_all;
   if (p.causal) n_tiles = min(n_tiles, min(i0 + kBM - 1, p.Sq - 1) / kBN + 1);
@@ -140,6 +155,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   tc05::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  PVQA_TRACE2(1);
 
   if (is_issuer_wg) {
     // ------------------------------------------------------------------ issuer: TMA + tcgen05.mma, one thread
@@ -181,6 +197,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             tc05::mma_bf16_ss(tmem_base, tc05::smem_desc_sw128(q_addr + ks * 32, 16, 1024),
                               tc05::smem_desc_sw128(k_addr + ks * 32, 16, 1024), idesc_qk, ks > 0);
           tc05::mma_commit(bar_s);
+          PVQA_TRACE2(2 + 5 * t);                 // issuer: S_{t+1} issued
         }
         // O (+)= P_t V_t: V_t landed, P_t written (and O rescaled) by the softmax warps
         tc05::mbar_wait(bar_v + (t & 1), (t >> 1) & 1);
@@ -193,6 +210,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                             tc05::smem_desc_sw128(p_addr + (ks >> 2) * (kBM * 128) + (ks & 3) * 32, 16, 1024),
                             tc05::smem_desc_sw128(v_addr + ks * 2048, 16, 1024), idesc_pv, (t > 0 || ks > 0) ? 1u : 0u);
         tc05::mma_commit(bar_o);
+        PVQA_TRACE2(3 + 5 * t);                   // issuer: PV_t issued
       }
     }
     __syncwarp();
@@ -222,6 +240,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const bool diag = p.causal && (j0 + kBN - 1 > i0);     // tile touches the diagonal (CTA-uniform)
       tc05::mbar_wait(bar_s, t & 1);
       tc05::tc_fence_after_sync();
+      PVQA_TRACE2(2 + 5 * t);                     // softmax: S_t ready
       // ---- S_t -> registers (once), then hand the TMEM buffer back to the issuer ----
 #pragma unroll
       for (int c = 0; c < 4; ++c)
@@ -230,6 +249,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tc05::tmem_ld_wait();
       tc05::tc_fence_before_sync();
       tc05::mbar_arrive(bar_sfree);
+      PVQA_TRACE2(3 + 5 * t);                     // softmax: S_t in registers
 
       // ---- biased scores in the exp2 domain and the row max ----
       float mx = -INFINITY;
@@ -271,6 +291,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
       const float alpha = fast_exp2(m_run - m_safe);      // 1 when the max did not move, 0 for the first live tile
       const float m_sub = m_safe - m_shift;
+      PVQA_TRACE2(4 + 5 * t);                     // softmax: bias + max done
 
       if (t > 0) {
         // O += P_{t-1} V_{t-1} has completed: O may be rescaled and the P buffer may be overwritten
@@ -290,6 +311,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
       }
 
+      PVQA_TRACE2(5 + 5 * t);                     // softmax: O_{t-1} complete (and rescaled)
       // ---- p = exp2(s - m) (dropout folded in), row sum, bf16 P -> smem (K-major, 128B swizzle) ----
       float sum = 0.f;
 #pragma unroll
@@ -333,11 +355,13 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tc05::fence_proxy_async_smem();
       tc05::tc_fence_before_sync();
       tc05::mbar_arrive(bar_p);
+      PVQA_TRACE2(6 + 5 * t);                     // softmax: P_t stored
     }
 
     // ---- epilogue: O (TMEM) / l -> bf16 rows, lse (natural log) ----
     tc05::mbar_wait(bar_o, (n_tiles - 1) & 1);
     tc05::tc_fence_after_sync();
+    PVQA_TRACE2(29);                              // softmax: last product done
     if (!rows_dead) {
       const float inv = l_run > 0.f ? (DROP ? p.drop_scale : 1.f) / l_run : 0.f;
       __nv_bfloat16* orow = p.o + (long long)b * p.o_stride_b + (long long)min(i, p.Sq - 1) * p.o_stride_s +
@@ -360,8 +384,10 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             l_run > 0.f ? (m_run + log2f(l_run) - m_shift) * (1.0f / kLog2e) : -INFINITY;
     }
   }
+  PVQA_TRACE2(30);
   tc05::tc_fence_before_sync();
   __syncthreads();
+  PVQA_TRACE2(31);
   if (is_issuer_warp) tc05::tmem_dealloc(tmem_base, kF2TmemCols);
 }
 

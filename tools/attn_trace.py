@@ -18,6 +18,12 @@ FWD_EV = {0: "start", 1: "prologue done", 30: "epilogue stores issued", 31: "end
 for t in range(4):
     FWD_EV.update({2 + 6 * t: f"t{t} S ready", 3 + 6 * t: f"t{t} pass A done", 4 + 6 * t: f"t{t} max exchanged",
                    5 + 6 * t: f"t{t} pass B done", 6 + 6 * t: f"t{t} O_j ready", 7 + 6 * t: f"t{t} tile end"})
+# second-generation forward (PVQA_ATTN_FWD_V2=1): softmax thread 0 | issuer thread
+FWD2_EV = {0: "start", 1: "prologue done", 29: "last PV done", 30: "epilogue stores issued", 31: "end"}
+for t in range(5):
+    FWD2_EV.update({2 + 5 * t: f"t{t} S ready | S(t+1) issued", 3 + 5 * t: f"t{t} S in registers | PV issued",
+                    4 + 5 * t: f"t{t} bias + max done", 5 + 5 * t: f"t{t} O(t-1) complete, rescaled",
+                    6 + 5 * t: f"t{t} P stored"})
 BWD_EV = {0: "start", 1: "prologue done", 25: "last GEMMs done", 26: "last dQ staged", 27: "dK/dV stored", 28: "bins synced",
           30: "epilogue stores issued", 31: "end"}
 for t in range(5):
@@ -40,7 +46,7 @@ def report(tr, names, title):
     import numpy as np
     tr = np.asarray(tr, dtype=np.int64).reshape(64, 64)
     print(f"== {title}")
-    for who, base in (("thread 0", 0), ("last warp", 32)):
+    for who, base in (("thread 0", 0), ("last warp / issuer", 32)):
         ev = tr[:, base:base + 32]
         live = ev[:, 0] > 0
         ev = ev[live]
@@ -82,7 +88,8 @@ def main():
         o, lse = ops.attention_fwd_raw(q, k, v, 1.0, rb, ka, False, drop)
         torch.cuda.synchronize()
         lib.pvqa_debug_attn_trace(ctypes.addressof(buf), 1)
-        report(list(buf), FWD_EV, f"fwd enc_self B={B} p={p}")
+        report(list(buf), FWD2_EV if ops.ATTN_FWD_V2 else FWD_EV,
+               f"fwd{' v2' if ops.ATTN_FWD_V2 else ''} enc_self B={B} p={p}")
         dkv = torch.empty_like(kv)
         for _ in range(2):
             ops.attention_bwd_raw(q, k, v, o, go, lse, 1.0, rb, ka, False, dkv[:, :, 0], dkv[:, :, 1], True, drop)

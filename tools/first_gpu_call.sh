@@ -27,4 +27,6 @@ python bench.py --workload phonoprestu --steps 5 --warmup 3 --no-cpu-baseline > 
 python bench.py --workload phonoprestu --image 384 --batch 32 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_prestu384.json 2> gpurun_out/bench_prestu384.err
 python bench.py --workload phonosal --batch 32 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_sal.json 2> gpurun_out/bench_sal.err
 python bench.py --impl eager-gpu --batch 64 --steps 5 --warmup 2 > gpurun_out/bench_eager_gpu.json 2> gpurun_out/bench_eager_gpu.err
-ls -la gpurun_out | tail -n 20
+
+PVQA_ATTN_FWD_V2=1 run attn_trace_v2 bash -c "python tools/attn_trace.py build && python tools/attn_trace.py 64"
+ls -la gpurun_out | tail -n 24
