@@ -23,7 +23,7 @@ from .modules import (SHADOWS, BaseDecoder, RelativePositionBias1D, RelativePosi
 
 __all__ = ["LaTr_config", "PreSTU_config", "SaL_config", "CustomizedLaTr_config", "CustomizedPreSTU_config",
            "CustomizedSaL_config", "LaTr", "PreSTU", "SaL", "CustomizedLaTr", "CustomizedPreSTU", "CustomizedSaL",
-           "PhonemeLaTr", "PhonemePreSTU", "PhonemeSaL"]
+           "PhonemeLaTr", "PhonemePreSTU", "PhonemeSaL", "phoneme_beam_search", "reference_beam_select"]
 
 
 def _random_init(config) -> bool:
@@ -349,6 +349,35 @@ class PhonemeLaTr(nn.Module, _VisionMixin):
                 break
         return ys
 
+    # -- beam search over the factorised (onset, rhyme, tone) product -------------------------
+    @torch.no_grad()
+    def beam_generate(self, pixel_values, coordinates, input_ids, src_attention_mask, ocr_attention_mask,
+                      tokenized_ocr, start_symbol, end_symbol, max_len=100, num_beam=2):
+        """Beam search with the key/value cache.  The reference's core class ignores `isgreedy` / `num_beam`
+        (`generate` above stays greedy, like core/model/PhonemeLaTr.py:146-167); the prototype it was refactored
+        from scores a triple by log p(onset) + log p(rhyme) + log p(tone) and ranks the full V_o x V_r x V_t product
+        with Python loops (PhonoLaTr/ModelLaTr.py:294-377).  This is that scoring rule as a standard batched beam
+        search: the joint top-k is taken exactly from the per-head top-k lists (`phoneme_beam_search`), all beams of
+        all samples go through ONE cached decoder step per position, finished beams are frozen."""
+        enc, attention_mask = self._encode(pixel_values, coordinates, input_ids, ocr_attention_mask,
+                                           src_attention_mask, tokenized_ocr)
+        bz, K = enc.shape[0], int(num_beam)
+        mem = enc.repeat_interleave(K, dim=0)
+        mask = attention_mask.repeat_interleave(K, dim=0)
+        cache = self.decoder.new_cache(mem, max_len + 1, self.compute_dtype)
+        pe = self.positional_encoding.pos_embedding
+
+        def step(tok, t, src):
+            if src is not None:
+                cache.reorder(src)
+            cache.len = t
+            emb = self.tgt_tok_emb(tok, pe[:, t:t + 1], out_dtype=torch.float32)
+            out = self.decoder.step(emb, cache, mask, self.compute_dtype)
+            # like the greedy loop (reference :195-205) the heads read the decoder output directly
+            return tuple(torch.log_softmax(x[:, -1].float(), dim=-1) for x in self._heads(out.to(self.compute_dtype)))
+
+        return phoneme_beam_search(step, bz, K, start_symbol, end_symbol, max_len, enc.device)
+
     def _decode_step_ids(self, tok, t, cache, attention_mask):
         """one cached greedy step: last emitted triples (B,1,3) at target position t -> next triples (B,3)"""
         emb = self.tgt_tok_emb(tok, self.positional_encoding.pos_embedding[:, t:t + 1], out_dtype=torch.float32)
@@ -413,6 +442,60 @@ class PhonemeLaTr(nn.Module, _VisionMixin):
                     n_done = int(first.max())
                     break
         return ws["ys"][:, :n_done + 1].clone()
+
+
+def phoneme_beam_search(step, bz, num_beam, start_symbol, end_symbol, max_len, device):
+    """Batched beam search over phoneme triples.
+
+    step(tok (bz*K, 1, 3) int64, t, src (bz*K,) int64 or None) -> three log-prob tensors (bz*K, V_o / V_r / V_t) for
+    target position t + 1; `src[n]` names the row (of the previous call) whose state row n continues.
+    Score of a hypothesis = sum over positions of log p(onset) + log p(rhyme) + log p(tone).  Because that sum is
+    separable, the K best triples of one beam lie in the product of the K best entries of each head, so the joint
+    top-K over all K * V_o * V_r * V_t continuations is found exactly among K * K^3 candidates.  A beam that has
+    emitted `end_symbol` (onset column) is finished: it keeps its score and is extended by (end_symbol, 0, 0) only.
+    Returns (bz, L, 3): the best hypothesis per sample, L <= max_len + 1, positions after <eos> hold (end_symbol, 0, 0).
+    Ties are broken by torch.topk's order (lower flat index first)."""
+    K = num_beam
+    NEG = float("-inf")
+    seqs = torch.zeros((bz, K, 1, 3), dtype=torch.long, device=device)
+    seqs[:, :, 0, 0] = start_symbol
+    scores = torch.full((bz, K), NEG, device=device)
+    scores[:, 0] = 0.0                                   # all beams start identical: only beam 0 may expand
+    finished = torch.zeros((bz, K), dtype=torch.bool, device=device)
+    src = None
+    base = (torch.arange(bz, device=device) * K)[:, None]
+    for t in range(max_len):
+        on, rh, to = step(seqs[:, :, -1].reshape(bz * K, 1, 3), t, src)
+        k_o, k_r, k_t = min(K, on.shape[-1]), min(K, rh.shape[-1]), min(K, to.shape[-1])
+        ov, oi = on.view(bz, K, -1).topk(k_o, dim=-1)
+        rv, ri = rh.view(bz, K, -1).topk(k_r, dim=-1)
+        tv, ti = to.view(bz, K, -1).topk(k_t, dim=-1)
+        joint = ov[:, :, :, None, None] + rv[:, :, None, :, None] + tv[:, :, None, None, :]     # (bz,K,ko,kr,kt)
+        # finished beams: one continuation, (end, 0, 0), at no cost
+        only_first = torch.full_like(joint, NEG)
+        only_first[:, :, 0, 0, 0] = 0.0
+        joint = torch.where(finished[:, :, None, None, None], only_first, joint)
+        cand = (scores[:, :, None, None, None] + joint).reshape(bz, -1)
+        scores, flat = cand.topk(K, dim=-1)
+        per_beam = k_o * k_r * k_t
+        beam = flat // per_beam
+        rem = flat % per_beam
+        a, b_, c = rem // (k_r * k_t), (rem // k_t) % k_r, rem % k_t
+        was_finished = finished.gather(1, beam)
+        new_o = oi[torch.arange(bz, device=device)[:, None], beam, a]
+        new_r = ri[torch.arange(bz, device=device)[:, None], beam, b_]
+        new_t = ti[torch.arange(bz, device=device)[:, None], beam, c]
+        new_o = torch.where(was_finished, torch.full_like(new_o, end_symbol), new_o)
+        new_r = torch.where(was_finished, torch.zeros_like(new_r), new_r)
+        new_t = torch.where(was_finished, torch.zeros_like(new_t), new_t)
+        nxt = torch.stack([new_o, new_r, new_t], dim=-1)                                          # (bz,K,3)
+        seqs = torch.cat([seqs.gather(1, beam[:, :, None, None].expand(-1, -1, seqs.shape[2], 3)), nxt[:, :, None]], dim=2)
+        finished = was_finished | (new_o == end_symbol)
+        src = (base + beam).reshape(-1)
+        if bool(finished.all()):
+            break
+    best = scores.argmax(dim=-1)
+    return seqs[torch.arange(bz, device=device), best]
 
 
 class PhonemePreSTU(nn.Module, _VisionMixin):

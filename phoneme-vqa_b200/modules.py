@@ -630,6 +630,13 @@ class DecoderCache:
         self.set_memory(memory)
 
     @torch.no_grad()
+    def reorder(self, src):
+        """beam search: row n of the self-attention cache continues row src[n] (the memory K/V are per sample and
+        identical across the beams of a sample, so they stay where they are)"""
+        for li, buf in enumerate(self.self_kv):
+            self.self_kv[li] = buf.index_select(0, src)
+
+    @torch.no_grad()
     def set_memory(self, memory):
         """project a new encoder memory into the (address-stable) cross-attention K/V buffers and rewind"""
         B, S, d = memory.shape

@@ -159,3 +159,92 @@ def test_customized_sal_beam_ids_follow_the_reference_rule():
         ys = torch.ones(3, 1, dtype=torch.long)
         prob = model.lm_head(model.decode(ys, enc, mask)[:, -1])
     assert np.array_equal(reference_beam_select(prob, ys, 2, 4, 2).numpy(), g["beam2_ids"])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# factorised beam search: the batched, cache-reordering implementation against a naive
+# per-sample search over the FULL onset x rhyme x tone product
+# ---------------------------------------------------------------------------------------------------------------
+class _ToyDecoder:
+    """stateful stand-in for the cached decoder step: the log-probs of a row depend on the whole history of that
+    row (a running hash), so a wrong cache reorder changes the result"""
+
+    def __init__(self, bz, K, vocab, seed):
+        g = torch.Generator().manual_seed(seed)
+        self.V = vocab
+        self.W = [torch.randn(64, v, generator=g) * 2.0 for v in vocab]
+        self.sample_bias = torch.randn(bz, 64, generator=g)
+        self.K = K
+        self.state = None
+
+    def _feat(self, state):
+        idx = torch.arange(64)[None, :]
+        return torch.sin(state[:, None].double() * (idx + 1) * 0.37).float()
+
+    def logp(self, state, sample):
+        f = self._feat(state) + self.sample_bias[sample]
+        return [torch.log_softmax(f @ w, dim=-1) for w in self.W]
+
+    @staticmethod
+    def advance(state, tok):
+        return (state * 31 + tok[:, 0] * 7 + tok[:, 1] * 3 + tok[:, 2] + 1) % 1000003
+
+    def step(self, tok, t, src):
+        n = tok.shape[0]
+        sample = torch.arange(n) // self.K
+        if self.state is None:
+            self.state = torch.zeros(n, dtype=torch.long)
+        if src is not None:
+            self.state = self.state[src]
+        self.state = self.advance(self.state, tok[:, 0])
+        return tuple(self.logp(self.state, sample))
+
+
+def _naive_beam(toy, sample, K, start, end, max_len):
+    beams = [(0.0, [[start, 0, 0]], False, toy.advance(torch.zeros(1, dtype=torch.long), torch.tensor([[start, 0, 0]])))]
+    for _ in range(max_len):
+        cands = []
+        for score, seq, fin, state in beams:
+            if fin:
+                cands.append((score, seq + [[end, 0, 0]], True, state))
+                continue
+            on, rh, to = toy.logp(state, torch.tensor([sample]))
+            for o in range(toy.V[0]):
+                for r in range(toy.V[1]):
+                    for c in range(toy.V[2]):
+                        s = score + float(on[0, o]) + float(rh[0, r]) + float(to[0, c])
+                        tok = [o, r, c]
+                        cands.append((s, seq + [tok], o == end, toy.advance(state, torch.tensor([tok]))))
+        cands.sort(key=lambda x: -x[0])
+        beams = cands[:K]
+        if all(b[2] for b in beams):
+            break
+    return beams[0][1], beams[0][0]
+
+
+@pytest.mark.parametrize("K", [1, 2, 3, 5])
+def test_factorised_beam_search_equals_full_product_search(K):
+    from phoneme_vqa_b200.models import phoneme_beam_search
+    bz, vocab, start, end, max_len = 3, (6, 5, 4), 0, 1, 7
+    toy = _ToyDecoder(bz, K, vocab, seed=10 + K)
+    got = phoneme_beam_search(toy.step, bz, K, start, end, max_len, torch.device("cpu"))
+    assert got.dtype == torch.long and got.shape[0] == bz and got.shape[2] == 3
+    for b in range(bz):
+        want, _ = _naive_beam(toy, b, K, start, end, max_len)
+        assert got[b, : len(want)].tolist() == want, (b, got[b].tolist(), want)
+
+
+def test_beam_search_with_one_beam_is_greedy():
+    from phoneme_vqa_b200.models import phoneme_beam_search
+    bz, vocab = 4, (7, 6, 3)
+    toy = _ToyDecoder(bz, 1, vocab, seed=3)
+    got = phoneme_beam_search(toy.step, bz, 1, 0, 1, 6, torch.device("cpu"))
+    state = toy.advance(torch.zeros(bz, dtype=torch.long), torch.tensor([[0, 0, 0]] * bz))
+    done = torch.zeros(bz, dtype=torch.bool)
+    for t in range(1, got.shape[1]):
+        on, rh, to = toy.logp(state, torch.arange(bz))
+        tok = torch.stack([on.argmax(-1), rh.argmax(-1), to.argmax(-1)], dim=-1)
+        tok = torch.where(done[:, None], torch.tensor([[1, 0, 0]]), tok)
+        assert torch.equal(got[:, t], tok)
+        done = done | (tok[:, 0] == 1)
+        state = toy.advance(state, tok)

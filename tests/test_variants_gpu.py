@@ -204,3 +204,32 @@ def test_sal_variants_match_oracle(name, dtype):
         assert worst[0][1] <= 1e-3, worst
     else:
         assert all(torch.isfinite(v).all() for v in got.values())
+
+
+def test_phoneme_latr_beam_search_with_kv_cache():
+    """SURVEY §8f rank 1.  One beam == the reference's greedy ids; several beams == the same search driven by the
+    reference-style uncached decode over the growing prefix (so cache reordering is exercised), and the winning
+    hypothesis never scores below the greedy one."""
+    import phoneme_vqa_b200.models as M
+    g = np.load(os.path.join(GOLD, "model_phonemelatr_tiny.npz"))
+    cfg = ref_model.tiny_config()
+    model = M.PhonemeLaTr(cfg, *VOCAB)
+    model.load_state_dict(ref_model.deterministic_state_dict(model), strict=True)
+    model = model.to(DEV).eval()
+    batch = ref_model.synthetic_batch(3, cfg, T=9, L_ocr=12, L_q=6, V_sub=VOCAB, seed=7, image=32)
+    args = [batch[k].to(DEV) for k in ref_model.LATR_KEYS]
+    one = model.beam_generate(*args, start_symbol=3, end_symbol=4, max_len=6, num_beam=1)
+    assert np.array_equal(one.cpu().numpy(), g["greedy_ids"][:, : one.shape[1]])
+    K = 3
+    got = model.beam_generate(*args, start_symbol=3, end_symbol=4, max_len=5, num_beam=K)
+    with torch.no_grad():
+        enc, mask = model._encode(args[0], args[1], args[2], args[4], args[3], args[5])
+        mem, mk = enc.repeat_interleave(K, dim=0), mask.repeat_interleave(K, dim=0)
+        hist = {"seq": None}
+
+        def step(tok, t, src):
+            hist["seq"] = tok if hist["seq"] is None else torch.cat([hist["seq"][src], tok], dim=1)
+            out = model.decode(hist["seq"], mem, mk)[:, -1:]
+            return tuple(torch.log_softmax(x[:, -1].float(), dim=-1) for x in model._heads(out))
+        want = M.phoneme_beam_search(step, 3, K, 3, 4, 5, torch.device(DEV))
+    assert torch.equal(got, want)
