@@ -361,6 +361,9 @@ class PhonemeLaTr(nn.Module, _VisionMixin):
         all samples go through ONE cached decoder step per position, finished beams are frozen."""
         enc, attention_mask = self._encode(pixel_values, coordinates, input_ids, ocr_attention_mask,
                                            src_attention_mask, tokenized_ocr)
+        return self._beam_from_memory(enc, attention_mask, start_symbol, end_symbol, max_len, num_beam)
+
+    def _beam_from_memory(self, enc, attention_mask, start_symbol, end_symbol, max_len, num_beam):
         bz, K = enc.shape[0], int(num_beam)
         mem = enc.repeat_interleave(K, dim=0)
         mask = attention_mask.repeat_interleave(K, dim=0)
@@ -560,6 +563,16 @@ class PhonemePreSTU(nn.Module, _VisionMixin):
     def generate(self, pixel_values, input_ids, src_attention_mask, start_symbol, end_symbol, max_length=20,
                  isgreedy=True, num_beam=2):
         return self.greedy_generate(pixel_values, input_ids, src_attention_mask, start_symbol, end_symbol, max_length)
+
+    _beam_from_memory = PhonemeLaTr._beam_from_memory
+
+    @torch.no_grad()
+    def beam_generate(self, pixel_values, input_ids, src_attention_mask, start_symbol, end_symbol, max_len=100,
+                      num_beam=2):
+        """factorised beam search with the key/value cache (see PhonemeLaTr.beam_generate)"""
+        inputs_embeds, attention_mask = self._calculate_embedding(pixel_values, input_ids, src_attention_mask)
+        enc = self.encoder.encoder(inputs_embeds, attention_mask, compute_dtype=self.compute_dtype)
+        return self._beam_from_memory(enc, attention_mask, start_symbol, end_symbol, max_len, num_beam)
 
     @torch.no_grad()
     def greedy_generate(self, pixel_values, input_ids, src_attention_mask, start_symbol, end_symbol, max_len=100,
