@@ -12,7 +12,7 @@ import torch
 
 import test_attn_gpu as base
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300, method="thread"),
               pytest.mark.skipif(os.environ.get("PVQA_TEST_ATTN_V2", "0") != "1",
                                  reason="opt-in kernel: set PVQA_TEST_ATTN_V2=1 (not yet validated on a device)")]
 DEV = "cuda:0"

@@ -17,7 +17,7 @@ import torch
 
 from oracle import ref_model
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600, method="thread")]   # a hung launch cannot be interrupted by a signal
 DEV = "cuda:0"
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
