@@ -213,7 +213,7 @@ int pvqa_attn_fwd(const void* q, const void* k, const void* v, void* o, float* l
  * pvqa_attn_bwd consumes its lse / o unchanged).  One thread per query row: the score tile is read from TMEM once,
  * O accumulates in TMEM across key tiles, the next tile's QK^T is issued while the current softmax runs, the T5
  * bias is read with 128-bit shared loads (phoneme-vqa_b200/csrc/attn_fwd2.cuh).  OPT-IN (host: PVQA_ATTN_FWD_V2=1):
- * written after round 1's GPU budget was spent, compiled and host-checked but not yet validated on a device. */
+ * results agree with pvqa_attn_fwd on the device (profiles/r01_optin_kernels_probe.log) but it is not yet faster. */
 int pvqa_attn_fwd_v2(const void* q, const void* k, const void* v, void* o, float* lse,
                      const float* rel_bias, const float* key_add,
                      int64_t B, int64_t H, int64_t Sq, int64_t Sk, int64_t D,

@@ -1086,7 +1086,8 @@ extern "C" int pvqa_attn_bwd(const void* q, const void* k, const void* v, const 
   const bool rel = rel_bias != nullptr, drop = p.drop_thr8 != 0;
   auto kern = rel ? (drop ? attn_bwd_kernel<true, true> : attn_bwd_kernel<true, false>)
                   : (drop ? attn_bwd_kernel<false, true> : attn_bwd_kernel<false, false>);
-  static const bool lean_opt_in = [] { const char* e = getenv("PVQA_ATTN_BWD_LEAN"); return e && e[0] == '1'; }();
+  const char* lean_env = getenv("PVQA_ATTN_BWD_LEAN");      // read per call: cheap, and a process can compare both variants
+  const bool lean_opt_in = lean_env && lean_env[0] == '1';
   const bool lean = lean_opt_in && rel && scp_bucket == nullptr && !causal;
   if (lean) kern = drop ? attn_bwd_kernel<true, true, false> : attn_bwd_kernel<true, false, false>;
   static bool attr_set[6] = {false, false, false, false, false, false};

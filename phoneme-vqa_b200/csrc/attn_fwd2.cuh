@@ -1,9 +1,10 @@
 // attn_fwd2.cuh — second-generation attention forward (same contract as pvqa_attn_fwd; included by attn.cu).
 //
-// OPT-IN: exported as pvqa_attn_fwd_v2 and selected by the host only when PVQA_ATTN_FWD_V2=1.  It was written
-// after round 1's GPU budget was spent: it compiles for sm_100a and its index arithmetic is unit-tested on the
-// host (tests/test_attn_v2_layout_cpu.py), but it has NOT run on a GPU yet.  pvqa_attn_fwd stays the product path
-// until the parity tests in tests/test_attn_gpu.py pass with the switch on.
+// OPT-IN: exported as pvqa_attn_fwd_v2 and selected by the host only when PVQA_ATTN_FWD_V2=1.  First device run
+// (profiles/r01_optin_kernels_probe.log, _timing.log): results agree with attn_fwd_kernel (lse within 1e-6, o within
+// one bf16 ulp) on plain / bias / dropout / causal / cross cases, but at the bench shape it is 5 % SLOWER (148 vs
+// 142 us): half as many softmax warps per SM hide less latency than the halved instruction count buys.  It stays off
+// until that is fixed (two query tiles per CTA); pvqa_attn_fwd is the product path.
 //
 // Why a second kernel (measured on the first one, profiles/r01_attn_ncu_b64_v2.txt, r01_attn_phase_trace.txt):
 //   * every score is read from TMEM twice (pass A: bias + max, written back; pass B: exp) because a row is shared

@@ -1,9 +1,9 @@
-"""The opt-in second-generation forward kernel (pvqa_attn_fwd_v2, csrc/attn_fwd2.cuh) against the same oracle cases
-as the product kernel, plus bit-level agreement with it.
+"""The opt-in attention kernels — forward v2 (pvqa_attn_fwd_v2, csrc/attn_fwd2.cuh) and the lean backward
+(PVQA_ATTN_BWD_LEAN=1) — against the same oracle cases as the product kernels, plus direct comparisons with them.
 
-Skipped unless PVQA_TEST_ATTN_V2=1: the kernel was written after round 1's GPU budget was spent and has not run on a
-device yet; `PVQA_TEST_ATTN_V2=1 python -m pytest tests/test_attn_v2_gpu.py -m gpu` is the first thing to run before
-flipping ops.ATTN_FWD_V2 on."""
+Skipped unless PVQA_TEST_ATTN_V2=1: neither is a default path yet.  Both passed a five-case probe on the device at
+the very end of round 1 (profiles/r01_optin_kernels_probe.log); this file is the full check to run before a switch
+is flipped: `PVQA_TEST_ATTN_V2=1 python -m pytest tests/test_attn_v2_gpu.py -m gpu`."""
 import math
 import os
 
@@ -14,7 +14,7 @@ import test_attn_gpu as base
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300, method="thread"),
               pytest.mark.skipif(os.environ.get("PVQA_TEST_ATTN_V2", "0") != "1",
-                                 reason="opt-in kernel: set PVQA_TEST_ATTN_V2=1 (not yet validated on a device)")]
+                                 reason="opt-in kernels: set PVQA_TEST_ATTN_V2=1")]
 DEV = "cuda:0"
 
 
@@ -76,3 +76,31 @@ def test_v2_agrees_with_the_product_kernel(B, Sq, Sk, H, causal, p, monkeypatch)
     torch.testing.assert_close(o2.float(), o1.float(), rtol=2e-2, atol=2e-3)
     if p > 0:   # V = identity trick is in the dropout test; here: the same entries of o are exactly zero-contribution
         assert (o2.float() - o1.float()).abs().max().item() < 5e-2
+
+
+@pytest.mark.parametrize("p", [0.0, 0.25])
+def test_lean_backward_equals_full_backward(p, monkeypatch):
+    """PVQA_ATTN_BWD_LEAN=1 (SCP + causal code compiled out of plain bidirectional launches) against the validated
+    kernel on the same inputs and dropout triple — the launcher reads the switch per call"""
+    from phoneme_vqa_b200 import ops
+    monkeypatch.setattr(ops, "ATTN_FWD_V2", False)
+    B, S, H = 2, 327, 3
+    g = torch.Generator().manual_seed(11)
+    q = (torch.randn(B, S, H, 64, generator=g) * 0.4).bfloat16().to(DEV)
+    kv = (torch.randn(B, S, 2, H, 64, generator=g) * 0.4).bfloat16().to(DEV)
+    k, v = kv[:, :, 0], kv[:, :, 1]
+    rel = torch.randn(H, 2 * S - 1, generator=g).to(DEV)
+    ka = torch.where(torch.rand(B, S, generator=g) > 0.2, 0.0, float("-inf"))
+    ka[:, 0] = 0.0
+    ka = ka.to(DEV)
+    go = torch.randn(B, S, H, 64, generator=g).bfloat16().to(DEV)
+    drop = (p, 99, 5) if p > 0 else (0.0, 0, 0)
+    o, lse = ops.attention_fwd_raw(q, k, v, 1.0, rel, ka, False, drop)
+    res = {}
+    for lean in ("0", "1"):
+        monkeypatch.setenv("PVQA_ATTN_BWD_LEAN", lean)
+        dkv = torch.zeros_like(kv)
+        dq, d_rel, _ = ops.attention_bwd_raw(q, k, v, o, go, lse, 1.0, rel, ka, False, dkv[:, :, 0], dkv[:, :, 1], True, drop)
+        res[lean] = (dq, dkv, d_rel)
+    for a, b in zip(res["0"], res["1"]):
+        torch.testing.assert_close(a.float(), b.float(), rtol=1e-5, atol=1e-6)
