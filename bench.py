@@ -369,7 +369,7 @@ def attention_flops(name, B, cfg):
     """attn_{fwd,bwd}[Sq=..,Sk=..]: 4*B*H*Sq*Sk*D forward (2 GEMMs), 2.5x that backward (5 GEMMs);
     the causal decoder self-attention (Sq == Sk == T) only needs the lower triangle."""
     import re
-    m = re.match(r"attn_(fwd|bwd)(?:_v2)?\[Sq=(\d+),Sk=(\d+)\]", name)
+    m = re.match(r"attn_(fwd|bwd)(?:_v[23])?\[Sq=(\d+),Sk=(\d+)\]", name)
     if not m:
         return None
     sq, sk = int(m.group(2)), int(m.group(3))

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PVQA_ABI_VERSION 6
+#define PVQA_ABI_VERSION 7
 
 typedef enum {
   PVQA_OK = 0,
@@ -215,6 +215,22 @@ int pvqa_attn_fwd(const void* q, const void* k, const void* v, void* o, float* l
  * bias is read with 128-bit shared loads (phoneme-vqa_b200/csrc/attn_fwd2.cuh).  OPT-IN (host: PVQA_ATTN_FWD_V2=1):
  * results agree with pvqa_attn_fwd on the device (profiles/r01_optin_kernels_probe.log) but it is not yet faster. */
 int pvqa_attn_fwd_v2(const void* q, const void* k, const void* v, void* o, float* lse,
+                     const float* rel_bias, const float* key_add,
+                     int64_t B, int64_t H, int64_t Sq, int64_t Sk, int64_t D,
+                     int64_t q_stride_b, int64_t q_stride_s, int64_t q_stride_h,
+                     int64_t k_stride_b, int64_t k_stride_s, int64_t k_stride_h,
+                     int64_t v_stride_b, int64_t v_stride_s, int64_t v_stride_h,
+                     int64_t o_stride_b, int64_t o_stride_s, int64_t o_stride_h,
+                     float scale, int causal,
+                     float dropout_p, uint64_t seed, uint64_t offset,
+                     const uint8_t* scp_bucket, const float* scp_table, int64_t scp_q0, int64_t scp_L,
+                     void* stream);
+
+/* Third-generation forward (phoneme-vqa_b200/csrc/attn_fwd3.cuh), same contract again.  Keeps pvqa_attn_fwd's two
+ * threads per query row (16 softmax warps per SM — what v2's first device run showed to matter) and adds v2's
+ * mechanisms: scores held in registers across the row-max exchange, O accumulated in TMEM, a separate issuer warp.
+ * OPT-IN (host: PVQA_ATTN_FWD_V3=1); written after round 1's GPU budget was spent, not yet run on a device. */
+int pvqa_attn_fwd_v3(const void* q, const void* k, const void* v, void* o, float* lse,
                      const float* rel_bias, const float* key_add,
                      int64_t B, int64_t H, int64_t Sq, int64_t Sk, int64_t D,
                      int64_t q_stride_b, int64_t q_stride_s, int64_t q_stride_h,

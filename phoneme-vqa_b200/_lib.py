@@ -18,7 +18,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libpvqa_sm100.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 SOURCES = ["api.cu", "embed.cu", "head.cu", "attn.cu", "attn_simt.cu", "norm.cu"]
-HEADERS = ["common.cuh", "tc05.cuh", "attn_fwd2.cuh", "attn_fwd2_layout.h"]
+HEADERS = ["common.cuh", "tc05.cuh", "attn_fwd2.cuh", "attn_fwd3.cuh", "attn_fwd2_layout.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -27,7 +27,7 @@ NVCC_FLAGS = [
 ]
 
 PVQA_F32, PVQA_BF16 = 0, 1
-ABI_VERSION = 6  # must equal PVQA_ABI_VERSION in include/pvqa.h
+ABI_VERSION = 7  # must equal PVQA_ABI_VERSION in include/pvqa.h
 
 
 def _stale() -> bool:
@@ -75,6 +75,7 @@ _SIGNATURES = {
     "pvqa_vocab_ce_grad": (c_int, [_vp, _vp, _i64, _vp, _vp, _vp] + _i64x(3) + [_vp]),
     "pvqa_attn_fwd": (c_int, [_vp] * 7 + _i64x(5) + _i64x(12) + [_f, c_int, _f, c_uint64, c_uint64, _vp, _vp, _i64, _i64, _vp]),
     "pvqa_attn_fwd_v2": (c_int, [_vp] * 7 + _i64x(5) + _i64x(12) + [_f, c_int, _f, c_uint64, c_uint64, _vp, _vp, _i64, _i64, _vp]),
+    "pvqa_attn_fwd_v3": (c_int, [_vp] * 7 + _i64x(5) + _i64x(12) + [_f, c_int, _f, c_uint64, c_uint64, _vp, _vp, _i64, _i64, _vp]),
     "pvqa_attn_bwd": (c_int, [_vp] * 13 + _i64x(5) + _i64x(21) + [_f, c_int, _f, c_uint64, c_uint64, _vp, _vp, _vp, _i64, _i64, _vp]),
     "pvqa_attn_f32_fwd": (c_int, [_vp] * 7 + _i64x(5) + _i64x(12) + [_f, c_int, _f, c_uint64, c_uint64, _vp, _vp, _i64, _i64, _vp]),
     "pvqa_rms_norm_fwd": (c_int, [_vp] * 4 + _i64x(2) + [_f, c_int, c_int, _vp]),

@@ -1105,3 +1105,4 @@ extern "C" int pvqa_attn_bwd(const void* q, const void* k, const void* v, const 
 }
 
 #include "attn_fwd2.cuh"
+#include "attn_fwd3.cuh"

@@ -39,3 +39,26 @@ PVQA_HD constexpr int rel_copy_row_base(int Sq, int i, int cs) {
 }
 
 }  // namespace pvqa_f2
+
+// ---- third-generation forward (attn_fwd3.cuh): same shifted-copy scheme with a 0..3 element left pad.  Rows past the
+// end of the sequence (dead rows of the last query tile) reuse the last live row's offset instead of reaching into a
+// 128-element pad, which makes the four copies 2 KB smaller — the room the row-max exchange buffer needs to keep two
+// CTAs per SM at S = 327.
+namespace pvqa_f3 {
+
+PVQA_HD constexpr int rel_pad(int Sq) { return (4 - (Sq & 3)) & 3; }
+
+PVQA_HD constexpr int rel_copy_stride(int Sq, int n_kpad) {
+  return ((rel_pad(Sq) + Sq + n_kpad + 31) / 32) * 32 + 8;
+}
+
+PVQA_HD constexpr int rel_copy_source(int idx, int cs, int Sq) {
+  return idx - (idx / cs) * cs + (idx / cs) - rel_pad(Sq);
+}
+
+PVQA_HD constexpr int rel_copy_row_base(int Sq, int i, int cs) {
+  return (((Sq - 1 - (i < Sq ? i : Sq - 1)) + rel_pad(Sq)) & 3) * cs +
+         (((Sq - 1 - (i < Sq ? i : Sq - 1)) + rel_pad(Sq)) & ~3);
+}
+
+}  // namespace pvqa_f3

@@ -561,9 +561,10 @@ def relu_dropout(x, p, training):
 # ----------------------------------------------------------------------------------
 # K2 / K3: attention.  bf16 -> tcgen05/TMA flash kernels; fp32 (parity mode) -> fp32 CUDA-core kernels.
 # ----------------------------------------------------------------------------------
-# Opt-in second-generation forward kernel (csrc/attn_fwd2.cuh).  Off by default until it has passed the parity
-# tests on a device; both entry points have the same contract, so this is a switch, not a fallback.
+# Opt-in forward kernels (csrc/attn_fwd2.cuh, attn_fwd3.cuh).  All entry points have the same contract, so these are
+# switches, not fallbacks.  v2: correct on the device but not faster than the product kernel; v3: not yet run.
 ATTN_FWD_V2 = os.environ.get("PVQA_ATTN_FWD_V2", "0") == "1"
+ATTN_FWD_V3 = os.environ.get("PVQA_ATTN_FWD_V3", "0") == "1"
 
 
 def _check_attn_operand(t, name, dtype):
@@ -611,6 +612,8 @@ def attention_fwd_raw(q, k, v, scale, rel_bias=None, key_add=None, causal=False,
         raise ValueError(f"key_add must be (B, Sk) = {(B, Sk)}, got {tuple(key_add.shape)}")
     if dtype != torch.bfloat16:
         fn, name = lib.pvqa_attn_f32_fwd, "attn_f32_fwd"
+    elif ATTN_FWD_V3:
+        fn, name = lib.pvqa_attn_fwd_v3, "attn_fwd_v3"
     elif ATTN_FWD_V2:
         fn, name = lib.pvqa_attn_fwd_v2, "attn_fwd_v2"
     else:

@@ -1,5 +1,5 @@
 """The opt-in attention kernels — forward v2 (pvqa_attn_fwd_v2, csrc/attn_fwd2.cuh) and the lean backward
-(PVQA_ATTN_BWD_LEAN=1) — against the same oracle cases as the product kernels, plus direct comparisons with them.
+(PVQA_ATTN_BWD_LEAN=1), and forward v3 (pvqa_attn_fwd_v3, csrc/attn_fwd3.cuh, not yet run on a device) — against the same oracle cases as the product kernels, plus direct comparisons with them.
 
 Skipped unless PVQA_TEST_ATTN_V2=1: neither is a default path yet.  Both passed a five-case probe on the device at
 the very end of round 1 (profiles/r01_optin_kernels_probe.log); this file is the full check to run before a switch
@@ -18,12 +18,14 @@ pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300, method="thread"),
 DEV = "cuda:0"
 
 
-@pytest.fixture(autouse=True)
-def v2(monkeypatch):
+@pytest.fixture(autouse=True, params=["v2", "v3"])
+def variant(request, monkeypatch):
+    """every test of this file runs once per opt-in forward kernel"""
     from phoneme_vqa_b200 import ops
-    monkeypatch.setattr(ops, "ATTN_FWD_V2", True)
+    monkeypatch.setattr(ops, "ATTN_FWD_V2", request.param == "v2")
+    monkeypatch.setattr(ops, "ATTN_FWD_V3", request.param == "v3")
     c0 = ops._lib.launch_count()
-    yield
+    yield request.param
     assert ops._lib.launch_count() > c0
 
 
@@ -71,6 +73,7 @@ def test_v2_agrees_with_the_product_kernel(B, Sq, Sk, H, causal, p, monkeypatch)
     scale = 1.0 if rel is not None else 1.0 / math.sqrt(64)
     o2, lse2 = ops.attention_fwd_raw(q, k, v, scale, rel, key_add, causal, drop)
     monkeypatch.setattr(ops, "ATTN_FWD_V2", False)
+    monkeypatch.setattr(ops, "ATTN_FWD_V3", False)
     o1, lse1 = ops.attention_fwd_raw(q, k, v, scale, rel, key_add, causal, drop)
     torch.testing.assert_close(lse2, lse1, rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(o2.float(), o1.float(), rtol=2e-2, atol=2e-3)
@@ -84,6 +87,7 @@ def test_lean_backward_equals_full_backward(p, monkeypatch):
     kernel on the same inputs and dropout triple — the launcher reads the switch per call"""
     from phoneme_vqa_b200 import ops
     monkeypatch.setattr(ops, "ATTN_FWD_V2", False)
+    monkeypatch.setattr(ops, "ATTN_FWD_V3", False)
     B, S, H = 2, 327, 3
     g = torch.Generator().manual_seed(11)
     q = (torch.randn(B, S, H, 64, generator=g) * 0.4).bfloat16().to(DEV)

@@ -19,6 +19,9 @@ extern "C" int f2_stride(int Sq, int n_kpad) { return pvqa_f2::rel_copy_stride(S
 extern "C" int f2_source(int idx, int cs, int Sq) { return pvqa_f2::rel_copy_source(idx, cs, Sq); }
 extern "C" int f2_row_base(int Sq, int i, int cs) { return pvqa_f2::rel_copy_row_base(Sq, i, cs); }
 extern "C" int f2_pad() { return pvqa_f2::kRelPadF2; }
+extern "C" int f3_stride(int Sq, int n_kpad) { return pvqa_f3::rel_copy_stride(Sq, n_kpad); }
+extern "C" int f3_source(int idx, int cs, int Sq) { return pvqa_f3::rel_copy_source(idx, cs, Sq); }
+extern "C" int f3_row_base(int Sq, int i, int cs) { return pvqa_f3::rel_copy_row_base(Sq, i, cs); }
 """
 
 
@@ -66,3 +69,37 @@ def test_quarter_warps_are_bank_conflict_free(f2, Sq):
                 for step in (0, 4, 28, 96):                    # any 16-byte step inside a chunk: same shift for all lanes
                     groups = {((f2.f2_row_base(Sq, i, cs) + step) // 4) % 8 for i in rows}
                     assert len(groups) == 8, (i0, warp, quarter, step)
+
+
+# ---- third-generation layout (attn_fwd3.cuh): 0..3 element pad, dead rows clamped to the last live row ----
+@pytest.mark.parametrize("Sq,Sk", [(327, 327), (127, 127), (464, 464), (707, 707), (5, 5), (128, 128), (326, 326), (325, 325)])
+def test_v3_shifted_copies_return_the_reference_bias(f2, Sq, Sk):
+    n_kpad = (Sk + 127) // 128 * 128
+    cs = f2.f3_stride(Sq, n_kpad)
+    assert cs % 32 == 8
+    n_rel = Sq + Sk - 1
+    rel = np.arange(1, n_rel + 1, dtype=np.float64)
+    staged = np.zeros(4 * cs)
+    for idx in range(4 * cs):
+        r = f2.f3_source(idx, cs, Sq)
+        staged[idx] = rel[r] if 0 <= r < n_rel else 0.0
+    for i in range((Sq + 127) // 128 * 128):
+        base = f2.f3_row_base(Sq, i, cs)
+        assert base % 4 == 0 and 0 <= base and base + n_kpad <= 4 * cs, (i, base)
+        if i < Sq:
+            j = np.arange(Sk)
+            assert np.array_equal(staged[base: base + Sk], rel[j - i + Sq - 1]), (i,)
+
+
+@pytest.mark.parametrize("Sq", [327, 127, 464, 5, 326, 325, 707])
+def test_v3_quarter_warps_are_bank_conflict_free(f2, Sq):
+    n_kpad = (Sq + 127) // 128 * 128
+    cs = f2.f3_stride(Sq, n_kpad)
+    for i0 in range(0, (Sq + 127) // 128 * 128, 128):
+        for warp in range(4):
+            for quarter in range(4):
+                rows = [i0 + warp * 32 + quarter * 8 + l for l in range(8)]
+                # lanes past the end share the last live row's address (one broadcast), the others must be distinct
+                bases = {f2.f3_row_base(Sq, i, cs) for i in rows}
+                groups = {(b // 4) % 8 for b in bases}
+                assert len(groups) == len(bases), (i0, warp, quarter)

@@ -10,18 +10,20 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 import attn_v2_protocol_sim as sim  # noqa: E402
 
 
+@pytest.mark.parametrize("n_warps", [4, 8])                   # attn_fwd2 / attn_fwd3
 @pytest.mark.parametrize("n_tiles", [1, 2, 3, 4, 6])          # S = 327 -> 3 key tiles, 707 -> 6
-def test_protocol_has_no_deadlock_or_hazard(n_tiles):
-    for seed in range(400):
-        assert sim.run(n_tiles, seed) > 0
+def test_protocol_has_no_deadlock_or_hazard(n_tiles, n_warps):
+    for seed in range(300):
+        assert sim.run(n_tiles, seed, n_warps=n_warps) > 0
 
 
-@pytest.mark.parametrize("skip", ["sfree", "o_before_k", "o_before_p", "s_before_v"])
-def test_model_detects_a_missing_wait(skip):
+@pytest.mark.parametrize("skip,n_warps", [("sfree", 4), ("o_before_k", 4), ("o_before_p", 4), ("s_before_v", 4),
+                                          ("sfree", 8), ("o_before_p", 8), ("pair", 8)])
+def test_model_detects_a_missing_wait(skip, n_warps):
     caught = 0
     for seed in range(300):
         try:
-            sim.run(4, seed, skip=(skip,))
+            sim.run(4, seed, skip=(skip,), n_warps=n_warps)
         except (AssertionError, sim.Deadlock):
             caught += 1
     assert caught > 0, f"removing the '{skip}' wait went unnoticed in 300 schedules"

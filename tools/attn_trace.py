@@ -88,8 +88,9 @@ def main():
         o, lse = ops.attention_fwd_raw(q, k, v, 1.0, rb, ka, False, drop)
         torch.cuda.synchronize()
         lib.pvqa_debug_attn_trace(ctypes.addressof(buf), 1)
-        report(list(buf), FWD2_EV if ops.ATTN_FWD_V2 else FWD_EV,
-               f"fwd{' v2' if ops.ATTN_FWD_V2 else ''} enc_self B={B} p={p}")
+        new = ops.ATTN_FWD_V2 or ops.ATTN_FWD_V3          # v2 and v3 share the event numbering
+        report(list(buf), FWD2_EV if new else FWD_EV,
+               f"fwd{' v3' if ops.ATTN_FWD_V3 else ' v2' if ops.ATTN_FWD_V2 else ''} enc_self B={B} p={p}")
         dkv = torch.empty_like(kv)
         for _ in range(2):
             ops.attention_bwd_raw(q, k, v, o, go, lse, 1.0, rb, ka, False, dkv[:, :, 0], dkv[:, :, 1], True, drop)

@@ -1,4 +1,5 @@
-"""Randomised interleaving model of the synchronisation protocol of csrc/attn_fwd2.cuh (the opt-in forward kernel).
+"""Randomised interleaving model of the synchronisation protocol of csrc/attn_fwd2.cuh / attn_fwd3.cuh (the opt-in
+forward kernels; attn_fwd2 ran correctly on the device the first time it was launched).
 
 The kernel could not be run on a device when it was written, so the part that cannot be checked by compiling — who
 waits for whom, on which mbarrier phase, and which buffer may be overwritten when — is restated here statement by
@@ -42,19 +43,24 @@ class Barrier:
 
 
 class Sim:
-    def __init__(self, n_tiles, seed, skip=()):
-        """`skip`: names of waits to leave out ("sfree", "o_before_k", "o_before_p", "s_before_v") — used by the
-        test to prove that the model notices a broken protocol."""
-        self.n, self.rng, self.skip = n_tiles, random.Random(seed), set(skip)
+    def __init__(self, n_tiles, seed, skip=(), n_warps=4):
+        """`skip`: names of waits to leave out ("sfree", "o_before_k", "o_before_p", "s_before_v", "pair") — used by
+        the test to prove that the model notices a broken protocol.  n_warps = 4 models attn_fwd2 (one thread per
+        row), n_warps = 8 models attn_fwd3: warps w and w + 4 share rows and exchange the row max through a
+        two-slot (tile parity) buffer and a named barrier."""
+        self.n, self.rng, self.skip, self.W = n_tiles, random.Random(seed), set(skip), n_warps
         self.bar = {k: Barrier(k, c) for k, c in (("q", 1), ("k0", 1), ("k1", 1), ("v0", 1), ("v1", 1), ("s", 1),
-                                                  ("sfree", 4), ("p", 4), ("o", 1))}
+                                                  ("sfree", n_warps), ("p", n_warps), ("o", 1))}
+        for pr in range(4):
+            self.bar[f"pair{pr}"] = Barrier(f"pair{pr}", 2)      # hardware named barrier: counts, no parity aliasing
+        self.xbuf = {}                                 # (parity, warp) -> tile whose max that slot holds
         self.kv = [None, None, None]                   # tags of the three rotating buffers
         self.q_loaded = False
-        self.p_tag = [None] * 4                        # per softmax warp: tile whose P rows it wrote last
+        self.p_tag = [None] * n_warps                  # per softmax warp: tile whose P rows it wrote last
         self.s_tag = None                              # tile whose scores sit in TMEM
-        self.s_read = [None] * 4                       # per warp: last tile copied to registers
+        self.s_read = [None] * n_warps                 # per warp: last tile copied to registers
         self.o_products = 0                            # number of P_t V_t folded into O
-        self.o_rescaled = [0] * 4                      # per warp: rescales applied (tile index of the last one)
+        self.o_rescaled = [0] * n_warps                # per warp: rescales applied (tile index of the last one)
         self.pipe = []                                 # in-order tensor pipe: ("mma", kind, t) / ("commit", bar)
         self.pipe_busy = None
         self.tma = []                                  # [remaining delay, action]
@@ -158,6 +164,8 @@ class Sim:
             self.s_read[w] = t
             self.bar["sfree"].arrive()
             yield None                                     # bias, max
+            if self.W == 8:
+                yield from self._pair_exchange(w, t, t & 1)
             if t > 0:
                 if "o_before_p" not in self.skip:
                     yield ("wait", "o", t - 1)
@@ -173,13 +181,30 @@ class Sim:
             assert all(op[:2] != ("mma", "pv") for op in self.pipe), f"warp {w}: writes P_{t} with a PV product queued"
             self.p_tag[w] = t
             self.bar["p"].arrive()
+        if self.W == 8:
+            yield from self._pair_exchange(w, n, n & 1)     # the two half-row sums, in the slot the last tile left free
         yield ("wait", "o", n - 1)
         assert self.o_products == n, f"warp {w}: epilogue reads O with {self.o_products}/{n} products"
+
+    def _pair_exchange(self, w, t, parity):
+        """write own slot, named barrier with the partner warp, read the partner's slot"""
+        partner = w ^ 4
+        self.xbuf[(parity, w)] = t
+        yield None
+        if "pair" not in self.skip:
+            b = self.bar[f"pair{w & 3}"]
+            gen = b.completed
+            b.arrive()
+            while b.completed == gen:                      # bar.sync: block until the partner has arrived too
+                yield None
+        assert self.xbuf.get((parity, partner)) == t, (f"warp {w}: reads the exchange slot of tile "
+                                                       f"{self.xbuf.get((parity, partner))} instead of {t}")
+        yield None
 
     # ---- scheduler ------------------------------------------------------------------------------------------
     def run(self, max_steps=200000):
         threads = {"issuer": self.issuer()}
-        threads.update({f"w{w}": self.softmax(w) for w in range(4)})
+        threads.update({f"w{w}": self.softmax(w) for w in range(self.W)})
         blocked = {}
         while threads:
             self.steps += 1
@@ -217,13 +242,15 @@ class Sim:
         return self.steps
 
 
-def run(n_tiles, seed, skip=()):
-    return Sim(n_tiles, seed, skip).run()
+def run(n_tiles, seed, skip=(), n_warps=4):
+    return Sim(n_tiles, seed, skip, n_warps).run()
 
 
 if __name__ == "__main__":
     import sys
     n_seeds = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
-    for n_tiles in (1, 2, 3, 4, 6, 9):
-        total = sum(run(n_tiles, s) for s in range(n_seeds))
-        print(f"n_tiles={n_tiles}: {n_seeds} random schedules ok ({total / n_seeds:.0f} steps on average)")
+    for n_warps in (4, 8):
+        for n_tiles in (1, 2, 3, 4, 6, 9):
+            total = sum(run(n_tiles, s, n_warps=n_warps) for s in range(n_seeds))
+            print(f"{n_warps} softmax warps, n_tiles={n_tiles}: {n_seeds} random schedules ok "
+                  f"({total / n_seeds:.0f} steps on average)")

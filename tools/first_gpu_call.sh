@@ -12,10 +12,15 @@ run tests_gpu            python -m pytest tests -m gpu -q -x --deselect tests/te
 run tests_variants       python -m pytest tests/test_variants_gpu.py -m gpu -q
 run smoke                python -c "import __graft_entry__ as g; g.smoke()"
 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
-# 2. the opt-in forward kernel: parity first, then its timing alone and inside the step
+# 2. the opt-in kernels: a staged probe that logs before every launch (a hang still tells where), then the full parity
+#    file, then timings alone and inside the step
+PVQA_ATTN_BWD_LEAN=1 run probe python tools/quick_v2_probe.py
+run timing python tools/quick_v2_timing.py
 PVQA_TEST_ATTN_V2=1 run tests_attn_v2 python -m pytest tests/test_attn_v2_gpu.py -m gpu -q
 run kbench_attn_v1       python tools/kbench.py attn
 PVQA_ATTN_FWD_V2=1 run kbench_attn_v2 python tools/kbench.py attn
+PVQA_ATTN_FWD_V3=1 run kbench_attn_v3 python tools/kbench.py attn
+PVQA_ATTN_FWD_V3=1 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_attn_v3.json 2> gpurun_out/bench_attn_v3.err
 PVQA_ATTN_FWD_V2=1 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_attn_v2.json 2> gpurun_out/bench_attn_v2.err
 # 2b. the lean backward variant (SCP code compiled out of non-SaL launches): same tests in a process that opts in
 PVQA_ATTN_BWD_LEAN=1 run tests_bwd_lean python -m pytest tests/test_attn_gpu.py tests/test_model_gpu.py -m gpu -q
@@ -30,3 +35,4 @@ python bench.py --impl eager-gpu --batch 64 --steps 5 --warmup 2 > gpurun_out/be
 
 PVQA_ATTN_FWD_V2=1 run attn_trace_v2 bash -c "python tools/attn_trace.py build && python tools/attn_trace.py 64"
 ls -la gpurun_out | tail -n 24
+PVQA_ATTN_FWD_V3=1 run attn_trace_v3 python tools/attn_trace.py 64

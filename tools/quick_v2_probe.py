@@ -43,14 +43,15 @@ def case(B, H, Sq, Sk, rel, causal, p, tag):
     o1, l1 = ops.attention_fwd_raw(q, k, v, scale, rb, ka, causal, drop)
     torch.cuda.synchronize()
     log(f"{tag}: v1 forward done")
-    ops.ATTN_FWD_V2 = True
-    log(f"{tag}: launching v2 forward")
-    o2, l2 = ops.attention_fwd_raw(q, k, v, scale, rb, ka, causal, drop)
-    torch.cuda.synchronize()
-    ops.ATTN_FWD_V2 = False
     fin = torch.isfinite(l1)
-    log(f"{tag}: v2 forward done: max|o2-o1| = {(o2.float() - o1.float()).abs().max().item():.3e}, "
-        f"max|lse2-lse1| = {(l2[fin] - l1[fin]).abs().max().item():.3e}, nan in o2: {bool(torch.isnan(o2.float()).any())}")
+    for ver in ("V2", "V3"):
+        setattr(ops, "ATTN_FWD_" + ver, True)
+        log(f"{tag}: launching {ver} forward")
+        o2, l2 = ops.attention_fwd_raw(q, k, v, scale, rb, ka, causal, drop)
+        torch.cuda.synchronize()
+        setattr(ops, "ATTN_FWD_" + ver, False)
+        log(f"{tag}: {ver} forward done: max|o-o1| = {(o2.float() - o1.float()).abs().max().item():.3e}, "
+            f"max|lse-lse1| = {(l2[fin] - l1[fin]).abs().max().item():.3e}, nan in o: {bool(torch.isnan(o2.float()).any())}")
     if p == 0.0:
         # backward (lean variant when PVQA_ATTN_BWD_LEAN=1 and rel and not causal) against fp32 autograd on the device
         go = torch.randn(B, Sq, H, 64, generator=g).bfloat16().to(dev)

@@ -52,11 +52,11 @@ def timed(fn, n=5):
 
 for p in (0.1, 0.0):
     drop = (p, 1234, 0) if p > 0 else (0.0, 0, 0)
-    for v2 in (False, True):
-        ops.ATTN_FWD_V2 = v2
+    for ver in ("v1", "v2", "v3"):
+        ops.ATTN_FWD_V2, ops.ATTN_FWD_V3 = ver == "v2", ver == "v3"
         med, mn = timed(lambda: ops.attention_fwd_raw(q, k, v, 1.0, rb, ka, False, drop))
-        log(f"p={p} forward {'v2' if v2 else 'v1'}: median {med:.1f} us, min {mn:.1f} us")
-    ops.ATTN_FWD_V2 = False
+        log(f"p={p} forward {ver}: median {med:.1f} us, min {mn:.1f} us")
+    ops.ATTN_FWD_V2 = ops.ATTN_FWD_V3 = False
     o, lse = ops.attention_fwd_raw(q, k, v, 1.0, rb, ka, False, drop)
     for lean in ("0", "1"):
         os.environ["PVQA_ATTN_BWD_LEAN"] = lean
