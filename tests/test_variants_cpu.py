@@ -248,3 +248,24 @@ def test_beam_search_with_one_beam_is_greedy():
         assert torch.equal(got[:, t], tok)
         done = done | (tok[:, 0] == 1)
         state = toy.advance(state, tok)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# synthetic batches of the sibling bench workloads (bench.py --workload phonoprestu / phonosal)
+# ---------------------------------------------------------------------------------------------------------------
+def test_sibling_workload_batches_have_the_dataset_contract():
+    from phoneme_vqa_b200 import synthetic
+    b = synthetic.phoneme_prestu_batch(3, 500, T=9, L_in=14, image=32)
+    assert set(b) == {"pixel_values", "input_ids", "src_attention_mask", "label_ids", "label_attention_mask"}
+    assert b["input_ids"].shape == (3, 14) and b["input_ids"].dtype == torch.int64
+    assert b["label_ids"].shape == (3, 10, 3) and b["pixel_values"].shape == (3, 3, 32, 32)
+    assert torch.equal(b["label_ids"][:, 0], torch.tensor([[synthetic.BOS_ID, 0, 0]] * 3))
+    s = synthetic.phoneme_sal_batch(3, 500, T=9, L_q=16, L_ocr=32, L_obj=16, ocr_hidden=24, obj_hidden=40)
+    assert tuple(s) == synthetic.SAL_FIELDS or set(s) == set(synthetic.SAL_FIELDS)
+    assert s["label_attention_mask"].dtype == torch.bool and s["ocr_coordinates"].shape == (3, 32, 4)
+    assert float(s["ocr_coordinates"].max()) < 1.0 and float(s["ocr_coordinates"].min()) >= 0.0
+    assert torch.equal(s["label_ids"][:, 1:], s["shifted_right_label_ids"][:, :-1])        # shifted by one
+    assert (s["label_ids"][:, 0] == 1).all() and ((s["shifted_right_label_ids"] == 2).sum(1) == 1).all()
+    # every sequence field ends with </s> (id 1) then pads, and the float masks cover exactly the non-pad prefix
+    for ids, mask in ((s["input_ids"], s["src_attention_mask"]), (s["tokenized_ocr"], s["ocr_attention_mask"])):
+        assert torch.equal(mask.bool(), ids != 0)
