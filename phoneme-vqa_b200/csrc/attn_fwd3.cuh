@@ -48,6 +48,17 @@ constexpr int kF3OffFloats = kF3OffXchg + 2 * 2 * kBM * 4;  // key_add[n_kpad], 
 
 // SCP: the SaL spatial bias is compiled in only for launches that carry one (it costs registers in every variant
 // that merely might)
+// 64-thread named barrier between the two warps that own the two halves of the same 32 rows (ids 1..4, immediate
+// operands so that ptxas reserves five barriers, not all sixteen)
+__device__ __forceinline__ void pair_sync(int quad) {
+  switch (quad) {
+    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+  }
+}
+
 template <bool HAS_REL, bool DROP, bool SCP>
 __global__ void __launch_bounds__(kF3Threads, 2)
 attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -205,7 +216,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kF3RegsSoftmax));
     const int rowl = (warp & 3) * 32 + lane;            // row in the tile == TMEM lane
     const int half = warp >> 2;                         // column half owned by this thread
-    const int pair_bar = 1 + (warp & 3);                // named barrier shared by warps w and w + 4 (same rows)
+    const int quad = warp & 3;                          // warps w and w + 4 own the two halves of the same rows
     const uint32_t tmem_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const int i = i0 + rowl;
     const bool rows_dead = i0 + (warp & 3) * 32 >= p.Sq;      // all 32 query rows of this warp are past the end
@@ -279,7 +290,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       //      parity, so the write of tile t+2 cannot overtake the partner's read of tile t: barrier t+1 lies between)
       float* xbuf = s_x + (t & 1) * (2 * kBM);
       xbuf[half * kBM + rowl] = mx;
-      tc05::named_bar_sync(pair_bar, 64);
+      pair_sync(quad);
       mx = fmaxf(mx, xbuf[(half ^ 1) * kBM + rowl]);
       const float m_new = fmaxf(m_run, mx);
       const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
@@ -351,7 +362,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     // ---- epilogue: combine the two half-row sums, O (TMEM) / l -> bf16 rows, lse (natural log) ----
     float* xbuf = s_x + (n_tiles & 1) * (2 * kBM);      // the parity the last tile did not use
     xbuf[half * kBM + rowl] = l_run;
-    tc05::named_bar_sync(pair_bar, 64);
+    pair_sync(quad);
     const float l_tot = l_run + xbuf[(half ^ 1) * kBM + rowl];       // carries the 1/keep factor when DROP
     tc05::mbar_wait(bar_o, (n_tiles - 1) & 1);
     tc05::tc_fence_after_sync();
