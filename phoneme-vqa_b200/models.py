@@ -964,10 +964,12 @@ def reference_beam_select(prob, ys, end_symbol, max_len, num_beam):
             beam_probs[b] = beam_probs[b] + log_vals * eos_mask
         if all(done):
             break
-    beam_probs = torch.cat(beam_probs, dim=-1)
-    beams = torch.stack(beams, dim=1)
+    # like the reference, the selection itself happens on the host (CustomizedLaTr.py:241-247): torch's CPU argmax
+    # semantics for NaN scores are then the reference's by construction
+    beam_probs = torch.cat(beam_probs, dim=-1).cpu()
+    beams = torch.stack(beams, dim=1).cpu()
     beam_idx = torch.argmax(beam_probs, dim=-1)
-    return beams[torch.arange(bz, device=beams.device), beam_idx.flatten(), :].cpu()
+    return beams[torch.arange(bz), beam_idx.flatten(), :]
 
 
 class CustomizedLaTr(nn.Module, _VisionMixin, _FlatTargetMixin):
