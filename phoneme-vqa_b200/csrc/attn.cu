@@ -1088,10 +1088,12 @@ extern "C" int pvqa_attn_bwd(const void* q, const void* k, const void* v, const 
                   : (drop ? attn_bwd_kernel<false, true> : attn_bwd_kernel<false, false>);
   const char* lean_env = getenv("PVQA_ATTN_BWD_LEAN");      // read per call: cheap, and a process can compare both variants
   const bool lean_opt_in = lean_env && lean_env[0] == '1';
-  const bool lean = lean_opt_in && rel && scp_bucket == nullptr && !causal;
-  if (lean) kern = drop ? attn_bwd_kernel<true, true, false> : attn_bwd_kernel<true, false, false>;
-  static bool attr_set[6] = {false, false, false, false, false, false};
-  const int vi = lean ? 4 + (drop ? 1 : 0) : (rel ? 2 : 0) + (drop ? 1 : 0);
+  const bool lean = lean_opt_in && scp_bucket == nullptr && !causal;       // encoder self- and decoder cross-attention
+  if (lean)
+    kern = rel ? (drop ? attn_bwd_kernel<true, true, false> : attn_bwd_kernel<true, false, false>)
+               : (drop ? attn_bwd_kernel<false, true, false> : attn_bwd_kernel<false, false, false>);
+  static bool attr_set[8] = {false, false, false, false, false, false, false, false};
+  const int vi = (lean ? 4 : 0) + (rel ? 2 : 0) + (drop ? 1 : 0);
   if (!attr_set[vi]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
     if (e != cudaSuccess) return fail(PVQA_ERR_CUDA, "attn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
