@@ -19,7 +19,8 @@ def log(msg):
     os.fsync(LOG.fileno())
 
 
-log(f"start, BWD_LEAN={os.environ.get('PVQA_ATTN_BWD_LEAN')}")
+LEAN0 = os.environ.get("PVQA_ATTN_BWD_LEAN", "0")
+log(f"start, BWD_LEAN={LEAN0}")
 import torch  # noqa: E402
 log("torch imported")
 from phoneme_vqa_b200 import ops  # noqa: E402
@@ -52,6 +53,20 @@ def case(B, H, Sq, Sk, rel, causal, p, tag):
         setattr(ops, "ATTN_FWD_" + ver, False)
         log(f"{tag}: {ver} forward done: max|o-o1| = {(o2.float() - o1.float()).abs().max().item():.3e}, "
             f"max|lse-lse1| = {(l2[fin] - l1[fin]).abs().max().item():.3e}, nan in o: {bool(torch.isnan(o2.float()).any())}")
+    if p > 0.0:
+        # dropout: the mask cannot be reproduced by autograd, so compare the lean backward with the validated one
+        go = torch.randn(B, Sq, H, 64, generator=g).bfloat16().to(dev)
+        res = {}
+        for lean in ("0", "1"):
+            os.environ["PVQA_ATTN_BWD_LEAN"] = lean
+            dk, dv = torch.zeros_like(k), torch.zeros_like(v)
+            log(f"{tag}: launching backward with dropout, lean={lean}")
+            dq, d_rel, _ = ops.attention_bwd_raw(q, k, v, o1, go, l1, scale, rb, ka, causal, dk, dv, rel, drop)
+            torch.cuda.synchronize()
+            res[lean] = (dq, dk, dv) + ((d_rel,) if rel else ())
+        diffs = [float((a.float() - b_.float()).abs().max()) for a, b_ in zip(res["0"], res["1"])]
+        log(f"{tag}: dropout backward lean vs full: max abs diff dq/dk/dv(/d_rel) = {diffs}")
+        os.environ["PVQA_ATTN_BWD_LEAN"] = LEAN0
     if p == 0.0:
         # backward (lean variant when PVQA_ATTN_BWD_LEAN=1 and rel and not causal) against fp32 autograd on the device
         go = torch.randn(B, Sq, H, 64, generator=g).bfloat16().to(dev)
