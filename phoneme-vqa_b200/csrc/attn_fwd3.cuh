@@ -241,22 +241,27 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tc05::mbar_wait(bar_s, t & 1);
       tc05::tc_fence_after_sync();
       PVQA_TRACE3(2 + 5 * t);                     // softmax: S_t ready
-      // ---- S_t -> registers (once), then hand the TMEM buffer back to the issuer ----
-#pragma unroll
-      for (int c = 0; c < 2; ++c)
-        if (jh + c * 32 < p.Sk && !rows_dead)              // warp-uniform
-          tc05::tmem_ld_32x32(tmem_row + half * 64 + c * 32, reinterpret_cast<uint32_t(&)[32]>(sf[c * 32]));
-      tc05::tmem_ld_wait();
-      tc05::tc_fence_before_sync();
-      tc05::mbar_arrive(bar_sfree);
-      PVQA_TRACE3(3 + 5 * t);                     // softmax: S_t in registers
+      // ---- S_t -> registers (once).  The second 32-column chunk is in flight while the first one gets its bias;
+      //      once both have landed the TMEM buffer goes back to the issuer ----
+      const bool live0 = jh < p.Sk && !rows_dead, live1 = jh + 32 < p.Sk && !rows_dead;      // warp-uniform
+      if (live0) {
+        tc05::tmem_ld_32x32(tmem_row + half * 64, reinterpret_cast<uint32_t(&)[32]>(sf[0]));
+        tc05::tmem_ld_wait();
+      }
+      if (live1) tc05::tmem_ld_32x32(tmem_row + half * 64 + 32, reinterpret_cast<uint32_t(&)[32]>(sf[32]));
 
       // ---- biased scores in the exp2 domain and the max over this thread's 64 columns ----
       float mx = -INFINITY;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int jb = jh + c * 32;
-        if (jb >= p.Sk || rows_dead) continue;
+        if (c == 1) {
+          tc05::tmem_ld_wait();
+          tc05::tc_fence_before_sync();
+          tc05::mbar_arrive(bar_sfree);
+          PVQA_TRACE3(3 + 5 * t);                 // softmax: S_t in registers
+        }
+        if (!(c == 0 ? live0 : live1)) continue;
         const float4* ka4 = reinterpret_cast<const float4*>(s_kadd + jb);
         const float4* rl4 = reinterpret_cast<const float4*>(relc + jb);
 #pragma unroll
