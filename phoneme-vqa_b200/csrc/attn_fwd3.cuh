@@ -28,7 +28,7 @@ constexpr int kF3RegsSoftmax = 104;
 constexpr int kF3RegsIssuer = 32;            // 256 * 104 + 128 * 32 == 384 * 80
 constexpr uint32_t kF3TmemCols = 256;           // S: [0,128)   O: [128,192)
 constexpr int kF3OffQ = 0;
-constexpr int kF3OffKV = kF3OffQ + kBM * kD * 2;          // three rotating 16 KB buffers: K_t (2t)%3, V_t (2t+1)%3
+constexpr int kF3OffKV = kF3OffQ + kBM * kD * 2;          // three 16 KB buffers: K_0 -> 0, K_t -> 2, V_t -> t odd ? 0 : 1
 constexpr int kF3OffP = kF3OffKV + 3 * kKVBuf;            // 64 KB: P as two [128][64] K-major SW128 sub-tiles
 constexpr int kF3OffBar = kF3OffP + kBM * kBN * 2;        // 96 KB
 constexpr int kF3OffXchg = kF3OffBar + 128;               // [2 tile parities][2 halves][128 rows] floats
@@ -162,50 +162,54 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const uint32_t idesc_pv = tc05::idesc_bf16(kBM, kD, 0, 1);      // B = V is MN-major (d contiguous)
       const uint32_t q_addr = tc05::smem_u32(smem + kF3OffQ), kv_addr = tc05::smem_u32(smem + kF3OffKV);
       const uint32_t p_addr = tc05::smem_u32(smem + kF3OffP);
+      // Buffer plan (three 16 KB buffers): K_0 -> 0, K_t (t >= 1) -> 2, V_t -> (t odd ? 0 : 1).
+      //   buffer 2 is free as soon as S_t = Q K_t^T has completed, so K_{t+1} is fetched a whole tile before it is
+      //   needed (the product kernel and v2 fetch it behind P_{t-1} V_{t-1}, which puts the TMA latency on the path
+      //   to S_{t+1}); V_{t+1} takes the buffer of V_{t-1} (or of K_0) and is not needed before the end of tile t+1.
+      auto k_buf = [&](int t) { return kv_addr + (t == 0 ? 0 : 2) * kKVBuf; };
+      auto v_buf = [&](int t) { return kv_addr + ((t & 1) ? 0 : 1) * kKVBuf; };
       tc05::mbar_wait(bar_q, 0);
       tc05::mbar_wait(bar_k, 0);
       tc05::tc_fence_after_sync();
 #pragma unroll
       for (int ks = 0; ks < kD / 16; ++ks)
         tc05::mma_bf16_ss(tmem_base, tc05::smem_desc_sw128(q_addr + ks * 32, 16, 1024),
-                          tc05::smem_desc_sw128(kv_addr + ks * 32, 16, 1024), idesc_qk, ks > 0);
+                          tc05::smem_desc_sw128(k_buf(0) + ks * 32, 16, 1024), idesc_qk, ks > 0);
       tc05::mma_commit(bar_s);
       for (int t = 0; t < n_tiles; ++t) {
         const int j0 = t * kBN;
         if (t + 1 < n_tiles) {
-          // V_{t+1} takes K_t's buffer: S_t = Q K_t^T must have completed
-          tc05::mbar_wait(bar_s, t & 1);
-          tc05::mbar_expect_tx(bar_v + ((t + 1) & 1), kKVBuf);
-          tc05::tma_load_4d(smem + kF3OffKV + ((2 * t) % 3) * kKVBuf, &tmV, bar_v + ((t + 1) & 1), 0, h, j0 + kBN, b);
-          if (t >= 1) {
-            // K_{t+1} takes V_{t-1}'s buffer: O += P_{t-1} V_{t-1} must have completed (K_1 was fetched up front)
-            tc05::mbar_wait(bar_o, (t - 1) & 1);
-            tc05::mbar_expect_tx(bar_k + ((t + 1) & 1), kKVBuf);
-            tc05::tma_load_4d(smem + kF3OffKV + ((2 * t + 2) % 3) * kKVBuf, &tmK, bar_k + ((t + 1) & 1), 0, h,
-                              j0 + kBN, b);
-          }
-          // S_{t+1}: K_{t+1} landed and the softmax warps hold S_t in registers
+          // S_{t+1}: K_{t+1} landed (fetched one tile ago) and the softmax warps hold S_t in registers
           tc05::mbar_wait(bar_k + ((t + 1) & 1), ((t + 1) >> 1) & 1);
           tc05::mbar_wait(bar_sfree, t & 1);
           tc05::tc_fence_after_sync();
-          const uint32_t k_addr = kv_addr + ((2 * t + 2) % 3) * kKVBuf;
 #pragma unroll
           for (int ks = 0; ks < kD / 16; ++ks)
             tc05::mma_bf16_ss(tmem_base, tc05::smem_desc_sw128(q_addr + ks * 32, 16, 1024),
-                              tc05::smem_desc_sw128(k_addr + ks * 32, 16, 1024), idesc_qk, ks > 0);
+                              tc05::smem_desc_sw128(k_buf(t + 1) + ks * 32, 16, 1024), idesc_qk, ks > 0);
           tc05::mma_commit(bar_s);
           PVQA_TRACE3(2 + 5 * t);                 // issuer: S_{t+1} issued
+          if (t + 2 < n_tiles) {
+            // K_{t+2} reuses buffer 2 as soon as S_{t+1} has been computed from it (a few hundred cycles from now)
+            tc05::mbar_wait(bar_s, (t + 1) & 1);
+            tc05::mbar_expect_tx(bar_k + (t & 1), kKVBuf);
+            tc05::tma_load_4d(smem + kF3OffKV + 2 * kKVBuf, &tmK, bar_k + (t & 1), 0, h, j0 + 2 * kBN, b);
+          }
+          // V_{t+1} takes V_{t-1}'s buffer (O += P_{t-1} V_{t-1} must have completed) or, for t = 0, K_0's
+          if (t >= 1) tc05::mbar_wait(bar_o, (t - 1) & 1);
+          tc05::mbar_expect_tx(bar_v + ((t + 1) & 1), kKVBuf);
+          tc05::tma_load_4d(smem + kF3OffKV + (((t + 1) & 1) ? 0 : 1) * kKVBuf, &tmV, bar_v + ((t + 1) & 1), 0, h,
+                            j0 + kBN, b);
         }
         // O (+)= P_t V_t: V_t landed, P_t written (and O rescaled) by the softmax warps
         tc05::mbar_wait(bar_v + (t & 1), (t >> 1) & 1);
         tc05::mbar_wait(bar_p, t & 1);
         tc05::tc_fence_after_sync();
-        const uint32_t v_addr = kv_addr + ((2 * t + 1) % 3) * kKVBuf;
 #pragma unroll
         for (int ks = 0; ks < kBN / 16; ++ks)
           tc05::mma_bf16_ss(tmem_base + kBN,
                             tc05::smem_desc_sw128(p_addr + (ks >> 2) * (kBM * 128) + (ks & 3) * 32, 16, 1024),
-                            tc05::smem_desc_sw128(v_addr + ks * 2048, 16, 1024), idesc_pv, (t > 0 || ks > 0) ? 1u : 0u);
+                            tc05::smem_desc_sw128(v_buf(t) + ks * 2048, 16, 1024), idesc_pv, (t > 0 || ks > 0) ? 1u : 0u);
         tc05::mma_commit(bar_o);
         PVQA_TRACE3(3 + 5 * t);                   // issuer: PV_t issued
       }

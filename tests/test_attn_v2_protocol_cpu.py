@@ -18,7 +18,8 @@ def test_protocol_has_no_deadlock_or_hazard(n_tiles, n_warps):
 
 
 @pytest.mark.parametrize("skip,n_warps", [("sfree", 4), ("o_before_k", 4), ("o_before_p", 4), ("s_before_v", 4),
-                                          ("sfree", 8), ("o_before_p", 8), ("pair", 8)])
+                                          ("sfree", 8), ("o_before_p", 8), ("pair", 8), ("s_before_k", 8),
+                                          ("o_before_v", 8)])
 def test_model_detects_a_missing_wait(skip, n_warps):
     caught = 0
     for seed in range(300):

@@ -81,6 +81,8 @@ class Sim:
 
     def _operand_buffer(self, op):
         kind, t = op[1], op[2]
+        if self.W == 8:                                # attn_fwd3: K_0 -> 0, K_t -> 2, V_t -> t odd ? 0 : 1
+            return (0 if t == 0 else 2) if kind == "qk" else (0 if t & 1 else 1)
         return (2 * t) % 3 if kind == "qk" else (2 * t + 1) % 3
 
     def _mma_check(self, op, starting):
@@ -125,6 +127,9 @@ class Sim:
 
     # ---- threads (generators yield ("wait", barrier, phase) or None for a plain scheduling point) -----------
     def issuer(self):
+        if self.W == 8:
+            yield from self.issuer_v3()
+            return
         n = self.n
         # prologue (before the CTA barrier): Q, K_0, V_0 and K_1
         self.tma.append([self.rng.randint(1, 40), lambda: (setattr(self, "q_loaded", True), self.bar["q"].arrive())])
@@ -149,6 +154,37 @@ class Sim:
                 if "sfree" not in self.skip:
                     yield ("wait", "sfree", t)
                 self.pipe += [("mma", "qk", t + 1), ("commit", "s")]
+            yield ("wait", f"v{t & 1}", t >> 1)
+            yield ("wait", "p", t)
+            self.pipe += [("mma", "pv", t), ("commit", "o")]
+            yield None
+
+    def issuer_v3(self):
+        """attn_fwd3: K_{t+2} is fetched into buffer 2 as soon as S_{t+1} has been computed from it; V_{t+1} takes
+        V_{t-1}'s (or K_0's) buffer"""
+        n = self.n
+        self.tma.append([self.rng.randint(1, 40), lambda: (setattr(self, "q_loaded", True), self.bar["q"].arrive())])
+        self.tma_issue(0, ("K", 0), "k0")
+        self.tma_issue(1, ("V", 0), "v0")
+        if n > 1:
+            self.tma_issue(2, ("K", 1), "k1")
+        yield None
+        yield ("wait", "q", 0)
+        yield ("wait", "k0", 0)
+        self.pipe += [("mma", "qk", 0), ("commit", "s")]
+        for t in range(n):
+            if t + 1 < n:
+                yield ("wait", f"k{(t + 1) & 1}", (t + 1) >> 1)
+                if "sfree" not in self.skip:
+                    yield ("wait", "sfree", t)
+                self.pipe += [("mma", "qk", t + 1), ("commit", "s")]
+                if t + 2 < n:
+                    if "s_before_k" not in self.skip:
+                        yield ("wait", "s", t + 1)
+                    self.tma_issue(2, ("K", t + 2), f"k{t & 1}")
+                if t >= 1 and "o_before_v" not in self.skip:
+                    yield ("wait", "o", t - 1)
+                self.tma_issue(0 if (t + 1) & 1 else 1, ("V", t + 1), f"v{(t + 1) & 1}")
             yield ("wait", f"v{t & 1}", t >> 1)
             yield ("wait", "p", t)
             self.pipe += [("mma", "pv", t), ("commit", "o")]
