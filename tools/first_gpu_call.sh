@@ -36,3 +36,24 @@ python bench.py --impl eager-gpu --batch 64 --steps 5 --warmup 2 > gpurun_out/be
 PVQA_ATTN_FWD_V2=1 run attn_trace_v2 bash -c "python tools/attn_trace.py build && python tools/attn_trace.py 64"
 ls -la gpurun_out | tail -n 24
 PVQA_ATTN_FWD_V3=1 run attn_trace_v3 python tools/attn_trace.py 64
+# compact summary (also kept as gpurun_out/summary.txt): last line of every log, headline numbers of every bench line
+python - <<'PY' | tee gpurun_out/summary.txt
+import glob, json, os
+for f in sorted(glob.glob("gpurun_out/*.log")):
+    lines = [l.rstrip() for l in open(f, errors="ignore") if l.strip()]
+    print(f"{os.path.basename(f):28s} {lines[-1][:150] if lines else '(empty)'}")
+for f in sorted(glob.glob("gpurun_out/bench_*.json")):
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        extra = {k: round(v["samples_per_s"], 1) for k, v in d.get("variants", {}).items()}
+        print(f"{os.path.basename(f):28s} {d.get('metric', '?')}: value {d.get('value', 0):.1f} "
+              f"ms/step {d.get('ms_per_step', 0) or 0:.2f} e2e {(d.get('e2e') or {}).get('value', 0):.1f} {extra or ''}")
+    except Exception as e:
+        err = f.replace(".json", ".err")
+        tail = open(err, errors="ignore").read().strip().splitlines()[-1][:150] if os.path.exists(err) else ""
+        print(f"{os.path.basename(f):28s} no JSON line ({type(e).__name__}); stderr: {tail}")
+for f in ("gpurun_out/quick_v2_probe.log", "gpurun_out/quick_v2_timing.log"):
+    if os.path.exists(f):
+        print("----", f)
+        print(open(f).read())
+PY
