@@ -84,3 +84,17 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 txt = open(os.path.join(dirpath, f), encoding="utf-8").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_opt_in_kernels_are_off_by_default():
+    """the product path is pvqa_attn_fwd / the full backward unless a PVQA_ATTN_* switch is set explicitly"""
+    import subprocess
+    import sys
+    env = {k: v for k, v in os.environ.items() if not k.startswith("PVQA_ATTN_")}
+    code = ("import sys; sys.path.insert(0, %r); from phoneme_vqa_b200 import ops; "
+            "print(ops.ATTN_FWD_V2, ops.ATTN_FWD_V3)" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout
+    assert out.split() == ["False", "False"]
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "phoneme-vqa_b200", "csrc",
+                            "attn.cu")).read()
+    assert 'getenv("PVQA_ATTN_BWD_LEAN")' in src and "lean_env && lean_env[0] == '1'" in src
