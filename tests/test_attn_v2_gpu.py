@@ -29,7 +29,11 @@ def variant(request, monkeypatch):
     assert ops._lib.launch_count() > c0
 
 
-@pytest.mark.parametrize("B,Sq,Sk,H", base.T5_CASES)
+# every residue of Sq mod 4 (the shifted bias copies are padded by 0..3 elements), single-row and ragged shapes
+EXTRA_T5_CASES = [(1, 326, 326, 1), (2, 325, 325, 2), (1, 324, 324, 1), (1, 130, 130, 3), (2, 33, 33, 1)]
+
+
+@pytest.mark.parametrize("B,Sq,Sk,H", base.T5_CASES + EXTRA_T5_CASES)
 def test_t5_attention_fwd(B, Sq, Sk, H):
     base.test_t5_attention_fwd(B, Sq, Sk, H)
 
