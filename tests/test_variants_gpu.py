@@ -261,3 +261,31 @@ def test_phoneme_latr_beam_search_with_kv_cache():
             assert got.shape == want.shape
             torch.testing.assert_close(score(got), score(want), rtol=0, atol=1e-3)
 
+
+
+def test_phoneme_sal_matches_reference_golden_fp32():
+    """product PhonemeSaL directly against the outputs recorded from the real reference class
+    (tests/golden/model_phonemesal_tiny.npz; test_model_gpu.py compares it with the oracle restatement)"""
+    import phoneme_vqa_b200.models as M
+    g = np.load(os.path.join(GOLD, "model_phonemesal_tiny.npz"))
+    cfg = ref_model.sal_config()
+    model = M.PhonemeSaL(cfg, 253)
+    assert list(model.state_dict().keys()) == list(g["state_dict_keys"])
+    model.load_state_dict(ref_model.deterministic_state_dict(model), strict=True)
+    model = model.to(DEV).eval()
+    bd = _to(ref_model.sal_batch(3, cfg))
+    fkeys = ("input_ids", "src_attention_mask", "label_ids", "shifted_right_label_ids", "label_attention_mask") + SAL_GEN_KEYS[2:]
+    with torch.no_grad():
+        logits, _ = model(**{k: bd[k] for k in fkeys})
+    np.testing.assert_allclose(logits.cpu().numpy(), g["logits"], rtol=2e-4, atol=2e-5)
+    ys = model.generate(*[bd[k] for k in SAL_GEN_KEYS], 1, 2, max_len=5)
+    assert np.array_equal(ys.cpu().numpy(), g["greedy_ids"])
+    model.train()
+    _no_dropout(model)
+    _, loss = model(**{k: bd[k] for k in fkeys})
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) <= 1e-3 * abs(float(g["loss"]))
+    grads = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+    assert sorted(grads) == list(g["grad_keys"])
+    norms = np.array([grads[k].double().norm().item() for k in sorted(grads)])
+    np.testing.assert_allclose(norms, g["grad_norms"], rtol=1e-3, atol=1e-6)
