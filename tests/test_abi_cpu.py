@@ -46,6 +46,15 @@ def test_argument_errors_are_reported_without_a_device():
     rc = lib.pvqa_attn_fwd(None, None, None, None, None, None, None, 1, 1, 8, 8, 32,
                            0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1.0, 0, 0.0, 0, 0, None, None, 0, 0, None)
     assert rc == 1 and b"head dim" in lib.pvqa_last_error()
+    for fn, tag in ((lib.pvqa_attn_fwd_v2, b"attn_fwd_v2"), (lib.pvqa_attn_fwd_v3, b"attn_fwd_v3")):   # same contract
+        rc = fn(None, None, None, None, None, None, None, 1, 1, 8, 8, 32,
+                0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1.0, 0, 0.0, 0, 0, None, None, 0, 0, None)
+        assert rc == 1 and b"head dim" in lib.pvqa_last_error() and tag in lib.pvqa_last_error()
+        rc = fn(None, None, None, None, None, None, None, 1, 1, 8, 8, 64,
+                0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1.0, 0, 1.5, 0, 0, None, None, 0, 0, None)
+        assert rc == 1 and b"dropout_p" in lib.pvqa_last_error()
+        assert fn(None, None, None, None, None, None, None, 0, 1, 8, 8, 64,
+                  0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1.0, 0, 0.0, 0, 0, None, None, 0, 0, None) == 0       # empty batch
     rc = lib.pvqa_embed_tgt_fwd(None, None, None, None, None, None, 1, 1, 10, 4, 4, 1, 1, 1, 0, 0, 0.0, 0, 0, None, None)
     assert rc == 1 and b"on_dim" in lib.pvqa_last_error()
     rc = lib.pvqa_phoneme_head_ce_fwd(None, None, 3, None, None, None, None, None, None, None, None, None, None, None,
