@@ -1,10 +1,10 @@
 #!/usr/bin/env bash
 # One gpurun call that validates everything written after round 1's GPU budget ran out, in the order that matters:
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- bash tools/first_gpu_call.sh
+#   /usr/local/graft/bin/gpurun --timeout 2400 -- bash tools/first_gpu_call.sh
 # Every step writes its own log under gpurun_out/; a failing step does not stop the later ones.
 set -u
 mkdir -p gpurun_out
-run() { local name=$1; shift; echo "== $name"; timeout 600 "$@" > "gpurun_out/$name.log" 2>&1; echo "   rc=$? ($(tail -n 1 "gpurun_out/$name.log" | cut -c1-150))"; }
+run() { local name=$1; shift; echo "== $name"; timeout 1200 "$@" > "gpurun_out/$name.log" 2>&1; echo "   rc=$? ($(tail -n 1 "gpurun_out/$name.log" | cut -c1-150))"; }
 
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1
 # 1. the product path: full GPU suite (the model-family tests in test_variants_gpu.py are new), smoke, default bench
