@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PVQA_ABI_VERSION 7
+#define PVQA_ABI_VERSION 8
 
 typedef enum {
   PVQA_OK = 0,
@@ -209,43 +209,16 @@ int pvqa_attn_fwd(const void* q, const void* k, const void* v, void* o, float* l
                   const uint8_t* scp_bucket, const float* scp_table, int64_t scp_q0, int64_t scp_L,
                   void* stream);
 
-/* Second-generation forward, same contract, arguments, outputs and dropout stream as pvqa_attn_fwd (so
- * pvqa_attn_bwd consumes its lse / o unchanged).  One thread per query row: the score tile is read from TMEM once,
- * O accumulates in TMEM across key tiles, the next tile's QK^T is issued while the current softmax runs, the T5
- * bias is read with 128-bit shared loads (phoneme-vqa_b200/csrc/attn_fwd2.cuh).  OPT-IN (host: PVQA_ATTN_FWD_V2=1):
- * results agree with pvqa_attn_fwd on the device (profiles/r01_optin_kernels_probe.log) but it is not yet faster. */
-int pvqa_attn_fwd_v2(const void* q, const void* k, const void* v, void* o, float* lse,
-                     const float* rel_bias, const float* key_add,
-                     int64_t B, int64_t H, int64_t Sq, int64_t Sk, int64_t D,
-                     int64_t q_stride_b, int64_t q_stride_s, int64_t q_stride_h,
-                     int64_t k_stride_b, int64_t k_stride_s, int64_t k_stride_h,
-                     int64_t v_stride_b, int64_t v_stride_s, int64_t v_stride_h,
-                     int64_t o_stride_b, int64_t o_stride_s, int64_t o_stride_h,
-                     float scale, int causal,
-                     float dropout_p, uint64_t seed, uint64_t offset,
-                     const uint8_t* scp_bucket, const float* scp_table, int64_t scp_q0, int64_t scp_L,
-                     void* stream);
-
-/* Third-generation forward (phoneme-vqa_b200/csrc/attn_fwd3.cuh), same contract again.  Keeps pvqa_attn_fwd's two
- * threads per query row (16 softmax warps per SM — what v2's first device run showed to matter) and adds v2's
- * mechanisms: scores held in registers across the row-max exchange, O accumulated in TMEM, a separate issuer warp.
- * OPT-IN (host: PVQA_ATTN_FWD_V3=1); written after round 1's GPU budget was spent, not yet run on a device. */
-int pvqa_attn_fwd_v3(const void* q, const void* k, const void* v, void* o, float* lse,
-                     const float* rel_bias, const float* key_add,
-                     int64_t B, int64_t H, int64_t Sq, int64_t Sk, int64_t D,
-                     int64_t q_stride_b, int64_t q_stride_s, int64_t q_stride_h,
-                     int64_t k_stride_b, int64_t k_stride_s, int64_t k_stride_h,
-                     int64_t v_stride_b, int64_t v_stride_s, int64_t v_stride_h,
-                     int64_t o_stride_b, int64_t o_stride_s, int64_t o_stride_h,
-                     float scale, int causal,
-                     float dropout_p, uint64_t seed, uint64_t offset,
-                     const uint8_t* scp_bucket, const float* scp_table, int64_t scp_q0, int64_t scp_L,
-                     void* stream);
-
 /* backward.  dk, dv: bf16 with explicit strides (may point into a packed d(qkv) buffer).
  * dq_accum: fp32 (B,Sq,H,64) contiguous, ZERO-INITIALISED by the caller — every 128-key tile
  * adds its partial dQ with fp32 reductions; the caller converts/copies it to bf16.
  * d_rel_bias (H, Sq+Sk-1) fp32, accumulated (caller zero-initialises) = sum_{b,i,j: j-i fixed} dS, or NULL.
+ * rel_far: 0, or a promise about rel_bias that lets the kernel skip the per-diagonal reduction far from the diagonal:
+ *   rel_bias[h][r] is the same for all r with (r - (Sq-1)) >= rel_far, and the same for all r with
+ *   (r - (Sq-1)) <= -rel_far (T5's bucketed bias: every offset beyond the last bucket boundary shares one table entry,
+ *   HF modeling_t5.py:_relative_position_bucket).  The gradient of such a tail is then returned on ONE offset of the
+ *   tail per 32x32 block — exact for any caller that sums d_rel_bias over offsets sharing a bias value, which is what
+ *   the bucket scatter of the T5 table does.
  * o, d_o: forward output and its gradient (bf16, strided). */
 int pvqa_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* d_o,
                   const float* lse, const float* rel_bias, const float* key_add,
@@ -262,7 +235,7 @@ int pvqa_attn_bwd(const void* q, const void* k, const void* v, const void* o, co
                   float scale, int causal,
                   float dropout_p, uint64_t seed, uint64_t offset,
                   const uint8_t* scp_bucket, const float* scp_table, float* d_scp_table,
-                  int64_t scp_q0, int64_t scp_L, void* stream);
+                  int64_t scp_q0, int64_t scp_L, int64_t rel_far, void* stream);
 
 /* ------------------------------------------------------------------------
  * fp32 parity-mode attention (CUDA cores, no tensor-core rounding): same score definition as

@@ -18,7 +18,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libpvqa_sm100.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 SOURCES = ["api.cu", "embed.cu", "head.cu", "attn.cu", "attn_simt.cu", "norm.cu"]
-HEADERS = ["common.cuh", "tc05.cuh", "attn_fwd2.cuh", "attn_fwd3.cuh", "attn_fwd2_layout.h"]
+HEADERS = ["common.cuh", "tc05.cuh", "attn_fwd.cuh", "attn_bwd.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -27,7 +27,7 @@ NVCC_FLAGS = [
 ]
 
 PVQA_F32, PVQA_BF16 = 0, 1
-ABI_VERSION = 7  # must equal PVQA_ABI_VERSION in include/pvqa.h
+ABI_VERSION = 8  # must equal PVQA_ABI_VERSION in include/pvqa.h
 
 
 def _stale() -> bool:
@@ -39,20 +39,36 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source for sm_100a into csrc/libpvqa_sm100.so (in-tree)."""
+    """Compile every CUDA source for sm_100a into csrc/libpvqa_sm100.so (in-tree).  The translation units are
+    compiled concurrently (attn.cu alone instantiates twenty tcgen05 kernels) and linked by one nvcc call."""
     if not force and not _stale():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libpvqa_sm100.so")
-    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH + ".tmp"] + srcs
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    objdir = os.path.join(CSRC, "build")
+    os.makedirs(objdir, exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+    procs = []
+    for src in srcs:
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        procs.append((src, obj, subprocess.Popen([nvcc] + compile_flags + ["-c", os.path.join(CSRC, src), "-o", obj],
+                                                 stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    objs, log = [], []
+    for src, obj, pr in procs:
+        out = pr.communicate()[0]
+        log.append(out)
+        if pr.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{out}")
+        objs.append(obj)
+    res = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH + ".tmp"] + objs,
+                         capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     os.replace(LIB_PATH + ".tmp", LIB_PATH)
     if verbose:
-        print(res.stderr)
+        print("".join(log))
     return LIB_PATH
 
 
@@ -74,9 +90,8 @@ _SIGNATURES = {
     "pvqa_phoneme_head_ce_bwd": (c_int, [_vp, _vp, _i64] + [_vp] * 12 + _i64x(8) + [c_int, c_int, _vp]),
     "pvqa_vocab_ce_grad": (c_int, [_vp, _vp, _i64, _vp, _vp, _vp] + _i64x(3) + [_vp]),
     "pvqa_attn_fwd": (c_int, [_vp] * 7 + _i64x(5) + _i64x(12) + [_f, c_int, _f, c_uint64, c_uint64, _vp, _vp, _i64, _i64, _vp]),
-    "pvqa_attn_fwd_v2": (c_int, [_vp] * 7 + _i64x(5) + _i64x(12) + [_f, c_int, _f, c_uint64, c_uint64, _vp, _vp, _i64, _i64, _vp]),
-    "pvqa_attn_fwd_v3": (c_int, [_vp] * 7 + _i64x(5) + _i64x(12) + [_f, c_int, _f, c_uint64, c_uint64, _vp, _vp, _i64, _i64, _vp]),
-    "pvqa_attn_bwd": (c_int, [_vp] * 13 + _i64x(5) + _i64x(21) + [_f, c_int, _f, c_uint64, c_uint64, _vp, _vp, _vp, _i64, _i64, _vp]),
+    "pvqa_attn_bwd": (c_int, [_vp] * 13 + _i64x(5) + _i64x(21) + [_f, c_int, _f, c_uint64, c_uint64, _vp, _vp, _vp, _i64, _i64,
+                              _i64, _vp]),
     "pvqa_attn_f32_fwd": (c_int, [_vp] * 7 + _i64x(5) + _i64x(12) + [_f, c_int, _f, c_uint64, c_uint64, _vp, _vp, _i64, _i64, _vp]),
     "pvqa_rms_norm_fwd": (c_int, [_vp] * 4 + _i64x(2) + [_f, c_int, c_int, _vp]),
     "pvqa_rms_norm_bwd": (c_int, [_vp] * 7 + _i64x(2) + [c_int, c_int, _vp]),

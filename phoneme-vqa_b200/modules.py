@@ -285,6 +285,26 @@ def t5_bucket_lut(q_len, k_len, bidirectional, num_buckets, max_distance, device
     return lut
 
 
+def t5_bucket_far(q_len, k_len, bidirectional, num_buckets, max_distance):
+    """Smallest F >= 1 such that the bucket id is one constant for every offset rel >= F and one constant for every
+    rel <= -F (with 32 buckets / max distance 128: F = 91).  The attention backward uses it to credit the bias gradient
+    of blocks that lie entirely in those tails to a single offset (include/pvqa.h: rel_far) — exact, because the table
+    gradient sums d_rel over all offsets of a bucket anyway.  0 when the vector has no such tails."""
+    key = ("far", q_len, k_len, bidirectional, num_buckets, max_distance)
+    far = _BUCKET_CACHE.get(key)
+    if far is None:
+        lut = t5_bucket_lut(q_len, k_len, bidirectional, num_buckets, max_distance, "cpu")
+        zero = q_len - 1                                   # index of rel = 0
+        far = 0
+        for f in range(1, min(q_len, k_len)):
+            pos, neg = lut[zero + f:], lut[:zero - f + 1]
+            if bool((pos == pos[0]).all()) and bool((neg == neg[0]).all()):
+                far = f
+                break
+        _BUCKET_CACHE[key] = far
+    return far
+
+
 class T5Attention(nn.Module):
     def __init__(self, config, has_relative_attention_bias=False):
         super().__init__()
@@ -308,7 +328,10 @@ class T5Attention(nn.Module):
         """(H, q_len + k_len - 1) fp32: bias as a function of the relative offset j - i."""
         lut = t5_bucket_lut(q_len, k_len, not self.is_decoder, self.relative_attention_num_buckets,
                             self.relative_attention_max_distance, self.relative_attention_bias.weight.device)
-        return self.relative_attention_bias.weight.float()[lut].t().contiguous()
+        rb = self.relative_attention_bias.weight.float()[lut].t().contiguous()
+        rb.pvqa_rel_far = t5_bucket_far(q_len, k_len, not self.is_decoder, self.relative_attention_num_buckets,
+                                        self.relative_attention_max_distance)
+        return rb
 
     def forward(self, x, rel_bias, key_add, kv=None, causal=False, scp=None):
         """x (B,S,d) compute dtype.  Self-attention when kv is None, else cross-attention on kv."""
@@ -750,7 +773,9 @@ class _RelBiasTable(nn.Module):
 class RelativePositionBias1D(_RelBiasTable):
     def rel_vector(self, S):
         lut = t5_bucket_lut(S, S, True, 32, 128, self.relative_attention_bias.weight.device)
-        return self.relative_attention_bias.weight.float()[lut].t().contiguous()
+        rb = self.relative_attention_bias.weight.float()[lut].t().contiguous()
+        rb.pvqa_rel_far = t5_bucket_far(S, S, True, 32, 128)
+        return rb
 
 
 class SCPRelativePositionBias(_RelBiasTable):
@@ -769,8 +794,9 @@ class SCPRelativePositionBias(_RelBiasTable):
     def buckets(self, coordinates):
         """coordinates (B,L,4) in [0,1) -> uint8 (B,L,L) bucket ids (SaL_utils.py:152-168, on the device)."""
         g = self.GRID
-        xc = coordinates[:, :, [0, 2]].mean(dim=-1)
-        yc = coordinates[:, :, [1, 3]].mean(dim=-1)
+        # mean of two values == (a + b) / 2 exactly; list indexing would build a host index tensor (not capturable)
+        xc = (coordinates[:, :, 0] + coordinates[:, :, 2]) / 2
+        yc = (coordinates[:, :, 1] + coordinates[:, :, 3]) / 2
         cx = torch.floor(xc * g).to(torch.long).clamp_(0, g - 1)
         cy = torch.floor(yc * g).to(torch.long).clamp_(0, g - 1)
         cell = cx * g + cy

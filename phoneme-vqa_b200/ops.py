@@ -561,12 +561,6 @@ def relu_dropout(x, p, training):
 # ----------------------------------------------------------------------------------
 # K2 / K3: attention.  bf16 -> tcgen05/TMA flash kernels; fp32 (parity mode) -> fp32 CUDA-core kernels.
 # ----------------------------------------------------------------------------------
-# Opt-in forward kernels (csrc/attn_fwd2.cuh, attn_fwd3.cuh).  All entry points have the same contract, so these are
-# switches, not fallbacks.  v2: correct on the device but not faster than the product kernel; v3: not yet run.
-ATTN_FWD_V2 = os.environ.get("PVQA_ATTN_FWD_V2", "0") == "1"
-ATTN_FWD_V3 = os.environ.get("PVQA_ATTN_FWD_V3", "0") == "1"
-
-
 def _check_attn_operand(t, name, dtype):
     if t.dtype != dtype or t.dim() != 4 or t.stride(3) != 1:
         raise TypeError(f"attention {name} must be a {dtype} (B,S,H,D) view with unit stride on D")
@@ -579,7 +573,8 @@ def _st3(t):
 def _drop_args(dropout_p, B, H, Sq, Sk):
     if dropout_p <= 0.0:
         return 0.0, 0, 0
-    seed, off = _Rng.next(8 * B * H * Sq * ((Sk + 15) // 16))
+    # one Philox counter per (query row, 32-key block) (csrc/attn_fwd.cuh: AttnDrop); _Rng.next reserves n / 8 counters
+    seed, off = _Rng.next(8 * B * H * Sq * ((Sk + 31) // 32))
     return float(dropout_p), seed, off
 
 
@@ -612,10 +607,6 @@ def attention_fwd_raw(q, k, v, scale, rel_bias=None, key_add=None, causal=False,
         raise ValueError(f"key_add must be (B, Sk) = {(B, Sk)}, got {tuple(key_add.shape)}")
     if dtype != torch.bfloat16:
         fn, name = lib.pvqa_attn_f32_fwd, "attn_f32_fwd"
-    elif ATTN_FWD_V3:
-        fn, name = lib.pvqa_attn_fwd_v3, "attn_fwd_v3"
-    elif ATTN_FWD_V2:
-        fn, name = lib.pvqa_attn_fwd_v2, "attn_fwd_v2"
     else:
         fn, name = lib.pvqa_attn_fwd, "attn_fwd"
     with torch.cuda.device(dev), _prof(f"{name}[Sq={Sq},Sk={Sk}]"):
@@ -626,7 +617,7 @@ def attention_fwd_raw(q, k, v, scale, rel_bias=None, key_add=None, causal=False,
 
 
 def attention_bwd_raw(q, k, v, o, d_o, lse, scale, rel_bias, key_add, causal, dk, dv, want_d_rel, drop=(0.0, 0, 0),
-                      scp=None, want_d_scp=False):
+                      scp=None, want_d_scp=False, rel_far=0):
     """Backward through the C-ABI.  dk/dv are caller-provided (B,Sk,H,D) views (possibly into a packed
     buffer) in q's dtype.  Returns (dq fp32 (B,Sq,H,D), d_rel fp32 or None)."""
     lib = _lib.load()
@@ -647,7 +638,7 @@ def attention_bwd_raw(q, k, v, o, d_o, lse, scale, rel_bias, key_add, causal, dk
                                     _p(dq), _p(dk), _p(dv), _p(d_rel), _p(ws), B, H, Sq, Sk, D,
                                     *_st3(q), *_st3(k), *_st3(v), *_st3(o), *_st3(d_o), *_st3(dk), *_st3(dv),
                                     float(scale), int(bool(causal)), float(drop[0]), int(drop[1]), int(drop[2]),
-                                    sb, st_, _p(d_scp), sq0, sL, _stream()), "pvqa_attn_bwd")
+                                    sb, st_, _p(d_scp), sq0, sL, int(rel_far), _stream()), "pvqa_attn_bwd")
     else:
         dq = torch.empty((B, Sq, H, D), dtype=torch.float32, device=dev)
         ws = torch.empty((B, H, Sq), dtype=torch.float32, device=dev)
@@ -686,6 +677,8 @@ class _AttnSelf(torch.autograd.Function):
                     None if rel_bias is None else rel_bias.dtype, drop,
                     None if scp is None else scp[2], scp is not None and ctx.needs_input_grad[7],
                     None if scp_table is None else scp_table.dtype)
+        # producers of bucketed T5 vectors tag them with the start of their constant tails (modules.t5_bucket_far)
+        ctx.rel_far = int(getattr(rel_bias, "pvqa_rel_far", 0)) if rel_bias is not None else 0
         return o
 
     @staticmethod
@@ -695,7 +688,8 @@ class _AttnSelf(torch.autograd.Function):
         scp = (scp_t[0], scp_t[1], scp_q0) if scp_t else None
         dqkv = torch.empty_like(qkv)
         dq, d_rel, d_scp = attention_bwd_raw(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], o, d_o, lse, scale, rb, ka,
-                                             causal, dqkv[:, :, 1], dqkv[:, :, 2], want_rel, drop, scp, want_scp)
+                                             causal, dqkv[:, :, 1], dqkv[:, :, 2], want_rel, drop, scp, want_scp,
+                                             rel_far=ctx.rel_far)
         B_, S_, _, H_, D_ = dqkv.shape
         if (H_ * D_) % 8 == 0:          # fp32 accumulator -> q slot of the packed gradient, one vectorised pass
             with torch.cuda.device(dqkv.device), _prof("cast_rows"):
@@ -720,6 +714,7 @@ class _AttnCross(torch.autograd.Function):
         ctx.save_for_backward(q, kv, o, lse, rb, ka)
         ctx.meta = (float(scale), rel_bias is not None and ctx.needs_input_grad[2],
                     None if rel_bias is None else rel_bias.dtype, drop)
+        ctx.rel_far = int(getattr(rel_bias, "pvqa_rel_far", 0)) if rel_bias is not None else 0
         return o
 
     @staticmethod
@@ -728,7 +723,7 @@ class _AttnCross(torch.autograd.Function):
         scale, want_rel, rel_dtype, drop = ctx.meta
         dkv = torch.empty_like(kv)
         dq, d_rel, _ = attention_bwd_raw(q, kv[:, :, 0], kv[:, :, 1], o, d_o, lse, scale, rb, ka, False,
-                                         dkv[:, :, 0], dkv[:, :, 1], want_rel, drop)
+                                         dkv[:, :, 0], dkv[:, :, 1], want_rel, drop, rel_far=ctx.rel_far)
         return dq.to(q.dtype), dkv, (d_rel.to(rel_dtype) if want_rel else None), None, None, None
 
 

@@ -46,15 +46,6 @@ def test_argument_errors_are_reported_without_a_device():
     rc = lib.pvqa_attn_fwd(None, None, None, None, None, None, None, 1, 1, 8, 8, 32,
                            0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1.0, 0, 0.0, 0, 0, None, None, 0, 0, None)
     assert rc == 1 and b"head dim" in lib.pvqa_last_error()
-    for fn, tag in ((lib.pvqa_attn_fwd_v2, b"attn_fwd_v2"), (lib.pvqa_attn_fwd_v3, b"attn_fwd_v3")):   # same contract
-        rc = fn(None, None, None, None, None, None, None, 1, 1, 8, 8, 32,
-                0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1.0, 0, 0.0, 0, 0, None, None, 0, 0, None)
-        assert rc == 1 and b"head dim" in lib.pvqa_last_error() and tag in lib.pvqa_last_error()
-        rc = fn(None, None, None, None, None, None, None, 1, 1, 8, 8, 64,
-                0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1.0, 0, 1.5, 0, 0, None, None, 0, 0, None)
-        assert rc == 1 and b"dropout_p" in lib.pvqa_last_error()
-        assert fn(None, None, None, None, None, None, None, 0, 1, 8, 8, 64,
-                  0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1.0, 0, 0.0, 0, 0, None, None, 0, 0, None) == 0       # empty batch
     rc = lib.pvqa_embed_tgt_fwd(None, None, None, None, None, None, 1, 1, 10, 4, 4, 1, 1, 1, 0, 0, 0.0, 0, 0, None, None)
     assert rc == 1 and b"on_dim" in lib.pvqa_last_error()
     rc = lib.pvqa_phoneme_head_ce_fwd(None, None, 3, None, None, None, None, None, None, None, None, None, None, None,
@@ -93,17 +84,3 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 txt = open(os.path.join(dirpath, f), encoding="utf-8").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
-
-
-def test_opt_in_kernels_are_off_by_default():
-    """the product path is pvqa_attn_fwd / the full backward unless a PVQA_ATTN_* switch is set explicitly"""
-    import subprocess
-    import sys
-    env = {k: v for k, v in os.environ.items() if not k.startswith("PVQA_ATTN_")}
-    code = ("import sys; sys.path.insert(0, %r); from phoneme_vqa_b200 import ops; "
-            "print(ops.ATTN_FWD_V2, ops.ATTN_FWD_V3)" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout
-    assert out.split() == ["False", "False"]
-    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "phoneme-vqa_b200", "csrc",
-                            "attn.cu")).read()
-    assert 'getenv("PVQA_ATTN_BWD_LEAN")' in src and "lean_env && lean_env[0] == '1'" in src
