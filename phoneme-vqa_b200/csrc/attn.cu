@@ -160,18 +160,20 @@ extern "C" int pvqa_attn_fwd(const void* q, const void* k, const void* v, void* 
   PVQA_REQUIRE((reinterpret_cast<uintptr_t>(o) & 15) == 0 && o_stride_s % 8 == 0 && o_stride_h % 8 == 0 &&
                    o_stride_b % 8 == 0,
                PVQA_ERR_ALIGN, "attn_fwd: output rows must be 16-byte aligned");
-  const int n_kt = (int)((Sk + kFBN - 1) / kFBN);
-  const int n_kpad = n_kt * kFBN;
-  const int n_last = (int)(((Sk - (int64_t)(n_kt - 1) * kFBN) + 31) / 32 * 32);     // remainder rounded up to 32
+  // key tiles: n_full of width 128, then the remainder r as (32), (64), (64, 32) or (128)
+  const int n_full = (int)(Sk / kBN), rem = (int)(Sk % kBN);
+  const int w_a = rem == 0 ? 0 : rem <= 32 ? 32 : rem <= 96 ? 64 : 128;
+  const int w_b = (rem > 64 && rem <= 96) ? 32 : 0;
+  const int n_kt = n_full + (w_a ? 1 : 0) + (w_b ? 1 : 0);
+  const int n_kpad = n_kt * kBN;
   const int64_t n_floats = 2 * (int64_t)n_kpad + (rel_bias ? 2 * (int64_t)f_rel_copy_stride(n_kpad) + 32 : 0);
   const size_t smem_bytes = 1024 + kFOffFloats + (size_t)n_floats * 4;
-  // up to 113 KB two CTAs share an SM; beyond that (Sk > ~700 with a relative bias) the kernel runs one CTA per SM
   PVQA_REQUIRE(smem_bytes <= 227 * 1024, PVQA_ERR_SHAPE, "attn_fwd: Sk too large for the bias staging buffers");
   CUtensorMap tq, tk, tv;
   int rc;
   if ((rc = make_tmap(&tq, q, B, Sq, H, q_stride_b, q_stride_s, q_stride_h, kBM, "q"))) return rc;
-  if ((rc = make_tmap(&tk, k, B, Sk, H, k_stride_b, k_stride_s, k_stride_h, kFBN, "k"))) return rc;
-  if ((rc = make_tmap(&tv, v, B, Sk, H, v_stride_b, v_stride_s, v_stride_h, kFBN, "v"))) return rc;
+  if ((rc = make_tmap(&tk, k, B, Sk, H, k_stride_b, k_stride_s, k_stride_h, kBN, "k"))) return rc;
+  if ((rc = make_tmap(&tv, v, B, Sk, H, v_stride_b, v_stride_s, v_stride_h, kBN, "v"))) return rc;
   AttnFwdParams p{};
   p.o = reinterpret_cast<__nv_bfloat16*>(o); p.lse = lse; p.rel_bias = rel_bias; p.key_add = key_add;
   p.B = (int)B; p.H = (int)H; p.Sq = (int)Sq; p.Sk = (int)Sk;
@@ -179,7 +181,7 @@ extern "C" int pvqa_attn_fwd(const void* q, const void* k, const void* v, void* 
   p.sl2 = scale * kLog2e;
   const uint32_t thr8 = fill_drop(&p.drop, dropout_p, seed, offset, Sk);
   p.scp_bucket = scp_bucket; p.scp_tab = scp_table; p.scp_q0 = (int)scp_q0; p.scp_L = (int)scp_L;
-  p.n_qt = (int)((Sq + kBM - 1) / kBM); p.n_kt = n_kt; p.n_last = n_last;
+  p.n_qt = (int)((Sq + kBM - 1) / kBM); p.n_kt = n_kt; p.n_full = n_full; p.w_a = w_a; p.w_b = w_b;
   const int64_t n_items = H * (int64_t)p.n_qt * B;
   PVQA_REQUIRE(n_items < (1ll << 30), PVQA_ERR_SHAPE, "attn_fwd: too many (batch, head, query tile) items");
   p.n_items = (int)n_items;
@@ -199,9 +201,8 @@ extern "C" int pvqa_attn_fwd(const void* q, const void* k, const void* v, void* 
     if (e != cudaSuccess) return fail(PVQA_ERR_CUDA, "attn_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set[vi] = true;
   }
-  // persistent: two CTAs per SM (one when the staging buffers push a CTA past half an SM's shared memory)
-  const int per_sm = smem_bytes <= 113 * 1024 ? 2 : 1;
-  const int64_t max_ctas = (int64_t)num_sms() * per_sm;
+  // persistent: one CTA per SM walks a contiguous range of (head, query tile, batch) items
+  const int64_t max_ctas = num_sms();
   dim3 grid((unsigned)(n_items < max_ctas ? n_items : max_ctas));
   kern<<<grid, kFThreads, smem_bytes, (cudaStream_t)stream>>>(tq, tk, tv, p);
   count_launch();

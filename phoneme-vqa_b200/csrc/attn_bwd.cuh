@@ -144,8 +144,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     kt = hk % p.n_kt;
     h = hk / p.n_kt;
   };
+  // items are walked incrementally (b fastest, then key tile, then head): integer division by a run-time divisor costs
+  // ~150 cycles, and the first flat version paid a dozen of them per tile
+  struct Item { int h, kt, b; };
+  auto item_of = [&](int w) { Item x; decode(w, x.h, x.kt, x.b); return x; };
+  auto next_item = [&](Item x) {
+    if (++x.b == p.B) { x.b = 0; if (++x.kt == p.n_kt) { x.kt = 0; ++x.h; } }
+    return x;
+  };
   // query tiles an item visits: [m_first, n_qt); tiles entirely above the diagonal see nothing
-  auto first_tile = [&](int kt) { return CAUSAL ? (kt * kBN) / kBM : 0; };
+  auto first_tile = [&](int kt) { return CAUSAL ? kt : 0; };        // (kBN == kBM)
   PVQA_TRACEB(0);
 
   if (is_issuer) {
@@ -211,175 +219,190 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (is_issuer_wg) {
     if (is_issuer && w0 < w1) {
-      // ================= issuer warp: every lane walks the tile sequence (the named barriers are warp-wide), lane 0
-      // alone touches TMA, tcgen05 and the mbarriers =================
-      const bool L0 = lane == 0;
+      // ================= issuer warp.  Every lane walks the tile sequence and waits on the barriers; one elected lane
+      // issues TMA / tcgen05.  Everything is warp-uniform, so addresses and descriptors live in uniform registers
+      // (under `if (lane == 0)` ptxas moved each tcgen05.mma operand through an R2UR waterfall: ~100 cycles per MMA,
+      // 3 000 per tile for the 32 MMAs — profiles/r02_call3_attn_phase_trace.txt) =================
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       const uint32_t idesc_s = tc05::idesc_bf16(kBM, kBN, 0, 0);
       const uint32_t idesc_dkv = tc05::idesc_bf16(kBN, kD, 1, 1);   // A = P^T / dS^T (MN-major), B = dO / Q (MN-major)
       const uint32_t idesc_dq = tc05::idesc_bf16(kBM, kD, 0, 1);    // A = dS (K-major), B = K (MN-major)
       const uint32_t smem0 = tc05::smem_u32(smem);
-      struct Cursor { int w, it; };                        // a (item, query tile) position in this CTA's sequence
-      auto enter = [&](Cursor& c, int w) {
-        int h, kt, b;
-        decode(w, h, kt, b);
-        c.w = w; c.it = first_tile(kt);
-      };
+      struct Cursor { int w, it; Item x; };                // a (item, query tile) position in this CTA's sequence
+      auto enter = [&](Cursor& c, int w, Item x) { c.w = w; c.x = x; c.it = first_tile(x.kt); };
       auto advance = [&](Cursor& c) {
         if (++c.it < p.n_qt) return true;
         if (c.w + 1 >= w1) return false;
-        enter(c, c.w + 1);
+        enter(c, c.w + 1, next_item(c.x));
         return true;
       };
-      auto is_first = [&](const Cursor& c) {
-        int h, kt, b;
-        decode(c.w, h, kt, b);
-        return c.it == first_tile(kt);
-      };
+      auto is_first = [&](const Cursor& c) { return c.it == first_tile(c.x.kt); };
       auto load_k = [&](const Cursor& c) {
-        int h, kt, b;
-        decode(c.w, h, kt, b);
+        const int h = c.x.h, kt = c.x.kt, b = c.x.b;
         const int nb = (c.w - w0) & 1;
-        tc05::mbar_expect_tx(bar_k + nb, kBTile);
-        tc05::tma_load_4d(smem + kBOffK + nb * kBTile, &tmK, bar_k + nb, 0, h, kt * kBN, b);
+        if (tc05::elect_one()) {
+          tc05::mbar_expect_tx(bar_k + nb, kBTile);
+          tc05::tma_load_4d(smem + kBOffK + nb * kBTile, &tmK, bar_k + nb, 0, h, kt * kBN, b);
+        }
       };
       auto load_v = [&](const Cursor& c) {
-        int h, kt, b;
-        decode(c.w, h, kt, b);
-        tc05::mbar_expect_tx(bar_v, kBTile);
-        tc05::tma_load_4d(smem + kBOffV, &tmV, bar_v, 0, h, kt * kBN, b);
+        const int h = c.x.h, kt = c.x.kt, b = c.x.b;
+        if (tc05::elect_one()) {
+          tc05::mbar_expect_tx(bar_v, kBTile);
+          tc05::tma_load_4d(smem + kBOffV, &tmV, bar_v, 0, h, kt * kBN, b);
+        }
       };
       auto load_qdo = [&](const Cursor& c, int gx) {
-        int h, kt, b;
-        decode(c.w, h, kt, b);
+        const int h = c.x.h, b = c.x.b;
         uint8_t* dst = smem + kBOffQ + (gx & 1) * (2 * kBTile);
-        tc05::mbar_expect_tx(bar_ld + (gx & 1), 2 * kBTile);
-        tc05::tma_load_4d(dst, &tmQ, bar_ld + (gx & 1), 0, h, c.it * kBM, b);
-        tc05::tma_load_4d(dst + kBTile, &tmdO, bar_ld + (gx & 1), 0, h, c.it * kBM, b);
+        if (tc05::elect_one()) {
+          tc05::mbar_expect_tx(bar_ld + (gx & 1), 2 * kBTile);
+          tc05::tma_load_4d(dst, &tmQ, bar_ld + (gx & 1), 0, h, c.it * kBM, b);
+          tc05::tma_load_4d(dst + kBTile, &tmdO, bar_ld + (gx & 1), 0, h, c.it * kBM, b);
+        }
       };
-      auto issue_s_dp = [&](const Cursor& c, int gx) {      // S = Q K^T and dP = dO V^T of tile gx
-        const uint32_t qa = smem0 + kBOffQ + (gx & 1) * (2 * kBTile), da = qa + kBTile;
-        const uint32_t ka = smem0 + kBOffK + ((c.w - w0) & 1) * kBTile, va = smem0 + kBOffV;
+      auto issue_s = [&](const Cursor& c, int gx) {         // S = Q K^T of tile gx
+        const uint64_t qd_ = tc05::desc_sw128_k(smem0 + kBOffQ + (gx & 1) * (2 * kBTile));
+        const uint64_t kd_ = tc05::desc_sw128_k(smem0 + kBOffK + ((c.w - w0) & 1) * kBTile);
+        if (tc05::elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < kD / 16; ++ks)
-          tc05::mma_bf16_ss(tmem_base, tc05::smem_desc_sw128(qa + ks * 32, 16, 1024),
-                            tc05::smem_desc_sw128(ka + ks * 32, 16, 1024), idesc_s, ks > 0);
+          for (int ks = 0; ks < kD / 16; ++ks)
+            tc05::mma_bf16_ss(tmem_u, tc05::desc_step(qd_, ks * 32), tc05::desc_step(kd_, ks * 32), idesc_s, ks > 0);
+        }
+      };
+      auto issue_dp = [&](int gx) {                         // dP = dO V^T of tile gx, then "S/dP ready"
+        const uint64_t dd_ = tc05::desc_sw128_k(smem0 + kBOffQ + (gx & 1) * (2 * kBTile) + kBTile);
+        const uint64_t vd_ = tc05::desc_sw128_k(smem0 + kBOffV);
+        if (tc05::elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < kD / 16; ++ks)
-          tc05::mma_bf16_ss(tmem_base + kBN, tc05::smem_desc_sw128(da + ks * 32, 16, 1024),
-                            tc05::smem_desc_sw128(va + ks * 32, 16, 1024), idesc_s, ks > 0);
-        tc05::mma_commit(bar_s);
+          for (int ks = 0; ks < kD / 16; ++ks)
+            tc05::mma_bf16_ss(tmem_u + kBN, tc05::desc_step(dd_, ks * 32), tc05::desc_step(vd_, ks * 32), idesc_s, ks > 0);
+          tc05::mma_commit(bar_s);
+        }
       };
       auto reduce_dq = [&](const Cursor& c) {   // staging tile (fp32, two [128][32] SW128 halves) += into dq_accum
-        int h, kt, b;
-        decode(c.w, h, kt, b);
-        tc05::tma_reduce_add_4d(&tmdQ, smem + kBOffStg, 0, h, c.it * kBM, b);
-        tc05::tma_reduce_add_4d(&tmdQ, smem + kBOffStg + kBM * 128, 32, h, c.it * kBM, b);
-        tc05::bulk_commit_group();
-        tc05::bulk_wait_group_read0();          // the reduce has read the staging tile: hand it back
-        tc05::mbar_arrive(bar_stg);
+        const int h = c.x.h, b = c.x.b;
+        if (tc05::elect_one()) {
+          tc05::tma_reduce_add_4d(&tmdQ, smem + kBOffStg, 0, h, c.it * kBM, b);
+          tc05::tma_reduce_add_4d(&tmdQ, smem + kBOffStg + kBM * 128, 32, h, c.it * kBM, b);
+          tc05::bulk_commit_group();
+        }
+      };
+      auto release_stg = [&]() {                // the reduce has read the staging tile: hand it back (same elected lane:
+        if (tc05::elect_one()) {                //  bulk groups belong to the thread that committed them)
+          tc05::bulk_wait_group_read0();
+          tc05::mbar_arrive(bar_stg);
+        }
       };
 
       Cursor c_g, c_s, c_ld, c_prev;            // tiles g, g + 1, g + 2 and g - 1
-      enter(c_g, w0);
+      enter(c_g, w0, item_of(w0));
       c_s = c_g; c_ld = c_g; c_prev = c_g;
       int items_k = 1;                          // items whose K load has been issued
       int n_v = 1;                              // V loads issued (one per item: the phase of bar_v)
-      if (L0) { load_k(c_g); load_v(c_g); load_qdo(c_ld, 0); }
+      load_k(c_g); load_v(c_g); load_qdo(c_ld, 0);
       bool has_ld = advance(c_ld);
       if (has_ld) {
         if (c_ld.w != c_g.w) {                  // (the V buffer is still the first item's)
-          if (L0) load_k(c_ld);
+          load_k(c_ld);
           items_k = 2;
         }
-        if (L0) load_qdo(c_ld, 1);
+        load_qdo(c_ld, 1);
       }
       bool has_s = has_ld;
       if (has_ld) has_ld = advance(c_ld);
-      if (L0) {
-        tc05::mbar_wait(bar_k, 0);
-        tc05::mbar_wait(bar_v, 0);
-        tc05::mbar_wait(bar_ld, 0);
-        tc05::tc_fence_after_sync();
-        issue_s_dp(c_s, 0);
-      }
+      tc05::mbar_wait(bar_k, 0);
+      tc05::mbar_wait(bar_v, 0);
+      tc05::mbar_wait(bar_ld, 0);
+      tc05::tc_fence_after_sync();
+      issue_s(c_s, 0);
+      issue_dp(0);
       if (has_s) advance(c_s);
       for (int g = 0;; ++g) {
         const bool last_of_item = c_g.it + 1 == p.n_qt;
         const bool first = is_first(c_g);
-        // (1) every compute thread holds S/dP of tile g in registers: TMEM S/dP can take tile g + 1
+        const bool tr = g < 3;
+        if (tr) PVQA_TRACEB(2 + 6 * g);
+        // (1) every compute thread holds S/dP of tile g in registers: TMEM S/dP can take tile g + 1.  When tile g + 1 opens
+        //     the next item, its V is fetched into the buffer that just became free and dP waits for it at the end of
+        //     this turn; S needs only K, which arrived an item ago.
         tc05::named_bar_sync(1, kBSyncThreads);
+        if (tr) PVQA_TRACEB(3 + 6 * g);
+        bool dp_pending = false;
         if (has_s) {
+          tc05::tc_fence_after_sync();
           if (last_of_item) {
-            // S/dP of this item's last tile are complete (the compute threads have read them): V takes the next item's
-            if (L0) load_v(c_s);
+            load_v(c_s);
+            tc05::mbar_wait(bar_k + ((c_s.w - w0) & 1), ((c_s.w - w0) >> 1) & 1);
             ++n_v;
+            dp_pending = true;
           }
-          if (L0) {
-            tc05::tc_fence_after_sync();
-            if (last_of_item) {                               // tile g + 1 opens an item: its K and V
-              tc05::mbar_wait(bar_k + ((c_s.w - w0) & 1), ((c_s.w - w0) >> 1) & 1);
-              tc05::mbar_wait(bar_v, (n_v - 1) & 1);
-            }
-            tc05::mbar_wait(bar_ld + ((g + 1) & 1), ((g + 1) >> 1) & 1);
-            tc05::tc_fence_after_sync();
-            issue_s_dp(c_s, g + 1);
-          }
+          tc05::mbar_wait(bar_ld + ((g + 1) & 1), ((g + 1) >> 1) & 1);
+          tc05::tc_fence_after_sync();
+          issue_s(c_s, g + 1);
+          if (!last_of_item) issue_dp(g + 1);
           has_s = advance(c_s);
         }
-        __syncwarp();
-        // (2) P/dS of tile g are in smem, dQ of the previous tile of the item is staged and, for the first tile of an
-        //     item, the compute warps have drained the previous item's dK / dV
+        if (tr) PVQA_TRACEB(4 + 6 * g);
+        // (2) P/dS of tile g are in smem, dQ of tile g-1 is staged and, when tile g opens an item, the compute warps have
+        //     drained the previous item's dK / dV
         tc05::named_bar_sync(3, kBSyncThreads);
-        if (L0) {
-          tc05::tc_fence_after_sync();
-          const uint32_t q_addr = smem0 + kBOffQ + (g & 1) * (2 * kBTile), do_addr = q_addr + kBTile;
-          const uint32_t k_addr = smem0 + kBOffK + ((c_g.w - w0) & 1) * kBTile;
-          const uint32_t p_addr = smem0 + kBOffP, ds_addr = smem0 + kBOffdS;
-          const uint32_t dq_col = tmem_base + 384 + (g & 1) * 64;
+        if (tr) PVQA_TRACEB(5 + 6 * g);
+        tc05::tc_fence_after_sync();
+        {
+          const uint32_t q_addr = smem0 + kBOffQ + (g & 1) * (2 * kBTile);
+          const uint64_t qd_ = tc05::desc_sw128_k(q_addr), dod_ = tc05::desc_sw128_k(q_addr + kBTile);
+          const uint64_t kd_ = tc05::desc_sw128_k(smem0 + kBOffK + ((c_g.w - w0) & 1) * kBTile);
+          const uint64_t pt_ = tc05::smem_desc_sw128(smem0 + kBOffP, kBM * 128, 1024);      // P^T: MN-major A
+          const uint64_t dst_ = tc05::smem_desc_sw128(smem0 + kBOffdS, kBM * 128, 1024);    // dS^T
+          const uint64_t dsd_ = tc05::desc_sw128_k(smem0 + kBOffdS);                        // dS: K-major A
+          const uint32_t dq_col = tmem_u + 384 + (g & 1) * 64;
+          const uint32_t acc0 = first ? 0u : 1u;
+          if (tc05::elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < kBM / 16; ++ks)     // dV += P^T dO   (K = 128 query rows, 16 per step)
-            tc05::mma_bf16_ss(tmem_base + 256, tc05::smem_desc_sw128(p_addr + ks * 2048, kBM * 128, 1024),
-                              tc05::smem_desc_sw128(do_addr + ks * 2048, 16, 1024), idesc_dkv, (!first || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < kBM / 16; ++ks)     // dV += P^T dO   (K = 128 query rows, 16 per step)
+              tc05::mma_bf16_ss(tmem_u + 256, tc05::desc_step(pt_, ks * 2048), tc05::desc_step(dod_, ks * 2048), idesc_dkv,
+                                ks > 0 ? 1u : acc0);
 #pragma unroll
-          for (int ks = 0; ks < kBM / 16; ++ks)     // dK += dS^T Q
-            tc05::mma_bf16_ss(tmem_base + 320, tc05::smem_desc_sw128(ds_addr + ks * 2048, kBM * 128, 1024),
-                              tc05::smem_desc_sw128(q_addr + ks * 2048, 16, 1024), idesc_dkv, (!first || ks > 0) ? 1u : 0u);
-          tc05::mma_commit(bar_r);                  // Q / dO of this tile have been consumed: the ring stage is free
+            for (int ks = 0; ks < kBM / 16; ++ks)     // dK += dS^T Q
+              tc05::mma_bf16_ss(tmem_u + 320, tc05::desc_step(dst_, ks * 2048), tc05::desc_step(qd_, ks * 2048), idesc_dkv,
+                                ks > 0 ? 1u : acc0);
+            tc05::mma_commit(bar_r);                  // Q / dO of this tile have been consumed: the ring stage is free
 #pragma unroll
-          for (int ks = 0; ks < kBN / 16; ++ks)     // dQ_m = dS K    (K = 128 keys)
-            tc05::mma_bf16_ss(dq_col,
-                              tc05::smem_desc_sw128(ds_addr + (ks >> 2) * (kBM * 128) + (ks & 3) * 32, 16, 1024),
-                              tc05::smem_desc_sw128(k_addr + ks * 2048, 16, 1024), idesc_dq, ks > 0);
-          tc05::mma_commit(bar_g);
-          if (g < 9) PVQA_TRACEB(2 + 3 * g);
-          if (!first) reduce_dq(c_prev);
+            for (int ks = 0; ks < kBN / 16; ++ks)     // dQ_m = dS K    (K = 128 keys)
+              tc05::mma_bf16_ss(dq_col, tc05::desc_step(dsd_, (ks >> 2) * (kBM * 128) + (ks & 3) * 32),
+                                tc05::desc_step(kd_, ks * 2048), idesc_dq, ks > 0);
+            tc05::mma_commit(bar_g);
+          }
+          if (g > 0) { reduce_dq(c_prev); release_stg(); }
         }
+        if (tr) PVQA_TRACEB(6 + 6 * g);
         // the ring stage of tile g takes tile g + 2 as soon as dV / dK of tile g are done; a new item's K goes out with
         // its first Q / dO (into the buffer of the item before the current one, whose GEMMs finished long ago)
         if (has_ld) {
           const bool need_k = c_ld.w - w0 >= items_k;
-          if (L0) {
-            tc05::mbar_wait(bar_r, g & 1);
-            load_qdo(c_ld, g + 2);
-            if (need_k) {                           // the K buffer may have fed dQ of tile g (single-tile items)
-              tc05::mbar_wait(bar_g, g & 1);
-              load_k(c_ld);
-            }
+          tc05::mbar_wait(bar_r, g & 1);
+          load_qdo(c_ld, g + 2);
+          if (need_k) {                             // the K buffer may have fed dQ of tile g (single-tile items)
+            tc05::mbar_wait(bar_g, g & 1);
+            load_k(c_ld);
+            ++items_k;
           }
-          if (need_k) ++items_k;
           has_ld = advance(c_ld);
         }
-        c_prev = c_g;
-        __syncwarp();
-        if (last_of_item) {
-          // (3) dQ of the item's last tile is staged (the compute warps drain dK / dV next)
-          tc05::named_bar_sync(3, kBSyncThreads);
-          if (L0) reduce_dq(c_prev);
-          __syncwarp();
+        if (dp_pending) {                           // the next item's V has had a whole tile of time to land
+          tc05::mbar_wait(bar_v, (n_v - 1) & 1);
+          tc05::tc_fence_after_sync();
+          issue_dp(g + 1);
         }
+        c_prev = c_g;
+        if (tr) PVQA_TRACEB(7 + 6 * g);
         if (!advance(c_g)) break;
       }
-      if (L0) tc05::bulk_wait_group0();             // all reductions performed before the CTA retires
+      // dQ of the sequence's last tile is staged
+      tc05::named_bar_sync(3, kBSyncThreads);
+      reduce_dq(c_prev);
+      if (tc05::elect_one()) tc05::bulk_wait_group0();      // all reductions performed before the CTA retires
       __syncwarp();
     }
   }
@@ -399,78 +422,127 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // bias of local key jl for query i: relc[(n_qpad - 1 - i) + jl]; the parity of that offset is fixed per thread
     const float* relc_t = s_relc + ((n_qpad - 1 - rowl) & 1) * cs - ((n_qpad - 1 - rowl) & 1) + jl0;
 
+    // The tiles of all items form ONE sequence g = 0, 1, ...: after the math of tile g the thread stores P/dS(g), stages
+    // dQ(g-1) and, when tile g-1 closed an item, drains that item's dK / dV — so the wait for the previous tile's GEMMs
+    // and the drain sit behind a tile of math instead of forming a serial tail per item (37 % of an item in
+    // profiles/r02_call3_attn_phase_trace.txt).
     int g = 0;
     int h_cur = -1, kt_cur = -1;
-    for (int w = w0, n = 0; w < w1; ++w, ++n) {
-      int h, kt, b;
-      decode(w, h, kt, b);
-      const int j0 = kt * kBN;
-      const int m_first = first_tile(kt);
-      if (n == 0) { h_cur = h; kt_cur = kt; }
-      if (HAS_REL && (h != h_cur || kt != kt_cur)) {
-        // every compute thread finished the previous item (its dK / dV drain follows all bias reads and bin updates)
-        tc05::named_bar_sync(2, kBComputeThreads);
-        flush_rel(h_cur, kt_cur);
-        tc05::named_bar_sync(2, kBComputeThreads);
-        stage_rel(h, kt);
-        h_cur = h; kt_cur = kt;
-        tc05::named_bar_sync(2, kBComputeThreads);
-      }
-      // key term of the NEXT item into the other buffer (readers: after two more named barriers of this item)
-      if (w + 1 < w1 && tid < kBN) {
-        int h2, kt2, b2;
-        decode(w + 1, h2, kt2, b2);
-        const int j = kt2 * kBN + tid;
-        s_kadd[((n + 1) & 1) * kBN + tid] =
-            (j < p.Sk) ? (p.key_add ? p.key_add[(long long)b2 * p.Sk + j] * kLog2e : 0.f) : -INFINITY;
-      }
-      const float* kadd = s_kadd + (n & 1) * kBN + jl0;
-      const bool cols_dead = j0 + jl0 >= p.Sk;          // all 32 keys of this thread are past the end (warp-uniform)
-
-      // per-row statistics of a query tile, fetched one tile ahead so the global-load latency hides behind the math
-      auto load_stats = [&](int it, float& l_out, float& d_out) {
-        const int in = it * kBM + rowl;
-        l_out = -INFINITY; d_out = 0.f;
-        if (it < p.n_qt && in < p.Sq) {
-          const long long ri = ((long long)b * p.H + h) * p.Sq + in;
+    int w = w0;
+    Item cur = item_of(w0), prv = cur;             // the item of tile g, and of tile g - 1
+    int it = first_tile(cur.kt);
+    h_cur = cur.h; kt_cur = cur.kt;
+    // per-row statistics of a query tile, fetched one tile ahead so the global-load latency hides behind the math
+    auto load_stats = [&](bool valid, const Item& x, int it_, float& l_out, float& d_out) {
+      l_out = -INFINITY; d_out = 0.f;
+      if (valid) {
+        const int in = it_ * kBM + rowl;
+        if (in < p.Sq) {
+          const long long ri = ((long long)x.b * p.H + x.h) * p.Sq + in;
           l_out = p.lse[ri];
           d_out = p.delta[ri];
         }
-      };
-      // dQ of the previous tile (complete in TMEM) -> fp32 staging tile in smem (the issuer reduces it into dq_accum)
-      auto stage_dq = [&](int gp) {
-        if (gp > 0) tc05::mbar_wait(bar_stg, (gp - 1) & 1);       // the reduce of the tile before has read the buffer
-        uint32_t r[16];
-        tc05::tmem_ld_32x16(tmem_row + 384 + (gp & 1) * 64 + qd * 16, r);
-        tc05::tmem_ld_wait();
+      }
+    };
+    // dQ of tile gp (complete in TMEM) -> fp32 staging tile in smem (the issuer reduces it into dq_accum)
+    auto stage_dq = [&](int gp) {
+      if (gp > 0) tc05::mbar_wait(bar_stg, (gp - 1) & 1);         // the reduce of the tile before has read the buffer
+      uint32_t r[16];
+      tc05::tmem_ld_32x16(tmem_row + 384 + (gp & 1) * 64 + qd * 16, r);
+      tc05::tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                       :: "r"(stg_x ^ (uint32_t)(q << 4)), "r"(r[4 * q]), "r"(r[4 * q + 1]), "r"(r[4 * q + 2]), "r"(r[4 * q + 3])
-                       : "memory");
-      };
-      float lse_nx, delta_nx;
-      load_stats(m_first, lse_nx, delta_nx);
-      for (int it = m_first; it < p.n_qt; ++it, ++g) {
-        const int i0 = it * kBM;
-        const int i = i0 + rowl;
-        // +inf => p = exp2(s - inf) = 0 for dead rows and for rows whose softmax was empty (lse = -inf)
-        const float lse2 = (lse_nx != -INFINITY) ? lse_nx * kLog2e : INFINITY;
-        const float delta = delta_nx;
-        load_stats(it + 1, lse_nx, delta_nx);
-        const bool dead = cols_dead || i0 + quad * 32 >= p.Sq;      // warp-uniform
-        const bool diag = CAUSAL && (j0 + kBN - 1 > i0);
-        tc05::mbar_wait(bar_s, g & 1);
-        tc05::tc_fence_after_sync();
-        if (g < 9) PVQA_TRACEB(2 + 3 * g);
+      for (int q = 0; q < 4; ++q)
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                     :: "r"(stg_x ^ (uint32_t)(q << 4)), "r"(r[4 * q]), "r"(r[4 * q + 1]), "r"(r[4 * q + 2]), "r"(r[4 * q + 3])
+                     : "memory");
+    };
+    // dV / dK rows of a finished item (key j0 + rowl), columns [16 qd, +16): TMEM -> bf16 -> global
+    auto drain_dkv = [&](const Item& x) {
+      const int h = x.h, b = x.b;
+      const int j = x.kt * kBN + rowl;
+      uint32_t rv[16], rk[16];
+      tc05::tmem_ld_32x16(tmem_row + 256 + qd * 16, rv);
+      tc05::tmem_ld_32x16(tmem_row + 320 + qd * 16, rk);
+      tc05::tmem_ld_wait();
+      if (j < p.Sk) {
+        __nv_bfloat16* dvrow = p.dv + b * p.dv_stride_b + j * p.dv_stride_s + h * p.dv_stride_h + qd * 16;
+        __nv_bfloat16* dkrow = p.dk + b * p.dk_stride_b + j * p.dk_stride_s + h * p.dk_stride_h + qd * 16;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint4 uv, uk;
+          uv.x = f32x2_to_bf16x2(__uint_as_float(rv[c * 8 + 0]), __uint_as_float(rv[c * 8 + 1]));
+          uv.y = f32x2_to_bf16x2(__uint_as_float(rv[c * 8 + 2]), __uint_as_float(rv[c * 8 + 3]));
+          uv.z = f32x2_to_bf16x2(__uint_as_float(rv[c * 8 + 4]), __uint_as_float(rv[c * 8 + 5]));
+          uv.w = f32x2_to_bf16x2(__uint_as_float(rv[c * 8 + 6]), __uint_as_float(rv[c * 8 + 7]));
+          uk.x = f32x2_to_bf16x2(__uint_as_float(rk[c * 8 + 0]), __uint_as_float(rk[c * 8 + 1]));
+          uk.y = f32x2_to_bf16x2(__uint_as_float(rk[c * 8 + 2]), __uint_as_float(rk[c * 8 + 3]));
+          uk.z = f32x2_to_bf16x2(__uint_as_float(rk[c * 8 + 4]), __uint_as_float(rk[c * 8 + 5]));
+          uk.w = f32x2_to_bf16x2(__uint_as_float(rk[c * 8 + 6]), __uint_as_float(rk[c * 8 + 7]));
+          *reinterpret_cast<uint4*>(dvrow + c * 8) = uv;
+          *reinterpret_cast<uint4*>(dkrow + c * 8) = uk;
+        }
+      }
+    };
+    float lse_nx, delta_nx;
+    load_stats(true, cur, it, lse_nx, delta_nx);
+    bool prev_closed_item = false;                 // tile g-1 was the last query tile of its item (`prv`)
+    for (;; ++g) {
+      const int h = cur.h, kt = cur.kt, b = cur.b;
+      const int n = w - w0;
+      const int j0 = kt * kBN;
+      const int m_first = first_tile(kt);
+      if (it == m_first) {
+        // a new item.  Every compute thread is past the previous item's math (bias reads, bin updates): the bins can
+        // be flushed and restaged if the (head, key tile) changed, and the key term of the item AFTER this one can
+        // overwrite the buffer the previous item read.
+        tc05::named_bar_sync(2, kBComputeThreads);
+        if (HAS_REL && (h != h_cur || kt != kt_cur)) {
+          flush_rel(h_cur, kt_cur);
+          tc05::named_bar_sync(2, kBComputeThreads);
+          stage_rel(h, kt);
+          h_cur = h; kt_cur = kt;
+          tc05::named_bar_sync(2, kBComputeThreads);
+        }
+        if (w + 1 < w1 && tid < kBN) {             // (read after the named barrier that opens item n + 1)
+          const Item nx = next_item(cur);
+          const int j = nx.kt * kBN + tid;
+          s_kadd[((n + 1) & 1) * kBN + tid] =
+              (j < p.Sk) ? (p.key_add ? p.key_add[(long long)nx.b * p.Sk + j] * kLog2e : 0.f) : -INFINITY;
+        }
+      }
+      const float* kadd = s_kadd + (n & 1) * kBN + jl0;
+      const bool cols_dead = j0 + jl0 >= p.Sk;          // all 32 keys of this thread are past the end (warp-uniform)
+      const int i0 = it * kBM;
+      const int i = i0 + rowl;
+      const bool last_of_item = it + 1 == p.n_qt;
+      // the tile after this one (for the prefetch of its row statistics)
+      Item x_nx = cur;
+      int it_nx = it + 1;
+      bool has_nx = true;
+      if (last_of_item) {
+        x_nx = next_item(cur);
+        it_nx = first_tile(x_nx.kt);
+        has_nx = w + 1 < w1;
+      }
+      // +inf => p = exp2(s - inf) = 0 for dead rows and for rows whose softmax was empty (lse = -inf)
+      const float lse2 = (lse_nx != -INFINITY) ? lse_nx * kLog2e : INFINITY;
+      const float delta = delta_nx;
+      load_stats(has_nx, x_nx, it_nx, lse_nx, delta_nx);
+      const bool dead = cols_dead || i0 + quad * 32 >= p.Sq;      // warp-uniform
+      const bool diag = CAUSAL && (j0 + kBN - 1 > i0);
+      const bool tr = g < 3;
+      if (tr) PVQA_TRACEB(2 + 6 * g);
+      tc05::mbar_wait(bar_s, g & 1);
+      tc05::tc_fence_after_sync();
+      if (tr) PVQA_TRACEB(3 + 6 * g);
 
-        uint32_t pw[16], dw[16];                 // bf16x2 words of this thread's P and dS columns
-        if (dead) {
-          tc05::tc_fence_before_sync();
-          tc05::named_bar_arrive(1, kBSyncThreads);
+      uint32_t pw[16], dw[16];                 // bf16x2 words of this thread's P and dS columns
+      if (dead) {
+        tc05::tc_fence_before_sync();
+        tc05::named_bar_arrive(1, kBSyncThreads);
 #pragma unroll
-          for (int x = 0; x < 16; ++x) { pw[x] = 0u; dw[x] = 0u; }
-        } else {
+        for (int x = 0; x < 16; ++x) { pw[x] = 0u; dw[x] = 0u; }
+      } else {
           // ---- e = s * scale * log2e + bias - lse  (exp2 domain; 1/keep rides in the exponent with dropout);
           //      p = exp2(e);  ds = scale * p * (M dP / keep - delta):  with dropout pk = p / keep, pm = pk & M and
           //      ds = pm * (scale dP) + pk * (-scale keep_prob delta).  Eight columns at a time keeps registers short.
@@ -480,12 +552,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const float2 nd2 = make_float2(nd, nd), sc2 = make_float2(p.scale, p.scale);
           const float4* ka4 = reinterpret_cast<const float4*>(kadd);
           const float2* rl2 = reinterpret_cast<const float2*>(relc_t + (n_qpad - 1 - rowl) - i0);
-          uint32_t kw[8];
-          if (DROP) {
-            const uint64_t ctr = rng_off + ((uint64_t)(b * p.H + h) * p.Sq + min(i, p.Sq - 1)) * p.drop.blk_per_row +
-                                 (uint32_t)((j0 + jl0) >> 5);
-            keep_shifted(keep_bits32(p.drop, ctr), kw);
-          }
           const bool row_in = SCP && i < p.Sq && i >= p.scp_q0 && i < p.scp_q0 + p.scp_L;
           const uint8_t* scp_row = SCP ? p.scp_bucket + ((long long)b * p.scp_L + (i - p.scp_q0)) * p.scp_L : nullptr;
           // d_rel: diagonals lane (mod 32) of this warp's 32 x 32 block — or, when every offset of the block lies in one
@@ -496,11 +562,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const int d_lo = (j0 + jl0) - (i0 + quad * 32 + 31), d_hi = (j0 + jl0 + 31) - (i0 + quad * 32);
           const bool far = HAS_REL && p.rel_far > 0 && (d_lo >= p.rel_far || d_hi <= -p.rel_far);       // warp-uniform
           float2 s2[8], dp2[8];                   // 16 columns of S and of dP at a time
+          uint32_t kw[8];
 #pragma unroll
           for (int c8 = 0; c8 < 4; ++c8) {
             if ((c8 & 1) == 0) {
               tc05::tmem_ld_32x16(tmem_row + jl0 + c8 * 8, *reinterpret_cast<uint32_t(*)[16]>(s2));
               tc05::tmem_ld_32x16(tmem_row + kBN + jl0 + c8 * 8, *reinterpret_cast<uint32_t(*)[16]>(dp2));
+              if (DROP && c8 == 0) {               // the dropout bits (integer work) hide under the TMEM load
+                const uint64_t ctr = rng_off + ((uint64_t)(b * p.H + h) * p.Sq + min(i, p.Sq - 1)) * p.drop.blk_per_row +
+                                     (uint32_t)((j0 + jl0) >> 5);
+                keep_shifted(keep_bits32(p.drop, ctr), kw);
+              }
               tc05::tmem_ld_wait();
               if (c8 == 2) {
                 // S/dP of this tile now live in registers: the issuer may overwrite TMEM with the next tile's
@@ -605,71 +677,54 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
               }
             }
           }
-        }
-        // P/dS smem is still read by the GEMMs of tile g-1: wait for them right before the stores (long done by then)
-        if (g > 0) {
-          tc05::mbar_wait(bar_g, (g - 1) & 1);
-          tc05::tc_fence_after_sync();
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                       :: "r"(prow_x ^ (uint32_t)(q << 4)), "r"(pw[4 * q]), "r"(pw[4 * q + 1]), "r"(pw[4 * q + 2]), "r"(pw[4 * q + 3])
-                       : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                       :: "r"(dsrow_x ^ (uint32_t)(q << 4)), "r"(dw[4 * q]), "r"(dw[4 * q + 1]), "r"(dw[4 * q + 2]), "r"(dw[4 * q + 3])
-                       : "memory");
-        }
-        // dQ of the previous tile of THIS item (the last tile of an item is staged in the item's tail below)
-        if (it > m_first) stage_dq(g - 1);
-        tc05::fence_proxy_async_smem();
-        tc05::tc_fence_before_sync();
-        tc05::named_bar_arrive(3, kBSyncThreads);
       }
-      // ---- item tail: dQ of the last tile, then dV / dK rows (key j0 + rowl), columns [16 qd, +16) ----
-      if (p.n_qt > m_first) {
+      if (tr) PVQA_TRACEB(4 + 6 * g);
+      // P/dS smem is still read by the GEMMs of tile g-1: wait for them right before the stores (long done by then)
+      if (g > 0) {
         tc05::mbar_wait(bar_g, (g - 1) & 1);
         tc05::tc_fence_after_sync();
-        stage_dq(g - 1);
-        tc05::fence_proxy_async_smem();
-        tc05::tc_fence_before_sync();
-        tc05::named_bar_arrive(3, kBSyncThreads);
       }
-      {
-        const int j = j0 + rowl;
-        uint32_t rv[16], rk[16];
-        if (p.n_qt > m_first) {
-          tc05::tmem_ld_32x16(tmem_row + 256 + qd * 16, rv);
-          tc05::tmem_ld_32x16(tmem_row + 320 + qd * 16, rk);
-          tc05::tmem_ld_wait();
-          tc05::tc_fence_before_sync();
-        } else {
+      if (tr) PVQA_TRACEB(5 + 6 * g);
 #pragma unroll
-          for (int x = 0; x < 16; ++x) { rv[x] = 0u; rk[x] = 0u; }
-        }
-        if (j < p.Sk) {
-          __nv_bfloat16* dvrow = p.dv + b * p.dv_stride_b + j * p.dv_stride_s + h * p.dv_stride_h + qd * 16;
-          __nv_bfloat16* dkrow = p.dk + b * p.dk_stride_b + j * p.dk_stride_s + h * p.dk_stride_h + qd * 16;
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint4 uv, uk;
-            uv.x = f32x2_to_bf16x2(__uint_as_float(rv[c * 8 + 0]), __uint_as_float(rv[c * 8 + 1]));
-            uv.y = f32x2_to_bf16x2(__uint_as_float(rv[c * 8 + 2]), __uint_as_float(rv[c * 8 + 3]));
-            uv.z = f32x2_to_bf16x2(__uint_as_float(rv[c * 8 + 4]), __uint_as_float(rv[c * 8 + 5]));
-            uv.w = f32x2_to_bf16x2(__uint_as_float(rv[c * 8 + 6]), __uint_as_float(rv[c * 8 + 7]));
-            uk.x = f32x2_to_bf16x2(__uint_as_float(rk[c * 8 + 0]), __uint_as_float(rk[c * 8 + 1]));
-            uk.y = f32x2_to_bf16x2(__uint_as_float(rk[c * 8 + 2]), __uint_as_float(rk[c * 8 + 3]));
-            uk.z = f32x2_to_bf16x2(__uint_as_float(rk[c * 8 + 4]), __uint_as_float(rk[c * 8 + 5]));
-            uk.w = f32x2_to_bf16x2(__uint_as_float(rk[c * 8 + 6]), __uint_as_float(rk[c * 8 + 7]));
-            *reinterpret_cast<uint4*>(dvrow + c * 8) = uv;
-            *reinterpret_cast<uint4*>(dkrow + c * 8) = uk;
-          }
-        }
+      for (int q = 0; q < 4; ++q) {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                     :: "r"(prow_x ^ (uint32_t)(q << 4)), "r"(pw[4 * q]), "r"(pw[4 * q + 1]), "r"(pw[4 * q + 2]), "r"(pw[4 * q + 3])
+                     : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                     :: "r"(dsrow_x ^ (uint32_t)(q << 4)), "r"(dw[4 * q]), "r"(dw[4 * q + 1]), "r"(dw[4 * q + 2]), "r"(dw[4 * q + 3])
+                     : "memory");
       }
-      tc05::named_bar_sync(2, kBComputeThreads);      // next item's key term (written at this item's start) is visible
-      if (n == 0) PVQA_TRACEB(29);
+      if (tr) PVQA_TRACEB(6 + 6 * g);
+      if (g > 0) {
+        stage_dq(g - 1);                          // its GEMMs are complete (bar_g above)
+        if (prev_closed_item) drain_dkv(prv);     // before this tile's GEMMs (accumulate = 0) overwrite dV / dK
+      }
+      tc05::fence_proxy_async_smem();
+      tc05::tc_fence_before_sync();
+      tc05::named_bar_arrive(3, kBSyncThreads);
+      if (tr) PVQA_TRACEB(7 + 6 * g);
+      prev_closed_item = last_of_item;
+      prv = cur;
+      // next tile of the sequence
+      if (!last_of_item) {
+        ++it;
+      } else {
+        if (n == 0) PVQA_TRACEB(28);
+        if (n == 1) PVQA_TRACEB(29);
+        if (++w >= w1) break;
+        cur = x_nx;
+        it = it_nx;
+      }
     }
-    // the bins of the last (head, key tile) this CTA worked on
+    // ---- tail of the sequence: dQ of the last tile, dV / dK of the last item, the bins of the last (head, key tile)
+    ++g;                                          // (g now counts the tiles done)
+    tc05::mbar_wait(bar_g, (g - 1) & 1);
+    tc05::tc_fence_after_sync();
+    stage_dq(g - 1);
+    tc05::fence_proxy_async_smem();
+    tc05::tc_fence_before_sync();
+    tc05::named_bar_arrive(3, kBSyncThreads);
+    drain_dkv(prv);
     if (HAS_REL) {
       tc05::named_bar_sync(2, kBComputeThreads);
       flush_rel(h_cur, kt_cur);

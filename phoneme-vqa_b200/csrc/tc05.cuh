@@ -39,6 +39,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) { }
 }
 
+// One lane of a converged warp (deterministic for a given member mask).  Code that runs warp-uniformly and predicates
+// only the TMA / tcgen05 instruction on this keeps its descriptors in UNIFORM registers; the same code under
+// `if (lane == 0)` makes ptxas move every operand through an R2UR waterfall loop (~100 cycles per tcgen05.mma).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------- proxies / fences ----------------
 // generic-proxy smem writes (st.shared) -> visible to the async proxy (UMMA / TMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
@@ -136,6 +149,12 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, ui
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// SW128 descriptor of a tile whose rows are 128 bytes (SBO = 1024: eight rows per swizzle atom).  The start address
+// sits in the low 14 bits (>> 4), so stepping through a tile is an ADD on the low word: + (bytes >> 4).
+__device__ __forceinline__ uint64_t desc_sw128_k(uint32_t smem_addr) { return smem_desc_sw128(smem_addr, 16, 1024); }
+__device__ __forceinline__ uint64_t desc_step(uint64_t d, uint32_t bytes) {
+  return (d & 0xffffffff00000000ull) | (uint32_t)((uint32_t)d + (bytes >> 4));
 }
 // arrive on an mbarrier when all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {

@@ -97,6 +97,47 @@ class _Rng:
         return cls.seed, off
 
 
+_RNG_COUNTERS = {}      # device -> int64 tensor, alive as long as the library's pointer to it
+
+
+def rng_step_counter(device) -> torch.Tensor:
+    """The device-resident dropout step counter every dropout kernel adds to its Philox offset (CUDA-graph replays
+    bump it to draw fresh masks).  The C side keeps the raw pointer (pvqa_set_rng_step_counter), so the tensor is
+    owned HERE, for the life of the process — not by whichever TrainStep happened to create it."""
+    dev = torch.device(device)
+    key = (dev.type, dev.index if dev.index is not None else torch.cuda.current_device())
+    t = _RNG_COUNTERS.get(key)
+    if t is None:
+        t = torch.zeros(1, dtype=torch.int64, device=dev)
+        _RNG_COUNTERS[key] = t
+    _lib.load().pvqa_set_rng_step_counter(t.data_ptr())
+    return t
+
+
+_ERR_FLAGS = []         # int32 device flags the embedding kernels raise on an out-of-range index
+
+
+def _new_err_flag(dev) -> torch.Tensor:
+    """one persistent flag per device; kernels only ever set it, check_index_errors() reads and clears it"""
+    for f in _ERR_FLAGS:
+        if f.device == dev:
+            return f
+    f = torch.zeros(1, dtype=torch.int32, device=dev)
+    _ERR_FLAGS.append(f)
+    return f
+
+
+def check_index_errors() -> None:
+    """Raise if an embedding kernel saw a token / coordinate / label index outside its table since the last check
+    (the reference's nn.Embedding raises a device assert, e.g. for coordinates >= max_2d_position_embeddings; the
+    kernels zero the row and set this flag).  One host sync: call it per epoch or every N steps, outside captures."""
+    for f in _ERR_FLAGS:
+        if int(f.item()) != 0:
+            f.zero_()
+            raise IndexError("pvqa: an embedding kernel received an index outside its table "
+                             "(token id, layout coordinate or phoneme label); the offending rows were zeroed")
+
+
 def manual_seed(seed: int) -> None:
     """Seed the in-kernel dropout generator (independent from torch's generator)."""
     _Rng.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
@@ -140,7 +181,7 @@ class _EmbedMM(torch.autograd.Function):
         shared_c = shared_w.contiguous()
         out = torch.empty((B, S, d), dtype=out_dtype, device=dev)
         out_mask = torch.empty((B, S), dtype=torch.float32, device=dev)
-        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        err = _new_err_flag(dev)      # persistent (no per-call allocation / memset); read by check_index_errors()
         tabs = _ptr_array(layout_w) if has_ocr else None
         with torch.cuda.device(dev), _prof("embed_mm_fwd"):
             check(lib.pvqa_embed_mm_fwd(_p(img_feat), _p(coords), _p(ocr_ids), _p(q_ids), _p(ocr_mask), _p(q_mask),
@@ -223,7 +264,7 @@ class _EmbedTgt(torch.autograd.Function):
         pe2 = pe2.contiguous()
         dev = onset_w.device
         out = torch.empty((B, T, d), dtype=out_dtype, device=dev)
-        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        err = _new_err_flag(dev)      # persistent (no per-call allocation / memset); read by check_index_errors()
         seed, offset = _Rng.next(B * T * d) if dropout_p > 0 else (0, 0)
         ow, rw, tw = onset_w.contiguous(), rhyme_w.contiguous(), tone_w.contiguous()
         with torch.cuda.device(dev), _prof("embed_tgt_fwd"):

@@ -2,8 +2,8 @@
 
 `python tools/attn_trace.py build` compiles a private copy of the library with -DPVQA_ATTN_TRACE into
 tools/_trace/ (git-ignored, travels with gpurun); `python tools/attn_trace.py [B]` runs the encoder self-attention
-shape on the GPU and prints, per traced event, the mean clock64() delta to the previous event over the traced CTAs
-(thread 0 = MMA issuer, and the first lane of the last warp).
+shape on the GPU and prints, per traced event, the mean clock64() delta to the previous event over the first 64 CTAs
+(thread 0 = a softmax / compute thread, and the issuer thread).
 """
 import ctypes
 import os
@@ -14,23 +14,20 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 TRACE_LIB = os.path.join(ROOT, "tools", "_trace", "libpvqa_trace.so")
 
-FWD_EV = {0: "start", 1: "prologue done", 30: "epilogue stores issued", 31: "end"}
-for t in range(4):
-    FWD_EV.update({2 + 6 * t: f"t{t} S ready", 3 + 6 * t: f"t{t} pass A done", 4 + 6 * t: f"t{t} max exchanged",
-                   5 + 6 * t: f"t{t} pass B done", 6 + 6 * t: f"t{t} O_j ready", 7 + 6 * t: f"t{t} tile end"})
-# second-generation forward (PVQA_ATTN_FWD_V2=1): softmax thread 0 | issuer thread
-FWD2_EV = {0: "start", 1: "prologue done", 29: "last PV done", 30: "epilogue stores issued", 31: "end"}
-for t in range(5):
-    FWD2_EV.update({2 + 5 * t: f"t{t} S ready | S(t+1) issued", 3 + 5 * t: f"t{t} S in registers | PV issued",
-                    4 + 5 * t: f"t{t} bias + max done", 5 + 5 * t: f"t{t} O(t-1) complete, rescaled",
-                    6 + 5 * t: f"t{t} P stored"})
-BWD_EV = {0: "start", 1: "prologue done", 25: "last GEMMs done", 26: "last dQ staged", 27: "dK/dV stored", 28: "bins synced",
-          30: "epilogue stores issued", 31: "end"}
-for t in range(5):
-    # thread 0 (compute): S/dP ready -> P/dS stored -> dQ(t-1) staged + arrived;  issuer: barrier passed -> all MMAs
-    # issued -> ring refilled
-    BWD_EV.update({2 + 5 * t: f"t{t} S,dP ready | P/dS full", 3 + 5 * t: f"t{t} P,dS stored | MMAs issued",
-                   4 + 5 * t: f"t{t} dQ(t-1) staged | refilled"})
+# event numbering of the persistent kernels (csrc/attn_fwd.cuh, attn_bwd.cuh): softmax / compute thread 0 | issuer
+FWD_EV = {0: "start", 1: "prologue done", 26: "item 0: tiles done | -", 27: "item 0: last PV done | -",
+          28: "item 0 stored | -", 29: "item 1 stored | -", 30: "all items done", 31: "end"}
+for t in range(3):
+    FWD_EV.update({2 + 6 * t: f"t{t} tile start | turn start", 3 + 6 * t: f"t{t} S ready | S(t+1) issued",
+                   4 + 6 * t: f"t{t} S in registers | V landed", 5 + 6 * t: f"t{t} bias + max done | P ready",
+                   6 + 6 * t: f"t{t} O(t-1) done (rescaled) | PV issued", 7 + 6 * t: f"t{t} P stored | loads issued"})
+BWD_EV = {0: "start", 1: "prologue done", 24: "item 0: tiles done | -", 25: "item 0: last GEMMs done | -",
+          26: "item 0: last dQ staged | -", 27: "item 0: dK/dV stored | -", 28: "item 0 synced | -",
+          29: "item 1 done | -", 30: "all items done", 31: "end"}
+for t in range(3):
+    BWD_EV.update({2 + 6 * t: f"t{t} tile start | turn start", 3 + 6 * t: f"t{t} S,dP ready | barrier 1 passed",
+                   4 + 6 * t: f"t{t} math done | S,dP(t+1) issued", 5 + 6 * t: f"t{t} GEMMs(t-1) done | barrier 3 passed",
+                   6 + 6 * t: f"t{t} P,dS stored | GEMMs issued", 7 + 6 * t: f"t{t} dQ(t-1) staged | refilled"})
 
 
 def build():
@@ -88,9 +85,7 @@ def main():
         o, lse = ops.attention_fwd_raw(q, k, v, 1.0, rb, ka, False, drop)
         torch.cuda.synchronize()
         lib.pvqa_debug_attn_trace(ctypes.addressof(buf), 1)
-        new = ops.ATTN_FWD_V2 or ops.ATTN_FWD_V3          # v2 and v3 share the event numbering
-        report(list(buf), FWD2_EV if new else FWD_EV,
-               f"fwd{' v3' if ops.ATTN_FWD_V3 else ' v2' if ops.ATTN_FWD_V2 else ''} enc_self B={B} p={p}")
+        report(list(buf), FWD_EV, f"fwd enc_self B={B} p={p}")
         dkv = torch.empty_like(kv)
         for _ in range(2):
             ops.attention_bwd_raw(q, k, v, o, go, lse, 1.0, rb, ka, False, dkv[:, :, 0], dkv[:, :, 1], True, drop)
