@@ -51,10 +51,13 @@ def err(a, b):
     return float((a.float() - b.float()).norm() / (b.float().norm() + 1e-12))
 
 
-def case(B, H, Sq, Sk, rel, causal, tag, masked=True, bwd=True):
+def case(B, H, Sq, Sk, rel, causal, tag, masked=True, bwd=True, grow=False):
     g = torch.Generator().manual_seed(Sq * 7 + Sk + B)
     q = (torch.randn(B, Sq, H, 64, generator=g) * 0.4).bfloat16().to(dev)
-    k = (torch.randn(B, Sk, H, 64, generator=g) * 0.4).bfloat16().to(dev)
+    k = torch.randn(B, Sk, H, 64, generator=g) * 0.4
+    if grow:        # logits that grow from key tile to key tile: every tile moves the running reference (redo path)
+        k = k * (1.0 + 4.0 * (torch.arange(Sk) // 64).float())[None, :, None, None]
+    k = k.bfloat16().to(dev)
     v = torch.randn(B, Sk, H, 64, generator=g).bfloat16().to(dev)
     rb = torch.randn(H, Sq + Sk - 1, generator=g).to(dev) if rel else None
     ka = None
@@ -105,6 +108,8 @@ if what in ("parity", "all"):
     case(1, 2, 200, 200, True, True, "F 200 rel causal")
     case(40, 12, 327, 327, True, False, "G 40x12x327 persistent (bias restage)")
     case(3, 1, 1, 5, True, False, "H tiny 1x5")
+    case(2, 2, 327, 327, True, False, "J 327 rel, growing logits (reference moves every tile)", grow=True)
+    case(2, 2, 200, 200, False, False, "K 200 no mask", masked=False)
     dropout_case(2, 2, 327, 0.1, "I")
     log("parity stages finished")
 

@@ -1,0 +1,9 @@
+#!/usr/bin/env bash
+set -u
+mkdir -p gpurun_out
+rm -f gpurun_out/attn_probe.log
+timeout 120 python tools/attn_probe.py all > gpurun_out/probe_all.out 2>&1; echo "probe rc=$?"
+grep -E "done|median" gpurun_out/attn_probe.log | cut -c1-200
+timeout 300 python -m pytest tests/test_attn_gpu.py -m gpu -q -x > gpurun_out/tests_attn.log 2>&1; echo "tests_attn rc=$?"; tail -n 5 gpurun_out/tests_attn.log
+timeout 200 bash -c "python tools/attn_trace.py build && timeout 60 python tools/attn_trace.py 64" > gpurun_out/attn_trace.log 2>&1; echo "trace rc=$?"
+grep -A25 "== fwd enc_self B=64 p=0.1" gpurun_out/attn_trace.log
