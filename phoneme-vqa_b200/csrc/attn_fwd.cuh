@@ -36,8 +36,8 @@ constexpr int kFTileBytes = kBN * kD * 2;                  // 16 KB
 constexpr int kFOffQ = 0;                                  // 2 x 16 KB  Q of item n in buffer n & 1
 constexpr int kFOffK = kFOffQ + 2 * kBM * kD * 2;          // 3 x 16 KB
 constexpr int kFOffV = kFOffK + kFStages * kFTileBytes;    // 3 x 16 KB
-constexpr int kFOffP = kFOffV + kFStages * kFTileBytes;    // 2 x 32 KB: P_g in buffer g & 1, two [128][64] K-major SW128 sub-tiles
-constexpr int kFOffBar = kFOffP + 2 * kBM * kBN * 2;       // 192 KB
+constexpr int kFOffP = kFOffV + kFStages * kFTileBytes;    // 32 KB: P as two [128][64] K-major SW128 sub-tiles
+constexpr int kFOffBar = kFOffP + kBM * kBN * 2;           // 160 KB
 constexpr int kFOffXchg = kFOffBar + 192;                  // [2 tile parities][4 quarters][128 rows] + [4][128] floats
 constexpr int kFOffFloats = kFOffXchg + 3 * 4 * kBM * 4;   // kadd[2][n_kpad], relc[2][cs], scp table[32]
 
@@ -279,6 +279,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       };
       const uint32_t idesc_pv = tc05::idesc_bf16(kBM, kD, 0, 1);      // B = V is MN-major (d contiguous)
       const uint32_t smem0 = tc05::smem_u32(smem);
+      const uint64_t p_desc = tc05::desc_sw128_k(smem0 + kFOffP);
       // The loads of a tile go out in two parts, each at the first point where the buffer it overwrites is known free
       // WITHOUT a wait of its own (every mbarrier wait costs ~100 cycles even when it succeeds at once):
       //   K_{g+2} -> slot of K_{g-1}: S_{g-1} completed before the softmax threads arrived on bar_p(g-1) (seen last turn)
@@ -353,7 +354,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc05::tc_fence_after_sync();
         if (g < 3) PVQA_TRACEF(5 + 6 * g);
         const uint64_t vd = tc05::desc_sw128_k(smem0 + kFOffV + (g % kFStages) * kFTileBytes);
-        const uint64_t p_desc = tc05::desc_sw128_k(smem0 + kFOffP + (g & 1) * (kBM * kBN * 2));
         const int ksteps = tile_width(c_pv.t) / 16;
         const uint32_t acc0 = c_pv.t > 0 ? 1u : 0u;
         if (tc05::elect_one()) {
@@ -478,175 +478,113 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tc05::tmem_ld_32x32(tmem_row + (g & 1) * kBN + qd * nc, *reinterpret_cast<uint32_t(*)[32]>(s));
           if (DROP) {
             // the dropout bits of this thread's columns (ONE 32-key block, starting at bit jb & 31 of its keep word) are
-            // pure integer work: done here it hides under the TMEM load
+            // pure integer work: done here it hides under the TMEM load and the latency-bound bias phase instead of
+            // competing with the MUFU-bound exponential phase
             const uint32_t keep = keep_bits32(p.drop, drop_ctr + (uint32_t)(jb >> 5));
             keep_shifted(keep >> (jb & 31), kw);
           }
           tc05::tmem_ld_wait();
         }
-        if (tr) PVQA_TRACEF(4 + 6 * g);
-        const float4* ka4 = reinterpret_cast<const float4*>(kadd + jb);
-        const float2* rl2 = reinterpret_cast<const float2*>(relc + jb);
-        // biased scores (exp2 domain) of the 8 columns of chunk c8, in place; returns their maximum
-        auto bias_chunk = [&](int c8) {
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const float4 ka = ka4[c8 * 2 + q];
-            float2 b0 = make_float2(ka.x, ka.y), b1 = make_float2(ka.z, ka.w);
-            if (HAS_REL) {
-              b0 = add2(b0, rl2[c8 * 4 + 2 * q]);
-              b1 = add2(b1, rl2[c8 * 4 + 2 * q + 1]);
-            }
-            s[c8 * 4 + 2 * q] = fma2(s[c8 * 4 + 2 * q], make_float2(p.sl2, p.sl2), b0);
-            s[c8 * 4 + 2 * q + 1] = fma2(s[c8 * 4 + 2 * q + 1], make_float2(p.sl2, p.sl2), b1);
-          }
-          if (SCP) {
-            const int jj = jb + c8 * 8 - p.scp_q0;                  // block-relative; 8-column groups are in or out
-            if (scp_row != nullptr && jj >= 0 && jj < p.scp_L) {
-              const uint2 u = __ldg(reinterpret_cast<const uint2*>(scp_row + jj));
-#pragma unroll
-              for (int k = 0; k < 8; ++k) sf[c8 * 8 + k] += s_scp[((k < 4 ? u.x : u.y) >> (8 * (k & 3))) & 31u];
-            }
-          }
-          if (CAUSAL) {
-            if (jb + c8 * 8 + 7 > i0) {                             // chunk may reach above the diagonal (warp-uniform)
-#pragma unroll
-              for (int x = 0; x < 8; ++x)
-                if (jb + c8 * 8 + x > i) sf[c8 * 8 + x] = -INFINITY;
-            }
-          }
-          float mx = fmaxf(sf[c8 * 8], sf[c8 * 8 + 1]);
-#pragma unroll
-          for (int x = 2; x < 8; x += 2) mx = fmaxf(fmaxf(mx, sf[c8 * 8 + x]), sf[c8 * 8 + x + 1]);
-          return mx;
-        };
-        // this thread's first 16-byte chunk (8 keys) of the P row, 128-byte swizzle folded in: chunk c8 of the thread
-        // lives at pst ^ (c8 << 4)  (the thread's chunks never cross a 64-key sub-tile or carry in the chunk index).
-        // P_g goes to buffer g & 1: its previous reader P V of tile g-2 was issued before S_g, which has completed.
-        const int ch0 = (qd * nc) >> 3;
-        const uint32_t pst = p_base + (uint32_t)((g & 1) * (kBM * kBN * 2)) + (uint32_t)((ch0 >> 3) * (kBM * 128)) +
-                             (uint32_t)((((ch0 & 7) ^ (rowl & 7))) << 4);
-        // p = exp2(s - m) (1/keep folded in) of chunk c8: row sum, dropout on the packed words, bf16 P -> smem
-        auto exp_chunk = [&](int c8, float2 nm, float2& sum2) {
-          uint32_t pw[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float2 e = add2(s[c8 * 4 + q], nm);
-            e.x = fast_exp2(e.x);
-            e.y = fast_exp2(e.y);
-            sum2 = add2(sum2, e);
-            pw[q] = f32x2_to_bf16x2(e.x, e.y);
-            if (DROP) pw[q] &= prmt(kw[7 - 2 * q], kw[6 - 2 * q], pair_sel(c8));
-          }
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                       :: "r"(pst ^ (uint32_t)(c8 << 4)), "r"(pw[0]), "r"(pw[1]), "r"(pw[2]), "r"(pw[3]) : "memory");
-        };
-        const float m_shift = DROP ? p.drop.m_shift : 0.f;
-        float* xbuf = s_x + (g & 1) * (4 * kBM);
         // Lazy rescaling: the running reference m_run moves only when a row's maximum exceeds it by more than 8 (a
         // factor 256 in the exp2 domain), so p = exp2(s - m_run) stays below 256 — exact enough in bf16, far from any
         // overflow in the fp32 row sum — and O in TMEM is touched only on those rare tiles, not on every new maximum.
-        // From an item's second tile on (every row of the warp has a finite reference) that makes the softmax ONE pass:
-        // bias, exponentials against the running reference and P stores run chunk by chunk with nothing but this
-        // thread's own data — the MUFU work of one chunk overlaps the ALU work of the next — and the row-max exchange
-        // afterwards only has to confirm that no row outgrew its reference.  If one did (rare), the tile is redone.
-        const bool speculative = t > 0 && __all_sync(0xffffffffu, m_run != -INFINITY) && !rows_dead;
         float m_new = m_run;
-        float2 sum2 = make_float2(0.f, 0.f);
-        if (speculative) {
-          const float m_sub = m_run - m_shift;
-          const float2 nm = make_float2(-m_sub, -m_sub);
+        bool grow = false;
+        if (tr) PVQA_TRACEF(4 + 6 * g);
+        if (!rows_dead) {
+          // ---- biased scores in the exp2 domain and the max over this thread's columns ----
+          const float4* ka4 = reinterpret_cast<const float4*>(kadd + jb);
+          const float2* rl2 = reinterpret_cast<const float2*>(relc + jb);
           float mx = -INFINITY;
 #pragma unroll
           for (int c8 = 0; c8 < 4; ++c8) {
             if (c8 * 8 >= nc) break;
-            mx = fmaxf(mx, bias_chunk(c8));
-            exp_chunk(c8, nm, sum2);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const float4 ka = ka4[c8 * 2 + q];
+              float2 b0 = make_float2(ka.x, ka.y), b1 = make_float2(ka.z, ka.w);
+              if (HAS_REL) {
+                b0 = add2(b0, rl2[c8 * 4 + 2 * q]);
+                b1 = add2(b1, rl2[c8 * 4 + 2 * q + 1]);
+              }
+              s[c8 * 4 + 2 * q] = fma2(s[c8 * 4 + 2 * q], make_float2(p.sl2, p.sl2), b0);
+              s[c8 * 4 + 2 * q + 1] = fma2(s[c8 * 4 + 2 * q + 1], make_float2(p.sl2, p.sl2), b1);
+            }
+            if (SCP) {
+              const int jj = jb + c8 * 8 - p.scp_q0;                // block-relative; 8-column groups are in or out
+              if (scp_row != nullptr && jj >= 0 && jj < p.scp_L) {
+                const uint2 u = __ldg(reinterpret_cast<const uint2*>(scp_row + jj));
+#pragma unroll
+                for (int k = 0; k < 8; ++k) sf[c8 * 8 + k] += s_scp[((k < 4 ? u.x : u.y) >> (8 * (k & 3))) & 31u];
+              }
+            }
+            if (CAUSAL) {
+              if (jb + c8 * 8 + 7 > i0) {                           // chunk may reach above the diagonal (warp-uniform)
+#pragma unroll
+                for (int x = 0; x < 8; ++x)
+                  if (jb + c8 * 8 + x > i) sf[c8 * 8 + x] = -INFINITY;
+              }
+            }
+#pragma unroll
+            for (int x = 0; x < 8; x += 2) mx = fmaxf(fmaxf(mx, sf[c8 * 8 + x]), sf[c8 * 8 + x + 1]);
           }
+          // ---- row max: exchange with the three threads that own the other quarters of this row (buffers alternate
+          //      by tile parity, so the write of tile g+2 cannot overtake a partner's read of tile g) ----
+          float* xbuf = s_x + (g & 1) * (4 * kBM);
           xbuf[qd * kBM + rowl] = mx;
           quad_sync(quad);
           mx = fmaxf(fmaxf(xbuf[rowl], xbuf[kBM + rowl]), fmaxf(xbuf[2 * kBM + rowl], xbuf[3 * kBM + rowl]));
-          const bool grow = mx > m_run + 8.f;
-          if (tr) PVQA_TRACEF(5 + 6 * g);
-          if (__any_sync(0xffffffffu, grow)) {
-            // a row outgrew its reference: O += P_{g-1} V_{g-1} must have completed before O is rescaled, then this
-            // thread's part of the tile is recomputed against the new reference (rows that did not grow: same values)
-            tc05::mbar_wait(bar_o, (g - 1) & 1);
-            tc05::tc_fence_after_sync();
-            if (grow) m_new = mx;
-            const float alpha = grow ? fast_exp2(m_run - m_new) : 1.f;
-            uint32_t r[16];                                   // this thread's 16 of the 64 output columns
-            tc05::tmem_ld_32x16(tmem_row + 2 * kBN + qd * 16, r);
-            tc05::tmem_ld_wait();
+          grow = mx > m_run + 8.f;                // also true for the first live tile (m_run = -inf)
+          if (grow) m_new = mx;
+        }
+        if (tr) PVQA_TRACEF(5 + 6 * g);
+        if (g > 0) {
+          // O += P_{g-1} V_{g-1} has completed (it was issued a tile ago): the P buffer may be overwritten, and O may be
+          // read out (first tile of an item: the previous item's epilogue) or rescaled
+          tc05::mbar_wait(bar_o, (g - 1) & 1);
+          tc05::tc_fence_after_sync();
+        }
+        if (t == 0) {
+          if (n > 0) epilogue(prv, m_prev, l_prev);
+        } else if (!rows_dead && __any_sync(0xffffffffu, grow)) {
+          const float alpha = grow ? fast_exp2(m_run - m_new) : 1.f;          // exp2(-inf) = 0 for a first live tile
+          uint32_t r[16];                                     // this thread's 16 of the 64 output columns
+          tc05::tmem_ld_32x16(tmem_row + 2 * kBN + qd * 16, r);
+          tc05::tmem_ld_wait();
 #pragma unroll
-            for (int x = 0; x < 16; ++x) r[x] = __float_as_uint(__uint_as_float(r[x]) * alpha);
-            tc05::tmem_st_32x16(tmem_row + 2 * kBN + qd * 16, r);
-            tc05::tmem_st_wait();
-            l_run *= alpha;
-            const float m_sub2 = m_new - m_shift;
-            const float2 nm2 = make_float2(-m_sub2, -m_sub2);
-            sum2 = make_float2(0.f, 0.f);
+          for (int x = 0; x < 16; ++x) r[x] = __float_as_uint(__uint_as_float(r[x]) * alpha);
+          tc05::tmem_st_32x16(tmem_row + 2 * kBN + qd * 16, r);
+          tc05::tmem_st_wait();
+          l_run *= alpha;
+        }
+        if (tr) PVQA_TRACEF(6 + 6 * g);
+        if (!rows_dead) {
+          // ---- p = exp2(s - m) (1/keep folded in), row sum, dropout on the packed words, bf16 P -> smem ----
+          const float m_sub = ((m_new == -INFINITY) ? 0.f : m_new) - (DROP ? p.drop.m_shift : 0.f);
+          const float2 nm = make_float2(-m_sub, -m_sub);
+          float2 sum2 = make_float2(0.f, 0.f);
+          // this thread's first 16-byte chunk (8 keys) of the P row, 128-byte swizzle folded in: chunk c8 of the thread
+          // lives at pst ^ (c8 << 4)  (the thread's chunks never cross a 64-key sub-tile or carry in the chunk index)
+          const int ch0 = (qd * nc) >> 3;
+          const uint32_t pst = p_base + (uint32_t)((ch0 >> 3) * (kBM * 128)) + (uint32_t)((((ch0 & 7) ^ (rowl & 7))) << 4);
 #pragma unroll
-            for (int c8 = 0; c8 < 4; ++c8) {
-              if (c8 * 8 >= nc) break;
-              exp_chunk(c8, nm2, sum2);
+          for (int c8 = 0; c8 < 4; ++c8) {                       // 8 keys = one 16-byte chunk of the P row
+            if (c8 * 8 >= nc) break;
+            uint32_t pw[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              float2 e = add2(s[c8 * 4 + q], nm);
+              e.x = fast_exp2(e.x);
+              e.y = fast_exp2(e.y);
+              sum2 = add2(sum2, e);
+              pw[q] = f32x2_to_bf16x2(e.x, e.y);
+              if (DROP) pw[q] &= prmt(kw[7 - 2 * q], kw[6 - 2 * q], pair_sel(c8));
             }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                         :: "r"(pst ^ (uint32_t)(c8 << 4)), "r"(pw[0]), "r"(pw[1]), "r"(pw[2]), "r"(pw[3]) : "memory");
           }
-          if (tr) PVQA_TRACEF(6 + 6 * g);
           l_run += sum2.x + sum2.y;
           m_run = m_new;
-        } else {
-          // two passes: an item's first tile (no reference yet), rows whose keys were all masked so far, dead rows
-          bool grow = false;
-          if (!rows_dead) {
-            float mx = -INFINITY;
-#pragma unroll
-            for (int c8 = 0; c8 < 4; ++c8) {
-              if (c8 * 8 >= nc) break;
-              mx = fmaxf(mx, bias_chunk(c8));
-            }
-            // row max: exchange with the three threads that own the other quarters of this row (buffers alternate by
-            // tile parity, so the write of tile g+2 cannot overtake a partner's read of tile g)
-            xbuf[qd * kBM + rowl] = mx;
-            quad_sync(quad);
-            mx = fmaxf(fmaxf(xbuf[rowl], xbuf[kBM + rowl]), fmaxf(xbuf[2 * kBM + rowl], xbuf[3 * kBM + rowl]));
-            grow = mx > m_run + 8.f;                // also true for the first live tile (m_run = -inf)
-            if (grow) m_new = mx;
-          }
-          if (tr) PVQA_TRACEF(5 + 6 * g);
-          if (t == 0) {
-            if (n > 0) {
-              // the previous item's O is complete once its last P V product is: read it out (its epilogue) before this
-              // tile's product overwrites it
-              tc05::mbar_wait(bar_o, (g - 1) & 1);
-              tc05::tc_fence_after_sync();
-              epilogue(prv, m_prev, l_prev);
-            }
-          } else if (!rows_dead && __any_sync(0xffffffffu, grow)) {
-            tc05::mbar_wait(bar_o, (g - 1) & 1);
-            tc05::tc_fence_after_sync();
-            const float alpha = grow ? fast_exp2(m_run - m_new) : 1.f;          // exp2(-inf) = 0 for a first live tile
-            uint32_t r[16];
-            tc05::tmem_ld_32x16(tmem_row + 2 * kBN + qd * 16, r);
-            tc05::tmem_ld_wait();
-#pragma unroll
-            for (int x = 0; x < 16; ++x) r[x] = __float_as_uint(__uint_as_float(r[x]) * alpha);
-            tc05::tmem_st_32x16(tmem_row + 2 * kBN + qd * 16, r);
-            tc05::tmem_st_wait();
-            l_run *= alpha;
-          }
-          if (tr) PVQA_TRACEF(6 + 6 * g);
-          if (!rows_dead) {
-            const float m_sub = ((m_new == -INFINITY) ? 0.f : m_new) - m_shift;
-            const float2 nm = make_float2(-m_sub, -m_sub);
-#pragma unroll
-            for (int c8 = 0; c8 < 4; ++c8) {
-              if (c8 * 8 >= nc) break;
-              exp_chunk(c8, nm, sum2);
-            }
-            l_run += sum2.x + sum2.y;
-            m_run = m_new;
-          }
         }
         if (stage_next && t + 1 == nt) {
           float* dst = s_kadd + ((n + 1) & 1) * n_kpad;
@@ -656,11 +594,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int j = tid + 2 * kFSoftmaxThreads; j < n_kpad; j += kFSoftmaxThreads)     // Sk > 1024 only
             dst[j] = (j < p.Sk) ? (p.key_add ? p.key_add[(long long)b_next * p.Sk + j] * kLog2e : 0.f) : -INFINITY;
         }
-        // Back-pressure: nobody arrives on bar_p(g) before O += P_{g-1} V_{g-1} has completed.  The issuer issues that
-        // product only after it has SEEN phase g-1 of bar_p, so phase g cannot complete behind its back (mbarrier waits
-        // tell phases apart by parity only), and seeing phase g tells it that V_{g-1}'s slot is free.  The product was
-        // issued a whole tile ago: the wait itself never blocks.
-        if (g > 0) tc05::mbar_wait(bar_o, (g - 1) & 1);
         tc05::fence_proxy_async_smem();
         tc05::tc_fence_before_sync();
         tc05::mbar_arrive(bar_p);
