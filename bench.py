@@ -348,12 +348,21 @@ def run_b200_arm(args):
             line["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
         _emit(line)
     if world > 1:
-        # Every collective of the run has completed (the max-over-ranks reductions above were the last ones).
-        # Tearing NCCL down after CUDA-graph-captured collectives was observed to hang at exit on 8 ranks,
-        # so leave without the destroy/barrier handshake.
+        # Orderly teardown: the captured graph (which holds NCCL kernels) goes first, then the communicator.  A watchdog
+        # keeps the driver's scaling run from ever hanging at exit should the handshake stall (observed once in round 1
+        # when the communicator was destroyed underneath a live graph).
+        import gc
+        import threading
+        watchdog = threading.Timer(60.0, lambda: os._exit(0))
+        watchdog.daemon = True
+        watchdog.start()
+        trainer.close()
+        del trainer, reducer
+        gc.collect()
         torch.cuda.synchronize()
-        sys.stderr.flush()
-        os._exit(0)
+        dist.barrier()
+        dist.destroy_process_group()
+        watchdog.cancel()
 
 
 def _measured_traffic():

@@ -89,6 +89,8 @@ class _LinearLP(torch.autograd.Function):
         ctx.n_w = n_masters
         ctx.has_bias = b_lp is not None
         ctx.rows = [m.shape[0] for m in masters[:n_masters]]
+        import weakref
+        ctx.slot_of = weakref.ref(masters[0]) if n_masters == 1 else None
         return F.linear(x, w_lp, b_lp)
 
     @staticmethod
@@ -97,10 +99,20 @@ class _LinearLP(torch.autograd.Function):
         dy2 = dy.reshape(-1, dy.shape[-1])
         x2 = x.reshape(-1, x.shape[-1])
         dx = (dy2 @ w_lp).view(x.shape) if ctx.needs_input_grad[0] else None
-        dW = torch.mm(dy2.t(), x2, out_dtype=torch.float32)
+        # data-parallel runs: a single-master weight gradient is written straight into its all-reduce bucket slot
+        # (parallel.grad_slot) and that view is returned as the gradient — autograd adopts it, the reducer's hook sees
+        # its own storage and skips the copy
+        slot = None
+        if ctx.n_w == 1 and ctx.slot_of is not None:
+            from .parallel import grad_slot
+            slot = grad_slot(ctx.slot_of())
+        if slot is not None:
+            dW = torch.mm(dy2.t(), x2, out_dtype=torch.float32, out=slot)
+        else:
+            dW = torch.mm(dy2.t(), x2, out_dtype=torch.float32)
         grads, off = [], 0
         for r in ctx.rows:
-            grads.append(dW[off:off + r])
+            grads.append(dW[off:off + r] if len(ctx.rows) > 1 else dW)
             off += r
         if ctx.has_bias:
             db = ops.col_sum(dy2)
@@ -389,39 +401,25 @@ class T5DenseActDense(nn.Module):
         self.wo = nn.Linear(config.d_ff, config.d_model, bias=False)
         self.dropout = nn.Dropout(config.dropout_rate)
         self.act_name = config.dense_act_fn
+        if self.act_name != "relu":
+            # VietAI/vit5-base / -large (every YAML of the reference) are ReLU T5s; there is no PyTorch fall-through:
+            # unsupported shapes are errors
+            raise NotImplementedError(f"T5 feed-forward activation {self.act_name!r}: the B200 path implements the "
+                                      "ReLU feed-forward of the reference's backbones only")
 
     def forward(self, x):
         h = _lin(x, self.wi.weight)
-        if self.act_name == "relu":
-            h = ops.relu_dropout(h, self.dropout.p, self.training)
-        else:
-            h = F.gelu(h, approximate="tanh" if self.act_name == "gelu_new" else "none")
-            h = F.dropout(h, self.dropout.p, self.training)
-        return _lin(h, self.wo.weight)
-
-
-class T5DenseGatedActDense(nn.Module):
-    def __init__(self, config):
-        super().__init__()
-        self.wi_0 = nn.Linear(config.d_model, config.d_ff, bias=False)
-        self.wi_1 = nn.Linear(config.d_model, config.d_ff, bias=False)
-        self.wo = nn.Linear(config.d_ff, config.d_model, bias=False)
-        self.dropout = nn.Dropout(config.dropout_rate)
-        self.act_name = config.dense_act_fn
-
-    def forward(self, x):
-        g = _lin(x, self.wi_0.weight)
-        g = F.relu(g) if self.act_name == "relu" else F.gelu(g, approximate="tanh" if self.act_name == "gelu_new" else "none")
-        h = g * _lin(x, self.wi_1.weight)
-        h = F.dropout(h, self.dropout.p, self.training)
+        h = ops.relu_dropout(h, self.dropout.p, self.training)
         return _lin(h, self.wo.weight)
 
 
 class T5LayerFF(nn.Module):
     def __init__(self, config):
         super().__init__()
-        gated = getattr(config, "is_gated_act", False)
-        self.DenseReluDense = T5DenseGatedActDense(config) if gated else T5DenseActDense(config)
+        if getattr(config, "is_gated_act", False):
+            raise NotImplementedError("gated T5 feed-forward (T5 v1.1): not used by the reference's backbones, not "
+                                      "implemented on the B200 path (no PyTorch fall-through)")
+        self.DenseReluDense = T5DenseActDense(config)
         self.layer_norm = T5LayerNorm(config.d_model, eps=config.layer_norm_epsilon)
         self.dropout = nn.Dropout(config.dropout_rate)
 
@@ -460,10 +458,6 @@ def _t5_init(module, config):
             nn.init.constant_(m.weight, factor * 1.0)
         elif isinstance(m, T5DenseActDense):
             nn.init.normal_(m.wi.weight, mean=0.0, std=factor * (d_model ** -0.5))
-            nn.init.normal_(m.wo.weight, mean=0.0, std=factor * (d_ff ** -0.5))
-        elif isinstance(m, T5DenseGatedActDense):
-            nn.init.normal_(m.wi_0.weight, mean=0.0, std=factor * (d_model ** -0.5))
-            nn.init.normal_(m.wi_1.weight, mean=0.0, std=factor * (d_model ** -0.5))
             nn.init.normal_(m.wo.weight, mean=0.0, std=factor * (d_ff ** -0.5))
         elif isinstance(m, T5Attention):
             nn.init.normal_(m.q.weight, mean=0.0, std=factor * ((d_model * d_kv) ** -0.5))
@@ -511,10 +505,10 @@ class T5Stack(nn.Module):
         mem = None if memory is None else memory.to(compute_dtype)
         mem_key_add = self.key_add_from_mask(memory_mask) if memory is not None else None
         d = hidden.shape[-1]
-        if len(self.block) == 0 or d % 8 != 0 or d > 1024:
-            for blk in self.block:
-                hidden = blk(hidden, rel_bias, key_add, compute_dtype, memory=mem, memory_key_add=mem_key_add,
-                             causal=self.is_decoder, scp=scp)
+        if d % 8 != 0 or d > 1024:
+            raise ValueError(f"d_model = {d}: the fused norm kernels keep a row in registers (d % 8 == 0, d <= 1024); "
+                             "there is no PyTorch fall-through")
+        if len(self.block) == 0:
             hidden = self.final_layer_norm(hidden, out_dtype=torch.float32)
             return F.dropout(hidden, self.dropout.p, self.training)
         # Pre-norm chain: every `hidden + dropout(sublayer)` is fused with the T5LayerNorm that opens the NEXT
@@ -723,16 +717,14 @@ class BaseDecoder(nn.Module):
         B, _, d = x.shape
         t = cache.len
         assert t < cache.max_len, "decoder cache is full"
-        fused = d % 8 == 0 and d <= 1024
+        if d % 8 != 0 or d > 1024:
+            raise ValueError(f"d_model = {d}: the fused norm kernels need d % 8 == 0 and d <= 1024")
         lp = compute_dtype == torch.bfloat16
 
         def tail(x, upd, norm):
             """norm(x + upd) -> (fp32 stream, compute-dtype copy): the same fused launch the full layer pass uses"""
-            if fused:
-                y, y_lp = ops.add_dropout_layer_norm(x, upd, norm.weight, norm.bias, norm.eps, 0.0, False, want_lp=lp)
-                return y, (y_lp if lp else y)
-            y = F.layer_norm(x + upd.float(), (d,), norm.weight, norm.bias, norm.eps)
-            return y, y.to(compute_dtype)
+            y, y_lp = ops.add_dropout_layer_norm(x, upd, norm.weight, norm.bias, norm.eps, 0.0, False, want_lp=lp)
+            return y, (y_lp if lp else y)
 
         xc = x.to(compute_dtype)
         for li, layer in enumerate(self.decoder.layers):

@@ -3,10 +3,13 @@ with backward (the only collective on the path — SURVEY.md §8e; the reference
 
 `GradReducer` is a thin, dependency-free DDP: parameters are grouped in reverse registration
 order (heads -> decoder -> encoder -> embeddings, the order gradients become ready) into flat
-fp32 buckets of ~`bucket_mb`; a post-accumulate-grad hook copies each gradient into its bucket
-slot and, when the bucket is full, launches an async all-reduce (NCCL runs it on its own
-stream, so it overlaps the remaining backward); `finish()` waits, and leaves `p.grad` as views
-into the averaged buckets (no copy back).  The trainable set can change between epochs (encoder
+fp32 buckets of ~`bucket_mb`; when the last gradient of a bucket is ready an async all-reduce
+is launched (NCCL runs it on its own stream, so it overlaps the remaining backward); `finish()`
+waits, and leaves `p.grad` as views into the averaged buckets (no copy back).
+Per-step passes over the 600 MB of gradients that round 1 paid and this version does not:
+  * the weight-gradient GEMMs of the linears write straight INTO their bucket slot
+    (`grad_slot()`, used by modules._LinearLP) — no gradient -> bucket `copy_` for ~95 % of the bytes;
+  * the average is taken by the collective itself (`ReduceOp.AVG` on NCCL) — no `div_` pass.  The trainable set can change between epochs (encoder
 freeze toggle, core/executor/PhonemeLaTr_Executor.py:152-159): `rebuild()` re-buckets.
 Works with any torch.distributed backend (NCCL on GPUs; gloo in the CPU tests).
 """
@@ -14,6 +17,20 @@ from __future__ import annotations
 
 import torch
 import torch.distributed as dist
+
+_ACTIVE = None          # the reducer whose bucket slots gradient producers may write into directly
+
+
+def grad_slot(param):
+    """The bucket view a producer may write `param`'s gradient into (fp32, param's shape), or None.  A producer that
+    uses it returns the view itself as the gradient: autograd then adopts it as `param.grad` without a copy."""
+    r = _ACTIVE
+    if r is None or r.world == 1:
+        return None
+    loc = r._slot.get(id(param))
+    if loc is None:
+        return None
+    return r._views[loc[0]][loc[1]]
 
 
 class GradReducer:
@@ -23,8 +40,12 @@ class GradReducer:
         self.pg = process_group
         self.average = average
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        # NCCL averages inside the collective; gloo (CPU tests) has no AVG: divide, then sum
+        self._native_avg = bool(average and dist.is_initialized() and dist.get_backend(process_group) == "nccl")
         self._hooks = []
         self.rebuild()
+        global _ACTIVE
+        _ACTIVE = self
 
     # -- setup -------------------------------------------------------------------
     def broadcast_parameters(self, src: int = 0):
@@ -89,7 +110,9 @@ class GradReducer:
     # -- per-step ------------------------------------------------------------------
     def _on_grad(self, p):
         bi, pi = self._slot[id(p)]
-        self._views[bi][pi].copy_(p.grad)
+        view = self._views[bi][pi]
+        if p.grad.data_ptr() != view.data_ptr():        # (a producer that wrote into the slot already is a no-op here)
+            view.copy_(p.grad)
         p.grad = None
         self._filled.add((bi, pi))
         self._pending[bi] -= 1
@@ -98,6 +121,9 @@ class GradReducer:
 
     def _launch(self, bi):
         flat = self._flat[bi]
+        if self._native_avg:
+            self._works[bi] = dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.pg, async_op=True)
+            return
         if self.average:
             flat.div_(self.world)
         self._works[bi] = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)

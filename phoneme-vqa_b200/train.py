@@ -149,6 +149,11 @@ class TrainStep:
         self.lr_t.fill_(self._lr_now())
         return self.static_loss
 
+    def close(self):
+        """Release the captured graph and its static buffers.  Call before dist.destroy_process_group(): the graph
+        holds the captured NCCL kernels, and tearing the communicator down underneath it is what hung at exit."""
+        self.graph, self.static, self.static_loss = None, None, None
+
     def check_indices(self):
         """Raise if any embedding kernel of this process saw an out-of-range token / coordinate / label index since
         the last check (the reference's nn.Embedding raises a device assert).  One .item() — call it per epoch or

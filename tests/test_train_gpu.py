@@ -1,0 +1,191 @@
+"""Training-step parity on the GPU beyond the tiny single-step tests of test_model_gpu.py:
+
+  * one PhonemeLaTr forward + loss + backward at T5-BASE dims (d 768, 12 layers, 12 heads, S = 327, T = 127 — the
+    BASELINE config 3 shape at batch 2) against the oracle: fp32 mode loss / selected gradients <= 1e-3, bf16 logits
+    <= 1e-2, and the bf16 gradient quality per parameter as cosine + relative norm;
+  * 30 optimizer steps of the bf16, CUDA-graphed TrainStep against the fp32 oracle driven by torch.optim.Adam with
+    the reference's hyper-parameters (core/executor/PhonemeLaTr_Executor.py:262-266), same init, dropout 0: the two
+    loss curves stay within 1e-2 relative at every step;
+  * the reference's per-epoch encoder freeze toggle (PhonemeLaTr_Executor.py:152-159) under the graphed step: the
+    captured graph is dropped and re-captured, frozen parameters stop moving, unfrozen ones move again;
+  * eager eval right after graph replays sees the weights of the LAST optimizer step (bf16 shadows are invalidated).
+"""
+import copy
+
+import pytest
+import torch
+
+from oracle import ref_model
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+VOCAB = (21, 33, 7)
+
+
+def _no_dropout(model):
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+        for attr in ("dropout", "p"):
+            if isinstance(getattr(m, attr, None), float):
+                setattr(m, attr, 0.0)
+
+
+def _pair(cfg, vocab=VOCAB):
+    import phoneme_vqa_b200.models as M
+    oracle = ref_model.PhonemeLaTr(cfg, *vocab)
+    oracle.load_state_dict(ref_model.deterministic_state_dict(oracle), strict=True)
+    model = M.PhonemeLaTr(cfg, *vocab)
+    model.load_state_dict(oracle.state_dict(), strict=True)
+    return oracle, model.to(DEV)
+
+
+def _to(batch, dev):
+    return {k: v.to(dev) for k, v in batch.items()}
+
+
+def _loss(model, b):
+    labels = b["label_ids"]
+    return model.forward_loss(b["pixel_values"], b["coordinates"], b["input_ids"], labels[:, :-1],
+                              b["src_attention_mask"], b["label_attention_mask"][:, :-1], b["ocr_attention_mask"],
+                              b["tokenized_ocr"], targets=labels[:, 1:], ignore_index=2)
+
+
+# the parameters whose gradients are compared in full at base dims (one per kernel family on the path)
+PROBE = ("spatial_feat_extractor.width_emb.weight", "tgt_tok_emb.rhyme_embedding.weight",
+         "encoder.encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight",
+         "encoder.encoder.block.5.layer.0.SelfAttention.q.weight", "encoder.encoder.block.11.layer.1.DenseReluDense.wo.weight",
+         "decoder.decoder.layers.0.self_attn.in_proj_weight", "decoder.decoder.layers.3.multihead_attn.out_proj.weight",
+         "shared_lm_head.weight", "onset_lm_head.weight", "visual_projector.weight")
+
+
+def test_t5_base_dims_forward_loss_backward_match_oracle():
+    cfg = ref_model.make_config(vit_config=dict(hidden_size=64, num_hidden_layers=2, num_attention_heads=2,
+                                                intermediate_size=128, image_size=224, patch_size=16),
+                                vocab_size=2048)        # T5-base encoder dims; small ViT / vocabulary keep the CPU oracle fast
+    oracle, model = _pair(cfg)
+    batch = ref_model.synthetic_batch(2, cfg, T=127, L_ocr=100, L_q=30, V_sub=VOCAB, seed=21, image=224)
+    oracle.train(); model.train()
+    _no_dropout(oracle); _no_dropout(model)
+    ref_loss = ref_model.phoneme_latr_loss(oracle, batch, 2)
+    ref_loss.backward()
+    ref = dict(oracle.named_parameters())
+    b = _to(batch, DEV)
+    # ---- fp32 mode: loss and the probed gradients within 1e-3
+    loss = _loss(model, b)
+    loss.backward()
+    assert abs(loss.item() - ref_loss.item()) <= 1e-3 * abs(ref_loss.item()), (loss.item(), ref_loss.item())
+    got = dict(model.named_parameters())
+    for name in PROBE:
+        a, r = got[name].grad.float().cpu(), ref[name].grad
+        err = float((a - r).norm() / (r.norm() + 1e-12))
+        assert err <= 1e-3, (name, err)
+    # ---- bf16 mode: logits within 1e-2, loss within 1e-3; gradient quality as cosine / relative norm per parameter
+    with torch.no_grad():
+        labels = batch["label_ids"]
+        ref_logits = oracle(pixel_values=batch["pixel_values"], coordinates=batch["coordinates"], input_ids=batch["input_ids"],
+                            labels=labels[:, :-1], src_attention_mask=batch["src_attention_mask"],
+                            label_attention_mask=batch["label_attention_mask"][:, :-1],
+                            ocr_attention_mask=batch["ocr_attention_mask"], tokenized_ocr=batch["tokenized_ocr"])
+    model.zero_grad(set_to_none=True)
+    model.set_compute_dtype(torch.bfloat16)
+    with torch.no_grad():
+        lg = model(pixel_values=b["pixel_values"], coordinates=b["coordinates"], input_ids=b["input_ids"],
+                   labels=b["label_ids"][:, :-1], src_attention_mask=b["src_attention_mask"],
+                   label_attention_mask=b["label_attention_mask"][:, :-1], ocr_attention_mask=b["ocr_attention_mask"],
+                   tokenized_ocr=b["tokenized_ocr"])
+    for a, r in zip(lg, ref_logits):
+        err = float((a.float().cpu() - r).norm() / (r.norm() + 1e-12))
+        assert err <= 1e-2, err
+    loss16 = _loss(model, b)
+    loss16.backward()
+    assert abs(loss16.item() - ref_loss.item()) <= 1e-3 * abs(ref_loss.item()), (loss16.item(), ref_loss.item())
+    report = {}
+    for name, p in model.named_parameters():
+        if p.grad is None or ref[name].grad is None:
+            continue
+        a, r = p.grad.float().cpu().flatten(), ref[name].grad.flatten()
+        if float(r.norm()) == 0.0:
+            continue
+        report[name] = (float(torch.dot(a, r) / (a.norm() * r.norm() + 1e-30)), float(a.norm() / r.norm()))
+    worst_cos = min(report.items(), key=lambda kv: kv[1][0])
+    worst_norm = max(report.items(), key=lambda kv: abs(kv[1][1] - 1.0))
+    print(f"[bf16 gradient quality at T5-base dims] {len(report)} parameters; worst cosine {worst_cos}; "
+          f"worst norm ratio {worst_norm}")
+    # the bar: every parameter's bf16 gradient points the way the fp32 gradient does
+    # (cosine >= 0.98) with the right length (norm ratio within 5 %)
+    assert worst_cos[1][0] >= 0.98, worst_cos
+    assert abs(worst_norm[1][1] - 1.0) <= 0.05, worst_norm
+
+
+def test_thirty_graphed_bf16_steps_track_the_fp32_oracle():
+    from phoneme_vqa_b200 import train
+    cfg = ref_model.tiny_config()
+    oracle, model = _pair(cfg)
+    oracle.train(); model.train()
+    _no_dropout(oracle); _no_dropout(model)
+    model.set_compute_dtype(torch.bfloat16)
+    batches = [ref_model.synthetic_batch(4, cfg, T=17, L_ocr=20, L_q=8, V_sub=VOCAB, seed=100 + i, image=32) for i in range(4)]
+    lr, warm = 1e-3, 10
+    opt = torch.optim.Adam(oracle.parameters(), lr=lr, betas=(0.9, 0.98), eps=1e-9)
+    sched = torch.optim.lr_scheduler.LinearLR(opt, total_iters=warm)          # the reference's scheduler, per iteration
+    step = train.TrainStep(model, None, lr=lr, betas=(0.9, 0.98), eps=1e-9, warmup_iters=warm, ignore_index=2, use_graph=True)
+    ref_curve, got_curve = [], []
+    for i in range(30):
+        b = batches[i % 4]
+        opt.zero_grad()
+        l = ref_model.phoneme_latr_loss(oracle, b, 2)
+        l.backward()
+        opt.step(); sched.step()
+        ref_curve.append(float(l))
+        got_curve.append(float(step(_to(b, DEV)).item()))
+    assert step.captures == 1 and step.replays == 30
+    for i, (a, r) in enumerate(zip(got_curve, ref_curve)):
+        assert abs(a - r) <= 1e-2 * abs(r), (i, a, r, got_curve, ref_curve)
+    assert ref_curve[-1] < 0.9 * ref_curve[0]                                  # and it actually trained
+    # eager evaluation right after the replays runs on the weights of the LAST step (shadows were invalidated)
+    model.eval()
+    with torch.no_grad():
+        l_eval = float(_loss(model, _to(batches[0], DEV)))
+        model.set_compute_dtype(torch.float32)
+        l_eval32 = float(_loss(model, _to(batches[0], DEV)))
+    assert abs(l_eval - l_eval32) <= 1e-2 * abs(l_eval32), (l_eval, l_eval32)
+
+
+def test_graphed_step_follows_the_epoch_freeze_toggle():
+    from phoneme_vqa_b200 import train
+    cfg = ref_model.tiny_config()
+    _, model = _pair(cfg)
+    model.train(); _no_dropout(model)
+    model.set_compute_dtype(torch.bfloat16)
+    b = _to(ref_model.synthetic_batch(4, cfg, T=17, L_ocr=20, L_q=8, V_sub=VOCAB, seed=5, image=32), DEV)
+    step = train.TrainStep(model, None, lr=1e-3, warmup_iters=1, ignore_index=2, use_graph=True)
+    assert len(step.optim.param_groups) == 1
+    assert len(step.optim.param_groups[0]["params"]) == len(list(model.parameters()))      # ALL parameters, like the reference
+    enc_w = model.encoder.encoder.block[0].layer[1].DenseReluDense.wi.weight
+    dec_w = model.decoder.decoder.layers[0].linear1.weight
+
+    def freeze(flag):            # core/executor/PhonemeLaTr_Executor.py:152-159
+        for child in model.encoder.children():
+            for p in child.parameters():
+                p.requires_grad = not flag
+
+    freeze(True)
+    e0, d0 = enc_w.detach().clone(), dec_w.detach().clone()
+    step(b); step(b)
+    assert step.captures == 1
+    assert torch.equal(enc_w, e0) and not torch.equal(dec_w, d0)
+    freeze(False)                                         # epoch > NUM_FREEZE_EPOCH
+    step(b); step(b)
+    assert step.captures == 2, "the trainable set changed: the step must be captured again"
+    assert not torch.equal(enc_w, e0)
+    e1 = enc_w.detach().clone()
+    freeze(True)
+    step(b)
+    assert step.captures == 3 and torch.equal(enc_w, e1)
+    # a short tail batch (DataLoader drop_last=False) runs eagerly instead of being broadcast into the static buffers
+    tail = {k: v[:1] for k, v in b.items()}
+    loss_tail = step(tail)
+    assert torch.isfinite(loss_tail) and step.captures == 3
