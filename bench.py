@@ -135,17 +135,41 @@ def run_eager_gpu_arm(args):
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    cfg = ref_model.make_config()
     torch.manual_seed(0)
-    model = ref_model.PhonemeLaTr(cfg, 84, 187, 7).to(dev).train()
+    metric = "train samples/sec (PhonoLaTr-base)"
+    workload = WORKLOAD.format(B=args.batch)
+    if args.workload == "latr":              # BASELINE config 2: HF T5ForConditionalGeneration + 36 096-way head
+        cfg = ref_model.make_config(num_decoder_layers=12)
+        model = ref_model.LaTr(cfg).to(dev).train()
+        batch = ref_model.latr_batch(args.batch, cfg, T=127, L_ocr=100, L_q=30, seed=1234, image=224)
+        loss_of = lambda: ref_model.latr_loss(model, batch, 0)      # noqa: E731
+        metric = "train samples/sec (LaTr-base)"
+        workload = f"LaTr T5-base (12+12 layers, 36096-way vocabulary head), per-GPU batch {args.batch}, S=327, T=127"
+    elif args.workload == "phonosal":        # BASELINE config 5: T5-large dims, S = 464
+        cfg = ref_model.make_config(d_model=1024, num_heads=16, d_ff=4096, num_layers=24, n_head=16)
+        cfg.update({"ocr_hidden": 512, "obj_hidden": 2048, "new_token_embedding_size": cfg.vocab_size})
+        model = ref_model.PhonemeSaL(cfg, 253).to(dev).train()
+        batch = ref_model.sal_batch(args.batch, cfg, T=39, L_q=80, L_ocr=256, L_obj=128, vocab=253, seed=1234)
+        loss_of = lambda: model(batch)[1]                           # noqa: E731
+        metric = "train samples/sec (PhonoSaL-large)"
+        workload = f"PhonemeSaL T5-large, per-GPU batch {args.batch}, S=464, T=39"
+    elif args.workload == "phonoprestu":
+        _emit({"impl": "eager-gpu", "unavailable": "the oracle has no PhonemePreSTU module graph (that class is pinned "
+                                                   "by fixtures recorded from the real reference, tests/golden)"})
+        return
+    else:
+        cfg = ref_model.make_config()
+        model = ref_model.PhonemeLaTr(cfg, 84, 187, 7).to(dev).train()
+        batch = ref_model.synthetic_batch(args.batch, cfg, seed=1234)
+        loss_of = lambda: ref_model.phoneme_latr_loss(model, batch, 2)       # noqa: E731
     optim = torch.optim.Adam(model.parameters(), lr=5e-5, betas=(0.9, 0.98), eps=1e-9)
     sched = torch.optim.lr_scheduler.LinearLR(optim, total_iters=2000)
-    batch = {k: v.to(dev) for k, v in ref_model.synthetic_batch(args.batch, cfg, seed=1234).items()}
+    batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
     out = {}
     for name, amp in (("f32", False), ("bf16_autocast", True)):
         def step():
             with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
-                loss = ref_model.phoneme_latr_loss(model, batch, 2)
+                loss = loss_of()
             optim.zero_grad()
             loss.backward()
             optim.step()
@@ -162,9 +186,9 @@ def run_eager_gpu_arm(args):
         torch.cuda.synchronize()
         ms = a.elapsed_time(e) / args.steps
         out[name] = {"samples_per_s": args.batch / (ms / 1e3), "ms_per_step": ms, "final_loss": float(last.item())}
-    _emit({"impl": "eager-gpu", "metric": "train samples/sec (PhonoLaTr-base)", "unit": "samples/s", "n_gpus": 1,
+    _emit({"impl": "eager-gpu", "metric": metric, "unit": "samples/s", "n_gpus": 1,
            "steps": args.steps, "warmup": max(args.warmup, 1), "data": "synthetic",
-           "config": {"workload": WORKLOAD.format(B=args.batch) + " — reference module graph, PyTorch eager"},
+           "config": {"workload": workload + " — reference module graph, PyTorch eager"},
            "value": out["bf16_autocast"]["samples_per_s"], "dtype": "bf16 autocast", "variants": out})
 
 

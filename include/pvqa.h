@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PVQA_ABI_VERSION 8
+#define PVQA_ABI_VERSION 9
 
 typedef enum {
   PVQA_OK = 0,
@@ -147,6 +147,23 @@ int pvqa_phoneme_head_ce_fwd(const void* h, const int64_t* targets /* (N,3) stri
                              int64_t N, int64_t d, int64_t on_dim, int64_t rt_dim,
                              int64_t V_o, int64_t V_r, int64_t V_t, int64_t ignore_index,
                              int w_dtype, int act_dtype, void* stream);
+
+/* K4 on the Blackwell tensor path: shared_lm_head + column split + the three heads + 3x cross-entropy in ONE tcgen05
+ * kernel (phoneme-vqa_b200/csrc/head_tc.cu).  replaces core/model/PhonemeLaTr.py:121-130 and
+ * core/executor/PhonemeLaTr_Executor.py:181-190 on the fused-loss path.
+ *   x (N,768) bf16 = decoder output;  W_shared (768,768) bf16, b_shared (768) fp32;  W_k (V_k,256) bf16, b_k (V_k) fp32
+ *   writes h_out (N,768) bf16 = shared_lm_head(x) (what pvqa_phoneme_head_ce_bwd recomputes from), loss_sum[3],
+ *   count[3], lse (N,3) — same meaning as pvqa_phoneme_head_ce_fwd.  Specialised for d = 768 (slices 256|256|256) and
+ *   sub-vocabularies of at most 192 entries; other shapes: PVQA_ERR_SHAPE (use pvqa_phoneme_head_ce_fwd on the output
+ *   of a library GEMM). */
+int pvqa_phoneme_head_fused_fwd(const void* x, const void* W_shared, const float* b_shared,
+                                const int64_t* targets /* (N,3) strided */, int64_t tgt_row_stride,
+                                const void* W_onset, const float* b_onset,
+                                const void* W_rhyme, const float* b_rhyme,
+                                const void* W_tone, const float* b_tone,
+                                void* h_out, float* loss_sum /*3*/, int32_t* count /*3*/, float* lse /*N,3*/,
+                                int64_t N, int64_t d, int64_t on_dim, int64_t rt_dim,
+                                int64_t V_o, int64_t V_r, int64_t V_t, int64_t ignore_index, void* stream);
 
 int pvqa_phoneme_head_ce_bwd(const void* h, const int64_t* targets, int64_t tgt_row_stride,
                              const void* W_onset, const void* b_onset,

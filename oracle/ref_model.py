@@ -272,15 +272,15 @@ def sal_position_bias(rel_table, scp_table, S, coordinates, max_ques, max_ocr):
     B = coordinates.shape[0]
     pos = torch.arange(S)
     rel = ref_ops.t5_relative_bucket((pos[None, :] - pos[:, None]).numpy(), True, 32, 128)
-    bias = torch.nn.functional.embedding(torch.as_tensor(rel), rel_table).permute(2, 0, 1)[None].repeat(B, 1, 1, 1)
+    bias = torch.nn.functional.embedding(torch.as_tensor(rel).to(rel_table.device), rel_table).permute(2, 0, 1)[None].repeat(B, 1, 1, 1)
     xc = coordinates[:, :, [0, 2]].mean(dim=-1)
     yc = coordinates[:, :, [1, 3]].mean(dim=-1)
-    xi = np.int32(np.floor(xc.numpy() * 11))
-    yi = np.int32(np.floor(yc.numpy() * 11))
+    xi = np.int32(np.floor(xc.cpu().numpy() * 11))
+    yi = np.int32(np.floor(yc.cpu().numpy() * 11))
     lut = scp_distance_lut()
     d = lut[xi[:, :, None], yi[:, :, None], xi[:, None, :], yi[:, None, :]]          # (B,L,L)
     bk = ref_ops.t5_relative_bucket(torch.tensor(d).to(torch.long).numpy(), True, 32, 100)
-    scp = torch.nn.functional.embedding(torch.as_tensor(bk), scp_table).permute(0, 3, 1, 2)
+    scp = torch.nn.functional.embedding(torch.as_tensor(bk).to(scp_table.device), scp_table).permute(0, 3, 1, 2)
     bias[:, :, max_ques:max_ques + max_ocr, max_ques:max_ques + max_ocr] += scp
     return bias
 

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libpvqa_sm100.so")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
-SOURCES = ["api.cu", "embed.cu", "head.cu", "attn.cu", "attn_simt.cu", "norm.cu"]
+SOURCES = ["api.cu", "embed.cu", "head.cu", "head_tc.cu", "attn.cu", "attn_simt.cu", "norm.cu"]
 HEADERS = ["common.cuh", "tc05.cuh", "attn_fwd.cuh", "attn_bwd.cuh"]
 
 NVCC_FLAGS = [
@@ -27,7 +27,7 @@ NVCC_FLAGS = [
 ]
 
 PVQA_F32, PVQA_BF16 = 0, 1
-ABI_VERSION = 8  # must equal PVQA_ABI_VERSION in include/pvqa.h
+ABI_VERSION = 9  # must equal PVQA_ABI_VERSION in include/pvqa.h
 
 
 def _stale() -> bool:
@@ -88,6 +88,7 @@ _SIGNATURES = {
     "pvqa_embed_tgt_bwd": (c_int, [_vp] * 5 + _i64x(8) + [c_int, _f, c_uint64, c_uint64, _vp]),
     "pvqa_phoneme_head_ce_fwd": (c_int, [_vp, _vp, _i64] + [_vp] * 12 + _i64x(8) + [c_int, c_int, _vp]),
     "pvqa_phoneme_head_ce_bwd": (c_int, [_vp, _vp, _i64] + [_vp] * 12 + _i64x(8) + [c_int, c_int, _vp]),
+    "pvqa_phoneme_head_fused_fwd": (c_int, [_vp, _vp, _vp, _vp, _i64] + [_vp] * 6 + [_vp] * 4 + _i64x(8) + [_vp]),
     "pvqa_vocab_ce_grad": (c_int, [_vp, _vp, _i64, _vp, _vp, _vp] + _i64x(3) + [_vp]),
     "pvqa_attn_fwd": (c_int, [_vp] * 7 + _i64x(5) + _i64x(12) + [_f, c_int, _f, c_uint64, c_uint64, _vp, _vp, _i64, _i64, _vp]),
     "pvqa_attn_bwd": (c_int, [_vp] * 13 + _i64x(5) + _i64x(21) + [_f, c_int, _f, c_uint64, c_uint64, _vp, _vp, _vp, _i64, _i64,

@@ -30,6 +30,21 @@ def _random_init(config) -> bool:
     return os.environ.get("PVQA_RANDOM_INIT", "0") == "1" or bool(getattr(config, "random_init", False))
 
 
+def _phoneme_head_loss(m, dec, targets, ignore_index):
+    """K4: shared_lm_head + the three heads + 3x cross-entropy.  bf16 at d = 768: ONE tcgen05 kernel (csrc/head_tc.cu);
+    other dtypes / widths: library GEMM for shared_lm_head + the mma.sync / fp32 head kernel."""
+    x = dec.reshape(-1, dec.shape[-1])
+    tg = targets.reshape(-1, 3)
+    heads = (m.onset_lm_head.weight, m.onset_lm_head.bias, m.rhyme_lm_head.weight, m.rhyme_lm_head.bias,
+             m.tone_lm_head.weight, m.tone_lm_head.bias)
+    if ops.phoneme_head_fused_supported(x, heads[0], heads[2], heads[4]):
+        from .modules import SHADOWS
+        w_lp = SHADOWS.get([m.shared_lm_head.weight], torch.bfloat16)
+        return ops.phoneme_head_fused(x, w_lp, m.shared_lm_head.weight, m.shared_lm_head.bias, tg, *heads, ignore_index)
+    h = _lin(dec, m.shared_lm_head.weight, m.shared_lm_head.bias)
+    return ops.phoneme_head_ce(h.reshape(-1, h.shape[-1]), tg, *heads, ignore_index)
+
+
 def _auto_config(name):
     from transformers import AutoConfig
     return AutoConfig.from_pretrained(name)
@@ -306,11 +321,7 @@ class PhonemeLaTr(nn.Module, _VisionMixin):
         enc, attention_mask = self._encode(pixel_values, coordinates, input_ids, ocr_attention_mask,
                                            src_attention_mask, tokenized_ocr)
         dec = self.decode(labels, enc, attention_mask, label_attention_mask)
-        h = _lin(dec.to(self.compute_dtype), self.shared_lm_head.weight, self.shared_lm_head.bias)
-        return ops.phoneme_head_ce(h.reshape(-1, h.shape[-1]), targets.reshape(-1, 3),
-                                   self.onset_lm_head.weight, self.onset_lm_head.bias,
-                                   self.rhyme_lm_head.weight, self.rhyme_lm_head.bias,
-                                   self.tone_lm_head.weight, self.tone_lm_head.bias, ignore_index)
+        return _phoneme_head_loss(self, dec.to(self.compute_dtype), targets, ignore_index)
 
     # -- reference :146-217 ---------------------------------------------------------
     def generate(self, pixel_values, coordinates, input_ids, src_attention_mask, ocr_attention_mask, tokenized_ocr,
@@ -551,11 +562,7 @@ class PhonemePreSTU(nn.Module, _VisionMixin):
         inputs_embeds, attention_mask = self._calculate_embedding(pixel_values, input_ids, src_attention_mask)
         enc = self.encoder.encoder(inputs_embeds, attention_mask, compute_dtype=self.compute_dtype)
         dec = self.decode(labels, enc, attention_mask, label_attention_mask)
-        h = _lin(dec.to(self.compute_dtype), self.shared_lm_head.weight, self.shared_lm_head.bias)
-        return ops.phoneme_head_ce(h.reshape(-1, h.shape[-1]), targets.reshape(-1, 3),
-                                   self.onset_lm_head.weight, self.onset_lm_head.bias,
-                                   self.rhyme_lm_head.weight, self.rhyme_lm_head.bias,
-                                   self.tone_lm_head.weight, self.tone_lm_head.bias, ignore_index)
+        return _phoneme_head_loss(self, dec.to(self.compute_dtype), targets, ignore_index)
 
     # The call the executor makes (core/executor/PhonemePreSTU_Executor.py:41-49): the class's own `generate`
     # (PhonemePreSTU.py:103-199) still carries PhonemeLaTr's argument list and cannot run, so the

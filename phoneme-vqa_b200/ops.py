@@ -841,6 +841,84 @@ class _PhonemeHeadCE(torch.autograd.Function):
         return (d_h, None, *grads, None)
 
 
+class _PhonemeHeadFused(torch.autograd.Function):
+    """K4 on tcgen05: loss = 3x CE(heads(shared_lm_head(x))) in one kernel (csrc/head_tc.cu).  The backward recomputes
+    the sub-vocabulary logits from the saved bf16 h (pvqa_phoneme_head_ce_bwd) and leaves the GEMMs of the gradient to
+    the library, exactly like _PhonemeHeadCE + the shared linear's backward."""
+
+    @staticmethod
+    def forward(ctx, x, Ws_lp, Ws, bs, targets, W_on, b_on, W_rh, b_rh, W_to, b_to, ignore_index):
+        lib = _lib.load()
+        _need_cuda(x, Ws_lp, bs, targets, W_on, b_on, W_rh, b_rh, W_to, b_to)
+        if targets.dtype != torch.int64 or targets.shape[-1] != 3 or targets.stride(-1) != 1:
+            raise TypeError("targets must be int64 (N,3) with unit inner stride")
+        x = x.contiguous()
+        N, d = x.shape
+        V_o, on_dim = W_on.shape
+        V_r, rt_dim = W_rh.shape
+        V_t, _ = W_to.shape
+        dev = x.device
+        wk = [t.to(torch.bfloat16).contiguous() for t in (W_on, W_rh, W_to)]
+        bk = [t.to(torch.float32).contiguous() for t in (b_on, b_rh, b_to)]
+        bs32 = bs.to(torch.float32).contiguous()
+        h = torch.empty((N, d), dtype=torch.bfloat16, device=dev)
+        loss_sum = torch.empty(3, dtype=torch.float32, device=dev)
+        count = torch.empty(3, dtype=torch.int32, device=dev)
+        lse = torch.empty((N, 3), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev), _prof("phoneme_head_fused_fwd"):
+            check(lib.pvqa_phoneme_head_fused_fwd(_p(x), _p(Ws_lp), _p(bs32), _p(targets), targets.stride(0),
+                                                  _p(wk[0]), _p(bk[0]), _p(wk[1]), _p(bk[1]), _p(wk[2]), _p(bk[2]),
+                                                  _p(h), _p(loss_sum), _p(count), _p(lse), N, d, on_dim, rt_dim,
+                                                  V_o, V_r, V_t, int(ignore_index), _stream()),
+                  "pvqa_phoneme_head_fused_fwd")
+        loss = (loss_sum / count.to(torch.float32)).sum()
+        bkl = [t.to(torch.bfloat16) for t in bk]
+        ctx.save_for_backward(x, Ws_lp, h, targets, lse, count, wk[0], bkl[0], wk[1], bkl[1], wk[2], bkl[2])
+        ctx.meta = (N, d, on_dim, rt_dim, V_o, V_r, V_t, int(ignore_index), W_on.dtype, b_on.dtype, bs.dtype)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        x, Ws_lp, h, targets, lse, count, W_on, b_on, W_rh, b_rh, W_to, b_to = ctx.saved_tensors
+        N, d, on_dim, rt_dim, V_o, V_r, V_t, ignore_index, w_dtype, b_dtype, bs_dtype = ctx.meta
+        dev = h.device
+        g = g.to(torch.float32).reshape(1).contiguous()
+        dls = [torch.empty((N, V), dtype=h.dtype, device=dev) for V in (V_o, V_r, V_t)]
+        with torch.cuda.device(dev), _prof("phoneme_head_ce_bwd"):
+            check(lib.pvqa_phoneme_head_ce_bwd(_p(h), _p(targets), targets.stride(0), _p(W_on), _p(b_on), _p(W_rh),
+                                               _p(b_rh), _p(W_to), _p(b_to), _p(lse), _p(count), _p(g),
+                                               _p(dls[0]), _p(dls[1]), _p(dls[2]),
+                                               N, d, on_dim, rt_dim, V_o, V_r, V_t, ignore_index,
+                                               _dt(W_on.dtype), _dt(h.dtype), _stream()),
+                  "pvqa_phoneme_head_ce_bwd")
+        d_h = torch.empty_like(h)
+        offs = (0, on_dim, on_dim + rt_dim)
+        widths = (on_dim, rt_dim, rt_dim)
+        grads = []
+        for dl, W, off, w in zip(dls, (W_on, W_rh, W_to), offs, widths):
+            d_h[:, off:off + w] = dl @ W
+            grads.append(torch.mm(dl.t(), h[:, off:off + w], out_dtype=torch.float32).to(w_dtype))
+            grads.append(dl.sum(0, dtype=torch.float32).to(b_dtype))
+        dx = d_h @ Ws_lp if ctx.needs_input_grad[0] else None
+        dWs = torch.mm(d_h.t(), x, out_dtype=torch.float32)
+        dbs = col_sum(d_h).to(bs_dtype)
+        return (dx, None, dWs, dbs, None, *grads, None)
+
+
+def phoneme_head_fused(x, W_shared_lp, W_shared, b_shared, targets, W_onset, b_onset, W_rhyme, b_rhyme, W_tone, b_tone,
+                       ignore_index):
+    """K4, one tcgen05 kernel: x (N,768) bf16 = decoder output; W_shared_lp = bf16 shadow of the fp32 master W_shared
+    (the gradient goes to the master).  Returns the scalar onset+rhyme+tone cross-entropy."""
+    return _PhonemeHeadFused.apply(x, W_shared_lp, W_shared, b_shared, targets, W_onset, b_onset, W_rhyme, b_rhyme,
+                                   W_tone, b_tone, ignore_index)
+
+
+def phoneme_head_fused_supported(x, W_onset, W_rhyme, W_tone):
+    return (x.dtype == torch.bfloat16 and x.shape[-1] == 768 and W_onset.shape[1] == 256 and W_rhyme.shape[1] == 256
+            and max(W_onset.shape[0], W_rhyme.shape[0], W_tone.shape[0]) <= 192)
+
+
 def phoneme_head_ce(h, targets, W_onset, b_onset, W_rhyme, b_rhyme, W_tone, b_tone, ignore_index):
     """K4.  h (N,d) = shared_lm_head output, targets (N,3) int64.  Returns the scalar
     onset+rhyme+tone cross-entropy of core/executor/PhonemeLaTr_Executor.py:181-190."""
