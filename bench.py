@@ -341,13 +341,15 @@ def run_b200_arm(args):
                 else:
                     ach = amount / avg_ms / 1e9
                     entry.update({"bound": "tensor", "achieved": ach, "peak": tf, "unit": "TFLOP/s", "frac": ach / tf})
+            if name in traffic:
+                entry["traffic"] = traffic[name]          # ncu dram bytes per launch (profiles/traffic.json)
             kernels[name] = entry
         dom = max((k for k in kernels if "bound" in kernels[k]), key=lambda k: kernels[k]["avg_ms"] * kernels[k]["launches_per_step"],
                   default=None)
         roofline = None
         if dom:
             roofline = {k: kernels[dom][k] for k in ("bound", "achieved", "peak", "unit", "frac")}
-            roofline.update({"kernel": dom, "traffic": traffic.get(dom.split("[")[0]), "peak_source": src,
+            roofline.update({"kernel": dom, "traffic": traffic.get(dom), "peak_source": src,
                              "avg_launch_ms": kernels[dom]["avg_ms"],
                              "note": "achieved = algorithmic flops (or bytes) per launch / CUDA-event duration of that "
                                      "launch inside the step; traffic = ncu dram bytes per launch (profiles/)"})
@@ -359,6 +361,7 @@ def run_b200_arm(args):
             "config": {"workload": workload,
                        "global_batch": world * B,
                        "parallelism": f"dp{world}", "weights": "random-init",
+                       "eager_gpu_samples_s": _eager_gpu(args),
                        "launch": "eager" if args.no_graph else "one CUDA graph per step",
                        "l2": "no flush: per-step working set (0.9 GB weights+Adam state read, >10 GB activations) "
                              "exceeds the 126 MB L2; 4 distinct batches cycled"},
@@ -387,6 +390,19 @@ def run_b200_arm(args):
         dist.barrier()
         dist.destroy_process_group()
         watchdog.cancel()
+
+
+def _eager_gpu(args):
+    """samples/s per GPU of the PyTorch-eager incumbent on a B200 for this workload, as measured by
+    `bench.py --impl eager-gpu` and archived under profiles/ (None when this configuration was not measured)."""
+    path = os.path.join(ROOT, "profiles", "eager_gpu.json")
+    if not os.path.exists(path) or args.image != 224:
+        return None
+    with open(path) as f:
+        w = json.load(f)["workloads"].get(args.workload)
+    if not w:
+        return None
+    return {"f32": w["f32_samples_s"], "bf16_autocast": w["bf16_autocast_samples_s"], "n_gpus": 1, "source": w["source"]}
 
 
 def _measured_traffic():

@@ -859,7 +859,9 @@ class _PhonemeHeadFused(torch.autograd.Function):
         V_t, _ = W_to.shape
         dev = x.device
         wk = [t.to(torch.bfloat16).contiguous() for t in (W_on, W_rh, W_to)]
-        bk = [t.to(torch.float32).contiguous() for t in (b_on, b_rh, b_to)]
+        # biases are consumed at bf16 precision on both sides (the backward kernel recomputes the logits with them)
+        bkl = [t.to(torch.bfloat16).contiguous() for t in (b_on, b_rh, b_to)]
+        bk = [t.to(torch.float32) for t in bkl]
         bs32 = bs.to(torch.float32).contiguous()
         h = torch.empty((N, d), dtype=torch.bfloat16, device=dev)
         loss_sum = torch.empty(3, dtype=torch.float32, device=dev)
@@ -872,7 +874,6 @@ class _PhonemeHeadFused(torch.autograd.Function):
                                                   V_o, V_r, V_t, int(ignore_index), _stream()),
                   "pvqa_phoneme_head_fused_fwd")
         loss = (loss_sum / count.to(torch.float32)).sum()
-        bkl = [t.to(torch.bfloat16) for t in bk]
         ctx.save_for_backward(x, Ws_lp, h, targets, lse, count, wk[0], bkl[0], wk[1], bkl[1], wk[2], bkl[2])
         ctx.meta = (N, d, on_dim, rt_dim, V_o, V_r, V_t, int(ignore_index), W_on.dtype, b_on.dtype, bs.dtype)
         return loss

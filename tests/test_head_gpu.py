@@ -77,6 +77,7 @@ def test_phoneme_head_fused_tcgen05(N, V, frac):
     bsh = torch.randn(d, generator=g) * 0.1
     _, tg, Ws, bs = _inputs(N, d, V=V, seed=N, frac_ignored=frac)
     Ws = [w.bfloat16().float() for w in Ws]
+    bs = [b.bfloat16().float() for b in bs]
     leaves = [x, Wsh, bsh] + Ws + bs
     for t in leaves:
         t.requires_grad_(True)
@@ -98,8 +99,8 @@ def test_phoneme_head_fused_tcgen05(N, V, frac):
     got = [xc.grad.float()] + [t.grad for t in c[1:]]
     for name, a, b in zip(("x", "W_shared", "b_shared", "W_on", "W_rh", "W_to", "b_on", "b_rh", "b_to"), got, leaves):
         a, r = a.float().cpu().flatten(), b.grad.flatten()
-        if float(r.norm()) == 0.0:
-            assert float(a.norm()) == 0.0, name
+        if float(r.norm()) == 0.0:                           # one-entry vocabulary: softmax == 1, gradient exactly 0 in exact
+            assert float(a.norm()) <= 1e-5, (name, float(a.norm()))   # arithmetic; two GEMM orders differ by rounding
             continue
         cos = float(torch.dot(a, r) / (a.norm() * r.norm()))
         rel = float((a - r).norm() / r.norm())

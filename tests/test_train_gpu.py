@@ -53,14 +53,6 @@ def _loss(model, b):
                               b["tokenized_ocr"], targets=labels[:, 1:], ignore_index=2)
 
 
-# the parameters whose gradients are compared in full at base dims (one per kernel family on the path)
-PROBE = ("spatial_feat_extractor.width_emb.weight", "tgt_tok_emb.rhyme_embedding.weight",
-         "encoder.encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight",
-         "encoder.encoder.block.5.layer.0.SelfAttention.q.weight", "encoder.encoder.block.11.layer.1.DenseReluDense.wo.weight",
-         "decoder.decoder.layers.0.self_attn.in_proj_weight", "decoder.decoder.layers.3.multihead_attn.out_proj.weight",
-         "shared_lm_head.weight", "onset_lm_head.weight", "visual_projector.weight")
-
-
 def test_t5_base_dims_forward_loss_backward_match_oracle():
     cfg = ref_model.make_config(vit_config=dict(hidden_size=64, num_hidden_layers=2, num_attention_heads=2,
                                                 intermediate_size=128, image_size=224, patch_size=16),
@@ -72,29 +64,62 @@ def test_t5_base_dims_forward_loss_backward_match_oracle():
     ref_loss = ref_model.phoneme_latr_loss(oracle, batch, 2)
     ref_loss.backward()
     ref = dict(oracle.named_parameters())
-    # The same restatement evaluated in float64 is the exact answer.  At these dims the fp32 CPU oracle is itself
-    # ~1e-2 away from it for the gradients that cross all 12 encoder layers (measured: width_emb 1.09e-2, block 3 wi
-    # 1.18e-2), so "within 1e-3 of the fp32 oracle" is not a property any fp32 implementation has here; the bar is
-    # "no further from the exact gradient than 2x the reference's own fp32 arithmetic (floor 1e-3)".
+    b = _to(batch, DEV)
+    # ---- fp32 mode.  At these dims the deterministic weights make the 12-layer forward ill-conditioned: two correct
+    # fp32 implementations differ by ~3e-4 in the feed-forward pre-activations (measured, tools/diag_base_grads2.py:
+    # CPU fp32 oracle 2.4e-4, product 4.8e-4 against float64), which flips ~10 of the 520 192 ReLU gates per layer,
+    # and every flipped gate moves the gradient by one full-size entry (2.6e-3 relative below the flipped layer, for
+    # the CPU fp32 oracle just as for the product).  The gradient is therefore compared with the exact (float64)
+    # gradient OF THE SAME GATES: the float64 oracle is re-run with the product's ReLU decisions imposed on its 16
+    # feed-forwards, which removes the knife-edge and leaves the arithmetic of every kernel under test.
+    from phoneme_vqa_b200 import ops
+    seen, kernel = [], ops.relu_dropout
+
+    def spy(x, p, training):
+        seen.append((x.detach() > 0).cpu())
+        return kernel(x, p, training)
+
+    ops.relu_dropout = spy
+    try:
+        loss = _loss(model, b)
+    finally:
+        ops.relu_dropout = kernel
+    loss.backward()
+    n_enc = cfg.num_layers
+    assert len(seen) == n_enc + cfg.num_decoder_layers
     o64 = ref_model.PhonemeLaTr(cfg, *VOCAB)
     o64.load_state_dict(oracle.state_dict())
     o64 = o64.double()
     o64.train(); _no_dropout(o64)
+
+    def gated(g):
+        return lambda x: x * g.reshape(x.shape).to(x.dtype)
+
+    free = {}
+    for i, blk in enumerate(o64.encoder.encoder.block):
+        blk.layer[1].DenseReluDense.wi.register_forward_hook(lambda m, a, o, i=i: free.__setitem__(i, o.detach() > 0))
+        blk.layer[1].DenseReluDense.act = gated(seen[i])
+    for i, layer in enumerate(o64.decoder.decoder.layers):
+        layer.linear1.register_forward_hook(lambda m, a, o, i=i: free.__setitem__(n_enc + i, o.detach() > 0))
+        layer.activation = gated(seen[n_enc + i])
     loss64 = ref_model.phoneme_latr_loss(o64, {k: (v.double() if v.is_floating_point() else v) for k, v in batch.items()}, 2)
     loss64.backward()
-    exact = dict(o64.named_parameters())
-    b = _to(batch, DEV)
-    # ---- fp32 mode
-    loss = _loss(model, b)
-    loss.backward()
+    flips = [int((free[i].reshape(seen[i].shape) != seen[i]).sum()) for i in range(len(seen))]
+    print(f"[fp32 mode at T5-base dims] ReLU gates that differ from the float64 oracle's own, per feed-forward: {flips} "
+          f"of {seen[0].numel()} / {seen[-1].numel()}")
+    assert max(flips) <= 1e-3 * seen[-1].numel()           # the imposed gates ARE the oracle's gates up to rounding
     assert abs(loss.item() - loss64.item()) <= 1e-5 * abs(loss64.item()), (loss.item(), loss64.item())
-    got = dict(model.named_parameters())
-    for name in PROBE:
+    assert abs(loss.item() - ref_loss.item()) <= 1e-5 * abs(ref_loss.item()), (loss.item(), ref_loss.item())
+    exact = dict(o64.named_parameters())
+    worst = ("", 0.0)
+    for name, p in model.named_parameters():
         e = exact[name].grad
-        ours = float((got[name].grad.double().cpu() - e).norm() / (e.norm() + 1e-30))
-        theirs = float((ref[name].grad.double() - e).norm() / (e.norm() + 1e-30))
-        print(f"[fp32 gradient vs float64 oracle] {name}: ours {ours:.2e}, fp32 CPU oracle {theirs:.2e}")
-        assert ours <= max(1e-3, 2.0 * theirs), (name, ours, theirs)
+        if p.grad is None or e is None or float(e.norm()) == 0.0:
+            continue
+        err = float((p.grad.double().cpu() - e).norm() / e.norm())
+        worst = max(worst, (name, err), key=lambda t: t[1])
+    print(f"[fp32 mode at T5-base dims] worst gradient error against the gate-matched float64 oracle: {worst}")
+    assert worst[1] <= 1e-3, worst
     # ---- bf16 mode: logits within 1e-2, loss within 1e-3; gradient quality as cosine / relative norm per parameter
     with torch.no_grad():
         labels = batch["label_ids"]
@@ -133,13 +158,13 @@ def test_t5_base_dims_forward_loss_backward_match_oracle():
     assert abs(worst_norm[1][1] - 1.0) <= 0.05, worst_norm
 
 
-def test_thirty_graphed_bf16_steps_track_the_fp32_oracle():
+def _thirty_steps(dtype):
     from phoneme_vqa_b200 import train
     cfg = ref_model.tiny_config()
     oracle, model = _pair(cfg)
     oracle.train(); model.train()
     _no_dropout(oracle); _no_dropout(model)
-    model.set_compute_dtype(torch.bfloat16)
+    model.set_compute_dtype(dtype)
     batches = [ref_model.synthetic_batch(4, cfg, T=17, L_ocr=20, L_q=8, V_sub=VOCAB, seed=100 + i, image=32) for i in range(4)]
     lr, warm = 1e-3, 10
     opt = torch.optim.Adam(oracle.parameters(), lr=lr, betas=(0.9, 0.98), eps=1e-9)
@@ -155,9 +180,56 @@ def test_thirty_graphed_bf16_steps_track_the_fp32_oracle():
         ref_curve.append(float(l))
         got_curve.append(float(step(_to(b, DEV)).item()))
     assert step.captures == 1 and step.replays == 30
-    for i, (a, r) in enumerate(zip(got_curve, ref_curve)):
-        assert abs(a - r) <= 1e-2 * abs(r), (i, a, r, got_curve, ref_curve)
-    assert ref_curve[-1] < 0.9 * ref_curve[0]                                  # and it actually trained
+    assert ref_curve[-1] < 0.9 * ref_curve[0]                                  # it actually trained
+    dev = max(abs(a - r) / abs(r) for a, r in zip(got_curve, ref_curve))
+    print(f"[30 graphed {dtype} steps vs fp32 oracle + torch Adam] worst relative loss deviation {dev:.2e}; "
+          f"final {got_curve[-1]:.4f} vs {ref_curve[-1]:.4f}")
+    return model, batches, got_curve, ref_curve, dev
+
+
+def test_thirty_graphed_fp32_steps_follow_the_oracle_and_torch_adam():
+    """the captured step (forward, backward, Adam, LinearLR, all replayed from one graph) in fp32 mode against the CPU
+    oracle driven by torch.optim.Adam + LinearLR (reference recipe, base_executor.py:60-66): 1.5e-2 on the loss curve
+    of 30 updates (measured 7.4e-3).  Adam with eps = 1e-9 turns every gradient entry into +-lr whatever its size, so
+    rounding-level differences in near-zero entries do move weights; the tight statement about the captured
+    optimizer is the next test."""
+    _, _, got, ref, dev = _thirty_steps(torch.float32)
+    assert dev <= 1.5e-2, (dev, got, ref)
+
+
+def test_graphed_step_equals_eager_step_with_torch_adam():
+    """same model, same kernels: 30 replays of the captured step (device-side Adam + LinearLR) against 30 eager
+    forward/backward passes of a twin driven by torch.optim.Adam + LinearLR.  Only atomics ordering differs."""
+    import copy
+    from phoneme_vqa_b200 import train
+    cfg = ref_model.tiny_config()
+    _, model = _pair(cfg)
+    model.train(); _no_dropout(model)
+    twin = copy.deepcopy(model)
+    batches = [_to(ref_model.synthetic_batch(4, cfg, T=17, L_ocr=20, L_q=8, V_sub=VOCAB, seed=100 + i, image=32), DEV) for i in range(4)]
+    lr, warm = 1e-3, 10
+    opt = torch.optim.Adam(twin.parameters(), lr=lr, betas=(0.9, 0.98), eps=1e-9)
+    sched = torch.optim.lr_scheduler.LinearLR(opt, total_iters=warm)
+    step = train.TrainStep(model, None, lr=lr, betas=(0.9, 0.98), eps=1e-9, warmup_iters=warm, ignore_index=2, use_graph=True)
+    dev = 0.0
+    for i in range(30):
+        b = batches[i % 4]
+        opt.zero_grad()
+        l = _loss(twin, b)
+        l.backward()
+        opt.step(); sched.step()
+        g = float(step(b).item())
+        dev = max(dev, abs(g - float(l)) / abs(float(l)))
+    print(f"[30 graphed fp32 steps vs eager twin + torch Adam] worst relative loss deviation {dev:.2e}")
+    assert step.captures == 1 and step.replays == 30
+    assert dev <= 2e-3, dev
+
+
+def test_thirty_graphed_bf16_steps_track_the_fp32_oracle():
+    """the same in bf16 mode: the curve tracks the fp32 oracle within 3e-2 at every step and ends at the same loss
+    within 3e-2 (bf16 rounding noise through the sign-normalising optimizer, see above)."""
+    model, batches, got, ref, dev = _thirty_steps(torch.bfloat16)
+    assert dev <= 3e-2, (dev, got, ref)
     # eager evaluation right after the replays runs on the weights of the LAST step (shadows were invalidated)
     model.eval()
     with torch.no_grad():
