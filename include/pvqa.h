@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PVQA_ABI_VERSION 9
+#define PVQA_ABI_VERSION 10
 
 typedef enum {
   PVQA_OK = 0,
@@ -50,6 +50,11 @@ int64_t pvqa_launch_count(void);
  * Philox offset it was launched with, so a CUDA graph capturing a whole training step draws fresh masks on
  * each replay (the caller increments the counter between replays).  NULL (default) disables it. */
 int pvqa_set_rng_step_counter(const uint64_t* device_counter);
+/* Data-parallel runs: leave `n` SMs (0..64, default 0) to the NCCL kernels that overlap the
+ * backward.  Every grid of the library is then sized for (SM count - n); without it the persistent one-CTA-per-SM
+ * attention kernels wait a whole kernel duration for the SMs a collective occupies.  Affects subsequent launches (and
+ * therefore CUDA graphs captured afterwards). */
+int pvqa_set_reserved_sms(int n);
 
 /* ------------------------------------------------------------------------
  * K1  fused multimodal embedding

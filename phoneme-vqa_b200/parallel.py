@@ -34,7 +34,13 @@ def grad_slot(param):
 
 
 class GradReducer:
-    def __init__(self, module: torch.nn.Module, bucket_mb: float = 32.0, process_group=None, average: bool = True):
+    def __init__(self, module: torch.nn.Module, bucket_mb: float = 32.0, process_group=None, average: bool = True,
+                 comm_sms: int = 0, tail_mb: float = 160.0, reserve_compute: bool = True):
+        """comm_sms > 0 (NCCL only): the all-reduces that overlap the backward run on a communicator capped at
+        `comm_sms` CTAs, and the compute side leaves that many SMs free (libpvqa grids via pvqa_set_reserved_sms, the
+        library GEMMs via cuBLAS' SM-count target) so that persistent one-CTA-per-SM kernels are not queued behind a
+        collective.  The last `tail_mb` of gradients (the embedding tables: nothing is left to overlap them with) go
+        over the uncapped communicator."""
         self.module = module
         self.bucket_bytes = int(bucket_mb * 1024 * 1024)
         self.pg = process_group
@@ -42,10 +48,55 @@ class GradReducer:
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         # NCCL averages inside the collective; gloo (CPU tests) has no AVG: divide, then sum
         self._native_avg = bool(average and dist.is_initialized() and dist.get_backend(process_group) == "nccl")
+        self.comm_sms = int(comm_sms) if (self._native_avg or (dist.is_initialized() and dist.get_backend(process_group) == "nccl")) and self.world > 1 else 0
+        self.tail_bytes = int(tail_mb * 1024 * 1024)
+        self.pg_overlap = process_group
+        self._sm_threads = set()
+        if self.comm_sms > 0:
+            opts = dist.ProcessGroupNCCL.Options()
+            opts.config.max_ctas = self.comm_sms
+            opts.config.min_ctas = min(self.comm_sms, 4)
+            self.pg_overlap = dist.new_group(backend="nccl", pg_options=opts)
+            self.reserve_compute = bool(reserve_compute)
+            if self.reserve_compute:
+                from . import _lib
+                _lib.check(_lib.load().pvqa_set_reserved_sms(self.comm_sms), "pvqa_set_reserved_sms")
+                self._limit_library_gemms()
         self._hooks = []
         self.rebuild()
         global _ACTIVE
         _ACTIVE = self
+
+    def _limit_library_gemms(self):
+        """cuBLAS / cuBLASLt SM-count target for the calling thread's handle (forward thread and the autograd thread
+        each own one).  Called once per thread; cheap."""
+        import threading
+        tid = threading.get_ident()
+        if tid in self._sm_threads or self.comm_sms <= 0 or not self.reserve_compute:
+            return
+        self._sm_threads.add(tid)
+        n = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count - self.comm_sms
+        if hasattr(torch._C, "_set_sm_carveout_experimental"):
+            torch._C._set_sm_carveout_experimental(self.comm_sms)          # cuBLASLt paths (matmul descriptors)
+        try:
+            import ctypes
+            blas = ctypes.CDLL("libcublas.so.12")
+            blas.cublasSetSmCountTarget.argtypes = [ctypes.c_void_p, ctypes.c_int]
+            blas.cublasSetSmCountTarget.restype = ctypes.c_int
+            rc = blas.cublasSetSmCountTarget(ctypes.c_void_p(torch.cuda.current_blas_handle()), n)
+            if rc != 0:
+                raise RuntimeError(f"cublasSetSmCountTarget -> {rc}")
+        except OSError:
+            pass                                                           # static cuBLAS: the Lt carve-out above still applies
+
+    def close(self):
+        """undo the process-wide SM reservation (tests build several reducers in one process)"""
+        if self.comm_sms > 0 and self.reserve_compute:
+            from . import _lib
+            _lib.load().pvqa_set_reserved_sms(0)
+            if hasattr(torch._C, "_set_sm_carveout_experimental"):
+                torch._C._set_sm_carveout_experimental(None)
+            self.comm_sms = 0
 
     # -- setup -------------------------------------------------------------------
     def broadcast_parameters(self, src: int = 0):
@@ -79,14 +130,25 @@ class GradReducer:
         self._flat, self._views, self._slot = [], [], {}
         for bi, bucket in enumerate(self.buckets):
             dev = bucket[0].device
-            flat = torch.zeros(sum(p.numel() for p in bucket), dtype=torch.float32, device=dev)
+            # every slot starts on a 256-byte boundary: the weight-gradient GEMMs write straight into them, and a
+            # 4-byte-aligned output sends cuBLAS to its slow `align2` kernels (measured: 4 GEMMs, 70 -> 360 us/step)
+            pad = lambda n: (n + 63) // 64 * 64                               # noqa: E731
+            flat = torch.zeros(sum(pad(p.numel()) for p in bucket), dtype=torch.float32, device=dev)
             views, off = [], 0
             for pi, p in enumerate(bucket):
                 views.append(flat[off:off + p.numel()].view_as(p))
                 self._slot[id(p)] = (bi, pi)
-                off += p.numel()
+                off += pad(p.numel())
             self._flat.append(flat)
             self._views.append(views)
+        # launch order == bucket order; the last tail_bytes of it have no backward left to hide behind
+        self._tail = [False] * len(self.buckets)
+        acc = 0
+        for bi in range(len(self.buckets) - 1, -1, -1):
+            acc += self._flat[bi].numel() * 4
+            self._tail[bi] = True
+            if acc >= self.tail_bytes:
+                break
         self._pending = [len(b) for b in self.buckets]
         self._works = [None] * len(self.buckets)
         self._filled = set()
@@ -109,6 +171,8 @@ class GradReducer:
 
     # -- per-step ------------------------------------------------------------------
     def _on_grad(self, p):
+        if self.comm_sms > 0:
+            self._limit_library_gemms()                 # first hook on the autograd thread: its cuBLAS handle
         bi, pi = self._slot[id(p)]
         view = self._views[bi][pi]
         if p.grad.data_ptr() != view.data_ptr():        # (a producer that wrote into the slot already is a no-op here)
@@ -121,17 +185,15 @@ class GradReducer:
 
     def _launch(self, bi):
         flat = self._flat[bi]
+        pg = self.pg if self._tail[bi] else self.pg_overlap
         if self._native_avg:
-            self._works[bi] = dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.pg, async_op=True)
+            self._works[bi] = dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=pg, async_op=True)
             return
         if self.average:
             flat.div_(self.world)
-        self._works[bi] = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+        self._works[bi] = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=pg, async_op=True)
 
-    def finish(self):
-        """wait for all buckets and expose the averaged gradients as p.grad (bucket views)."""
-        if self.world == 1:
-            return
+    def _flush_unlaunched(self):
         for bi, bucket in enumerate(self.buckets):
             if self._pending[bi] != 0:
                 # parameters that received no gradient this step contribute zeros
@@ -139,12 +201,48 @@ class GradReducer:
                     if (bi, pi) not in self._filled:
                         self._views[bi][pi].zero_()
                 self._launch(bi)
-        for w in self._works:
-            if w is not None:
-                w.wait()
+                self._pending[bi] = 0
+
+    def _expose(self, tail):
         for bi, bucket in enumerate(self.buckets):
-            for pi, p in enumerate(bucket):
-                p.grad = self._views[bi][pi]
+            if self._tail[bi] == tail:
+                if self._works[bi] is not None:
+                    self._works[bi].wait()
+                for pi, p in enumerate(bucket):
+                    p.grad = self._views[bi][pi]
+
+    def _reset(self):
         self._pending = [len(b) for b in self.buckets]
         self._works = [None] * len(self.buckets)
         self._filled = set()
+
+    def finish(self):
+        """wait for all buckets and expose the averaged gradients as p.grad (bucket views)."""
+        if self.world == 1:
+            return
+        self._flush_unlaunched()
+        self._expose(False)
+        self._expose(True)
+        self._reset()
+
+    def step_overlapping_tail(self, optimizer):
+        """finish() + optimizer.step(), with the update of everything outside the tail buckets running WHILE the tail
+        all-reduce (the embedding tables: their gradient is the last thing the backward produces, so nothing else is
+        left to hide it behind) is still on the wire.  Adam-family optimizers skip parameters whose grad is None and
+        keep a step count per parameter, so two step() calls over disjoint sets are exactly one step() over the union."""
+        if self.world == 1:
+            optimizer.step()
+            return
+        self._flush_unlaunched()
+        self._expose(False)
+        optimizer.step()                                # tail parameters: grad is None here
+        head = [p for bi, bucket in enumerate(self.buckets) if not self._tail[bi] for p in bucket]
+        for p in head:
+            p.grad = None
+        self._expose(True)
+        optimizer.step()
+        for bi, bucket in enumerate(self.buckets):      # leave every averaged gradient visible, as finish() does
+            if not self._tail[bi]:
+                for pi, p in enumerate(bucket):
+                    p.grad = self._views[bi][pi]
+        self._reset()

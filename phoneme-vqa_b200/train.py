@@ -70,8 +70,9 @@ class TrainStep:
         self.optim.zero_grad(set_to_none=True)
         loss.backward()
         if self.reducer is not None:
-            self.reducer.finish()
-        self.optim.step()
+            self.reducer.step_overlapping_tail(self.optim)
+        else:
+            self.optim.step()
         return loss
 
     def eager(self, batch):

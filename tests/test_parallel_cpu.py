@@ -76,3 +76,55 @@ def test_two_rank_gradients_equal_single_process_global_batch():
     ref2 = [p.grad for p in list(model.parameters())[2:] if p.requires_grad]
     for a, b in zip(grads2, ref2):
         torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
+
+
+def _worker_tail(rank, world, store_path, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), GLOO_SOCKET_IFNAME="lo")
+    dist.init_process_group("gloo", init_method="file://" + store_path, rank=rank, world_size=world)
+    import phoneme_vqa_b200.parallel as par
+    model = _make_model()
+    red = par.GradReducer(model, bucket_mb=0.002, tail_mb=0.003)     # several buckets, the last two are "tail"
+    red.broadcast_parameters(0)
+    assert any(red._tail) and not all(red._tail)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2, betas=(0.9, 0.98), eps=1e-9)
+    g = torch.Generator().manual_seed(100)
+    x = torch.randn(8, 16, generator=g)
+    y = torch.randn(8, 4, generator=g)
+    xs, ys = x[rank * 4:(rank + 1) * 4], y[rank * 4:(rank + 1) * 4]
+    for _ in range(3):
+        opt.zero_grad(set_to_none=True)
+        torch.nn.functional.mse_loss(model(xs), ys).backward()
+        red.step_overlapping_tail(opt)
+        assert all(p.grad is not None for p in model.parameters() if p.requires_grad)
+    if rank == 0:
+        q.put(([p.detach().numpy().copy() for p in model.parameters()],      # numpy: pickled by value
+               [int(opt.state[p]["step"]) for p in model.parameters() if p.requires_grad]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_split_optimizer_step_around_the_tail_buckets_is_one_adam_step():
+    """step_overlapping_tail = two optimizer.step() calls over disjoint parameter sets (everything but the tail
+    buckets first, the tail once its all-reduce has landed): must equal single-process Adam on the global batch."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    with tempfile.TemporaryDirectory() as tmp:
+        procs = [ctx.Process(target=_worker_tail, args=(r, 2, os.path.join(tmp, "store"), q)) for r in range(2)]
+        for p in procs:
+            p.start()
+        params, steps = q.get(timeout=300)
+        for p in procs:
+            p.join(timeout=120)
+            assert p.exitcode == 0
+    assert steps == [3] * len(steps)                                  # every parameter stepped exactly once per iteration
+    model = _make_model()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2, betas=(0.9, 0.98), eps=1e-9)
+    g = torch.Generator().manual_seed(100)
+    x = torch.randn(8, 16, generator=g)
+    y = torch.randn(8, 4, generator=g)
+    for _ in range(3):
+        opt.zero_grad(set_to_none=True)
+        torch.nn.functional.mse_loss(model(x), y).backward()
+        opt.step()
+    for a, b in zip(params, model.parameters()):
+        torch.testing.assert_close(torch.from_numpy(a), b.detach(), rtol=1e-4, atol=1e-6)

@@ -1,6 +1,6 @@
 """Data-parallel gradient exchange over NCCL: two ranks, each on its own GPU, run the
 CUDA-graph-captured TrainStep with parallel.GradReducer on their shard; the averaged gradients every rank ends up
-with must equal the gradients of ONE process on the global batch.  Skipped on boxes with fewer than two GPUs (the
+with must equal the mean of the gradients ONE process computes on each shard in turn (data-parallel semantics).  Skipped on boxes with fewer than two GPUs (the
 gloo version of the same check runs on CPU in test_parallel_cpu.py)."""
 import os
 import tempfile
@@ -32,7 +32,6 @@ def _model_and_batch(dev):
     model = model.to(dev)
     model.train(); _no_dropout(model)
     model.set_compute_dtype(torch.bfloat16)
-    # equal target lengths on both shards: the mean of the per-rank token means is then the global token mean
     batch = ref_model.synthetic_batch(4, cfg, T=17, L_ocr=20, L_q=8, V_sub=VOCAB, seed=11, image=32)
     return model, batch
 
@@ -66,15 +65,21 @@ def test_graph_captured_nccl_gradients_equal_the_global_batch():
     out = os.path.join(tmp, "grads.pt")
     mp.spawn(_worker, args=(2, os.path.join(tmp, "store"), out), nprocs=2, join=True)
     got = torch.load(out)
+    # data-parallel semantics (what torch DDP computes): the mean over ranks of each rank's own mean-token loss
+    # gradient.  (Not the gradient of the global batch's token mean: the shards hold different numbers of targets.)
     model, batch = _model_and_batch(torch.device("cuda", 0))
-    b = {k: v.to("cuda:0") for k, v in batch.items()}
-    labels = b["label_ids"]
-    loss = model.forward_loss(b["pixel_values"], b["coordinates"], b["input_ids"], labels[:, :-1], b["src_attention_mask"],
-                              b["label_attention_mask"][:, :-1], b["ocr_attention_mask"], b["tokenized_ocr"],
-                              targets=labels[:, 1:], ignore_index=2)
-    loss.backward()
-    ref = {k: p.grad.detach().float().cpu() for k, p in model.named_parameters() if p.grad is not None}
+    ref = None
+    for r in range(2):
+        b = {k: v[r * 2:(r + 1) * 2].to("cuda:0") for k, v in batch.items()}
+        labels = b["label_ids"]
+        model.zero_grad(set_to_none=True)
+        loss = model.forward_loss(b["pixel_values"], b["coordinates"], b["input_ids"], labels[:, :-1], b["src_attention_mask"],
+                                  b["label_attention_mask"][:, :-1], b["ocr_attention_mask"], b["tokenized_ocr"],
+                                  targets=labels[:, 1:], ignore_index=2)
+        loss.backward()
+        g = {k: p.grad.detach().float().cpu() / 2 for k, p in model.named_parameters() if p.grad is not None}
+        ref = g if ref is None else {k: ref[k] + g[k] for k in g}
     assert set(ref) == set(got)
-    for k in ref:
-        err = float((got[k] - ref[k]).norm() / (ref[k].norm() + 1e-12))
-        assert err <= 2e-2, (k, err)          # bf16 compute on different batch splits; exact in exact arithmetic
+    worst = max(((k, float((got[k] - ref[k]).norm() / (ref[k].norm() + 1e-12))) for k in ref), key=lambda t: t[1])
+    print(f"[2-rank NCCL, graph-captured] worst relative gradient difference to the mean of the per-shard gradients: {worst}")
+    assert worst[1] <= 2e-3, worst            # same kernels on the same shards: only atomics order and the fp32 AVG differ
