@@ -262,7 +262,7 @@ def run_b200_arm(args):
     model.set_compute_dtype(torch.bfloat16 if args.dtype == "bf16" else torch.float32)
     model.train()
     ops.manual_seed(1234 + rank)
-    reducer = parallel.GradReducer(model, bucket_mb=32.0, comm_sms=args.comm_sms if world > 1 else 0)
+    reducer = parallel.GradReducer(model, bucket_mb=32.0, attn_bwd_waves=args.attn_bwd_waves)
     reducer.broadcast_parameters(0)
     trainer = train.TrainStep(model, reducer if world > 1 else None, lr=5e-5, betas=(0.9, 0.98), eps=1e-9,
                               warmup_iters=2000, ignore_index=ignore_index, use_graph=not args.no_graph,
@@ -360,7 +360,7 @@ def run_b200_arm(args):
             "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": workload,
                        "global_batch": world * B,
-                       "parallelism": f"dp{world}", "weights": "random-init", "comm_sms": reducer.comm_sms,
+                       "parallelism": f"dp{world}", "weights": "random-init", "attn_bwd_waves": reducer.attn_bwd_waves,
                        "eager_gpu_samples_s": _eager_gpu(args),
                        "launch": "eager" if args.no_graph else "one CUDA graph per step",
                        "l2": "no flush: per-step working set (0.9 GB weights+Adam state read, >10 GB activations) "
@@ -474,8 +474,8 @@ def main():
                     help="phonolatr = the headline metric (BASELINE config 3's per-GPU shard); the others are the "
                          "sibling configs 2, 4 and 5")
     ap.add_argument("--image", type=int, default=224, choices=[224, 384], help="phonoprestu: ViT input size")
-    ap.add_argument("--comm-sms", type=int, default=0,
-                    help="N > 1: SMs left to the NCCL all-reduces that overlap the backward (0 = NCCL's own choice)")
+    ap.add_argument("--attn-bwd-waves", type=int, default=None,
+                    help="N > 1: CTAs per SM of the attention backward (default: 1 up to 2 ranks, 4 beyond)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of one CUDA graph")
     args = ap.parse_args()
     _quiet_stdout()

@@ -50,11 +50,12 @@ int64_t pvqa_launch_count(void);
  * Philox offset it was launched with, so a CUDA graph capturing a whole training step draws fresh masks on
  * each replay (the caller increments the counter between replays).  NULL (default) disables it. */
 int pvqa_set_rng_step_counter(const uint64_t* device_counter);
-/* Data-parallel runs: leave `n` SMs (0..64, default 0) to the NCCL kernels that overlap the
- * backward.  Every grid of the library is then sized for (SM count - n); without it the persistent one-CTA-per-SM
- * attention kernels wait a whole kernel duration for the SMs a collective occupies.  Affects subsequent launches (and
- * therefore CUDA graphs captured afterwards). */
-int pvqa_set_reserved_sms(int n);
+/* Data-parallel runs: cut the persistent attention backward into k CTAs per SM (1..16, default
+ * 1 = one static item range per SM).  The NCCL all-reduces that overlap the backward hold some SMs for part of a
+ * launch; with k = 1 the CTAs that were meant for those SMs queue behind the collective with a whole range of work
+ * (measured at 8 ranks: 235 -> 327 us per launch), with k = 4 the block scheduler spreads the finer ranges over the
+ * SMs that are free.  Affects subsequent launches (and therefore CUDA graphs captured afterwards). */
+int pvqa_set_attn_bwd_waves(int k);
 
 /* ------------------------------------------------------------------------
  * K1  fused multimodal embedding

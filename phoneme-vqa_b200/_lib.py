@@ -82,7 +82,7 @@ _SIGNATURES = {
     "pvqa_last_error": (c_char_p, []),
     "pvqa_launch_count": (c_int64, []),
     "pvqa_set_rng_step_counter": (c_int, [_vp]),
-    "pvqa_set_reserved_sms": (c_int, [c_int]),
+    "pvqa_set_attn_bwd_waves": (c_int, [c_int]),
     "pvqa_embed_mm_fwd": (c_int, [_vp] * 7 + [POINTER(c_void_p), _vp, _vp] + _i64x(7) + [c_int, c_int, _vp, _vp]),
     "pvqa_embed_mm_bwd": (c_int, [_vp] * 5 + [POINTER(c_void_p)] + _i64x(7) + [c_int, _vp]),
     "pvqa_embed_tgt_fwd": (c_int, [_vp] * 6 + _i64x(8) + [c_int, c_int, _f, c_uint64, c_uint64, _vp, _vp]),

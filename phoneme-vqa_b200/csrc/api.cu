@@ -17,7 +17,7 @@ int fail(int code, const char* fmt, ...) {
 
 std::atomic<long long> g_launch_count{0};
 const unsigned long long* g_rng_base = nullptr;
-static std::atomic<int> g_reserved_sms{0};
+std::atomic<int> g_attn_bwd_waves{1};
 
 int num_sms() {
   // cached per device id; the library is used with one device per process (one rank per GPU)
@@ -31,10 +31,7 @@ int num_sms() {
       cached_dev = dev;
     }
   }
-  // SMs left to a concurrent communication kernel (pvqa_set_reserved_sms): every grid of this library, the persistent
-  // one-CTA-per-SM attention kernels above all, is sized for the remaining ones
-  const int r = g_reserved_sms.load(std::memory_order_relaxed);
-  return cached_sms - r > 8 ? cached_sms - r : cached_sms;
+  return cached_sms;
 }
 
 }  // namespace pvqa
@@ -42,9 +39,9 @@ int num_sms() {
 extern "C" int pvqa_abi_version(void) { return PVQA_ABI_VERSION; }
 extern "C" const char* pvqa_last_error(void) { return pvqa::last_error_buf(); }
 extern "C" int64_t pvqa_launch_count(void) { return (int64_t)pvqa::g_launch_count.load(); }
-extern "C" int pvqa_set_reserved_sms(int n) {
-  if (n < 0 || n > 64) return pvqa::fail(PVQA_ERR_SHAPE, "pvqa_set_reserved_sms: %d is outside 0..64", n);
-  pvqa::g_reserved_sms.store(n);
+extern "C" int pvqa_set_attn_bwd_waves(int k) {
+  if (k < 1 || k > 16) return pvqa::fail(PVQA_ERR_SHAPE, "pvqa_set_attn_bwd_waves: %d is outside 1..16", k);
+  pvqa::g_attn_bwd_waves.store(k);
   return PVQA_OK;
 }
 extern "C" int pvqa_set_rng_step_counter(const uint64_t* device_counter) {

@@ -310,8 +310,11 @@ extern "C" int pvqa_attn_bwd(const void* q, const void* k, const void* v, const 
     if (e != cudaSuccess) return fail(PVQA_ERR_CUDA, "attn_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set[vi] = true;
   }
-  // persistent: one CTA per SM walks a contiguous range of (head, key tile, batch) items
-  const int64_t max_ctas = num_sms();
+  // persistent: one CTA per SM walks a contiguous range of (head, key tile, batch) items.  With waves = k > 1
+  // (pvqa_set_attn_bwd_waves, data-parallel runs) the same ranges are cut k times finer and the hardware hands the CTAs
+  // to SMs as they free up: an SM that a concurrent NCCL kernel holds for part of the launch then costs its share of
+  // the work, not a whole static range queued behind it.
+  const int64_t max_ctas = (int64_t)num_sms() * g_attn_bwd_waves.load(std::memory_order_relaxed);
   dim3 grid((unsigned)(n_items < max_ctas ? n_items : max_ctas));
   kern<<<grid, kBThreads, smem_bytes, st>>>(tq, tk, tv, tdo, tdq, p);
   count_launch();

@@ -17,6 +17,7 @@ int fail(int code, const char* fmt, ...);     // formats into last_error_buf, re
 extern std::atomic<long long> g_launch_count;
 inline void count_launch(int n = 1) { g_launch_count.fetch_add(n, std::memory_order_relaxed); }
 int num_sms();                                // SM count of the current device (cached)
+extern std::atomic<int> g_attn_bwd_waves;     // pvqa_set_attn_bwd_waves: CTAs per SM the attention backward is cut into
 // Optional device-resident dropout step counter (pvqa_set_rng_step_counter): every dropout kernel adds
 // *g_rng_base to its Philox offset, so a CUDA-graph replay of a whole training step draws fresh masks
 // without re-capturing (the host-side offsets are baked into the graph, the counter is not).

@@ -35,68 +35,38 @@ def grad_slot(param):
 
 class GradReducer:
     def __init__(self, module: torch.nn.Module, bucket_mb: float = 32.0, process_group=None, average: bool = True,
-                 comm_sms: int = 0, tail_mb: float = 160.0, reserve_compute: bool = True):
-        """comm_sms > 0 (NCCL only): the all-reduces that overlap the backward run on a communicator capped at
-        `comm_sms` CTAs, and the compute side leaves that many SMs free (libpvqa grids via pvqa_set_reserved_sms, the
-        library GEMMs via cuBLAS' SM-count target) so that persistent one-CTA-per-SM kernels are not queued behind a
-        collective.  The last `tail_mb` of gradients (the embedding tables: nothing is left to overlap them with) go
-        over the uncapped communicator."""
+                 tail_mb: float = 160.0, attn_bwd_waves: int | None = None):
+        """tail_mb: the last `tail_mb` of gradients in launch order (the embedding tables: the backward produces them
+        last, nothing is left to hide their all-reduce behind) are the "tail"; step_overlapping_tail() updates every
+        other parameter while the tail is still on the wire.
+        attn_bwd_waves: CTAs per SM the persistent attention backward is cut into while collectives share the GPU
+        (pvqa_set_attn_bwd_waves).  Default: 1 up to 2 ranks, 4 beyond (profiles/r02_ddp_timeline_n8.txt)."""
         self.module = module
         self.bucket_bytes = int(bucket_mb * 1024 * 1024)
         self.pg = process_group
         self.average = average
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        nccl = dist.is_initialized() and dist.get_backend(process_group) == "nccl"
         # NCCL averages inside the collective; gloo (CPU tests) has no AVG: divide, then sum
-        self._native_avg = bool(average and dist.is_initialized() and dist.get_backend(process_group) == "nccl")
-        self.comm_sms = int(comm_sms) if (self._native_avg or (dist.is_initialized() and dist.get_backend(process_group) == "nccl")) and self.world > 1 else 0
+        self._native_avg = bool(average and nccl)
         self.tail_bytes = int(tail_mb * 1024 * 1024)
-        self.pg_overlap = process_group
-        self._sm_threads = set()
-        if self.comm_sms > 0:
-            opts = dist.ProcessGroupNCCL.Options()
-            opts.config.max_ctas = self.comm_sms
-            opts.config.min_ctas = min(self.comm_sms, 4)
-            self.pg_overlap = dist.new_group(backend="nccl", pg_options=opts)
-            self.reserve_compute = bool(reserve_compute)
-            if self.reserve_compute:
-                from . import _lib
-                _lib.check(_lib.load().pvqa_set_reserved_sms(self.comm_sms), "pvqa_set_reserved_sms")
-                self._limit_library_gemms()
+        self.attn_bwd_waves = 1
+        if nccl and self.world > 1:
+            self.attn_bwd_waves = int(attn_bwd_waves) if attn_bwd_waves is not None else (4 if self.world > 2 else 1)
+            from . import _lib
+            _lib.check(_lib.load().pvqa_set_attn_bwd_waves(self.attn_bwd_waves), "pvqa_set_attn_bwd_waves")
         self._hooks = []
+        self._unused = None          # (bucket, slot) pairs that received no gradient in the first step
         self.rebuild()
         global _ACTIVE
         _ACTIVE = self
 
-    def _limit_library_gemms(self):
-        """cuBLAS / cuBLASLt SM-count target for the calling thread's handle (forward thread and the autograd thread
-        each own one).  Called once per thread; cheap."""
-        import threading
-        tid = threading.get_ident()
-        if tid in self._sm_threads or self.comm_sms <= 0 or not self.reserve_compute:
-            return
-        self._sm_threads.add(tid)
-        n = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count - self.comm_sms
-        if hasattr(torch._C, "_set_sm_carveout_experimental"):
-            torch._C._set_sm_carveout_experimental(self.comm_sms)          # cuBLASLt paths (matmul descriptors)
-        try:
-            import ctypes
-            blas = ctypes.CDLL("libcublas.so.12")
-            blas.cublasSetSmCountTarget.argtypes = [ctypes.c_void_p, ctypes.c_int]
-            blas.cublasSetSmCountTarget.restype = ctypes.c_int
-            rc = blas.cublasSetSmCountTarget(ctypes.c_void_p(torch.cuda.current_blas_handle()), n)
-            if rc != 0:
-                raise RuntimeError(f"cublasSetSmCountTarget -> {rc}")
-        except OSError:
-            pass                                                           # static cuBLAS: the Lt carve-out above still applies
-
     def close(self):
-        """undo the process-wide SM reservation (tests build several reducers in one process)"""
-        if self.comm_sms > 0 and self.reserve_compute:
+        """undo the process-wide launch setting (tests build several reducers in one process)"""
+        if self.attn_bwd_waves != 1:
             from . import _lib
-            _lib.load().pvqa_set_reserved_sms(0)
-            if hasattr(torch._C, "_set_sm_carveout_experimental"):
-                torch._C._set_sm_carveout_experimental(None)
-            self.comm_sms = 0
+            _lib.load().pvqa_set_attn_bwd_waves(1)
+            self.attn_bwd_waves = 1
 
     # -- setup -------------------------------------------------------------------
     def broadcast_parameters(self, src: int = 0):
@@ -149,6 +119,7 @@ class GradReducer:
             self._tail[bi] = True
             if acc >= self.tail_bytes:
                 break
+        self._unused = None
         self._pending = [len(b) for b in self.buckets]
         self._works = [None] * len(self.buckets)
         self._filled = set()
@@ -171,9 +142,10 @@ class GradReducer:
 
     # -- per-step ------------------------------------------------------------------
     def _on_grad(self, p):
-        if self.comm_sms > 0:
-            self._limit_library_gemms()                 # first hook on the autograd thread: its cuBLAS handle
         bi, pi = self._slot[id(p)]
+        if self._unused and (bi, pi) in self._unused:
+            raise RuntimeError("GradReducer: a parameter that received no gradient in the first step received one now; "
+                               "its bucket may already be on the wire.  Call rebuild() when the used set changes.")
         view = self._views[bi][pi]
         if p.grad.data_ptr() != view.data_ptr():        # (a producer that wrote into the slot already is a no-op here)
             view.copy_(p.grad)
@@ -185,23 +157,27 @@ class GradReducer:
 
     def _launch(self, bi):
         flat = self._flat[bi]
-        pg = self.pg if self._tail[bi] else self.pg_overlap
         if self._native_avg:
-            self._works[bi] = dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=pg, async_op=True)
+            self._works[bi] = dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.pg, async_op=True)
             return
         if self.average:
             flat.div_(self.world)
-        self._works[bi] = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=pg, async_op=True)
+        self._works[bi] = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
 
     def _flush_unlaunched(self):
-        for bi, bucket in enumerate(self.buckets):
-            if self._pending[bi] != 0:
-                # parameters that received no gradient this step contribute zeros
-                for pi in range(len(bucket)):
-                    if (bi, pi) not in self._filled:
-                        self._views[bi][pi].zero_()
-                self._launch(bi)
-                self._pending[bi] = 0
+        """Buckets still waiting for a gradient at the end of the backward hold parameters the loss does not reach
+        (e.g. layer 0's relative_attention_bias under an external position bias).  The first step finds them here
+        and launches those buckets late — behind the tail on the in-order NCCL stream; from then on they are known
+        (`_unused`), contribute zeros, and their buckets go out as soon as the live gradients are in."""
+        late = [bi for bi in range(len(self.buckets)) if self._pending[bi] != 0]
+        if self._unused is None:
+            self._unused = {(bi, pi) for bi in late for pi in range(len(self.buckets[bi])) if (bi, pi) not in self._filled}
+        for bi in late:
+            for pi in range(len(self.buckets[bi])):
+                if (bi, pi) not in self._filled:
+                    self._views[bi][pi].zero_()
+            self._launch(bi)
+            self._pending[bi] = 0
 
     def _expose(self, tail):
         for bi, bucket in enumerate(self.buckets):
@@ -212,7 +188,8 @@ class GradReducer:
                     p.grad = self._views[bi][pi]
 
     def _reset(self):
-        self._pending = [len(b) for b in self.buckets]
+        unused = self._unused or ()
+        self._pending = [len(b) - sum(1 for pi in range(len(b)) if (bi, pi) in unused) for bi, b in enumerate(self.buckets)]
         self._works = [None] * len(self.buckets)
         self._filled = set()
 

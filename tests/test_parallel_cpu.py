@@ -37,7 +37,7 @@ def _worker(rank, world, store_path, q):
     loss = torch.nn.functional.mse_loss(model(xs), ys)
     loss.backward()
     red.finish()
-    grads = [p.grad.clone() for p in model.parameters() if p.requires_grad]
+    grads = [p.grad.numpy().copy() for p in model.parameters() if p.requires_grad]   # numpy: pickled by value
     # toggle the trainable set (encoder freeze, PhonemeLaTr_Executor.py:152-159) and make sure re-bucketing works
     for p in model[0].parameters():
         p.requires_grad = False
@@ -46,7 +46,7 @@ def _worker(rank, world, store_path, q):
     loss = torch.nn.functional.mse_loss(model(xs), ys)
     loss.backward()
     red.finish()
-    grads2 = [p.grad.clone() for p in model.parameters() if p.requires_grad]
+    grads2 = [p.grad.numpy().copy() for p in model.parameters() if p.requires_grad]
     if rank == 0:
         q.put((grads, grads2))
     dist.barrier()
@@ -72,10 +72,10 @@ def test_two_rank_gradients_equal_single_process_global_batch():
     ref = [p.grad for p in model.parameters() if p.requires_grad]
     assert len(ref) == len(grads)
     for a, b in zip(grads, ref):
-        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(torch.from_numpy(a), b, rtol=1e-5, atol=1e-6)
     ref2 = [p.grad for p in list(model.parameters())[2:] if p.requires_grad]
     for a, b in zip(grads2, ref2):
-        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(torch.from_numpy(a), b, rtol=1e-5, atol=1e-6)
 
 
 def _worker_tail(rank, world, store_path, q):

@@ -1,7 +1,7 @@
 """Kernel timeline of one data-parallel training step: where the NCCL all-reduces sit against
 the backward, what they run next to, and how much of them is exposed after the last compute kernel.
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
-        tools/ddp_timeline.py [--comm-sms K] [--out gpurun_out/ddp_timeline_nN]
+        tools/ddp_timeline.py [--waves K] [--out gpurun_out/ddp_timeline_nN]
 Rank 0 profiles 2 graph replays with torch.profiler (CUPTI kernel activity), writes <out>.txt (summary) and
 <out>.kernels.json (name, stream, start, duration of every kernel of ONE step)."""
 import argparse
@@ -18,8 +18,7 @@ import phoneme_vqa_b200 as pv  # noqa: E402
 from phoneme_vqa_b200 import models, ops, parallel, synthetic, train  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--comm-sms", type=int, default=0)
-ap.add_argument("--no-reserve", action="store_true", help="cap the NCCL CTAs only; compute grids keep every SM")
+ap.add_argument("--waves", type=int, default=None, help="attention-backward CTAs per SM (GradReducer default if omitted)")
 ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--out", default="gpurun_out/ddp_timeline")
 args = ap.parse_args()
@@ -35,7 +34,7 @@ model.train()
 ops.manual_seed(1234 + rank)
 reducer = None
 if world > 1:
-    reducer = parallel.GradReducer(model, bucket_mb=32.0, comm_sms=args.comm_sms, reserve_compute=not args.no_reserve)
+    reducer = parallel.GradReducer(model, bucket_mb=32.0, attn_bwd_waves=args.waves)
     reducer.broadcast_parameters(0)
 tr = train.TrainStep(model, reducer, lr=5e-5, betas=(0.9, 0.98), eps=1e-9, warmup_iters=2000, ignore_index=synthetic.PAD_ID)
 batches = [synthetic.phoneme_latr_batch(args.batch, cfg.vocab_size, seed=1234 + rank * 1000 + i, device=dev) for i in range(2)]
@@ -79,7 +78,7 @@ if rank == 0:
     adam = [c for c in comp if "multi_tensor" in c[2] or "adam" in c[2].lower()]
     first_adam = min((c[0] for c in adam), default=end)
     last_bwd = max((c[0] + c[1] for c in comp if c[0] < first_adam), default=0.0)
-    lines = [f"world {world}  comm_sms {args.comm_sms}  step {ms_step:.3f} ms (CUDA events, 10 replays)  "
+    lines = [f"world {world}  attn_bwd_waves {reducer.attn_bwd_waves if reducer else 1}  step {ms_step:.3f} ms (CUDA events, 10 replays)  "
              f"profiled step span {end / 1e3:.3f} ms  kernels {len(comp)} compute + {len(nccl)} nccl",
              inter,
              f"compute kernel time {sum(c[1] for c in comp) / 1e3:.3f} ms   nccl kernel time {sum(c[1] for c in nccl) / 1e3:.3f} ms",

@@ -1,12 +1,14 @@
 #!/usr/bin/env bash
-# N-rank check of the data-parallel path: NCCL gradient test, kernel timeline, bench at N and at 1 on the same box
+# N-rank check of the data-parallel path: kernel timelines (attention backward cut into 1 and 4 CTAs per SM), bench at N and at 1
 set -u
 N=${1:-2}
 mkdir -p gpurun_out
-P=29560
+P=29600
 run() { P=$((P+1)); timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $P "$@"; }
-timeout 600 python -m pytest tests/test_parallel_gpu.py -m gpu -q -s > gpurun_out/tests_parallel.log 2>&1; echo "tests_parallel rc=$?"; grep -E "passed|failed|skipped|\[2-rank|Error|assert" gpurun_out/tests_parallel.log | tail -n 6
-run tools/ddp_timeline.py --out gpurun_out/ddp_timeline_n${N} > gpurun_out/tl.log 2>&1; echo "timeline rc=$?"; head -n 3 gpurun_out/ddp_timeline_n${N}.txt || tail -n 5 gpurun_out/tl.log
+for W in 1 4; do
+run tools/ddp_timeline.py --waves $W --out gpurun_out/ddp_timeline_n${N}_waves$W > gpurun_out/tl_w$W.log 2>&1; echo "timeline waves $W rc=$?"; head -n 4 gpurun_out/ddp_timeline_n${N}_waves$W.txt | cut -c1-200 || tail -n 5 gpurun_out/tl_w$W.log
+grep "attn_bwd_kernel" gpurun_out/ddp_timeline_n${N}_waves$W.txt | cut -c1-160
+done
 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err; echo "bench n1 rc=$?"
 run bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; echo "bench n$N rc=$?"
 python - <<PY
@@ -14,7 +16,7 @@ import json
 for n in (1, $N):
     try:
         d = json.loads(open(f"gpurun_out/bench_n{n}.json").read().strip().splitlines()[-1])
-        print(n, "value", round(d["value"], 1), "ms/step", round(d["ms_per_step"], 3), "e2e", round(d["e2e"]["value"], 1), "per-gpu", round(d["value"] / n, 1))
+        print(n, "value", round(d["value"], 1), "ms/step", round(d["ms_per_step"], 3), "e2e", round(d["e2e"]["value"], 1), "per-gpu", round(d["value"] / n, 1), d["config"].get("attn_bwd_waves"))
     except Exception as e:
         print(n, "no line", e)
 PY
