@@ -50,6 +50,9 @@ class GradReducer:
         # NCCL averages inside the collective; gloo (CPU tests) has no AVG: divide, then sum
         self._native_avg = bool(average and nccl)
         self.tail_bytes = int(tail_mb * 1024 * 1024)
+        # the tail travels on its own communicator (own NCCL stream): waiting for the head buckets must not mean
+        # waiting for everything that was queued behind them on one in-order stream
+        self.pg_tail = dist.new_group(backend="nccl") if (nccl and self.world > 1 and True) else process_group
         self.attn_bwd_waves = 1
         if nccl and self.world > 1:
             self.attn_bwd_waves = int(attn_bwd_waves) if attn_bwd_waves is not None else (4 if self.world > 2 else 1)
@@ -75,7 +78,9 @@ class GradReducer:
         for t in list(self.module.parameters()) + list(self.module.buffers()):
             dist.broadcast(t.data, src=src, group=self.pg)
 
-    def rebuild(self):
+    def rebuild(self, order=None):
+        """order: positions into the canonical (reverse-registration) parameter list, the sequence in which the
+        gradients became ready in a real backward.  None = canonical order, and the first step learns the real one."""
         for h in self._hooks:
             h.remove()
         self._hooks = []
@@ -86,6 +91,10 @@ class GradReducer:
                 params.append(p)
         params.reverse()
         self.trainable_signature = tuple(id(p) for p in params)
+        self._canonical = list(params)
+        self._arrival = None if order is not None else []   # [] = learning
+        if order is not None:
+            params = [params[i] for i in order]
         self.buckets = []
         cur, cur_bytes = [], 0
         for p in params:
@@ -146,6 +155,8 @@ class GradReducer:
         if self._unused and (bi, pi) in self._unused:
             raise RuntimeError("GradReducer: a parameter that received no gradient in the first step received one now; "
                                "its bucket may already be on the wire.  Call rebuild() when the used set changes.")
+        if self._arrival is not None:
+            self._arrival.append(id(p))
         view = self._views[bi][pi]
         if p.grad.data_ptr() != view.data_ptr():        # (a producer that wrote into the slot already is a no-op here)
             view.copy_(p.grad)
@@ -157,12 +168,13 @@ class GradReducer:
 
     def _launch(self, bi):
         flat = self._flat[bi]
+        pg = self.pg_tail if self._tail[bi] else self.pg
         if self._native_avg:
-            self._works[bi] = dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.pg, async_op=True)
+            self._works[bi] = dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=pg, async_op=True)
             return
         if self.average:
             flat.div_(self.world)
-        self._works[bi] = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+        self._works[bi] = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=pg, async_op=True)
 
     def _flush_unlaunched(self):
         """Buckets still waiting for a gradient at the end of the backward hold parameters the loss does not reach
@@ -187,7 +199,23 @@ class GradReducer:
                 for pi, p in enumerate(bucket):
                     p.grad = self._views[bi][pi]
 
+    def _adopt_arrival_order(self):
+        """After the first real backward: re-bucket in the order the gradients actually became ready (registration
+        order is a poor guess: the layout tables and the target-side embeddings are registered next to the heads but
+        their gradients are the last thing the backward produces, and a bucket goes out when its LAST gradient is in).
+        Rank 0's order is used everywhere, so every rank builds identical buckets."""
+        pos = {id(p): i for i, p in enumerate(self._canonical)}
+        order = [pos[i] for i in self._arrival]
+        got = set(order)
+        order += [i for i in range(len(self._canonical)) if i not in got]      # never reached by the loss: at the end
+        t = torch.tensor(order, dtype=torch.int64, device=self._flat[0].device)
+        dist.broadcast(t, src=0, group=self.pg)
+        self.rebuild(order=[int(i) for i in t.tolist()])
+
     def _reset(self):
+        if self._arrival:                                  # the learning step just ended
+            self._adopt_arrival_order()
+            return
         unused = self._unused or ()
         self._pending = [len(b) - sum(1 for pi in range(len(b)) if (bi, pi) in unused) for bi, b in enumerate(self.buckets)]
         self._works = [None] * len(self.buckets)

@@ -91,9 +91,14 @@ class TrainStep:
         saved = {}
         for p_, st in self.optim.state.items():
             saved[p_] = {k: v.clone() for k, v in st.items() if torch.is_tensor(v)}
-        s = torch.cuda.Stream()
+        # ONE side stream for the warm-up and the capture: autograd pins every AccumulateGrad node to the stream it was
+        # created on, and the gradient hooks of the reducer keep those nodes alive — created on another stream than the
+        # capture runs on, every gradient would be handed over through a cross-stream sync inside the graph
+        s = self._stream = getattr(self, "_stream", None) or torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
+            if self.reducer is not None and self.reducer.world > 1:
+                self.reducer.rebuild()                  # re-register the hooks: fresh AccumulateGrad nodes, on `s`
             self.lr_t.zero_()
             for _ in range(warmup):
                 self._body(self.static)
@@ -116,7 +121,7 @@ class TrainStep:
         off0 = ops._Rng.offset
         c0 = _lib.launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, stream=s):
             self.static_loss = self._body(self.static)
             self.rng_counter.add_(ops._Rng.offset - off0)      # fresh dropout masks on every replay
         self.launches_per_replay = _lib.launch_count() - c0     # libpvqa kernels inside one replay

@@ -132,26 +132,46 @@ def test_t5_base_dims_forward_loss_backward_match_oracle():
         worst[side] = max(worst[side], (name, err), key=lambda t: t[1])
     print(f"[fp32 mode at T5-base dims] worst gradient error against the gate-matched float64 oracle: {worst}")
     assert worst["target side"][1] <= 1e-3 and worst["encoder side"][1] <= 5e-3, worst
-    # ---- bf16 mode: logits within 1e-2, loss within 1e-3; gradient quality as cosine / relative norm per parameter
+
+
+def test_t5_base_dims_bf16_gradient_quality_against_the_fp32_oracle():
+    """bf16 mode at T5-base dims (12 + 4 layers, d 768, S 327, T 127) with the architecture's own random init (HF
+    `_init_weights`, seeded): the regime the bench and real training start in.  (The deterministic test weights of the
+    fp32 test above make the 12-layer forward chaotic — fp32 rounding alone moves pre-activations by 3e-4 there — so
+    they say nothing about a 2^-9 arithmetic.)  Bars: logits 1e-2 and loss 1e-3 (north_star's bf16 bars; measured 7.7e-3
+    and 1.5e-4), and for EVERY parameter the bf16 gradient points the way the fp32 gradient does (cosine >= 0.99;
+    measured worst 0.9987) with the right length (norm ratio within 3 %; measured worst 1.006) — DESIGN.md section 5."""
+    cfg = ref_model.make_config(vit_config=dict(hidden_size=64, num_hidden_layers=2, num_attention_heads=2,
+                                                intermediate_size=128, image_size=224, patch_size=16), vocab_size=2048)
+    import phoneme_vqa_b200.models as M
+    torch.manual_seed(7)
+    oracle = ref_model.PhonemeLaTr(cfg, *VOCAB)
+    model = M.PhonemeLaTr(cfg, *VOCAB)
+    model.load_state_dict(oracle.state_dict(), strict=True)
+    model = model.to(DEV)
+    batch = ref_model.synthetic_batch(2, cfg, T=127, L_ocr=100, L_q=30, V_sub=VOCAB, seed=21, image=224)
+    oracle.train(); model.train()
+    _no_dropout(oracle); _no_dropout(model)
+    ref_loss = ref_model.phoneme_latr_loss(oracle, batch, 2)
+    ref_loss.backward()
+    ref = dict(oracle.named_parameters())
+    b = _to(batch, DEV)
     with torch.no_grad():
         labels = batch["label_ids"]
         ref_logits = oracle(pixel_values=batch["pixel_values"], coordinates=batch["coordinates"], input_ids=batch["input_ids"],
                             labels=labels[:, :-1], src_attention_mask=batch["src_attention_mask"],
                             label_attention_mask=batch["label_attention_mask"][:, :-1],
                             ocr_attention_mask=batch["ocr_attention_mask"], tokenized_ocr=batch["tokenized_ocr"])
-    model.zero_grad(set_to_none=True)
     model.set_compute_dtype(torch.bfloat16)
     with torch.no_grad():
         lg = model(pixel_values=b["pixel_values"], coordinates=b["coordinates"], input_ids=b["input_ids"],
                    labels=b["label_ids"][:, :-1], src_attention_mask=b["src_attention_mask"],
                    label_attention_mask=b["label_attention_mask"][:, :-1], ocr_attention_mask=b["ocr_attention_mask"],
                    tokenized_ocr=b["tokenized_ocr"])
-    for a, r in zip(lg, ref_logits):
-        err = float((a.float().cpu() - r).norm() / (r.norm() + 1e-12))
-        assert err <= 1e-2, err
-    loss16 = _loss(model, b)
+    logit_err = [float((a.float().cpu() - r).norm() / (r.norm() + 1e-12)) for a, r in zip(lg, ref_logits)]
+    loss16 = _loss(model, b)                       # the one-kernel tcgen05 K4 is on this path (d = 768)
     loss16.backward()
-    assert abs(loss16.item() - ref_loss.item()) <= 1e-3 * abs(ref_loss.item()), (loss16.item(), ref_loss.item())
+    loss_err = abs(loss16.item() - ref_loss.item()) / abs(ref_loss.item())
     report = {}
     for name, p in model.named_parameters():
         if p.grad is None or ref[name].grad is None:
@@ -162,12 +182,12 @@ def test_t5_base_dims_forward_loss_backward_match_oracle():
         report[name] = (float(torch.dot(a, r) / (a.norm() * r.norm() + 1e-30)), float(a.norm() / r.norm()))
     worst_cos = min(report.items(), key=lambda kv: kv[1][0])
     worst_norm = max(report.items(), key=lambda kv: abs(kv[1][1] - 1.0))
-    print(f"[bf16 gradient quality at T5-base dims] {len(report)} parameters; worst cosine {worst_cos}; "
-          f"worst norm ratio {worst_norm}")
-    # the bar: every parameter's bf16 gradient points the way the fp32 gradient does
-    # (cosine >= 0.98) with the right length (norm ratio within 5 %)
-    assert worst_cos[1][0] >= 0.98, worst_cos
-    assert abs(worst_norm[1][1] - 1.0) <= 0.05, worst_norm
+    print(f"[bf16 at T5-base dims, HF init] logits rel err {logit_err}; loss rel err {loss_err:.2e}; {len(report)} parameters; "
+          f"worst gradient cosine {worst_cos}; worst norm ratio {worst_norm}")
+    assert max(logit_err) <= 1e-2, logit_err
+    assert loss_err <= 1e-3, (loss16.item(), ref_loss.item())
+    assert worst_cos[1][0] >= 0.99, worst_cos
+    assert abs(worst_norm[1][1] - 1.0) <= 0.03, worst_norm
 
 
 def _thirty_steps(dtype):
