@@ -52,7 +52,7 @@ class GradReducer:
         self.tail_bytes = int(tail_mb * 1024 * 1024)
         # the tail travels on its own communicator (own NCCL stream): waiting for the head buckets must not mean
         # waiting for everything that was queued behind them on one in-order stream
-        self.pg_tail = dist.new_group(backend="nccl") if (nccl and self.world > 1 and True) else process_group
+        self.pg_tail = dist.new_group(backend="nccl") if (nccl and self.world > 1) else process_group
         self.attn_bwd_waves = 1
         if nccl and self.world > 1:
             self.attn_bwd_waves = int(attn_bwd_waves) if attn_bwd_waves is not None else (4 if self.world > 2 else 1)
