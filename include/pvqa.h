@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PVQA_ABI_VERSION 10
+#define PVQA_ABI_VERSION 11
 
 typedef enum {
   PVQA_OK = 0,
@@ -159,7 +159,9 @@ int pvqa_phoneme_head_ce_fwd(const void* h, const int64_t* targets /* (N,3) stri
  * core/executor/PhonemeLaTr_Executor.py:181-190 on the fused-loss path.
  *   x (N,768) bf16 = decoder output;  W_shared (768,768) bf16, b_shared (768) fp32;  W_k (V_k,256) bf16, b_k (V_k) fp32
  *   writes h_out (N,768) bf16 = shared_lm_head(x) (what pvqa_phoneme_head_ce_bwd recomputes from), loss_sum[3],
- *   count[3], lse (N,3) — same meaning as pvqa_phoneme_head_ce_fwd.  Specialised for d = 768 (slices 256|256|256) and
+ *   count[3], lse (N,3) — same meaning as pvqa_phoneme_head_ce_fwd — and, when the dl_* pointers are given, the
+ *   UNSCALED logit gradients softmax - onehot (zero rows for ignored targets; rows padded to 16 columns, pad = 0):
+ *   the backward needs no recompute kernel, it scales by g / count_k inside its GEMMs.  Specialised for d = 768 (slices 256|256|256) and
  *   sub-vocabularies of at most 192 entries; other shapes: PVQA_ERR_SHAPE (use pvqa_phoneme_head_ce_fwd on the output
  *   of a library GEMM). */
 int pvqa_phoneme_head_fused_fwd(const void* x, const void* W_shared, const float* b_shared,
@@ -168,6 +170,7 @@ int pvqa_phoneme_head_fused_fwd(const void* x, const void* W_shared, const float
                                 const void* W_rhyme, const float* b_rhyme,
                                 const void* W_tone, const float* b_tone,
                                 void* h_out, float* loss_sum /*3*/, int32_t* count /*3*/, float* lse /*N,3*/,
+                                void* dl_onset, void* dl_rhyme, void* dl_tone /* all three or none: (N, round16(V_k)) bf16 */,
                                 int64_t N, int64_t d, int64_t on_dim, int64_t rt_dim,
                                 int64_t V_o, int64_t V_r, int64_t V_t, int64_t ignore_index, void* stream);
 

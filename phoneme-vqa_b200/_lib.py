@@ -27,7 +27,7 @@ NVCC_FLAGS = [
 ]
 
 PVQA_F32, PVQA_BF16 = 0, 1
-ABI_VERSION = 10  # must equal PVQA_ABI_VERSION in include/pvqa.h
+ABI_VERSION = 11  # must equal PVQA_ABI_VERSION in include/pvqa.h
 
 
 def _stale() -> bool:
@@ -89,7 +89,7 @@ _SIGNATURES = {
     "pvqa_embed_tgt_bwd": (c_int, [_vp] * 5 + _i64x(8) + [c_int, _f, c_uint64, c_uint64, _vp]),
     "pvqa_phoneme_head_ce_fwd": (c_int, [_vp, _vp, _i64] + [_vp] * 12 + _i64x(8) + [c_int, c_int, _vp]),
     "pvqa_phoneme_head_ce_bwd": (c_int, [_vp, _vp, _i64] + [_vp] * 12 + _i64x(8) + [c_int, c_int, _vp]),
-    "pvqa_phoneme_head_fused_fwd": (c_int, [_vp, _vp, _vp, _vp, _i64] + [_vp] * 6 + [_vp] * 4 + _i64x(8) + [_vp]),
+    "pvqa_phoneme_head_fused_fwd": (c_int, [_vp, _vp, _vp, _vp, _i64] + [_vp] * 6 + [_vp] * 7 + _i64x(8) + [_vp]),
     "pvqa_vocab_ce_grad": (c_int, [_vp, _vp, _i64, _vp, _vp, _vp] + _i64x(3) + [_vp]),
     "pvqa_attn_fwd": (c_int, [_vp] * 7 + _i64x(5) + _i64x(12) + [_f, c_int, _f, c_uint64, c_uint64, _vp, _vp, _i64, _i64, _vp]),
     "pvqa_attn_bwd": (c_int, [_vp] * 13 + _i64x(5) + _i64x(21) + [_f, c_int, _f, c_uint64, c_uint64, _vp, _vp, _vp, _i64, _i64,

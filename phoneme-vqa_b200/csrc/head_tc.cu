@@ -43,6 +43,7 @@ struct HeadTcParams {
   float* loss_sum;              // [3]  (zero-initialised by the launcher)
   int* count;                   // [3]
   float* lse;                   // (N,3)
+  __nv_bfloat16* dl[3];         // optional (N, round16(V_k)) bf16: softmax - onehot, zero rows for ignored targets
   int N;
   int V[3];
   long long ignore_index;
@@ -219,10 +220,43 @@ phoneme_head_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
         ssum = ssum * __expf(m - mn) + cs;
         m = mn;
       }
-      tc05::tc_fence_before_sync();
-      tc05::mbar_arrive(bar_e2);
       const float lse = m + __logf(ssum);
       const bool valid = live && tgt != p.ignore_index;
+      if (p.dl[k] != nullptr) {
+        // second pass over D2 (still in TMEM): the UNSCALED logit gradient softmax - onehot, bf16, rows padded to 16
+        // columns.  The backward scales by g / count_k (known only when the whole grid is done) inside its small GEMMs.
+        const int vpad = (V + 15) & ~15;
+        __nv_bfloat16* drow = p.dl[k] + (long long)(live ? row : 0) * vpad;
+#pragma unroll 1
+        for (int c = 0; c < nchunk; ++c) {
+          uint32_t r[32];
+          tc05::tmem_ld_32x32(tmem_row + kHW + c * 32, r);
+          tc05::tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int col0 = c * 32 + q * 8;
+            if (col0 < vpad) {
+              float g[8];
+#pragma unroll
+              for (int x = 0; x < 8; ++x) {
+                const int col = col0 + x;
+                float pr = 0.f;
+                if (valid && col < V) {
+                  pr = __expf(__uint_as_float(r[q * 8 + x]) + __ldg(bk + col) - lse);
+                  if ((long long)col == tgt) pr -= 1.f;
+                }
+                g[x] = pr;
+              }
+              uint4 u;
+              u.x = f32x2_to_bf16x2(g[0], g[1]); u.y = f32x2_to_bf16x2(g[2], g[3]);
+              u.z = f32x2_to_bf16x2(g[4], g[5]); u.w = f32x2_to_bf16x2(g[6], g[7]);
+              if (live) *reinterpret_cast<uint4*>(drow + col0) = u;
+            }
+          }
+        }
+      }
+      tc05::tc_fence_before_sync();
+      tc05::mbar_arrive(bar_e2);
       if (live) p.lse[(long long)row * 3 + k] = lse;
       float nll = valid ? lse - tgt_logit : 0.f;
       int cnt = valid ? 1 : 0;
@@ -277,7 +311,8 @@ extern "C" int pvqa_phoneme_head_fused_fwd(const void* x, const void* W_shared, 
                                            const int64_t* targets, int64_t tgt_row_stride,
                                            const void* W_onset, const float* b_onset, const void* W_rhyme,
                                            const float* b_rhyme, const void* W_tone, const float* b_tone, void* h_out,
-                                           float* loss_sum, int32_t* count, float* lse, int64_t N, int64_t d,
+                                           float* loss_sum, int32_t* count, float* lse, void* dl_onset,
+                                           void* dl_rhyme, void* dl_tone, int64_t N, int64_t d,
                                            int64_t on_dim, int64_t rt_dim, int64_t V_o, int64_t V_r, int64_t V_t,
                                            int64_t ignore_index, void* stream) {
   PVQA_REQUIRE(d == kHD && on_dim == kHW && rt_dim == kHW, PVQA_ERR_SHAPE,
@@ -295,6 +330,10 @@ extern "C" int pvqa_phoneme_head_fused_fwd(const void* x, const void* W_shared, 
                    h_out && lse,
                PVQA_ERR_NULL, "phoneme_head_fused: NULL pointer");
   PVQA_REQUIRE(aligned16(h_out) && aligned16(b_shared), PVQA_ERR_ALIGN, "phoneme_head_fused: h_out / b_shared must be 16-byte aligned");
+  PVQA_REQUIRE((dl_onset != nullptr) == (dl_rhyme != nullptr) && (dl_onset != nullptr) == (dl_tone != nullptr), PVQA_ERR_NULL,
+               "phoneme_head_fused: the three logit-gradient outputs come together or not at all");
+  PVQA_REQUIRE(aligned16(dl_onset) && aligned16(dl_rhyme) && aligned16(dl_tone), PVQA_ERR_ALIGN,
+               "phoneme_head_fused: logit-gradient outputs must be 16-byte aligned");
   CUtensorMap tx, tws, tw0, tw1, tw2;
   int rc;
   if ((rc = make_tmap_2d(&tx, x, N, kHD, kHRows, "x"))) return rc;
@@ -306,6 +345,8 @@ extern "C" int pvqa_phoneme_head_fused_fwd(const void* x, const void* W_shared, 
   p.targets = targets; p.tgt_stride = tgt_row_stride; p.b_shared = b_shared;
   p.b_head[0] = b_onset; p.b_head[1] = b_rhyme; p.b_head[2] = b_tone;
   p.h_out = reinterpret_cast<__nv_bfloat16*>(h_out); p.loss_sum = loss_sum; p.count = count; p.lse = lse;
+  p.dl[0] = reinterpret_cast<__nv_bfloat16*>(dl_onset); p.dl[1] = reinterpret_cast<__nv_bfloat16*>(dl_rhyme);
+  p.dl[2] = reinterpret_cast<__nv_bfloat16*>(dl_tone);
   p.N = (int)N; p.V[0] = (int)V_o; p.V[1] = (int)V_r; p.V[2] = (int)V_t; p.ignore_index = ignore_index;
   static bool attr_set = false;
   if (!attr_set) {

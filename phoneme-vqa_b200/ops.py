@@ -842,9 +842,9 @@ class _PhonemeHeadCE(torch.autograd.Function):
 
 
 class _PhonemeHeadFused(torch.autograd.Function):
-    """K4 on tcgen05: loss = 3x CE(heads(shared_lm_head(x))) in one kernel (csrc/head_tc.cu).  The backward recomputes
-    the sub-vocabulary logits from the saved bf16 h (pvqa_phoneme_head_ce_bwd) and leaves the GEMMs of the gradient to
-    the library, exactly like _PhonemeHeadCE + the shared linear's backward."""
+    """K4 on tcgen05: loss = 3x CE(heads(shared_lm_head(x))) in one kernel (csrc/head_tc.cu).  The same kernel leaves
+    the unscaled logit gradients (softmax - onehot, bf16) behind, so the backward is library GEMMs only: the factor
+    g / count_k is folded into the small operands."""
 
     @staticmethod
     def forward(ctx, x, Ws_lp, Ws, bs, targets, W_on, b_on, W_rh, b_rh, W_to, b_to, ignore_index):
@@ -854,53 +854,46 @@ class _PhonemeHeadFused(torch.autograd.Function):
             raise TypeError("targets must be int64 (N,3) with unit inner stride")
         x = x.contiguous()
         N, d = x.shape
-        V_o, on_dim = W_on.shape
-        V_r, rt_dim = W_rh.shape
-        V_t, _ = W_to.shape
+        V = (W_on.shape[0], W_rh.shape[0], W_to.shape[0])
+        on_dim, rt_dim = W_on.shape[1], W_rh.shape[1]
         dev = x.device
         wk = [t.to(torch.bfloat16).contiguous() for t in (W_on, W_rh, W_to)]
-        # biases are consumed at bf16 precision on both sides (the backward kernel recomputes the logits with them)
-        bkl = [t.to(torch.bfloat16).contiguous() for t in (b_on, b_rh, b_to)]
-        bk = [t.to(torch.float32) for t in bkl]
+        # biases are consumed at bf16 precision, like the weights (and like the unfused path)
+        bk = [t.to(torch.bfloat16).to(torch.float32).contiguous() for t in (b_on, b_rh, b_to)]
         bs32 = bs.to(torch.float32).contiguous()
         h = torch.empty((N, d), dtype=torch.bfloat16, device=dev)
         loss_sum = torch.empty(3, dtype=torch.float32, device=dev)
         count = torch.empty(3, dtype=torch.int32, device=dev)
         lse = torch.empty((N, 3), dtype=torch.float32, device=dev)
+        want_grad = any(ctx.needs_input_grad)
+        dls = [torch.empty((N, (v + 15) // 16 * 16), dtype=torch.bfloat16, device=dev) for v in V] if want_grad else [None] * 3
         with torch.cuda.device(dev), _prof("phoneme_head_fused_fwd"):
             check(lib.pvqa_phoneme_head_fused_fwd(_p(x), _p(Ws_lp), _p(bs32), _p(targets), targets.stride(0),
                                                   _p(wk[0]), _p(bk[0]), _p(wk[1]), _p(bk[1]), _p(wk[2]), _p(bk[2]),
-                                                  _p(h), _p(loss_sum), _p(count), _p(lse), N, d, on_dim, rt_dim,
-                                                  V_o, V_r, V_t, int(ignore_index), _stream()),
+                                                  _p(h), _p(loss_sum), _p(count), _p(lse), _p(dls[0]), _p(dls[1]), _p(dls[2]),
+                                                  N, d, on_dim, rt_dim, V[0], V[1], V[2], int(ignore_index), _stream()),
                   "pvqa_phoneme_head_fused_fwd")
         loss = (loss_sum / count.to(torch.float32)).sum()
-        ctx.save_for_backward(x, Ws_lp, h, targets, lse, count, wk[0], bkl[0], wk[1], bkl[1], wk[2], bkl[2])
-        ctx.meta = (N, d, on_dim, rt_dim, V_o, V_r, V_t, int(ignore_index), W_on.dtype, b_on.dtype, bs.dtype)
+        if want_grad:
+            ctx.save_for_backward(x, Ws_lp, h, count, *dls, *wk)
+        ctx.meta = (V, on_dim, rt_dim, W_on.dtype, b_on.dtype, bs.dtype)
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        lib = _lib.load()
-        x, Ws_lp, h, targets, lse, count, W_on, b_on, W_rh, b_rh, W_to, b_to = ctx.saved_tensors
-        N, d, on_dim, rt_dim, V_o, V_r, V_t, ignore_index, w_dtype, b_dtype, bs_dtype = ctx.meta
-        dev = h.device
-        g = g.to(torch.float32).reshape(1).contiguous()
-        dls = [torch.empty((N, V), dtype=h.dtype, device=dev) for V in (V_o, V_r, V_t)]
-        with torch.cuda.device(dev), _prof("phoneme_head_ce_bwd"):
-            check(lib.pvqa_phoneme_head_ce_bwd(_p(h), _p(targets), targets.stride(0), _p(W_on), _p(b_on), _p(W_rh),
-                                               _p(b_rh), _p(W_to), _p(b_to), _p(lse), _p(count), _p(g),
-                                               _p(dls[0]), _p(dls[1]), _p(dls[2]),
-                                               N, d, on_dim, rt_dim, V_o, V_r, V_t, ignore_index,
-                                               _dt(W_on.dtype), _dt(h.dtype), _stream()),
-                  "pvqa_phoneme_head_ce_bwd")
+        x, Ws_lp, h, count, dl0, dl1, dl2, w0, w1, w2 = ctx.saved_tensors
+        V, on_dim, rt_dim, w_dtype, b_dtype, bs_dtype = ctx.meta
+        scale = g.to(torch.float32).reshape(1) / count.to(torch.float32)          # (3,): d loss / d (sum of NLL)_k
         d_h = torch.empty_like(h)
         offs = (0, on_dim, on_dim + rt_dim)
         widths = (on_dim, rt_dim, rt_dim)
         grads = []
-        for dl, W, off, w in zip(dls, (W_on, W_rh, W_to), offs, widths):
-            d_h[:, off:off + w] = dl @ W
-            grads.append(torch.mm(dl.t(), h[:, off:off + w], out_dtype=torch.float32).to(w_dtype))
-            grads.append(dl.sum(0, dtype=torch.float32).to(b_dtype))
+        for k, (dl_pad, W, off, w) in enumerate(zip((dl0, dl1, dl2), (w0, w1, w2), offs, widths)):
+            dl = dl_pad[:, :V[k]]                                                # (N, V_k) view, row stride round16(V_k)
+            hk = h[:, off:off + w]
+            torch.mm(dl, (W.to(torch.float32) * scale[k]).to(torch.bfloat16), out=d_h[:, off:off + w])
+            grads.append((torch.mm(dl.t(), hk, out_dtype=torch.float32) * scale[k]).to(w_dtype))
+            grads.append((dl.sum(0, dtype=torch.float32) * scale[k]).to(b_dtype))
         dx = d_h @ Ws_lp if ctx.needs_input_grad[0] else None
         dWs = torch.mm(d_h.t(), x, out_dtype=torch.float32)
         dbs = col_sum(d_h).to(bs_dtype)
