@@ -343,6 +343,8 @@ def run_b200_arm(args):
                     entry.update({"bound": "tensor", "achieved": ach, "peak": tf, "unit": "TFLOP/s", "frac": ach / tf})
             if name in traffic:
                 entry["traffic"] = traffic[name]          # ncu dram bytes per launch (profiles/traffic.json)
+                # the same launch rated by what ncu saw move to and from DRAM (cold L2) instead of by algorithmic bytes
+                entry["dram_frac"] = traffic[name] / avg_ms / 1e6 / hbm
             kernels[name] = entry
         dom = max((k for k in kernels if "bound" in kernels[k]), key=lambda k: kernels[k]["avg_ms"] * kernels[k]["launches_per_step"],
                   default=None)
@@ -429,17 +431,41 @@ def attention_flops(name, B, cfg):
 
 
 def kernel_algorithmic(B, cfg, S_img=197, L_ocr=100, L_q=30, T=127):
-    """algorithmic bytes / flops per launch of each C-ABI kernel."""
+    """algorithmic bytes / flops per launch of each C-ABI kernel.  Kernels
+    that run at two shapes inside the step (encoder and target-decoder feed-forward) carry the launch-weighted mean,
+    like the measured average they are divided by."""
     d, H, D = cfg.d_model, cfg.num_heads, cfg.d_kv
     S = S_img + L_ocr + L_q
     e_tab, e_act = 4, 2
+    n_enc, n_dec, n_vit = B * S * d, B * T * d, B * S_img * d          # elements of one activation tensor
+    L_enc, L_dec = cfg.num_layers, cfg.num_decoder_layers
+    ff_enc, ff_dec = B * S * cfg.d_ff, B * T * 2048                     # nn.TransformerDecoderLayer default dim_feedforward
+
+    def mix(enc, dec):
+        return (L_enc * enc + L_dec * dec) / (L_enc + L_dec)
+
+    N = B * T
+    head_flops = 2.0 * N * d * d + 2.0 * N * (d // 3) * 278
     return {
         "embed_mm_fwd": ("hbm", B * ((7 * L_ocr + L_q) * (d * e_tab + 8) + S_img * d * e_act) + B * S * d * e_act),
-        "embed_mm_bwd": ("hbm", B * ((L_ocr + L_q) * d * e_act + (7 * L_ocr + L_q) * 8 + 2 * (7 * L_ocr + L_q) * d * 4)),
+        # gradient rows read once + indices + one fp32 reduction per (token, table) row (run-length merged in registers)
+        "embed_mm_bwd": ("hbm", B * ((L_ocr + L_q) * d * e_act + (7 * L_ocr + L_q) * 8 + (7 * L_ocr + L_q) * d * 4)),
         "embed_tgt_fwd": ("hbm", B * T * (3 * 8 + d * 4 + d * 4 + d * 4)),
         "embed_tgt_bwd": ("hbm", B * T * (3 * 8 + d * 4 + 2 * d * 4)),
         "phoneme_head_ce_fwd": ("hbm", B * T * (d * e_act + 3 * 8 + 3 * 4)),
         "phoneme_head_ce_bwd": ("hbm", B * T * (d * e_act + 3 * 8 + 3 * 4 + 278 * e_act)),
+        "phoneme_head_fused_fwd": ("tensor", head_flops),               # shared_lm_head GEMM + three head GEMMs
+        # fp32 residual stream + bf16 update in, stream + bf16 normed row out  /  three gradients in, two out
+        "add_dropout_rms_fwd": ("hbm", n_enc * (4 + 2 + 4 + 2)),
+        "add_dropout_rms_bwd": ("hbm", n_enc * (2 + 4 + 4 + 4 + 2)),
+        "add_dropout_ln_fwd": ("hbm", n_dec * (4 + 2 + 4 + 4 + 2)),
+        "add_dropout_ln_bwd": ("hbm", n_dec * (4 + 2 + 4 + 4 + 2)),
+        "add_ln_lp": ("hbm", n_vit * (2 + 2 + 2 + 2)),                  # frozen ViT: bf16 stream
+        "relu_dropout_fwd": ("hbm", mix(ff_enc, ff_dec) * (2 + 2)),
+        "relu_dropout_bwd": ("hbm", mix(ff_enc, ff_dec) * (2 + 2 + 2)),
+        "cast_rows": ("hbm", mix(n_enc, n_dec) * (4 + 2)),
+        "rms_norm_fwd": ("hbm", n_enc * (4 + 2)),
+        "rms_norm_bwd": ("hbm", n_enc * (2 + 4 + 4 + 4)),
     }
 
 
