@@ -154,6 +154,19 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   }
   return ctr;
 }
+// Philox4x32 with R rounds.  R = 7 is the smallest round count that passes BigCrush (Salmon et al., SC'11).
+template <int R>
+__device__ __forceinline__ uint4 philox4x32_r(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0; key.y += W1;
+  }
+  return ctr;
+}
 // keep-mask for 8 consecutive elements starting at element index e0 (e0 % 8 == 0).
 // One Philox call yields 4x32 bits -> 8x16-bit uniforms; keep iff u16 >= p*65536.
 __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t offset, uint64_t e0, uint32_t thr16) {

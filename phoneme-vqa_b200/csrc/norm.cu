@@ -175,18 +175,38 @@ residual_dropout_bwd_kernel(const float* __restrict__ d_out, UT* __restrict__ d_
 }
 
 // ---------------- y = dropout(relu(x)) in place-able form; backward needs only y ----------------
+// The kernel was issue-bound on its random numbers (ncu: 53 % issue-active, 36 % DRAM with one Philox4x32-10 call and
+// eight 16-bit compares per 8 elements), so a thread now owns 16 consecutive elements and spends ONE Philox4x32-7 call
+// on them: 8 random bits per element, keep iff byte >= thr8 (the drop probability is thr8 / 256, p quantised to 1/256
+// like the attention kernels; the 1/keep scale uses the quantised value, and the backward takes it from the same
+// drop_consts8).  The mask is never needed again: the backward reads it off y != 0.
 template <typename T>
 __global__ void __launch_bounds__(kNormThreads)
-relu_dropout_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long n8, uint32_t thr16, float scale,
+relu_dropout_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long n8, uint32_t thr8, float scale,
                         uint64_t seed, uint64_t offset, const unsigned long long* rng_base) {
-  if (thr16 && rng_base) offset += *rng_base;
-  for (long long i = (long long)blockIdx.x * kNormThreads + threadIdx.x; i < n8; i += (long long)gridDim.x * kNormThreads) {
-    f8 v = Vec8<T>::load_stream(x + i * 8);
-    uint32_t m = 0xffu;
-    if (thr16) m = dropout_keep8(seed, offset, (uint64_t)i * 8, thr16);
+  if (thr8 && rng_base) offset += *rng_base;
+  const long long n16 = (n8 + 1) >> 1;                     // units of 16 elements; the last one may hold only 8
+  for (long long i = (long long)blockIdx.x * kNormThreads + threadIdx.x; i < n16; i += (long long)gridDim.x * kNormThreads) {
+    const bool two = 2 * i + 1 < n8;
+    f8 a = Vec8<T>::load_stream(x + i * 16);
+    f8 b{};
+    if (two) b = Vec8<T>::load_stream(x + i * 16 + 8);
+    uint32_t w[4] = {~0u, ~0u, ~0u, ~0u};
+    if (thr8) {
+      const uint64_t c = (uint64_t)i + offset;
+      const uint4 r = philox4x32_r<7>(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0x5A19u, 0u),
+                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+      w[0] = r.x; w[1] = r.y; w[2] = r.z; w[3] = r.w;
+    }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v.v[j] = (((m >> j) & 1u) && v.v[j] > 0.f) ? v.v[j] * scale : 0.f;
-    Vec8<T>::store(y + i * 8, v);
+    for (int j = 0; j < 8; ++j) {
+      const bool ka = ((w[j >> 2] >> (8 * (j & 3))) & 0xffu) >= thr8;
+      const bool kb = ((w[2 + (j >> 2)] >> (8 * (j & 3))) & 0xffu) >= thr8;
+      a.v[j] = (ka && a.v[j] > 0.f) ? a.v[j] * scale : 0.f;
+      b.v[j] = (kb && b.v[j] > 0.f) ? b.v[j] * scale : 0.f;
+    }
+    Vec8<T>::store(y + i * 16, a);
+    if (two) Vec8<T>::store(y + i * 16 + 8, b);
   }
 }
 // dx = (y != 0) ? dy * scale : 0     (y != 0 <=> x > 0 and kept)
@@ -443,6 +463,13 @@ static void drop_consts(float p, uint32_t& thr16, float& scale) {
   thr16 = p > 0.f ? (uint32_t)lrintf(p * 65536.f) : 0u;
   scale = thr16 ? 65536.f / (65536.f - (float)thr16) : 1.f;
 }
+// 8-bit decisions (relu_dropout): p quantised to 1/256, never rounded down to "no dropout" for p > 0
+static void drop_consts8(float p, uint32_t& thr8, float& scale) {
+  thr8 = p > 0.f ? (uint32_t)lrintf(p * 256.f) : 0u;
+  if (p > 0.f && thr8 == 0) thr8 = 1;
+  if (thr8 > 255) thr8 = 255;
+  scale = thr8 ? 256.f / (256.f - (float)thr8) : 1.f;
+}
 
 }  // namespace pvqa
 
@@ -550,12 +577,13 @@ extern "C" int pvqa_relu_dropout_fwd(const void* x, void* y, int64_t n, int dtyp
   PVQA_REQUIRE(x && y, PVQA_ERR_NULL, "relu_dropout_fwd: NULL pointer");
   PVQA_REQUIRE(aligned32(x) && aligned32(y), PVQA_ERR_ALIGN, "relu_dropout_fwd: 32-byte alignment required");
   uint32_t thr; float sc;
-  drop_consts(dropout_p, thr, sc);
+  drop_consts8(dropout_p, thr, sc);
   cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ew_grid((n / 8 + 1) / 2);
   if (dtype == PVQA_BF16)
-    relu_dropout_fwd_kernel<__nv_bfloat16><<<ew_grid(n / 8), kNormThreads, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n / 8, thr, sc, seed, offset, g_rng_base);
+    relu_dropout_fwd_kernel<__nv_bfloat16><<<grid, kNormThreads, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n / 8, thr, sc, seed, offset, g_rng_base);
   else if (dtype == PVQA_F32)
-    relu_dropout_fwd_kernel<float><<<ew_grid(n / 8), kNormThreads, 0, st>>>((const float*)x, (float*)y, n / 8, thr, sc, seed, offset, g_rng_base);
+    relu_dropout_fwd_kernel<float><<<grid, kNormThreads, 0, st>>>((const float*)x, (float*)y, n / 8, thr, sc, seed, offset, g_rng_base);
   else
     return fail(PVQA_ERR_DTYPE, "relu_dropout_fwd: bad dtype");
   count_launch();
@@ -571,7 +599,7 @@ extern "C" int pvqa_relu_dropout_bwd(const void* dy, const void* y, void* dx, in
   PVQA_REQUIRE(dy && y && dx, PVQA_ERR_NULL, "relu_dropout_bwd: NULL pointer");
   PVQA_REQUIRE(aligned32(dy) && aligned32(y) && aligned32(dx), PVQA_ERR_ALIGN, "relu_dropout_bwd: 32-byte alignment required");
   uint32_t thr; float sc;
-  drop_consts(dropout_p, thr, sc);
+  drop_consts8(dropout_p, thr, sc);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == PVQA_BF16)
     relu_dropout_bwd_kernel<__nv_bfloat16><<<ew_grid(n / 8), kNormThreads, 0, st>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)y, (__nv_bfloat16*)dx, n / 8, sc);

@@ -888,12 +888,15 @@ class _PhonemeHeadFused(torch.autograd.Function):
         offs = (0, on_dim, on_dim + rt_dim)
         widths = (on_dim, rt_dim, rt_dim)
         grads = []
-        for k, (dl_pad, W, off, w) in enumerate(zip((dl0, dl1, dl2), (w0, w1, w2), offs, widths)):
-            dl = dl_pad[:, :V[k]]                                                # (N, V_k) view, row stride round16(V_k)
+        for k, (dl, W, off, w) in enumerate(zip((dl0, dl1, dl2), (w0, w1, w2), offs, widths)):
+            # the GEMMs run on the padded (N, round16(V_k)) gradient (pad columns are zero) against zero-padded weight
+            # rows: every operand 16-byte aligned (V_t = 7 would send cuBLAS to its `align1` kernels: 62 us for 14 MFLOP)
             hk = h[:, off:off + w]
-            torch.mm(dl, (W.to(torch.float32) * scale[k]).to(torch.bfloat16), out=d_h[:, off:off + w])
-            grads.append((torch.mm(dl.t(), hk, out_dtype=torch.float32) * scale[k]).to(w_dtype))
-            grads.append((dl.sum(0, dtype=torch.float32) * scale[k]).to(b_dtype))
+            Wp = torch.zeros((dl.shape[1], w), dtype=torch.bfloat16, device=dl.device)
+            Wp[:V[k]] = W.to(torch.float32) * scale[k]
+            torch.mm(dl, Wp, out=d_h[:, off:off + w])
+            grads.append((torch.mm(dl.t(), hk, out_dtype=torch.float32)[:V[k]] * scale[k]).to(w_dtype))
+            grads.append((dl.sum(0, dtype=torch.float32)[:V[k]] * scale[k]).to(b_dtype))
         dx = d_h @ Ws_lp if ctx.needs_input_grad[0] else None
         dWs = torch.mm(d_h.t(), x, out_dtype=torch.float32)
         dbs = col_sum(d_h).to(bs_dtype)
