@@ -126,12 +126,13 @@ def load() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("PVQA_LIB_PATH", LIB_PATH)      # A/B builds of the same ABI (tools/); the product uses LIB_PATH
+    if not os.path.exists(path):
         raise RuntimeError(
-            f"{LIB_PATH} is missing: the sm_100a extension has not been built. "
+            f"{path} is missing: the sm_100a extension has not been built. "
             "Run `python -c 'import __graft_entry__ as g; g.build()'`. There is no CPU/PyTorch fallback."
         )
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(path)
     for name, (restype, argtypes) in _SIGNATURES.items():
         if not hasattr(lib, name):
             continue

@@ -12,6 +12,10 @@
 namespace pvqa {
 
 constexpr int kNormThreads = 256;
+#ifndef PVQA_LN_BWD_CTAS
+#define PVQA_LN_BWD_CTAS 2     // resident CTAs per SM of add_dropout_ln_bwd: 128 registers at 2; at 3 (80 registers + 100-350 B
+                               // of spills) the encoder launch measured 66 us instead of 60 (gpu call 32) — stays 2
+#endif
 constexpr int kMaxVec = 8;          // float4 chunks per lane: d <= 32 * 4 * 8 = 1024
 
 __device__ __forceinline__ float warp_sum_n(float x) {
@@ -227,8 +231,10 @@ relu_dropout_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __
 // mask uses the same flat element index (row * d + col) as residual_dropout_add, so the fused kernel is
 // bit-compatible with the unfused pair.  Outputs: z (pre-norm sum, saved for backward), y (fp32 residual
 // stream) and optionally y_lp (the low-precision copy the next GEMM reads).
+// 4 CTAs per SM (64 registers, no spills up to NV = 3): the kernel is latency-bound on its loads (ncu: long
+// scoreboard, 31 % warps active at 3 CTAs per SM), and 8 CTAs per SM of grid then make exactly two waves.
 template <typename HT, typename UT, typename LT, int NV>
-__global__ void __launch_bounds__(kNormThreads)
+__global__ void __launch_bounds__(kNormThreads, 4)
 add_dropout_ln_fwd_kernel(const HT* __restrict__ hidden, const UT* __restrict__ upd, const float* __restrict__ gamma,
                           const float* __restrict__ beta, HT* __restrict__ z, float* __restrict__ y,
                           LT* __restrict__ y_lp, float* __restrict__ mean, float* __restrict__ rstd, int N, int d,
@@ -301,7 +307,7 @@ add_dropout_ln_fwd_kernel(const HT* __restrict__ hidden, const UT* __restrict__ 
 //   dz = rstd * (wg - mean(wg) - xhat * mean(wg * xhat));  d_hidden = dz;  d_update = mask * dz / keep
 //   dgamma += sum_rows g * xhat;  dbeta += sum_rows g      (register partials -> smem -> one global atomic per CTA column)
 template <typename UT, typename LT, int NV, bool LN>      // LN: LayerNorm (mean, beta); otherwise T5 RMS norm
-__global__ void __launch_bounds__(kNormThreads, 2)
+__global__ void __launch_bounds__(kNormThreads, PVQA_LN_BWD_CTAS)
 add_dropout_ln_bwd_kernel(const float* __restrict__ dy, const LT* __restrict__ dy_lp, const float* __restrict__ d_res,
                           const float* __restrict__ z,
                           const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -686,7 +692,7 @@ extern "C" int pvqa_add_dropout_ln_bwd(const float* dy, const void* dy_lp, int l
   uint32_t thr; float sc;
   drop_consts(dropout_p, thr, sc);
   const int warps = kNormThreads / 32, nv = (int)((d + 255) / 256);
-  long long need = (N + warps - 1) / warps, cap = (long long)num_sms() * 2;
+  long long need = (N + warps - 1) / warps, cap = (long long)num_sms() * PVQA_LN_BWD_CTAS;
   const int grid = (int)(need < cap ? need : cap);
   const size_t smem = (size_t)2 * d * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
@@ -777,7 +783,7 @@ extern "C" int pvqa_add_dropout_rms_bwd(const void* dy, int y_dtype, const float
   uint32_t thr; float sc;
   drop_consts(dropout_p, thr, sc);
   const int warps = kNormThreads / 32, nv = (int)((d + 255) / 256);
-  long long need = (N + warps - 1) / warps, cap = (long long)num_sms() * 2;
+  long long need = (N + warps - 1) / warps, cap = (long long)num_sms() * PVQA_LN_BWD_CTAS;
   const int grid = (int)(need < cap ? need : cap);
   const size_t smem = (size_t)2 * d * sizeof(float);
   cudaStream_t st = (cudaStream_t)stream;
