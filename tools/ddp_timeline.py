@@ -19,6 +19,7 @@ from phoneme_vqa_b200 import models, ops, parallel, synthetic, train  # noqa: E4
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--waves", type=int, default=None, help="attention-backward CTAs per SM (GradReducer default if omitted)")
+ap.add_argument("--bucket-mb", type=float, default=32.0)
 ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--out", default="gpurun_out/ddp_timeline")
 args = ap.parse_args()
@@ -34,7 +35,7 @@ model.train()
 ops.manual_seed(1234 + rank)
 reducer = None
 if world > 1:
-    reducer = parallel.GradReducer(model, bucket_mb=32.0, attn_bwd_waves=args.waves)
+    reducer = parallel.GradReducer(model, bucket_mb=args.bucket_mb, attn_bwd_waves=args.waves)
     reducer.broadcast_parameters(0)
 tr = train.TrainStep(model, reducer, lr=5e-5, betas=(0.9, 0.98), eps=1e-9, warmup_iters=2000, ignore_index=synthetic.PAD_ID)
 batches = [synthetic.phoneme_latr_batch(args.batch, cfg.vocab_size, seed=1234 + rank * 1000 + i, device=dev) for i in range(2)]
@@ -78,7 +79,7 @@ if rank == 0:
     adam = [c for c in comp if "multi_tensor" in c[2] or "adam" in c[2].lower()]
     first_adam = min((c[0] for c in adam), default=end)
     last_bwd = max((c[0] + c[1] for c in comp if c[0] < first_adam), default=0.0)
-    lines = [f"world {world}  attn_bwd_waves {reducer.attn_bwd_waves if reducer else 1}  step {ms_step:.3f} ms (CUDA events, 10 replays)  "
+    lines = [f"world {world}  attn_bwd_waves {reducer.attn_bwd_waves if reducer else 1}  bucket_mb {args.bucket_mb:g}  step {ms_step:.3f} ms (CUDA events, 10 replays)  "
              f"profiled step span {end / 1e3:.3f} ms  kernels {len(comp)} compute + {len(nccl)} nccl",
              inter,
              f"compute kernel time {sum(c[1] for c in comp) / 1e3:.3f} ms   nccl kernel time {sum(c[1] for c in nccl) / 1e3:.3f} ms",
