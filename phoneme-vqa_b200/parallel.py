@@ -1,17 +1,19 @@
-"""Data-parallel training: one process per GPU, NCCL bucketed gradient all-reduce overlapped
-with backward (the only collective on the path — SURVEY.md §8e; the reference has none).
+"""Data-parallel training: one process per GPU, NCCL gradient all-reduce overlapped with backward
+(the only collective on the path — SURVEY.md §8e; the reference has none).
 
-`GradReducer` is a thin, dependency-free DDP: parameters are grouped in reverse registration
-order (heads -> decoder -> encoder -> embeddings, the order gradients become ready) into flat
-fp32 buckets of ~`bucket_mb`; when the last gradient of a bucket is ready an async all-reduce
-is launched (NCCL runs it on its own stream, so it overlaps the remaining backward); `finish()`
-waits, and leaves `p.grad` as views into the averaged buckets (no copy back).
-Per-step passes over the 600 MB of gradients that round 1 paid and this version does not:
-  * the weight-gradient GEMMs of the linears write straight INTO their bucket slot
-    (`grad_slot()`, used by modules._LinearLP) — no gradient -> bucket `copy_` for ~95 % of the bytes;
-  * the average is taken by the collective itself (`ReduceOp.AVG` on NCCL) — no `div_` pass.  The trainable set can change between epochs (encoder
-freeze toggle, core/executor/PhonemeLaTr_Executor.py:152-159): `rebuild()` re-buckets.
-Works with any torch.distributed backend (NCCL on GPUs; gloo in the CPU tests).
+`GradReducer` is a thin, dependency-free DDP: flat fp32 buckets of ~`bucket_mb` with 256-byte aligned
+slots; when the last gradient of a bucket is ready an async all-reduce is launched (NCCL runs it on its own stream, so
+it overlaps the remaining backward); `finish()` / `step_overlapping_tail()` wait and leave `p.grad` as views into the
+averaged buckets (no copy back).
+  * the weight-gradient GEMMs of the linears write straight INTO their bucket slot (`grad_slot()`, used by
+    modules._LinearLP) — no gradient -> bucket `copy_` for ~95 % of the bytes;
+  * the average is taken by the collective itself (`ReduceOp.AVG` on NCCL) — no `div_` pass;
+  * buckets start in reverse registration order and are rebuilt, after the first backward, in the order the gradients
+    really became ready (rank 0's order, broadcast); parameters the loss never reaches are learned in the next step;
+  * the last `tail_mb` in that order (the embedding tables) go over a second communicator, and the optimizer updates
+    everything else while they are on the wire.
+The trainable set can change between epochs (encoder freeze toggle, core/executor/PhonemeLaTr_Executor.py:152-159):
+`maybe_rebuild()` re-buckets.  Works with any torch.distributed backend (NCCL on GPUs; gloo in the CPU tests).
 """
 from __future__ import annotations
 
@@ -28,8 +30,9 @@ def grad_slot(param):
     if r is None or r.world == 1:
         return None
     loc = r._slot.get(id(param))
-    if loc is None:
-        return None
+    if loc is None or loc in r._handed_out:
+        return None          # a second producer of the same parameter in one step must not overwrite the first
+    r._handed_out.add(loc)
     return r._views[loc[0]][loc[1]]
 
 
@@ -132,6 +135,7 @@ class GradReducer:
         self._pending = [len(b) for b in self.buckets]
         self._works = [None] * len(self.buckets)
         self._filled = set()
+        self._handed_out = set()
         if self.world > 1:
             for p in params:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
@@ -213,9 +217,12 @@ class GradReducer:
         self.rebuild(order=[int(i) for i in t.tolist()])
 
     def _reset(self):
+        self._handed_out = set()
         if self._arrival:                                  # the learning step just ended
-            self._adopt_arrival_order()
-            return
+            if not (torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()):
+                self._adopt_arrival_order()                # (never inside a capture: it broadcasts and reallocates)
+                return
+            self._arrival = None
         unused = self._unused or ()
         self._pending = [len(b) - sum(1 for pi in range(len(b)) if (bi, pi) in unused) for bi, b in enumerate(self.buckets)]
         self._works = [None] * len(self.buckets)
