@@ -168,11 +168,12 @@ __device__ __forceinline__ uint4 philox4x32_r(uint4 ctr, uint2 key) {
   return ctr;
 }
 // keep-mask for 8 consecutive elements starting at element index e0 (e0 % 8 == 0).
-// One Philox call yields 4x32 bits -> 8x16-bit uniforms; keep iff u16 >= p*65536.
+// One Philox4x32-7 call yields 4x32 bits -> 8x16-bit uniforms; keep iff u16 >= p*65536.  (Forward and backward of every
+// fused kernel regenerate their masks through this one function, so the round count is a single decision.)
 __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t offset, uint64_t e0, uint32_t thr16) {
   uint64_t c = (e0 >> 3) + offset;
-  uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u),
-                          make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  uint4 r = philox4x32_r<7>(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u),
+                            make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
   uint32_t w[4] = {r.x, r.y, r.z, r.w};
   uint32_t m = 0;
 #pragma unroll
