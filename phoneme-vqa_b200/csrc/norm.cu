@@ -329,8 +329,25 @@ add_dropout_ln_bwd_kernel(const float* __restrict__ dy, const LT* __restrict__ d
       if (LN) acc_b[c].v[j] = 0.f;
     }
   }
-  for (int row = blockIdx.x * (kNormThreads / 32) + (threadIdx.x >> 5); row < N; row += gridDim.x * (kNormThreads / 32)) {
+  const int row_stride = gridDim.x * (kNormThreads / 32);
+  for (int row = blockIdx.x * (kNormThreads / 32) + (threadIdx.x >> 5); row < N; row += row_stride) {
     const long long base = (long long)row * d;
+    // The kernel keeps its column sums in registers, so few warps walk many rows (2 CTAs per SM, ~9 rows per warp) and
+    // every row used to pay two dependent DRAM round trips (z / dy, then d_res after the warp reduction).  The next
+    // row's operands are pulled into L2 while this row is computed: prefetches need no destination registers.
+    if (row + row_stride < N) {
+      const long long nb = (long long)(row + row_stride) * d;
+#pragma unroll
+      for (int c = 0; c < NV; ++c) {
+        const int col = (c * 32 + lane) * 8;
+        if (col < d) {
+          prefetch_l2(z + nb + col);
+          if (dy) prefetch_l2(dy + nb + col);
+          if (dy_lp) prefetch_l2(dy_lp + nb + col);
+          if (d_res) prefetch_l2(d_res + nb + col);
+        }
+      }
+    }
     const float mu = LN ? mean[row] : 0.f, r = rstd[row];
     f8 xh[NV], wg[NV];
     float s1 = 0.f, s2 = 0.f;
