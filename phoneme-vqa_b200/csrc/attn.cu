@@ -160,10 +160,13 @@ extern "C" int pvqa_attn_fwd(const void* q, const void* k, const void* v, void* 
   PVQA_REQUIRE((reinterpret_cast<uintptr_t>(o) & 15) == 0 && o_stride_s % 8 == 0 && o_stride_h % 8 == 0 &&
                    o_stride_b % 8 == 0,
                PVQA_ERR_ALIGN, "attn_fwd: output rows must be 16-byte aligned");
-  // key tiles: n_full of width 128, then the remainder r as (32), (64), (64, 32) or (128)
+  // key tiles: n_full of width 128, then the remainder r as ONE tile of width 32, 64 or 128 (masked past Sk).  A tile
+  // costs a fixed ~1.5 k cycles of barriers / TMEM traffic whatever its width, so covering r = 71 (S = 327) with a 64-
+  // and a 32-wide tile — less padding, one tile more — measured slower than one masked 128-wide tile: 153 vs 139 us
+  // per encoder launch, 67 vs 58 us at S = 197 (gpu call 41).  The kernel still accepts a second remainder tile (w_b).
   const int n_full = (int)(Sk / kBN), rem = (int)(Sk % kBN);
-  const int w_a = rem == 0 ? 0 : rem <= 32 ? 32 : rem <= 96 ? 64 : 128;
-  const int w_b = (rem > 64 && rem <= 96) ? 32 : 0;
+  const int w_a = rem == 0 ? 0 : rem <= 32 ? 32 : rem <= 64 ? 64 : 128;
+  const int w_b = 0;
   const int n_kt = n_full + (w_a ? 1 : 0) + (w_b ? 1 : 0);
   const int n_kpad = n_kt * kBN;
   const int64_t n_floats = 2 * (int64_t)n_kpad + (rel_bias ? 2 * (int64_t)f_rel_copy_stride(n_kpad) + 32 : 0);

@@ -21,8 +21,9 @@
 //     tile of the next item, after its scores are in registers — no serial per-item tail;
 //   * S is read from TMEM once and stays in registers; O accumulates in TMEM and is rescaled in place only when a row
 //     maximum outgrows the running reference by more than 2^8 (lazy rescaling);
-//   * key tiles are 128 wide; the remainder of a row is covered by a 64- and / or a 32-wide tile (S = 327:
-//     128 + 128 + 64 + 32 instead of 3 x 128).
+//   * key tiles are 128 wide; the remainder of a row is ONE tile of width 32, 64 or 128, masked past Sk (S = 327:
+//     128 + 128 + 128).  Splitting the remainder into 64 + 32 saves padding but costs a tile's fixed overhead and
+//     measured 10 % slower (see the launcher in attn.cu).
 #pragma once
 
 namespace pvqa {
