@@ -11,7 +11,10 @@
 //   epilogue D1 + b_shared -> bf16 h: to shared memory (K-major SW128, the A operand of GEMM 2) and to h_out (the
 //            backward recomputes from it)
 //   GEMM 2   D2[128 x V_k]  = h_k[128 x 256] . W_k^T                              tcgen05.mma, weights through the same ring
-//   epilogue D2 + b_k -> online log-sum-exp over the sub-vocabulary, NLL of the target, lse (N,3) for the backward
+//   epilogue D2 + b_k -> online log-sum-exp over the sub-vocabulary, NLL of the target, lse (N,3); then a second pass
+//            over D2 (still in TMEM) writes the UNSCALED logit gradient softmax - onehot as bf16 (rows of ignored
+//            targets are zero), so the backward is library GEMMs only: the factor g / count_k — known when the whole
+//            grid is done — is folded into their small operands (ops._PhonemeHeadFused)
 // GEMM 1 of head k+1 runs under the cross-entropy epilogue of head k.  The logits never exist outside TMEM.
 // 4 epilogue warps (thread = row = TMEM lane) + 1 issuer warp (warp-uniform, tc05::elect_one per instruction).
 #include "common.cuh"
